@@ -1,0 +1,117 @@
+// Interface between the hot path (CUDA kernels; restated on the CPU by oracle/) and the
+// host-side symbol packer (av1_pack.cpp): "per-block {mode, tx_type, quantized coeffs,
+// reconstructed plane} streamed back for symbol packing" (BASELINE.json north_star).
+// Plain C so that the oracle, the CUDA translation units and the C++ host all share it.
+#ifndef B200_RECORDS_H_
+#define B200_RECORDS_H_
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B200_HD __host__ __device__
+#else
+#define B200_HD
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+// AV1 enumerations (AV1 bitstream numbering)
+enum {
+  BLOCK_4X4 = 0, BLOCK_4X8, BLOCK_8X4, BLOCK_8X8, BLOCK_8X16, BLOCK_16X8, BLOCK_16X16, BLOCK_16X32,
+  BLOCK_32X16, BLOCK_32X32, BLOCK_32X64, BLOCK_64X32, BLOCK_64X64, BLOCK_64X128, BLOCK_128X64, BLOCK_128X128,
+  BLOCK_INVALID = 255
+};
+enum { TX_4X4 = 0, TX_8X8, TX_16X16, TX_32X32, TX_64X64 };
+enum {
+  DC_PRED = 0, V_PRED, H_PRED, D45_PRED, D135_PRED, D113_PRED, D157_PRED, D203_PRED, D67_PRED,
+  SMOOTH_PRED, SMOOTH_V_PRED, SMOOTH_H_PRED, PAETH_PRED, UV_CFL_PRED = 13
+};
+enum { TX_DCT_DCT = 0, TX_ADST_DCT = 1, TX_DCT_ADST = 2, TX_ADST_ADST = 3, TX_IDTX = 9 };
+
+#define B200_MAX_TILE_COLS 64
+#define B200_MAX_TILE_ROWS 64
+#define B200_SB_COEFS 4096           // 64x64 coefficient slots per plane per superblock
+
+// One entry per 4x4 "mode info" unit (replicated over the whole block).
+typedef struct B200Mi {
+  uint8_t bsize;     // AV1 BLOCK_SIZE of the block covering this unit
+  uint8_t y_mode;    // 0..12
+  uint8_t uv_mode;   // 0..13 (13 = CFL)
+  uint8_t angle;     // (angle_delta_y + 3) | (angle_delta_uv + 3) << 4
+  uint8_t tx_size;   // TX_SIZE of the luma transform (== largest for the block)
+  uint8_t tx_type;   // luma transform type (chroma is derived from uv_mode)
+  uint8_t flags;     // bit0: skip; bits1..3: cfl joint sign (0..7)
+  uint8_t cfl;       // cfl_alpha_u index (low nibble), cfl_alpha_v index (high nibble)
+} B200Mi;
+
+// Frame-level description: inputs (geometry, quantiser, tool switches) + decisions made by the
+// in-loop-filter search.  Filled by b200av1_frame_setup().
+typedef struct B200Frame {
+  int32_t width, height;            // visible size
+  int32_t bit_depth;                // 8 | 10
+  int32_t planes;                   // 3 (4:4:4) or 1 (monochrome)
+  int32_t mi_cols, mi_rows;         // 4x4 units, multiple of 2 (8-pixel aligned)
+  int32_t sb_cols, sb_rows;         // 64x64 superblocks
+  int32_t tile_cols_log2, tile_rows_log2, tile_cols, tile_rows;
+  int32_t tile_col_start_sb[B200_MAX_TILE_COLS + 1];
+  int32_t tile_row_start_sb[B200_MAX_TILE_ROWS + 1];
+  int32_t base_q_idx;               // 1..255
+  int32_t dc_q, ac_q;               // quantiser step sizes (table lookups at base_q_idx)
+  int32_t reduced_tx_set;
+  int32_t enable_cdef, enable_restoration;
+  int32_t color_description_present, color_primaries, transfer_characteristics, matrix_coefficients, full_range;
+  // encoder search controls (ravif SpeedTweaks, av1encoder.rs:555-605)
+  int32_t partition_min, partition_max;     // 4|8|16|32|64 pixels
+  int32_t rdo_tx_decision;                  // search transform type per block
+  int32_t fine_directional_intra;           // angle_delta search
+  int32_t enable_cfl;
+  int32_t lambda_q8;                        // RD multiplier: J = (SSE << 8) + ((lambda_q8 * R_q8) >> 8), R in 1/256 bit
+  int32_t lambda_satd_q8;                   // pre-ranking: J = satd * 64 + ((lambda_satd_q8 * R_q8) >> 8)
+  int32_t y_mode_mask, uv_mode_mask;        // allowed intra modes (bit = mode index); conformance tests force single modes
+  int32_t tx_type_mask;                     // allowed luma transform types: bit0 DCT_DCT 1 ADST_DCT 2 DCT_ADST 3 ADST_ADST 4 IDTX
+  // decisions of the in-loop filter stages
+  int32_t lf_level[4];                      // y vertical, y horizontal, u, v
+  int32_t lf_sharpness;
+  int32_t cdef_damping, cdef_bits;
+  int32_t cdef_y_strength[8], cdef_uv_strength[8];   // pri*4 + sec
+  int32_t lr_type[3];                       // 0 none (only value emitted for now)
+} B200Frame;
+
+// Static rate model used by the RDO (costs in 1/256 bit, derived from the default CDFs of the
+// frame's quantiser class, no adaptation).  Built on the host by b200av1_build_rate_tables().
+typedef struct B200RateTables {
+  uint16_t partition[20][10];
+  uint16_t skip[3][2];
+  uint16_t y_mode[5][5][13];
+  uint16_t uv_mode[2][13][14];
+  uint16_t angle_delta[8][7];
+  uint16_t cfl_sign[8];
+  uint16_t cfl_alpha[6][16];
+  uint16_t intra_tx[2][4][13][16];          // [0: 7-type set, 1: 5-type set][tx size][y mode][tx_type]
+  uint16_t txb_skip[5][13][2];
+  uint16_t eob_pt[4][2][12];                // [TX_4X4..TX_32X32][plane type][eob_pt - 1]
+  uint16_t eob_extra[5][2][9][2];
+  uint16_t dc_sign[2][3][2];
+  uint16_t coeff_base_eob[5][2][4][3];
+  uint16_t coeff_base[5][2][42][4];
+  uint16_t coeff_br[4][2][21][13];          // cost of base_range 0..12 (12 = 12 or more, golomb extra not included)
+} B200RateTables;
+
+// z-order index (0..255) of the 4x4 unit (r, c) inside its 64x64 superblock, r,c in 0..15.
+static inline B200_HD int b200_zidx(int r, int c) {
+  int z = 0;
+  for (int i = 0; i < 4; i++) z |= (((c >> i) & 1) << (2 * i)) | (((r >> i) & 1) << (2 * i + 1));
+  return z;
+}
+// First coefficient slot of the transform block whose top-left 4x4 unit is (mi_row, mi_col).
+// Coefficients of a block are stored in SCAN ORDER, contiguous, in its z-order slot range.
+static inline B200_HD int64_t b200_coef_offset(const B200Frame *f, int mi_row, int mi_col) {
+  const int sb = (mi_row >> 4) * f->sb_cols + (mi_col >> 4);
+  return (int64_t)sb * B200_SB_COEFS + b200_zidx(mi_row & 15, mi_col & 15) * 16;
+}
+
+#ifdef __cplusplus
+}
+#endif
+#endif  // B200_RECORDS_H_

@@ -1,0 +1,541 @@
+/* ORACLE (test infrastructure, never linked into the product path).
+ *
+ * CPU restatement of the device hot path: per-tile AV1 intra rate-distortion search
+ * (intra prediction, forward transform, quantisation, reconstruction, distortion,
+ * partition / mode / transform-type decisions) producing the block records of
+ * cavif_rs_b200/csrc/records.h plus the reconstructed planes.
+ *
+ * In the reference this is rav1e's encode_tile / rdo_mode_decision / encode_tx_block
+ * [EXT: crates.io rav1e 0.8.1, not on disk; driven only from
+ * /root/reference/ravif/src/av1encoder.rs:749-771 with the tool switches of :555-605].
+ * PARITY UNPINNED against rav1e (no source, no vectors - SURVEY.md section 0.3).  What IS
+ * pinned: every normative stage (predictors, dequantisation, inverse transforms,
+ * reconstruction) sample-exactly by dav1d 1.5.3 decoding the packed bitstream, and
+ * predictors/transforms against libaom 3.13.1's C reference functions (tests/).
+ *
+ * The CUDA kernels in cavif_rs_b200/csrc/rdo.cu must reproduce this file bit-exactly.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../cavif_rs_b200/csrc/records.h"
+#include "../cavif_rs_b200/csrc/av1_tables.h"
+#include "../cavif_rs_b200/csrc/av1_tables_extra.h"
+
+void orc_fwd_txfm2d(const int16_t *resid, int stride, int32_t *coef, int n, int tx_type);
+void orc_inv_txfm2d_add(const int32_t *coef, uint16_t *dst, int stride, int n, int tx_type, int bd);
+
+typedef struct {
+  const B200Frame *f;
+  const B200RateTables *rt;
+  uint16_t *src[3];   /* padded source planes, stride = mi_cols*4 */
+  uint16_t *rec[3];   /* reconstruction (before in-loop filters) */
+  int stride;
+  B200Mi *mi;
+  uint16_t *eob[3];
+  int16_t *coef[3];
+  uint8_t *decoded;   /* per-4x4 "already reconstructed" flags (whole frame, tile-local meaning) */
+  int tr0, tr1, tc0, tc1;   /* current tile bounds in mi units */
+} enc_t;
+
+/* one block candidate (all planes) */
+typedef struct {
+  int64_t cost;
+  B200Mi mi;
+  uint16_t eob[3];
+  int16_t qcoef[3][1024];     /* scan order */
+  uint16_t recon[3][32 * 32];
+} cand_t;
+
+static const uint16_t *scan_for(int n) {
+  return n == 4 ? av1_default_scan_4x4 : n == 8 ? av1_default_scan_8x8 : n == 16 ? av1_default_scan_16x16 : av1_default_scan_32x32;
+}
+static int txs_of(int n) { return n == 4 ? 0 : n == 8 ? 1 : n == 16 ? 2 : 3; }
+static int bsize_of(int n) { return n == 4 ? BLOCK_4X4 : n == 8 ? BLOCK_8X8 : n == 16 ? BLOCK_16X16 : n == 32 ? BLOCK_32X32 : BLOCK_64X64; }
+static const uint8_t k_bw4[22] = {1, 1, 2, 2, 2, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 1, 4, 2, 8, 4, 16};
+static const uint8_t k_bh4[22] = {1, 2, 1, 2, 4, 2, 4, 8, 4, 8, 16, 8, 16, 32, 16, 32, 4, 1, 8, 2, 16, 4};
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+
+/* ---- intra edge preparation: AV1 spec 7.11.2 (no intra edge filter / upsampling: the sequence
+ * header sets enable_intra_edge_filter = 0). above[-1..2n-1], left[-1..2n-1] via offset 16. */
+#define EOFF 16
+static void build_edges(const enc_t *e, int plane, int x, int y, int n, uint16_t *above, uint16_t *left,
+                        int *have_above, int *have_left) {
+  const B200Frame *f = e->f;
+  const uint16_t *r = e->rec[plane];
+  const int st = e->stride;
+  const int mi_r = y >> 2, mi_c = x >> 2, n4 = n >> 2;
+  const int ha = mi_r > e->tr0, hl = mi_c > e->tc0;
+  const int max_x = f->mi_cols * 4 - 1, max_y = f->mi_rows * 4 - 1;
+  const int base = 1 << (f->bit_depth - 1);
+  int have_ar = 0, have_bl = 0;
+  if (ha && mi_c + n4 < e->tc1) have_ar = e->decoded[(mi_r - 1) * f->mi_cols + mi_c + n4];
+  if (hl && mi_r + n4 < e->tr1) have_bl = e->decoded[(mi_r + n4) * f->mi_cols + mi_c - 1];
+  uint16_t *A = above + EOFF, *L = left + EOFF;
+  if (!ha && hl) { for (int i = 0; i < 2 * n; i++) A[i] = r[y * st + x - 1]; }
+  else if (!ha && !hl) { for (int i = 0; i < 2 * n; i++) A[i] = (uint16_t)(base - 1); }
+  else {
+    for (int i = 0; i < n; i++) { int xx = x + i; if (xx > max_x) xx = max_x; A[i] = r[(y - 1) * st + xx]; }
+    for (int i = n; i < 2 * n; i++) {
+      int xx = have_ar ? x + i : x + n - 1;
+      if (xx > max_x) xx = max_x;
+      A[i] = r[(y - 1) * st + xx];
+    }
+  }
+  if (!hl && ha) { for (int i = 0; i < 2 * n; i++) L[i] = r[(y - 1) * st + x]; }
+  else if (!hl && !ha) { for (int i = 0; i < 2 * n; i++) L[i] = (uint16_t)(base + 1); }
+  else {
+    for (int i = 0; i < n; i++) { int yy = y + i; if (yy > max_y) yy = max_y; L[i] = r[yy * st + x - 1]; }
+    for (int i = n; i < 2 * n; i++) {
+      int yy = have_bl ? y + i : y + n - 1;
+      if (yy > max_y) yy = max_y;
+      L[i] = r[yy * st + x - 1];
+    }
+  }
+  uint16_t tl;
+  if (ha && hl) tl = r[(y - 1) * st + x - 1];
+  else if (ha) tl = r[(y - 1) * st + x];
+  else if (hl) tl = r[y * st + x - 1];
+  else tl = (uint16_t)base;
+  A[-1] = tl; L[-1] = tl;
+  *have_above = ha; *have_left = hl;
+}
+
+static const uint8_t *sm_weights(int n) {
+  return n == 4 ? av1_sm_weights_4 : n == 8 ? av1_sm_weights_8 : n == 16 ? av1_sm_weights_16 : n == 32 ? av1_sm_weights_32 : av1_sm_weights_64;
+}
+
+/* AV1 spec 7.11.2.x intra predictors for an n x n block. angle_delta in -3..3. */
+void orc_predict_intra(int mode, int angle_delta, int n, const uint16_t *above, const uint16_t *left, int have_above,
+                       int have_left, int bit_depth, uint16_t *pred /* n*n */) {
+  const uint16_t *A = above + EOFF, *L = left + EOFF;
+  if (mode == DC_PRED) {
+    int v;
+    if (have_above && have_left) { int s = 0; for (int i = 0; i < n; i++) s += A[i] + L[i]; v = (s + n) / (2 * n); }
+    else if (have_left) { int s = 0; for (int i = 0; i < n; i++) s += L[i]; v = (s + (n >> 1)) / n; }
+    else if (have_above) { int s = 0; for (int i = 0; i < n; i++) s += A[i]; v = (s + (n >> 1)) / n; }
+    else v = 1 << (bit_depth - 1);
+    for (int i = 0; i < n * n; i++) pred[i] = (uint16_t)v;
+    return;
+  }
+  if (mode == PAETH_PRED) {
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        const int b = A[j] + L[i] - A[-1];
+        const int pl = abs(b - L[i]), pt = abs(b - A[j]), ptl = abs(b - A[-1]);
+        pred[i * n + j] = (pl <= pt && pl <= ptl) ? L[i] : (pt <= ptl ? A[j] : A[-1]);
+      }
+    return;
+  }
+  if (mode == SMOOTH_PRED || mode == SMOOTH_V_PRED || mode == SMOOTH_H_PRED) {
+    const uint8_t *w = sm_weights(n);
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        int v;
+        if (mode == SMOOTH_PRED)
+          v = (w[i] * A[j] + (256 - w[i]) * L[n - 1] + w[j] * L[i] + (256 - w[j]) * A[n - 1] + 256) >> 9;
+        else if (mode == SMOOTH_V_PRED) v = (w[i] * A[j] + (256 - w[i]) * L[n - 1] + 128) >> 8;
+        else v = (w[j] * L[i] + (256 - w[j]) * A[n - 1] + 128) >> 8;
+        pred[i * n + j] = (uint16_t)v;
+      }
+    return;
+  }
+  /* directional */
+  const int p_angle = av1_mode_to_angle[mode] + angle_delta * 3;
+  if (p_angle == 90) { for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) pred[i * n + j] = A[j]; return; }
+  if (p_angle == 180) { for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) pred[i * n + j] = L[i]; return; }
+  if (p_angle < 90) {
+    const int dx = av1_dr_intra_derivative[p_angle];
+    const int max_base = 2 * n - 1;
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        const int idx = (i + 1) * dx, base = (idx >> 6) + j, shift = (idx >> 1) & 31;
+        pred[i * n + j] = base < max_base ? (uint16_t)((A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5) : A[max_base];
+      }
+  } else if (p_angle < 180) {
+    const int dx = av1_dr_intra_derivative[180 - p_angle], dy = av1_dr_intra_derivative[p_angle - 90];
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        int idx = (j << 6) - (i + 1) * dx, base = idx >> 6;
+        if (base >= -1) {
+          const int shift = (idx >> 1) & 31;
+          pred[i * n + j] = (uint16_t)((A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5);
+        } else {
+          idx = (i << 6) - (j + 1) * dy; base = idx >> 6;
+          const int shift = (idx >> 1) & 31;
+          pred[i * n + j] = (uint16_t)((L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5);
+        }
+      }
+  } else {
+    const int dy = av1_dr_intra_derivative[270 - p_angle];
+    const int max_base = 2 * n - 1;
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        const int idx = (j + 1) * dy, base = (idx >> 6) + i, shift = (idx >> 1) & 31;
+        pred[i * n + j] = base < max_base ? (uint16_t)((L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5) : L[max_base];
+      }
+  }
+}
+
+/* sum of absolute 4x4 Hadamard coefficients over all 4x4 sub-blocks of an n x n residual */
+static uint32_t satd4(const uint16_t *src, int sstride, const uint16_t *pred, int n) {
+  uint32_t total = 0;
+  for (int by = 0; by < n; by += 4)
+    for (int bx = 0; bx < n; bx += 4) {
+      int d[16], t[16];
+      for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) d[i * 4 + j] = (int)src[(by + i) * sstride + bx + j] - (int)pred[(by + i) * n + bx + j];
+      for (int i = 0; i < 4; i++) {
+        const int a = d[i * 4] + d[i * 4 + 1], b = d[i * 4] - d[i * 4 + 1], c = d[i * 4 + 2] + d[i * 4 + 3], e = d[i * 4 + 2] - d[i * 4 + 3];
+        t[i * 4] = a + c; t[i * 4 + 1] = b + e; t[i * 4 + 2] = a - c; t[i * 4 + 3] = b - e;
+      }
+      for (int j = 0; j < 4; j++) {
+        const int a = t[j] + t[4 + j], b = t[j] - t[4 + j], c = t[8 + j] + t[12 + j], e = t[8 + j] - t[12 + j];
+        total += (uint32_t)(abs(a + c) + abs(b + e) + abs(a - c) + abs(b - e));
+      }
+    }
+  return total;
+}
+
+/* quantise -> levels in scan order + eob; dequantise -> dq (row-major).  Levels clamped to int16. */
+static int quantize(const B200Frame *f, const int32_t *coef, int n, int16_t *qc_scan, int32_t *dq) {
+  const uint16_t *scan = scan_for(n);
+  const int n2 = n * n;
+  int eob = 0;
+  const int shift = n == 32 ? 1 : 0;   /* 32x32: forward scale is half, dequant >> 1 */
+  for (int i = 0; i < n2; i++) {
+    const int pos = scan[i];
+    const int q = pos == 0 ? f->dc_q : f->ac_q;
+    const int off = pos == 0 ? (q * 109) >> 8 : (q * 98) >> 8;
+    const int32_t c = coef[pos];
+    const uint32_t a = (uint32_t)(c < 0 ? -c : c);
+    uint32_t lv = (uint32_t)(((uint64_t)(a << shift) + (uint32_t)off) / (uint32_t)q);
+    if (lv > 32767) lv = 32767;
+    const int32_t dqa = (int32_t)(((uint64_t)lv * (uint32_t)q) & 0xFFFFFF) >> shift;
+    qc_scan[i] = (int16_t)(c < 0 ? -(int)lv : (int)lv);
+    dq[pos] = c < 0 ? -dqa : dqa;
+    if (lv) eob = i + 1;
+  }
+  return eob;
+}
+
+/* static-CDF rate of one transform block (mirrors the packer's symbol sequence), 1/256 bit */
+static uint32_t coef_rate(const enc_t *e, int plane, int n, int tx_type, int y_mode, const int16_t *qc, int eob) {
+  const B200RateTables *rt = e->rt;
+  const int txs = txs_of(n), ptype = plane > 0;
+  const int skip_ctx = plane == 0 ? 0 : 7;
+  if (eob == 0) return rt->txb_skip[txs][skip_ctx][1];
+  uint32_t r = rt->txb_skip[txs][skip_ctx][0];
+  if (plane == 0 && n <= 16) r += rt->intra_tx[(e->f->reduced_tx_set || n == 16) ? 1 : 0][txs][y_mode][tx_type];
+  static const int16_t group_start[12] = {0, 1, 2, 3, 5, 9, 17, 33, 65, 129, 257, 513};
+  static const int8_t offset_bits[12] = {0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9};
+  int t = 0;
+  while (t < 11 && group_start[t + 1] <= eob) t++;
+  r += rt->eob_pt[txs][ptype][t - 1];
+  if (offset_bits[t] > 0) {
+    const int extra = eob - group_start[t], nb = offset_bits[t];
+    r += rt->eob_extra[txs][ptype][t - 3][(extra >> (nb - 1)) & 1];
+    r += 256u * (uint32_t)(nb - 1);
+  }
+  const uint16_t *scan = scan_for(n);
+  const int stride = n + 4;
+  uint8_t lev[36 * 36];
+  memset(lev, 0, (size_t)stride * (n + 4));
+  for (int i = 0; i < eob; i++) {
+    const int pos = scan[i];
+    const int a = abs(qc[i]);
+    lev[(pos / n) * stride + pos % n] = (uint8_t)(a > 127 ? 127 : a);
+  }
+  for (int i = eob - 1; i >= 0; i--) {
+    const int pos = scan[i], rr = pos / n, cc = pos % n;
+    const int level = abs(qc[i]);
+    const uint8_t *L = lev + rr * stride + cc;
+#define M3(v) ((v) > 3 ? 3 : (v))
+#define M15(v) ((v) > 15 ? 15 : (v))
+    if (i == eob - 1) {
+      const int c4 = i == 0 ? 0 : (i <= (n * n) / 8 ? 1 : (i <= (n * n) / 4 ? 2 : 3));
+      r += rt->coeff_base_eob[txs][ptype][c4][M3(level) - 1];
+    } else {
+      const int mag = M3(L[1]) + M3(L[stride]) + M3(L[stride + 1]) + M3(L[2]) + M3(L[2 * stride]);
+      int ctx = (mag + 1) >> 1;
+      if (ctx > 4) ctx = 4;
+      if (rr == 0 && cc == 0) ctx = 0;
+      else ctx += (rr + cc < 2) ? 1 : (rr + cc < 4) ? 6 : 21;
+      r += rt->coeff_base[txs][ptype][ctx][M3(level)];
+    }
+    if (level > 2) {
+      int mag = M15(L[1]) + M15(L[stride]) + M15(L[stride + 1]);
+      mag = (mag + 1) >> 1;
+      if (mag > 6) mag = 6;
+      const int bctx = (rr == 0 && cc == 0) ? mag : ((rr < 2 && cc < 2) ? mag + 7 : mag + 14);
+      const int br = level - 3;
+      r += rt->coeff_br[txs > 3 ? 3 : txs][ptype][bctx][br > 12 ? 12 : br];
+      if (level > 14) {   /* golomb(level - 15): 2*len - 1 bits */
+        int x = level - 15 + 1, len = 0;
+        while (x) { x >>= 1; len++; }
+        r += 256u * (uint32_t)(2 * len - 1);
+      }
+    }
+    if (level) r += (i == 0) ? rt->dc_sign[ptype][0][qc[i] < 0] : 256u;
+  }
+  return r;
+}
+
+static uint64_t sse_block(const uint16_t *src, int sstride, const uint16_t *rec, int n) {
+  uint64_t s = 0;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) { const int d = (int)src[i * sstride + j] - (int)rec[i * n + j]; s += (uint64_t)(d * d); }
+  return s;
+}
+
+/* full trial of one plane: pred -> residual -> fwd -> quant -> rate, dequant -> inverse -> recon, SSE.
+ * recon (n*n) receives the reconstruction. returns distortion; *rate out. */
+static uint64_t trial_plane(const enc_t *e, int plane, int x, int y, int n, const uint16_t *pred, int tx_type, int y_mode,
+                            int16_t *qc, uint16_t *eob_out, uint16_t *recon, uint32_t *rate) {
+  const B200Frame *f = e->f;
+  const uint16_t *src = e->src[plane] + y * e->stride + x;
+  int16_t resid[32 * 32];
+  int32_t coef[32 * 32], dq[32 * 32];
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) resid[i * n + j] = (int16_t)((int)src[i * e->stride + j] - (int)pred[i * n + j]);
+  orc_fwd_txfm2d(resid, n, coef, n, tx_type);
+  const int eob = quantize(f, coef, n, qc, dq);
+  memcpy(recon, pred, sizeof(uint16_t) * n * n);
+  if (eob) orc_inv_txfm2d_add(dq, recon, n, n, tx_type, f->bit_depth);
+  *eob_out = (uint16_t)eob;
+  *rate = coef_rate(e, plane, n, tx_type, y_mode, qc, eob);
+  return sse_block(src, e->stride, recon, n);
+}
+
+static inline int64_t rd_cost(const B200Frame *f, uint64_t sse, uint32_t rate) {
+  return (int64_t)(sse << 8) + (((int64_t)f->lambda_q8 * (int64_t)rate) >> 8);
+}
+
+static const uint8_t k_tx_types[5] = {TX_DCT_DCT, TX_ADST_DCT, TX_DCT_ADST, TX_ADST_ADST, TX_IDTX};
+
+/* chroma transform type derived from the uv mode (AV1 spec get_tx_type for intra chroma),
+ * restricted to what the (reduced) intra set allows for this size */
+static int chroma_tx_type(int uv_mode, int n) {
+  if (uv_mode == UV_CFL_PRED) return TX_DCT_DCT;
+  if (n >= 32) return TX_DCT_DCT;
+  return av1_intra_mode_to_tx_type[uv_mode];   /* DCT/ADST combinations are in every intra set up to 16x16 */
+}
+
+/* Evaluate one block (all planes) at (x,y) size n against the current reconstruction; fills cand. */
+static void trial_block(enc_t *e, int x, int y, int n, cand_t *cd) {
+  const B200Frame *f = e->f;
+  const B200RateTables *rt = e->rt;
+  const int mi_r = y >> 2, mi_c = x >> 2;
+  const int avail_u = mi_r > e->tr0, avail_l = mi_c > e->tc0;
+  uint16_t above[EOFF + 64 + 2], left[EOFF + 64 + 2];
+  int ha, hl;
+  uint16_t pred[32 * 32], best_pred_unused;
+  (void)best_pred_unused;
+  const uint16_t *src = e->src[0] + y * e->stride + x;
+
+  /* --- mode contexts */
+  const int am = avail_u ? e->mi[(mi_r - 1) * f->mi_cols + mi_c].y_mode : DC_PRED;
+  const int lm = avail_l ? e->mi[mi_r * f->mi_cols + mi_c - 1].y_mode : DC_PRED;
+  const uint16_t *ymode_cost = rt->y_mode[av1_intra_mode_context[am]][av1_intra_mode_context[lm]];
+
+  /* --- luma: rank modes by SATD + mode rate */
+  build_edges(e, 0, x, y, n, above, left, &ha, &hl);
+  int64_t best_c[2] = {INT64_MAX, INT64_MAX};
+  int best_m[2] = {-1, -1};
+  for (int m = 0; m < 13; m++) {
+    if (!((f->y_mode_mask >> m) & 1)) continue;
+    orc_predict_intra(m, 0, n, above, left, ha, hl, f->bit_depth, pred);
+    uint32_t mrate = ymode_cost[m];
+    if (n >= 8 && m >= V_PRED && m <= D67_PRED) mrate += rt->angle_delta[m - V_PRED][3];
+    const int64_t c = (int64_t)satd4(src, e->stride, pred, n) * 64 + (((int64_t)f->lambda_satd_q8 * mrate) >> 8);
+    if (c < best_c[0]) { best_c[1] = best_c[0]; best_m[1] = best_m[0]; best_c[0] = c; best_m[0] = m; }
+    else if (c < best_c[1]) { best_c[1] = c; best_m[1] = m; }
+  }
+  /* --- full trial of the top-2 modes with the first allowed transform type, then tx type search */
+  int first_tt = -1;
+  for (int k = 0; k < 5; k++) if ((f->tx_type_mask >> k) & 1) { first_tt = k_tx_types[k]; break; }
+  if (n >= 32) first_tt = TX_DCT_DCT;
+  int64_t bestJ = INT64_MAX;
+  int best_mode = best_m[0], best_tt = first_tt;
+  int16_t qc[1024];
+  uint16_t recon[1024], eobv;
+  for (int k = 0; k < 2; k++) {
+    const int m = best_m[k];
+    if (m < 0) continue;
+    orc_predict_intra(m, 0, n, above, left, ha, hl, f->bit_depth, pred);
+    uint32_t rate;
+    const uint64_t d = trial_plane(e, 0, x, y, n, pred, first_tt, m, qc, &eobv, recon, &rate);
+    uint32_t mrate = ymode_cost[m];
+    if (n >= 8 && m >= V_PRED && m <= D67_PRED) mrate += rt->angle_delta[m - V_PRED][3];
+    const int64_t J = rd_cost(f, d, rate + mrate);
+    if (J < bestJ) {
+      bestJ = J; best_mode = m; best_tt = first_tt;
+      memcpy(cd->qcoef[0], qc, sizeof(int16_t) * n * n);
+      memcpy(cd->recon[0], recon, sizeof(uint16_t) * n * n);
+      cd->eob[0] = eobv;
+    }
+  }
+  if (f->rdo_tx_decision && n <= 16) {
+    orc_predict_intra(best_mode, 0, n, above, left, ha, hl, f->bit_depth, pred);
+    uint32_t mrate = ymode_cost[best_mode];
+    if (n >= 8 && best_mode >= V_PRED && best_mode <= D67_PRED) mrate += rt->angle_delta[best_mode - V_PRED][3];
+    for (int k = 0; k < 5; k++) {
+      const int tt = k_tx_types[k];
+      if (!((f->tx_type_mask >> k) & 1) || tt == first_tt) continue;
+      uint32_t rate;
+      const uint64_t d = trial_plane(e, 0, x, y, n, pred, tt, best_mode, qc, &eobv, recon, &rate);
+      const int64_t J = rd_cost(f, d, rate + mrate);
+      if (J < bestJ) {
+        bestJ = J; best_tt = tt;
+        memcpy(cd->qcoef[0], qc, sizeof(int16_t) * n * n);
+        memcpy(cd->recon[0], recon, sizeof(uint16_t) * n * n);
+        cd->eob[0] = eobv;
+      }
+    }
+  }
+  int64_t total = bestJ;
+  memset(&cd->mi, 0, sizeof(cd->mi));
+  cd->mi.bsize = (uint8_t)bsize_of(n);
+  cd->mi.y_mode = (uint8_t)best_mode;
+  cd->mi.angle = 3 | (3 << 4);
+  cd->mi.tx_size = (uint8_t)txs_of(n);
+  cd->mi.tx_type = (uint8_t)best_tt;
+  cd->mi.uv_mode = DC_PRED;
+
+  /* --- chroma: pick the uv mode by SATD (both planes) + rate, one full trial */
+  if (f->planes > 1) {
+    const int cfl_allowed = n <= 32;
+    const uint16_t *uvcost = rt->uv_mode[cfl_allowed][best_mode];
+    uint16_t aU[EOFF + 66], lU[EOFF + 66], aV[EOFF + 66], lV[EOFF + 66];
+    int hau, hlu;
+    build_edges(e, 1, x, y, n, aU, lU, &hau, &hlu);
+    build_edges(e, 2, x, y, n, aV, lV, &hau, &hlu);
+    int64_t bc = INT64_MAX;
+    int buv = DC_PRED;
+    for (int m = 0; m < 13; m++) {
+      if (!((f->uv_mode_mask >> m) & 1)) continue;
+      uint32_t mrate = uvcost[m];
+      if (n >= 8 && m >= V_PRED && m <= D67_PRED) mrate += rt->angle_delta[m - V_PRED][3];
+      orc_predict_intra(m, 0, n, aU, lU, hau, hlu, f->bit_depth, pred);
+      uint32_t s = satd4(e->src[1] + y * e->stride + x, e->stride, pred, n);
+      orc_predict_intra(m, 0, n, aV, lV, hau, hlu, f->bit_depth, pred);
+      s += satd4(e->src[2] + y * e->stride + x, e->stride, pred, n);
+      const int64_t c = (int64_t)s * 64 + (((int64_t)f->lambda_satd_q8 * mrate) >> 8);
+      if (c < bc) { bc = c; buv = m; }
+    }
+    cd->mi.uv_mode = (uint8_t)buv;
+    uint32_t mrate = uvcost[buv];
+    if (n >= 8 && buv >= V_PRED && buv <= D67_PRED) mrate += rt->angle_delta[buv - V_PRED][3];
+    const int ctt = chroma_tx_type(buv, n);
+    uint32_t rate;
+    orc_predict_intra(buv, 0, n, aU, lU, hau, hlu, f->bit_depth, pred);
+    uint64_t d = trial_plane(e, 1, x, y, n, pred, ctt, best_mode, cd->qcoef[1], &cd->eob[1], cd->recon[1], &rate);
+    uint32_t rsum = rate + mrate;
+    orc_predict_intra(buv, 0, n, aV, lV, hau, hlu, f->bit_depth, pred);
+    d += trial_plane(e, 2, x, y, n, pred, ctt, best_mode, cd->qcoef[2], &cd->eob[2], cd->recon[2], &rate);
+    rsum += rate;
+    total += rd_cost(f, d, rsum);
+  }
+  /* --- skip flag */
+  const int all_zero = cd->eob[0] == 0 && (f->planes == 1 || (cd->eob[1] == 0 && cd->eob[2] == 0));
+  {
+    const int a = avail_u ? (e->mi[(mi_r - 1) * f->mi_cols + mi_c].flags & 1) : 0;
+    const int l = avail_l ? (e->mi[mi_r * f->mi_cols + mi_c - 1].flags & 1) : 0;
+    total += ((int64_t)f->lambda_q8 * rt->skip[a + l][all_zero]) >> 8;
+  }
+  if (all_zero) cd->mi.flags |= 1;
+  cd->cost = total;
+}
+
+/* write a candidate into the frame state (reconstruction, records, decoded flags) */
+static void commit_block(enc_t *e, int x, int y, int n, const cand_t *cd) {
+  const B200Frame *f = e->f;
+  const int mi_r = y >> 2, mi_c = x >> 2, n4 = n >> 2;
+  for (int p = 0; p < f->planes; p++) {
+    for (int i = 0; i < n; i++) memcpy(e->rec[p] + (y + i) * e->stride + x, cd->recon[p] + i * n, sizeof(uint16_t) * n);
+    e->eob[p][mi_r * f->mi_cols + mi_c] = cd->eob[p];
+    memcpy(e->coef[p] + b200_coef_offset(f, mi_r, mi_c), cd->qcoef[p], sizeof(int16_t) * n * n);
+  }
+  for (int i = 0; i < n4; i++)
+    for (int j = 0; j < n4; j++) {
+      e->mi[(mi_r + i) * f->mi_cols + mi_c + j] = cd->mi;
+      e->decoded[(mi_r + i) * f->mi_cols + mi_c + j] = 1;
+    }
+}
+
+static int64_t partition_cost(const enc_t *e, int mi_r, int mi_c, int n, int split) {
+  const B200Frame *f = e->f;
+  const int bsl = ilog2(n) - 2;   /* 8 -> 1 */
+  const int n4 = n >> 2, hbs = n4 >> 1;
+  const int has_rows = (mi_r + hbs) < f->mi_rows, has_cols = (mi_c + hbs) < f->mi_cols;
+  if (!has_rows || !has_cols) return 0;   /* forced / 1-bit cases: ignored by the rate model */
+  const int au = mi_r > e->tr0, al = mi_c > e->tc0;
+  const int above = au && ilog2(k_bw4[e->mi[(mi_r - 1) * f->mi_cols + mi_c].bsize]) < bsl;
+  const int left = al && ilog2(k_bh4[e->mi[mi_r * f->mi_cols + mi_c - 1].bsize]) < bsl;
+  const int ctx = (bsl - 1) * 4 + left * 2 + above;
+  return ((int64_t)f->lambda_q8 * e->rt->partition[ctx][split ? 3 : 0]) >> 8;
+}
+
+/* recursive partition search over square sizes partition_min..partition_max */
+static int64_t encode_tree(enc_t *e, int x, int y, int n) {
+  const B200Frame *f = e->f;
+  const int W = f->mi_cols * 4, H = f->mi_rows * 4;
+  if (x >= W || y >= H) return 0;
+  const int inside = (x + n <= W) && (y + n <= H);
+  const int can_none = inside && n <= f->partition_max && n <= 32;
+  const int can_split = n > 4 && (n > f->partition_min || !inside);
+  const int mi_r = y >> 2, mi_c = x >> 2;
+  if (can_none && !can_split) {
+    cand_t *cd = (cand_t *)malloc(sizeof(cand_t));
+    trial_block(e, x, y, n, cd);
+    const int64_t c = cd->cost + (n >= 8 ? partition_cost(e, mi_r, mi_c, n, 0) : 0);
+    commit_block(e, x, y, n, cd);
+    free(cd);
+    return c;
+  }
+  cand_t *cd = NULL;
+  int64_t j_none = INT64_MAX;
+  if (can_none) {
+    cd = (cand_t *)malloc(sizeof(cand_t));
+    trial_block(e, x, y, n, cd);
+    j_none = cd->cost + partition_cost(e, mi_r, mi_c, n, 0);
+  }
+  const int64_t pc_split = partition_cost(e, mi_r, mi_c, n, 1);   /* context read before children commit */
+  const int h = n >> 1;
+  int64_t j_split = pc_split;
+  j_split += encode_tree(e, x, y, h);
+  j_split += encode_tree(e, x + h, y, h);
+  j_split += encode_tree(e, x, y + h, h);
+  j_split += encode_tree(e, x + h, y + h, h);
+  if (can_none && j_none <= j_split) {
+    commit_block(e, x, y, n, cd);
+    j_split = j_none;
+  }
+  if (cd) free(cd);
+  return j_split;
+}
+
+/* Encode one tile (tile_row, tile_col): superblocks in raster order. */
+void orc_encode_tile(const B200Frame *f, const B200RateTables *rt, uint16_t *const src[3], uint16_t *const rec[3],
+                     B200Mi *mi, uint16_t *const eob[3], int16_t *const coef[3], uint8_t *decoded, int tile_row,
+                     int tile_col) {
+  enc_t e;
+  memset(&e, 0, sizeof(e));
+  e.f = f; e.rt = rt; e.stride = f->mi_cols * 4; e.mi = mi; e.decoded = decoded;
+  for (int p = 0; p < 3; p++) { e.src[p] = src[p]; e.rec[p] = rec[p]; e.eob[p] = eob[p]; e.coef[p] = coef[p]; }
+  e.tr0 = f->tile_row_start_sb[tile_row] * 16;
+  e.tr1 = f->tile_row_start_sb[tile_row + 1] * 16; if (e.tr1 > f->mi_rows) e.tr1 = f->mi_rows;
+  e.tc0 = f->tile_col_start_sb[tile_col] * 16;
+  e.tc1 = f->tile_col_start_sb[tile_col + 1] * 16; if (e.tc1 > f->mi_cols) e.tc1 = f->mi_cols;
+  for (int r = e.tr0; r < e.tr1; r += 16)
+    for (int c = e.tc0; c < e.tc1; c += 16) encode_tree(&e, c * 4, r * 4, 64);
+}
+
+void orc_encode_frame(const B200Frame *f, const B200RateTables *rt, uint16_t *const src[3], uint16_t *const rec[3],
+                      B200Mi *mi, uint16_t *const eob[3], int16_t *const coef[3]) {
+  uint8_t *decoded = (uint8_t *)calloc((size_t)f->mi_rows * f->mi_cols, 1);
+  for (int tr = 0; tr < f->tile_rows; tr++)
+    for (int tc = 0; tc < f->tile_cols; tc++) orc_encode_tile(f, rt, src, rec, mi, eob, coef, decoded, tr, tc);
+  free(decoded);
+}

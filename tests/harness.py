@@ -1,0 +1,149 @@
+"""Shared test plumbing: ctypes views of records.h, oracle + product library loaders, synthetic images."""
+import ctypes, os, subprocess, sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+class B200Frame(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "width", "height", "bit_depth", "planes", "mi_cols", "mi_rows", "sb_cols", "sb_rows",
+        "tile_cols_log2", "tile_rows_log2", "tile_cols", "tile_rows")] + [
+        ("tile_col_start_sb", ctypes.c_int32 * 65), ("tile_row_start_sb", ctypes.c_int32 * 65)] + [
+        (n, ctypes.c_int32) for n in (
+        "base_q_idx", "dc_q", "ac_q", "reduced_tx_set", "enable_cdef", "enable_restoration",
+        "color_description_present", "color_primaries", "transfer_characteristics", "matrix_coefficients", "full_range",
+        "partition_min", "partition_max", "rdo_tx_decision", "fine_directional_intra", "enable_cfl",
+        "lambda_q8", "lambda_satd_q8", "y_mode_mask", "uv_mode_mask", "tx_type_mask")] + [
+        ("lf_level", ctypes.c_int32 * 4), ("lf_sharpness", ctypes.c_int32),
+        ("cdef_damping", ctypes.c_int32), ("cdef_bits", ctypes.c_int32),
+        ("cdef_y_strength", ctypes.c_int32 * 8), ("cdef_uv_strength", ctypes.c_int32 * 8),
+        ("lr_type", ctypes.c_int32 * 3)]
+
+class B200Records(ctypes.Structure):
+    _fields_ = [("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3),
+                ("cdef_idx", ctypes.c_void_p)]
+
+RATE_TABLES_BYTES = 2 * (20 * 10 + 3 * 2 + 5 * 5 * 13 + 2 * 13 * 14 + 8 * 7 + 8 + 6 * 16 + 2 * 4 * 13 * 16 + 5 * 13 * 2 +
+                         4 * 2 * 12 + 5 * 2 * 9 * 2 + 2 * 3 * 2 + 5 * 2 * 4 * 3 + 5 * 2 * 42 * 4 + 4 * 2 * 21 * 13)
+
+MI_DTYPE = np.dtype([("bsize", "u1"), ("y_mode", "u1"), ("uv_mode", "u1"), ("angle", "u1"),
+                     ("tx_size", "u1"), ("tx_type", "u1"), ("flags", "u1"), ("cfl", "u1")])
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s" % (" ".join(cmd), r.stderr[-4000:]))
+
+_oracle = None
+def oracle():
+    """gcc-built CPU restatement (oracle/)."""
+    global _oracle
+    if _oracle is None:
+        _run(["make", "-s", "oracle"])
+        _oracle = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+    return _oracle
+
+_host = None
+def hostlib():
+    """Product library. On a box without nvcc output falls back to nothing: tests that need it build it."""
+    global _host
+    if _host is None:
+        _run(["make", "-s", "lib"])
+        _host = ctypes.CDLL(os.path.join(ROOT, "cavif_rs_b200", "libcavif_b200.so"))
+        _host.b200av1_frame_setup.argtypes = [ctypes.POINTER(B200Frame)] + [ctypes.c_int] * 6
+        _host.b200av1_build_rate_tables.argtypes = [ctypes.c_int, ctypes.c_void_p]
+        _host.b200av1_pack_frame.argtypes = [ctypes.POINTER(B200Frame), ctypes.POINTER(B200Records),
+                                             ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
+    return _host
+
+def frame_setup(w, h, depth=8, planes=3, quantizer=121, tiles=1):
+    f = B200Frame()
+    rc = hostlib().b200av1_frame_setup(ctypes.byref(f), w, h, depth, planes, quantizer, tiles)
+    assert rc == 0
+    return f
+
+def rate_tables(qidx):
+    buf = np.zeros(RATE_TABLES_BYTES // 2, np.uint16)
+    hostlib().b200av1_build_rate_tables(qidx, buf.ctypes.data)
+    return buf
+
+def pad_planes(planes, f):
+    """Replicate-pad visible planes (h, w) to the 8-aligned coded size (mi_rows*4, mi_cols*4), as uint16."""
+    H, W = f.mi_rows * 4, f.mi_cols * 4
+    out = []
+    for p in planes:
+        a = np.asarray(p, dtype=np.uint16)
+        a = np.pad(a, ((0, H - a.shape[0]), (0, W - a.shape[1])), mode="edge")
+        out.append(np.ascontiguousarray(a))
+    return out
+
+class Records:
+    def __init__(self, f):
+        n_mi = f.mi_rows * f.mi_cols
+        self.f = f
+        self.mi = np.zeros(n_mi, MI_DTYPE)
+        self.eob = [np.zeros(n_mi, np.uint16) for _ in range(3)]
+        self.coef = [np.zeros(f.sb_rows * f.sb_cols * 4096, np.int16) for _ in range(3)]
+        self.cdef_idx = np.zeros(f.sb_rows * f.sb_cols, np.int8)
+        self.rec = [np.zeros((f.mi_rows * 4, f.mi_cols * 4), np.uint16) for _ in range(3)]
+    def c_records(self):
+        r = B200Records()
+        r.mi = self.mi.ctypes.data
+        for p in range(3):
+            r.eob[p] = self.eob[p].ctypes.data
+            r.coef[p] = self.coef[p].ctypes.data
+        r.cdef_idx = self.cdef_idx.ctypes.data
+        return r
+
+def ptr3(arrs):
+    return (ctypes.c_void_p * 3)(*[a.ctypes.data for a in arrs])
+
+def oracle_encode(f, rt, src):
+    """Run the oracle hot path on padded uint16 planes. Returns Records (with .rec)."""
+    L = oracle()
+    rec = Records(f)
+    src3 = list(src) + [src[0]] * (3 - len(src))
+    L.orc_encode_frame(ctypes.byref(f), rt.ctypes.data, ptr3(src3), ptr3(rec.rec), rec.mi.ctypes.data,
+                       ptr3(rec.eob), ptr3(rec.coef))
+    return rec
+
+def pack(f, rec):
+    out = ctypes.c_void_p()
+    n = ctypes.c_size_t()
+    cr = rec.c_records()
+    rc = hostlib().b200av1_pack_frame(ctypes.byref(f), ctypes.byref(cr), ctypes.byref(out), ctypes.byref(n))
+    assert rc == 0, rc
+    data = ctypes.string_at(out.value, n.value)
+    ctypes.CDLL(None).free(out)
+    return data
+
+def synth_image(w, h, seed=0, alpha=False):
+    """Deterministic natural-ish RGBA test frame (SURVEY.md 8d recipe: octave sinusoids + flat rectangles + noise)."""
+    rng = np.random.default_rng(0xC0FFEE + seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.zeros((h, w, 4), np.float32)
+    lum_noise = rng.normal(0, 3, (h, w)).astype(np.float32)
+    for c in range(3):
+        acc = np.full((h, w), 128, np.float32)
+        for o in range(4):
+            fx = rng.uniform(0.5, 3) * (2 ** o) / w
+            fy = rng.uniform(0.5, 3) * (2 ** o) / h
+            ph = rng.uniform(0, 2 * np.pi)
+            acc += (96 / 2 ** o) * np.sin(2 * np.pi * (fx * xx + fy * yy) + ph) * 0.5
+        img[..., c] = acc + lum_noise
+    for _ in range(24):
+        rw = int(rng.integers(16, max(17, w // 4))); rh = int(rng.integers(16, max(17, h // 4)))
+        x0 = int(rng.integers(0, max(1, w - rw))); y0 = int(rng.integers(0, max(1, h - rh)))
+        img[y0:y0 + rh, x0:x0 + rw, :3] = rng.integers(0, 256, 3)
+    img[..., 3] = 255
+    if alpha:
+        cy, cx = h / 2, w / 2
+        d = np.sqrt(((yy - cy) / (h * 0.45)) ** 2 + ((xx - cx) / (w * 0.45)) ** 2)
+        ramp = 24.0 / min(w, h)
+        img[..., 3] = np.clip((1.0 - d) / ramp, 0, 1) * 255
+        for _ in range(8):
+            rw = int(rng.integers(8, max(9, w // 6))); rh = int(rng.integers(8, max(9, h // 6)))
+            x0 = int(rng.integers(0, max(1, w - rw))); y0 = int(rng.integers(0, max(1, h - rh)))
+            img[y0:y0 + rh, x0:x0 + rw, 3] = 0
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
