@@ -231,12 +231,14 @@ struct TilePacker {
     };
     int psum = 0;
     // partition symbols: 0 NONE 1 HORZ 2 VERT 3 SPLIT 4 HORZ_A 5 HORZ_B 6 VERT_A 7 VERT_B 8 HORZ_4 9 VERT_4
-    if (has_cols) {   // !has_rows: split_or_horz
-      psum = prob(1) + prob(3);
-      if (nsym > 4) { psum += prob(4) + prob(5) + prob(6); if (nsym == 10) psum += prob(8); }
-    } else {          // !has_cols: split_or_vert
+    // The forced direction is implied; P(split) gathers the mass of every partition type that also
+    // splits in the OTHER direction.
+    if (has_cols) {   // bottom edge (!has_rows): split_or_horz -> "vertical-alike" mass
       psum = prob(2) + prob(3);
       if (nsym > 4) { psum += prob(4) + prob(6) + prob(7); if (nsym == 10) psum += prob(9); }
+    } else {          // right edge (!has_cols): split_or_vert -> "horizontal-alike" mass
+      psum = prob(1) + prob(3);
+      if (nsym > 4) { psum += prob(4) + prob(5) + prob(6); if (nsym == 10) psum += prob(8); }
     }
     uint16_t tmp[3] = {(uint16_t)(32768 - (32768 - psum)), 0, 0};
     // symbol 1 ("split") has probability psum; icdf[0] = 32768 - P(symbol 0) = psum
