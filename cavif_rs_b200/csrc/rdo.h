@@ -1,0 +1,34 @@
+// Device job descriptors of the RDO kernel (rdo.cu).
+#ifndef B200_RDO_H_
+#define B200_RDO_H_
+#include <stdint.h>
+#include "records.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+// One AV1 frame to encode (the colour planes of an image, or its alpha plane): all pointers are
+// device pointers.  Planes are uint16 samples, row stride mi_cols*4, mi_rows*4 rows.
+typedef struct B200RdoJob {
+  B200Frame frame;
+  const B200RateTables *rate;
+  const uint16_t *src[3];
+  uint16_t *rec[3];
+  B200Mi *mi;
+  uint16_t *eob[3];
+  int16_t *coef[3];
+  uint8_t *decoded;       // mi_rows*mi_cols bytes, zero-initialised
+} B200RdoJob;
+
+typedef struct B200TileRef {
+  int32_t job;
+  int16_t tile_row, tile_col;
+} B200TileRef;
+
+// Launch one CTA per tile on `stream` (cudaStream_t).  Returns a cudaError_t value.
+int b200_rdo_launch(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int n_tiles, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

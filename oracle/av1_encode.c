@@ -352,10 +352,10 @@ static void trial_block(enc_t *e, int x, int y, int n, cand_t *cd) {
     if (c < best_c[0]) { best_c[1] = best_c[0]; best_m[1] = best_m[0]; best_c[0] = c; best_m[0] = m; }
     else if (c < best_c[1]) { best_c[1] = c; best_m[1] = m; }
   }
-  /* --- full trial of the top-2 modes with the first allowed transform type, then tx type search */
+  /* --- full trials: top-2 modes x allowed transform types (all types when rdo_tx_decision, else the
+   * first allowed one); candidate order (mode rank, type index), strict '<' keeps the earliest. */
   int first_tt = -1;
   for (int k = 0; k < 5; k++) if ((f->tx_type_mask >> k) & 1) { first_tt = k_tx_types[k]; break; }
-  if (n >= 32) first_tt = TX_DCT_DCT;
   int64_t bestJ = INT64_MAX;
   int best_mode = best_m[0], best_tt = first_tt;
   int16_t qc[1024];
@@ -364,30 +364,17 @@ static void trial_block(enc_t *e, int x, int y, int n, cand_t *cd) {
     const int m = best_m[k];
     if (m < 0) continue;
     orc_predict_intra(m, 0, n, above, left, ha, hl, f->bit_depth, pred);
-    uint32_t rate;
-    const uint64_t d = trial_plane(e, 0, x, y, n, pred, first_tt, m, qc, &eobv, recon, &rate);
     uint32_t mrate = ymode_cost[m];
     if (n >= 8 && m >= V_PRED && m <= D67_PRED) mrate += rt->angle_delta[m - V_PRED][3];
-    const int64_t J = rd_cost(f, d, rate + mrate);
-    if (J < bestJ) {
-      bestJ = J; best_mode = m; best_tt = first_tt;
-      memcpy(cd->qcoef[0], qc, sizeof(int16_t) * n * n);
-      memcpy(cd->recon[0], recon, sizeof(uint16_t) * n * n);
-      cd->eob[0] = eobv;
-    }
-  }
-  if (f->rdo_tx_decision && n <= 16) {
-    orc_predict_intra(best_mode, 0, n, above, left, ha, hl, f->bit_depth, pred);
-    uint32_t mrate = ymode_cost[best_mode];
-    if (n >= 8 && best_mode >= V_PRED && best_mode <= D67_PRED) mrate += rt->angle_delta[best_mode - V_PRED][3];
-    for (int k = 0; k < 5; k++) {
-      const int tt = k_tx_types[k];
-      if (!((f->tx_type_mask >> k) & 1) || tt == first_tt) continue;
+    for (int t = 0; t < 5; t++) {
+      const int tt = k_tx_types[t];
+      if (!((f->tx_type_mask >> t) & 1)) continue;
+      if (!(f->rdo_tx_decision && n <= 16) && tt != first_tt) continue;
       uint32_t rate;
-      const uint64_t d = trial_plane(e, 0, x, y, n, pred, tt, best_mode, qc, &eobv, recon, &rate);
+      const uint64_t d = trial_plane(e, 0, x, y, n, pred, tt, m, qc, &eobv, recon, &rate);
       const int64_t J = rd_cost(f, d, rate + mrate);
       if (J < bestJ) {
-        bestJ = J; best_tt = tt;
+        bestJ = J; best_mode = m; best_tt = tt;
         memcpy(cd->qcoef[0], qc, sizeof(int16_t) * n * n);
         memcpy(cd->recon[0], recon, sizeof(uint16_t) * n * n);
         cd->eob[0] = eobv;
@@ -403,7 +390,7 @@ static void trial_block(enc_t *e, int x, int y, int n, cand_t *cd) {
   cd->mi.tx_type = (uint8_t)best_tt;
   cd->mi.uv_mode = DC_PRED;
 
-  /* --- chroma: pick the uv mode by SATD (both planes) + rate, one full trial */
+  /* --- chroma: rank uv modes by SATD (U+V) + rate, full trial of the top-2, keep the better */
   if (f->planes > 1) {
     const int cfl_allowed = n <= 32;
     const uint16_t *uvcost = rt->uv_mode[cfl_allowed][best_mode];
@@ -411,8 +398,8 @@ static void trial_block(enc_t *e, int x, int y, int n, cand_t *cd) {
     int hau, hlu;
     build_edges(e, 1, x, y, n, aU, lU, &hau, &hlu);
     build_edges(e, 2, x, y, n, aV, lV, &hau, &hlu);
-    int64_t bc = INT64_MAX;
-    int buv = DC_PRED;
+    int64_t bc[2] = {INT64_MAX, INT64_MAX};
+    int buv[2] = {-1, -1};
     for (int m = 0; m < 13; m++) {
       if (!((f->uv_mode_mask >> m) & 1)) continue;
       uint32_t mrate = uvcost[m];
@@ -422,20 +409,33 @@ static void trial_block(enc_t *e, int x, int y, int n, cand_t *cd) {
       orc_predict_intra(m, 0, n, aV, lV, hau, hlu, f->bit_depth, pred);
       s += satd4(e->src[2] + y * e->stride + x, e->stride, pred, n);
       const int64_t c = (int64_t)s * 64 + (((int64_t)f->lambda_satd_q8 * mrate) >> 8);
-      if (c < bc) { bc = c; buv = m; }
+      if (c < bc[0]) { bc[1] = bc[0]; buv[1] = buv[0]; bc[0] = c; buv[0] = m; }
+      else if (c < bc[1]) { bc[1] = c; buv[1] = m; }
     }
-    cd->mi.uv_mode = (uint8_t)buv;
-    uint32_t mrate = uvcost[buv];
-    if (n >= 8 && buv >= V_PRED && buv <= D67_PRED) mrate += rt->angle_delta[buv - V_PRED][3];
-    const int ctt = chroma_tx_type(buv, n);
-    uint32_t rate;
-    orc_predict_intra(buv, 0, n, aU, lU, hau, hlu, f->bit_depth, pred);
-    uint64_t d = trial_plane(e, 1, x, y, n, pred, ctt, best_mode, cd->qcoef[1], &cd->eob[1], cd->recon[1], &rate);
-    uint32_t rsum = rate + mrate;
-    orc_predict_intra(buv, 0, n, aV, lV, hau, hlu, f->bit_depth, pred);
-    d += trial_plane(e, 2, x, y, n, pred, ctt, best_mode, cd->qcoef[2], &cd->eob[2], cd->recon[2], &rate);
-    rsum += rate;
-    total += rd_cost(f, d, rsum);
+    int64_t bestC = INT64_MAX;
+    for (int k = 0; k < 2; k++) {
+      const int m = buv[k];
+      if (m < 0) continue;
+      uint32_t mrate = uvcost[m];
+      if (n >= 8 && m >= V_PRED && m <= D67_PRED) mrate += rt->angle_delta[m - V_PRED][3];
+      const int ctt = chroma_tx_type(m, n);
+      int16_t q1[1024], q2[1024];
+      uint16_t r1[1024], r2[1024], e1, e2;
+      uint32_t rate1, rate2;
+      orc_predict_intra(m, 0, n, aU, lU, hau, hlu, f->bit_depth, pred);
+      uint64_t d = trial_plane(e, 1, x, y, n, pred, ctt, best_mode, q1, &e1, r1, &rate1);
+      orc_predict_intra(m, 0, n, aV, lV, hau, hlu, f->bit_depth, pred);
+      d += trial_plane(e, 2, x, y, n, pred, ctt, best_mode, q2, &e2, r2, &rate2);
+      const int64_t J = rd_cost(f, d, rate1 + rate2 + mrate);
+      if (J < bestC) {
+        bestC = J;
+        cd->mi.uv_mode = (uint8_t)m;
+        memcpy(cd->qcoef[1], q1, sizeof(int16_t) * n * n); memcpy(cd->qcoef[2], q2, sizeof(int16_t) * n * n);
+        memcpy(cd->recon[1], r1, sizeof(uint16_t) * n * n); memcpy(cd->recon[2], r2, sizeof(uint16_t) * n * n);
+        cd->eob[1] = e1; cd->eob[2] = e2;
+      }
+    }
+    total += bestC;
   }
   /* --- skip flag */
   const int all_zero = cd->eob[0] == 0 && (f->planes == 1 || (cd->eob[1] == 0 && cd->eob[2] == 0));

@@ -1,0 +1,4 @@
+// TEST-ONLY: builds the CUDA kernels as host code on top of cuda_emu.h (see that header).
+#define CUDA_EMU_IMPLEMENTATION
+#include "cuda_emu.h"
+#include "../../cavif_rs_b200/csrc/rdo.cu"
