@@ -1,0 +1,276 @@
+#!/usr/bin/env python3
+"""Benchmark of the B200 AVIF encode path (contract: see the task statement / DESIGN.md section 'Measurement').
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload 1080p|4k]
+
+One "step" = one pass of the whole hot path over one batch of synthetic RGBA frames per GPU
+(BASELINE.json configs[1]: 64 x 1920x1080 RGBA, quality 80, speed 4, 8-bit), producing the AVIF files
+in host memory.  `value` = Mpixels/s with the inputs already resident in HBM; `e2e` = the same through
+the public API with pinned HOST input buffers (H2D and D2H inside the timed region).
+Reference arm (`--impl reference`): the reference's codec (rav1e, crates.io) cannot be built here (no Rust
+toolchain, no network - BASELINE.md section 2), so the CPU arm is the oracle PORT of the same algorithm
+(oracle/ hot path + host packer) on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    "1080p": dict(name="64x1920x1080 RGBA8 opaque, quality 80, speed 4, 8-bit (BASELINE configs[1])",
+                  n=64, w=1920, h=1080, quality=80.0, speed=4, depth=8),
+    "4k": dict(name="16x3840x2160 RGBA8 opaque, quality 80, speed 4, 10-bit (BASELINE configs[2])",
+               n=16, w=3840, h=2160, quality=80.0, speed=4, depth=10),
+}
+# algorithmic bytes per pixel moved by the RDO kernel: 3 source planes read + 3 reconstructed planes
+# written + 3 coefficient planes written (all 16-bit samples) + 8 B mode info and 3 x 2 B eob per 4x4 unit
+RDO_BYTES_PER_PX = 3 * 2 + 3 * 2 + 3 * 2 + (8 + 6) / 16.0
+
+
+def make_images(wl, seed0=0):
+    """Deterministic synthetic frames (SURVEY.md 8d recipe). 8 base frames, the rest are cyclic shifts of them
+    (distinct content, same statistics) to keep set-up time low."""
+    import numpy as np
+    import harness as H
+    base = [H.synth_image(wl["w"], wl["h"], seed0 + i) for i in range(min(8, wl["n"]))]
+    imgs = []
+    for i in range(wl["n"]):
+        b = base[i % len(base)]
+        k = i // len(base)
+        imgs.append(np.ascontiguousarray(np.roll(b, (37 * k, 91 * k), axis=(0, 1))) if k else b)
+    return imgs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            p = [x.strip() for x in s.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0])); mx = float(p[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons)}
+
+
+def _cpu_worker(args):
+    """Encode one image with the oracle CPU pipeline; returns pixels encoded."""
+    w, h, seed, quality, speed, depth = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_encode as CE
+    import harness as H
+    img = H.synth_image(w, h, seed)
+    t0 = time.perf_counter()
+    CE.encode_rgba(img, quality, speed, depth)
+    return w * h, time.perf_counter() - t0
+
+
+def cpu_baseline(wl, images_per_core=1):
+    """Oracle port on all host cores, one process per core, bounded sample of the workload's frames."""
+    from concurrent.futures import ProcessPoolExecutor
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n = cores * images_per_core
+    jobs = [(wl["w"], wl["h"], i % 8, wl["quality"], wl["speed"], wl["depth"]) for i in range(n)]
+    # warm the build (make) in the parent so workers only load
+    import harness as H
+    H.oracle(); H.hostlib()
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as ex:
+        res = list(ex.map(_cpu_worker, jobs))
+    dt = time.perf_counter() - t0
+    px = sum(r[0] for r in res)
+    return {"value": px / 1e6 / dt, "unit": "Mpixels/s", "cores": cores, "kind": "port",
+            "sample": "%d frames of %dx%d (one per core, %d processes), wall %.1f s incl. process start; "
+                      "reference rav1e CPU path: not runnable in this environment" % (n, wl["w"], wl["h"], cores, dt)}
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(wl)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = sum(vals) / len(vals)
+    cb["value"] = v
+    px = (os.cpu_count() or 1) * wl["w"] * wl["h"]
+    out = {"impl": "reference", "metric": "Mpixels/s encoded", "value": v, "unit": "Mpixels/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": px / 1e6 / v * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+           "config": {"workload": wl["name"], "sample": cb["sample"]}, "cpu_baseline": cb,
+           "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import numpy as np
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    # CPU baseline first (rank 0, N == 1 only), before CUDA is initialised in this process
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(wl)
+
+    import cavif_rs_b200 as C
+    if C.device_count() <= 0:
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        # north_star: NCCL only to broadcast the quantiser/rate tables (rank 0 -> all), once per batch
+        import harness as H
+        q = C.quality_to_quantizer(wl["quality"])
+        tbl = torch.from_numpy(H.rate_tables(max(q, 1)).astype(np.int32)).to(dev) if rank == 0 else \
+            torch.zeros(H.RATE_TABLES_BYTES // 2, dtype=torch.int32, device=dev)
+        dist.broadcast(tbl, src=0)
+
+    imgs = make_images(wl, seed0=1000 * rank)     # every rank encodes its own batch (images are independent units)
+    px_per_step = wl["n"] * wl["w"] * wl["h"]
+    enc = (C.Encoder.new().with_quality(wl["quality"]).with_speed(wl["speed"]).with_bit_depth(wl["depth"])
+           .with_alpha_color_mode(C.AlphaColorMode.UnassociatedDirty).with_device(local_rank))
+    d_imgs = [torch.from_numpy(a).to(dev) for a in imgs]                       # resident in HBM
+    h_imgs = [torch.from_numpy(a).pin_memory() for a in imgs]                  # pinned host buffers for e2e
+    h_np = [t.numpy() for t in h_imgs]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        s0 = C.stats()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        out_bytes = 0
+        for _ in range(steps):
+            res = fn()
+            out_bytes += sum(len(r.avif_file) for r in res)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        # the step contains host work (symbol packing): the events bracket it on the launching stream, like the wall clock
+        s1 = C.stats()
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        delta = {k: s1[k] - s0[k] for k in s0}
+        return ms, wall, delta, clocks, out_bytes
+
+    ms, wall, d, clocks, out_bytes = timed(lambda: enc.encode_batch(d_imgs), args.steps, args.warmup, True)
+    ms2, wall2, d2, _, _ = timed(lambda: enc.encode_batch(h_np), args.steps, max(1, args.warmup // 2), False)
+
+    if rank == 0:
+        total_px = px_per_step * world * args.steps
+        value = total_px / 1e6 / (ms / 1e3)
+        e2e = total_px / 1e6 / (ms2 / 1e3)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = json.load(open(peaks_path))["hbm_gbs"]; peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
+        rdo_launches = max(args.steps, 1)
+        rdo_ms = d["gpu_ms_rdo"] / rdo_launches
+        achieved = RDO_BYTES_PER_PX * px_per_step / 1e9 / (rdo_ms / 1e3) if rdo_ms > 0 else 0.0
+        out = {
+            "metric": "Mpixels/s encoded", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+            "config": {"workload": wl["name"], "images_per_gpu": wl["n"], "quality": wl["quality"], "speed": wl["speed"],
+                       "depth": wl["depth"], "parallelism": "images sharded one batch per GPU, no data-path collective",
+                       "l2": "inputs (%.0f MB/step) larger than L2, no flush needed" % (px_per_step * 4 / 1e6),
+                       "tools": "filters off (deblock/CDEF/LR not emitted yet), partitions 4..16, 13 intra modes, 5 tx types",
+                       "avif_bytes_per_step": out_bytes // max(args.steps, 1)},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "Mpixels/s", "h2d_bytes_per_step": d2["h2d_bytes"] // args.steps,
+                    "d2h_bytes_per_step": d2["d2h_bytes"] // args.steps, "ms_per_step": ms2 / args.steps},
+            "gpu_launches": int(d["kernel_launches"]),
+            "breakdown_ms_per_step": {"gpu_rdo_kernel": rdo_ms, "gpu_all": d["gpu_ms_total"] / args.steps,
+                                      "host_pack_mux": d["host_ms_pack"] / args.steps, "wall": wall * 1e3 / args.steps},
+            "roofline": {"bound": "hbm", "kernel": "b200_rdo_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "RDO is dependency/ALU-bound, not DRAM-bound (SURVEY.md 8d); algorithmic bytes = %.2f B/px" % RDO_BYTES_PER_PX},
+            "cpu_baseline": cb,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

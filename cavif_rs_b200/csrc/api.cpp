@@ -1,0 +1,705 @@
+// C ABI + host pipeline of the B200 AVIF encode path (include/b200avif.h).
+//
+// Host-side mirror of ravif::Encoder (/root/reference/ravif/src/av1encoder.rs:66-481): the
+// builder state, encode_rgba / encode_rgb / encode_raw_planes_* flow, the colour||alpha split into
+// two independent AV1 encodes (:400-481) and the call into the muxer (:457-473).  The body of
+// encode_to_av1 (:749-771) is replaced by: H2D copy -> convert kernel -> RDO kernel (one CTA per
+// tile, all tiles of all images of the batch in ONE launch) -> D2H of the block records -> CPU
+// symbol packing (thread pool over frames) -> AVIF mux.
+//
+// No CPU fallback: every encode entry point fails with B200AVIF_ENCODING_ERROR when CUDA is
+// unavailable.
+#include "../../include/b200avif.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "av1_pack.h"
+#include "avif_mux.h"
+#include "b200_dev.h"
+#include "ravif_settings.h"
+#include "rdo.h"
+
+struct b200avif_encoder {
+  uint8_t quantizer, alpha_quantizer, speed;
+  bool premultiplied_alpha;
+  int color_model;
+  size_t threads;   // 0 = None
+  int alpha_color_mode;
+  int output_depth; // 0 auto
+  std::vector<uint8_t> exif;
+  int device;       // -1: current
+};
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+std::atomic<uint64_t> g_launches{0}, g_h2d{0}, g_d2h{0};
+std::mutex g_stat_mu;
+double g_ms_rdo = 0, g_ms_total = 0, g_ms_pack = 0;
+
+#define CU(call)                                                                                 \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) {                                                                     \
+      g_err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call;               \
+      return B200AVIF_ENCODING_ERROR;                                                            \
+    }                                                                                            \
+  } while (0)
+
+// ---- a tiny thread pool for symbol packing -------------------------------------------------------
+void parallel_for(size_t n, const std::function<void(size_t)> &fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 4;
+  const size_t nt = std::min<size_t>(hw, n);
+  if (nt <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < nt; t++)
+    th.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); });
+  for (auto &t : th) t.join();
+}
+
+// ---- reusable device / pinned-host arenas (one context per concurrent call) ----------------------
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, used = 0;
+  bool host;
+  explicit Arena(bool h) : host(h) {}
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    release();
+    const size_t want = bytes + bytes / 8;
+    cudaError_t e = host ? cudaHostAlloc((void **)&base, want, cudaHostAllocDefault) : cudaMalloc((void **)&base, want);
+    if (e != cudaSuccess) { base = nullptr; cap = 0; g_err = std::string("CUDA alloc failed: ") + cudaGetErrorString(e); return 1; }
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (base) { if (host) cudaFreeHost(base); else cudaFree(base); }
+    base = nullptr; cap = 0;
+  }
+  void reset() { used = 0; }
+  template <typename T> T *take(size_t count) {
+    used = (used + 255) & ~(size_t)255;
+    T *p = (T *)(base + used);
+    used += count * sizeof(T);
+    return p;
+  }
+};
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct Context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Arena dev{false}, pin{true};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::map<int, B200RateTables *> d_rate;   // per base_q_idx
+  ~Context() {}
+};
+std::mutex g_ctx_mu;
+std::vector<std::unique_ptr<Context>> g_ctx_free;
+
+int acquire_context(int device, std::unique_ptr<Context> &out) {
+  int cur = 0;
+  if (device < 0) { if (cudaGetDevice(&cur) != cudaSuccess) return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)"); device = cur; }
+  {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    for (size_t i = 0; i < g_ctx_free.size(); i++)
+      if (g_ctx_free[i]->device == device) { out = std::move(g_ctx_free[i]); g_ctx_free.erase(g_ctx_free.begin() + i); break; }
+  }
+  CU(cudaSetDevice(device));
+  if (!out) {
+    out.reset(new Context());
+    out->device = device;
+    CU(cudaStreamCreateWithFlags(&out->stream, cudaStreamNonBlocking));
+    for (auto &e : out->ev) CU(cudaEventCreate(&e));
+  }
+  return 0;
+}
+void release_context(std::unique_ptr<Context> &c) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  g_ctx_free.push_back(std::move(c));
+}
+
+// ---- one AV1 frame to encode (colour or alpha of an image) ------------------------------------------
+struct FrameJob {
+  B200Frame f;
+  // device
+  uint16_t *d_src[3] = {nullptr, nullptr, nullptr}, *d_rec[3] = {nullptr, nullptr, nullptr};
+  B200Mi *d_mi = nullptr;
+  uint16_t *d_eob[3] = {nullptr, nullptr, nullptr};
+  int16_t *d_coef[3] = {nullptr, nullptr, nullptr};
+  uint8_t *d_decoded = nullptr;
+  // pinned host
+  B200Mi *h_mi = nullptr;
+  uint16_t *h_eob[3] = {nullptr, nullptr, nullptr};
+  int16_t *h_coef[3] = {nullptr, nullptr, nullptr};
+  std::vector<uint8_t> obu;
+  int status = 0;
+  size_t n_mi() const { return (size_t)f.mi_rows * f.mi_cols; }
+  size_t n_px() const { return n_mi() * 16; }
+  size_t n_coef() const { return (size_t)f.sb_rows * f.sb_cols * B200_SB_COEFS; }
+};
+
+size_t job_dev_bytes(const FrameJob &j, bool own_src) {
+  const int P = j.f.planes;
+  size_t b = 0;
+  if (own_src) b += P * align256(j.n_px() * 2);
+  b += P * align256(j.n_px() * 2);                 // rec
+  b += align256(j.n_mi() * sizeof(B200Mi));
+  b += P * align256(j.n_mi() * 2);
+  b += P * align256(j.n_coef() * 2);
+  b += align256(j.n_mi());
+  return b + 4096;
+}
+size_t job_pin_bytes(const FrameJob &j) {
+  const int P = j.f.planes;
+  return align256(j.n_mi() * sizeof(B200Mi)) + P * align256(j.n_mi() * 2) + P * align256(j.n_coef() * 2) + 4096;
+}
+void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
+  const int P = j.f.planes;
+  for (int p = 0; p < P; p++) {
+    if (own_src) j.d_src[p] = dev.take<uint16_t>(j.n_px());
+    j.d_rec[p] = dev.take<uint16_t>(j.n_px());
+    j.d_eob[p] = dev.take<uint16_t>(j.n_mi());
+    j.d_coef[p] = dev.take<int16_t>(j.n_coef());
+    j.h_eob[p] = pin.take<uint16_t>(j.n_mi());
+    j.h_coef[p] = pin.take<int16_t>(j.n_coef());
+  }
+  j.d_mi = dev.take<B200Mi>(j.n_mi());
+  j.d_decoded = dev.take<uint8_t>(j.n_mi());
+  j.h_mi = pin.take<B200Mi>(j.n_mi());
+}
+
+// Apply ravif's SpeedTweaks (av1encoder.rs:555-605) + rav1e_config (:662-708) to a frame description.
+int configure_frame(B200Frame *f, size_t w, size_t h, int depth, bool mono, int quantizer, int speed, size_t threads,
+                    int full_range, bool has_cd, int mc) {
+  B200SpeedTweaks tw;
+  b200_speed_tweaks(speed, quantizer, &tw);
+  size_t tiles = b200_tile_target(threads, w, h, (size_t)tw.min_tile_size);
+  tiles = std::min<size_t>(std::max<size_t>(tiles, 1), 4096);
+  if (b200av1_frame_setup(f, (int)w, (int)h, depth, mono ? 1 : 3, quantizer, (int)tiles) != 0)
+    return fail(B200AVIF_INVALID_ARGUMENT, "unsupported frame geometry");
+  f->reduced_tx_set = tw.reduced_tx_set;
+  f->rdo_tx_decision = tw.rdo_tx_decision;
+  f->partition_min = tw.partition_min;
+  // The device RDO currently searches square partitions up to 16x16 (ravif reaches 32x32/64x64 only at
+  // speed <= 2 with low quantizers, av1encoder.rs:563-570); larger maxima are clamped.
+  f->partition_max = std::min(tw.partition_max, 16);
+  f->partition_min = std::min(f->partition_min, f->partition_max);
+  f->fine_directional_intra = tw.fine_directional_intra;
+  f->enable_cdef = 0;          // in-loop filter stages: not emitted yet (valid bitstream, filters off)
+  f->enable_restoration = 0;
+  f->full_range = full_range;
+  f->color_description_present = has_cd ? 1 : 0;
+  if (has_cd) { f->color_primaries = 1; f->transfer_characteristics = 13; f->matrix_coefficients = mc; }
+  return 0;
+}
+
+// Upload (cached) rate tables for this frame's quantiser.
+int rate_tables_for(Context &c, int qidx, B200RateTables **out) {
+  auto it = c.d_rate.find(qidx);
+  if (it != c.d_rate.end()) { *out = it->second; return 0; }
+  B200RateTables host;
+  b200av1_build_rate_tables(qidx, &host);
+  B200RateTables *d = nullptr;
+  CU(cudaMalloc((void **)&d, sizeof(host)));
+  CU(cudaMemcpy(d, &host, sizeof(host), cudaMemcpyHostToDevice));
+  c.d_rate[qidx] = d;
+  *out = d;
+  return 0;
+}
+
+// Launch the RDO kernel for a set of jobs (device buffers ready, sources filled) and fetch records.
+int run_rdo_and_fetch(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin, bool fetch_rec,
+                      std::vector<std::vector<uint16_t>> *rec_out) {
+  std::vector<B200RdoJob> hj(jobs.size());
+  std::vector<B200TileRef> tiles;
+  for (size_t i = 0; i < jobs.size(); i++) {
+    FrameJob &j = *jobs[i];
+    B200RdoJob &r = hj[i];
+    memset(&r, 0, sizeof(r));
+    r.frame = j.f;
+    B200RateTables *rt;
+    if (int e = rate_tables_for(c, j.f.base_q_idx, &rt)) return e;
+    r.rate = rt;
+    for (int p = 0; p < 3; p++) {
+      const int q = p < j.f.planes ? p : 0;
+      r.src[p] = j.d_src[q]; r.rec[p] = j.d_rec[q]; r.eob[p] = j.d_eob[q]; r.coef[p] = j.d_coef[q];
+    }
+    r.mi = j.d_mi; r.decoded = j.d_decoded;
+    for (int tr = 0; tr < j.f.tile_rows; tr++)
+      for (int tc = 0; tc < j.f.tile_cols; tc++) tiles.push_back(B200TileRef{(int32_t)i, (int16_t)tr, (int16_t)tc});
+    CU(cudaMemsetAsync(j.d_decoded, 0, j.n_mi(), c.stream));
+  }
+  B200RdoJob *d_jobs = dev.take<B200RdoJob>(hj.size());
+  B200TileRef *d_tiles = dev.take<B200TileRef>(tiles.size());
+  CU(cudaMemcpyAsync(d_jobs, hj.data(), hj.size() * sizeof(B200RdoJob), cudaMemcpyHostToDevice, c.stream));
+  CU(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(B200TileRef), cudaMemcpyHostToDevice, c.stream));
+  CU(cudaEventRecord(c.ev[1], c.stream));
+  const int le = b200_rdo_launch(d_jobs, d_tiles, (int)tiles.size(), c.stream);
+  if (le != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("RDO kernel launch failed: ") + cudaGetErrorString((cudaError_t)le));
+  g_launches += 1;
+  CU(cudaEventRecord(c.ev[2], c.stream));
+  uint64_t d2h = 0;
+  for (FrameJob *jp : jobs) {
+    FrameJob &j = *jp;
+    CU(cudaMemcpyAsync(j.h_mi, j.d_mi, j.n_mi() * sizeof(B200Mi), cudaMemcpyDeviceToHost, c.stream));
+    d2h += j.n_mi() * sizeof(B200Mi);
+    for (int p = 0; p < j.f.planes; p++) {
+      CU(cudaMemcpyAsync(j.h_eob[p], j.d_eob[p], j.n_mi() * 2, cudaMemcpyDeviceToHost, c.stream));
+      CU(cudaMemcpyAsync(j.h_coef[p], j.d_coef[p], j.n_coef() * 2, cudaMemcpyDeviceToHost, c.stream));
+      d2h += j.n_mi() * 2 + j.n_coef() * 2;
+    }
+  }
+  if (fetch_rec && rec_out) {
+    rec_out->clear();
+    for (FrameJob *jp : jobs)
+      for (int p = 0; p < jp->f.planes; p++) {
+        rec_out->emplace_back(jp->n_px());
+        CU(cudaMemcpyAsync(rec_out->back().data(), jp->d_rec[p], jp->n_px() * 2, cudaMemcpyDeviceToHost, c.stream));
+      }
+  }
+  CU(cudaEventRecord(c.ev[3], c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  g_d2h += d2h;
+  float ms_rdo = 0, ms_tot = 0;
+  cudaEventElapsedTime(&ms_rdo, c.ev[1], c.ev[2]);
+  cudaEventElapsedTime(&ms_tot, c.ev[0], c.ev[3]);
+  {
+    std::lock_guard<std::mutex> lk(g_stat_mu);
+    g_ms_rdo += ms_rdo; g_ms_total += ms_tot;
+  }
+  return 0;
+}
+
+void pack_jobs(std::vector<FrameJob *> &jobs) {
+  const auto t0 = std::chrono::steady_clock::now();
+  parallel_for(jobs.size(), [&](size_t i) {
+    FrameJob &j = *jobs[i];
+    B200Records rec;
+    memset(&rec, 0, sizeof(rec));
+    rec.mi = j.h_mi;
+    for (int p = 0; p < j.f.planes; p++) { rec.eob[p] = j.h_eob[p]; rec.coef[p] = j.h_coef[p]; }
+    uint8_t *out = nullptr;
+    size_t len = 0;
+    j.status = b200av1_pack_frame(&j.f, &rec, &out, &len);
+    if (j.status == 0) { j.obu.assign(out, out + len); free(out); }
+  });
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  std::lock_guard<std::mutex> lk(g_stat_mu);
+  g_ms_pack += ms;
+}
+
+struct ImageWork {
+  // input
+  const uint8_t *pixels = nullptr; bool on_device = false; int channels = 4;
+  size_t w = 0, h = 0, stride = 0;
+  std::vector<uint8_t> cleaned;     // alpha-cleaned copy (host) if any
+  // raw planes input (encode_raw_planes_*)
+  bool raw = false; std::vector<uint16_t> raw_planes[3], raw_alpha; bool raw_has_alpha = false;
+  int raw_range = 1, raw_mc = 6;
+  // work
+  uint8_t *d_in = nullptr; int *d_flag = nullptr;
+  int depth = 10;
+  bool use_alpha = false;
+  FrameJob color, alpha;
+  uint16_t *d_alpha_src = nullptr;
+  int status = 0;
+};
+
+int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b200avif_image *outs, int *status) {
+  if (b200avif_device_count() <= 0)
+    return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
+  std::unique_ptr<Context> ctx;
+  if (int e = acquire_context(enc.device, ctx)) return e;
+  Context &c = *ctx;
+  struct Release { std::unique_ptr<Context> &c; ~Release() { release_context(c); } } rel{ctx};
+  const int depth = enc.output_depth == 8 ? 8 : 10;
+  const int mc = enc.color_model == B200AVIF_COLOR_YCBCR ? B200AVIF_MC_BT601 : B200AVIF_MC_IDENTITY;
+
+  // ---- host-side alpha pre-clean (av1encoder.rs:277-299)
+  for (ImageWork &im : imgs) {
+    im.depth = depth;
+    if (im.raw || im.channels != 4 || im.on_device) continue;
+    if (enc.alpha_color_mode == B200AVIF_ALPHA_UNASSOCIATED_CLEAN) {
+      im.cleaned.resize(im.w * im.h * 4);
+      if (b200_blurred_dirty_alpha(im.pixels, im.w, im.h, im.stride, im.cleaned.data())) { im.pixels = im.cleaned.data(); im.stride = im.w; }
+      else im.cleaned.clear();
+    } else if (enc.alpha_color_mode == B200AVIF_ALPHA_PREMULTIPLIED) {
+      im.cleaned.resize(im.w * im.h * 4);
+      b200_premultiplied_branch(im.pixels, im.w, im.h, im.stride, im.cleaned.data());
+      im.pixels = im.cleaned.data(); im.stride = im.w;
+    }
+  }
+  // ---- frame descriptions + arena sizing
+  size_t dev_bytes = 1 << 20, pin_bytes = 1 << 20;
+  for (ImageWork &im : imgs) {
+    const int cmc = im.raw ? im.raw_mc : mc;
+    const int range = im.raw ? im.raw_range : 1;
+    if (int e = configure_frame(&im.color.f, im.w, im.h, depth, false, enc.quantizer, enc.speed, enc.threads, range, true, cmc)) { im.status = e; continue; }
+    if (int e = configure_frame(&im.alpha.f, im.w, im.h, depth, true, enc.alpha_quantizer, enc.speed, enc.threads, 1, false, 2)) { im.status = e; continue; }
+    dev_bytes += job_dev_bytes(im.color, true) + job_dev_bytes(im.alpha, true);
+    pin_bytes += job_pin_bytes(im.color) + job_pin_bytes(im.alpha);
+    const size_t in_bytes = im.raw ? (im.w * im.h * 2 * 4) : (im.stride * im.h * im.channels);
+    dev_bytes += align256(in_bytes) + 512;
+    if (!im.on_device) pin_bytes += align256(in_bytes) + 512;
+  }
+  if (c.dev.reserve(dev_bytes) || c.pin.reserve(pin_bytes)) return B200AVIF_ENCODING_ERROR;
+  c.dev.reset(); c.pin.reset();
+  CU(cudaEventRecord(c.ev[0], c.stream));
+  // ---- upload + convert
+  uint64_t h2d = 0;
+  int *h_flags = c.pin.take<int>(imgs.size());
+  int *d_flags = c.dev.take<int>(imgs.size());
+  CU(cudaMemsetAsync(d_flags, 0, imgs.size() * sizeof(int), c.stream));
+  for (size_t i = 0; i < imgs.size(); i++) {
+    ImageWork &im = imgs[i];
+    if (im.status) continue;
+    job_take(im.color, c.dev, c.pin, true);
+    job_take(im.alpha, c.dev, c.pin, true);
+    const int cw = im.color.f.mi_cols * 4, ch = im.color.f.mi_rows * 4;
+    if (im.raw) {
+      for (int p = 0; p < 3; p++) {
+        uint16_t *stage = c.pin.take<uint16_t>(im.w * im.h);
+        memcpy(stage, im.raw_planes[p].data(), im.w * im.h * 2);
+        uint16_t *d = c.dev.take<uint16_t>(im.w * im.h);
+        CU(cudaMemcpyAsync(d, stage, im.w * im.h * 2, cudaMemcpyHostToDevice, c.stream));
+        if (int e = b200_pad_plane_launch(d, (int)im.w, (int)im.h, (int)im.w, im.color.d_src[p], cw, ch, c.stream)) return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
+        g_launches++; h2d += im.w * im.h * 2;
+      }
+      if (im.raw_has_alpha) {
+        uint16_t *stage = c.pin.take<uint16_t>(im.w * im.h);
+        memcpy(stage, im.raw_alpha.data(), im.w * im.h * 2);
+        uint16_t *d = c.dev.take<uint16_t>(im.w * im.h);
+        CU(cudaMemcpyAsync(d, stage, im.w * im.h * 2, cudaMemcpyHostToDevice, c.stream));
+        if (int e = b200_pad_plane_launch(d, (int)im.w, (int)im.h, (int)im.w, im.alpha.d_src[0], cw, ch, c.stream)) return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
+        g_launches++; h2d += im.w * im.h * 2;
+      }
+      continue;
+    }
+    const uint8_t *d_in;
+    if (im.on_device) d_in = im.pixels;
+    else {
+      const size_t bytes = (im.stride * (im.h - 1) + im.w) * im.channels;
+      uint8_t *stage = c.pin.take<uint8_t>(bytes);
+      memcpy(stage, im.pixels, bytes);
+      uint8_t *d = c.dev.take<uint8_t>(bytes + 16);
+      CU(cudaMemcpyAsync(d, stage, bytes, cudaMemcpyHostToDevice, c.stream));
+      h2d += bytes;
+      d_in = d;
+    }
+    if (int e = b200_convert_launch(d_in, im.channels, (int)im.w, (int)im.h, (int)im.stride, cw, ch, depth, enc.color_model,
+                                    im.color.d_src[0], im.color.d_src[1], im.color.d_src[2],
+                                    im.channels == 4 ? im.alpha.d_src[0] : nullptr, im.channels == 4 ? d_flags + i : nullptr, c.stream))
+      return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
+    g_launches++;
+  }
+  g_h2d += h2d;
+  CU(cudaMemcpyAsync(h_flags, d_flags, imgs.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  // ---- jobs
+  std::vector<FrameJob *> jobs;
+  for (size_t i = 0; i < imgs.size(); i++) {
+    ImageWork &im = imgs[i];
+    if (im.status) continue;
+    im.use_alpha = im.raw ? im.raw_has_alpha : (im.channels == 4 && h_flags[i] != 0);
+    jobs.push_back(&im.color);
+    if (im.use_alpha) jobs.push_back(&im.alpha);
+  }
+  if (!jobs.empty()) {
+    if (int e = run_rdo_and_fetch(c, jobs, c.dev, c.pin, false, nullptr)) return e;
+    pack_jobs(jobs);
+  }
+  // ---- mux
+  const auto t0 = std::chrono::steady_clock::now();
+  int first_err = 0;
+  for (size_t i = 0; i < imgs.size(); i++) {
+    ImageWork &im = imgs[i];
+    memset(&outs[i], 0, sizeof(outs[i]));
+    if (!im.status && (im.color.status || (im.use_alpha && im.alpha.status))) im.status = B200AVIF_ENCODING_ERROR;
+    if (!im.status) {
+      B200AvifMuxInput mi;
+      memset(&mi, 0, sizeof(mi));
+      mi.color = im.color.obu.data(); mi.color_len = im.color.obu.size();
+      if (im.use_alpha) { mi.alpha = im.alpha.obu.data(); mi.alpha_len = im.alpha.obu.size(); }
+      if (!enc.exif.empty()) { mi.exif = enc.exif.data(); mi.exif_len = enc.exif.size(); }
+      mi.width = (uint32_t)im.w; mi.height = (uint32_t)im.h; mi.depth = depth;
+      mi.matrix_coefficients = im.raw ? im.raw_mc : mc;
+      mi.premultiplied_alpha = enc.premultiplied_alpha;
+      mi.color_level_idx = b200av1_seq_level_idx(&im.color.f);
+      mi.alpha_level_idx = b200av1_seq_level_idx(&im.alpha.f);
+      if (b200avif_mux(&mi, &outs[i].avif_file, &outs[i].avif_len) != 0) im.status = B200AVIF_ENCODING_ERROR;
+      outs[i].color_byte_size = im.color.obu.size();
+      outs[i].alpha_byte_size = im.use_alpha ? im.alpha.obu.size() : 0;
+    }
+    if (status) status[i] = im.status;
+    if (im.status && !first_err) first_err = im.status;
+  }
+  {
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::lock_guard<std::mutex> lk(g_stat_mu);
+    g_ms_pack += ms;
+  }
+  return first_err;
+}
+
+bool valid_mc(int mc) {
+  return mc == 0 || mc == 1 || mc == 2 || mc == 6 || mc == 8 || mc == 9 || mc == 10;
+}
+
+template <typename P>
+int encode_raw(const b200avif_encoder *enc, size_t w, size_t h, const P *planes, size_t n_px, const P *alpha, size_t n_alpha,
+               int range, int mc, int depth, b200avif_image *out) {
+  if (!enc || !out || !planes || w == 0 || h == 0) return fail(B200AVIF_INVALID_ARGUMENT, "null/zero argument");
+  if (!valid_mc(mc)) return fail(B200AVIF_UNSUPPORTED, "matrix coefficients");   // av1encoder.rs:468
+  if (n_px < w * h || (alpha && n_alpha < w * h)) return fail(B200AVIF_TOO_FEW_PIXELS, "Provided buffer is smaller than width * height");
+  std::vector<ImageWork> imgs(1);
+  ImageWork &im = imgs[0];
+  im.raw = true; im.w = w; im.h = h; im.raw_range = range; im.raw_mc = mc;
+  for (int p = 0; p < 3; p++) {
+    im.raw_planes[p].resize(w * h);
+    for (size_t i = 0; i < w * h; i++) im.raw_planes[p][i] = planes[i * 3 + p];
+  }
+  if (alpha) { im.raw_has_alpha = true; im.raw_alpha.assign(alpha, alpha + w * h); }
+  b200avif_encoder e2 = *enc;
+  e2.output_depth = depth;
+  return encode_images(e2, imgs, out, nullptr);
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+b200avif_encoder *b200avif_encoder_new(void) {
+  b200avif_encoder *e = new b200avif_encoder();
+  e->quantizer = b200_quality_to_quantizer(80.f);          // av1encoder.rs:88-102
+  e->alpha_quantizer = b200_quality_to_quantizer(80.f);
+  e->speed = 5;
+  e->output_depth = 0;
+  e->premultiplied_alpha = false;
+  e->color_model = B200AVIF_COLOR_YCBCR;
+  e->threads = 0;
+  e->alpha_color_mode = B200AVIF_ALPHA_UNASSOCIATED_CLEAN;
+  e->device = -1;
+  return e;
+}
+b200avif_encoder *b200avif_encoder_clone(const b200avif_encoder *enc) { return enc ? new b200avif_encoder(*enc) : nullptr; }
+void b200avif_encoder_free(b200avif_encoder *enc) { delete enc; }
+
+int b200avif_encoder_with_quality(b200avif_encoder *enc, float q) {
+  if (!enc || !(q >= 1.f && q <= 100.f)) return fail(B200AVIF_INVALID_ARGUMENT, "quality must be in 1..=100");
+  enc->quantizer = b200_quality_to_quantizer(q);
+  return 0;
+}
+int b200avif_encoder_with_alpha_quality(b200avif_encoder *enc, float q) {
+  if (!enc || !(q >= 1.f && q <= 100.f)) return fail(B200AVIF_INVALID_ARGUMENT, "alpha quality must be in 1..=100");
+  enc->alpha_quantizer = b200_quality_to_quantizer(q);
+  return 0;
+}
+int b200avif_encoder_with_speed(b200avif_encoder *enc, uint8_t s) {
+  if (!enc || s < 1 || s > 10) return fail(B200AVIF_INVALID_ARGUMENT, "speed must be in 1..=10");
+  enc->speed = s;
+  return 0;
+}
+int b200avif_encoder_with_bit_depth(b200avif_encoder *enc, int d) {
+  if (!enc || (d != 0 && d != 8 && d != 10)) return fail(B200AVIF_INVALID_ARGUMENT, "bit depth must be 0 (auto), 8 or 10");
+  enc->output_depth = d;
+  return 0;
+}
+int b200avif_encoder_with_internal_color_model(b200avif_encoder *enc, int m) {
+  if (!enc || (m != 0 && m != 1)) return fail(B200AVIF_INVALID_ARGUMENT, "unknown color model");
+  enc->color_model = m;
+  return 0;
+}
+int b200avif_encoder_with_alpha_color_mode(b200avif_encoder *enc, int m) {
+  if (!enc || m < 0 || m > 2) return fail(B200AVIF_INVALID_ARGUMENT, "unknown alpha color mode");
+  enc->alpha_color_mode = m;
+  enc->premultiplied_alpha = m == B200AVIF_ALPHA_PREMULTIPLIED;   // av1encoder.rs:200-203
+  return 0;
+}
+int b200avif_encoder_with_num_threads(b200avif_encoder *enc, size_t n) {
+  if (!enc) return fail(B200AVIF_INVALID_ARGUMENT, "null encoder");
+  enc->threads = n;
+  return 0;
+}
+int b200avif_encoder_set_exif(b200avif_encoder *enc, const uint8_t *exif, size_t len) {
+  if (!enc || (!exif && len)) return fail(B200AVIF_INVALID_ARGUMENT, "null exif");
+  enc->exif.assign(exif, exif + len);
+  return 0;
+}
+int b200avif_encoder_set_device(b200avif_encoder *enc, int dev) {
+  if (!enc) return fail(B200AVIF_INVALID_ARGUMENT, "null encoder");
+  enc->device = dev;
+  return 0;
+}
+
+int b200avif_encode_rgba_batch(const b200avif_encoder *enc, const b200avif_input *in, size_t n, b200avif_image *out, int *status) {
+  if (!enc || !in || !out) return fail(B200AVIF_INVALID_ARGUMENT, "null argument");
+  if (n == 0) return 0;
+  std::vector<ImageWork> imgs(n);
+  for (size_t i = 0; i < n; i++) {
+    ImageWork &im = imgs[i];
+    im.pixels = in[i].pixels; im.on_device = in[i].on_device != 0; im.channels = in[i].channels;
+    im.w = in[i].width; im.h = in[i].height; im.stride = in[i].stride_px ? in[i].stride_px : in[i].width;
+    if (!im.pixels || im.w == 0 || im.h == 0 || (im.channels != 3 && im.channels != 4) || im.stride < im.w) im.status = B200AVIF_INVALID_ARGUMENT;
+    if (im.w > 65536 || im.h > 65536) im.status = B200AVIF_UNSUPPORTED;
+  }
+  return encode_images(*enc, imgs, out, status);
+}
+
+int b200avif_encode_rgba(const b200avif_encoder *enc, const uint8_t *rgba, size_t w, size_t h, size_t stride_px, b200avif_image *out) {
+  b200avif_input in{rgba, w, h, stride_px, 4, 0};
+  int st = 0;
+  const int r = b200avif_encode_rgba_batch(enc, &in, 1, out, &st);
+  return r ? r : st;
+}
+int b200avif_encode_rgb(const b200avif_encoder *enc, const uint8_t *rgb, size_t w, size_t h, size_t stride_px, b200avif_image *out) {
+  b200avif_input in{rgb, w, h, stride_px, 3, 0};
+  int st = 0;
+  const int r = b200avif_encode_rgba_batch(enc, &in, 1, out, &st);
+  return r ? r : st;
+}
+int b200avif_encode_raw_planes_8_bit(const b200avif_encoder *enc, size_t w, size_t h, const uint8_t *planes, size_t n_px,
+                                     const uint8_t *alpha, size_t n_alpha, int range, int mc, b200avif_image *out) {
+  return encode_raw<uint8_t>(enc, w, h, planes, n_px, alpha, n_alpha, range, mc, 8, out);
+}
+int b200avif_encode_raw_planes_10_bit(const b200avif_encoder *enc, size_t w, size_t h, const uint16_t *planes, size_t n_px,
+                                      const uint16_t *alpha, size_t n_alpha, int range, int mc, b200avif_image *out) {
+  return encode_raw<uint16_t>(enc, w, h, planes, n_px, alpha, n_alpha, range, mc, 10, out);
+}
+
+void b200avif_image_free(b200avif_image *img) {
+  if (img && img->avif_file) { free(img->avif_file); img->avif_file = nullptr; img->avif_len = 0; }
+}
+const char *b200avif_last_error_message(void) { return g_err.c_str(); }
+uint8_t b200avif_quality_to_quantizer(float q) { return b200_quality_to_quantizer(q); }
+
+int b200avif_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+void b200avif_get_stats(b200avif_stats *out) {
+  if (!out) return;
+  std::lock_guard<std::mutex> lk(g_stat_mu);
+  out->kernel_launches = g_launches; out->h2d_bytes = g_h2d; out->d2h_bytes = g_d2h;
+  out->gpu_ms_rdo = g_ms_rdo; out->gpu_ms_total = g_ms_total; out->host_ms_pack = g_ms_pack;
+}
+
+// ---- narrowest seam ------------------------------------------------------------------------------
+int b200av1_encode_planes(const b200av1_config *cfg, const uint16_t *const planes[3], const size_t strides[3], uint8_t **obu, size_t *obu_len) {
+  if (!cfg || !planes || !strides || !obu || !obu_len) return fail(B200AVIF_INVALID_ARGUMENT, "null argument");
+  if (b200avif_device_count() <= 0) return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
+  FrameJob job;
+  if (int e = configure_frame(&job.f, cfg->width, cfg->height, cfg->bit_depth, cfg->monochrome != 0, cfg->quantizer, cfg->speed,
+                              cfg->threads, cfg->pixel_range, cfg->has_color_description != 0, cfg->matrix_coefficients)) return e;
+  std::unique_ptr<Context> ctx;
+  if (int e = acquire_context(-1, ctx)) return e;
+  Context &c = *ctx;
+  struct Release { std::unique_ptr<Context> &c; ~Release() { release_context(c); } } rel{ctx};
+  const size_t w = cfg->width, h = cfg->height;
+  if (c.dev.reserve(job_dev_bytes(job, true) + job.f.planes * align256(w * h * 2) + (1 << 20)) ||
+      c.pin.reserve(job_pin_bytes(job) + job.f.planes * align256(w * h * 2) + (1 << 20))) return B200AVIF_ENCODING_ERROR;
+  c.dev.reset(); c.pin.reset();
+  CU(cudaEventRecord(c.ev[0], c.stream));
+  job_take(job, c.dev, c.pin, true);
+  const int cw = job.f.mi_cols * 4, ch = job.f.mi_rows * 4;
+  for (int p = 0; p < job.f.planes; p++) {
+    uint16_t *stage = c.pin.take<uint16_t>(w * h);
+    for (size_t y = 0; y < h; y++) memcpy(stage + y * w, planes[p] + y * strides[p], w * 2);
+    uint16_t *d = c.dev.take<uint16_t>(w * h);
+    CU(cudaMemcpyAsync(d, stage, w * h * 2, cudaMemcpyHostToDevice, c.stream));
+    if (int e = b200_pad_plane_launch(d, (int)w, (int)h, (int)w, job.d_src[p], cw, ch, c.stream)) return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
+    g_launches++; g_h2d += w * h * 2;
+  }
+  std::vector<FrameJob *> jobs{&job};
+  if (int e = run_rdo_and_fetch(c, jobs, c.dev, c.pin, false, nullptr)) return e;
+  pack_jobs(jobs);
+  if (job.status) return fail(B200AVIF_ENCODING_ERROR, "packer failed");
+  *obu = (uint8_t *)malloc(job.obu.size());
+  memcpy(*obu, job.obu.data(), job.obu.size());
+  *obu_len = job.obu.size();
+  return 0;
+}
+
+// ---- test seam: colour conversion kernel on host pixels -> coded planes (mi-aligned, edge replicated)
+int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h, size_t stride_px, int depth, int color_model,
+                        uint16_t *const planes[4] /* y,u,v,alpha (alpha may be NULL) */, int *any_alpha) {
+  if (!pixels || !planes || w == 0 || h == 0) return fail(B200AVIF_INVALID_ARGUMENT, "null argument");
+  if (b200avif_device_count() <= 0) return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
+  std::unique_ptr<Context> ctx;
+  if (int e = acquire_context(-1, ctx)) return e;
+  Context &c = *ctx;
+  struct Release { std::unique_ptr<Context> &c; ~Release() { release_context(c); } } rel{ctx};
+  const int cw = 8 * (int)((w + 7) >> 3), ch = 8 * (int)((h + 7) >> 3);
+  const size_t npx = (size_t)cw * ch, in_bytes = (stride_px * (h - 1) + w) * channels;
+  if (c.dev.reserve(4 * align256(npx * 2) + align256(in_bytes) + 8192) || c.pin.reserve(4096)) return B200AVIF_ENCODING_ERROR;
+  c.dev.reset(); c.pin.reset();
+  uint8_t *d_in = c.dev.take<uint8_t>(in_bytes + 16);
+  uint16_t *d_p[4];
+  for (int p = 0; p < 4; p++) d_p[p] = c.dev.take<uint16_t>(npx);
+  int *d_flag = c.dev.take<int>(1);
+  CU(cudaMemcpyAsync(d_in, pixels, in_bytes, cudaMemcpyHostToDevice, c.stream));
+  CU(cudaMemsetAsync(d_flag, 0, sizeof(int), c.stream));
+  if (int e = b200_convert_launch(d_in, channels, (int)w, (int)h, (int)stride_px, cw, ch, depth, color_model, d_p[0], d_p[1], d_p[2],
+                                  channels == 4 ? d_p[3] : nullptr, channels == 4 ? d_flag : nullptr, c.stream))
+    return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
+  g_launches++;
+  for (int p = 0; p < 4; p++)
+    if (planes[p] && (p < 3 || channels == 4)) CU(cudaMemcpyAsync(planes[p], d_p[p], npx * 2, cudaMemcpyDeviceToHost, c.stream));
+  int flag = 0;
+  CU(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  if (any_alpha) *any_alpha = flag;
+  return 0;
+}
+
+// ---- test seam: run the device hot path on caller-provided coded planes and frame description -----
+int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi, uint16_t *const eob[3], int16_t *const coef[3],
+                    uint16_t *const rec[3]) {
+  if (!f || !src || !mi) return fail(B200AVIF_INVALID_ARGUMENT, "null argument");
+  if (b200avif_device_count() <= 0) return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
+  FrameJob job;
+  job.f = *f;
+  std::unique_ptr<Context> ctx;
+  if (int e = acquire_context(-1, ctx)) return e;
+  Context &c = *ctx;
+  struct Release { std::unique_ptr<Context> &c; ~Release() { release_context(c); } } rel{ctx};
+  if (c.dev.reserve(job_dev_bytes(job, true) + (1 << 20)) || c.pin.reserve(job_pin_bytes(job) + (1 << 20))) return B200AVIF_ENCODING_ERROR;
+  c.dev.reset(); c.pin.reset();
+  CU(cudaEventRecord(c.ev[0], c.stream));
+  job_take(job, c.dev, c.pin, true);
+  for (int p = 0; p < job.f.planes; p++) CU(cudaMemcpyAsync(job.d_src[p], src[p], job.n_px() * 2, cudaMemcpyHostToDevice, c.stream));
+  std::vector<FrameJob *> jobs{&job};
+  std::vector<std::vector<uint16_t>> recs;
+  if (int e = run_rdo_and_fetch(c, jobs, c.dev, c.pin, true, &recs)) return e;
+  memcpy(mi, job.h_mi, job.n_mi() * sizeof(B200Mi));
+  for (int p = 0; p < job.f.planes; p++) {
+    if (eob && eob[p]) memcpy(eob[p], job.h_eob[p], job.n_mi() * 2);
+    if (coef && coef[p]) memcpy(coef[p], job.h_coef[p], job.n_coef() * 2);
+    if (rec && rec[p]) memcpy(rec[p], recs[p].data(), job.n_px() * 2);
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -625,6 +625,8 @@ void write_frame_header(const B200Frame &f, BitWriter &b) {
 
 }  // namespace
 
+extern "C" int b200av1_seq_level_idx(const B200Frame *f) { return level_for(*f); }
+
 extern "C" int b200av1_pack_frame(const B200Frame *fp, const B200Records *rec, uint8_t **out, size_t *out_len) {
   const B200Frame &f = *fp;
   if (!out || !out_len || f.base_q_idx < 1 || f.base_q_idx > 255) return 4;

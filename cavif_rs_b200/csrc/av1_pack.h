@@ -25,6 +25,9 @@ int b200av1_frame_setup(B200Frame *f, int width, int height, int bit_depth, int 
 // Static RDO rate model for the quantiser class of base_q_idx.
 void b200av1_build_rate_tables(int base_q_idx, B200RateTables *t);
 
+// seq_level_idx_0 written into the sequence header (needed by the av1C box).
+int b200av1_seq_level_idx(const B200Frame *f);
+
 // Pack one frame.  *out is malloc()ed; caller frees with free().  Returns 0 on success.
 int b200av1_pack_frame(const B200Frame *f, const B200Records *rec, uint8_t **out, size_t *out_len);
 

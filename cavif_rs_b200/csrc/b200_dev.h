@@ -1,0 +1,25 @@
+// Internal device-side entry points (kernel launchers) and the test seam of the hot path.
+#ifndef B200_DEV_H_
+#define B200_DEV_H_
+#include <stddef.h>
+#include <stdint.h>
+#include "records.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+int b200_convert_launch(const uint8_t *d_in, int channels, int width, int height, int stride_px, int cw, int ch, int depth,
+                        int color_model, uint16_t *p0, uint16_t *p1, uint16_t *p2, uint16_t *alpha, int *any_alpha,
+                        void *stream);
+int b200_pad_plane_launch(const uint16_t *d_in, int width, int height, int in_stride, uint16_t *d_out, int cw, int ch,
+                          void *stream);
+// Test seam: colour-conversion kernel.  planes[p]: (8*ceil(h/8)) x (8*ceil(w/8)) uint16 each.
+int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h, size_t stride_px, int depth, int color_model,
+                        uint16_t *const planes[4], int *any_alpha);
+// Test seam: run the device hot path (RDO) on host-provided CODED planes (mi_rows*4 x mi_cols*4 uint16,
+// stride mi_cols*4) and return the block records and the reconstruction.  Synchronous.
+int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi, uint16_t *const eob[3],
+                    int16_t *const coef[3], uint16_t *const rec[3]);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,74 @@
+"""Decoder conformance: oracle hot path -> product symbol packer -> dav1d 1.5.3.
+The decoded planes must equal the encoder's own reconstruction SAMPLE-EXACTLY; this pins predictors,
+dequantisation, inverse transforms, reconstruction, every CDF/context and the range coder."""
+import numpy as np
+import pytest
+import dav1d
+import harness as H
+
+pytestmark = pytest.mark.skipif(not dav1d.available(), reason="dav1d not available")
+
+
+def roundtrip(w, h, depth=8, planes=3, q=121, tiles=1, ymask=0x1fff, uvmask=0x1fff, txmask=0x1f, pmin=4, pmax=16, rdo_tx=1,
+              seed=0, reduced=1):
+    f = H.frame_setup(w, h, depth, planes, q, tiles)
+    f.y_mode_mask = ymask; f.uv_mode_mask = uvmask; f.tx_type_mask = txmask
+    f.partition_min = pmin; f.partition_max = pmax; f.rdo_tx_decision = rdo_tx; f.reduced_tx_set = reduced
+    rt = H.rate_tables(f.base_q_idx)
+    img = H.synth_image(w, h, seed)
+    pl = [img[..., c].astype(np.uint16) * (4 if depth == 10 else 1) for c in range(planes)]
+    rec = H.oracle_encode(f, rt, H.pad_planes(pl, f))
+    obu = H.pack(f, rec)
+    dec, bpc, layout = dav1d.decode(obu)
+    assert bpc == depth and layout == (3 if planes == 3 else 0)
+    for p in range(planes):
+        assert np.array_equal(dec[p], rec.rec[p][:h, :w]), "plane %d differs from the encoder reconstruction" % p
+    mse = np.mean((rec.rec[0][:h, :w].astype(float) - pl[0]) ** 2)
+    return len(obu), 10 * np.log10(((1 << depth) - 1) ** 2 / max(mse, 1e-9))
+
+
+@pytest.mark.parametrize("mode", range(13))
+def test_each_luma_predictor(mode):
+    roundtrip(136, 104, ymask=1 << mode, uvmask=1, pmin=16, rdo_tx=0, txmask=1)
+
+
+@pytest.mark.parametrize("mode", range(13))
+def test_each_chroma_predictor_and_derived_tx_type(mode):
+    roundtrip(72, 56, ymask=1, uvmask=1 << mode, pmin=8, pmax=8, rdo_tx=0, txmask=1)
+
+
+@pytest.mark.parametrize("size", [4, 8, 16, 32])
+@pytest.mark.parametrize("tx", range(5))
+def test_each_transform_type_and_size(size, tx):
+    if size == 32 and tx != 0:
+        pytest.skip("32x32 intra blocks are DCT only")
+    roundtrip(96, 64, txmask=1 << tx, pmin=size, pmax=size, rdo_tx=0)
+
+
+@pytest.mark.parametrize("w,h", [(8, 8), (16, 300), (1000, 24), (129, 101), (128, 85), (72, 40), (200, 136)])
+def test_frame_edges_and_forced_splits(w, h):
+    roundtrip(w, h)
+
+
+@pytest.mark.parametrize("depth,planes", [(8, 3), (10, 3), (8, 1), (10, 1)])
+def test_full_search_depth_and_monochrome(depth, planes):
+    size, psnr = roundtrip(300, 200, depth=depth, planes=planes, tiles=4)
+    assert psnr > 30
+
+
+def test_many_tiles_and_quantisers():
+    roundtrip(640, 360, depth=10, tiles=12)
+    roundtrip(256, 256, q=200, pmax=32)
+    roundtrip(256, 192, q=20)
+    roundtrip(256, 192, q=255)
+    roundtrip(256, 192, q=1, pmin=8)
+
+
+def test_full_tx_set_signalling():
+    roundtrip(136, 104, reduced=0)
+
+
+def test_rate_increases_with_quality():
+    s_lo, p_lo = roundtrip(256, 192, q=180)
+    s_hi, p_hi = roundtrip(256, 192, q=60)
+    assert s_hi > s_lo and p_hi > p_lo

@@ -1,0 +1,64 @@
+"""Kernel logic check without a GPU: rdo.cu compiled as host C++ on the test-only CUDA emulator
+(tests/emu/cuda_emu.h: one fibre per CUDA thread) must reproduce the oracle's records and
+reconstruction bit-exactly.  The same comparison runs against the real kernel in test_gpu_parity.py."""
+import ctypes, os, subprocess
+import numpy as np
+import pytest
+import harness as H
+
+
+class RdoJob(ctypes.Structure):
+    _fields_ = [("frame", H.B200Frame), ("rate", ctypes.c_void_p), ("src", ctypes.c_void_p * 3), ("rec", ctypes.c_void_p * 3),
+                ("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3), ("decoded", ctypes.c_void_p)]
+
+
+class TileRef(ctypes.Structure):
+    _fields_ = [("job", ctypes.c_int32), ("tile_row", ctypes.c_int16), ("tile_col", ctypes.c_int16)]
+
+
+def emu_lib():
+    out = os.path.join(H.ROOT, "build", "libemu.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    src = [os.path.join(H.ROOT, p) for p in ("tests/emu/emu_main.cpp", "tests/emu/cuda_emu.h", "cavif_rs_b200/csrc/rdo.cu")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in src):
+        r = subprocess.run(["g++", "-O1", "-std=c++17", "-DB200_EMU", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-Itests/emu",
+                            "-Icavif_rs_b200/csrc", "-o", out, "tests/emu/emu_main.cpp"], cwd=H.ROOT, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+    return ctypes.CDLL(out)
+
+
+def compare(ref, out, planes):
+    for p in range(planes):
+        assert np.array_equal(ref.rec[p], out.rec[p]), "reconstruction plane %d" % p
+        assert np.array_equal(ref.eob[p], out.eob[p]), "eob plane %d" % p
+        assert np.array_equal(ref.coef[p], out.coef[p]), "coefficients plane %d" % p
+    assert np.array_equal(ref.mi, out.mi), "mode info"
+
+
+@pytest.mark.parametrize("w,h,depth,planes,tiles,kw", [
+    (64, 48, 8, 3, 1, {}),
+    (40, 72, 10, 1, 2, dict(partition_min=8, rdo_tx_decision=0)),
+])
+def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
+    E = emu_lib()
+    f = H.frame_setup(w, h, depth, planes, 121, tiles)
+    for k, v in kw.items():
+        setattr(f, k, v)
+    rt = H.rate_tables(f.base_q_idx)
+    img = H.synth_image(w, h, 3)
+    src = H.pad_planes([img[..., c].astype(np.uint16) * (4 if depth == 10 else 1) for c in range(planes)], f)
+    ref = H.oracle_encode(f, rt, src)
+    out = H.Records(f)
+    dec = np.zeros(f.mi_rows * f.mi_cols, np.uint8)
+    job = RdoJob(); job.frame = f; job.rate = rt.ctypes.data
+    src3 = list(src) + [src[0]] * (3 - len(src))
+    for p in range(3):
+        job.src[p] = src3[p].ctypes.data; job.rec[p] = out.rec[p].ctypes.data
+        job.eob[p] = out.eob[p].ctypes.data; job.coef[p] = out.coef[p].ctypes.data
+    job.mi = out.mi.ctypes.data; job.decoded = dec.ctypes.data
+    nt = f.tile_cols * f.tile_rows
+    trs = (TileRef * nt)()
+    for i in range(nt):
+        trs[i].job = 0; trs[i].tile_row = i // f.tile_cols; trs[i].tile_col = i % f.tile_cols
+    E.b200_rdo_launch_emu(ctypes.byref(job), trs, nt)
+    compare(ref, out, planes)
