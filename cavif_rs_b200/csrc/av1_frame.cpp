@@ -77,7 +77,27 @@ extern "C" int b200av1_frame_setup(B200Frame *f, int width, int height, int bit_
   f->partition_min = 4; f->partition_max = 16;
   f->rdo_tx_decision = 1;
   f->y_mode_mask = 0x1fff; f->uv_mode_mask = 0x1fff; f->tx_type_mask = 0x1f;
-  f->cdef_damping = 3;
+  // In-loop filter strengths: closed-form picks from the quantiser (encoder freedom; the filters themselves
+  // are normative).  Deblock level: libaom's "pick from q" fit; CDEF: one frame-wide strength pair.
+  {
+    const int q = f->ac_q;
+    int lvl = bit_depth == 8 ? (int)(((int64_t)q * 17563 - 421574 + (1 << 17)) >> 18)
+                             : (int)(((int64_t)q * 20723 + 4060632 + (1 << 19)) >> 20);
+    lvl = std::min(std::max(lvl, 0), 63);
+    f->lf_level[0] = f->lf_level[1] = f->lf_level[2] = f->lf_level[3] = lvl;
+    f->lf_sharpness = 0;
+    const int q8 = q >> (bit_depth - 8);
+    // CDEF: four candidate strength pairs (cdef_bits = 2) scaled from the quantiser; index 0 = off.  The
+    // per-superblock index is chosen on the device by squared error against the source (cdef_search).
+    const int yp = std::min(std::max((q8 * 7 + 512) >> 10, 1), 15);
+    const int up = std::min(std::max((q8 * 7 + 1024) >> 11, 1), 15);
+    f->cdef_damping = 3 + (q8 >= 128) + (q8 >= 512);
+    f->cdef_bits = 2;
+    const int ypri[4] = {0, yp, std::min(2 * yp, 15), std::min(3 * yp + 1, 15)}, ysec[4] = {0, 0, 1, 2};
+    const int upri[4] = {0, up, std::min(2 * up, 15), std::min(3 * up + 1, 15)}, usec[4] = {0, 0, 1, 1};
+    for (int i = 0; i < 4; i++) { f->cdef_y_strength[i] = ypri[i] * 4 + ysec[i]; f->cdef_uv_strength[i] = upri[i] * 4 + usec[i]; }
+    f->enable_cdef = 1;
+  }
   f->color_description_present = 0; f->color_primaries = 2; f->transfer_characteristics = 2;
   f->matrix_coefficients = 2; f->full_range = 1;
   return 0;

@@ -48,7 +48,8 @@ def configure(w, h, depth, planes, quantizer, speed, threads=None):
     f.partition_max = min(tw.partition_max, 16)
     f.partition_min = min(tw.partition_min, f.partition_max)
     f.fine_directional_intra = tw.fine_directional_intra
-    f.enable_cdef = 0; f.enable_restoration = 0
+    f.enable_cdef = 1 if tw.cdef else 0
+    f.enable_restoration = 0
     return f
 
 
@@ -70,7 +71,9 @@ def encode_frame(planes, w, h, depth, quantizer, speed, threads=None, color=True
     f.full_range = 1
     if color:
         f.color_description_present = 1; f.color_primaries = 1; f.transfer_characteristics = 13; f.matrix_coefficients = mc
-    rec = H.oracle_encode(f, H.rate_tables(f.base_q_idx), H.pad_planes(planes, f))
+    src = H.pad_planes(planes, f)
+    rec = H.oracle_encode(f, H.rate_tables(f.base_q_idx), src)
+    rec.final, rec.deblocked = H.oracle_filters(f, rec, src)      # also fills rec.cdef_idx
     return H.pack(f, rec), rec, f
 
 

@@ -41,7 +41,27 @@ def oracle():
     global _oracle
     if _oracle is None:
         _run(["make", "-s", "oracle"])
-        _oracle = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+        L = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+        V, I, Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+        # NB: without argtypes ctypes passes Python ints as 32-bit C ints and truncates pointers.
+        L.orc_encode_frame.argtypes = [V, V, V, V, V, V, V]
+        L.orc_deblock_frame.argtypes = [V, V, V]
+        L.orc_cdef_frame.argtypes = [V, V, V, V, V]
+        L.orc_cdef_search_frame.argtypes = [V, V, V, V, V, V]
+        L.orc_convert_image.argtypes = [V, I, Z, Z, Z, I, I, V, V, V, V]
+        L.orc_any_alpha.argtypes = [V, Z, Z, Z]
+        L.orc_blurred_dirty_alpha.argtypes = [V, Z, Z, Z, V]
+        L.orc_premultiplied_branch.argtypes = [V, Z, Z, Z, V]
+        L.orc_fwd_txfm2d.argtypes = [V, I, V, I, I]
+        L.orc_inv_txfm2d_add.argtypes = [V, V, I, I, I, I]
+        L.orc_pixel_planes.argtypes = [ctypes.c_uint8] * 3 + [I, I, V]
+        L.orc_premultiplied_minmax.argtypes = [ctypes.c_uint8, ctypes.c_uint8, V]
+        L.orc_speed_tweaks_from_my_preset.argtypes = [I, I, V]
+        L.orc_quality_to_quantizer.restype = ctypes.c_uint8
+        L.orc_quality_to_quantizer.argtypes = [ctypes.c_float]
+        L.orc_tile_target.restype = Z
+        L.orc_tile_target.argtypes = [Z] * 4
+        _oracle = L
     return _oracle
 
 _host = None
@@ -55,6 +75,17 @@ def hostlib():
         _host.b200av1_build_rate_tables.argtypes = [ctypes.c_int, ctypes.c_void_p]
         _host.b200av1_pack_frame.argtypes = [ctypes.POINTER(B200Frame), ctypes.POINTER(B200Records),
                                              ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
+        V, I, Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+        _host.b200av1_rdo_run.argtypes = [V, V, V, V, V, V]
+        _host.b200av1_convert_run.argtypes = [V, I, Z, Z, Z, I, I, V, V]
+        _host.b200av1_seq_level_idx.argtypes = [V]
+        _host.b200avif_mux.argtypes = [V, V, V]
+        _host.b200_blurred_dirty_alpha.argtypes = [V, Z, Z, Z, V]
+        _host.b200_premultiplied_branch.argtypes = [V, Z, Z, Z, V]
+        _host.b200_speed_tweaks.argtypes = [I, I, V]
+        _host.b200avif_quality_to_quantizer.restype = ctypes.c_uint8
+        _host.b200avif_quality_to_quantizer.argtypes = [ctypes.c_float]
+        _host.b200avif_last_error_message.restype = ctypes.c_char_p
     return _host
 
 def frame_setup(w, h, depth=8, planes=3, quantizer=121, tiles=1):
@@ -108,6 +139,18 @@ def oracle_encode(f, rt, src):
                        ptr3(rec.eob), ptr3(rec.coef))
     return rec
 
+def oracle_filters(f, rec, src):
+    """In-loop filter stage of the oracle: deblock the reconstruction, search the CDEF strength index per
+    superblock against `src` (fills rec.cdef_idx) and apply it.  Returns (final planes, deblocked planes)."""
+    L = oracle()
+    deb = [r.copy() for r in rec.rec]
+    L.orc_deblock_frame(ctypes.byref(f), ptr3(deb), rec.mi.ctypes.data)
+    out = [np.zeros_like(r) for r in rec.rec]
+    src3 = list(src) + [src[0]] * (3 - len(src))
+    L.orc_cdef_search_frame(ctypes.byref(f), ptr3(deb), ptr3(src3), ptr3(out), rec.mi.ctypes.data, rec.cdef_idx.ctypes.data)
+    return out, deb
+
+
 def pack(f, rec):
     out = ctypes.c_void_p()
     n = ctypes.c_size_t()
@@ -115,7 +158,9 @@ def pack(f, rec):
     rc = hostlib().b200av1_pack_frame(ctypes.byref(f), ctypes.byref(cr), ctypes.byref(out), ctypes.byref(n))
     assert rc == 0, rc
     data = ctypes.string_at(out.value, n.value)
-    ctypes.CDLL(None).free(out)
+    libc = ctypes.CDLL(None)
+    libc.free.argtypes = [ctypes.c_void_p]
+    libc.free(out)
     return data
 
 def synth_image(w, h, seed=0, alpha=False):

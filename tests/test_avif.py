@@ -19,7 +19,9 @@ def encode_obu(planes, w, h, depth, q=100):
     f = H.frame_setup(w, h, depth, len(planes), q, 1)
     if len(planes) == 3:
         f.color_description_present = 1; f.color_primaries = 1; f.transfer_characteristics = 13; f.matrix_coefficients = 0
-    rec = H.oracle_encode(f, H.rate_tables(f.base_q_idx), H.pad_planes(planes, f))
+    src = H.pad_planes(planes, f)
+    rec = H.oracle_encode(f, H.rate_tables(f.base_q_idx), src)
+    rec.final, _ = H.oracle_filters(f, rec, src)
     return H.pack(f, rec), rec, f
 
 
@@ -38,7 +40,6 @@ def test_mux_is_parsed_by_libavif(with_alpha):
         mi.alpha = ctypes.addressof(ab); mi.alpha_len = len(al)
     mi.width = w; mi.height = h; mi.depth = 8; mi.matrix_coefficients = 0
     L = H.hostlib()
-    L.b200av1_seq_level_idx.argtypes = [ctypes.POINTER(H.B200Frame)]
     mi.color_level_idx = L.b200av1_seq_level_idx(ctypes.byref(f)); mi.alpha_level_idx = mi.color_level_idx
     out = ctypes.c_void_p(); n = ctypes.c_size_t()
     assert L.b200avif_mux(ctypes.byref(mi), ctypes.byref(out), ctypes.byref(n)) == 0
@@ -48,7 +49,7 @@ def test_mux_is_parsed_by_libavif(with_alpha):
     assert im.size == (w, h)
     assert im.mode == ("RGBA" if with_alpha else "RGB")
     arr = np.asarray(im.convert("RGBA" if with_alpha else "RGB"))
-    g, b, r = [rec.rec[p][:h, :w] for p in range(3)]
+    g, b, r = [rec.final[p][:h, :w] for p in range(3)]
     assert np.array_equal(arr[..., 0], r) and np.array_equal(arr[..., 1], g) and np.array_equal(arr[..., 2], b)
     if with_alpha:
-        assert np.array_equal(arr[..., 3], arec.rec[0][:h, :w])
+        assert np.array_equal(arr[..., 3], arec.final[0][:h, :w])

@@ -17,13 +17,17 @@ def roundtrip(w, h, depth=8, planes=3, q=121, tiles=1, ymask=0x1fff, uvmask=0x1f
     rt = H.rate_tables(f.base_q_idx)
     img = H.synth_image(w, h, seed)
     pl = [img[..., c].astype(np.uint16) * (4 if depth == 10 else 1) for c in range(planes)]
-    rec = H.oracle_encode(f, rt, H.pad_planes(pl, f))
+    src = H.pad_planes(pl, f)
+    rec = H.oracle_encode(f, rt, src)
+    final, deblocked = H.oracle_filters(f, rec, src)
     obu = H.pack(f, rec)
-    dec, bpc, layout = dav1d.decode(obu)
-    assert bpc == depth and layout == (3 if planes == 3 else 0)
-    for p in range(planes):
-        assert np.array_equal(dec[p], rec.rec[p][:h, :w]), "plane %d differs from the encoder reconstruction" % p
-    mse = np.mean((rec.rec[0][:h, :w].astype(float) - pl[0]) ** 2)
+    # three decodes: in-loop filters off / deblocking only / everything -> pins each stage separately
+    for flt, ref, what in ((0, rec.rec, "reconstruction"), (dav1d.INLOOP_DEBLOCK, deblocked, "deblocked"), (dav1d.INLOOP_ALL, final, "CDEF output")):
+        dec, bpc, layout = dav1d.decode(obu, flt)
+        assert bpc == depth and layout == (3 if planes == 3 else 0)
+        for p in range(planes):
+            assert np.array_equal(dec[p], ref[p][:h, :w]), "plane %d: dav1d differs from the encoder's %s" % (p, what)
+    mse = np.mean((final[0][:h, :w].astype(float) - pl[0]) ** 2)
     return len(obu), 10 * np.log10(((1 << depth) - 1) ** 2 / max(mse, 1e-9))
 
 
@@ -66,6 +70,25 @@ def test_many_tiles_and_quantisers():
 
 def test_full_tx_set_signalling():
     roundtrip(136, 104, reduced=0)
+
+
+@pytest.mark.parametrize("lf,cdef", [((20, 25, 15, 30), (15 * 4 + 3, 9 * 4 + 2, 5)), ((63, 40, 50, 10), (7 * 4 + 1, 3, 6)), ((0, 0, 0, 0), (2, 12, 3))])
+def test_forced_filter_strengths(lf, cdef):
+    """deblock levels / CDEF strengths far from the closed-form picks, 8 and 10 bit"""
+    for depth in (8, 10):
+        f = H.frame_setup(200, 136, depth, 3, 150, 2)
+        for i in range(4):
+            f.lf_level[i] = lf[i]
+        f.cdef_bits = 0; f.cdef_y_strength[0] = cdef[0]; f.cdef_uv_strength[0] = cdef[1]; f.cdef_damping = cdef[2]
+        img = H.synth_image(200, 136, 11)
+        src = H.pad_planes([img[..., c].astype(np.uint16) * (4 if depth == 10 else 1) for c in range(3)], f)
+        rec = H.oracle_encode(f, H.rate_tables(f.base_q_idx), src)
+        final, deb = H.oracle_filters(f, rec, src)
+        obu = H.pack(f, rec)
+        for flt, ref in ((dav1d.INLOOP_DEBLOCK, deb), (dav1d.INLOOP_ALL, final)):
+            dec, _, _ = dav1d.decode(obu, flt)
+            for p in range(3):
+                assert np.array_equal(dec[p], ref[p][:200 and 136, :200])
 
 
 def test_rate_increases_with_quality():

@@ -87,8 +87,6 @@ def test_dirty_alpha_product_matches_oracle(seed):
     img = H.synth_image(97, 61, seed, alpha=True)
     a = np.zeros_like(img); b = np.zeros_like(img)
     ra = L.orc_blurred_dirty_alpha(img.ctypes.data, 97, 61, 97, a.ctypes.data)
-    P.b200_blurred_dirty_alpha.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]
-    L.orc_blurred_dirty_alpha.argtypes = P.b200_blurred_dirty_alpha.argtypes
     ra = L.orc_blurred_dirty_alpha(img.ctypes.data, 97, 61, 97, a.ctypes.data)
     rb = P.b200_blurred_dirty_alpha(img.ctypes.data, 97, 61, 97, b.ctypes.data)
     assert ra == rb == 1 and np.array_equal(a, b)
@@ -97,8 +95,6 @@ def test_dirty_alpha_product_matches_oracle(seed):
     assert np.array_equal(a[opaque], img[opaque])            # opaque pixels untouched
     op = img.copy(); op[..., 3] = 255
     assert L.orc_blurred_dirty_alpha(op.ctypes.data, 97, 61, 97, a.ctypes.data) == 0   # None for opaque images
-    L.orc_premultiplied_branch.argtypes = P.b200_blurred_dirty_alpha.argtypes
-    P.b200_premultiplied_branch.argtypes = P.b200_blurred_dirty_alpha.argtypes
     L.orc_premultiplied_branch(img.ctypes.data, 97, 61, 97, a.ctypes.data)
     P.b200_premultiplied_branch(img.ctypes.data, 97, 61, 97, b.ctypes.data)
     assert np.array_equal(a, b)

@@ -50,8 +50,6 @@ def test_convert_kernel_bit_exact(depth, color_model):
                                (ctypes.c_void_p * 4)(*[d.ctypes.data for d in dev]), ctypes.byref(flag))
     assert rc == 0, L.b200avif_last_error_message()
     ref = [np.zeros((h, w), np.uint16) for _ in range(4)]
-    O.orc_convert_image.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
-                                    ctypes.c_int] + [ctypes.c_void_p] * 4
     O.orc_convert_image(buf.ctypes.data, 4, w, h, stride, color_model, depth, *[r.ctypes.data for r in ref])
     for p in range(4):
         assert np.array_equal(dev[p][:h, :w], ref[p]), "plane %d" % p
@@ -74,8 +72,6 @@ def test_convert_exhaustive_2_24_colours(depth):
                                (ctypes.c_void_p * 4)(*([d.ctypes.data for d in dev] + [None])), None)
     assert rc == 0, L.b200avif_last_error_message()
     ref = [np.zeros((4096, 4096), np.uint16) for _ in range(3)]
-    O.orc_convert_image.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
-                                    ctypes.c_int] + [ctypes.c_void_p] * 4
     O.orc_convert_image(img.ctypes.data, 3, 4096, 4096, 4096, 0, depth, ref[0].ctypes.data, ref[1].ctypes.data, ref[2].ctypes.data, None)
     for p in range(3):
         assert np.array_equal(dev[p], ref[p])
