@@ -148,6 +148,9 @@ struct FrameJob {
   uint16_t *d_eob[3] = {nullptr, nullptr, nullptr};
   int16_t *d_coef[3] = {nullptr, nullptr, nullptr};
   uint8_t *d_decoded = nullptr;
+  int8_t *d_cdef = nullptr;
+  uint16_t *d_fin[3] = {nullptr, nullptr, nullptr};   // only for the test seam
+  int8_t *h_cdef = nullptr;
   // pinned host
   B200Mi *h_mi = nullptr;
   uint16_t *h_eob[3] = {nullptr, nullptr, nullptr};
@@ -157,6 +160,7 @@ struct FrameJob {
   size_t n_mi() const { return (size_t)f.mi_rows * f.mi_cols; }
   size_t n_px() const { return n_mi() * 16; }
   size_t n_coef() const { return (size_t)f.sb_rows * f.sb_cols * B200_SB_COEFS; }
+  size_t n_sb() const { return (size_t)f.sb_rows * f.sb_cols; }
 };
 
 size_t job_dev_bytes(const FrameJob &j, bool own_src) {
@@ -167,12 +171,12 @@ size_t job_dev_bytes(const FrameJob &j, bool own_src) {
   b += align256(j.n_mi() * sizeof(B200Mi));
   b += P * align256(j.n_mi() * 2);
   b += P * align256(j.n_coef() * 2);
-  b += align256(j.n_mi());
+  b += align256(j.n_mi()) + align256(j.n_sb());
   return b + 4096;
 }
 size_t job_pin_bytes(const FrameJob &j) {
   const int P = j.f.planes;
-  return align256(j.n_mi() * sizeof(B200Mi)) + P * align256(j.n_mi() * 2) + P * align256(j.n_coef() * 2) + 4096;
+  return align256(j.n_mi() * sizeof(B200Mi)) + P * align256(j.n_mi() * 2) + P * align256(j.n_coef() * 2) + align256(j.n_sb()) + 4096;
 }
 void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
   const int P = j.f.planes;
@@ -186,6 +190,8 @@ void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
   }
   j.d_mi = dev.take<B200Mi>(j.n_mi());
   j.d_decoded = dev.take<uint8_t>(j.n_mi());
+  j.d_cdef = dev.take<int8_t>(j.n_sb());
+  j.h_cdef = pin.take<int8_t>(j.n_sb());
   j.h_mi = pin.take<B200Mi>(j.n_mi());
 }
 
@@ -206,8 +212,8 @@ int configure_frame(B200Frame *f, size_t w, size_t h, int depth, bool mono, int 
   f->partition_max = std::min(tw.partition_max, 16);
   f->partition_min = std::min(f->partition_min, f->partition_max);
   f->fine_directional_intra = tw.fine_directional_intra;
-  f->enable_cdef = 0;          // in-loop filter stages: not emitted yet (valid bitstream, filters off)
-  f->enable_restoration = 0;
+  if (!tw.cdef) f->enable_cdef = 0;   // ravif: cdef = low_quality && speed <= 9 (av1encoder.rs:590)
+  f->enable_restoration = 0;          // loop restoration (lrf flag, :589) is not implemented: valid stream, LR off
   f->full_range = full_range;
   f->color_description_present = has_cd ? 1 : 0;
   if (has_cd) { f->color_primaries = 1; f->transfer_characteristics = 13; f->matrix_coefficients = mc; }
@@ -230,7 +236,7 @@ int rate_tables_for(Context &c, int qidx, B200RateTables **out) {
 
 // Launch the RDO kernel for a set of jobs (device buffers ready, sources filled) and fetch records.
 int run_rdo_and_fetch(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin, bool fetch_rec,
-                      std::vector<std::vector<uint16_t>> *rec_out) {
+                      std::vector<std::vector<uint16_t>> *rec_out, std::vector<std::vector<uint16_t>> *pre_filter_rec = nullptr) {
   std::vector<B200RdoJob> hj(jobs.size());
   std::vector<B200TileRef> tiles;
   for (size_t i = 0; i < jobs.size(); i++) {
@@ -246,6 +252,8 @@ int run_rdo_and_fetch(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Are
       r.src[p] = j.d_src[q]; r.rec[p] = j.d_rec[q]; r.eob[p] = j.d_eob[q]; r.coef[p] = j.d_coef[q];
     }
     r.mi = j.d_mi; r.decoded = j.d_decoded;
+    r.cdef_idx = j.d_cdef;
+    for (int p = 0; p < 3; p++) r.fin[p] = j.d_fin[p < j.f.planes ? p : 0];
     for (int tr = 0; tr < j.f.tile_rows; tr++)
       for (int tc = 0; tc < j.f.tile_cols; tc++) tiles.push_back(B200TileRef{(int32_t)i, (int16_t)tr, (int16_t)tc});
     CU(cudaMemsetAsync(j.d_decoded, 0, j.n_mi(), c.stream));
@@ -259,11 +267,31 @@ int run_rdo_and_fetch(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Are
   if (le != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("RDO kernel launch failed: ") + cudaGetErrorString((cudaError_t)le));
   g_launches += 1;
   CU(cudaEventRecord(c.ev[2], c.stream));
+  if (pre_filter_rec) {   // test seam: reconstruction before the in-loop filters
+    pre_filter_rec->clear();
+    for (FrameJob *jp : jobs)
+      for (int p = 0; p < jp->f.planes; p++) {
+        pre_filter_rec->emplace_back(jp->n_px());
+        CU(cudaMemcpyAsync(pre_filter_rec->back().data(), jp->d_rec[p], jp->n_px() * 2, cudaMemcpyDeviceToHost, c.stream));
+      }
+    CU(cudaStreamSynchronize(c.stream));
+  }
+  {
+    int max_edges = 0, max_sb = 0;
+    for (FrameJob *jp : jobs) {
+      max_edges = std::max(max_edges, (int)(jp->n_mi() * 4 * jp->f.planes));
+      max_sb = std::max(max_sb, (int)jp->n_sb());
+    }
+    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_edges, max_sb, c.stream);
+    if (fe != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("filter kernel launch failed: ") + cudaGetErrorString((cudaError_t)fe));
+    g_launches += 3;
+  }
   uint64_t d2h = 0;
   for (FrameJob *jp : jobs) {
     FrameJob &j = *jp;
     CU(cudaMemcpyAsync(j.h_mi, j.d_mi, j.n_mi() * sizeof(B200Mi), cudaMemcpyDeviceToHost, c.stream));
-    d2h += j.n_mi() * sizeof(B200Mi);
+    CU(cudaMemcpyAsync(j.h_cdef, j.d_cdef, j.n_sb(), cudaMemcpyDeviceToHost, c.stream));
+    d2h += j.n_mi() * sizeof(B200Mi) + j.n_sb();
     for (int p = 0; p < j.f.planes; p++) {
       CU(cudaMemcpyAsync(j.h_eob[p], j.d_eob[p], j.n_mi() * 2, cudaMemcpyDeviceToHost, c.stream));
       CU(cudaMemcpyAsync(j.h_coef[p], j.d_coef[p], j.n_coef() * 2, cudaMemcpyDeviceToHost, c.stream));
@@ -298,6 +326,7 @@ void pack_jobs(std::vector<FrameJob *> &jobs) {
     B200Records rec;
     memset(&rec, 0, sizeof(rec));
     rec.mi = j.h_mi;
+    rec.cdef_idx = j.h_cdef;
     for (int p = 0; p < j.f.planes; p++) { rec.eob[p] = j.h_eob[p]; rec.coef[p] = j.h_coef[p]; }
     uint8_t *out = nullptr;
     size_t len = 0;
@@ -676,7 +705,7 @@ int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h,
 
 // ---- test seam: run the device hot path on caller-provided coded planes and frame description -----
 int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi, uint16_t *const eob[3], int16_t *const coef[3],
-                    uint16_t *const rec[3]) {
+                    uint16_t *const rec[3], uint16_t *const deblocked[3], uint16_t *const fin[3], int8_t *cdef_idx) {
   if (!f || !src || !mi) return fail(B200AVIF_INVALID_ARGUMENT, "null argument");
   if (b200avif_device_count() <= 0) return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
   FrameJob job;
@@ -685,19 +714,25 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
   if (int e = acquire_context(-1, ctx)) return e;
   Context &c = *ctx;
   struct Release { std::unique_ptr<Context> &c; ~Release() { release_context(c); } } rel{ctx};
-  if (c.dev.reserve(job_dev_bytes(job, true) + (1 << 20)) || c.pin.reserve(job_pin_bytes(job) + (1 << 20))) return B200AVIF_ENCODING_ERROR;
+  if (c.dev.reserve(job_dev_bytes(job, true) + 3 * align256(job.n_px() * 2) + (1 << 20)) || c.pin.reserve(job_pin_bytes(job) + (1 << 20))) return B200AVIF_ENCODING_ERROR;
   c.dev.reset(); c.pin.reset();
   CU(cudaEventRecord(c.ev[0], c.stream));
   job_take(job, c.dev, c.pin, true);
-  for (int p = 0; p < job.f.planes; p++) CU(cudaMemcpyAsync(job.d_src[p], src[p], job.n_px() * 2, cudaMemcpyHostToDevice, c.stream));
+  for (int p = 0; p < job.f.planes; p++) {
+    job.d_fin[p] = c.dev.take<uint16_t>(job.n_px());
+    CU(cudaMemcpyAsync(job.d_src[p], src[p], job.n_px() * 2, cudaMemcpyHostToDevice, c.stream));
+  }
   std::vector<FrameJob *> jobs{&job};
-  std::vector<std::vector<uint16_t>> recs;
-  if (int e = run_rdo_and_fetch(c, jobs, c.dev, c.pin, true, &recs)) return e;
+  std::vector<std::vector<uint16_t>> deb, pre;
+  if (int e = run_rdo_and_fetch(c, jobs, c.dev, c.pin, true, &deb, &pre)) return e;
   memcpy(mi, job.h_mi, job.n_mi() * sizeof(B200Mi));
+  if (cdef_idx) memcpy(cdef_idx, job.h_cdef, job.n_sb());
   for (int p = 0; p < job.f.planes; p++) {
     if (eob && eob[p]) memcpy(eob[p], job.h_eob[p], job.n_mi() * 2);
     if (coef && coef[p]) memcpy(coef[p], job.h_coef[p], job.n_coef() * 2);
-    if (rec && rec[p]) memcpy(rec[p], recs[p].data(), job.n_px() * 2);
+    if (rec && rec[p]) memcpy(rec[p], pre[p].data(), job.n_px() * 2);
+    if (deblocked && deblocked[p]) memcpy(deblocked[p], deb[p].data(), job.n_px() * 2);
+    if (fin && fin[p]) CU(cudaMemcpy(fin[p], job.d_fin[p], job.n_px() * 2, cudaMemcpyDeviceToHost));
   }
   return 0;
 }

@@ -15,10 +15,12 @@ int b200_pad_plane_launch(const uint16_t *d_in, int width, int height, int in_st
 // Test seam: colour-conversion kernel.  planes[p]: (8*ceil(h/8)) x (8*ceil(w/8)) uint16 each.
 int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h, size_t stride_px, int depth, int color_model,
                         uint16_t *const planes[4], int *any_alpha);
-// Test seam: run the device hot path (RDO) on host-provided CODED planes (mi_rows*4 x mi_cols*4 uint16,
-// stride mi_cols*4) and return the block records and the reconstruction.  Synchronous.
+// Test seam: run the device hot path (RDO kernel, then deblock + CDEF search) on host-provided CODED planes
+// (mi_rows*4 x mi_cols*4 uint16, stride mi_cols*4).  Returns the block records, the reconstruction before the
+// in-loop filters (rec), after deblocking (deblocked), after CDEF (fin) and the per-superblock CDEF index.
 int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi, uint16_t *const eob[3],
-                    int16_t *const coef[3], uint16_t *const rec[3]);
+                    int16_t *const coef[3], uint16_t *const rec[3], uint16_t *const deblocked[3], uint16_t *const fin[3],
+                    int8_t *cdef_idx);
 #ifdef __cplusplus
 }
 #endif

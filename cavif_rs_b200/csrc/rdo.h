@@ -18,6 +18,10 @@ typedef struct B200RdoJob {
   uint16_t *eob[3];
   int16_t *coef[3];
   uint8_t *decoded;       // mi_rows*mi_cols bytes, zero-initialised
+  // in-loop filter stage (filters.cu): rec is deblocked IN PLACE; cdef_idx receives the per-superblock
+  // strength index (-1: nothing coded in the superblock); fin (optional, may be NULL) receives the CDEF output.
+  int8_t *cdef_idx;       // sb_rows*sb_cols
+  uint16_t *fin[3];
 } B200RdoJob;
 
 typedef struct B200TileRef {
@@ -27,6 +31,8 @@ typedef struct B200TileRef {
 
 // Launch one CTA per tile on `stream` (cudaStream_t).  Returns a cudaError_t value.
 int b200_rdo_launch(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int n_tiles, void *stream);
+// Deblock (2 launches) + CDEF search (1 launch) for all jobs: grid.y = job.
+int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, void *stream);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,8 @@ import harness as H
 
 class RdoJob(ctypes.Structure):
     _fields_ = [("frame", H.B200Frame), ("rate", ctypes.c_void_p), ("src", ctypes.c_void_p * 3), ("rec", ctypes.c_void_p * 3),
-                ("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3), ("decoded", ctypes.c_void_p)]
+                ("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3), ("decoded", ctypes.c_void_p),
+                ("cdef_idx", ctypes.c_void_p), ("fin", ctypes.c_void_p * 3)]
 
 
 class TileRef(ctypes.Structure):
@@ -19,7 +20,8 @@ class TileRef(ctypes.Structure):
 def emu_lib():
     out = os.path.join(H.ROOT, "build", "libemu.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    src = [os.path.join(H.ROOT, p) for p in ("tests/emu/emu_main.cpp", "tests/emu/cuda_emu.h", "cavif_rs_b200/csrc/rdo.cu")]
+    src = [os.path.join(H.ROOT, p) for p in ("tests/emu/emu_main.cpp", "tests/emu/cuda_emu.h", "cavif_rs_b200/csrc/rdo.cu",
+                                             "cavif_rs_b200/csrc/filters.cu", "cavif_rs_b200/csrc/rdo.h", "cavif_rs_b200/csrc/records.h")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in src):
         r = subprocess.run(["g++", "-O1", "-std=c++17", "-DB200_EMU", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-Itests/emu",
                             "-Icavif_rs_b200/csrc", "-o", out, "tests/emu/emu_main.cpp"], cwd=H.ROOT, capture_output=True, text=True)
@@ -60,5 +62,18 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
     trs = (TileRef * nt)()
     for i in range(nt):
         trs[i].job = 0; trs[i].tile_row = i // f.tile_cols; trs[i].tile_col = i % f.tile_cols
+    fin = [np.zeros_like(r) for r in out.rec]
+    for p in range(3):
+        job.fin[p] = fin[p].ctypes.data
+    job.cdef_idx = out.cdef_idx.ctypes.data
+    E.b200_rdo_launch_emu.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    E.b200_filters_launch_emu.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     E.b200_rdo_launch_emu(ctypes.byref(job), trs, nt)
     compare(ref, out, planes)
+    # in-loop filter stage: deblock in place, CDEF strength search, CDEF output
+    ref_fin, ref_deb = H.oracle_filters(f, ref, src)
+    E.b200_filters_launch_emu(ctypes.byref(job), f.mi_rows * f.mi_cols * 4 * planes, f.sb_rows * f.sb_cols)
+    for p in range(planes):
+        assert np.array_equal(out.rec[p], ref_deb[p]), "deblocked plane %d" % p
+        assert np.array_equal(fin[p], ref_fin[p]), "CDEF output plane %d" % p
+    assert np.array_equal(out.cdef_idx, ref.cdef_idx), "cdef index"

@@ -20,8 +20,11 @@ def _dev():
 def device_rdo(f, src):
     L = _dev()
     out = H.Records(f)
+    out.deblocked = [np.zeros_like(r) for r in out.rec]
+    out.final = [np.zeros_like(r) for r in out.rec]
     src3 = list(src) + [src[0]] * (3 - len(src))
-    rc = L.b200av1_rdo_run(ctypes.byref(f), H.ptr3(src3), out.mi.ctypes.data, H.ptr3(out.eob), H.ptr3(out.coef), H.ptr3(out.rec))
+    rc = L.b200av1_rdo_run(ctypes.byref(f), H.ptr3(src3), out.mi.ctypes.data, H.ptr3(out.eob), H.ptr3(out.coef), H.ptr3(out.rec),
+                           H.ptr3(out.deblocked), H.ptr3(out.final), out.cdef_idx.ctypes.data)
     assert rc == 0, L.b200avif_last_error_message()
     return out
 
@@ -98,12 +101,17 @@ def test_rdo_kernel_matches_oracle_and_dav1d(w, h, depth, planes, q, tiles, kw):
     img = H.synth_image(w, h, w + h)
     src = H.pad_planes([img[..., c].astype(np.uint16) * (4 if depth == 10 else 1) for c in range(planes)], f)
     ref = H.oracle_encode(f, rt, src)
+    ref_fin, ref_deb = H.oracle_filters(f, ref, src)
     out = device_rdo(f, src)
     check_records(ref, out, planes)
-    obu = H.pack(f, out)
-    dec, bpc, _ = dav1d.decode(obu)
     for p in range(planes):
-        assert np.array_equal(dec[p], out.rec[p][:h, :w])
+        assert np.array_equal(out.deblocked[p], ref_deb[p]), "deblocked plane %d" % p
+        assert np.array_equal(out.final[p], ref_fin[p]), "CDEF output plane %d" % p
+    assert np.array_equal(out.cdef_idx, ref.cdef_idx)
+    obu = H.pack(f, out)
+    dec, bpc, _ = dav1d.decode(obu)     # independent decoder, all in-loop filters on
+    for p in range(planes):
+        assert np.array_equal(dec[p], out.final[p][:h, :w])
 
 
 def test_rdo_full_hd_frame_parity():
@@ -118,5 +126,9 @@ def test_rdo_full_hd_frame_parity():
     assert f.tile_cols * f.tile_rows >= 31
     src = H.pad_planes(planes, f)
     ref = H.oracle_encode(f, H.rate_tables(f.base_q_idx), src)
+    ref_fin, ref_deb = H.oracle_filters(f, ref, src)
     out = device_rdo(f, src)
     check_records(ref, out, 3)
+    for p in range(3):
+        assert np.array_equal(out.final[p], ref_fin[p])
+    assert np.array_equal(out.cdef_idx, ref.cdef_idx)
