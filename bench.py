@@ -157,8 +157,12 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--images", type=int, default=0, help="override the batch size (profiling only; not a bench value)")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.images > 0:
+        wl["n"] = args.images
+        wl["name"] += " [batch overridden to %d images: profiling run]" % args.images
     if args.impl == "reference":
         run_reference(args, wl)
         return

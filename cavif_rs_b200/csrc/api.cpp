@@ -721,6 +721,10 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
   for (int p = 0; p < job.f.planes; p++) {
     job.d_fin[p] = c.dev.take<uint16_t>(job.n_px());
     CU(cudaMemcpyAsync(job.d_src[p], src[p], job.n_px() * 2, cudaMemcpyHostToDevice, c.stream));
+    // test seam only: slots of blocks outside the frame are never written (and never read by the packer);
+    // zero them so that whole-buffer comparisons against the oracle are meaningful
+    CU(cudaMemsetAsync(job.d_coef[p], 0, job.n_coef() * 2, c.stream));
+    CU(cudaMemsetAsync(job.d_eob[p], 0, job.n_mi() * 2, c.stream));
   }
   std::vector<FrameJob *> jobs{&job};
   std::vector<std::vector<uint16_t>> deb, pre;

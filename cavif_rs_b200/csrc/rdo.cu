@@ -1,17 +1,24 @@
-// AV1 intra rate-distortion search on the device: one CTA per TILE (tiles are the unit with no
-// cross dependencies: contexts reset, no prediction across tile edges), superblocks in raster
-// order inside the CTA, one WARP per candidate (prediction mode / transform type trial):
-// predict -> residual -> forward transform -> quantise -> static-CDF rate -> dequantise ->
-// inverse transform + reconstruct -> SSE.  Transforms are integer butterflies held in
-// registers, one lane per row/column, with shared-memory staging between the two passes.
+// AV1 intra rate-distortion search on the device.
 //
-// Replaces rav1e's encode_tile / rdo_mode_decision / encode_tx_block [EXT: crates.io
-// rav1e 0.8.1], which the reference reaches only through encode_to_av1
-// (/root/reference/ravif/src/av1encoder.rs:749-771).  The bit-exact CPU restatement of THIS
-// file is oracle/av1_encode.c; tests/test_rdo_parity.py compares records and reconstruction.
+// Mapping (v2): ONE WARP PER TILE.  Tiles are the unit with no cross dependencies (entropy contexts
+// reset, no prediction across tile edges); inside a tile every block depends on its left/top
+// reconstruction, so a tile is a serial chain.  A batch of images gives thousands of tiles, i.e.
+// thousands of independent warps (64 x 1080p -> 2048 tiles -> ~14 resident warps per SM), and a
+// single-warp CTA needs no block-level barriers at all.  Inside the warp the 32 lanes are kept busy by
+// evaluating G = 32/N candidates of an NxN block at once ("lane group" g = lane / N owns one candidate,
+// lane l = lane % N owns column l / row l of its transform): residual, forward transform, quantiser,
+// static-CDF rate, dequantiser, inverse transform, reconstruction and SSE run for G candidates in
+// lock-step, with the 1-D butterflies held in registers and only the transpose going through shared
+// memory.  Candidates sharing a lane batch are ordered so that they run the same transform kernels
+// (same transform type, different prediction modes), which keeps the warp convergent.
 //
-// No tensor cores on purpose: the work is 4..16-point integer butterflies with normative
-// rounding at every stage (BASELINE.json north_star).
+// Replaces rav1e's encode_tile / rdo_mode_decision / encode_tx_block [EXT: crates.io rav1e 0.8.1],
+// which the reference reaches only through encode_to_av1
+// (/root/reference/ravif/src/av1encoder.rs:749-771).  The bit-exact CPU restatement of THIS file is
+// oracle/av1_encode.c; tests/test_gpu_parity.py compares records and reconstruction.
+//
+// No tensor cores on purpose: the work is 4..16-point integer butterflies with normative rounding at
+// every stage (BASELINE.json north_star).
 #ifdef B200_EMU
 #include "cuda_emu.h"
 #else
@@ -31,12 +38,17 @@
 
 namespace {
 
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;
+constexpr int kThreads = 32;
 constexpr int EOFF = 16;          // edge arrays: index -1 .. 2n-1 stored at EOFF-1 ..
 constexpr int kEdge = EOFF + 34;  // n <= 16
 constexpr unsigned FULL = 0xffffffffu;
+constexpr long long kInf = 0x7fffffffffffffffll;
 
+// inverse scan tables (4x4 | 8x8 | 16x16) in GLOBAL memory: indexed per lane (divergent), which the constant
+// cache would serialise; __ldg keeps them L1 resident.
+__device__ const uint8_t dv_iscan_g[336] = {
+#include "iscan_init.inc"
+};
 __constant__ const uint8_t dv_sm_weights[4 + 8 + 16] = {255, 149, 85, 64, 255, 197, 146, 105, 73, 50, 37, 32,
                                                         255, 225, 196, 170, 145, 123, 102, 84, 68, 54, 43, 33, 26, 20, 17, 16};
 __constant__ const uint8_t dv_intra_mode_context[13] = {0, 1, 2, 3, 4, 4, 4, 4, 3, 0, 1, 2, 0};
@@ -44,35 +56,29 @@ __constant__ const uint8_t dv_tx_types[5] = {TX_DCT_DCT, TX_ADST_DCT, TX_DCT_ADS
 __constant__ const uint8_t dv_bw4[22] = {1, 1, 2, 2, 2, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 1, 4, 2, 8, 4, 16};
 __constant__ const uint8_t dv_bh4[22] = {1, 2, 1, 2, 4, 2, 4, 8, 4, 8, 16, 8, 16, 32, 16, 32, 4, 1, 8, 2, 16, 4};
 
-struct WarpScratch {
-  uint16_t pred[256];
-  int32_t buf[16 * 17];        // transform staging, row stride n + 1
-  int16_t qc[2][256];          // two result sets (a warp may run two candidates)
-  uint16_t recon[2][256];
-  uint8_t lev[20 * 20];        // padded |level| map for the rate contexts
-};
-
-struct Cand {
+template <int PX>
+struct CandT {
   long long cost;
   B200Mi mi;
   uint16_t eob[3];
-  int16_t qc[3][256];
-  uint16_t recon[3][256];
+  int16_t qc[3][PX];
+  uint16_t recon[3][PX];
 };
+typedef CandT<256> Cand;      // up to 16x16
+typedef CandT<64> Cand8;      // an 8x8 candidate parked while its four 4x4 children are tried
 
 struct Shared {
-  WarpScratch ws[kWarps];
-  Cand cur, held8, held16;
   uint16_t src[3][256];
   uint16_t above[3][kEdge], left[3][kEdge];
-  uint8_t scan[336], iscan[336];
-  uint32_t satd[2][13];
-  // per-task results of the full trials
-  long long taskJ[10];
+  uint16_t pred[512];          // luma: predictions of the two ranked modes; chroma: up to four (mode rank, plane) predictions
+  int32_t buf[32 * 17];        // G groups x N rows x (N+1): transform transpose staging
+  alignas(16) uint8_t lev[800];   // per group (N+4)^2 padded |level| map (rate contexts)
+  int16_t qc[512];             // per group n*n quantised levels in scan order
+  uint16_t rec[512];           // per group n*n reconstruction
+  Cand cur, held16;
+  Cand8 held8;
   uint32_t taskD[4], taskR[4];
-  uint16_t taskEob[10], taskEobC[4];
-  int sel[8];                  // small broadcast area
-  int have_above, have_left;
+  uint16_t taskE[4];
 };
 
 struct TileCtx {
@@ -89,7 +95,6 @@ struct TileCtx {
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 __device__ __forceinline__ int txs_of(int n) { return n == 4 ? 0 : n == 8 ? 1 : n == 16 ? 2 : 3; }
 __device__ __forceinline__ int scan_base(int n) { return n == 4 ? 0 : n == 8 ? 16 : 80; }
 __device__ __forceinline__ int ilog2_dev(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
@@ -98,13 +103,27 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
   for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
   return v;
 }
-__device__ __forceinline__ int warp_max(int v) {
-  for (int m = 16; m > 0; m >>= 1) v = max(v, __shfl_xor_sync(FULL, v, m));
+template <int N> __device__ __forceinline__ uint32_t group_sum(uint32_t v) {
+#pragma unroll
+  for (int m = N / 2; m > 0; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
   return v;
 }
+template <int N> __device__ __forceinline__ int group_max(int v) {
+#pragma unroll
+  for (int m = N / 2; m > 0; m >>= 1) v = max(v, __shfl_xor_sync(FULL, v, m));
+  return v;
+}
+// lexicographic minimum of (J, idx) over the warp
+__device__ __forceinline__ void warp_argmin(long long &J, int &idx) {
+  for (int m = 16; m > 0; m >>= 1) {
+    const long long oj = __shfl_xor_sync(FULL, J, m);
+    const int oi = __shfl_xor_sync(FULL, idx, m);
+    if (oj < J || (oj == J && oi < idx)) { J = oj; idx = oi; }
+  }
+}
 
-// ---- edges (AV1 spec 7.11.2, intra edge filter disabled) : executed by one warp ------------
-__device__ void build_edges(const TileCtx &t, Shared &sh, int plane, int x, int y, int n) {
+// ---- edges (AV1 spec 7.11.2, intra edge filter disabled) ----------------------------------------
+__device__ void build_edges(const TileCtx &t, Shared &sh, int plane, int x, int y, int n, int &ha_out, int &hl_out) {
   const B200Frame *f = t.f;
   const uint16_t *r = t.rec[plane];
   const int st = t.stride, lane = lane_id();
@@ -141,103 +160,92 @@ __device__ void build_edges(const TileCtx &t, Shared &sh, int plane, int x, int 
     else if (hl) tl = r[y * st + x - 1];
     else tl = (uint16_t)base;
     A[-1] = tl; L[-1] = tl;
-    if (plane == 0) { sh.have_above = ha; sh.have_left = hl; }
   }
+  ha_out = ha; hl_out = hl;
 }
 
-// ---- intra predictors (AV1 spec 7.11.2.x), warp-cooperative over the n*n pixels -------------
-__device__ void predict_intra(int mode, int n, const uint16_t *above, const uint16_t *left, int ha, int hl, int bd,
-                              uint16_t *pred) {
-  const uint16_t *A = above + EOFF, *L = left + EOFF;
-  const int lane = lane_id(), n2 = n * n, lg = n == 4 ? 2 : n == 8 ? 3 : 4;
-  if (mode == DC_PRED) {
-    int v;
-    if (ha && hl) { int s = 0; for (int i = 0; i < n; i++) s += A[i] + L[i]; v = (s + n) / (2 * n); }
-    else if (hl) { int s = 0; for (int i = 0; i < n; i++) s += L[i]; v = (s + (n >> 1)) / n; }
-    else if (ha) { int s = 0; for (int i = 0; i < n; i++) s += A[i]; v = (s + (n >> 1)) / n; }
-    else v = 1 << (bd - 1);
-    for (int p = lane; p < n2; p += 32) pred[p] = (uint16_t)v;
-    return;
-  }
-  if (mode == PAETH_PRED) {
-    const int tl = A[-1];
-    for (int p = lane; p < n2; p += 32) {
-      const int i = p >> lg, j = p & (n - 1);
-      const int b = A[j] + L[i] - tl;
+// ---- intra predictors (AV1 spec 7.11.2.x): value of pixel (i, j) of an n x n block ------------------
+__device__ __forceinline__ int dc_value(int n, const uint16_t *A, const uint16_t *L, int ha, int hl, int bd) {
+  if (ha && hl) { int s = 0; for (int i = 0; i < n; i++) s += A[i] + L[i]; return (s + n) / (2 * n); }
+  if (hl) { int s = 0; for (int i = 0; i < n; i++) s += L[i]; return (s + (n >> 1)) / n; }
+  if (ha) { int s = 0; for (int i = 0; i < n; i++) s += A[i]; return (s + (n >> 1)) / n; }
+  return 1 << (bd - 1);
+}
+// A, L point at index 0 of the edge arrays (index -1 valid).  dc: precomputed DC value (used for DC_PRED only).
+__device__ __forceinline__ int pred_px(int mode, int n, int i, int j, const uint16_t *A, const uint16_t *L, int dc) {
+  switch (mode) {
+    case DC_PRED: return dc;
+    case V_PRED: return A[j];
+    case H_PRED: return L[i];
+    case PAETH_PRED: {
+      const int tl = A[-1], b = A[j] + L[i] - tl;
       const int pl = abs(b - L[i]), pt = abs(b - A[j]), ptl = abs(b - tl);
-      pred[p] = (pl <= pt && pl <= ptl) ? L[i] : (pt <= ptl ? A[j] : (uint16_t)tl);
+      return (pl <= pt && pl <= ptl) ? L[i] : (pt <= ptl ? A[j] : tl);
     }
-    return;
-  }
-  if (mode >= SMOOTH_PRED && mode <= SMOOTH_H_PRED) {
-    const uint8_t *w = dv_sm_weights + (n == 4 ? 0 : n == 8 ? 4 : 12);
-    for (int p = lane; p < n2; p += 32) {
-      const int i = p >> lg, j = p & (n - 1);
-      int v;
-      if (mode == SMOOTH_PRED) v = (w[i] * A[j] + (256 - w[i]) * L[n - 1] + w[j] * L[i] + (256 - w[j]) * A[n - 1] + 256) >> 9;
-      else if (mode == SMOOTH_V_PRED) v = (w[i] * A[j] + (256 - w[i]) * L[n - 1] + 128) >> 8;
-      else v = (w[j] * L[i] + (256 - w[j]) * A[n - 1] + 128) >> 8;
-      pred[p] = (uint16_t)v;
+    case SMOOTH_PRED: {
+      const uint8_t *w = dv_sm_weights + (n == 4 ? 0 : n == 8 ? 4 : 12);
+      return (w[i] * A[j] + (256 - w[i]) * L[n - 1] + w[j] * L[i] + (256 - w[j]) * A[n - 1] + 256) >> 9;
     }
-    return;
+    case SMOOTH_V_PRED: {
+      const uint8_t *w = dv_sm_weights + (n == 4 ? 0 : n == 8 ? 4 : 12);
+      return (w[i] * A[j] + (256 - w[i]) * L[n - 1] + 128) >> 8;
+    }
+    case SMOOTH_H_PRED: {
+      const uint8_t *w = dv_sm_weights + (n == 4 ? 0 : n == 8 ? 4 : 12);
+      return (w[j] * L[i] + (256 - w[j]) * A[n - 1] + 128) >> 8;
+    }
+    default: break;
   }
   const int p_angle = dv_mode_to_angle[mode];
-  if (p_angle == 90) { for (int p = lane; p < n2; p += 32) pred[p] = A[p & (n - 1)]; return; }
-  if (p_angle == 180) { for (int p = lane; p < n2; p += 32) pred[p] = L[p >> lg]; return; }
   if (p_angle < 90) {
     const int dx = dv_dr_intra_derivative[p_angle], max_base = 2 * n - 1;
-    for (int p = lane; p < n2; p += 32) {
-      const int i = p >> lg, j = p & (n - 1);
-      const int idx = (i + 1) * dx, base = (idx >> 6) + j, shift = (idx >> 1) & 31;
-      pred[p] = base < max_base ? (uint16_t)((A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5) : A[max_base];
-    }
-  } else if (p_angle < 180) {
-    const int dx = dv_dr_intra_derivative[180 - p_angle], dy = dv_dr_intra_derivative[p_angle - 90];
-    for (int p = lane; p < n2; p += 32) {
-      const int i = p >> lg, j = p & (n - 1);
-      int idx = (j << 6) - (i + 1) * dx, base = idx >> 6;
-      if (base >= -1) {
-        const int shift = (idx >> 1) & 31;
-        pred[p] = (uint16_t)((A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5);
-      } else {
-        idx = (i << 6) - (j + 1) * dy; base = idx >> 6;
-        const int shift = (idx >> 1) & 31;
-        pred[p] = (uint16_t)((L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5);
-      }
-    }
-  } else {
-    const int dy = dv_dr_intra_derivative[270 - p_angle], max_base = 2 * n - 1;
-    for (int p = lane; p < n2; p += 32) {
-      const int i = p >> lg, j = p & (n - 1);
-      const int idx = (j + 1) * dy, base = (idx >> 6) + i, shift = (idx >> 1) & 31;
-      pred[p] = base < max_base ? (uint16_t)((L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5) : L[max_base];
-    }
+    const int idx = (i + 1) * dx, base = (idx >> 6) + j, shift = (idx >> 1) & 31;
+    return base < max_base ? (A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5 : A[max_base];
   }
+  if (p_angle < 180) {
+    const int dx = dv_dr_intra_derivative[180 - p_angle], dy = dv_dr_intra_derivative[p_angle - 90];
+    int idx = (j << 6) - (i + 1) * dx, base = idx >> 6;
+    if (base >= -1) {
+      const int shift = (idx >> 1) & 31;
+      return (A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5;
+    }
+    idx = (i << 6) - (j + 1) * dy; base = idx >> 6;
+    const int shift = (idx >> 1) & 31;
+    return (L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5;
+  }
+  const int dy = dv_dr_intra_derivative[270 - p_angle], max_base = 2 * n - 1;
+  const int idx = (j + 1) * dy, base = (idx >> 6) + i, shift = (idx >> 1) & 31;
+  return base < max_base ? (L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5 : L[max_base];
 }
 
-// sum of |4x4 Hadamard| over the 4x4 sub-blocks; one lane per sub-block, warp reduced
-__device__ uint32_t satd4_warp(const uint16_t *src, const uint16_t *pred, int n) {
-  const int nb = n >> 2, lane = lane_id();
-  uint32_t total = 0;
-  for (int s = lane; s < nb * nb; s += 32) {
-    const int by = (s / nb) * 4, bx = (s % nb) * 4;
-    int d[16], t[16];
+// whole-block prediction into shared memory, pixels spread over the 32 lanes
+__device__ void predict_block(int mode, int n, const uint16_t *above, const uint16_t *left, int ha, int hl, int bd, uint16_t *dst) {
+  const uint16_t *A = above + EOFF, *L = left + EOFF;
+  const int lg = n == 4 ? 2 : n == 8 ? 3 : 4;
+  const int dc = mode == DC_PRED ? dc_value(n, A, L, ha, hl, bd) : 0;
+  for (int p = lane_id(); p < n * n; p += 32) dst[p] = (uint16_t)pred_px(mode, n, p >> lg, p & (n - 1), A, L, dc);
+}
+
+// SATD (sum of |4x4 Hadamard|) of one 4x4 sub-block for `mode`, prediction computed on the fly
+__device__ __forceinline__ uint32_t satd_subblock(int mode, int n, int by, int bx, const uint16_t *src, const uint16_t *A,
+                                                  const uint16_t *L, int dc) {
+  int d[16], tt[16];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+  for (int i = 0; i < 4; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) d[i * 4 + j] = (int)src[(by + i) * n + bx + j] - (int)pred[(by + i) * n + bx + j];
+    for (int j = 0; j < 4; j++) d[i * 4 + j] = (int)src[(by + i) * n + bx + j] - pred_px(mode, n, by + i, bx + j, A, L, dc);
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int a = d[i * 4] + d[i * 4 + 1], b = d[i * 4] - d[i * 4 + 1], c = d[i * 4 + 2] + d[i * 4 + 3], e = d[i * 4 + 2] - d[i * 4 + 3];
-      t[i * 4] = a + c; t[i * 4 + 1] = b + e; t[i * 4 + 2] = a - c; t[i * 4 + 3] = b - e;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int a = t[j] + t[4 + j], b = t[j] - t[4 + j], c = t[8 + j] + t[12 + j], e = t[8 + j] - t[12 + j];
-      total += (uint32_t)(abs(a + c) + abs(b + e) + abs(a - c) + abs(b - e));
-    }
+  for (int i = 0; i < 4; i++) {
+    const int a = d[i * 4] + d[i * 4 + 1], b = d[i * 4] - d[i * 4 + 1], c = d[i * 4 + 2] + d[i * 4 + 3], e = d[i * 4 + 2] - d[i * 4 + 3];
+    tt[i * 4] = a + c; tt[i * 4 + 1] = b + e; tt[i * 4 + 2] = a - c; tt[i * 4 + 3] = b - e;
   }
-  return warp_sum(total);
+  uint32_t total = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int a = tt[j] + tt[4 + j], b = tt[j] - tt[4 + j], c = tt[8 + j] + tt[12 + j], e = tt[8 + j] - tt[12 + j];
+    total += (uint32_t)(abs(a + c) + abs(b + e) + abs(a - c) + abs(b - e));
+  }
+  return total;
 }
 
 // ---- 1-D transforms on register arrays -----------------------------------------------------
@@ -309,149 +317,111 @@ __device__ __forceinline__ int32_t clamp_bits(int32_t v, int bits) {
   return v < mn ? mn : (v > mx ? mx : v);
 }
 
-// forward 2-D transform of (src - pred) into buf (row stride N+1), libaom av1_fwd_txfm2d design
+// ---- one lane batch: G = 32/N candidates of an N x N block evaluated in lock-step -------------------
+// Lane group g = lane / N, lane-in-group l = lane % N.  plane / src / pred / tx_type / y_mode may differ per group
+// (identical for the lanes of one group).  Results (eob, rate, sse) are returned to every lane of the group; the
+// group's quantised levels (scan order) and reconstruction stay in sh.qc / sh.rec at offset g*N*N.
+// Mirrors oracle/av1_encode.c trial_plane(): forward transform (libaom av1_fwd_txfm2d design), quantize(),
+// coef_rate(), AV1 spec 7.13.3 inverse transform + reconstruction, SSE.
 template <int N>
-__device__ void fwd_txfm2d_warp(const uint16_t *src, const uint16_t *pred, int32_t *buf, int tx_type) {
-  constexpr int S = N + 1;
+__device__ void trial_batch(const TileCtx &t, Shared &sh, int plane, const uint16_t *src, const uint16_t *pred, int tx_type,
+                            int y_mode, int &eob_out, uint32_t &rate_out, uint32_t &sse_out) {
+  constexpr int S = N + 1, N2 = N * N, LS = N + 4;
   constexpr int shift1 = N == 4 ? 0 : (N == 8 ? 1 : 2);   // -fwd_shift[1]
   constexpr int cos_col = 13, cos_row = N == 16 ? 12 : 13;
-  const int lane = lane_id();
-  int vert, horz;
-  tx_kernels(tx_type, vert, horz);
-  for (int p = lane; p < N * N; p += 32) {
-    const int r = p / N, c = p % N;
-    buf[r * S + c] = ((int)src[p] - (int)pred[p]) * 4;   // fwd_shift[0] = 2
-  }
-  __syncwarp();
-  if (lane < N) {
-    int32_t x[N], o[N];
-#pragma unroll
-    for (int r = 0; r < N; r++) x[r] = buf[r * S + lane];
-    fwd1d<N>(vert, x, o, cos_col);
-#pragma unroll
-    for (int r = 0; r < N; r++) buf[r * S + lane] = rshift_round(o[r], shift1);
-  }
-  __syncwarp();
-  if (lane < N) {
-    int32_t x[N], o[N];
-#pragma unroll
-    for (int c = 0; c < N; c++) x[c] = buf[lane * S + c];
-    fwd1d<N>(horz, x, o, cos_row);
-#pragma unroll
-    for (int c = 0; c < N; c++) buf[lane * S + c] = o[c];
-  }
-  __syncwarp();
-}
-
-// inverse 2-D transform (AV1 spec 7.13.3) of buf (dequantised, stride N+1) added to pred -> recon
-template <int N>
-__device__ void inv_txfm2d_add_warp(int32_t *buf, const uint16_t *pred, uint16_t *recon, int tx_type, int bd) {
-  constexpr int S = N + 1;
   constexpr int row_shift = N == 4 ? 0 : (N == 8 ? 1 : 2);
-  const int lane = lane_id();
-  int vert, horz;
-  tx_kernels(tx_type, vert, horz);
-  if (lane < N) {
-    int32_t x[N], o[N];
-#pragma unroll
-    for (int c = 0; c < N; c++) x[c] = clamp_bits(buf[lane * S + c], bd + 8);
-    inv1d<N>(horz, x, o);
-#pragma unroll
-    for (int c = 0; c < N; c++) buf[lane * S + c] = rshift_round(o[c], row_shift);
-  }
-  __syncwarp();
-  if (lane < N) {
-    const int col_clamp = bd + 6 > 16 ? bd + 6 : 16;
-    const int mx = (1 << bd) - 1;
-    int32_t x[N], o[N];
-#pragma unroll
-    for (int r = 0; r < N; r++) x[r] = clamp_bits(buf[r * S + lane], col_clamp);
-    inv1d<N>(vert, x, o);
-#pragma unroll
-    for (int r = 0; r < N; r++) {
-      const int v = (int)pred[r * N + lane] + rshift_round(o[r], 4);
-      recon[r * N + lane] = (uint16_t)(v < 0 ? 0 : (v > mx ? mx : v));
-    }
-  }
-  __syncwarp();
-}
-
-// Full trial of one plane by one warp.  src/pred: n*n in shared memory.  Results: qc (scan order),
-// recon, *eob, returns SSE, *rate.  Mirrors oracle/av1_encode.c trial_plane().
-template <int N>
-__device__ uint32_t trial_plane_warp(const TileCtx &t, Shared &sh, WarpScratch &w, int set, int plane, const uint16_t *src,
-                                     int tx_type, int y_mode, int *eob_out, uint32_t *rate_out) {
-  constexpr int S = N + 1, N2 = N * N, LS = N + 4;
   const B200Frame *f = t.f;
   const B200RateTables *rt = t.rt;
-  const int lane = lane_id();
-  const uint8_t *iscan = sh.iscan + scan_base(N);
-  const uint16_t *pred = w.pred;
-  int16_t *qc = w.qc[set];
-  fwd_txfm2d_warp<N>(src, pred, w.buf, tx_type);
-  // ---- quantise / dequantise (oracle quantize())
-  for (int p = lane; p < LS * LS; p += 32) w.lev[p] = 0;
-  __syncwarp();
-  int eob = 0;
-  const int dc_q = f->dc_q, ac_q = f->ac_q;
-  for (int pos = lane; pos < N2; pos += 32) {
-    const int r = pos / N, c = pos % N;
-    const int q = pos == 0 ? dc_q : ac_q;
-    const int off = pos == 0 ? (q * 109) >> 8 : (q * 98) >> 8;
-    const int32_t cf = w.buf[r * S + c];
-    const uint32_t a = (uint32_t)(cf < 0 ? -cf : cf);
-    uint32_t lv = (a + (uint32_t)off) / (uint32_t)q;
-    if (lv > 32767) lv = 32767;
-    const int32_t dqa = (int32_t)(((unsigned long long)lv * (uint32_t)q) & 0xFFFFFF);
-    const int si = iscan[pos];
-    qc[si] = (int16_t)(cf < 0 ? -(int)lv : (int)lv);
-    w.buf[r * S + c] = cf < 0 ? -dqa : dqa;
-    w.lev[r * LS + c] = (uint8_t)(lv > 127 ? 127 : lv);
-    if (lv) eob = max(eob, si + 1);
+  const int lane = lane_id(), g = lane / N, l = lane % N;
+  int32_t *buf = sh.buf + g * N * S;
+  uint8_t *lev = sh.lev + g * LS * LS;
+  int16_t *qc = sh.qc + g * N2;
+  uint16_t *rec = sh.rec + g * N2;
+  const uint8_t *iscan = dv_iscan_g + scan_base(N);   // position -> scan index (global memory, L1 resident)
+  int vert, horz;
+  tx_kernels(tx_type, vert, horz);
+  const int bd = f->bit_depth;
+
+  // ---- forward: column l in registers (residual << 2), column transform, transpose through shared memory
+  {
+    int32_t x[N], o[N];
+#pragma unroll
+    for (int r = 0; r < N; r++) x[r] = ((int)src[r * N + l] - (int)pred[r * N + l]) * 4;
+    fwd1d<N>(vert, x, o, cos_col);
+#pragma unroll
+    for (int r = 0; r < N; r++) buf[r * S + l] = rshift_round(o[r], shift1);
   }
-  eob = warp_max(eob);
+  __syncwarp();
+  // ---- row l: row transform, quantise / dequantise in registers (oracle quantize())
+  int32_t dq[N];
+  int eob = 0;
+  {
+    int32_t x[N], o[N];
+#pragma unroll
+    for (int c = 0; c < N; c++) x[c] = buf[l * S + c];
+    fwd1d<N>(horz, x, o, cos_row);
+    const int dc_q = f->dc_q, ac_q = f->ac_q;
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+      const int pos = l * N + c;
+      const int q = pos == 0 ? dc_q : ac_q;
+      const int off = pos == 0 ? (q * 109) >> 8 : (q * 98) >> 8;
+      const int32_t cf = o[c];
+      const uint32_t a = (uint32_t)(cf < 0 ? -cf : cf);
+      uint32_t lv = (a + (uint32_t)off) / (uint32_t)q;
+      if (lv > 32767) lv = 32767;
+      const int32_t dqa = (int32_t)(((unsigned long long)lv * (uint32_t)q) & 0xFFFFFF);
+      const int si = __ldg(&iscan[pos]);
+      qc[si] = (int16_t)(cf < 0 ? -(int)lv : (int)lv);
+      dq[c] = cf < 0 ? -dqa : dqa;
+      lev[l * LS + c] = (uint8_t)(lv > 127 ? 127 : lv);
+      if (lv) eob = max(eob, si + 1);
+    }
+  }
+  eob = group_max<N>(eob);
   __syncwarp();
   // ---- rate (oracle coef_rate())
   const int txs = txs_of(N), ptype = plane > 0;
   const int skip_ctx = plane == 0 ? 0 : 7;
   uint32_t rate = 0;
   if (eob == 0) {
-    rate = rt->txb_skip[txs][skip_ctx][1];
+    if (l == 0) rate = rt->txb_skip[txs][skip_ctx][1];
   } else {
-    if (lane == 0) {
+    if (l == 0) {
       rate = rt->txb_skip[txs][skip_ctx][0];
       if (plane == 0) rate += rt->intra_tx[(f->reduced_tx_set || N == 16) ? 1 : 0][txs][y_mode][tx_type];
       int tg = 0;
-      const int group_start[12] = {0, 1, 2, 3, 5, 9, 17, 33, 65, 129, 257, 513};
-      while (tg < 11 && group_start[tg + 1] <= eob) tg++;
+      while (tg < 11 && (tg == 0 ? 1 : (tg == 1 ? 2 : (1 << (tg - 1)) + 1)) <= eob) tg++;   // group_start[tg + 1] <= eob
+      const int gstart = tg < 3 ? tg : (1 << (tg - 2)) + 1;                                 // group_start[tg]
       rate += rt->eob_pt[txs][ptype][tg - 1];
       const int nb = tg < 3 ? 0 : tg - 2;
       if (nb > 0) {
-        const int extra = eob - group_start[tg];
+        const int extra = eob - gstart;
         rate += rt->eob_extra[txs][ptype][tg - 3][(extra >> (nb - 1)) & 1];
         rate += 256u * (uint32_t)(nb - 1);
       }
     }
-    for (int pos = lane; pos < N2; pos += 32) {
-      const int si = iscan[pos];
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+      const int pos = l * N + c;
+      const int si = __ldg(&iscan[pos]);
       if (si >= eob) continue;
-      const int rr = pos / N, cc = pos % N;
       const int level = abs((int)qc[si]);
-      const uint8_t *L = w.lev + rr * LS + cc;
+      const uint8_t *L = lev + l * LS + c;
       if (si == eob - 1) {
         const int c4 = si == 0 ? 0 : (si <= N2 / 8 ? 1 : (si <= N2 / 4 ? 2 : 3));
         rate += rt->coeff_base_eob[txs][ptype][c4][min(level, 3) - 1];
       } else {
         const int mag = min((int)L[1], 3) + min((int)L[LS], 3) + min((int)L[LS + 1], 3) + min((int)L[2], 3) + min((int)L[2 * LS], 3);
         int ctx = min((mag + 1) >> 1, 4);
-        if (rr == 0 && cc == 0) ctx = 0;
-        else ctx += (rr + cc < 2) ? 1 : ((rr + cc < 4) ? 6 : 21);
+        if (l == 0 && c == 0) ctx = 0;
+        else ctx += (l + c < 2) ? 1 : ((l + c < 4) ? 6 : 21);
         rate += rt->coeff_base[txs][ptype][ctx][min(level, 3)];
       }
       if (level > 2) {
         int mag = min((int)L[1], 15) + min((int)L[LS], 15) + min((int)L[LS + 1], 15);
         mag = min((mag + 1) >> 1, 6);
-        const int bctx = (rr == 0 && cc == 0) ? mag : ((rr < 2 && cc < 2) ? mag + 7 : mag + 14);
+        const int bctx = (l == 0 && c == 0) ? mag : ((l < 2 && c < 2) ? mag + 7 : mag + 14);
         rate += rt->coeff_br[txs][ptype][bctx][min(level - 3, 12)];
         if (level > 14) {
           int xg = level - 15 + 1, len = 0;
@@ -461,202 +431,207 @@ __device__ uint32_t trial_plane_warp(const TileCtx &t, Shared &sh, WarpScratch &
       }
       if (level) rate += (si == 0) ? rt->dc_sign[ptype][0][qc[si] < 0] : 256u;
     }
-    rate = warp_sum(rate);
   }
-  // ---- reconstruct
+  rate = group_sum<N>(rate);
+  // ---- inverse (AV1 spec 7.13.3): row l from registers, transpose, column l, reconstruct, SSE
   if (eob) {
-    inv_txfm2d_add_warp<N>(w.buf, pred, w.recon[set], tx_type, f->bit_depth);
-  } else {
-    for (int p = lane; p < N2; p += 32) w.recon[set][p] = pred[p];
-    __syncwarp();
+    int32_t x[N], o[N];
+#pragma unroll
+    for (int c = 0; c < N; c++) x[c] = clamp_bits(dq[c], bd + 8);
+    inv1d<N>(horz, x, o);
+#pragma unroll
+    for (int c = 0; c < N; c++) buf[l * S + c] = rshift_round(o[c], row_shift);
   }
-  // ---- distortion
+  __syncwarp();
   uint32_t sse = 0;
-  for (int p = lane; p < N2; p += 32) {
-    const int d = (int)src[p] - (int)w.recon[set][p];
-    sse += (uint32_t)(d * d);
+  if (eob) {
+    const int col_clamp = bd + 6 > 16 ? bd + 6 : 16;
+    const int mx = (1 << bd) - 1;
+    int32_t x[N], o[N];
+#pragma unroll
+    for (int r = 0; r < N; r++) x[r] = clamp_bits(buf[r * S + l], col_clamp);
+    inv1d<N>(vert, x, o);
+#pragma unroll
+    for (int r = 0; r < N; r++) {
+      int v = (int)pred[r * N + l] + rshift_round(o[r], 4);
+      v = v < 0 ? 0 : (v > mx ? mx : v);
+      rec[r * N + l] = (uint16_t)v;
+      const int d = (int)src[r * N + l] - v;
+      sse += (uint32_t)(d * d);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < N; r++) {
+      const int v = pred[r * N + l];
+      rec[r * N + l] = (uint16_t)v;
+      const int d = (int)src[r * N + l] - v;
+      sse += (uint32_t)(d * d);
+    }
   }
-  sse = warp_sum(sse);
-  *eob_out = eob;
-  *rate_out = rate;
-  return sse;
+  sse = group_sum<N>(sse);
+  __syncwarp();
+  eob_out = eob; rate_out = rate; sse_out = sse;
 }
 
 __device__ __forceinline__ long long rd_cost(const B200Frame *f, unsigned long long sse, uint32_t rate) {
   return (long long)(sse << 8) + (((long long)f->lambda_q8 * (long long)rate) >> 8);
 }
-
-__device__ __forceinline__ uint32_t trial_plane_dispatch(int n, const TileCtx &t, Shared &sh, WarpScratch &w, int set, int plane,
-                                                         const uint16_t *src, int tx_type, int y_mode, int *eob,
-                                                         uint32_t *rate) {
-  if (n == 4) return trial_plane_warp<4>(t, sh, w, set, plane, src, tx_type, y_mode, eob, rate);
-  if (n == 8) return trial_plane_warp<8>(t, sh, w, set, plane, src, tx_type, y_mode, eob, rate);
-  return trial_plane_warp<16>(t, sh, w, set, plane, src, tx_type, y_mode, eob, rate);
-}
-
 __device__ __forceinline__ int chroma_tx_type(int uv_mode) { return dv_intra_mode_to_tx_type[uv_mode]; }
-
 __device__ __forceinline__ uint32_t mode_rate(const B200RateTables *rt, const uint16_t *cost_row, int m, int n) {
   uint32_t r = cost_row[m];
   if (n >= 8 && m >= V_PRED && m <= D67_PRED) r += rt->angle_delta[m - V_PRED][3];
   return r;
 }
 
-// Evaluate one block (all planes) at (x, y), size n (4|8|16): result in sh.cur.  All threads of the CTA.
-__device__ void trial_block(const TileCtx &t, Shared &sh, int x, int y, int n) {
+// top-2 of 13 mode costs held by lanes 0..12 (kInf when not allowed): lowest cost first, ties -> lowest index
+__device__ __forceinline__ void rank_top2(long long c, int &m0, int &m1) {
+  const int lane = lane_id();
+  long long j = lane < 13 ? c : kInf;
+  int i = lane < 13 ? lane : 99;
+  warp_argmin(j, i);
+  m0 = j == kInf ? -1 : i;
+  long long j2 = (lane < 13 && lane != m0) ? c : kInf;
+  int i2 = lane < 13 ? lane : 99;
+  warp_argmin(j2, i2);
+  m1 = j2 == kInf ? -1 : i2;
+}
+
+// Evaluate one block (all planes) at (x, y), size N: result in sh.cur.
+template <int N>
+__device__ void trial_block(const TileCtx &t, Shared &sh, int x, int y) {
+  constexpr int n = N, N2 = N * N, G = 32 / N, NB = N / 4;
   const B200Frame *f = t.f;
   const B200RateTables *rt = t.rt;
-  const int tid = threadIdx.x, wid = warp_id(), lane = lane_id();
-  const int n2 = n * n, planes = f->planes;
+  const int lane = lane_id(), g = lane / N;
+  const int planes = f->planes, bd = f->bit_depth;
   const int mi_r = y >> 2, mi_c = x >> 2;
   const int avail_u = mi_r > t.tr0, avail_l = mi_c > t.tc0;
-  // ---- P0: stage source block, build edges
-  for (int i = tid; i < planes * n2; i += kThreads) {
-    const int p = i / n2, q = i % n2;
-    sh.src[p][q] = t.src[p][(y + q / n) * t.stride + x + (q % n)];
+  // ---- stage source block and edges; clear the padded level maps
+  for (int i = lane; i < planes * N2; i += 32) {
+    const int p = i / N2, q = i % N2;
+    sh.src[p][q] = t.src[p][(y + q / N) * t.stride + x + (q % N)];
   }
-  if (wid < planes) build_edges(t, sh, wid, x, y, n);
-  __syncthreads();
-  const int ha = sh.have_above, hl = sh.have_left, bd = f->bit_depth;
-  // ---- P1: SATD of every allowed mode: luma tasks 0..12, chroma (U+V) tasks 13..25
-  {
-    WarpScratch &w = sh.ws[wid];
-    const int ntask = planes > 1 ? 26 : 13;
-    for (int task = wid; task < ntask; task += kWarps) {
-      const int g = task / 13, m = task % 13;
-      const int mask = g == 0 ? f->y_mode_mask : f->uv_mode_mask;
-      uint32_t s = 0xffffffffu;
-      if ((mask >> m) & 1) {
-        if (g == 0) {
-          predict_intra(m, n, sh.above[0], sh.left[0], ha, hl, bd, w.pred);
-          __syncwarp();
-          s = satd4_warp(sh.src[0], w.pred, n);
-        } else {
-          predict_intra(m, n, sh.above[1], sh.left[1], ha, hl, bd, w.pred);
-          __syncwarp();
-          s = satd4_warp(sh.src[1], w.pred, n);
-          __syncwarp();
-          predict_intra(m, n, sh.above[2], sh.left[2], ha, hl, bd, w.pred);
-          __syncwarp();
-          s += satd4_warp(sh.src[2], w.pred, n);
-        }
-        __syncwarp();
-      }
-      if (lane == 0) sh.satd[g][m] = s;
-    }
-  }
-  __syncthreads();
-  // ---- P2: rank luma modes (thread 0)
+  for (int i = lane; i < 200; i += 32) reinterpret_cast<uint32_t *>(sh.lev)[i] = 0;
+  int ha = 0, hl = 0;
+  for (int p = 0; p < planes; p++) build_edges(t, sh, p, x, y, n, ha, hl);
+  __syncwarp();
+  // ---- SATD of every mode: task = (plane, 4x4 sub-block) spread over the lanes, same mode for all lanes
   const int am = avail_u ? t.mi[(mi_r - 1) * f->mi_cols + mi_c].y_mode : DC_PRED;
   const int lm = avail_l ? t.mi[mi_r * f->mi_cols + mi_c - 1].y_mode : DC_PRED;
   const uint16_t *ymode_cost = rt->y_mode[dv_intra_mode_context[am]][dv_intra_mode_context[lm]];
-  if (tid == 0) {
-    long long bc0 = 0x7fffffffffffffffll, bc1 = 0x7fffffffffffffffll;
-    int bm0 = -1, bm1 = -1;
+  long long my_ycost = kInf;       // lane m (< 13) keeps the luma cost of mode m
+  uint32_t my_uvsatd = 0;          // lane m keeps the chroma (U+V) SATD of mode m
+  {
+    const int ntask = planes * NB * NB;
+    const int allowed = f->y_mode_mask | (planes > 1 ? f->uv_mode_mask : 0);
     for (int m = 0; m < 13; m++) {
-      if (!((f->y_mode_mask >> m) & 1)) continue;
-      const long long c = (long long)sh.satd[0][m] * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, m, n)) >> 8);
-      if (c < bc0) { bc1 = bc0; bm1 = bm0; bc0 = c; bm0 = m; }
-      else if (c < bc1) { bc1 = c; bm1 = m; }
+      if (!((allowed >> m) & 1)) continue;
+      uint32_t sy = 0, suv = 0;
+      for (int task = lane; task < ((ntask + 31) & ~31); task += 32) {
+        uint32_t s = 0;
+        int p = 0;
+        if (task < ntask) {
+          p = task / (NB * NB);
+          const int sb = task % (NB * NB);
+          const uint16_t *A = sh.above[p] + EOFF, *L = sh.left[p] + EOFF;
+          const int dc = m == DC_PRED ? dc_value(n, A, L, ha, hl, bd) : 0;
+          s = satd_subblock(m, n, (sb / NB) * 4, (sb % NB) * 4, sh.src[p], A, L, dc);
+        }
+        sy += warp_sum(p == 0 ? s : 0);
+        if (planes > 1) suv += warp_sum(p == 0 ? 0 : s);
+      }
+      if (lane == m) {
+        if ((f->y_mode_mask >> m) & 1)
+          my_ycost = (long long)sy * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, m, n)) >> 8);
+        my_uvsatd = suv;
+      }
     }
-    sh.sel[0] = bm0; sh.sel[1] = bm1;
   }
-  __syncthreads();
-  // ---- P3: luma full trials: candidate c = k * 5 + t  (mode rank k, transform type index t)
+  int m0, m1;
+  rank_top2(my_ycost, m0, m1);
+  // ---- luma full trials: candidate c = k * 5 + ti (mode rank k, transform type index ti); lane batches pair
+  //      the two modes on the same transform type so that a batch runs identical transform kernels
   int first_t = -1;
   for (int k = 0; k < 5; k++) if ((f->tx_type_mask >> k) & 1) { first_t = k; break; }
-  {
-    WarpScratch &w = sh.ws[wid];
-    int have = 0;              // number of candidates this warp already holds (kept in set 0)
-    long long myJ = 0;
-    for (int c = wid; c < 10; c += kWarps) {
-      const int k = c / 5, ti = c % 5;
-      const int m = sh.sel[k];
-      const bool ok = m >= 0 && ((f->tx_type_mask >> ti) & 1) && (f->rdo_tx_decision || ti == first_t);
-      if (!ok) { if (lane == 0) sh.taskJ[c] = 0x7fffffffffffffffll; continue; }
-      predict_intra(m, n, sh.above[0], sh.left[0], ha, hl, bd, w.pred);
-      __syncwarp();
-      int eob; uint32_t rate;
-      const int set = have ? 1 : 0;
-      const uint32_t d = trial_plane_dispatch(n, t, sh, w, set, 0, sh.src[0], dv_tx_types[ti], m, &eob, &rate);
-      const long long J = rd_cost(f, d, rate + mode_rate(rt, ymode_cost, m, n));
-      if (lane == 0) { sh.taskJ[c] = J; sh.taskEob[c] = (uint16_t)eob; }
-      if (have && J < myJ) {   // second candidate strictly better: move it to set 0
-        for (int p = lane; p < n2; p += 32) { w.qc[0][p] = w.qc[1][p]; w.recon[0][p] = w.recon[1][p]; }
-        myJ = J;
-      } else if (!have) { myJ = J; have = 1; }
-      __syncwarp();
+  predict_block(m0 >= 0 ? m0 : 0, n, sh.above[0], sh.left[0], ha, hl, bd, sh.pred);
+  predict_block(m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0), n, sh.above[0], sh.left[0], ha, hl, bd, sh.pred + 256);
+  __syncwarp();
+  long long bestJ = kInf;
+  int bestC = 1 << 20, bestEob = 0;
+  for (int b = 0; b * G < 10; b++) {
+    const int ci = b * G + g;                 // position in the (ti major, k minor) candidate order
+    const int ti = ci >> 1, k = ci & 1;
+    const int m = k == 0 ? m0 : m1;
+    const bool ok = ti < 5 && m >= 0 && ((f->tx_type_mask >> ti) & 1) && (f->rdo_tx_decision || ti == first_t);
+    if (!__ballot_sync(FULL, ok)) continue;   // nothing to do in this batch (warp-uniform)
+    int eob; uint32_t rate, sse;
+    trial_batch<N>(t, sh, 0, sh.src[0], sh.pred + (ok ? k : 0) * 256, dv_tx_types[ok ? ti : 0], ok ? m : (m0 >= 0 ? m0 : 0), eob, rate, sse);
+    long long J = kInf;
+    int c = 1 << 20;
+    if (ok) { J = rd_cost(f, sse, rate + mode_rate(rt, ymode_cost, m, n)); c = k * 5 + ti; }
+    long long wj = J;
+    int wc = c;
+    warp_argmin(wj, wc);
+    if (wj < bestJ || (wj == bestJ && wc < bestC)) {
+      bestJ = wj; bestC = wc;
+      const int wci = (wc % 5) * 2 + wc / 5;           // winner's position in the batch order
+      const int wg = wci - b * G;                      // its lane group
+      bestEob = __shfl_sync(FULL, eob, wg * N);
+      for (int p = lane; p < N2; p += 32) { sh.cur.qc[0][p] = sh.qc[wg * N2 + p]; sh.cur.recon[0][p] = sh.rec[wg * N2 + p]; }
     }
+    __syncwarp();
   }
-  __syncthreads();
-  // ---- P4: pick the luma winner
-  if (tid == 0) {
-    long long bj = 0x7fffffffffffffffll;
-    int bcand = 0;
-    for (int c = 0; c < 10; c++) if (sh.taskJ[c] < bj) { bj = sh.taskJ[c]; bcand = c; }
-    sh.sel[2] = bcand;
-  }
-  __syncthreads();
-  const int bcand = sh.sel[2];
-  const int best_mode = sh.sel[bcand / 5], best_tt = dv_tx_types[bcand % 5];
-  const long long lumaJ = sh.taskJ[bcand];
-  {
-    // the winner's data sit in set 0 of warp (bcand % kWarps)
-    const WarpScratch &w = sh.ws[bcand % kWarps];
-    for (int p = tid; p < n2; p += kThreads) { sh.cur.qc[0][p] = w.qc[0][p]; sh.cur.recon[0][p] = w.recon[0][p]; }
-    if (tid == 0) sh.cur.eob[0] = sh.taskEob[bcand];
-  }
-  long long total = lumaJ;
-  int uv_best = DC_PRED;
+  const int best_mode = bestC / 5 == 0 ? m0 : m1;
+  const int best_tt = dv_tx_types[bestC % 5];
+  long long total = bestJ;
+  int uv_best = DC_PRED, eobU = 0, eobV = 0;
   if (planes > 1) {
-    // ---- P5: rank uv modes
+    // ---- chroma: rank uv modes by SATD + rate, full trial of the top two on both planes
     const uint16_t *uvcost = rt->uv_mode[1][best_mode];   // cfl_allowed = 1 for n <= 32
-    if (tid == 0) {
-      long long bc0 = 0x7fffffffffffffffll, bc1 = 0x7fffffffffffffffll;
-      int bm0 = -1, bm1 = -1;
-      for (int m = 0; m < 13; m++) {
-        if (!((f->uv_mode_mask >> m) & 1)) continue;
-        const long long c = (long long)sh.satd[1][m] * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, uvcost, m, n)) >> 8);
-        if (c < bc0) { bc1 = bc0; bm1 = bm0; bc0 = c; bm0 = m; }
-        else if (c < bc1) { bc1 = c; bm1 = m; }
+    long long my_uvcost = kInf;
+    if (lane < 13 && ((f->uv_mode_mask >> lane) & 1))
+      my_uvcost = (long long)my_uvsatd * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, uvcost, lane, n)) >> 8);
+    int u0, u1;
+    rank_top2(my_uvcost, u0, u1);
+    long long bestCj = kInf;
+    for (int b = 0; b * G < 4; b++) {
+      const int ci = b * G + g;               // candidate = (k = ci >> 1, plane = 1 + (ci & 1))
+      const int k = (ci >> 1) & 1, p = 1 + (ci & 1);
+      const int m = k == 0 ? u0 : u1;
+      const bool ok = ci < 4 && m >= 0;
+      // predictions of the (mode rank, plane) pairs of this batch: slot = candidate index within the batch
+      for (int cc = b * G; cc < min((b + 1) * G, 4); cc++) {
+        const int mm = (cc >> 1) == 0 ? u0 : u1, pp = 1 + (cc & 1);
+        predict_block(mm >= 0 ? mm : 0, n, sh.above[pp], sh.left[pp], ha, hl, bd, sh.pred + (cc - b * G) * N2);
       }
-      sh.sel[3] = bm0; sh.sel[4] = bm1;
-    }
-    __syncthreads();   // also orders the copy of the luma winner before warps reuse their scratch
-    // ---- P6: chroma full trials: task = k * 2 + (plane - 1), warps 0..3
-    if (wid < 4) {
-      WarpScratch &w = sh.ws[wid];
-      const int k = wid >> 1, plane = 1 + (wid & 1);
-      const int m = sh.sel[3 + k];
-      if (m >= 0) {
-        predict_intra(m, n, sh.above[plane], sh.left[plane], ha, hl, bd, w.pred);
-        __syncwarp();
-        int eob; uint32_t rate;
-        const uint32_t d = trial_plane_dispatch(n, t, sh, w, 0, plane, sh.src[plane], chroma_tx_type(m), best_mode, &eob, &rate);
-        if (lane == 0) { sh.taskD[wid] = d; sh.taskR[wid] = rate; sh.taskEobC[wid] = (uint16_t)eob; }
+      __syncwarp();
+      int eob; uint32_t rate, sse;
+      trial_batch<N>(t, sh, p, sh.src[p], sh.pred + (ok ? g : 0) * N2, chroma_tx_type(m >= 0 ? m : 0), best_mode, eob, rate, sse);
+      if (ok && lane % N == 0) { sh.taskD[ci] = sse; sh.taskR[ci] = rate; sh.taskE[ci] = (uint16_t)eob; }
+      __syncwarp();
+      // mode ranks fully evaluated by this batch: both planes present
+      for (int kk = 0; kk < 2; kk++) {
+        const int cU = kk * 2, cV = kk * 2 + 1;
+        if (cV < b * G || cV >= (b + 1) * G) continue;     // (cU, cV) always land in the same batch (G even)
+        const int mm = kk == 0 ? u0 : u1;
+        if (mm < 0) continue;
+        const long long J = rd_cost(f, (unsigned long long)sh.taskD[cU] + sh.taskD[cV],
+                                    sh.taskR[cU] + sh.taskR[cV] + mode_rate(rt, uvcost, mm, n));
+        if (J < bestCj) {
+          bestCj = J; uv_best = mm; eobU = sh.taskE[cU]; eobV = sh.taskE[cV];
+          const int gU = cU - b * G, gV = cV - b * G;
+          for (int q = lane; q < N2; q += 32) {
+            sh.cur.qc[1][q] = sh.qc[gU * N2 + q]; sh.cur.recon[1][q] = sh.rec[gU * N2 + q];
+            sh.cur.qc[2][q] = sh.qc[gV * N2 + q]; sh.cur.recon[2][q] = sh.rec[gV * N2 + q];
+          }
+        }
       }
+      __syncwarp();
     }
-    __syncthreads();
-    // ---- P7: pick the chroma winner
-    long long bestC = 0x7fffffffffffffffll;
-    int bk = 0;
-    for (int k = 0; k < 2; k++) {
-      const int m = sh.sel[3 + k];
-      if (m < 0) continue;
-      const long long J = rd_cost(f, (unsigned long long)sh.taskD[2 * k] + sh.taskD[2 * k + 1],
-                                  sh.taskR[2 * k] + sh.taskR[2 * k + 1] + mode_rate(rt, uvcost, m, n));
-      if (J < bestC) { bestC = J; bk = k; }
-    }
-    uv_best = sh.sel[3 + bk];
-    total += bestC;
-    for (int p = tid; p < n2; p += kThreads) {
-      sh.cur.qc[1][p] = sh.ws[2 * bk].qc[0][p]; sh.cur.recon[1][p] = sh.ws[2 * bk].recon[0][p];
-      sh.cur.qc[2][p] = sh.ws[2 * bk + 1].qc[0][p]; sh.cur.recon[2][p] = sh.ws[2 * bk + 1].recon[0][p];
-    }
-    if (tid == 0) { sh.cur.eob[1] = sh.taskEobC[2 * bk]; sh.cur.eob[2] = sh.taskEobC[2 * bk + 1]; }
+    total += bestCj;
   }
   // ---- skip flag + totals
-  if (tid == 0) {
+  if (lane == 0) {
     B200Mi m;
     m.bsize = (uint8_t)(n == 4 ? BLOCK_4X4 : n == 8 ? BLOCK_8X8 : BLOCK_16X16);
     m.y_mode = (uint8_t)best_mode;
@@ -666,44 +641,47 @@ __device__ void trial_block(const TileCtx &t, Shared &sh, int x, int y, int n) {
     m.tx_type = (uint8_t)best_tt;
     m.flags = 0;
     m.cfl = 0;
-    const int all_zero = sh.cur.eob[0] == 0 && (planes == 1 || (sh.cur.eob[1] == 0 && sh.cur.eob[2] == 0));
+    const int all_zero = bestEob == 0 && (planes == 1 || (eobU == 0 && eobV == 0));
     const int a = avail_u ? (t.mi[(mi_r - 1) * f->mi_cols + mi_c].flags & 1) : 0;
     const int l = avail_l ? (t.mi[mi_r * f->mi_cols + mi_c - 1].flags & 1) : 0;
     total += ((long long)f->lambda_q8 * rt->skip[a + l][all_zero]) >> 8;
     if (all_zero) m.flags |= 1;
     sh.cur.mi = m;
     sh.cur.cost = total;
+    sh.cur.eob[0] = (uint16_t)bestEob; sh.cur.eob[1] = (uint16_t)eobU; sh.cur.eob[2] = (uint16_t)eobV;
   }
-  __syncthreads();
+  __syncwarp();
 }
 
-__device__ void copy_cand(Cand &dst, const Cand &src, int n, int planes) {
-  const int tid = threadIdx.x, n2 = n * n;
-  for (int i = tid; i < planes * n2; i += kThreads) {
+template <int n, typename D, typename S>
+__device__ void copy_cand(D &dst, const S &src, int planes) {
+  const int lane = lane_id(), n2 = n * n;
+  for (int i = lane; i < planes * n2; i += 32) {
     const int p = i / n2, q = i % n2;
     dst.qc[p][q] = src.qc[p][q];
     dst.recon[p][q] = src.recon[p][q];
   }
-  if (tid == 0) { dst.cost = src.cost; dst.mi = src.mi; dst.eob[0] = src.eob[0]; dst.eob[1] = src.eob[1]; dst.eob[2] = src.eob[2]; }
-  __syncthreads();
+  if (lane == 0) { dst.cost = src.cost; dst.mi = src.mi; dst.eob[0] = src.eob[0]; dst.eob[1] = src.eob[1]; dst.eob[2] = src.eob[2]; }
+  __syncwarp();
 }
 
-__device__ void commit_block(const TileCtx &t, const Cand &cd, int x, int y, int n) {
+template <int n, typename C>
+__device__ void commit_block(const TileCtx &t, const C &cd, int x, int y) {
   const B200Frame *f = t.f;
-  const int tid = threadIdx.x, n2 = n * n, planes = f->planes;
+  const int lane = lane_id(), n2 = n * n, planes = f->planes;
   const int mi_r = y >> 2, mi_c = x >> 2, n4 = n >> 2;
-  for (int i = tid; i < planes * n2; i += kThreads) {
+  for (int i = lane; i < planes * n2; i += 32) {
     const int p = i / n2, q = i % n2;
     t.rec[p][(y + q / n) * t.stride + x + (q % n)] = cd.recon[p][q];
     t.coef[p][b200_coef_offset(f, mi_r, mi_c) + q] = cd.qc[p][q];
   }
-  if (tid < planes) t.eob[tid][mi_r * f->mi_cols + mi_c] = cd.eob[tid];
-  for (int i = tid; i < n4 * n4; i += kThreads) {
+  if (lane < planes) t.eob[lane][mi_r * f->mi_cols + mi_c] = cd.eob[lane];
+  for (int i = lane; i < n4 * n4; i += 32) {
     const int idx = (mi_r + i / n4) * f->mi_cols + mi_c + (i % n4);
     t.mi[idx] = cd.mi;
     t.decoded[idx] = 1;
   }
-  __syncthreads();
+  __syncwarp();
 }
 
 __device__ long long partition_cost(const TileCtx &t, int mi_r, int mi_c, int n, int split) {
@@ -724,18 +702,18 @@ __device__ long long encode_tree8(const TileCtx &t, Shared &sh, int x, int y) {
   const B200Frame *f = t.f;
   const int mi_r = y >> 2, mi_c = x >> 2;
   const bool can_split = f->partition_min < 8;
-  trial_block(t, sh, x, y, 8);
+  trial_block<8>(t, sh, x, y);
   const long long j_none = sh.cur.cost + partition_cost(t, mi_r, mi_c, 8, 0);
-  if (!can_split) { commit_block(t, sh.cur, x, y, 8); return j_none; }
-  copy_cand(sh.held8, sh.cur, 8, f->planes);
+  if (!can_split) { commit_block<8>(t, sh.cur, x, y); return j_none; }
+  copy_cand<8>(sh.held8, sh.cur, f->planes);
   long long j_split = partition_cost(t, mi_r, mi_c, 8, 1);
   for (int k = 0; k < 4; k++) {
     const int xx = x + (k & 1) * 4, yy = y + (k >> 1) * 4;
-    trial_block(t, sh, xx, yy, 4);
+    trial_block<4>(t, sh, xx, yy);
     j_split += sh.cur.cost;
-    commit_block(t, sh.cur, xx, yy, 4);
+    commit_block<4>(t, sh.cur, xx, yy);
   }
-  if (j_none <= j_split) { commit_block(t, sh.held8, x, y, 8); return j_none; }
+  if (j_none <= j_split) { commit_block<8>(t, sh.held8, x, y); return j_none; }
   return j_split;
 }
 
@@ -748,12 +726,12 @@ __device__ long long encode_tree16(const TileCtx &t, Shared &sh, int x, int y) {
   const bool inside = (x + 16 <= W) && (y + 16 <= H);
   const bool can_none = inside && f->partition_max >= 16;
   const bool can_split = f->partition_min < 16 || !inside;
-  long long j_none = 0x7fffffffffffffffll;
+  long long j_none = kInf;
   if (can_none) {
-    trial_block(t, sh, x, y, 16);
+    trial_block<16>(t, sh, x, y);
     j_none = sh.cur.cost + partition_cost(t, mi_r, mi_c, 16, 0);
-    if (!can_split) { commit_block(t, sh.cur, x, y, 16); return j_none; }
-    copy_cand(sh.held16, sh.cur, 16, f->planes);
+    if (!can_split) { commit_block<16>(t, sh.cur, x, y); return j_none; }
+    copy_cand<16>(sh.held16, sh.cur, f->planes);
   }
   long long j_split = partition_cost(t, mi_r, mi_c, 16, 1);
   for (int k = 0; k < 4; k++) {
@@ -761,14 +739,14 @@ __device__ long long encode_tree16(const TileCtx &t, Shared &sh, int x, int y) {
     if (xx >= W || yy >= H) continue;
     j_split += encode_tree8(t, sh, xx, yy);
   }
-  if (can_none && j_none <= j_split) { commit_block(t, sh.held16, x, y, 16); return j_none; }
+  if (can_none && j_none <= j_split) { commit_block<16>(t, sh.held16, x, y); return j_none; }
   return j_split;
 }
 
 }  // namespace
 
-// One CTA per tile.  Partition sizes > 16 are always split (partition_max <= 16 in this kernel).
-__global__ void __launch_bounds__(kThreads) b200_rdo_tile_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
+// One single-warp CTA per tile.  Partition sizes > 16 are always split (partition_max <= 16 in this kernel).
+__global__ void __launch_bounds__(kThreads, 14) b200_rdo_tile_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
   __shared__ Shared sh;
   const B200TileRef tr = tiles[blockIdx.x];
   const B200RdoJob &job = jobs[tr.job];
@@ -781,8 +759,6 @@ __global__ void __launch_bounds__(kThreads) b200_rdo_tile_kernel(const B200RdoJo
   t.tr1 = min(f->tile_row_start_sb[tr.tile_row + 1] * 16, f->mi_rows);
   t.tc0 = f->tile_col_start_sb[tr.tile_col] * 16;
   t.tc1 = min(f->tile_col_start_sb[tr.tile_col + 1] * 16, f->mi_cols);
-  for (int i = threadIdx.x; i < 336; i += kThreads) { sh.scan[i] = dv_scan[i]; sh.iscan[i] = dv_iscan[i]; }
-  __syncthreads();
   for (int r = t.tr0; r < t.tr1; r += 16)
     for (int c = t.tc0; c < t.tc1; c += 16)
       // 64x64 -> 32x32 -> 16x16 in z-order (always split above 16x16)
@@ -795,6 +771,11 @@ __global__ void __launch_bounds__(kThreads) b200_rdo_tile_kernel(const B200RdoJo
 #ifndef B200_EMU
 extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int n_tiles, void *stream) {
   if (n_tiles <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {   // ask for the largest shared-memory carve-out: ~14 single-warp CTAs of ~15 KB per SM
+    cudaFuncSetAttribute(b200_rdo_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
   b200_rdo_tile_kernel<<<n_tiles, kThreads, 0, (cudaStream_t)stream>>>(d_jobs, d_tiles);
   return (int)cudaGetLastError();
 }
