@@ -263,7 +263,7 @@ int run_rdo_and_fetch(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Are
   CU(cudaMemcpyAsync(d_jobs, hj.data(), hj.size() * sizeof(B200RdoJob), cudaMemcpyHostToDevice, c.stream));
   CU(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(B200TileRef), cudaMemcpyHostToDevice, c.stream));
   CU(cudaEventRecord(c.ev[1], c.stream));
-  const int le = b200_rdo_launch(d_jobs, d_tiles, (int)tiles.size(), c.stream);
+  const int le = b200_rdo_launch(d_jobs, d_tiles, (int)tiles.size(), jobs[0]->f.bit_depth > 8, c.stream);   // one depth per call
   if (le != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("RDO kernel launch failed: ") + cudaGetErrorString((cudaError_t)le));
   g_launches += 1;
   CU(cudaEventRecord(c.ev[2], c.stream));

@@ -123,7 +123,7 @@ __device__ __forceinline__ void warp_argmin(long long &J, int &idx) {
 }
 
 // ---- edges (AV1 spec 7.11.2, intra edge filter disabled) ----------------------------------------
-__device__ void build_edges(const TileCtx &t, Shared &sh, int plane, int x, int y, int n, int &ha_out, int &hl_out) {
+__device__ __noinline__ void build_edges(const TileCtx &t, Shared &sh, int plane, int x, int y, int n, int &ha_out, int &hl_out) {
   const B200Frame *f = t.f;
   const uint16_t *r = t.rec[plane];
   const int st = t.stride, lane = lane_id();
@@ -218,36 +218,6 @@ __device__ __forceinline__ int pred_px(int mode, int n, int i, int j, const uint
   return base < max_base ? (L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5 : L[max_base];
 }
 
-// whole-block prediction into shared memory, pixels spread over the 32 lanes
-__device__ void predict_block(int mode, int n, const uint16_t *above, const uint16_t *left, int ha, int hl, int bd, uint16_t *dst) {
-  const uint16_t *A = above + EOFF, *L = left + EOFF;
-  const int lg = n == 4 ? 2 : n == 8 ? 3 : 4;
-  const int dc = mode == DC_PRED ? dc_value(n, A, L, ha, hl, bd) : 0;
-  for (int p = lane_id(); p < n * n; p += 32) dst[p] = (uint16_t)pred_px(mode, n, p >> lg, p & (n - 1), A, L, dc);
-}
-
-// SATD (sum of |4x4 Hadamard|) of one 4x4 sub-block for `mode`, prediction computed on the fly
-__device__ __forceinline__ uint32_t satd_subblock(int mode, int n, int by, int bx, const uint16_t *src, const uint16_t *A,
-                                                  const uint16_t *L, int dc) {
-  int d[16], tt[16];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) d[i * 4 + j] = (int)src[(by + i) * n + bx + j] - pred_px(mode, n, by + i, bx + j, A, L, dc);
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int a = d[i * 4] + d[i * 4 + 1], b = d[i * 4] - d[i * 4 + 1], c = d[i * 4 + 2] + d[i * 4 + 3], e = d[i * 4 + 2] - d[i * 4 + 3];
-    tt[i * 4] = a + c; tt[i * 4 + 1] = b + e; tt[i * 4 + 2] = a - c; tt[i * 4 + 3] = b - e;
-  }
-  uint32_t total = 0;
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const int a = tt[j] + tt[4 + j], b = tt[j] - tt[4 + j], c = tt[8 + j] + tt[12 + j], e = tt[8 + j] - tt[12 + j];
-    total += (uint32_t)(abs(a + c) + abs(b + e) + abs(a - c) + abs(b - e));
-  }
-  return total;
-}
-
 // ---- 1-D transforms on register arrays -----------------------------------------------------
 enum { K_DCT = 0, K_ADST = 1, K_IDT = 2 };
 __device__ __forceinline__ void tx_kernels(int tx_type, int &vert, int &horz) {
@@ -288,25 +258,33 @@ __device__ __forceinline__ void identity_dev(const int32_t *in, int32_t *out) {
     else out[i] = round_shift64((long long)in[i] * 2 * 5793, 12);
   }
 }
-template <int N>
+// HBD = false (8-bit video): every half-butterfly w0*a + w1*b fits int32 (DESIGN.md "int32 butterflies"), so the
+// multiply-accumulate is a single IMAD; HBD = true (10-bit) keeps the int64 form of the specification.
+template <int N, bool HBD>
 __device__ __forceinline__ void fwd1d(int kind, const int32_t *in, int32_t *out, int bit) {
   const int32_t *c = dv_cospi_arr[bit - 10];
   if (kind == K_IDT) { identity_dev<N>(in, out); return; }
   if (kind == K_DCT) {
-    if (N == 4) gen_fdct4(in, out, c, bit); else if (N == 8) gen_fdct8(in, out, c, bit); else gen_fdct16(in, out, c, bit);
+    if (HBD) { if (N == 4) gen_fdct4(in, out, c, bit); else if (N == 8) gen_fdct8(in, out, c, bit); else gen_fdct16(in, out, c, bit); }
+    else { if (N == 4) gen_fdct4_w32(in, out, c, bit); else if (N == 8) gen_fdct8_w32(in, out, c, bit); else gen_fdct16_w32(in, out, c, bit); }
   } else {
-    if (N == 4) fadst4_dev(in, out, bit); else if (N == 8) gen_fadst8(in, out, c, bit); else gen_fadst16(in, out, c, bit);
+    if (N == 4) fadst4_dev(in, out, bit);
+    else if (HBD) { if (N == 8) gen_fadst8(in, out, c, bit); else gen_fadst16(in, out, c, bit); }
+    else { if (N == 8) gen_fadst8_w32(in, out, c, bit); else gen_fadst16_w32(in, out, c, bit); }
   }
 }
-template <int N>
+template <int N, bool HBD>
 __device__ __forceinline__ void inv1d(int kind, const int32_t *in, int32_t *out) {
   const int bit = 12;
   const int32_t *c = dv_cospi_arr[bit - 10];
   if (kind == K_IDT) { identity_dev<N>(in, out); return; }
   if (kind == K_DCT) {
-    if (N == 4) gen_idct4(in, out, c, bit); else if (N == 8) gen_idct8(in, out, c, bit); else gen_idct16(in, out, c, bit);
+    if (HBD) { if (N == 4) gen_idct4(in, out, c, bit); else if (N == 8) gen_idct8(in, out, c, bit); else gen_idct16(in, out, c, bit); }
+    else { if (N == 4) gen_idct4_w32(in, out, c, bit); else if (N == 8) gen_idct8_w32(in, out, c, bit); else gen_idct16_w32(in, out, c, bit); }
   } else {
-    if (N == 4) iadst4_dev(in, out, bit); else if (N == 8) gen_iadst8(in, out, c, bit); else gen_iadst16(in, out, c, bit);
+    if (N == 4) iadst4_dev(in, out, bit);
+    else if (HBD) { if (N == 8) gen_iadst8(in, out, c, bit); else gen_iadst16(in, out, c, bit); }
+    else { if (N == 8) gen_iadst8_w32(in, out, c, bit); else gen_iadst16_w32(in, out, c, bit); }
   }
 }
 __device__ __forceinline__ int32_t rshift_round(int32_t v, int bit) {   // bit > 0: rounding right shift; <= 0: left shift
@@ -323,12 +301,15 @@ __device__ __forceinline__ int32_t clamp_bits(int32_t v, int bits) {
 // group's quantised levels (scan order) and reconstruction stay in sh.qc / sh.rec at offset g*N*N.
 // Mirrors oracle/av1_encode.c trial_plane(): forward transform (libaom av1_fwd_txfm2d design), quantize(),
 // coef_rate(), AV1 spec 7.13.3 inverse transform + reconstruction, SSE.
-template <int N>
-__device__ void trial_batch(const TileCtx &t, Shared &sh, int plane, const uint16_t *src, const uint16_t *pred, int tx_type,
-                            int y_mode, int &eob_out, uint32_t &rate_out, uint32_t &sse_out) {
+// Code size matters (the instruction cache is the first bottleneck of this kernel): the function is NOT inlined,
+// each 1-D transform kernel appears once (two-pass loops), and the per-coefficient loops are rolled.
+struct TrialOut { int eob; uint32_t rate, sse; };
+
+template <int N, bool HBD>
+__device__ __noinline__ TrialOut trial_batch(const TileCtx &t, Shared &sh, int plane, const uint16_t *src, const uint16_t *pred,
+                                             int tx_type, int y_mode) {
   constexpr int S = N + 1, N2 = N * N, LS = N + 4;
   constexpr int shift1 = N == 4 ? 0 : (N == 8 ? 1 : 2);   // -fwd_shift[1]
-  constexpr int cos_col = 13, cos_row = N == 16 ? 12 : 13;
   constexpr int row_shift = N == 4 ? 0 : (N == 8 ? 1 : 2);
   const B200Frame *f = t.f;
   const B200RateTables *rt = t.rt;
@@ -342,38 +323,48 @@ __device__ void trial_batch(const TileCtx &t, Shared &sh, int plane, const uint1
   tx_kernels(tx_type, vert, horz);
   const int bd = f->bit_depth;
 
-  // ---- forward: column l in registers (residual << 2), column transform, transpose through shared memory
-  {
+  // ---- forward: pass 0 = column l (residual << 2 -> column transform -> buf), pass 1 = row l (buf -> row transform -> buf)
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
     int32_t x[N], o[N];
+    if (pass == 0) {
 #pragma unroll
-    for (int r = 0; r < N; r++) x[r] = ((int)src[r * N + l] - (int)pred[r * N + l]) * 4;
-    fwd1d<N>(vert, x, o, cos_col);
+      for (int r = 0; r < N; r++) x[r] = ((int)src[r * N + l] - (int)pred[r * N + l]) * 4;
+    } else {
 #pragma unroll
-    for (int r = 0; r < N; r++) buf[r * S + l] = rshift_round(o[r], shift1);
+      for (int c = 0; c < N; c++) x[c] = buf[l * S + c];
+    }
+    fwd1d<N, HBD>(pass == 0 ? vert : horz, x, o, (pass == 1 && N == 16) ? 12 : 13);
+    if (pass == 0) {
+#pragma unroll
+      for (int r = 0; r < N; r++) buf[r * S + l] = rshift_round(o[r], shift1);
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int c = 0; c < N; c++) buf[l * S + c] = o[c];
+    }
   }
-  __syncwarp();
-  // ---- row l: row transform, quantise / dequantise in registers (oracle quantize())
-  int32_t dq[N];
+  // ---- quantise / dequantise row l in place (oracle quantize()); exact division by reciprocal multiplication
   int eob = 0;
   {
-    int32_t x[N], o[N];
-#pragma unroll
-    for (int c = 0; c < N; c++) x[c] = buf[l * S + c];
-    fwd1d<N>(horz, x, o, cos_row);
-    const int dc_q = f->dc_q, ac_q = f->ac_q;
-#pragma unroll
+    const uint32_t dc_q = (uint32_t)f->dc_q, ac_q = (uint32_t)f->ac_q;
+    const uint32_t dc_rcp = 0xffffffffu / dc_q, ac_rcp = 0xffffffffu / ac_q;
+#pragma unroll 1
     for (int c = 0; c < N; c++) {
       const int pos = l * N + c;
-      const int q = pos == 0 ? dc_q : ac_q;
-      const int off = pos == 0 ? (q * 109) >> 8 : (q * 98) >> 8;
-      const int32_t cf = o[c];
-      const uint32_t a = (uint32_t)(cf < 0 ? -cf : cf);
-      uint32_t lv = (a + (uint32_t)off) / (uint32_t)q;
+      const uint32_t q = pos == 0 ? dc_q : ac_q, rcp = pos == 0 ? dc_rcp : ac_rcp;
+      const uint32_t off = pos == 0 ? (q * 109) >> 8 : (q * 98) >> 8;
+      const int32_t cf = buf[l * S + c];
+      const uint32_t a = (uint32_t)(cf < 0 ? -cf : cf) + off;
+      uint32_t lv = __umulhi(a, rcp);           // floor(a / q) or one/two less
+      uint32_t rem = a - lv * q;
+      if (rem >= q) { lv++; rem -= q; }
+      if (rem >= q) lv++;
       if (lv > 32767) lv = 32767;
-      const int32_t dqa = (int32_t)(((unsigned long long)lv * (uint32_t)q) & 0xFFFFFF);
+      const int32_t dqa = (int32_t)((lv * q) & 0xFFFFFF);
       const int si = __ldg(&iscan[pos]);
       qc[si] = (int16_t)(cf < 0 ? -(int)lv : (int)lv);
-      dq[c] = cf < 0 ? -dqa : dqa;
+      buf[l * S + c] = cf < 0 ? -dqa : dqa;
       lev[l * LS + c] = (uint8_t)(lv > 127 ? 127 : lv);
       if (lv) eob = max(eob, si + 1);
     }
@@ -401,7 +392,7 @@ __device__ void trial_batch(const TileCtx &t, Shared &sh, int plane, const uint1
         rate += 256u * (uint32_t)(nb - 1);
       }
     }
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < N; c++) {
       const int pos = l * N + c;
       const int si = __ldg(&iscan[pos]);
@@ -423,54 +414,67 @@ __device__ void trial_batch(const TileCtx &t, Shared &sh, int plane, const uint1
         mag = min((mag + 1) >> 1, 6);
         const int bctx = (l == 0 && c == 0) ? mag : ((l < 2 && c < 2) ? mag + 7 : mag + 14);
         rate += rt->coeff_br[txs][ptype][bctx][min(level - 3, 12)];
-        if (level > 14) {
-          int xg = level - 15 + 1, len = 0;
-          while (xg) { xg >>= 1; len++; }
-          rate += 256u * (uint32_t)(2 * len - 1);
-        }
+        if (level > 14) rate += 256u * (uint32_t)(2 * (32 - __clz(level - 14)) - 1);   // golomb(level - 15)
       }
       if (level) rate += (si == 0) ? rt->dc_sign[ptype][0][qc[si] < 0] : 256u;
     }
   }
   rate = group_sum<N>(rate);
-  // ---- inverse (AV1 spec 7.13.3): row l from registers, transpose, column l, reconstruct, SSE
-  if (eob) {
-    int32_t x[N], o[N];
-#pragma unroll
-    for (int c = 0; c < N; c++) x[c] = clamp_bits(dq[c], bd + 8);
-    inv1d<N>(horz, x, o);
-#pragma unroll
-    for (int c = 0; c < N; c++) buf[l * S + c] = rshift_round(o[c], row_shift);
-  }
-  __syncwarp();
+  // ---- inverse (AV1 spec 7.13.3): pass 0 = row l (buf -> buf), pass 1 = column l -> reconstruction + SSE
   uint32_t sse = 0;
   if (eob) {
     const int col_clamp = bd + 6 > 16 ? bd + 6 : 16;
     const int mx = (1 << bd) - 1;
-    int32_t x[N], o[N];
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      int32_t x[N], o[N];
+      if (pass == 0) {
 #pragma unroll
-    for (int r = 0; r < N; r++) x[r] = clamp_bits(buf[r * S + l], col_clamp);
-    inv1d<N>(vert, x, o);
+        for (int c = 0; c < N; c++) x[c] = clamp_bits(buf[l * S + c], bd + 8);
+      } else {
 #pragma unroll
-    for (int r = 0; r < N; r++) {
-      int v = (int)pred[r * N + l] + rshift_round(o[r], 4);
-      v = v < 0 ? 0 : (v > mx ? mx : v);
-      rec[r * N + l] = (uint16_t)v;
-      const int d = (int)src[r * N + l] - v;
-      sse += (uint32_t)(d * d);
+        for (int r = 0; r < N; r++) x[r] = clamp_bits(buf[r * S + l], col_clamp);
+      }
+      inv1d<N, HBD>(pass == 0 ? horz : vert, x, o);
+      if (pass == 0) {
+#pragma unroll
+        for (int c = 0; c < N; c++) buf[l * S + c] = rshift_round(o[c], row_shift);
+      } else {
+#pragma unroll
+        for (int r = 0; r < N; r++) {
+          int v = (int)pred[r * N + l] + rshift_round(o[r], 4);
+          v = v < 0 ? 0 : (v > mx ? mx : v);
+          rec[r * N + l] = (uint16_t)v;
+          const int d = (int)src[r * N + l] - v;
+          sse += (uint32_t)(d * d);
+        }
+      }
+      __syncwarp();     // groups with eob == 0 skip this loop: see the matching barriers below
     }
   } else {
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < N; r++) {
       const int v = pred[r * N + l];
       rec[r * N + l] = (uint16_t)v;
       const int d = (int)src[r * N + l] - v;
       sse += (uint32_t)(d * d);
     }
+    __syncwarp();
+    __syncwarp();
   }
   sse = group_sum<N>(sse);
   __syncwarp();
-  eob_out = eob; rate_out = rate; sse_out = sse;
+  TrialOut o;
+  o.eob = eob; o.rate = rate; o.sse = sse;
+  return o;
+}
+
+template <bool HBD>
+__device__ __forceinline__ TrialOut trial_dispatch(int n, const TileCtx &t, Shared &sh, int plane, const uint16_t *src,
+                                                   const uint16_t *pred, int tx_type, int y_mode) {
+  if (n == 4) return trial_batch<4, HBD>(t, sh, plane, src, pred, tx_type, y_mode);
+  if (n == 8) return trial_batch<8, HBD>(t, sh, plane, src, pred, tx_type, y_mode);
+  return trial_batch<16, HBD>(t, sh, plane, src, pred, tx_type, y_mode);
 }
 
 __device__ __forceinline__ long long rd_cost(const B200Frame *f, unsigned long long sse, uint32_t rate) {
@@ -483,8 +487,54 @@ __device__ __forceinline__ uint32_t mode_rate(const B200RateTables *rt, const ui
   return r;
 }
 
+// whole-block prediction into shared memory, pixels spread over the 32 lanes (the only place pred_px is expanded)
+__device__ __noinline__ void predict_block(int mode, int lg, const uint16_t *above, const uint16_t *left, int ha, int hl, int bd,
+                                           uint16_t *dst) {
+  const uint16_t *A = above + EOFF, *L = left + EOFF;
+  const int n = 1 << lg;
+  const int dc = mode == DC_PRED ? dc_value(n, A, L, ha, hl, bd) : 0;
+#pragma unroll 1
+  for (int p = lane_id(); p < n * n; p += 32) dst[p] = (uint16_t)pred_px(mode, n, p >> lg, p & (n - 1), A, L, dc);
+}
+
+// sum of |4x4 Hadamard| over the 4x4 sub-blocks of planes [0, planes): pred/src are [plane][n*n]; one lane per
+// (plane, sub-block); returns the luma sum and the chroma (U+V) sum to every lane
+__device__ __noinline__ void satd_planes(const uint16_t *src, const uint16_t *pred, int lg, int planes, uint32_t &sy, uint32_t &suv) {
+  const int n = 1 << lg, nb = n >> 2, nbb = nb * nb, ntask = planes * nbb, lane = lane_id();
+  uint32_t y = 0, uv = 0;
+#pragma unroll 1
+  for (int task = lane; task < ((ntask + 31) & ~31); task += 32) {
+    uint32_t total = 0;
+    int p = 0;
+    if (task < ntask) {
+      p = task / nbb;
+      const int sb = task - p * nbb;
+      const int by = (sb >> (lg - 2)) * 4, bx = (sb & (nb - 1)) * 4;
+      const uint16_t *s = src + p * 256 + by * n + bx, *q = pred + p * 256 + by * n + bx;
+      int d[16], tt[16];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) d[i * 4 + j] = (int)s[i * n + j] - (int)q[i * n + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int a = d[i * 4] + d[i * 4 + 1], b = d[i * 4] - d[i * 4 + 1], c = d[i * 4 + 2] + d[i * 4 + 3], e = d[i * 4 + 2] - d[i * 4 + 3];
+        tt[i * 4] = a + c; tt[i * 4 + 1] = b + e; tt[i * 4 + 2] = a - c; tt[i * 4 + 3] = b - e;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int a = tt[j] + tt[4 + j], b = tt[j] - tt[4 + j], c = tt[8 + j] + tt[12 + j], e = tt[8 + j] - tt[12 + j];
+        total += (uint32_t)(abs(a + c) + abs(b + e) + abs(a - c) + abs(b - e));
+      }
+    }
+    y += warp_sum(p == 0 ? total : 0);
+    if (planes > 1) uv += warp_sum(p == 0 ? 0 : total);
+  }
+  sy = y; suv = uv;
+}
+
 // top-2 of 13 mode costs held by lanes 0..12 (kInf when not allowed): lowest cost first, ties -> lowest index
-__device__ __forceinline__ void rank_top2(long long c, int &m0, int &m1) {
+__device__ __noinline__ void rank_top2(long long c, int &m0, int &m1) {
   const int lane = lane_id();
   long long j = lane < 13 ? c : kInf;
   int i = lane < 13 ? lane : 99;
@@ -496,55 +546,46 @@ __device__ __forceinline__ void rank_top2(long long c, int &m0, int &m1) {
   m1 = j2 == kInf ? -1 : i2;
 }
 
-// Evaluate one block (all planes) at (x, y), size N: result in sh.cur.
-template <int N>
-__device__ void trial_block(const TileCtx &t, Shared &sh, int x, int y) {
-  constexpr int n = N, N2 = N * N, G = 32 / N, NB = N / 4;
+// Evaluate one block (all planes) at (x, y), size n = 1 << lg (4 | 8 | 16): result in sh.cur.
+template <bool HBD>
+__device__ __noinline__ void trial_block(const TileCtx &t, Shared &sh, int x, int y, int lg) {
+  const int n = 1 << lg, N2 = n * n, G = 32 >> lg;
   const B200Frame *f = t.f;
   const B200RateTables *rt = t.rt;
-  const int lane = lane_id(), g = lane / N;
+  const int lane = lane_id(), g = lane >> lg;
   const int planes = f->planes, bd = f->bit_depth;
   const int mi_r = y >> 2, mi_c = x >> 2;
   const int avail_u = mi_r > t.tr0, avail_l = mi_c > t.tc0;
+  uint16_t *scratch = reinterpret_cast<uint16_t *>(sh.buf);     // 3 x 256 predictions during the SATD stage
   // ---- stage source block and edges; clear the padded level maps
-  for (int i = lane; i < planes * N2; i += 32) {
-    const int p = i / N2, q = i % N2;
-    sh.src[p][q] = t.src[p][(y + q / N) * t.stride + x + (q % N)];
-  }
+  for (int p = 0; p < planes; p++)
+#pragma unroll 1
+    for (int q = lane; q < N2; q += 32) sh.src[p][q] = t.src[p][(y + (q >> lg)) * t.stride + x + (q & (n - 1))];
   for (int i = lane; i < 200; i += 32) reinterpret_cast<uint32_t *>(sh.lev)[i] = 0;
   int ha = 0, hl = 0;
   for (int p = 0; p < planes; p++) build_edges(t, sh, p, x, y, n, ha, hl);
   __syncwarp();
-  // ---- SATD of every mode: task = (plane, 4x4 sub-block) spread over the lanes, same mode for all lanes
+  // ---- SATD of every mode: predictions of all planes into scratch, one lane per (plane, 4x4 sub-block)
   const int am = avail_u ? t.mi[(mi_r - 1) * f->mi_cols + mi_c].y_mode : DC_PRED;
   const int lm = avail_l ? t.mi[mi_r * f->mi_cols + mi_c - 1].y_mode : DC_PRED;
   const uint16_t *ymode_cost = rt->y_mode[dv_intra_mode_context[am]][dv_intra_mode_context[lm]];
   long long my_ycost = kInf;       // lane m (< 13) keeps the luma cost of mode m
   uint32_t my_uvsatd = 0;          // lane m keeps the chroma (U+V) SATD of mode m
   {
-    const int ntask = planes * NB * NB;
     const int allowed = f->y_mode_mask | (planes > 1 ? f->uv_mode_mask : 0);
+#pragma unroll 1
     for (int m = 0; m < 13; m++) {
       if (!((allowed >> m) & 1)) continue;
-      uint32_t sy = 0, suv = 0;
-      for (int task = lane; task < ((ntask + 31) & ~31); task += 32) {
-        uint32_t s = 0;
-        int p = 0;
-        if (task < ntask) {
-          p = task / (NB * NB);
-          const int sb = task % (NB * NB);
-          const uint16_t *A = sh.above[p] + EOFF, *L = sh.left[p] + EOFF;
-          const int dc = m == DC_PRED ? dc_value(n, A, L, ha, hl, bd) : 0;
-          s = satd_subblock(m, n, (sb / NB) * 4, (sb % NB) * 4, sh.src[p], A, L, dc);
-        }
-        sy += warp_sum(p == 0 ? s : 0);
-        if (planes > 1) suv += warp_sum(p == 0 ? 0 : s);
-      }
+      for (int p = 0; p < planes; p++) predict_block(m, lg, sh.above[p], sh.left[p], ha, hl, bd, scratch + p * 256);
+      __syncwarp();
+      uint32_t sy, suv;
+      satd_planes(&sh.src[0][0], scratch, lg, planes, sy, suv);
       if (lane == m) {
         if ((f->y_mode_mask >> m) & 1)
           my_ycost = (long long)sy * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, m, n)) >> 8);
         my_uvsatd = suv;
       }
+      __syncwarp();
     }
   }
   int m0, m1;
@@ -553,30 +594,30 @@ __device__ void trial_block(const TileCtx &t, Shared &sh, int x, int y) {
   //      the two modes on the same transform type so that a batch runs identical transform kernels
   int first_t = -1;
   for (int k = 0; k < 5; k++) if ((f->tx_type_mask >> k) & 1) { first_t = k; break; }
-  predict_block(m0 >= 0 ? m0 : 0, n, sh.above[0], sh.left[0], ha, hl, bd, sh.pred);
-  predict_block(m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0), n, sh.above[0], sh.left[0], ha, hl, bd, sh.pred + 256);
+  predict_block(m0 >= 0 ? m0 : 0, lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred);
+  predict_block(m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0), lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred + 256);
   __syncwarp();
   long long bestJ = kInf;
   int bestC = 1 << 20, bestEob = 0;
+#pragma unroll 1
   for (int b = 0; b * G < 10; b++) {
     const int ci = b * G + g;                 // position in the (ti major, k minor) candidate order
     const int ti = ci >> 1, k = ci & 1;
     const int m = k == 0 ? m0 : m1;
     const bool ok = ti < 5 && m >= 0 && ((f->tx_type_mask >> ti) & 1) && (f->rdo_tx_decision || ti == first_t);
     if (!__ballot_sync(FULL, ok)) continue;   // nothing to do in this batch (warp-uniform)
-    int eob; uint32_t rate, sse;
-    trial_batch<N>(t, sh, 0, sh.src[0], sh.pred + (ok ? k : 0) * 256, dv_tx_types[ok ? ti : 0], ok ? m : (m0 >= 0 ? m0 : 0), eob, rate, sse);
-    long long J = kInf;
-    int c = 1 << 20;
-    if (ok) { J = rd_cost(f, sse, rate + mode_rate(rt, ymode_cost, m, n)); c = k * 5 + ti; }
-    long long wj = J;
-    int wc = c;
+    const TrialOut r = trial_dispatch<HBD>(n, t, sh, 0, sh.src[0], sh.pred + (ok ? k : 0) * 256, dv_tx_types[ok ? ti : 0],
+                                           ok ? m : (m0 >= 0 ? m0 : 0));
+    long long wj = kInf;
+    int wc = 1 << 20;
+    if (ok) { wj = rd_cost(f, r.sse, r.rate + mode_rate(rt, ymode_cost, m, n)); wc = k * 5 + ti; }
     warp_argmin(wj, wc);
     if (wj < bestJ || (wj == bestJ && wc < bestC)) {
       bestJ = wj; bestC = wc;
       const int wci = (wc % 5) * 2 + wc / 5;           // winner's position in the batch order
       const int wg = wci - b * G;                      // its lane group
-      bestEob = __shfl_sync(FULL, eob, wg * N);
+      bestEob = __shfl_sync(FULL, r.eob, wg << lg);
+#pragma unroll 1
       for (int p = lane; p < N2; p += 32) { sh.cur.qc[0][p] = sh.qc[wg * N2 + p]; sh.cur.recon[0][p] = sh.rec[wg * N2 + p]; }
     }
     __syncwarp();
@@ -594,20 +635,21 @@ __device__ void trial_block(const TileCtx &t, Shared &sh, int x, int y) {
     int u0, u1;
     rank_top2(my_uvcost, u0, u1);
     long long bestCj = kInf;
+#pragma unroll 1
     for (int b = 0; b * G < 4; b++) {
       const int ci = b * G + g;               // candidate = (k = ci >> 1, plane = 1 + (ci & 1))
       const int k = (ci >> 1) & 1, p = 1 + (ci & 1);
       const int m = k == 0 ? u0 : u1;
       const bool ok = ci < 4 && m >= 0;
       // predictions of the (mode rank, plane) pairs of this batch: slot = candidate index within the batch
+#pragma unroll 1
       for (int cc = b * G; cc < min((b + 1) * G, 4); cc++) {
         const int mm = (cc >> 1) == 0 ? u0 : u1, pp = 1 + (cc & 1);
-        predict_block(mm >= 0 ? mm : 0, n, sh.above[pp], sh.left[pp], ha, hl, bd, sh.pred + (cc - b * G) * N2);
+        predict_block(mm >= 0 ? mm : 0, lg, sh.above[pp], sh.left[pp], ha, hl, bd, sh.pred + (cc - b * G) * N2);
       }
       __syncwarp();
-      int eob; uint32_t rate, sse;
-      trial_batch<N>(t, sh, p, sh.src[p], sh.pred + (ok ? g : 0) * N2, chroma_tx_type(m >= 0 ? m : 0), best_mode, eob, rate, sse);
-      if (ok && lane % N == 0) { sh.taskD[ci] = sse; sh.taskR[ci] = rate; sh.taskE[ci] = (uint16_t)eob; }
+      const TrialOut r = trial_dispatch<HBD>(n, t, sh, p, sh.src[p], sh.pred + (ok ? g : 0) * N2, chroma_tx_type(m >= 0 ? m : 0), best_mode);
+      if (ok && (lane & (n - 1)) == 0) { sh.taskD[ci] = r.sse; sh.taskR[ci] = r.rate; sh.taskE[ci] = (uint16_t)r.eob; }
       __syncwarp();
       // mode ranks fully evaluated by this batch: both planes present
       for (int kk = 0; kk < 2; kk++) {
@@ -620,6 +662,7 @@ __device__ void trial_block(const TileCtx &t, Shared &sh, int x, int y) {
         if (J < bestCj) {
           bestCj = J; uv_best = mm; eobU = sh.taskE[cU]; eobV = sh.taskE[cV];
           const int gU = cU - b * G, gV = cV - b * G;
+#pragma unroll 1
           for (int q = lane; q < N2; q += 32) {
             sh.cur.qc[1][q] = sh.qc[gU * N2 + q]; sh.cur.recon[1][q] = sh.rec[gU * N2 + q];
             sh.cur.qc[2][q] = sh.qc[gV * N2 + q]; sh.cur.recon[2][q] = sh.rec[gV * N2 + q];
@@ -653,38 +696,38 @@ __device__ void trial_block(const TileCtx &t, Shared &sh, int x, int y) {
   __syncwarp();
 }
 
-template <int n, typename D, typename S>
-__device__ void copy_cand(D &dst, const S &src, int planes) {
-  const int lane = lane_id(), n2 = n * n;
-  for (int i = lane; i < planes * n2; i += 32) {
-    const int p = i / n2, q = i % n2;
-    dst.qc[p][q] = src.qc[p][q];
-    dst.recon[p][q] = src.recon[p][q];
-  }
+template <typename D, typename S>
+__device__ __noinline__ void copy_cand(D &dst, const S &src, int lg, int planes) {
+  const int lane = lane_id(), n2 = 1 << (2 * lg);
+  for (int p = 0; p < planes; p++)
+#pragma unroll 1
+    for (int q = lane; q < n2; q += 32) { dst.qc[p][q] = src.qc[p][q]; dst.recon[p][q] = src.recon[p][q]; }
   if (lane == 0) { dst.cost = src.cost; dst.mi = src.mi; dst.eob[0] = src.eob[0]; dst.eob[1] = src.eob[1]; dst.eob[2] = src.eob[2]; }
   __syncwarp();
 }
 
-template <int n, typename C>
-__device__ void commit_block(const TileCtx &t, const C &cd, int x, int y) {
+template <typename C>
+__device__ __noinline__ void commit_block(const TileCtx &t, const C &cd, int x, int y, int lg) {
   const B200Frame *f = t.f;
-  const int lane = lane_id(), n2 = n * n, planes = f->planes;
+  const int lane = lane_id(), n = 1 << lg, n2 = n * n, planes = f->planes;
   const int mi_r = y >> 2, mi_c = x >> 2, n4 = n >> 2;
-  for (int i = lane; i < planes * n2; i += 32) {
-    const int p = i / n2, q = i % n2;
-    t.rec[p][(y + q / n) * t.stride + x + (q % n)] = cd.recon[p][q];
-    t.coef[p][b200_coef_offset(f, mi_r, mi_c) + q] = cd.qc[p][q];
-  }
+  const long long coff = b200_coef_offset(f, mi_r, mi_c);
+  for (int p = 0; p < planes; p++)
+#pragma unroll 1
+    for (int q = lane; q < n2; q += 32) {
+      t.rec[p][(y + (q >> lg)) * t.stride + x + (q & (n - 1))] = cd.recon[p][q];
+      t.coef[p][coff + q] = cd.qc[p][q];
+    }
   if (lane < planes) t.eob[lane][mi_r * f->mi_cols + mi_c] = cd.eob[lane];
   for (int i = lane; i < n4 * n4; i += 32) {
-    const int idx = (mi_r + i / n4) * f->mi_cols + mi_c + (i % n4);
+    const int idx = (mi_r + (i >> (lg - 2))) * f->mi_cols + mi_c + (i & (n4 - 1));
     t.mi[idx] = cd.mi;
     t.decoded[idx] = 1;
   }
   __syncwarp();
 }
 
-__device__ long long partition_cost(const TileCtx &t, int mi_r, int mi_c, int n, int split) {
+__device__ __noinline__ long long partition_cost(const TileCtx &t, int mi_r, int mi_c, int n, int split) {
   const B200Frame *f = t.f;
   const int bsl = ilog2_dev(n) - 2;
   const int hbs = n >> 3;
@@ -698,26 +741,29 @@ __device__ long long partition_cost(const TileCtx &t, int mi_r, int mi_c, int n,
 }
 
 // 8x8 node: NONE vs four 4x4 (oracle encode_tree at n = 8).  Returns the cost; frame state holds the winner.
+template <bool HBD>
 __device__ long long encode_tree8(const TileCtx &t, Shared &sh, int x, int y) {
   const B200Frame *f = t.f;
   const int mi_r = y >> 2, mi_c = x >> 2;
   const bool can_split = f->partition_min < 8;
-  trial_block<8>(t, sh, x, y);
+  trial_block<HBD>(t, sh, x, y, 3);
   const long long j_none = sh.cur.cost + partition_cost(t, mi_r, mi_c, 8, 0);
-  if (!can_split) { commit_block<8>(t, sh.cur, x, y); return j_none; }
-  copy_cand<8>(sh.held8, sh.cur, f->planes);
+  if (!can_split) { commit_block(t, sh.cur, x, y, 3); return j_none; }
+  copy_cand(sh.held8, sh.cur, 3, f->planes);
   long long j_split = partition_cost(t, mi_r, mi_c, 8, 1);
+#pragma unroll 1
   for (int k = 0; k < 4; k++) {
     const int xx = x + (k & 1) * 4, yy = y + (k >> 1) * 4;
-    trial_block<4>(t, sh, xx, yy);
+    trial_block<HBD>(t, sh, xx, yy, 2);
     j_split += sh.cur.cost;
-    commit_block<4>(t, sh.cur, xx, yy);
+    commit_block(t, sh.cur, xx, yy, 2);
   }
-  if (j_none <= j_split) { commit_block<8>(t, sh.held8, x, y); return j_none; }
+  if (j_none <= j_split) { commit_block(t, sh.held8, x, y, 3); return j_none; }
   return j_split;
 }
 
 // 16x16 node
+template <bool HBD>
 __device__ long long encode_tree16(const TileCtx &t, Shared &sh, int x, int y) {
   const B200Frame *f = t.f;
   const int W = f->mi_cols * 4, H = f->mi_rows * 4;
@@ -728,24 +774,27 @@ __device__ long long encode_tree16(const TileCtx &t, Shared &sh, int x, int y) {
   const bool can_split = f->partition_min < 16 || !inside;
   long long j_none = kInf;
   if (can_none) {
-    trial_block<16>(t, sh, x, y);
+    trial_block<HBD>(t, sh, x, y, 4);
     j_none = sh.cur.cost + partition_cost(t, mi_r, mi_c, 16, 0);
-    if (!can_split) { commit_block<16>(t, sh.cur, x, y); return j_none; }
-    copy_cand<16>(sh.held16, sh.cur, f->planes);
+    if (!can_split) { commit_block(t, sh.cur, x, y, 4); return j_none; }
+    copy_cand(sh.held16, sh.cur, 4, f->planes);
   }
   long long j_split = partition_cost(t, mi_r, mi_c, 16, 1);
+#pragma unroll 1
   for (int k = 0; k < 4; k++) {
     const int xx = x + (k & 1) * 8, yy = y + (k >> 1) * 8;
     if (xx >= W || yy >= H) continue;
-    j_split += encode_tree8(t, sh, xx, yy);
+    j_split += encode_tree8<HBD>(t, sh, xx, yy);
   }
-  if (can_none && j_none <= j_split) { commit_block<16>(t, sh.held16, x, y); return j_none; }
+  if (can_none && j_none <= j_split) { commit_block(t, sh.held16, x, y, 4); return j_none; }
   return j_split;
 }
 
 }  // namespace
 
 // One single-warp CTA per tile.  Partition sizes > 16 are always split (partition_max <= 16 in this kernel).
+// HBD = false: every job of the launch is 8-bit (int32 butterflies); HBD = true: 10-bit.
+template <bool HBD>
 __global__ void __launch_bounds__(kThreads, 14) b200_rdo_tile_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
   __shared__ Shared sh;
   const B200TileRef tr = tiles[blockIdx.x];
@@ -759,32 +808,39 @@ __global__ void __launch_bounds__(kThreads, 14) b200_rdo_tile_kernel(const B200R
   t.tr1 = min(f->tile_row_start_sb[tr.tile_row + 1] * 16, f->mi_rows);
   t.tc0 = f->tile_col_start_sb[tr.tile_col] * 16;
   t.tc1 = min(f->tile_col_start_sb[tr.tile_col + 1] * 16, f->mi_cols);
+#pragma unroll 1
   for (int r = t.tr0; r < t.tr1; r += 16)
+#pragma unroll 1
     for (int c = t.tc0; c < t.tc1; c += 16)
       // 64x64 -> 32x32 -> 16x16 in z-order (always split above 16x16)
+#pragma unroll 1
       for (int q = 0; q < 16; q++) {
         const int bx = ((q & 1) | ((q >> 1) & 2)) * 16, by = (((q >> 1) & 1) | ((q >> 2) & 2)) * 16;
-        encode_tree16(t, sh, c * 4 + bx, r * 4 + by);
+        encode_tree16<HBD>(t, sh, c * 4 + bx, r * 4 + by);
       }
 }
 
 #ifndef B200_EMU
-extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int n_tiles, void *stream) {
+extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int n_tiles, int high_bitdepth, void *stream) {
   if (n_tiles <= 0) return 0;
   static bool configured = false;
   if (!configured) {   // ask for the largest shared-memory carve-out: ~14 single-warp CTAs of ~15 KB per SM
-    cudaFuncSetAttribute(b200_rdo_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(b200_rdo_tile_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(b200_rdo_tile_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  b200_rdo_tile_kernel<<<n_tiles, kThreads, 0, (cudaStream_t)stream>>>(d_jobs, d_tiles);
+  if (high_bitdepth) b200_rdo_tile_kernel<true><<<n_tiles, kThreads, 0, (cudaStream_t)stream>>>(d_jobs, d_tiles);
+  else b200_rdo_tile_kernel<false><<<n_tiles, kThreads, 0, (cudaStream_t)stream>>>(d_jobs, d_tiles);
   return (int)cudaGetLastError();
 }
 #else
 static const B200RdoJob *g_emu_jobs;
 static const B200TileRef *g_emu_tiles;
-static void emu_entry(void *) { b200_rdo_tile_kernel(g_emu_jobs, g_emu_tiles); }
+static int g_emu_hbd;
+static void emu_entry(void *) { if (g_emu_hbd) b200_rdo_tile_kernel<true>(g_emu_jobs, g_emu_tiles); else b200_rdo_tile_kernel<false>(g_emu_jobs, g_emu_tiles); }
 extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *tiles, int n_tiles) {
   g_emu_jobs = jobs; g_emu_tiles = tiles;
+  g_emu_hbd = jobs[0].frame.bit_depth > 8;
   emu::launch(emu_entry, nullptr, (unsigned)n_tiles, kThreads);
   return 0;
 }

@@ -30,7 +30,8 @@ typedef struct B200TileRef {
 } B200TileRef;
 
 // Launch one CTA per tile on `stream` (cudaStream_t).  Returns a cudaError_t value.
-int b200_rdo_launch(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int n_tiles, void *stream);
+// high_bitdepth: all jobs of the launch are 10-bit (int64 butterflies) / 8-bit (int32 butterflies).
+int b200_rdo_launch(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int n_tiles, int high_bitdepth, void *stream);
 // Deblock (2 launches) + CDEF search (1 launch) for all jobs: grid.y = job.
 int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, void *stream);
 

@@ -87,6 +87,7 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   return r;
 }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 template <typename T> static inline T __ldcg(const T *p) { return *p; }

@@ -184,7 +184,9 @@ def transpose(stage, n):
             out[w].append((kind, c, d))
     return out
 
-def emit_fn(name, n, stages, f):
+def emit_fn(name, n, stages, f, wide=True):
+    """wide=True: half_btf evaluated in int64 (always exact).  wide=False: int32 multiply-accumulate, exact as long
+    as |w0*a + w1*b| < 2^31 - which holds for 8-bit video (see DESIGN.md 'int32 butterflies')."""
     f.write("TXFM_FN void %s(const int32_t *in, int32_t *out, const int32_t *cospi, int bit) {\n" % name)
     cur = ["in[%d]" % i for i in range(n)]
     for si, st in enumerate(stages):
@@ -209,7 +211,7 @@ def emit_fn(name, n, stages, f):
                 assert all(t[0] == 'cos' for t in terms) and len(terms) == 2, (name, si, d, terms)
                 parts = []
                 for (_, (s, k), w) in terms:
-                    parts.append("%s(int64_t)cospi[%d] * %s" % ("-" if s < 0 else "", k, cur[w]))
+                    parts.append("%s%scospi[%d] * %s" % ("-" if s < 0 else "", "(int64_t)" if wide else "", k, cur[w]))
                 expr = "(int32_t)((%s + %s + rnd) >> bit)" % (parts[0], parts[1])
             v = "s%d_%d" % (si, d)
             decl.append("  const int32_t %s = %s;\n" % (v, expr))
@@ -234,19 +236,25 @@ def generate(path):
             body_i = [transpose(s, n) for s in reversed(st)]
             for nm, body in (("gen_fdct%d" % n, body_f), ("gen_idct%d" % n, body_i)):
                 import io
-                buf = io.StringIO()
-                emit_fn(nm, n, body, buf)
-                txt = buf.getvalue().replace("{\n", "{\n  const int64_t rnd = (int64_t)1 << (bit - 1);\n", 1)
-                f.write(txt)
+                for wide in (True, False):
+                    if not wide and n == 32:
+                        continue
+                    buf = io.StringIO()
+                    emit_fn(nm + ("" if wide else "_w32"), n, body, buf, wide)
+                    ty = "int64_t" if wide else "int32_t"
+                    txt = buf.getvalue().replace("{\n", "{\n  const %s rnd = (%s)1 << (bit - 1);\n" % (ty, ty), 1)
+                    f.write(txt)
         for n in (8, 16):
             st = adst_stages(n)
             body_i = [transpose(s, n) for s in reversed(st)]
             for nm, body in (("gen_fadst%d" % n, st), ("gen_iadst%d" % n, body_i)):
                 import io
-                buf = io.StringIO()
-                emit_fn(nm, n, body, buf)
-                txt = buf.getvalue().replace("{\n", "{\n  const int64_t rnd = (int64_t)1 << (bit - 1);\n", 1)
-                f.write(txt)
+                for wide in (True, False):
+                    buf = io.StringIO()
+                    emit_fn(nm + ("" if wide else "_w32"), n, body, buf, wide)
+                    ty = "int64_t" if wide else "int32_t"
+                    txt = buf.getvalue().replace("{\n", "{\n  const %s rnd = (%s)1 << (bit - 1);\n" % (ty, ty), 1)
+                    f.write(txt)
         f.write("#endif  // TXFM1D_GEN_H_\n")
 
 if __name__ == "__main__":
