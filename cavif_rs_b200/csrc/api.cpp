@@ -147,7 +147,8 @@ struct FrameJob {
   B200Mi *d_mi = nullptr;
   uint16_t *d_eob[3] = {nullptr, nullptr, nullptr};
   int16_t *d_coef[3] = {nullptr, nullptr, nullptr};
-  uint8_t *d_decoded = nullptr;
+  B200BlockDec *d_dec[3] = {nullptr, nullptr, nullptr};
+  uint32_t *d_satd[3] = {nullptr, nullptr, nullptr};
   int8_t *d_cdef = nullptr;
   uint16_t *d_fin[3] = {nullptr, nullptr, nullptr};   // only for the test seam
   int8_t *h_cdef = nullptr;
@@ -161,6 +162,7 @@ struct FrameJob {
   size_t n_px() const { return n_mi() * 16; }
   size_t n_coef() const { return (size_t)f.sb_rows * f.sb_cols * B200_SB_COEFS; }
   size_t n_sb() const { return (size_t)f.sb_rows * f.sb_cols; }
+  size_t n_blk(int lv) const { return (size_t)(f.mi_rows >> lv) * (f.mi_cols >> lv); }
 };
 
 size_t job_dev_bytes(const FrameJob &j, bool own_src) {
@@ -171,8 +173,9 @@ size_t job_dev_bytes(const FrameJob &j, bool own_src) {
   b += align256(j.n_mi() * sizeof(B200Mi));
   b += P * align256(j.n_mi() * 2);
   b += P * align256(j.n_coef() * 2);
-  b += align256(j.n_mi()) + align256(j.n_sb());
-  return b + 4096;
+  b += align256(j.n_sb());
+  for (int lv = 0; lv < 3; lv++) b += align256(j.n_blk(lv) * sizeof(B200BlockDec)) + align256(j.n_blk(lv) * 26 * 4);
+  return b + 8192;
 }
 size_t job_pin_bytes(const FrameJob &j) {
   const int P = j.f.planes;
@@ -189,7 +192,10 @@ void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
     j.h_coef[p] = pin.take<int16_t>(j.n_coef());
   }
   j.d_mi = dev.take<B200Mi>(j.n_mi());
-  j.d_decoded = dev.take<uint8_t>(j.n_mi());
+  for (int lv = 0; lv < 3; lv++) {
+    j.d_dec[lv] = dev.take<B200BlockDec>(j.n_blk(lv));
+    j.d_satd[lv] = dev.take<uint32_t>(j.n_blk(lv) * 26);
+  }
   j.d_cdef = dev.take<int8_t>(j.n_sb());
   j.h_cdef = pin.take<int8_t>(j.n_sb());
   j.h_mi = pin.take<B200Mi>(j.n_mi());
@@ -251,21 +257,24 @@ int run_rdo_and_fetch(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Are
       const int q = p < j.f.planes ? p : 0;
       r.src[p] = j.d_src[q]; r.rec[p] = j.d_rec[q]; r.eob[p] = j.d_eob[q]; r.coef[p] = j.d_coef[q];
     }
-    r.mi = j.d_mi; r.decoded = j.d_decoded;
+    r.mi = j.d_mi;
+    for (int lv = 0; lv < 3; lv++) { r.dec[lv] = j.d_dec[lv]; r.satd[lv] = j.d_satd[lv]; }
     r.cdef_idx = j.d_cdef;
     for (int p = 0; p < 3; p++) r.fin[p] = j.d_fin[p < j.f.planes ? p : 0];
     for (int tr = 0; tr < j.f.tile_rows; tr++)
       for (int tc = 0; tc < j.f.tile_cols; tc++) tiles.push_back(B200TileRef{(int32_t)i, (int16_t)tr, (int16_t)tc});
-    CU(cudaMemsetAsync(j.d_decoded, 0, j.n_mi(), c.stream));
   }
   B200RdoJob *d_jobs = dev.take<B200RdoJob>(hj.size());
   B200TileRef *d_tiles = dev.take<B200TileRef>(tiles.size());
   CU(cudaMemcpyAsync(d_jobs, hj.data(), hj.size() * sizeof(B200RdoJob), cudaMemcpyHostToDevice, c.stream));
   CU(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(B200TileRef), cudaMemcpyHostToDevice, c.stream));
   CU(cudaEventRecord(c.ev[1], c.stream));
-  const int le = b200_rdo_launch(d_jobs, d_tiles, (int)tiles.size(), jobs[0]->f.bit_depth > 8, c.stream);   // one depth per call
+  int max_blocks4 = 0;
+  for (FrameJob *jp : jobs) max_blocks4 = std::max(max_blocks4, (int)jp->n_mi());
+  const int le = b200_rdo_launch(d_jobs, (int)jobs.size(), d_tiles, (int)tiles.size(), max_blocks4, jobs[0]->f.bit_depth > 8,
+                                 c.stream);   // one bit depth per call
   if (le != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("RDO kernel launch failed: ") + cudaGetErrorString((cudaError_t)le));
-  g_launches += 1;
+  g_launches += 8;   // 3 x (SATD + analysis) + partition decision + reconstruction
   CU(cudaEventRecord(c.ev[2], c.stream));
   if (pre_filter_rec) {   // test seam: reconstruction before the in-loop filters
     pre_filter_rec->clear();
@@ -705,7 +714,8 @@ int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h,
 
 // ---- test seam: run the device hot path on caller-provided coded planes and frame description -----
 int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi, uint16_t *const eob[3], int16_t *const coef[3],
-                    uint16_t *const rec[3], uint16_t *const deblocked[3], uint16_t *const fin[3], int8_t *cdef_idx) {
+                    uint16_t *const rec[3], uint16_t *const deblocked[3], uint16_t *const fin[3], int8_t *cdef_idx,
+                    B200BlockDec *const dec[3], uint32_t *const satd[3]) {
   if (!f || !src || !mi) return fail(B200AVIF_INVALID_ARGUMENT, "null argument");
   if (b200avif_device_count() <= 0) return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
   FrameJob job;
@@ -726,11 +736,19 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
     CU(cudaMemsetAsync(job.d_coef[p], 0, job.n_coef() * 2, c.stream));
     CU(cudaMemsetAsync(job.d_eob[p], 0, job.n_mi() * 2, c.stream));
   }
+  for (int lv = 0; lv < 3; lv++) {   // levels outside the partition range are not analysed: keep them comparable
+    CU(cudaMemsetAsync(job.d_dec[lv], 0, job.n_blk(lv) * sizeof(B200BlockDec), c.stream));
+    CU(cudaMemsetAsync(job.d_satd[lv], 0, job.n_blk(lv) * 26 * 4, c.stream));
+  }
   std::vector<FrameJob *> jobs{&job};
   std::vector<std::vector<uint16_t>> deb, pre;
   if (int e = run_rdo_and_fetch(c, jobs, c.dev, c.pin, true, &deb, &pre)) return e;
   memcpy(mi, job.h_mi, job.n_mi() * sizeof(B200Mi));
   if (cdef_idx) memcpy(cdef_idx, job.h_cdef, job.n_sb());
+  for (int lv = 0; lv < 3; lv++) {
+    if (dec && dec[lv]) CU(cudaMemcpy(dec[lv], job.d_dec[lv], job.n_blk(lv) * sizeof(B200BlockDec), cudaMemcpyDeviceToHost));
+    if (satd && satd[lv]) CU(cudaMemcpy(satd[lv], job.d_satd[lv], job.n_blk(lv) * 26 * 4, cudaMemcpyDeviceToHost));
+  }
   for (int p = 0; p < job.f.planes; p++) {
     if (eob && eob[p]) memcpy(eob[p], job.h_eob[p], job.n_mi() * 2);
     if (coef && coef[p]) memcpy(coef[p], job.h_coef[p], job.n_coef() * 2);

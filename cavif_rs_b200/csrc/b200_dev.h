@@ -17,10 +17,11 @@ int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h,
                         uint16_t *const planes[4], int *any_alpha);
 // Test seam: run the device hot path (RDO kernel, then deblock + CDEF search) on host-provided CODED planes
 // (mi_rows*4 x mi_cols*4 uint16, stride mi_cols*4).  Returns the block records, the reconstruction before the
-// in-loop filters (rec), after deblocking (deblocked), after CDEF (fin) and the per-superblock CDEF index.
+// in-loop filters (rec), after deblocking (deblocked), after CDEF (fin), the per-superblock CDEF index and the
+// open-loop analysis outputs per level (decisions, SATD tables).
 int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi, uint16_t *const eob[3],
                     int16_t *const coef[3], uint16_t *const rec[3], uint16_t *const deblocked[3], uint16_t *const fin[3],
-                    int8_t *cdef_idx);
+                    int8_t *cdef_idx, B200BlockDec *const dec[3], uint32_t *const satd[3]);
 #ifdef __cplusplus
 }
 #endif

@@ -1,24 +1,26 @@
-// AV1 intra rate-distortion search on the device.
+// AV1 intra rate-distortion search on the device, in three stages (v4):
 //
-// Mapping (v2): ONE WARP PER TILE.  Tiles are the unit with no cross dependencies (entropy contexts
-// reset, no prediction across tile edges); inside a tile every block depends on its left/top
-// reconstruction, so a tile is a serial chain.  A batch of images gives thousands of tiles, i.e.
-// thousands of independent warps (64 x 1080p -> 2048 tiles -> ~14 resident warps per SM), and a
-// single-warp CTA needs no block-level barriers at all.  Inside the warp the 32 lanes are kept busy by
-// evaluating G = 32/N candidates of an NxN block at once ("lane group" g = lane / N owns one candidate,
-// lane l = lane % N owns column l / row l of its transform): residual, forward transform, quantiser,
-// static-CDF rate, dequantiser, inverse transform, reconstruction and SSE run for G candidates in
-// lock-step, with the 1-D butterflies held in registers and only the transpose going through shared
-// memory.  Candidates sharing a lane batch are ordered so that they run the same transform kernels
-// (same transform type, different prediction modes), which keeps the warp convergent.
+//   A. ANALYSIS (open loop, embarrassingly parallel).  Every block of every level (4x4, 8x8, 16x16) of every image is
+//      analysed independently, predicting from SOURCE neighbours: SATD ranking of the 13 intra modes
+//      (b200_satd_kernel: one thread per (block, plane group)), then full trials of the top-2 modes x transform types
+//      and of the top-2 chroma modes (b200_analyze_kernel: one warp per block, lane-batched candidates: lane group
+//      g = lane / N owns one candidate, lane l = lane % N owns column l / row l of its transform; butterflies in
+//      registers, transpose through shared memory, quantiser / rate / dequantiser on the row, SSE by shuffles).
+//   B. PARTITION DECISION (b200_decide_kernel: one thread per 16x16 region) from the analysed RD costs.
+//   C. RECONSTRUCTION (closed loop, b200_recon_kernel: one warp per TILE): the only stage that needs reconstructed
+//      neighbours; one trial per decided block and plane, Y/U/V batched over the lane groups.
 //
-// Replaces rav1e's encode_tile / rdo_mode_decision / encode_tx_block [EXT: crates.io rav1e 0.8.1],
-// which the reference reaches only through encode_to_av1
-// (/root/reference/ravif/src/av1encoder.rs:749-771).  The bit-exact CPU restatement of THIS file is
-// oracle/av1_encode.c; tests/test_gpu_parity.py compares records and reconstruction.
+// Only stage C is a serial chain (a tile's blocks depend on their left/top reconstruction); stages A/B carry >95 % of
+// the arithmetic and scale with the number of blocks in the batch.
 //
-// No tensor cores on purpose: the work is 4..16-point integer butterflies with normative rounding at
-// every stage (BASELINE.json north_star).
+// Replaces rav1e's encode_tile / rdo_mode_decision / encode_tx_block [EXT: crates.io rav1e 0.8.1], which the
+// reference reaches only through encode_to_av1 (/root/reference/ravif/src/av1encoder.rs:749-771).  rav1e searches
+// closed-loop inside one serial chain per tile; the open-loop split is this implementation's GPU-first choice
+// (encoder freedom; the bitstream and the reconstruction stay exact).  The bit-exact CPU restatement of THIS file is
+// oracle/av1_encode.c; tests/test_gpu_parity.py compares every stage.
+//
+// No tensor cores on purpose: the work is 4..16-point integer butterflies with normative rounding at every stage
+// (BASELINE.json north_star).
 #ifdef B200_EMU
 #include "cuda_emu.h"
 #else
@@ -56,17 +58,6 @@ __constant__ const uint8_t dv_tx_types[5] = {TX_DCT_DCT, TX_ADST_DCT, TX_DCT_ADS
 __constant__ const uint8_t dv_bw4[22] = {1, 1, 2, 2, 2, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 1, 4, 2, 8, 4, 16};
 __constant__ const uint8_t dv_bh4[22] = {1, 2, 1, 2, 4, 2, 4, 8, 4, 8, 16, 8, 16, 32, 16, 32, 4, 1, 8, 2, 16, 4};
 
-template <int PX>
-struct CandT {
-  long long cost;
-  B200Mi mi;
-  uint16_t eob[3];
-  int16_t qc[3][PX];
-  uint16_t recon[3][PX];
-};
-typedef CandT<256> Cand;      // up to 16x16
-typedef CandT<64> Cand8;      // an 8x8 candidate parked while its four 4x4 children are tried
-
 struct Shared {
   uint16_t src[3][256];
   uint16_t above[3][kEdge], left[3][kEdge];
@@ -75,8 +66,6 @@ struct Shared {
   alignas(16) uint8_t lev[800];   // per group (N+4)^2 padded |level| map (rate contexts)
   int16_t qc[512];             // per group n*n quantised levels in scan order
   uint16_t rec[512];           // per group n*n reconstruction
-  Cand cur, held16;
-  Cand8 held8;
   uint32_t taskD[4], taskR[4];
   uint16_t taskE[4];
 };
@@ -89,7 +78,6 @@ struct TileCtx {
   B200Mi *mi;
   uint16_t *eob[3];
   int16_t *coef[3];
-  uint8_t *decoded;
   int stride;
   int tr0, tr1, tc0, tc1;
 };
@@ -122,19 +110,18 @@ __device__ __forceinline__ void warp_argmin(long long &J, int &idx) {
   }
 }
 
-// ---- edges (AV1 spec 7.11.2, intra edge filter disabled) ----------------------------------------
-__device__ __noinline__ void build_edges(const TileCtx &t, Shared &sh, int plane, int x, int y, int n, int &ha_out, int &hl_out) {
+// ---- edges (AV1 spec 7.11.2, intra edge filter disabled) from plane `r` (source in the analysis, reconstruction in
+// the final pass) into sh.above/left[slot]; top-right / bottom-left availability = static coding order predicate
+__device__ __noinline__ void build_edges(const TileCtx &t, Shared &sh, const uint16_t *r, int slot, int x, int y, int n, int &ha_out, int &hl_out) {
   const B200Frame *f = t.f;
-  const uint16_t *r = t.rec[plane];
   const int st = t.stride, lane = lane_id();
   const int mi_r = y >> 2, mi_c = x >> 2, n4 = n >> 2;
   const int ha = mi_r > t.tr0, hl = mi_c > t.tc0;
   const int max_x = f->mi_cols * 4 - 1, max_y = f->mi_rows * 4 - 1;
   const int base = 1 << (f->bit_depth - 1);
-  int have_ar = 0, have_bl = 0;
-  if (ha && mi_c + n4 < t.tc1) have_ar = t.decoded[(mi_r - 1) * f->mi_cols + mi_c + n4];
-  if (hl && mi_r + n4 < t.tr1) have_bl = t.decoded[(mi_r + n4) * f->mi_cols + mi_c - 1];
-  uint16_t *A = sh.above[plane] + EOFF, *L = sh.left[plane] + EOFF;
+  const int have_ar = ha && b200_unit_before(mi_r - 1, mi_c + n4, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
+  const int have_bl = hl && b200_unit_before(mi_r + n4, mi_c - 1, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
+  uint16_t *A = sh.above[slot] + EOFF, *L = sh.left[slot] + EOFF;
   for (int i = lane; i < 2 * n; i += 32) {
     uint16_t a, l;
     if (!ha && hl) a = r[y * st + x - 1];
@@ -497,42 +484,6 @@ __device__ __noinline__ void predict_block(int mode, int lg, const uint16_t *abo
   for (int p = lane_id(); p < n * n; p += 32) dst[p] = (uint16_t)pred_px(mode, n, p >> lg, p & (n - 1), A, L, dc);
 }
 
-// sum of |4x4 Hadamard| over the 4x4 sub-blocks of planes [0, planes): pred/src are [plane][n*n]; one lane per
-// (plane, sub-block); returns the luma sum and the chroma (U+V) sum to every lane
-__device__ __noinline__ void satd_planes(const uint16_t *src, const uint16_t *pred, int lg, int planes, uint32_t &sy, uint32_t &suv) {
-  const int n = 1 << lg, nb = n >> 2, nbb = nb * nb, ntask = planes * nbb, lane = lane_id();
-  uint32_t y = 0, uv = 0;
-#pragma unroll 1
-  for (int task = lane; task < ((ntask + 31) & ~31); task += 32) {
-    uint32_t total = 0;
-    int p = 0;
-    if (task < ntask) {
-      p = task / nbb;
-      const int sb = task - p * nbb;
-      const int by = (sb >> (lg - 2)) * 4, bx = (sb & (nb - 1)) * 4;
-      const uint16_t *s = src + p * 256 + by * n + bx, *q = pred + p * 256 + by * n + bx;
-      int d[16], tt[16];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) d[i * 4 + j] = (int)s[i * n + j] - (int)q[i * n + j];
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int a = d[i * 4] + d[i * 4 + 1], b = d[i * 4] - d[i * 4 + 1], c = d[i * 4 + 2] + d[i * 4 + 3], e = d[i * 4 + 2] - d[i * 4 + 3];
-        tt[i * 4] = a + c; tt[i * 4 + 1] = b + e; tt[i * 4 + 2] = a - c; tt[i * 4 + 3] = b - e;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int a = tt[j] + tt[4 + j], b = tt[j] - tt[4 + j], c = tt[8 + j] + tt[12 + j], e = tt[8 + j] - tt[12 + j];
-        total += (uint32_t)(abs(a + c) + abs(b + e) + abs(a - c) + abs(b - e));
-      }
-    }
-    y += warp_sum(p == 0 ? total : 0);
-    if (planes > 1) uv += warp_sum(p == 0 ? 0 : total);
-  }
-  sy = y; suv = uv;
-}
-
 // top-2 of 13 mode costs held by lanes 0..12 (kInf when not allowed): lowest cost first, ties -> lowest index
 __device__ __noinline__ void rank_top2(long long c, int &m0, int &m1) {
   const int lane = lane_id();
@@ -546,52 +497,47 @@ __device__ __noinline__ void rank_top2(long long c, int &m0, int &m1) {
   m1 = j2 == kInf ? -1 : i2;
 }
 
-// Evaluate one block (all planes) at (x, y), size n = 1 << lg (4 | 8 | 16): result in sh.cur.
+__device__ __forceinline__ void tile_of_unit(const B200Frame *f, int mi_r, int mi_c, TileCtx &t) {
+  int r = 0, c = 0;
+  while (f->tile_row_start_sb[r + 1] * 16 <= mi_r) r++;
+  while (f->tile_col_start_sb[c + 1] * 16 <= mi_c) c++;
+  t.tr0 = f->tile_row_start_sb[r] * 16; t.tr1 = min(f->tile_row_start_sb[r + 1] * 16, f->mi_rows);
+  t.tc0 = f->tile_col_start_sb[c] * 16; t.tc1 = min(f->tile_col_start_sb[c + 1] * 16, f->mi_cols);
+}
+__device__ __forceinline__ void ctx_from_job(const B200RdoJob &job, TileCtx &t) {
+  t.f = &job.frame; t.rt = job.rate;
+  for (int p = 0; p < 3; p++) { t.src[p] = job.src[p]; t.rec[p] = job.rec[p]; t.eob[p] = job.eob[p]; t.coef[p] = job.coef[p]; }
+  t.mi = job.mi; t.stride = job.frame.mi_cols * 4;
+}
+
+// ---- stage A: analysis of one block by one warp (oracle orc_analyze_block, minus the SATD table) ---------------
 template <bool HBD>
-__device__ __noinline__ void trial_block(const TileCtx &t, Shared &sh, int x, int y, int lg) {
+__device__ __noinline__ void analyze_block(const TileCtx &t, Shared &sh, int x, int y, int lg, const uint32_t *satd, B200BlockDec *out) {
   const int n = 1 << lg, N2 = n * n, G = 32 >> lg;
   const B200Frame *f = t.f;
   const B200RateTables *rt = t.rt;
   const int lane = lane_id(), g = lane >> lg;
   const int planes = f->planes, bd = f->bit_depth;
-  const int mi_r = y >> 2, mi_c = x >> 2;
-  const int avail_u = mi_r > t.tr0, avail_l = mi_c > t.tc0;
-  uint16_t *scratch = reinterpret_cast<uint16_t *>(sh.buf);     // 3 x 256 predictions during the SATD stage
-  // ---- stage source block and edges; clear the padded level maps
+  // ---- stage source block and SOURCE edges; clear the padded level maps
   for (int p = 0; p < planes; p++)
 #pragma unroll 1
     for (int q = lane; q < N2; q += 32) sh.src[p][q] = t.src[p][(y + (q >> lg)) * t.stride + x + (q & (n - 1))];
   for (int i = lane; i < 200; i += 32) reinterpret_cast<uint32_t *>(sh.lev)[i] = 0;
   int ha = 0, hl = 0;
-  for (int p = 0; p < planes; p++) build_edges(t, sh, p, x, y, n, ha, hl);
+  for (int p = 0; p < planes; p++) build_edges(t, sh, t.src[p], p, x, y, n, ha, hl);
   __syncwarp();
-  // ---- SATD of every mode: predictions of all planes into scratch, one lane per (plane, 4x4 sub-block)
-  const int am = avail_u ? t.mi[(mi_r - 1) * f->mi_cols + mi_c].y_mode : DC_PRED;
-  const int lm = avail_l ? t.mi[mi_r * f->mi_cols + mi_c - 1].y_mode : DC_PRED;
-  const uint16_t *ymode_cost = rt->y_mode[dv_intra_mode_context[am]][dv_intra_mode_context[lm]];
-  long long my_ycost = kInf;       // lane m (< 13) keeps the luma cost of mode m
-  uint32_t my_uvsatd = 0;          // lane m keeps the chroma (U+V) SATD of mode m
-  {
-    const int allowed = f->y_mode_mask | (planes > 1 ? f->uv_mode_mask : 0);
-#pragma unroll 1
-    for (int m = 0; m < 13; m++) {
-      if (!((allowed >> m) & 1)) continue;
-      for (int p = 0; p < planes; p++) predict_block(m, lg, sh.above[p], sh.left[p], ha, hl, bd, scratch + p * 256);
-      __syncwarp();
-      uint32_t sy, suv;
-      satd_planes(&sh.src[0][0], scratch, lg, planes, sy, suv);
-      if (lane == m) {
-        if ((f->y_mode_mask >> m) & 1)
-          my_ycost = (long long)sy * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, m, n)) >> 8);
-        my_uvsatd = suv;
-      }
-      __syncwarp();
-    }
+  // ---- ranking from the SATD table (context-0 mode rates)
+  const uint16_t *ymode_cost = rt->y_mode[0][0];
+  long long my_ycost = kInf;
+  uint32_t my_uvsatd = 0;
+  if (lane < 13) {
+    if ((f->y_mode_mask >> lane) & 1)
+      my_ycost = (long long)satd[lane] * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, lane, n)) >> 8);
+    my_uvsatd = satd[13 + lane];
   }
   int m0, m1;
   rank_top2(my_ycost, m0, m1);
-  // ---- luma full trials: candidate c = k * 5 + ti (mode rank k, transform type index ti); lane batches pair
-  //      the two modes on the same transform type so that a batch runs identical transform kernels
+  // ---- luma full trials: candidate c = k * 5 + ti; lane batches pair the two modes on the same transform type
   int first_t = -1;
   for (int k = 0; k < 5; k++) if ((f->tx_type_mask >> k) & 1) { first_t = k; break; }
   predict_block(m0 >= 0 ? m0 : 0, lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred);
@@ -601,11 +547,11 @@ __device__ __noinline__ void trial_block(const TileCtx &t, Shared &sh, int x, in
   int bestC = 1 << 20, bestEob = 0;
 #pragma unroll 1
   for (int b = 0; b * G < 10; b++) {
-    const int ci = b * G + g;                 // position in the (ti major, k minor) candidate order
+    const int ci = b * G + g;
     const int ti = ci >> 1, k = ci & 1;
     const int m = k == 0 ? m0 : m1;
     const bool ok = ti < 5 && m >= 0 && ((f->tx_type_mask >> ti) & 1) && (f->rdo_tx_decision || ti == first_t);
-    if (!__ballot_sync(FULL, ok)) continue;   // nothing to do in this batch (warp-uniform)
+    if (!__ballot_sync(FULL, ok)) continue;
     const TrialOut r = trial_dispatch<HBD>(n, t, sh, 0, sh.src[0], sh.pred + (ok ? k : 0) * 256, dv_tx_types[ok ? ti : 0],
                                            ok ? m : (m0 >= 0 ? m0 : 0));
     long long wj = kInf;
@@ -614,21 +560,16 @@ __device__ __noinline__ void trial_block(const TileCtx &t, Shared &sh, int x, in
     warp_argmin(wj, wc);
     if (wj < bestJ || (wj == bestJ && wc < bestC)) {
       bestJ = wj; bestC = wc;
-      const int wci = (wc % 5) * 2 + wc / 5;           // winner's position in the batch order
-      const int wg = wci - b * G;                      // its lane group
+      const int wg = (wc % 5) * 2 + wc / 5 - b * G;
       bestEob = __shfl_sync(FULL, r.eob, wg << lg);
-#pragma unroll 1
-      for (int p = lane; p < N2; p += 32) { sh.cur.qc[0][p] = sh.qc[wg * N2 + p]; sh.cur.recon[0][p] = sh.rec[wg * N2 + p]; }
     }
-    __syncwarp();
   }
   const int best_mode = bestC / 5 == 0 ? m0 : m1;
   const int best_tt = dv_tx_types[bestC % 5];
   long long total = bestJ;
   int uv_best = DC_PRED, eobU = 0, eobV = 0;
   if (planes > 1) {
-    // ---- chroma: rank uv modes by SATD + rate, full trial of the top two on both planes
-    const uint16_t *uvcost = rt->uv_mode[1][best_mode];   // cfl_allowed = 1 for n <= 32
+    const uint16_t *uvcost = rt->uv_mode[1][best_mode];
     long long my_uvcost = kInf;
     if (lane < 13 && ((f->uv_mode_mask >> lane) & 1))
       my_uvcost = (long long)my_uvsatd * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, uvcost, lane, n)) >> 8);
@@ -641,7 +582,6 @@ __device__ __noinline__ void trial_block(const TileCtx &t, Shared &sh, int x, in
       const int k = (ci >> 1) & 1, p = 1 + (ci & 1);
       const int m = k == 0 ? u0 : u1;
       const bool ok = ci < 4 && m >= 0;
-      // predictions of the (mode rank, plane) pairs of this batch: slot = candidate index within the batch
 #pragma unroll 1
       for (int cc = b * G; cc < min((b + 1) * G, 4); cc++) {
         const int mm = (cc >> 1) == 0 ? u0 : u1, pp = 1 + (cc & 1);
@@ -651,158 +591,253 @@ __device__ __noinline__ void trial_block(const TileCtx &t, Shared &sh, int x, in
       const TrialOut r = trial_dispatch<HBD>(n, t, sh, p, sh.src[p], sh.pred + (ok ? g : 0) * N2, chroma_tx_type(m >= 0 ? m : 0), best_mode);
       if (ok && (lane & (n - 1)) == 0) { sh.taskD[ci] = r.sse; sh.taskR[ci] = r.rate; sh.taskE[ci] = (uint16_t)r.eob; }
       __syncwarp();
-      // mode ranks fully evaluated by this batch: both planes present
       for (int kk = 0; kk < 2; kk++) {
         const int cU = kk * 2, cV = kk * 2 + 1;
-        if (cV < b * G || cV >= (b + 1) * G) continue;     // (cU, cV) always land in the same batch (G even)
+        if (cV < b * G || cV >= (b + 1) * G) continue;
         const int mm = kk == 0 ? u0 : u1;
         if (mm < 0) continue;
         const long long J = rd_cost(f, (unsigned long long)sh.taskD[cU] + sh.taskD[cV],
                                     sh.taskR[cU] + sh.taskR[cV] + mode_rate(rt, uvcost, mm, n));
-        if (J < bestCj) {
-          bestCj = J; uv_best = mm; eobU = sh.taskE[cU]; eobV = sh.taskE[cV];
-          const int gU = cU - b * G, gV = cV - b * G;
-#pragma unroll 1
-          for (int q = lane; q < N2; q += 32) {
-            sh.cur.qc[1][q] = sh.qc[gU * N2 + q]; sh.cur.recon[1][q] = sh.rec[gU * N2 + q];
-            sh.cur.qc[2][q] = sh.qc[gV * N2 + q]; sh.cur.recon[2][q] = sh.rec[gV * N2 + q];
-          }
-        }
+        if (J < bestCj) { bestCj = J; uv_best = mm; eobU = sh.taskE[cU]; eobV = sh.taskE[cV]; }
       }
       __syncwarp();
     }
     total += bestCj;
   }
-  // ---- skip flag + totals
   if (lane == 0) {
-    B200Mi m;
-    m.bsize = (uint8_t)(n == 4 ? BLOCK_4X4 : n == 8 ? BLOCK_8X8 : BLOCK_16X16);
-    m.y_mode = (uint8_t)best_mode;
-    m.uv_mode = (uint8_t)uv_best;
-    m.angle = 3 | (3 << 4);
-    m.tx_size = (uint8_t)txs_of(n);
-    m.tx_type = (uint8_t)best_tt;
-    m.flags = 0;
-    m.cfl = 0;
     const int all_zero = bestEob == 0 && (planes == 1 || (eobU == 0 && eobV == 0));
-    const int a = avail_u ? (t.mi[(mi_r - 1) * f->mi_cols + mi_c].flags & 1) : 0;
-    const int l = avail_l ? (t.mi[mi_r * f->mi_cols + mi_c - 1].flags & 1) : 0;
-    total += ((long long)f->lambda_q8 * rt->skip[a + l][all_zero]) >> 8;
-    if (all_zero) m.flags |= 1;
-    sh.cur.mi = m;
-    sh.cur.cost = total;
-    sh.cur.eob[0] = (uint16_t)bestEob; sh.cur.eob[1] = (uint16_t)eobU; sh.cur.eob[2] = (uint16_t)eobV;
+    total += ((long long)f->lambda_q8 * rt->skip[0][all_zero]) >> 8;
+    B200BlockDec d;
+    d.cost = total; d.y_mode = (uint8_t)best_mode; d.tx_type = (uint8_t)best_tt; d.uv_mode = (uint8_t)uv_best;
+    d.pad[0] = d.pad[1] = d.pad[2] = d.pad[3] = d.pad[4] = 0;
+    *out = d;
   }
   __syncwarp();
 }
 
-template <typename D, typename S>
-__device__ __noinline__ void copy_cand(D &dst, const S &src, int lg, int planes) {
-  const int lane = lane_id(), n2 = 1 << (2 * lg);
-  for (int p = 0; p < planes; p++)
-#pragma unroll 1
-    for (int q = lane; q < n2; q += 32) { dst.qc[p][q] = src.qc[p][q]; dst.recon[p][q] = src.recon[p][q]; }
-  if (lane == 0) { dst.cost = src.cost; dst.mi = src.mi; dst.eob[0] = src.eob[0]; dst.eob[1] = src.eob[1]; dst.eob[2] = src.eob[2]; }
-  __syncwarp();
-}
-
-template <typename C>
-__device__ __noinline__ void commit_block(const TileCtx &t, const C &cd, int x, int y, int lg) {
+// ---- stage C: closed-loop reconstruction of one decided block by one warp (oracle reconstruct_block) ----------------
+template <bool HBD>
+__device__ __noinline__ void reconstruct_block(const TileCtx &t, Shared &sh, int x, int y, int lg) {
+  const int n = 1 << lg, N2 = n * n, G = 32 >> lg;
   const B200Frame *f = t.f;
-  const int lane = lane_id(), n = 1 << lg, n2 = n * n, planes = f->planes;
+  const int lane = lane_id(), g = lane >> lg;
+  const int planes = f->planes, bd = f->bit_depth;
   const int mi_r = y >> 2, mi_c = x >> 2, n4 = n >> 2;
-  const long long coff = b200_coef_offset(f, mi_r, mi_c);
+  const B200Mi m = t.mi[mi_r * f->mi_cols + mi_c];
   for (int p = 0; p < planes; p++)
 #pragma unroll 1
-    for (int q = lane; q < n2; q += 32) {
-      t.rec[p][(y + (q >> lg)) * t.stride + x + (q & (n - 1))] = cd.recon[p][q];
-      t.coef[p][coff + q] = cd.qc[p][q];
-    }
-  if (lane < planes) t.eob[lane][mi_r * f->mi_cols + mi_c] = cd.eob[lane];
-  for (int i = lane; i < n4 * n4; i += 32) {
-    const int idx = (mi_r + (i >> (lg - 2))) * f->mi_cols + mi_c + (i & (n4 - 1));
-    t.mi[idx] = cd.mi;
-    t.decoded[idx] = 1;
-  }
+    for (int q = lane; q < N2; q += 32) sh.src[p][q] = t.src[p][(y + (q >> lg)) * t.stride + x + (q & (n - 1))];
+  for (int i = lane; i < 200; i += 32) reinterpret_cast<uint32_t *>(sh.lev)[i] = 0;
+  int ha = 0, hl = 0;
+  for (int p = 0; p < planes; p++) build_edges(t, sh, t.rec[p], p, x, y, n, ha, hl);
   __syncwarp();
-}
-
-__device__ __noinline__ long long partition_cost(const TileCtx &t, int mi_r, int mi_c, int n, int split) {
-  const B200Frame *f = t.f;
-  const int bsl = ilog2_dev(n) - 2;
-  const int hbs = n >> 3;
-  const int has_rows = (mi_r + hbs) < f->mi_rows, has_cols = (mi_c + hbs) < f->mi_cols;
-  if (!has_rows || !has_cols) return 0;
-  const int au = mi_r > t.tr0, al = mi_c > t.tc0;
-  const int above = au && ilog2_dev(dv_bw4[t.mi[(mi_r - 1) * f->mi_cols + mi_c].bsize]) < bsl;
-  const int left = al && ilog2_dev(dv_bh4[t.mi[mi_r * f->mi_cols + mi_c - 1].bsize]) < bsl;
-  const int ctx = (bsl - 1) * 4 + left * 2 + above;
-  return ((long long)f->lambda_q8 * t.rt->partition[ctx][split ? 3 : 0]) >> 8;
-}
-
-// 8x8 node: NONE vs four 4x4 (oracle encode_tree at n = 8).  Returns the cost; frame state holds the winner.
-template <bool HBD>
-__device__ long long encode_tree8(const TileCtx &t, Shared &sh, int x, int y) {
-  const B200Frame *f = t.f;
-  const int mi_r = y >> 2, mi_c = x >> 2;
-  const bool can_split = f->partition_min < 8;
-  trial_block<HBD>(t, sh, x, y, 3);
-  const long long j_none = sh.cur.cost + partition_cost(t, mi_r, mi_c, 8, 0);
-  if (!can_split) { commit_block(t, sh.cur, x, y, 3); return j_none; }
-  copy_cand(sh.held8, sh.cur, 3, f->planes);
-  long long j_split = partition_cost(t, mi_r, mi_c, 8, 1);
+  const long long coff = b200_coef_offset(f, mi_r, mi_c);
+  int any = 0;
 #pragma unroll 1
-  for (int k = 0; k < 4; k++) {
-    const int xx = x + (k & 1) * 4, yy = y + (k >> 1) * 4;
-    trial_block<HBD>(t, sh, xx, yy, 2);
-    j_split += sh.cur.cost;
-    commit_block(t, sh.cur, xx, yy, 2);
-  }
-  if (j_none <= j_split) { commit_block(t, sh.held8, x, y, 3); return j_none; }
-  return j_split;
-}
-
-// 16x16 node
-template <bool HBD>
-__device__ long long encode_tree16(const TileCtx &t, Shared &sh, int x, int y) {
-  const B200Frame *f = t.f;
-  const int W = f->mi_cols * 4, H = f->mi_rows * 4;
-  if (x >= W || y >= H) return 0;
-  const int mi_r = y >> 2, mi_c = x >> 2;
-  const bool inside = (x + 16 <= W) && (y + 16 <= H);
-  const bool can_none = inside && f->partition_max >= 16;
-  const bool can_split = f->partition_min < 16 || !inside;
-  long long j_none = kInf;
-  if (can_none) {
-    trial_block<HBD>(t, sh, x, y, 4);
-    j_none = sh.cur.cost + partition_cost(t, mi_r, mi_c, 16, 0);
-    if (!can_split) { commit_block(t, sh.cur, x, y, 4); return j_none; }
-    copy_cand(sh.held16, sh.cur, 4, f->planes);
-  }
-  long long j_split = partition_cost(t, mi_r, mi_c, 16, 1);
+  for (int b = 0; b * G < planes; b++) {       // plane p = b * G + g handled by lane group g
 #pragma unroll 1
-  for (int k = 0; k < 4; k++) {
-    const int xx = x + (k & 1) * 8, yy = y + (k >> 1) * 8;
-    if (xx >= W || yy >= H) continue;
-    j_split += encode_tree8<HBD>(t, sh, xx, yy);
+    for (int pp = b * G; pp < min((b + 1) * G, planes); pp++)
+      predict_block(pp == 0 ? m.y_mode : m.uv_mode, lg, sh.above[pp], sh.left[pp], ha, hl, bd, sh.pred + (pp - b * G) * N2);
+    __syncwarp();
+    const int p = b * G + g;
+    const bool ok = p < planes;
+    const int pe = ok ? p : 0;
+    const TrialOut r = trial_dispatch<HBD>(n, t, sh, pe, sh.src[pe], sh.pred + (ok ? g : 0) * N2,
+                                           pe == 0 ? m.tx_type : chroma_tx_type(m.uv_mode), m.y_mode);
+    if (ok) {
+      // every lane of the group writes its share of the block: reconstruction and scan-ordered levels
+      const int l = lane & (n - 1);
+#pragma unroll 1
+      for (int q = l; q < N2; q += n) {
+        t.rec[p][(y + (q >> lg)) * t.stride + x + (q & (n - 1))] = sh.rec[g * N2 + q];
+        t.coef[p][coff + q] = sh.qc[g * N2 + q];
+      }
+      if (l == 0) t.eob[p][mi_r * f->mi_cols + mi_c] = (uint16_t)r.eob;
+    }
+    any |= __ballot_sync(FULL, ok && r.eob != 0) != 0;
+    __syncwarp();
   }
-  if (can_none && j_none <= j_split) { commit_block(t, sh.held16, x, y, 4); return j_none; }
-  return j_split;
+  B200Mi mo = m;
+  if (!any) mo.flags |= 1;
+  for (int i = lane; i < n4 * n4; i += 32) t.mi[(mi_r + (i >> (lg - 2))) * f->mi_cols + mi_c + (i & (n4 - 1))] = mo;
+  __syncwarp();
 }
 
 }  // namespace
 
-// One single-warp CTA per tile.  Partition sizes > 16 are always split (partition_max <= 16 in this kernel).
-// HBD = false: every job of the launch is 8-bit (int32 butterflies); HBD = true: 10-bit.
+// ---- stage A.1: SATD of the 13 intra modes for every block of level lv, predicted from SOURCE neighbours.
+// One thread per (block, plane group): group 0 = luma, group 1 = U + V.  out: [block][2][13] uint32.
+__global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, int lv) {
+  const B200RdoJob &job = jobs[blockIdx.y];
+  const B200Frame *f = &job.frame;
+  const int n = 4 << lv, lg = 2 + lv;
+  if (n < f->partition_min || n > f->partition_max) return;
+  const int cols = b200_level_cols(f, lv), rows = b200_level_rows(f, lv);
+  const int groups = f->planes > 1 ? 2 : 1;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= cols * rows * groups) return;
+  const int grp = gid / (cols * rows), blk = gid % (cols * rows);     // same group for neighbouring threads
+  const int bx = blk % cols, by = blk / cols, x = bx * n, y = by * n;
+  TileCtx t;
+  ctx_from_job(job, t);
+  tile_of_unit(f, y >> 2, x >> 2, t);
+  const int st = t.stride, bd = f->bit_depth;
+  const int mi_r = y >> 2, mi_c = x >> 2, n4 = n >> 2;
+  const int ha = mi_r > t.tr0, hl = mi_c > t.tc0;
+  const int max_x = f->mi_cols * 4 - 1, max_y = f->mi_rows * 4 - 1;
+  const int base = 1 << (bd - 1);
+  const int have_ar = ha && b200_unit_before(mi_r - 1, mi_c + n4, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
+  const int have_bl = hl && b200_unit_before(mi_r + n4, mi_c - 1, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
+  const int mask = grp == 0 ? f->y_mode_mask : f->uv_mode_mask;
+  uint32_t acc[13];
+#pragma unroll
+  for (int m = 0; m < 13; m++) acc[m] = 0;
+  uint16_t Ab[EOFF + 34], Lb[EOFF + 34];
+#pragma unroll 1
+  for (int p = grp; p < (grp == 0 ? 1 : 3); p++) {
+    const uint16_t *r = job.src[p];
+    uint16_t *A = Ab + EOFF, *L = Lb + EOFF;
+#pragma unroll 1
+    for (int i = 0; i < 2 * n; i++) {
+      uint16_t a, l;
+      if (!ha && hl) a = r[y * st + x - 1];
+      else if (!ha && !hl) a = (uint16_t)(base - 1);
+      else { int xx = (i < n || have_ar) ? x + i : x + n - 1; if (xx > max_x) xx = max_x; a = r[(y - 1) * st + xx]; }
+      if (!hl && ha) l = r[(y - 1) * st + x];
+      else if (!hl && !ha) l = (uint16_t)(base + 1);
+      else { int yy = (i < n || have_bl) ? y + i : y + n - 1; if (yy > max_y) yy = max_y; l = r[yy * st + x - 1]; }
+      A[i] = a; L[i] = l;
+    }
+    {
+      uint16_t tl;
+      if (ha && hl) tl = r[(y - 1) * st + x - 1];
+      else if (ha) tl = r[(y - 1) * st + x];
+      else if (hl) tl = r[y * st + x - 1];
+      else tl = (uint16_t)base;
+      A[-1] = tl; L[-1] = tl;
+    }
+    const int dc = dc_value(n, A, L, ha, hl, bd);
+#pragma unroll 1
+    for (int sb = 0; sb < (n4 * n4); sb++) {
+      const int sy = (sb >> (lg - 2)) * 4, sx = (sb & (n4 - 1)) * 4;
+      int s[16];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) s[i * 4 + j] = r[(y + sy + i) * st + x + sx + j];
+#pragma unroll 1
+      for (int m = 0; m < 13; m++) {
+        if (!((mask >> m) & 1)) continue;
+        int tt[16];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int d0 = s[i * 4] - pred_px(m, n, sy + i, sx, A, L, dc), d1 = s[i * 4 + 1] - pred_px(m, n, sy + i, sx + 1, A, L, dc);
+          const int d2 = s[i * 4 + 2] - pred_px(m, n, sy + i, sx + 2, A, L, dc), d3 = s[i * 4 + 3] - pred_px(m, n, sy + i, sx + 3, A, L, dc);
+          const int a = d0 + d1, b = d0 - d1, c = d2 + d3, e = d2 - d3;
+          tt[i * 4] = a + c; tt[i * 4 + 1] = b + e; tt[i * 4 + 2] = a - c; tt[i * 4 + 3] = b - e;
+        }
+        uint32_t total = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int a = tt[j] + tt[4 + j], b = tt[j] - tt[4 + j], c = tt[8 + j] + tt[12 + j], e = tt[8 + j] - tt[12 + j];
+          total += (uint32_t)(abs(a + c) + abs(b + e) + abs(a - c) + abs(b - e));
+        }
+        acc[m] += total;
+      }
+    }
+  }
+  uint32_t *out = job.satd[lv] + ((size_t)blk * 2 + grp) * 13;
+#pragma unroll
+  for (int m = 0; m < 13; m++) out[m] = acc[m];
+}
+
+// ---- stage A.2: full trials.  One single-warp CTA loops over blocks of level lv (grid-stride), grid.y = job.
 template <bool HBD>
-__global__ void __launch_bounds__(kThreads, 14) b200_rdo_tile_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
+__global__ void __launch_bounds__(kThreads, 16) b200_analyze_kernel(const B200RdoJob *jobs, int lv) {
+  __shared__ Shared sh;
+  const B200RdoJob &job = jobs[blockIdx.y];
+  const B200Frame *f = &job.frame;
+  const int n = 4 << lv;
+  if (n < f->partition_min || n > f->partition_max) return;
+  TileCtx t;
+  ctx_from_job(job, t);
+  const int cols = b200_level_cols(f, lv), total = cols * b200_level_rows(f, lv);
+#pragma unroll 1
+  for (int blk = blockIdx.x; blk < total; blk += gridDim.x) {
+    const int x = (blk % cols) * n, y = (blk / cols) * n;
+    tile_of_unit(f, y >> 2, x >> 2, t);
+    analyze_block<HBD>(t, sh, x, y, 2 + lv, job.satd[lv] + (size_t)blk * 26, job.dec[lv] + blk);
+  }
+}
+
+// ---- stage B: partition decision, one thread per 16x16 region (oracle orc_decide_region)
+namespace {
+__device__ __forceinline__ long long part_cost0(const B200Frame *f, const B200RateTables *rt, int mi_r, int mi_c, int n, int split) {
+  const int bsl = ilog2_dev(n) - 2, hbs = n >> 3;
+  if (!((mi_r + hbs) < f->mi_rows && (mi_c + hbs) < f->mi_cols)) return 0;
+  return ((long long)f->lambda_q8 * rt->partition[(bsl - 1) * 4][split ? 3 : 0]) >> 8;
+}
+__device__ __forceinline__ void set_mi(const B200RdoJob &job, int x, int y, int n, const B200BlockDec &d) {
+  const B200Frame *f = &job.frame;
+  B200Mi m;
+  m.bsize = (uint8_t)(n == 4 ? BLOCK_4X4 : n == 8 ? BLOCK_8X8 : BLOCK_16X16);
+  m.y_mode = d.y_mode; m.uv_mode = d.uv_mode; m.angle = 3 | (3 << 4);
+  m.tx_size = (uint8_t)txs_of(n); m.tx_type = d.tx_type; m.flags = 0; m.cfl = 0;
+  for (int i = 0; i < n / 4; i++)
+    for (int j = 0; j < n / 4; j++) job.mi[((y >> 2) + i) * f->mi_cols + (x >> 2) + j] = m;
+}
+__device__ __forceinline__ const B200BlockDec &dec_at(const B200RdoJob &job, int lv, int x, int y) {
+  const int n = 4 << lv;
+  return job.dec[lv][(y / n) * b200_level_cols(&job.frame, lv) + (x / n)];
+}
+}  // namespace
+
+__global__ void __launch_bounds__(128) b200_decide_kernel(const B200RdoJob *jobs) {
+  const B200RdoJob &job = jobs[blockIdx.y];
+  const B200Frame *f = &job.frame;
+  const B200RateTables *rt = job.rate;
+  const int W = f->mi_cols * 4, H = f->mi_rows * 4;
+  const int rcols = (W + 15) >> 4, rrows = (H + 15) >> 4;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= rcols * rrows) return;
+  const int x = (gid % rcols) * 16, y = (gid / rcols) * 16;
+  const bool inside = (x + 16 <= W) && (y + 16 <= H);
+  const bool can_none = inside && f->partition_max >= 16;
+  const bool can_split = f->partition_min < 16 || !inside;
+  long long j_split = part_cost0(f, rt, y >> 2, x >> 2, 16, 1);
+  int split8 = 0;
+  for (int k = 0; k < 4; k++) {
+    const int xx = x + (k & 1) * 8, yy = y + (k >> 1) * 8;
+    if (xx >= W || yy >= H) continue;
+    const long long j8 = dec_at(job, 1, xx, yy).cost + part_cost0(f, rt, yy >> 2, xx >> 2, 8, 0);
+    long long best = j8;
+    if (f->partition_min < 8) {
+      long long j4 = part_cost0(f, rt, yy >> 2, xx >> 2, 8, 1);
+      for (int q = 0; q < 4; q++) j4 += dec_at(job, 0, xx + (q & 1) * 4, yy + (q >> 1) * 4).cost;
+      if (!(j8 <= j4)) { best = j4; split8 |= 1 << k; }
+    }
+    j_split += best;
+  }
+  if (can_none && (!can_split || dec_at(job, 2, x, y).cost + part_cost0(f, rt, y >> 2, x >> 2, 16, 0) <= j_split)) {
+    set_mi(job, x, y, 16, dec_at(job, 2, x, y));
+    return;
+  }
+  for (int k = 0; k < 4; k++) {
+    const int xx = x + (k & 1) * 8, yy = y + (k >> 1) * 8;
+    if (xx >= W || yy >= H) continue;
+    if (!((split8 >> k) & 1)) set_mi(job, xx, yy, 8, dec_at(job, 1, xx, yy));
+    else for (int q = 0; q < 4; q++) set_mi(job, xx + (q & 1) * 4, yy + (q >> 1) * 4, 4, dec_at(job, 0, xx + (q & 1) * 4, yy + (q >> 1) * 4));
+  }
+}
+
+// ---- stage C: one single-warp CTA per tile walks its superblocks in raster order and the decided blocks in z-order
+template <bool HBD>
+__global__ void __launch_bounds__(kThreads, 16) b200_recon_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
   __shared__ Shared sh;
   const B200TileRef tr = tiles[blockIdx.x];
   const B200RdoJob &job = jobs[tr.job];
   TileCtx t;
-  t.f = &job.frame; t.rt = job.rate;
-  for (int p = 0; p < 3; p++) { t.src[p] = job.src[p]; t.rec[p] = job.rec[p]; t.eob[p] = job.eob[p]; t.coef[p] = job.coef[p]; }
-  t.mi = job.mi; t.decoded = job.decoded; t.stride = job.frame.mi_cols * 4;
+  ctx_from_job(job, t);
   const B200Frame *f = t.f;
   t.tr0 = f->tile_row_start_sb[tr.tile_row] * 16;
   t.tr1 = min(f->tile_row_start_sb[tr.tile_row + 1] * 16, f->mi_rows);
@@ -812,36 +847,68 @@ __global__ void __launch_bounds__(kThreads, 14) b200_rdo_tile_kernel(const B200R
   for (int r = t.tr0; r < t.tr1; r += 16)
 #pragma unroll 1
     for (int c = t.tc0; c < t.tc1; c += 16)
-      // 64x64 -> 32x32 -> 16x16 in z-order (always split above 16x16)
 #pragma unroll 1
-      for (int q = 0; q < 16; q++) {
-        const int bx = ((q & 1) | ((q >> 1) & 2)) * 16, by = (((q >> 1) & 1) | ((q >> 2) & 2)) * 16;
-        encode_tree16<HBD>(t, sh, c * 4 + bx, r * 4 + by);
+      for (int z = 0; z < 256;) {          // 4x4 units of the superblock in z-order; skip over whole blocks
+        int ur = 0, uc = 0;
+        for (int b = 0; b < 4; b++) { uc |= ((z >> (2 * b)) & 1) << b; ur |= ((z >> (2 * b + 1)) & 1) << b; }
+        const int mr = r + ur, mc = c + uc;
+        if (mr >= f->mi_rows || mc >= f->mi_cols) { z++; continue; }
+        const int bs = t.mi[mr * f->mi_cols + mc].bsize;
+        const int lg = bs == BLOCK_4X4 ? 2 : (bs == BLOCK_8X8 ? 3 : 4);
+        reconstruct_block<HBD>(t, sh, mc * 4, mr * 4, lg);
+        z += 1 << (2 * (lg - 2));           // a block covers (n/4)^2 consecutive z indices
       }
 }
 
 #ifndef B200_EMU
-extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int n_tiles, int high_bitdepth, void *stream) {
-  if (n_tiles <= 0) return 0;
+extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200TileRef *d_tiles, int n_tiles, int max_blocks4,
+                               int high_bitdepth, void *stream) {
+  if (n_tiles <= 0 || n_jobs <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
   static bool configured = false;
-  if (!configured) {   // ask for the largest shared-memory carve-out: ~14 single-warp CTAs of ~15 KB per SM
-    cudaFuncSetAttribute(b200_rdo_tile_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(b200_rdo_tile_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (!configured) {
+    cudaFuncSetAttribute(b200_analyze_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(b200_analyze_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(b200_recon_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(b200_recon_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  if (high_bitdepth) b200_rdo_tile_kernel<true><<<n_tiles, kThreads, 0, (cudaStream_t)stream>>>(d_jobs, d_tiles);
-  else b200_rdo_tile_kernel<false><<<n_tiles, kThreads, 0, (cudaStream_t)stream>>>(d_jobs, d_tiles);
+  for (int lv = 0; lv < 3; lv++) {
+    const int nblk = max_blocks4 >> (2 * lv);
+    dim3 gs((nblk * 2 + 127) / 128, n_jobs);
+    b200_satd_kernel<<<gs, 128, 0, st>>>(d_jobs, lv);
+    // enough single-warp CTAs to fill the machine several times over, grid-stride inside
+    const int per_job = min(nblk, max(1, (148 * 16 * 4) / n_jobs));
+    dim3 ga(per_job, n_jobs);
+    if (high_bitdepth) b200_analyze_kernel<true><<<ga, kThreads, 0, st>>>(d_jobs, lv);
+    else b200_analyze_kernel<false><<<ga, kThreads, 0, st>>>(d_jobs, lv);
+  }
+  dim3 gd((max_blocks4 / 16 + 64 + 127) / 128, n_jobs);
+  b200_decide_kernel<<<gd, 128, 0, st>>>(d_jobs);
+  if (high_bitdepth) b200_recon_kernel<true><<<n_tiles, kThreads, 0, st>>>(d_jobs, d_tiles);
+  else b200_recon_kernel<false><<<n_tiles, kThreads, 0, st>>>(d_jobs, d_tiles);
   return (int)cudaGetLastError();
 }
 #else
 static const B200RdoJob *g_emu_jobs;
 static const B200TileRef *g_emu_tiles;
-static int g_emu_hbd;
-static void emu_entry(void *) { if (g_emu_hbd) b200_rdo_tile_kernel<true>(g_emu_jobs, g_emu_tiles); else b200_rdo_tile_kernel<false>(g_emu_jobs, g_emu_tiles); }
+static int g_emu_lv;
+static void emu_satd(void *) { b200_satd_kernel(g_emu_jobs, g_emu_lv); }
+static void emu_analyze(void *) { if (g_emu_jobs[0].frame.bit_depth > 8) b200_analyze_kernel<true>(g_emu_jobs, g_emu_lv); else b200_analyze_kernel<false>(g_emu_jobs, g_emu_lv); }
+static void emu_decide(void *) { b200_decide_kernel(g_emu_jobs); }
+static void emu_recon(void *) { if (g_emu_jobs[0].frame.bit_depth > 8) b200_recon_kernel<true>(g_emu_jobs, g_emu_tiles); else b200_recon_kernel<false>(g_emu_jobs, g_emu_tiles); }
 extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *tiles, int n_tiles) {
   g_emu_jobs = jobs; g_emu_tiles = tiles;
-  g_emu_hbd = jobs[0].frame.bit_depth > 8;
-  emu::launch(emu_entry, nullptr, (unsigned)n_tiles, kThreads);
+  const B200Frame *f = &jobs[0].frame;
+  const int nblk4 = f->mi_rows * f->mi_cols;
+  for (g_emu_lv = 0; g_emu_lv < 3; g_emu_lv++) {
+    const int nblk = (f->mi_rows >> g_emu_lv) * (f->mi_cols >> g_emu_lv);
+    if (nblk == 0) continue;
+    emu::launch(emu_satd, nullptr, (unsigned)((nblk * 2 + 127) / 128), 128);
+    emu::launch(emu_analyze, nullptr, (unsigned)std::min(nblk, 7), kThreads);
+  }
+  emu::launch(emu_decide, nullptr, (unsigned)((nblk4 / 16 + 64 + 127) / 128), 128);
+  emu::launch(emu_recon, nullptr, (unsigned)n_tiles, kThreads);
   return 0;
 }
 #endif

@@ -17,7 +17,8 @@ typedef struct B200RdoJob {
   B200Mi *mi;
   uint16_t *eob[3];
   int16_t *coef[3];
-  uint8_t *decoded;       // mi_rows*mi_cols bytes, zero-initialised
+  B200BlockDec *dec[3];   // analysis decisions per level (0: 4x4, 1: 8x8, 2: 16x16), b200_level_rows*cols entries
+  uint32_t *satd[3];      // SATD tables per level: [block][2 (Y, U+V)][13 modes]
   // in-loop filter stage (filters.cu): rec is deblocked IN PLACE; cdef_idx receives the per-superblock
   // strength index (-1: nothing coded in the superblock); fin (optional, may be NULL) receives the CDEF output.
   int8_t *cdef_idx;       // sb_rows*sb_cols
@@ -30,8 +31,10 @@ typedef struct B200TileRef {
 } B200TileRef;
 
 // Launch one CTA per tile on `stream` (cudaStream_t).  Returns a cudaError_t value.
-// high_bitdepth: all jobs of the launch are 10-bit (int64 butterflies) / 8-bit (int32 butterflies).
-int b200_rdo_launch(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int n_tiles, int high_bitdepth, void *stream);
+// All RDO stages for all jobs on `stream`: SATD + analysis per level, partition decision, reconstruction chain
+// (one warp per tile).  max_blocks4 = largest mi_rows*mi_cols over the jobs; high_bitdepth: all jobs are 10-bit.
+int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200TileRef *d_tiles, int n_tiles, int max_blocks4,
+                    int high_bitdepth, void *stream);
 // Deblock (2 launches) + CDEF search (1 launch) for all jobs: grid.y = job.
 int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, void *stream);
 

@@ -78,6 +78,16 @@ typedef struct B200Frame {
   int32_t lr_type[3];                       // 0 none (only value emitted for now)
 } B200Frame;
 
+// Decision of the open-loop analysis for one block (analysis stage -> partition decision -> reconstruction).
+typedef struct B200BlockDec {
+  int64_t cost;        // J = SSE*256 + lambda*R of the best (mode, transform type) per plane, + skip flag cost
+  uint8_t y_mode, tx_type, uv_mode, pad[5];
+} B200BlockDec;
+// Number of analysed blocks per row / column at level lv (0: 4x4, 1: 8x8, 2: 16x16); blocks that stick out of the
+// (8-pixel aligned) coded frame are not analysed.
+static inline B200_HD int b200_level_cols(const struct B200Frame *f, int lv);
+static inline B200_HD int b200_level_rows(const struct B200Frame *f, int lv);
+
 // Static rate model used by the RDO (costs in 1/256 bit, derived from the default CDFs of the
 // frame's quantiser class, no adaptation).  Built on the host by b200av1_build_rate_tables().
 typedef struct B200RateTables {
@@ -98,11 +108,24 @@ typedef struct B200RateTables {
   uint16_t coeff_br[4][2][21][13];          // cost of base_range 0..12 (12 = 12 or more, golomb extra not included)
 } B200RateTables;
 
+static inline B200_HD int b200_level_cols(const B200Frame *f, int lv) { return f->mi_cols >> lv; }
+static inline B200_HD int b200_level_rows(const B200Frame *f, int lv) { return f->mi_rows >> lv; }
+
 // z-order index (0..255) of the 4x4 unit (r, c) inside its 64x64 superblock, r,c in 0..15.
 static inline B200_HD int b200_zidx(int r, int c) {
   int z = 0;
   for (int i = 0; i < 4; i++) z |= (((c >> i) & 1) << (2 * i)) | (((r >> i) & 1) << (2 * i + 1));
   return z;
+}
+// Is the 4x4 unit (ur, uc) reconstructed before the block whose top-left unit is (br, bc)?  Coding order is
+// static: superblocks in raster order inside the tile [tr0,tr1) x [tc0,tc1), z-order inside a superblock; any block
+// containing the unit lies entirely before or after the current block.  (AV1 top-right / bottom-left availability.)
+static inline B200_HD int b200_unit_before(int ur, int uc, int br, int bc, int tr0, int tr1, int tc0, int tc1) {
+  if (ur < tr0 || ur >= tr1 || uc < tc0 || uc >= tc1) return 0;
+  const int usr = ur >> 4, usc = uc >> 4, bsr = br >> 4, bsc = bc >> 4;
+  if (usr != bsr) return usr < bsr;
+  if (usc != bsc) return usc < bsc;
+  return b200_zidx(ur & 15, uc & 15) < b200_zidx(br & 15, bc & 15);
 }
 // First coefficient slot of the transform block whose top-left 4x4 unit is (mi_row, mi_col).
 // Coefficients of a block are stored in SCAN ORDER, contiguous, in its z-order slot range.

@@ -35,43 +35,32 @@ typedef struct {
   B200Mi *mi;
   uint16_t *eob[3];
   int16_t *coef[3];
-  uint8_t *decoded;   /* per-4x4 "already reconstructed" flags (whole frame, tile-local meaning) */
+  B200BlockDec *dec[3];     /* analysis decisions per level (0: 4x4, 1: 8x8, 2: 16x16) */
   int tr0, tr1, tc0, tc1;   /* current tile bounds in mi units */
 } enc_t;
-
-/* one block candidate (all planes) */
-typedef struct {
-  int64_t cost;
-  B200Mi mi;
-  uint16_t eob[3];
-  int16_t qcoef[3][1024];     /* scan order */
-  uint16_t recon[3][32 * 32];
-} cand_t;
 
 static const uint16_t *scan_for(int n) {
   return n == 4 ? av1_default_scan_4x4 : n == 8 ? av1_default_scan_8x8 : n == 16 ? av1_default_scan_16x16 : av1_default_scan_32x32;
 }
 static int txs_of(int n) { return n == 4 ? 0 : n == 8 ? 1 : n == 16 ? 2 : 3; }
 static int bsize_of(int n) { return n == 4 ? BLOCK_4X4 : n == 8 ? BLOCK_8X8 : n == 16 ? BLOCK_16X16 : n == 32 ? BLOCK_32X32 : BLOCK_64X64; }
-static const uint8_t k_bw4[22] = {1, 1, 2, 2, 2, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 1, 4, 2, 8, 4, 16};
-static const uint8_t k_bh4[22] = {1, 2, 1, 2, 4, 2, 4, 8, 4, 8, 16, 8, 16, 32, 16, 32, 4, 1, 8, 2, 16, 4};
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
-/* ---- intra edge preparation: AV1 spec 7.11.2 (no intra edge filter / upsampling: the sequence
- * header sets enable_intra_edge_filter = 0). above[-1..2n-1], left[-1..2n-1] via offset 16. */
+/* ---- intra edge preparation: AV1 spec 7.11.2 (no intra edge filter / upsampling: the sequence header sets
+ * enable_intra_edge_filter = 0). above[-1..2n-1], left[-1..2n-1] via offset 16.  `r` is the plane the neighbours
+ * are read from: the SOURCE plane in the open-loop analysis, the reconstruction in the final pass.  Top-right /
+ * bottom-left availability is the static coding-order predicate b200_unit_before(). */
 #define EOFF 16
-static void build_edges(const enc_t *e, int plane, int x, int y, int n, uint16_t *above, uint16_t *left,
+static void build_edges(const enc_t *e, const uint16_t *r, int x, int y, int n, uint16_t *above, uint16_t *left,
                         int *have_above, int *have_left) {
   const B200Frame *f = e->f;
-  const uint16_t *r = e->rec[plane];
   const int st = e->stride;
   const int mi_r = y >> 2, mi_c = x >> 2, n4 = n >> 2;
   const int ha = mi_r > e->tr0, hl = mi_c > e->tc0;
   const int max_x = f->mi_cols * 4 - 1, max_y = f->mi_rows * 4 - 1;
   const int base = 1 << (f->bit_depth - 1);
-  int have_ar = 0, have_bl = 0;
-  if (ha && mi_c + n4 < e->tc1) have_ar = e->decoded[(mi_r - 1) * f->mi_cols + mi_c + n4];
-  if (hl && mi_r + n4 < e->tr1) have_bl = e->decoded[(mi_r + n4) * f->mi_cols + mi_c - 1];
+  const int have_ar = ha && b200_unit_before(mi_r - 1, mi_c + n4, mi_r, mi_c, e->tr0, e->tr1, e->tc0, e->tc1);
+  const int have_bl = hl && b200_unit_before(mi_r + n4, mi_c - 1, mi_r, mi_c, e->tr0, e->tr1, e->tc0, e->tc1);
   uint16_t *A = above + EOFF, *L = left + EOFF;
   if (!ha && hl) { for (int i = 0; i < 2 * n; i++) A[i] = r[y * st + x - 1]; }
   else if (!ha && !hl) { for (int i = 0; i < 2 * n; i++) A[i] = (uint16_t)(base - 1); }
@@ -102,6 +91,7 @@ static void build_edges(const enc_t *e, int plane, int x, int y, int n, uint16_t
   *have_above = ha; *have_left = hl;
 }
 
+static const uint8_t k_bw4[22] = {1, 1, 2, 2, 2, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 1, 4, 2, 8, 4, 16};
 static const uint8_t *sm_weights(int n) {
   return n == 4 ? av1_sm_weights_4 : n == 8 ? av1_sm_weights_8 : n == 16 ? av1_sm_weights_16 : n == 32 ? av1_sm_weights_32 : av1_sm_weights_64;
 }
@@ -322,50 +312,52 @@ static int chroma_tx_type(int uv_mode, int n) {
   return av1_intra_mode_to_tx_type[uv_mode];   /* DCT/ADST combinations are in every intra set up to 16x16 */
 }
 
-/* Evaluate one block (all planes) at (x,y) size n against the current reconstruction; fills cand. */
-static void trial_block(enc_t *e, int x, int y, int n, cand_t *cd) {
+static uint32_t mode_rate(const B200RateTables *rt, const uint16_t *row, int m, int n) {
+  uint32_t r = row[m];
+  if (n >= 8 && m >= V_PRED && m <= D67_PRED) r += rt->angle_delta[m - V_PRED][3];
+  return r;
+}
+
+/* ---- stage A: open-loop analysis of one block.  Every prediction reads SOURCE neighbours, so all blocks of all
+ * levels are independent of each other (one massively parallel kernel per level on the device).  Rate terms that
+ * would depend on neighbouring decisions use the context-0 tables. */
+void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_t satd_y[13], uint32_t satd_uv[13]) {
   const B200Frame *f = e->f;
   const B200RateTables *rt = e->rt;
-  const int mi_r = y >> 2, mi_c = x >> 2;
-  const int avail_u = mi_r > e->tr0, avail_l = mi_c > e->tc0;
-  uint16_t above[EOFF + 64 + 2], left[EOFF + 64 + 2];
-  int ha, hl;
-  uint16_t pred[32 * 32], best_pred_unused;
-  (void)best_pred_unused;
-  const uint16_t *src = e->src[0] + y * e->stride + x;
-
-  /* --- mode contexts */
-  const int am = avail_u ? e->mi[(mi_r - 1) * f->mi_cols + mi_c].y_mode : DC_PRED;
-  const int lm = avail_l ? e->mi[mi_r * f->mi_cols + mi_c - 1].y_mode : DC_PRED;
-  const uint16_t *ymode_cost = rt->y_mode[av1_intra_mode_context[am]][av1_intra_mode_context[lm]];
-
-  /* --- luma: rank modes by SATD + mode rate */
-  build_edges(e, 0, x, y, n, above, left, &ha, &hl);
-  int64_t best_c[2] = {INT64_MAX, INT64_MAX};
-  int best_m[2] = {-1, -1};
+  uint16_t A[3][EOFF + 66], L[3][EOFF + 66], pred[32 * 32];
+  int ha = 0, hl = 0;
+  for (int p = 0; p < f->planes; p++) build_edges(e, e->src[p], x, y, n, A[p], L[p], &ha, &hl);
+  const uint16_t *ymode_cost = rt->y_mode[0][0];
+  /* ranking: SATD + mode rate */
+  int64_t bc[2] = {INT64_MAX, INT64_MAX};
+  int bm[2] = {-1, -1};
   for (int m = 0; m < 13; m++) {
-    if (!((f->y_mode_mask >> m) & 1)) continue;
-    orc_predict_intra(m, 0, n, above, left, ha, hl, f->bit_depth, pred);
-    uint32_t mrate = ymode_cost[m];
-    if (n >= 8 && m >= V_PRED && m <= D67_PRED) mrate += rt->angle_delta[m - V_PRED][3];
-    const int64_t c = (int64_t)satd4(src, e->stride, pred, n) * 64 + (((int64_t)f->lambda_satd_q8 * mrate) >> 8);
-    if (c < best_c[0]) { best_c[1] = best_c[0]; best_m[1] = best_m[0]; best_c[0] = c; best_m[0] = m; }
-    else if (c < best_c[1]) { best_c[1] = c; best_m[1] = m; }
+    satd_y[m] = 0; satd_uv[m] = 0;
+    const int in_y = (f->y_mode_mask >> m) & 1, in_uv = f->planes > 1 && ((f->uv_mode_mask >> m) & 1);
+    if (!in_y && !in_uv) continue;
+    for (int p = 0; p < f->planes; p++) {
+      if (p == 0 ? !in_y : !in_uv) continue;
+      orc_predict_intra(m, 0, n, A[p], L[p], ha, hl, f->bit_depth, pred);
+      const uint32_t s = satd4(e->src[p] + y * e->stride + x, e->stride, pred, n);
+      if (p == 0) satd_y[m] = s; else satd_uv[m] += s;
+    }
+    if (!in_y) continue;
+    const int64_t c = (int64_t)satd_y[m] * 64 + (((int64_t)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, m, n)) >> 8);
+    if (c < bc[0]) { bc[1] = bc[0]; bm[1] = bm[0]; bc[0] = c; bm[0] = m; }
+    else if (c < bc[1]) { bc[1] = c; bm[1] = m; }
   }
-  /* --- full trials: top-2 modes x allowed transform types (all types when rdo_tx_decision, else the
-   * first allowed one); candidate order (mode rank, type index), strict '<' keeps the earliest. */
+  /* luma trials: top-2 modes x allowed transform types; order (mode rank, type index), strict '<' keeps the earliest */
   int first_tt = -1;
   for (int k = 0; k < 5; k++) if ((f->tx_type_mask >> k) & 1) { first_tt = k_tx_types[k]; break; }
   int64_t bestJ = INT64_MAX;
-  int best_mode = best_m[0], best_tt = first_tt;
+  int best_mode = bm[0], best_tt = first_tt, eob_y = 0;
   int16_t qc[1024];
   uint16_t recon[1024], eobv;
   for (int k = 0; k < 2; k++) {
-    const int m = best_m[k];
+    const int m = bm[k];
     if (m < 0) continue;
-    orc_predict_intra(m, 0, n, above, left, ha, hl, f->bit_depth, pred);
-    uint32_t mrate = ymode_cost[m];
-    if (n >= 8 && m >= V_PRED && m <= D67_PRED) mrate += rt->angle_delta[m - V_PRED][3];
+    orc_predict_intra(m, 0, n, A[0], L[0], ha, hl, f->bit_depth, pred);
+    const uint32_t mrate = mode_rate(rt, ymode_cost, m, n);
     for (int t = 0; t < 5; t++) {
       const int tt = k_tx_types[t];
       if (!((f->tx_type_mask >> t) & 1)) continue;
@@ -373,169 +365,178 @@ static void trial_block(enc_t *e, int x, int y, int n, cand_t *cd) {
       uint32_t rate;
       const uint64_t d = trial_plane(e, 0, x, y, n, pred, tt, m, qc, &eobv, recon, &rate);
       const int64_t J = rd_cost(f, d, rate + mrate);
-      if (J < bestJ) {
-        bestJ = J; best_mode = m; best_tt = tt;
-        memcpy(cd->qcoef[0], qc, sizeof(int16_t) * n * n);
-        memcpy(cd->recon[0], recon, sizeof(uint16_t) * n * n);
-        cd->eob[0] = eobv;
-      }
+      if (J < bestJ) { bestJ = J; best_mode = m; best_tt = tt; eob_y = eobv; }
     }
   }
   int64_t total = bestJ;
-  memset(&cd->mi, 0, sizeof(cd->mi));
-  cd->mi.bsize = (uint8_t)bsize_of(n);
-  cd->mi.y_mode = (uint8_t)best_mode;
-  cd->mi.angle = 3 | (3 << 4);
-  cd->mi.tx_size = (uint8_t)txs_of(n);
-  cd->mi.tx_type = (uint8_t)best_tt;
-  cd->mi.uv_mode = DC_PRED;
-
-  /* --- chroma: rank uv modes by SATD (U+V) + rate, full trial of the top-2, keep the better */
+  int uv_best = DC_PRED, eob_u = 0, eob_v = 0;
   if (f->planes > 1) {
-    const int cfl_allowed = n <= 32;
-    const uint16_t *uvcost = rt->uv_mode[cfl_allowed][best_mode];
-    uint16_t aU[EOFF + 66], lU[EOFF + 66], aV[EOFF + 66], lV[EOFF + 66];
-    int hau, hlu;
-    build_edges(e, 1, x, y, n, aU, lU, &hau, &hlu);
-    build_edges(e, 2, x, y, n, aV, lV, &hau, &hlu);
-    int64_t bc[2] = {INT64_MAX, INT64_MAX};
-    int buv[2] = {-1, -1};
+    const uint16_t *uvcost = rt->uv_mode[1][best_mode];
+    int64_t uc[2] = {INT64_MAX, INT64_MAX};
+    int um[2] = {-1, -1};
     for (int m = 0; m < 13; m++) {
       if (!((f->uv_mode_mask >> m) & 1)) continue;
-      uint32_t mrate = uvcost[m];
-      if (n >= 8 && m >= V_PRED && m <= D67_PRED) mrate += rt->angle_delta[m - V_PRED][3];
-      orc_predict_intra(m, 0, n, aU, lU, hau, hlu, f->bit_depth, pred);
-      uint32_t s = satd4(e->src[1] + y * e->stride + x, e->stride, pred, n);
-      orc_predict_intra(m, 0, n, aV, lV, hau, hlu, f->bit_depth, pred);
-      s += satd4(e->src[2] + y * e->stride + x, e->stride, pred, n);
-      const int64_t c = (int64_t)s * 64 + (((int64_t)f->lambda_satd_q8 * mrate) >> 8);
-      if (c < bc[0]) { bc[1] = bc[0]; buv[1] = buv[0]; bc[0] = c; buv[0] = m; }
-      else if (c < bc[1]) { bc[1] = c; buv[1] = m; }
+      const int64_t c = (int64_t)satd_uv[m] * 64 + (((int64_t)f->lambda_satd_q8 * mode_rate(rt, uvcost, m, n)) >> 8);
+      if (c < uc[0]) { uc[1] = uc[0]; um[1] = um[0]; uc[0] = c; um[0] = m; }
+      else if (c < uc[1]) { uc[1] = c; um[1] = m; }
     }
     int64_t bestC = INT64_MAX;
     for (int k = 0; k < 2; k++) {
-      const int m = buv[k];
+      const int m = um[k];
       if (m < 0) continue;
-      uint32_t mrate = uvcost[m];
-      if (n >= 8 && m >= V_PRED && m <= D67_PRED) mrate += rt->angle_delta[m - V_PRED][3];
       const int ctt = chroma_tx_type(m, n);
-      int16_t q1[1024], q2[1024];
-      uint16_t r1[1024], r2[1024], e1, e2;
-      uint32_t rate1, rate2;
-      orc_predict_intra(m, 0, n, aU, lU, hau, hlu, f->bit_depth, pred);
-      uint64_t d = trial_plane(e, 1, x, y, n, pred, ctt, best_mode, q1, &e1, r1, &rate1);
-      orc_predict_intra(m, 0, n, aV, lV, hau, hlu, f->bit_depth, pred);
-      d += trial_plane(e, 2, x, y, n, pred, ctt, best_mode, q2, &e2, r2, &rate2);
-      const int64_t J = rd_cost(f, d, rate1 + rate2 + mrate);
-      if (J < bestC) {
-        bestC = J;
-        cd->mi.uv_mode = (uint8_t)m;
-        memcpy(cd->qcoef[1], q1, sizeof(int16_t) * n * n); memcpy(cd->qcoef[2], q2, sizeof(int16_t) * n * n);
-        memcpy(cd->recon[1], r1, sizeof(uint16_t) * n * n); memcpy(cd->recon[2], r2, sizeof(uint16_t) * n * n);
-        cd->eob[1] = e1; cd->eob[2] = e2;
-      }
+      uint16_t e1, e2;
+      uint32_t r1, r2;
+      orc_predict_intra(m, 0, n, A[1], L[1], ha, hl, f->bit_depth, pred);
+      uint64_t d = trial_plane(e, 1, x, y, n, pred, ctt, best_mode, qc, &e1, recon, &r1);
+      orc_predict_intra(m, 0, n, A[2], L[2], ha, hl, f->bit_depth, pred);
+      d += trial_plane(e, 2, x, y, n, pred, ctt, best_mode, qc, &e2, recon, &r2);
+      const int64_t J = rd_cost(f, d, r1 + r2 + mode_rate(rt, uvcost, m, n));
+      if (J < bestC) { bestC = J; uv_best = m; eob_u = e1; eob_v = e2; }
     }
     total += bestC;
   }
-  /* --- skip flag */
-  const int all_zero = cd->eob[0] == 0 && (f->planes == 1 || (cd->eob[1] == 0 && cd->eob[2] == 0));
-  {
-    const int a = avail_u ? (e->mi[(mi_r - 1) * f->mi_cols + mi_c].flags & 1) : 0;
-    const int l = avail_l ? (e->mi[mi_r * f->mi_cols + mi_c - 1].flags & 1) : 0;
-    total += ((int64_t)f->lambda_q8 * rt->skip[a + l][all_zero]) >> 8;
-  }
-  if (all_zero) cd->mi.flags |= 1;
-  cd->cost = total;
+  const int all_zero = eob_y == 0 && (f->planes == 1 || (eob_u == 0 && eob_v == 0));
+  total += ((int64_t)f->lambda_q8 * rt->skip[0][all_zero]) >> 8;
+  memset(out, 0, sizeof(*out));
+  out->cost = total;
+  out->y_mode = (uint8_t)best_mode; out->tx_type = (uint8_t)best_tt; out->uv_mode = (uint8_t)uv_best;
 }
 
-/* write a candidate into the frame state (reconstruction, records, decoded flags) */
-static void commit_block(enc_t *e, int x, int y, int n, const cand_t *cd) {
+/* ---- stage B: partition decision of one 16x16 region from the analysed costs (context-0 partition rates) */
+static int64_t part_cost(const B200Frame *f, const B200RateTables *rt, int mi_r, int mi_c, int n, int split) {
+  const int bsl = ilog2(n) - 2, hbs = n >> 3;
+  if (!((mi_r + hbs) < f->mi_rows && (mi_c + hbs) < f->mi_cols)) return 0;   /* forced / 1-bit cases ignored */
+  return ((int64_t)f->lambda_q8 * rt->partition[(bsl - 1) * 4][split ? 3 : 0]) >> 8;
+}
+static void set_mi(enc_t *e, int x, int y, int n, const B200BlockDec *d) {
   const B200Frame *f = e->f;
-  const int mi_r = y >> 2, mi_c = x >> 2, n4 = n >> 2;
-  for (int p = 0; p < f->planes; p++) {
-    for (int i = 0; i < n; i++) memcpy(e->rec[p] + (y + i) * e->stride + x, cd->recon[p] + i * n, sizeof(uint16_t) * n);
-    e->eob[p][mi_r * f->mi_cols + mi_c] = cd->eob[p];
-    memcpy(e->coef[p] + b200_coef_offset(f, mi_r, mi_c), cd->qcoef[p], sizeof(int16_t) * n * n);
-  }
-  for (int i = 0; i < n4; i++)
-    for (int j = 0; j < n4; j++) {
-      e->mi[(mi_r + i) * f->mi_cols + mi_c + j] = cd->mi;
-      e->decoded[(mi_r + i) * f->mi_cols + mi_c + j] = 1;
-    }
+  B200Mi m;
+  memset(&m, 0, sizeof(m));
+  m.bsize = (uint8_t)bsize_of(n); m.y_mode = d->y_mode; m.uv_mode = d->uv_mode; m.angle = 3 | (3 << 4);
+  m.tx_size = (uint8_t)txs_of(n); m.tx_type = d->tx_type;
+  for (int i = 0; i < n / 4; i++)
+    for (int j = 0; j < n / 4; j++) e->mi[((y >> 2) + i) * f->mi_cols + (x >> 2) + j] = m;
 }
-
-static int64_t partition_cost(const enc_t *e, int mi_r, int mi_c, int n, int split) {
-  const B200Frame *f = e->f;
-  const int bsl = ilog2(n) - 2;   /* 8 -> 1 */
-  const int n4 = n >> 2, hbs = n4 >> 1;
-  const int has_rows = (mi_r + hbs) < f->mi_rows, has_cols = (mi_c + hbs) < f->mi_cols;
-  if (!has_rows || !has_cols) return 0;   /* forced / 1-bit cases: ignored by the rate model */
-  const int au = mi_r > e->tr0, al = mi_c > e->tc0;
-  const int above = au && ilog2(k_bw4[e->mi[(mi_r - 1) * f->mi_cols + mi_c].bsize]) < bsl;
-  const int left = al && ilog2(k_bh4[e->mi[mi_r * f->mi_cols + mi_c - 1].bsize]) < bsl;
-  const int ctx = (bsl - 1) * 4 + left * 2 + above;
-  return ((int64_t)f->lambda_q8 * e->rt->partition[ctx][split ? 3 : 0]) >> 8;
+static const B200BlockDec *dec_at(const enc_t *e, int lv, int x, int y) {
+  const int n = 4 << lv;
+  return &e->dec[lv][(y / n) * b200_level_cols(e->f, lv) + (x / n)];
 }
-
-/* recursive partition search over square sizes partition_min..partition_max */
-static int64_t encode_tree(enc_t *e, int x, int y, int n) {
+void orc_decide_region(enc_t *e, int x, int y) {
   const B200Frame *f = e->f;
   const int W = f->mi_cols * 4, H = f->mi_rows * 4;
-  if (x >= W || y >= H) return 0;
-  const int inside = (x + n <= W) && (y + n <= H);
-  const int can_none = inside && n <= f->partition_max && n <= 32;
-  const int can_split = n > 4 && (n > f->partition_min || !inside);
-  const int mi_r = y >> 2, mi_c = x >> 2;
-  if (can_none && !can_split) {
-    cand_t *cd = (cand_t *)malloc(sizeof(cand_t));
-    trial_block(e, x, y, n, cd);
-    const int64_t c = cd->cost + (n >= 8 ? partition_cost(e, mi_r, mi_c, n, 0) : 0);
-    commit_block(e, x, y, n, cd);
-    free(cd);
-    return c;
+  if (x >= W || y >= H) return;
+  const int inside = (x + 16 <= W) && (y + 16 <= H);
+  const int can_none = inside && f->partition_max >= 16;
+  const int can_split = f->partition_min < 16 || !inside;
+  int64_t j_split = part_cost(f, e->rt, y >> 2, x >> 2, 16, 1);
+  int split8[4] = {0, 0, 0, 0};
+  for (int k = 0; k < 4; k++) {
+    const int xx = x + (k & 1) * 8, yy = y + (k >> 1) * 8;
+    if (xx >= W || yy >= H) continue;
+    const int64_t j8 = dec_at(e, 1, xx, yy)->cost + part_cost(f, e->rt, yy >> 2, xx >> 2, 8, 0);
+    int64_t best = j8;
+    if (f->partition_min < 8) {
+      int64_t j4 = part_cost(f, e->rt, yy >> 2, xx >> 2, 8, 1);
+      for (int q = 0; q < 4; q++) j4 += dec_at(e, 0, xx + (q & 1) * 4, yy + (q >> 1) * 4)->cost;
+      if (!(j8 <= j4)) { best = j4; split8[k] = 1; }
+    }
+    j_split += best;
   }
-  cand_t *cd = NULL;
-  int64_t j_none = INT64_MAX;
-  if (can_none) {
-    cd = (cand_t *)malloc(sizeof(cand_t));
-    trial_block(e, x, y, n, cd);
-    j_none = cd->cost + partition_cost(e, mi_r, mi_c, n, 0);
+  if (can_none && (!can_split || dec_at(e, 2, x, y)->cost + part_cost(f, e->rt, y >> 2, x >> 2, 16, 0) <= j_split)) {
+    set_mi(e, x, y, 16, dec_at(e, 2, x, y));
+    return;
   }
-  const int64_t pc_split = partition_cost(e, mi_r, mi_c, n, 1);   /* context read before children commit */
-  const int h = n >> 1;
-  int64_t j_split = pc_split;
-  j_split += encode_tree(e, x, y, h);
-  j_split += encode_tree(e, x + h, y, h);
-  j_split += encode_tree(e, x, y + h, h);
-  j_split += encode_tree(e, x + h, y + h, h);
-  if (can_none && j_none <= j_split) {
-    commit_block(e, x, y, n, cd);
-    j_split = j_none;
+  for (int k = 0; k < 4; k++) {
+    const int xx = x + (k & 1) * 8, yy = y + (k >> 1) * 8;
+    if (xx >= W || yy >= H) continue;
+    if (!split8[k]) set_mi(e, xx, yy, 8, dec_at(e, 1, xx, yy));
+    else for (int q = 0; q < 4; q++) set_mi(e, xx + (q & 1) * 4, yy + (q >> 1) * 4, 4, dec_at(e, 0, xx + (q & 1) * 4, yy + (q >> 1) * 4));
   }
-  if (cd) free(cd);
-  return j_split;
 }
 
-/* Encode one tile (tile_row, tile_col): superblocks in raster order. */
-void orc_encode_tile(const B200Frame *f, const B200RateTables *rt, uint16_t *const src[3], uint16_t *const rec[3],
-                     B200Mi *mi, uint16_t *const eob[3], int16_t *const coef[3], uint8_t *decoded, int tile_row,
-                     int tile_col) {
+/* ---- stage C: closed-loop reconstruction of one decided block (the only stage that needs reconstructed neighbours) */
+static void reconstruct_block(enc_t *e, int x, int y, int n) {
+  const B200Frame *f = e->f;
+  const int mi_r = y >> 2, mi_c = x >> 2, n4 = n >> 2;
+  B200Mi m = e->mi[mi_r * f->mi_cols + mi_c];
+  uint16_t A[EOFF + 66], L[EOFF + 66], pred[32 * 32], recon[32 * 32];
+  int16_t qc[1024];
+  int all_zero = 1;
+  for (int p = 0; p < f->planes; p++) {
+    int ha, hl;
+    build_edges(e, e->rec[p], x, y, n, A, L, &ha, &hl);
+    const int mode = p == 0 ? m.y_mode : m.uv_mode;
+    const int tt = p == 0 ? m.tx_type : chroma_tx_type(m.uv_mode, n);
+    orc_predict_intra(mode, 0, n, A, L, ha, hl, f->bit_depth, pred);
+    uint16_t eobv;
+    uint32_t rate;
+    trial_plane(e, p, x, y, n, pred, tt, m.y_mode, qc, &eobv, recon, &rate);
+    for (int i = 0; i < n; i++) memcpy(e->rec[p] + (y + i) * e->stride + x, recon + i * n, sizeof(uint16_t) * n);
+    e->eob[p][mi_r * f->mi_cols + mi_c] = eobv;
+    memcpy(e->coef[p] + b200_coef_offset(f, mi_r, mi_c), qc, sizeof(int16_t) * n * n);
+    if (eobv) all_zero = 0;
+  }
+  if (all_zero) m.flags |= 1;
+  for (int i = 0; i < n4; i++)
+    for (int j = 0; j < n4; j++) e->mi[(mi_r + i) * f->mi_cols + mi_c + j] = m;
+}
+
+static void tile_bounds(enc_t *e, int tile_row, int tile_col) {
+  const B200Frame *f = e->f;
+  e->tr0 = f->tile_row_start_sb[tile_row] * 16;
+  e->tr1 = f->tile_row_start_sb[tile_row + 1] * 16; if (e->tr1 > f->mi_rows) e->tr1 = f->mi_rows;
+  e->tc0 = f->tile_col_start_sb[tile_col] * 16;
+  e->tc1 = f->tile_col_start_sb[tile_col + 1] * 16; if (e->tc1 > f->mi_cols) e->tc1 = f->mi_cols;
+}
+static void tile_of(const B200Frame *f, int mi_r, int mi_c, int *tr, int *tc) {
+  int r = 0, c = 0;
+  while (f->tile_row_start_sb[r + 1] * 16 <= mi_r) r++;
+  while (f->tile_col_start_sb[c + 1] * 16 <= mi_c) c++;
+  *tr = r; *tc = c;
+}
+
+/* Whole frame: analysis of every block at every allowed level, partition decision, reconstruction chain.
+ * dec[lv] (may be NULL): receives the analysis decisions, satd (may be NULL): [lv][block][2][13] for tests. */
+void orc_encode_frame(const B200Frame *f, const B200RateTables *rt, uint16_t *const src[3], uint16_t *const rec[3],
+                      B200Mi *mi, uint16_t *const eob[3], int16_t *const coef[3], B200BlockDec *const dec_out[3],
+                      uint32_t *const satd_out[3]) {
   enc_t e;
   memset(&e, 0, sizeof(e));
-  e.f = f; e.rt = rt; e.stride = f->mi_cols * 4; e.mi = mi; e.decoded = decoded;
+  e.f = f; e.rt = rt; e.stride = f->mi_cols * 4; e.mi = mi;
   for (int p = 0; p < 3; p++) { e.src[p] = src[p]; e.rec[p] = rec[p]; e.eob[p] = eob[p]; e.coef[p] = coef[p]; }
-  e.tr0 = f->tile_row_start_sb[tile_row] * 16;
-  e.tr1 = f->tile_row_start_sb[tile_row + 1] * 16; if (e.tr1 > f->mi_rows) e.tr1 = f->mi_rows;
-  e.tc0 = f->tile_col_start_sb[tile_col] * 16;
-  e.tc1 = f->tile_col_start_sb[tile_col + 1] * 16; if (e.tc1 > f->mi_cols) e.tc1 = f->mi_cols;
-  for (int r = e.tr0; r < e.tr1; r += 16)
-    for (int c = e.tc0; c < e.tc1; c += 16) encode_tree(&e, c * 4, r * 4, 64);
-}
-
-void orc_encode_frame(const B200Frame *f, const B200RateTables *rt, uint16_t *const src[3], uint16_t *const rec[3],
-                      B200Mi *mi, uint16_t *const eob[3], int16_t *const coef[3]) {
-  uint8_t *decoded = (uint8_t *)calloc((size_t)f->mi_rows * f->mi_cols, 1);
+  for (int lv = 0; lv < 3; lv++) {
+    const size_t nblk = (size_t)b200_level_rows(f, lv) * b200_level_cols(f, lv);
+    e.dec[lv] = (dec_out && dec_out[lv]) ? dec_out[lv] : (B200BlockDec *)calloc(nblk ? nblk : 1, sizeof(B200BlockDec));
+    const int n = 4 << lv;
+    if (n < f->partition_min || n > f->partition_max) continue;
+    for (int by = 0; by < b200_level_rows(f, lv); by++)
+      for (int bx = 0; bx < b200_level_cols(f, lv); bx++) {
+        int tr, tc;
+        tile_of(f, by * (n / 4), bx * (n / 4), &tr, &tc);
+        tile_bounds(&e, tr, tc);
+        uint32_t sy[13], suv[13];
+        const size_t bi = (size_t)by * b200_level_cols(f, lv) + bx;
+        orc_analyze_block(&e, bx * n, by * n, n, &e.dec[lv][bi], sy, suv);
+        if (satd_out && satd_out[lv]) { memcpy(satd_out[lv] + bi * 26, sy, sizeof(sy)); memcpy(satd_out[lv] + bi * 26 + 13, suv, sizeof(suv)); }
+      }
+  }
+  for (int y = 0; y < f->mi_rows * 4; y += 16)
+    for (int x = 0; x < f->mi_cols * 4; x += 16) orc_decide_region(&e, x, y);
   for (int tr = 0; tr < f->tile_rows; tr++)
-    for (int tc = 0; tc < f->tile_cols; tc++) orc_encode_tile(f, rt, src, rec, mi, eob, coef, decoded, tr, tc);
-  free(decoded);
+    for (int tc = 0; tc < f->tile_cols; tc++) {
+      tile_bounds(&e, tr, tc);
+      for (int r = e.tr0; r < e.tr1; r += 16)
+        for (int c = e.tc0; c < e.tc1; c += 16)
+          for (int z = 0; z < 256; z++) {          /* 4x4 units of the superblock in z-order */
+            int ur = 0, uc = 0;
+            for (int b = 0; b < 4; b++) { uc |= ((z >> (2 * b)) & 1) << b; ur |= ((z >> (2 * b + 1)) & 1) << b; }
+            const int mr = r + ur, mc = c + uc;
+            if (mr >= f->mi_rows || mc >= f->mi_cols) continue;
+            const int n = 4 * k_bw4[mi[mr * f->mi_cols + mc].bsize];
+            if ((mr * 4) % n || (mc * 4) % n) continue;      /* not the top-left unit of its block */
+            reconstruct_block(&e, mc * 4, mr * 4, n);
+          }
+    }
+  for (int lv = 0; lv < 3; lv++) if (!(dec_out && dec_out[lv])) free(e.dec[lv]);
 }

@@ -27,6 +27,7 @@ class B200Records(ctypes.Structure):
 RATE_TABLES_BYTES = 2 * (20 * 10 + 3 * 2 + 5 * 5 * 13 + 2 * 13 * 14 + 8 * 7 + 8 + 6 * 16 + 2 * 4 * 13 * 16 + 5 * 13 * 2 +
                          4 * 2 * 12 + 5 * 2 * 9 * 2 + 2 * 3 * 2 + 5 * 2 * 4 * 3 + 5 * 2 * 42 * 4 + 4 * 2 * 21 * 13)
 
+DEC_DTYPE = np.dtype([("cost", "<i8"), ("y_mode", "u1"), ("tx_type", "u1"), ("uv_mode", "u1"), ("pad", "u1", 5)])
 MI_DTYPE = np.dtype([("bsize", "u1"), ("y_mode", "u1"), ("uv_mode", "u1"), ("angle", "u1"),
                      ("tx_size", "u1"), ("tx_type", "u1"), ("flags", "u1"), ("cfl", "u1")])
 
@@ -44,7 +45,7 @@ def oracle():
         L = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
         V, I, Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
         # NB: without argtypes ctypes passes Python ints as 32-bit C ints and truncates pointers.
-        L.orc_encode_frame.argtypes = [V, V, V, V, V, V, V]
+        L.orc_encode_frame.argtypes = [V, V, V, V, V, V, V, V, V]
         L.orc_deblock_frame.argtypes = [V, V, V]
         L.orc_cdef_frame.argtypes = [V, V, V, V, V]
         L.orc_cdef_search_frame.argtypes = [V, V, V, V, V, V]
@@ -76,7 +77,7 @@ def hostlib():
         _host.b200av1_pack_frame.argtypes = [ctypes.POINTER(B200Frame), ctypes.POINTER(B200Records),
                                              ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
         V, I, Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
-        _host.b200av1_rdo_run.argtypes = [V] * 9
+        _host.b200av1_rdo_run.argtypes = [V] * 11
         _host.b200av1_convert_run.argtypes = [V, I, Z, Z, Z, I, I, V, V]
         _host.b200av1_seq_level_idx.argtypes = [V]
         _host.b200avif_mux.argtypes = [V, V, V]
@@ -118,6 +119,9 @@ class Records:
         self.coef = [np.zeros(f.sb_rows * f.sb_cols * 4096, np.int16) for _ in range(3)]
         self.cdef_idx = np.zeros(f.sb_rows * f.sb_cols, np.int8)
         self.rec = [np.zeros((f.mi_rows * 4, f.mi_cols * 4), np.uint16) for _ in range(3)]
+        # open-loop analysis outputs per level (0: 4x4, 1: 8x8, 2: 16x16)
+        self.dec = [np.zeros((f.mi_rows >> lv) * (f.mi_cols >> lv), DEC_DTYPE) for lv in range(3)]
+        self.satd = [np.zeros(((f.mi_rows >> lv) * (f.mi_cols >> lv), 2, 13), np.uint32) for lv in range(3)]
     def c_records(self):
         r = B200Records()
         r.mi = self.mi.ctypes.data
@@ -136,7 +140,7 @@ def oracle_encode(f, rt, src):
     rec = Records(f)
     src3 = list(src) + [src[0]] * (3 - len(src))
     L.orc_encode_frame(ctypes.byref(f), rt.ctypes.data, ptr3(src3), ptr3(rec.rec), rec.mi.ctypes.data,
-                       ptr3(rec.eob), ptr3(rec.coef))
+                       ptr3(rec.eob), ptr3(rec.coef), ptr3(rec.dec), ptr3(rec.satd))
     return rec
 
 def oracle_filters(f, rec, src):

@@ -9,7 +9,8 @@ import harness as H
 
 class RdoJob(ctypes.Structure):
     _fields_ = [("frame", H.B200Frame), ("rate", ctypes.c_void_p), ("src", ctypes.c_void_p * 3), ("rec", ctypes.c_void_p * 3),
-                ("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3), ("decoded", ctypes.c_void_p),
+                ("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3),
+                ("dec", ctypes.c_void_p * 3), ("satd", ctypes.c_void_p * 3),
                 ("cdef_idx", ctypes.c_void_p), ("fin", ctypes.c_void_p * 3)]
 
 
@@ -37,6 +38,17 @@ def compare(ref, out, planes):
     assert np.array_equal(ref.mi, out.mi), "mode info"
 
 
+def compare_analysis(ref, out, f):
+    """stage A outputs: SATD tables and per-block decisions of every analysed level"""
+    for lv in range(3):
+        n = 4 << lv
+        if n < f.partition_min or n > f.partition_max:
+            continue
+        assert np.array_equal(ref.satd[lv], out.satd[lv]), "SATD table level %d" % lv
+        for k in ("cost", "y_mode", "tx_type", "uv_mode"):
+            assert np.array_equal(ref.dec[lv][k], out.dec[lv][k]), "decision %s level %d" % (k, lv)
+
+
 @pytest.mark.parametrize("w,h,depth,planes,tiles,kw", [
     (64, 48, 8, 3, 1, {}),
     (40, 72, 10, 1, 2, dict(partition_min=8, rdo_tx_decision=0)),
@@ -51,13 +63,14 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
     src = H.pad_planes([img[..., c].astype(np.uint16) * (4 if depth == 10 else 1) for c in range(planes)], f)
     ref = H.oracle_encode(f, rt, src)
     out = H.Records(f)
-    dec = np.zeros(f.mi_rows * f.mi_cols, np.uint8)
     job = RdoJob(); job.frame = f; job.rate = rt.ctypes.data
     src3 = list(src) + [src[0]] * (3 - len(src))
     for p in range(3):
         job.src[p] = src3[p].ctypes.data; job.rec[p] = out.rec[p].ctypes.data
         job.eob[p] = out.eob[p].ctypes.data; job.coef[p] = out.coef[p].ctypes.data
-    job.mi = out.mi.ctypes.data; job.decoded = dec.ctypes.data
+    job.mi = out.mi.ctypes.data
+    for lv in range(3):
+        job.dec[lv] = out.dec[lv].ctypes.data; job.satd[lv] = out.satd[lv].ctypes.data
     nt = f.tile_cols * f.tile_rows
     trs = (TileRef * nt)()
     for i in range(nt):
@@ -69,6 +82,7 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
     E.b200_rdo_launch_emu.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     E.b200_filters_launch_emu.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     E.b200_rdo_launch_emu(ctypes.byref(job), trs, nt)
+    compare_analysis(ref, out, f)
     compare(ref, out, planes)
     # in-loop filter stage: deblock in place, CDEF strength search, CDEF output
     ref_fin, ref_deb = H.oracle_filters(f, ref, src)

@@ -24,9 +24,20 @@ def device_rdo(f, src):
     out.final = [np.zeros_like(r) for r in out.rec]
     src3 = list(src) + [src[0]] * (3 - len(src))
     rc = L.b200av1_rdo_run(ctypes.byref(f), H.ptr3(src3), out.mi.ctypes.data, H.ptr3(out.eob), H.ptr3(out.coef), H.ptr3(out.rec),
-                           H.ptr3(out.deblocked), H.ptr3(out.final), out.cdef_idx.ctypes.data)
+                           H.ptr3(out.deblocked), H.ptr3(out.final), out.cdef_idx.ctypes.data, H.ptr3(out.dec), H.ptr3(out.satd))
     assert rc == 0, L.b200avif_last_error_message()
     return out
+
+
+def check_analysis(ref, out, f):
+    """stage A: SATD tables and per-block decisions (cost, modes, transform type) of every analysed level"""
+    for lv in range(3):
+        n = 4 << lv
+        if n < f.partition_min or n > f.partition_max:
+            continue
+        assert np.array_equal(ref.satd[lv], out.satd[lv]), "SATD table level %d" % lv
+        for k in ("cost", "y_mode", "tx_type", "uv_mode"):
+            assert np.array_equal(ref.dec[lv][k], out.dec[lv][k]), "decision %s level %d" % (k, lv)
 
 
 def check_records(ref, out, planes):
@@ -103,6 +114,7 @@ def test_rdo_kernel_matches_oracle_and_dav1d(w, h, depth, planes, q, tiles, kw):
     ref = H.oracle_encode(f, rt, src)
     ref_fin, ref_deb = H.oracle_filters(f, ref, src)
     out = device_rdo(f, src)
+    check_analysis(ref, out, f)
     check_records(ref, out, planes)
     for p in range(planes):
         assert np.array_equal(out.deblocked[p], ref_deb[p]), "deblocked plane %d" % p
@@ -128,6 +140,7 @@ def test_rdo_full_hd_frame_parity():
     ref = H.oracle_encode(f, H.rate_tables(f.base_q_idx), src)
     ref_fin, ref_deb = H.oracle_filters(f, ref, src)
     out = device_rdo(f, src)
+    check_analysis(ref, out, f)
     check_records(ref, out, 3)
     for p in range(3):
         assert np.array_equal(out.final[p], ref_fin[p])
