@@ -101,13 +101,17 @@ template <int N> __device__ __forceinline__ int group_max(int v) {
   for (int m = N / 2; m > 0; m >>= 1) v = max(v, __shfl_xor_sync(FULL, v, m));
   return v;
 }
-// lexicographic minimum of (J, idx) over the warp
-__device__ __forceinline__ void warp_argmin(long long &J, int &idx) {
+// lexicographic minimum of (J, idx) over the warp: J >= 0 and idx < 32 are packed into one 64-bit key
+// (J < 2^58: SSE*256 of a 16x16 10-bit block is < 2^37), so the reduction is five 64-bit shuffles + min
+__device__ __noinline__ void warp_argmin(long long &J, int &idx) {
+  unsigned long long key = J == kInf ? ~0ull : (((unsigned long long)J << 5) | (unsigned)(idx & 31));
+#pragma unroll 1
   for (int m = 16; m > 0; m >>= 1) {
-    const long long oj = __shfl_xor_sync(FULL, J, m);
-    const int oi = __shfl_xor_sync(FULL, idx, m);
-    if (oj < J || (oj == J && oi < idx)) { J = oj; idx = oi; }
+    const unsigned long long o = __shfl_xor_sync(FULL, key, m);
+    key = o < key ? o : key;
   }
+  if (key == ~0ull) { J = kInf; idx = 1 << 20; }
+  else { J = (long long)(key >> 5); idx = (int)(key & 31); }
 }
 
 // ---- edges (AV1 spec 7.11.2, intra edge filter disabled) from plane `r` (source in the analysis, reconstruction in
@@ -160,49 +164,34 @@ __device__ __forceinline__ int dc_value(int n, const uint16_t *A, const uint16_t
 }
 // A, L point at index 0 of the edge arrays (index -1 valid).  dc: precomputed DC value (used for DC_PRED only).
 __device__ __forceinline__ int pred_px(int mode, int n, int i, int j, const uint16_t *A, const uint16_t *L, int dc) {
-  switch (mode) {
-    case DC_PRED: return dc;
-    case V_PRED: return A[j];
-    case H_PRED: return L[i];
-    case PAETH_PRED: {
-      const int tl = A[-1], b = A[j] + L[i] - tl;
-      const int pl = abs(b - L[i]), pt = abs(b - A[j]), ptl = abs(b - tl);
-      return (pl <= pt && pl <= ptl) ? L[i] : (pt <= ptl ? A[j] : tl);
-    }
-    case SMOOTH_PRED: {
-      const uint8_t *w = dv_sm_weights + (n == 4 ? 0 : n == 8 ? 4 : 12);
-      return (w[i] * A[j] + (256 - w[i]) * L[n - 1] + w[j] * L[i] + (256 - w[j]) * A[n - 1] + 256) >> 9;
-    }
-    case SMOOTH_V_PRED: {
-      const uint8_t *w = dv_sm_weights + (n == 4 ? 0 : n == 8 ? 4 : 12);
-      return (w[i] * A[j] + (256 - w[i]) * L[n - 1] + 128) >> 8;
-    }
-    case SMOOTH_H_PRED: {
-      const uint8_t *w = dv_sm_weights + (n == 4 ? 0 : n == 8 ? 4 : 12);
-      return (w[j] * L[i] + (256 - w[j]) * A[n - 1] + 128) >> 8;
-    }
-    default: break;
+  if (mode == DC_PRED) return dc;
+  if (mode == PAETH_PRED) {
+    const int tl = A[-1], b = A[j] + L[i] - tl;
+    const int pl = abs(b - L[i]), pt = abs(b - A[j]), ptl = abs(b - tl);
+    return (pl <= pt && pl <= ptl) ? L[i] : (pt <= ptl ? A[j] : tl);
+  }
+  if (mode >= SMOOTH_PRED) {   // SMOOTH, SMOOTH_V, SMOOTH_H share the two half sums
+    const uint8_t *w = dv_sm_weights + (n == 4 ? 0 : n == 8 ? 4 : 12);
+    const int v = w[i] * A[j] + (256 - w[i]) * L[n - 1], h = w[j] * L[i] + (256 - w[j]) * A[n - 1];
+    return mode == SMOOTH_PRED ? (v + h + 256) >> 9 : (mode == SMOOTH_V_PRED ? (v + 128) >> 8 : (h + 128) >> 8);
   }
   const int p_angle = dv_mode_to_angle[mode];
-  if (p_angle < 90) {
-    const int dx = dv_dr_intra_derivative[p_angle], max_base = 2 * n - 1;
-    const int idx = (i + 1) * dx, base = (idx >> 6) + j, shift = (idx >> 1) & 31;
-    return base < max_base ? (A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5 : A[max_base];
-  }
-  if (p_angle < 180) {
+  if (p_angle == 90) return A[j];
+  if (p_angle == 180) return L[i];
+  if (p_angle > 90 && p_angle < 180) {
     const int dx = dv_dr_intra_derivative[180 - p_angle], dy = dv_dr_intra_derivative[p_angle - 90];
     int idx = (j << 6) - (i + 1) * dx, base = idx >> 6;
-    if (base >= -1) {
-      const int shift = (idx >> 1) & 31;
-      return (A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5;
-    }
-    idx = (i << 6) - (j + 1) * dy; base = idx >> 6;
+    const uint16_t *e = A;
+    if (base < -1) { idx = (i << 6) - (j + 1) * dy; base = idx >> 6; e = L; }
     const int shift = (idx >> 1) & 31;
-    return (L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5;
+    return (e[base] * (32 - shift) + e[base + 1] * shift + 16) >> 5;
   }
-  const int dy = dv_dr_intra_derivative[270 - p_angle], max_base = 2 * n - 1;
-  const int idx = (j + 1) * dy, base = (idx >> 6) + i, shift = (idx >> 1) & 31;
-  return base < max_base ? (L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5 : L[max_base];
+  // zones 1 (< 90, above row) and 3 (> 180, left column) are the same walk with the roles of i / j swapped
+  const bool z1 = p_angle < 90;
+  const uint16_t *e = z1 ? A : L;
+  const int d = dv_dr_intra_derivative[z1 ? p_angle : 270 - p_angle], max_base = 2 * n - 1;
+  const int idx = ((z1 ? i : j) + 1) * d, base = (idx >> 6) + (z1 ? j : i), shift = (idx >> 1) & 31;
+  return base < max_base ? (e[base] * (32 - shift) + e[base + 1] * shift + 16) >> 5 : e[max_base];
 }
 
 // ---- 1-D transforms on register arrays -----------------------------------------------------
@@ -488,11 +477,11 @@ __device__ __noinline__ void predict_block(int mode, int lg, const uint16_t *abo
 __device__ __noinline__ void rank_top2(long long c, int &m0, int &m1) {
   const int lane = lane_id();
   long long j = lane < 13 ? c : kInf;
-  int i = lane < 13 ? lane : 99;
+  int i = lane & 15;
   warp_argmin(j, i);
   m0 = j == kInf ? -1 : i;
   long long j2 = (lane < 13 && lane != m0) ? c : kInf;
-  int i2 = lane < 13 ? lane : 99;
+  int i2 = lane & 15;
   warp_argmin(j2, i2);
   m1 = j2 == kInf ? -1 : i2;
 }
@@ -511,9 +500,11 @@ __device__ __forceinline__ void ctx_from_job(const B200RdoJob &job, TileCtx &t) 
 }
 
 // ---- stage A: analysis of one block by one warp (oracle orc_analyze_block, minus the SATD table) ---------------
-template <bool HBD>
-__device__ __noinline__ void analyze_block(const TileCtx &t, Shared &sh, int x, int y, int lg, const uint32_t *satd, B200BlockDec *out) {
-  const int n = 1 << lg, N2 = n * n, G = 32 >> lg;
+// LG is a template parameter so that each per-level kernel contains only ITS transform size (instruction-cache
+// footprint: ~30 KB for 4x4, the level that dominates the block count).
+template <int LG, bool HBD>
+__device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int x, int y, const uint32_t *satd, B200BlockDec *out) {
+  constexpr int lg = LG, n = 1 << LG, N2 = n * n, G = 32 >> LG;
   const B200Frame *f = t.f;
   const B200RateTables *rt = t.rt;
   const int lane = lane_id(), g = lane >> lg;
@@ -552,7 +543,7 @@ __device__ __noinline__ void analyze_block(const TileCtx &t, Shared &sh, int x, 
     const int m = k == 0 ? m0 : m1;
     const bool ok = ti < 5 && m >= 0 && ((f->tx_type_mask >> ti) & 1) && (f->rdo_tx_decision || ti == first_t);
     if (!__ballot_sync(FULL, ok)) continue;
-    const TrialOut r = trial_dispatch<HBD>(n, t, sh, 0, sh.src[0], sh.pred + (ok ? k : 0) * 256, dv_tx_types[ok ? ti : 0],
+    const TrialOut r = trial_batch<n, HBD>(t, sh, 0, sh.src[0], sh.pred + (ok ? k : 0) * 256, dv_tx_types[ok ? ti : 0],
                                            ok ? m : (m0 >= 0 ? m0 : 0));
     long long wj = kInf;
     int wc = 1 << 20;
@@ -588,7 +579,7 @@ __device__ __noinline__ void analyze_block(const TileCtx &t, Shared &sh, int x, 
         predict_block(mm >= 0 ? mm : 0, lg, sh.above[pp], sh.left[pp], ha, hl, bd, sh.pred + (cc - b * G) * N2);
       }
       __syncwarp();
-      const TrialOut r = trial_dispatch<HBD>(n, t, sh, p, sh.src[p], sh.pred + (ok ? g : 0) * N2, chroma_tx_type(m >= 0 ? m : 0), best_mode);
+      const TrialOut r = trial_batch<n, HBD>(t, sh, p, sh.src[p], sh.pred + (ok ? g : 0) * N2, chroma_tx_type(m >= 0 ? m : 0), best_mode);
       if (ok && (lane & (n - 1)) == 0) { sh.taskD[ci] = r.sse; sh.taskR[ci] = r.rate; sh.taskE[ci] = (uint16_t)r.eob; }
       __syncwarp();
       for (int kk = 0; kk < 2; kk++) {
@@ -671,7 +662,7 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
   const B200RdoJob &job = jobs[blockIdx.y];
   const B200Frame *f = &job.frame;
   const int n = 4 << lv, lg = 2 + lv;
-  if (n < f->partition_min || n > f->partition_max) return;
+  if (n < min(f->partition_min, 8) || n > f->partition_max) return;   // 8x8 always: forced splits at the frame edge
   const int cols = b200_level_cols(f, lv), rows = b200_level_rows(f, lv);
   const int groups = f->planes > 1 ? 2 : 1;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -689,6 +680,7 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
   const int have_ar = ha && b200_unit_before(mi_r - 1, mi_c + n4, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
   const int have_bl = hl && b200_unit_before(mi_r + n4, mi_c - 1, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
   const int mask = grp == 0 ? f->y_mode_mask : f->uv_mode_mask;
+  __shared__ int sh_d[128 * 17];     // per-thread 16 residuals (+1 pad: conflict-free), written by a rolled loop
   uint32_t acc[13];
 #pragma unroll
   for (int m = 0; m < 13; m++) acc[m] = 0;
@@ -728,12 +720,14 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
 #pragma unroll 1
       for (int m = 0; m < 13; m++) {
         if (!((mask >> m) & 1)) continue;
-        int tt[16];
+        int tt[16], d[16];
+#pragma unroll 1
+        for (int k = 0; k < 16; k++) sh_d[threadIdx.x * 17 + k] = s[k] - pred_px(m, n, sy + (k >> 2), sx + (k & 3), A, L, dc);
+#pragma unroll
+        for (int k = 0; k < 16; k++) d[k] = sh_d[threadIdx.x * 17 + k];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          const int d0 = s[i * 4] - pred_px(m, n, sy + i, sx, A, L, dc), d1 = s[i * 4 + 1] - pred_px(m, n, sy + i, sx + 1, A, L, dc);
-          const int d2 = s[i * 4 + 2] - pred_px(m, n, sy + i, sx + 2, A, L, dc), d3 = s[i * 4 + 3] - pred_px(m, n, sy + i, sx + 3, A, L, dc);
-          const int a = d0 + d1, b = d0 - d1, c = d2 + d3, e = d2 - d3;
+          const int a = d[i * 4] + d[i * 4 + 1], b = d[i * 4] - d[i * 4 + 1], c = d[i * 4 + 2] + d[i * 4 + 3], e = d[i * 4 + 2] - d[i * 4 + 3];
           tt[i * 4] = a + c; tt[i * 4 + 1] = b + e; tt[i * 4 + 2] = a - c; tt[i * 4 + 3] = b - e;
         }
         uint32_t total = 0;
@@ -752,13 +746,13 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
 }
 
 // ---- stage A.2: full trials.  One single-warp CTA loops over blocks of level lv (grid-stride), grid.y = job.
-template <bool HBD>
-__global__ void __launch_bounds__(kThreads, 16) b200_analyze_kernel(const B200RdoJob *jobs, int lv) {
+template <int LV, bool HBD>
+__global__ void __launch_bounds__(kThreads, 16) b200_analyze_kernel(const B200RdoJob *jobs) {
   __shared__ Shared sh;
   const B200RdoJob &job = jobs[blockIdx.y];
   const B200Frame *f = &job.frame;
-  const int n = 4 << lv;
-  if (n < f->partition_min || n > f->partition_max) return;
+  constexpr int lv = LV, n = 4 << LV;
+  if (n < min(f->partition_min, 8) || n > f->partition_max) return;   // 8x8 always: forced splits at the frame edge
   TileCtx t;
   ctx_from_job(job, t);
   const int cols = b200_level_cols(f, lv), total = cols * b200_level_rows(f, lv);
@@ -766,7 +760,7 @@ __global__ void __launch_bounds__(kThreads, 16) b200_analyze_kernel(const B200Rd
   for (int blk = blockIdx.x; blk < total; blk += gridDim.x) {
     const int x = (blk % cols) * n, y = (blk / cols) * n;
     tile_of_unit(f, y >> 2, x >> 2, t);
-    analyze_block<HBD>(t, sh, x, y, 2 + lv, job.satd[lv] + (size_t)blk * 26, job.dec[lv] + blk);
+    analyze_block<2 + LV, HBD>(t, sh, x, y, job.satd[lv] + (size_t)blk * 26, job.dec[lv] + blk);
   }
 }
 
@@ -867,8 +861,9 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
   cudaStream_t st = (cudaStream_t)stream;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(b200_analyze_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(b200_analyze_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#define B200_CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
+    B200_CARVE((b200_analyze_kernel<0, false>)); B200_CARVE((b200_analyze_kernel<1, false>)); B200_CARVE((b200_analyze_kernel<2, false>));
+    B200_CARVE((b200_analyze_kernel<0, true>)); B200_CARVE((b200_analyze_kernel<1, true>)); B200_CARVE((b200_analyze_kernel<2, true>));
     cudaFuncSetAttribute(b200_recon_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(b200_recon_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
@@ -880,8 +875,15 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     // enough single-warp CTAs to fill the machine several times over, grid-stride inside
     const int per_job = min(nblk, max(1, (148 * 16 * 4) / n_jobs));
     dim3 ga(per_job, n_jobs);
-    if (high_bitdepth) b200_analyze_kernel<true><<<ga, kThreads, 0, st>>>(d_jobs, lv);
-    else b200_analyze_kernel<false><<<ga, kThreads, 0, st>>>(d_jobs, lv);
+    if (high_bitdepth) {
+      if (lv == 0) b200_analyze_kernel<0, true><<<ga, kThreads, 0, st>>>(d_jobs);
+      else if (lv == 1) b200_analyze_kernel<1, true><<<ga, kThreads, 0, st>>>(d_jobs);
+      else b200_analyze_kernel<2, true><<<ga, kThreads, 0, st>>>(d_jobs);
+    } else {
+      if (lv == 0) b200_analyze_kernel<0, false><<<ga, kThreads, 0, st>>>(d_jobs);
+      else if (lv == 1) b200_analyze_kernel<1, false><<<ga, kThreads, 0, st>>>(d_jobs);
+      else b200_analyze_kernel<2, false><<<ga, kThreads, 0, st>>>(d_jobs);
+    }
   }
   dim3 gd((max_blocks4 / 16 + 64 + 127) / 128, n_jobs);
   b200_decide_kernel<<<gd, 128, 0, st>>>(d_jobs);
@@ -894,7 +896,12 @@ static const B200RdoJob *g_emu_jobs;
 static const B200TileRef *g_emu_tiles;
 static int g_emu_lv;
 static void emu_satd(void *) { b200_satd_kernel(g_emu_jobs, g_emu_lv); }
-static void emu_analyze(void *) { if (g_emu_jobs[0].frame.bit_depth > 8) b200_analyze_kernel<true>(g_emu_jobs, g_emu_lv); else b200_analyze_kernel<false>(g_emu_jobs, g_emu_lv); }
+static void emu_analyze(void *) {
+  const bool hbd = g_emu_jobs[0].frame.bit_depth > 8;
+  if (g_emu_lv == 0) { if (hbd) b200_analyze_kernel<0, true>(g_emu_jobs); else b200_analyze_kernel<0, false>(g_emu_jobs); }
+  else if (g_emu_lv == 1) { if (hbd) b200_analyze_kernel<1, true>(g_emu_jobs); else b200_analyze_kernel<1, false>(g_emu_jobs); }
+  else { if (hbd) b200_analyze_kernel<2, true>(g_emu_jobs); else b200_analyze_kernel<2, false>(g_emu_jobs); }
+}
 static void emu_decide(void *) { b200_decide_kernel(g_emu_jobs); }
 static void emu_recon(void *) { if (g_emu_jobs[0].frame.bit_depth > 8) b200_recon_kernel<true>(g_emu_jobs, g_emu_tiles); else b200_recon_kernel<false>(g_emu_jobs, g_emu_tiles); }
 extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *tiles, int n_tiles) {

@@ -509,7 +509,8 @@ void orc_encode_frame(const B200Frame *f, const B200RateTables *rt, uint16_t *co
     const size_t nblk = (size_t)b200_level_rows(f, lv) * b200_level_cols(f, lv);
     e.dec[lv] = (dec_out && dec_out[lv]) ? dec_out[lv] : (B200BlockDec *)calloc(nblk ? nblk : 1, sizeof(B200BlockDec));
     const int n = 4 << lv;
-    if (n < f->partition_min || n > f->partition_max) continue;
+    /* 8x8 is always analysed: 16x16 regions that stick out of the frame are forced to split down to 8x8 */
+    if (n < (f->partition_min < 8 ? f->partition_min : 8) || n > f->partition_max) continue;
     for (int by = 0; by < b200_level_rows(f, lv); by++)
       for (int bx = 0; bx < b200_level_cols(f, lv); bx++) {
         int tr, tc;

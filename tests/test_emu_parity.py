@@ -42,7 +42,7 @@ def compare_analysis(ref, out, f):
     """stage A outputs: SATD tables and per-block decisions of every analysed level"""
     for lv in range(3):
         n = 4 << lv
-        if n < f.partition_min or n > f.partition_max:
+        if n < min(f.partition_min, 8) or n > f.partition_max:
             continue
         assert np.array_equal(ref.satd[lv], out.satd[lv]), "SATD table level %d" % lv
         for k in ("cost", "y_mode", "tx_type", "uv_mode"):
@@ -52,6 +52,7 @@ def compare_analysis(ref, out, f):
 @pytest.mark.parametrize("w,h,depth,planes,tiles,kw", [
     (64, 48, 8, 3, 1, {}),
     (40, 72, 10, 1, 2, dict(partition_min=8, rdo_tx_decision=0)),
+    (72, 40, 8, 3, 1, dict(partition_min=16, partition_max=16, rdo_tx_decision=0)),   # forced 8x8 splits at the edges
 ])
 def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
     E = emu_lib()

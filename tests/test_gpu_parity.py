@@ -33,7 +33,7 @@ def check_analysis(ref, out, f):
     """stage A: SATD tables and per-block decisions (cost, modes, transform type) of every analysed level"""
     for lv in range(3):
         n = 4 << lv
-        if n < f.partition_min or n > f.partition_max:
+        if n < min(f.partition_min, 8) or n > f.partition_max:
             continue
         assert np.array_equal(ref.satd[lv], out.satd[lv]), "SATD table level %d" % lv
         for k in ("cost", "y_mode", "tx_type", "uv_mode"):
@@ -100,6 +100,7 @@ CASES = [
     (640, 360, 8, 3, 147, 12, dict(partition_min=8, rdo_tx_decision=0, reduced_tx_set=0)),
     (512, 512, 10, 3, 66, 16, {}),
     (256, 200, 8, 3, 199, 2, {}),
+    (129, 101, 10, 3, 181, 1, dict(partition_min=16, partition_max=16, rdo_tx_decision=0, enable_cdef=0)),
 ]
 
 
