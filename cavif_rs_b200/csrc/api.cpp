@@ -438,10 +438,18 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
     if (im.on_device) d_in = im.pixels;
     else {
       const size_t bytes = (im.stride * (im.h - 1) + im.w) * im.channels;
-      uint8_t *stage = c.pin.take<uint8_t>(bytes);
-      memcpy(stage, im.pixels, bytes);
+      // page-locked caller memory is copied straight to the device; pageable memory goes through the pinned arena
+      cudaPointerAttributes attr;
+      const bool pinned = cudaPointerGetAttributes(&attr, im.pixels) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+      if (!pinned) cudaGetLastError();
+      const uint8_t *from = im.pixels;
+      if (!pinned) {
+        uint8_t *stage = c.pin.take<uint8_t>(bytes);
+        memcpy(stage, im.pixels, bytes);
+        from = stage;
+      }
       uint8_t *d = c.dev.take<uint8_t>(bytes + 16);
-      CU(cudaMemcpyAsync(d, stage, bytes, cudaMemcpyHostToDevice, c.stream));
+      CU(cudaMemcpyAsync(d, from, bytes, cudaMemcpyHostToDevice, c.stream));
       h2d += bytes;
       d_in = d;
     }

@@ -600,7 +600,8 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
     total += ((long long)f->lambda_q8 * rt->skip[0][all_zero]) >> 8;
     B200BlockDec d;
     d.cost = total; d.y_mode = (uint8_t)best_mode; d.tx_type = (uint8_t)best_tt; d.uv_mode = (uint8_t)uv_best;
-    d.pad[0] = d.pad[1] = d.pad[2] = d.pad[3] = d.pad[4] = 0;
+    d.all_zero = (uint8_t)all_zero;
+    d.pad[0] = d.pad[1] = d.pad[2] = d.pad[3] = 0;
     *out = d;
   }
   __syncwarp();
@@ -669,6 +670,7 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
   if (gid >= cols * rows * groups) return;
   const int grp = gid / (cols * rows), blk = gid % (cols * rows);     // same group for neighbouring threads
   const int bx = blk % cols, by = blk / cols, x = bx * n, y = by * n;
+  if (lv == 0 && job.dec[1][(by >> 1) * b200_level_cols(f, 1) + (bx >> 1)].all_zero) return;   // pruned by the 8x8 parent
   TileCtx t;
   ctx_from_job(job, t);
   tile_of_unit(f, y >> 2, x >> 2, t);
@@ -747,7 +749,7 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
 
 // ---- stage A.2: full trials.  One single-warp CTA loops over blocks of level lv (grid-stride), grid.y = job.
 template <int LV, bool HBD>
-__global__ void __launch_bounds__(kThreads, 16) b200_analyze_kernel(const B200RdoJob *jobs) {
+__global__ void __launch_bounds__(kThreads, LV == 0 ? 24 : (LV == 1 ? 24 : 16)) b200_analyze_kernel(const B200RdoJob *jobs) {
   __shared__ Shared sh;
   const B200RdoJob &job = jobs[blockIdx.y];
   const B200Frame *f = &job.frame;
@@ -759,6 +761,15 @@ __global__ void __launch_bounds__(kThreads, 16) b200_analyze_kernel(const B200Rd
 #pragma unroll 1
   for (int blk = blockIdx.x; blk < total; blk += gridDim.x) {
     const int x = (blk % cols) * n, y = (blk / cols) * n;
+    if (LV == 0 && job.dec[1][((blk / cols) >> 1) * b200_level_cols(f, 1) + ((blk % cols) >> 1)].all_zero) {
+      if (lane_id() == 0) {   // pruned by the 8x8 parent: never split
+        B200BlockDec d;
+        d.cost = B200_COST_PRUNED; d.y_mode = 0; d.tx_type = 0; d.uv_mode = 0; d.all_zero = 0;
+        d.pad[0] = d.pad[1] = d.pad[2] = d.pad[3] = 0;
+        job.dec[0][blk] = d;
+      }
+      continue;
+    }
     tile_of_unit(f, y >> 2, x >> 2, t);
     analyze_block<2 + LV, HBD>(t, sh, x, y, job.satd[lv] + (size_t)blk * 26, job.dec[lv] + blk);
   }
@@ -868,7 +879,7 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     cudaFuncSetAttribute(b200_recon_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  for (int lv = 0; lv < 3; lv++) {
+  for (int lv = 2; lv >= 0; lv--) {   // large to small: 4x4 analysis is pruned by its 8x8 parent
     const int nblk = max_blocks4 >> (2 * lv);
     dim3 gs((nblk * 2 + 127) / 128, n_jobs);
     b200_satd_kernel<<<gs, 128, 0, st>>>(d_jobs, lv);
@@ -908,7 +919,7 @@ extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *ti
   g_emu_jobs = jobs; g_emu_tiles = tiles;
   const B200Frame *f = &jobs[0].frame;
   const int nblk4 = f->mi_rows * f->mi_cols;
-  for (g_emu_lv = 0; g_emu_lv < 3; g_emu_lv++) {
+  for (g_emu_lv = 2; g_emu_lv >= 0; g_emu_lv--) {
     const int nblk = (f->mi_rows >> g_emu_lv) * (f->mi_cols >> g_emu_lv);
     if (nblk == 0) continue;
     emu::launch(emu_satd, nullptr, (unsigned)((nblk * 2 + 127) / 128), 128);

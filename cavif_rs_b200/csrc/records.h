@@ -81,8 +81,13 @@ typedef struct B200Frame {
 // Decision of the open-loop analysis for one block (analysis stage -> partition decision -> reconstruction).
 typedef struct B200BlockDec {
   int64_t cost;        // J = SSE*256 + lambda*R of the best (mode, transform type) per plane, + skip flag cost
-  uint8_t y_mode, tx_type, uv_mode, pad[5];
+  uint8_t y_mode, tx_type, uv_mode;
+  uint8_t all_zero;    // every plane quantised to zero in the analysis (the block would be coded as "skip")
+  uint8_t pad[4];
 } B200BlockDec;
+// Early termination of the partition search: the four 4x4 children of an 8x8 block whose analysis quantised to
+// all-zero are not analysed; their cost is this sentinel so the split can never win.
+#define B200_COST_PRUNED ((int64_t)1 << 60)
 // Number of analysed blocks per row / column at level lv (0: 4x4, 1: 8x8, 2: 16x16); blocks that stick out of the
 // (8-pixel aligned) coded frame are not analysed.
 static inline B200_HD int b200_level_cols(const struct B200Frame *f, int lv);

@@ -401,6 +401,7 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
   memset(out, 0, sizeof(*out));
   out->cost = total;
   out->y_mode = (uint8_t)best_mode; out->tx_type = (uint8_t)best_tt; out->uv_mode = (uint8_t)uv_best;
+  out->all_zero = (uint8_t)all_zero;
 }
 
 /* ---- stage B: partition decision of one 16x16 region from the analysed costs (context-0 partition rates) */
@@ -508,6 +509,8 @@ void orc_encode_frame(const B200Frame *f, const B200RateTables *rt, uint16_t *co
   for (int lv = 0; lv < 3; lv++) {
     const size_t nblk = (size_t)b200_level_rows(f, lv) * b200_level_cols(f, lv);
     e.dec[lv] = (dec_out && dec_out[lv]) ? dec_out[lv] : (B200BlockDec *)calloc(nblk ? nblk : 1, sizeof(B200BlockDec));
+  }
+  for (int lv = 2; lv >= 0; lv--) {     /* large to small: 4x4 analysis is pruned by its 8x8 parent */
     const int n = 4 << lv;
     /* 8x8 is always analysed: 16x16 regions that stick out of the frame are forced to split down to 8x8 */
     if (n < (f->partition_min < 8 ? f->partition_min : 8) || n > f->partition_max) continue;
@@ -518,6 +521,12 @@ void orc_encode_frame(const B200Frame *f, const B200RateTables *rt, uint16_t *co
         tile_bounds(&e, tr, tc);
         uint32_t sy[13], suv[13];
         const size_t bi = (size_t)by * b200_level_cols(f, lv) + bx;
+        if (lv == 0 && e.dec[1][(size_t)(by >> 1) * b200_level_cols(f, 1) + (bx >> 1)].all_zero) {
+          memset(&e.dec[0][bi], 0, sizeof(B200BlockDec));
+          e.dec[0][bi].cost = B200_COST_PRUNED;
+          if (satd_out && satd_out[0]) memset(satd_out[0] + bi * 26, 0, 26 * sizeof(uint32_t));
+          continue;
+        }
         orc_analyze_block(&e, bx * n, by * n, n, &e.dec[lv][bi], sy, suv);
         if (satd_out && satd_out[lv]) { memcpy(satd_out[lv] + bi * 26, sy, sizeof(sy)); memcpy(satd_out[lv] + bi * 26 + 13, suv, sizeof(suv)); }
       }

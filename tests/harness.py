@@ -27,7 +27,7 @@ class B200Records(ctypes.Structure):
 RATE_TABLES_BYTES = 2 * (20 * 10 + 3 * 2 + 5 * 5 * 13 + 2 * 13 * 14 + 8 * 7 + 8 + 6 * 16 + 2 * 4 * 13 * 16 + 5 * 13 * 2 +
                          4 * 2 * 12 + 5 * 2 * 9 * 2 + 2 * 3 * 2 + 5 * 2 * 4 * 3 + 5 * 2 * 42 * 4 + 4 * 2 * 21 * 13)
 
-DEC_DTYPE = np.dtype([("cost", "<i8"), ("y_mode", "u1"), ("tx_type", "u1"), ("uv_mode", "u1"), ("pad", "u1", 5)])
+DEC_DTYPE = np.dtype([("cost", "<i8"), ("y_mode", "u1"), ("tx_type", "u1"), ("uv_mode", "u1"), ("all_zero", "u1"), ("pad", "u1", 4)])
 MI_DTYPE = np.dtype([("bsize", "u1"), ("y_mode", "u1"), ("uv_mode", "u1"), ("angle", "u1"),
                      ("tx_size", "u1"), ("tx_type", "u1"), ("flags", "u1"), ("cfl", "u1")])
 
