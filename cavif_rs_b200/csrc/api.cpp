@@ -240,9 +240,10 @@ int rate_tables_for(Context &c, int qidx, B200RateTables **out) {
   return 0;
 }
 
-// Launch the RDO kernel for a set of jobs (device buffers ready, sources filled) and fetch records.
-int run_rdo_and_fetch(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin, bool fetch_rec,
-                      std::vector<std::vector<uint16_t>> *rec_out, std::vector<std::vector<uint16_t>> *pre_filter_rec = nullptr) {
+// Issue (asynchronously, on c.stream) the RDO stages + in-loop filters for a set of jobs whose device buffers are
+// ready and sources filled, and the D2H copies of the block records.  finish_rdo() waits for it.
+int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin, bool fetch_rec,
+              std::vector<std::vector<uint16_t>> *rec_out, std::vector<std::vector<uint16_t>> *pre_filter_rec = nullptr) {
   std::vector<B200RdoJob> hj(jobs.size());
   std::vector<B200TileRef> tiles;
   for (size_t i = 0; i < jobs.size(); i++) {
@@ -316,16 +317,25 @@ int run_rdo_and_fetch(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Are
       }
   }
   CU(cudaEventRecord(c.ev[3], c.stream));
-  CU(cudaStreamSynchronize(c.stream));
   g_d2h += d2h;
+  return 0;
+}
+
+// Wait for the device work issued by issue_rdo() on this context and account its CUDA-event times.
+int finish_rdo(Context &c) {
+  CU(cudaStreamSynchronize(c.stream));
   float ms_rdo = 0, ms_tot = 0;
   cudaEventElapsedTime(&ms_rdo, c.ev[1], c.ev[2]);
   cudaEventElapsedTime(&ms_tot, c.ev[0], c.ev[3]);
-  {
-    std::lock_guard<std::mutex> lk(g_stat_mu);
-    g_ms_rdo += ms_rdo; g_ms_total += ms_tot;
-  }
+  std::lock_guard<std::mutex> lk(g_stat_mu);
+  g_ms_rdo += ms_rdo; g_ms_total += ms_tot;
   return 0;
+}
+
+int run_rdo_and_fetch(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin, bool fetch_rec,
+                      std::vector<std::vector<uint16_t>> *rec_out, std::vector<std::vector<uint16_t>> *pre_filter_rec = nullptr) {
+  if (int e = issue_rdo(c, jobs, dev, pin, fetch_rec, rec_out, pre_filter_rec)) return e;
+  return finish_rdo(c);
 }
 
 void pack_jobs(std::vector<FrameJob *> &jobs) {
@@ -369,7 +379,6 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
     return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
   std::unique_ptr<Context> ctx;
   if (int e = acquire_context(enc.device, ctx)) return e;
-  Context &c = *ctx;
   struct Release { std::unique_ptr<Context> &c; ~Release() { release_context(c); } } rel{ctx};
   const int depth = enc.output_depth == 8 ? 8 : 10;
   const int mc = enc.color_model == B200AVIF_COLOR_YCBCR ? B200AVIF_MC_BT601 : B200AVIF_MC_IDENTITY;
@@ -388,93 +397,124 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
       im.pixels = im.cleaned.data(); im.stride = im.w;
     }
   }
-  // ---- frame descriptions + arena sizing
-  size_t dev_bytes = 1 << 20, pin_bytes = 1 << 20;
+  // ---- frame descriptions
   for (ImageWork &im : imgs) {
     const int cmc = im.raw ? im.raw_mc : mc;
     const int range = im.raw ? im.raw_range : 1;
     if (int e = configure_frame(&im.color.f, im.w, im.h, depth, false, enc.quantizer, enc.speed, enc.threads, range, true, cmc)) { im.status = e; continue; }
     if (int e = configure_frame(&im.alpha.f, im.w, im.h, depth, true, enc.alpha_quantizer, enc.speed, enc.threads, 1, false, 2)) { im.status = e; continue; }
-    dev_bytes += job_dev_bytes(im.color, true) + job_dev_bytes(im.alpha, true);
-    pin_bytes += job_pin_bytes(im.color) + job_pin_bytes(im.alpha);
-    const size_t in_bytes = im.raw ? (im.w * im.h * 2 * 4) : (im.stride * im.h * im.channels);
-    dev_bytes += align256(in_bytes) + 512;
-    if (!im.on_device) pin_bytes += align256(in_bytes) + 512;
   }
-  if (c.dev.reserve(dev_bytes) || c.pin.reserve(pin_bytes)) return B200AVIF_ENCODING_ERROR;
-  c.dev.reset(); c.pin.reset();
-  CU(cudaEventRecord(c.ev[0], c.stream));
-  // ---- upload + convert
-  uint64_t h2d = 0;
-  int *h_flags = c.pin.take<int>(imgs.size());
-  int *d_flags = c.dev.take<int>(imgs.size());
-  CU(cudaMemsetAsync(d_flags, 0, imgs.size() * sizeof(int), c.stream));
-  for (size_t i = 0; i < imgs.size(); i++) {
-    ImageWork &im = imgs[i];
-    if (im.status) continue;
-    job_take(im.color, c.dev, c.pin, true);
-    job_take(im.alpha, c.dev, c.pin, true);
-    const int cw = im.color.f.mi_cols * 4, ch = im.color.f.mi_rows * 4;
-    if (im.raw) {
-      for (int p = 0; p < 3; p++) {
-        uint16_t *stage = c.pin.take<uint16_t>(im.w * im.h);
-        memcpy(stage, im.raw_planes[p].data(), im.w * im.h * 2);
-        uint16_t *d = c.dev.take<uint16_t>(im.w * im.h);
-        CU(cudaMemcpyAsync(d, stage, im.w * im.h * 2, cudaMemcpyHostToDevice, c.stream));
-        if (int e = b200_pad_plane_launch(d, (int)im.w, (int)im.h, (int)im.w, im.color.d_src[p], cw, ch, c.stream)) return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
-        g_launches++; h2d += im.w * im.h * 2;
-      }
-      if (im.raw_has_alpha) {
-        uint16_t *stage = c.pin.take<uint16_t>(im.w * im.h);
-        memcpy(stage, im.raw_alpha.data(), im.w * im.h * 2);
-        uint16_t *d = c.dev.take<uint16_t>(im.w * im.h);
-        CU(cudaMemcpyAsync(d, stage, im.w * im.h * 2, cudaMemcpyHostToDevice, c.stream));
-        if (int e = b200_pad_plane_launch(d, (int)im.w, (int)im.h, (int)im.w, im.alpha.d_src[0], cw, ch, c.stream)) return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
-        g_launches++; h2d += im.w * im.h * 2;
-      }
-      continue;
+  // ---- software pipeline over chunks of the batch on two contexts (stream + arenas each):
+  //      upload/convert of chunk k+1 overlaps the RDO of chunk k, symbol packing (CPU threads) of chunk k overlaps
+  //      the device work of chunk k+1.
+  const size_t n_img = imgs.size();
+  const size_t n_chunks = n_img >= 16 ? 4 : (n_img >= 4 ? 2 : 1);
+  std::unique_ptr<Context> ctx2;
+  if (n_chunks > 1) { if (int e = acquire_context(enc.device, ctx2)) return e; }
+  struct Release2 { std::unique_ptr<Context> &c; ~Release2() { if (c) release_context(c); } } rel2{ctx2};
+  Context *cx[2] = {ctx.get(), n_chunks > 1 ? ctx2.get() : ctx.get()};
+  struct Chunk { size_t a, b; int *h_flags = nullptr; std::vector<FrameJob *> jobs; std::thread packer; bool issued = false; };
+  std::vector<Chunk> chunks(n_chunks);
+  for (size_t k = 0; k < n_chunks; k++) { chunks[k].a = k * n_img / n_chunks; chunks[k].b = (k + 1) * n_img / n_chunks; }
+  auto join_all = [&]() { for (Chunk &ch : chunks) if (ch.packer.joinable()) ch.packer.join(); };
+  struct Joiner { std::function<void()> f; ~Joiner() { f(); } } joiner{join_all};
+
+  auto phase1 = [&](Context &c, Chunk &ch) -> int {       // upload + colour conversion + alpha flags (async)
+    size_t dev_bytes = 1 << 20, pin_bytes = 1 << 20;
+    for (size_t i = ch.a; i < ch.b; i++) {
+      ImageWork &im = imgs[i];
+      if (im.status) continue;
+      dev_bytes += job_dev_bytes(im.color, true) + job_dev_bytes(im.alpha, true);
+      pin_bytes += job_pin_bytes(im.color) + job_pin_bytes(im.alpha);
+      const size_t in_bytes = im.raw ? (im.w * im.h * 2 * 4) : (im.stride * im.h * im.channels);
+      dev_bytes += align256(in_bytes) + 512;
+      if (!im.on_device) pin_bytes += align256(in_bytes) + 512;
     }
-    const uint8_t *d_in;
-    if (im.on_device) d_in = im.pixels;
-    else {
-      const size_t bytes = (im.stride * (im.h - 1) + im.w) * im.channels;
-      // page-locked caller memory is copied straight to the device; pageable memory goes through the pinned arena
-      cudaPointerAttributes attr;
-      const bool pinned = cudaPointerGetAttributes(&attr, im.pixels) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-      if (!pinned) cudaGetLastError();
-      const uint8_t *from = im.pixels;
-      if (!pinned) {
-        uint8_t *stage = c.pin.take<uint8_t>(bytes);
-        memcpy(stage, im.pixels, bytes);
-        from = stage;
+    if (c.dev.reserve(dev_bytes) || c.pin.reserve(pin_bytes)) return B200AVIF_ENCODING_ERROR;
+    c.dev.reset(); c.pin.reset();
+    CU(cudaEventRecord(c.ev[0], c.stream));
+    uint64_t h2d = 0;
+    const size_t cnt = ch.b - ch.a;
+    ch.h_flags = c.pin.take<int>(cnt);
+    int *d_flags = c.dev.take<int>(cnt);
+    CU(cudaMemsetAsync(d_flags, 0, cnt * sizeof(int), c.stream));
+    for (size_t i = ch.a; i < ch.b; i++) {
+      ImageWork &im = imgs[i];
+      if (im.status) continue;
+      job_take(im.color, c.dev, c.pin, true);
+      job_take(im.alpha, c.dev, c.pin, true);
+      const int cw = im.color.f.mi_cols * 4, chh = im.color.f.mi_rows * 4;
+      if (im.raw) {
+        for (int p = 0; p < 4; p++) {
+          if (p == 3 && !im.raw_has_alpha) break;
+          const std::vector<uint16_t> &srcv = p < 3 ? im.raw_planes[p] : im.raw_alpha;
+          uint16_t *stage = c.pin.take<uint16_t>(im.w * im.h);
+          memcpy(stage, srcv.data(), im.w * im.h * 2);
+          uint16_t *d = c.dev.take<uint16_t>(im.w * im.h);
+          CU(cudaMemcpyAsync(d, stage, im.w * im.h * 2, cudaMemcpyHostToDevice, c.stream));
+          if (int e = b200_pad_plane_launch(d, (int)im.w, (int)im.h, (int)im.w, p < 3 ? im.color.d_src[p] : im.alpha.d_src[0], cw, chh, c.stream))
+            return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
+          g_launches++; h2d += im.w * im.h * 2;
+        }
+        continue;
       }
-      uint8_t *d = c.dev.take<uint8_t>(bytes + 16);
-      CU(cudaMemcpyAsync(d, from, bytes, cudaMemcpyHostToDevice, c.stream));
-      h2d += bytes;
-      d_in = d;
+      const uint8_t *d_in;
+      if (im.on_device) d_in = im.pixels;
+      else {
+        const size_t bytes = (im.stride * (im.h - 1) + im.w) * im.channels;
+        // page-locked caller memory is copied straight to the device; pageable memory goes through the pinned arena
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, im.pixels) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!pinned) cudaGetLastError();
+        const uint8_t *from = im.pixels;
+        if (!pinned) {
+          uint8_t *stage = c.pin.take<uint8_t>(bytes);
+          memcpy(stage, im.pixels, bytes);
+          from = stage;
+        }
+        uint8_t *d = c.dev.take<uint8_t>(bytes + 16);
+        CU(cudaMemcpyAsync(d, from, bytes, cudaMemcpyHostToDevice, c.stream));
+        h2d += bytes;
+        d_in = d;
+      }
+      if (int e = b200_convert_launch(d_in, im.channels, (int)im.w, (int)im.h, (int)im.stride, cw, chh, depth, enc.color_model,
+                                      im.color.d_src[0], im.color.d_src[1], im.color.d_src[2],
+                                      im.channels == 4 ? im.alpha.d_src[0] : nullptr, im.channels == 4 ? d_flags + (i - ch.a) : nullptr, c.stream))
+        return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
+      g_launches++;
     }
-    if (int e = b200_convert_launch(d_in, im.channels, (int)im.w, (int)im.h, (int)im.stride, cw, ch, depth, enc.color_model,
-                                    im.color.d_src[0], im.color.d_src[1], im.color.d_src[2],
-                                    im.channels == 4 ? im.alpha.d_src[0] : nullptr, im.channels == 4 ? d_flags + i : nullptr, c.stream))
-      return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
-    g_launches++;
+    g_h2d += h2d;
+    CU(cudaMemcpyAsync(ch.h_flags, d_flags, cnt * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    ch.issued = true;
+    return 0;
+  };
+  auto phase2 = [&](Context &c, Chunk &ch) -> int {       // needs the alpha flags: RDO + filters + record D2H (async)
+    CU(cudaStreamSynchronize(c.stream));
+    for (size_t i = ch.a; i < ch.b; i++) {
+      ImageWork &im = imgs[i];
+      if (im.status) continue;
+      im.use_alpha = im.raw ? im.raw_has_alpha : (im.channels == 4 && ch.h_flags[i - ch.a] != 0);
+      ch.jobs.push_back(&im.color);
+      if (im.use_alpha) ch.jobs.push_back(&im.alpha);
+    }
+    if (ch.jobs.empty()) return 0;
+    return issue_rdo(c, ch.jobs, c.dev, c.pin, false, nullptr);
+  };
+  auto phase3 = [&](Context &c, Chunk &ch) -> int {       // wait for the device, hand the records to the packer thread
+    if (ch.jobs.empty()) return 0;
+    if (int e = finish_rdo(c)) return e;
+    ch.packer = std::thread([&ch]() { pack_jobs(ch.jobs); });
+    return 0;
+  };
+  for (size_t k = 0; k < n_chunks; k++) {
+    Context &c = *cx[k & 1];
+    if (k >= 2 && chunks[k - 2].packer.joinable()) chunks[k - 2].packer.join();   // its pinned arena is about to be reused
+    if (int e = phase1(c, chunks[k])) return e;
+    if (int e = phase2(c, chunks[k])) return e;           // queue this chunk's device work before waiting for the previous one
+    if (k >= 1) { if (int e = phase3(*cx[(k - 1) & 1], chunks[k - 1])) return e; }
   }
-  g_h2d += h2d;
-  CU(cudaMemcpyAsync(h_flags, d_flags, imgs.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-  CU(cudaStreamSynchronize(c.stream));
-  // ---- jobs
-  std::vector<FrameJob *> jobs;
-  for (size_t i = 0; i < imgs.size(); i++) {
-    ImageWork &im = imgs[i];
-    if (im.status) continue;
-    im.use_alpha = im.raw ? im.raw_has_alpha : (im.channels == 4 && h_flags[i] != 0);
-    jobs.push_back(&im.color);
-    if (im.use_alpha) jobs.push_back(&im.alpha);
-  }
-  if (!jobs.empty()) {
-    if (int e = run_rdo_and_fetch(c, jobs, c.dev, c.pin, false, nullptr)) return e;
-    pack_jobs(jobs);
-  }
+  if (int e = phase3(*cx[(n_chunks - 1) & 1], chunks[n_chunks - 1])) return e;
+  join_all();
   // ---- mux
   const auto t0 = std::chrono::steady_clock::now();
   int first_err = 0;

@@ -53,10 +53,7 @@ __device__ const uint8_t dv_iscan_g[336] = {
 };
 __constant__ const uint8_t dv_sm_weights[4 + 8 + 16] = {255, 149, 85, 64, 255, 197, 146, 105, 73, 50, 37, 32,
                                                         255, 225, 196, 170, 145, 123, 102, 84, 68, 54, 43, 33, 26, 20, 17, 16};
-__constant__ const uint8_t dv_intra_mode_context[13] = {0, 1, 2, 3, 4, 4, 4, 4, 3, 0, 1, 2, 0};
 __constant__ const uint8_t dv_tx_types[5] = {TX_DCT_DCT, TX_ADST_DCT, TX_DCT_ADST, TX_ADST_ADST, TX_IDTX};
-__constant__ const uint8_t dv_bw4[22] = {1, 1, 2, 2, 2, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 1, 4, 2, 8, 4, 16};
-__constant__ const uint8_t dv_bh4[22] = {1, 2, 1, 2, 4, 2, 4, 8, 4, 8, 16, 8, 16, 32, 16, 32, 4, 1, 8, 2, 16, 4};
 
 struct Shared {
   uint16_t src[3][256];
@@ -102,29 +99,33 @@ template <int N> __device__ __forceinline__ int group_max(int v) {
   return v;
 }
 // lexicographic minimum of (J, idx) over the warp: J >= 0 and idx < 32 are packed into one 64-bit key
-// (J < 2^58: SSE*256 of a 16x16 10-bit block is < 2^37), so the reduction is five 64-bit shuffles + min
-__device__ __noinline__ void warp_argmin(long long &J, int &idx) {
-  unsigned long long key = J == kInf ? ~0ull : (((unsigned long long)J << 5) | (unsigned)(idx & 31));
-#pragma unroll 1
-  for (int m = 16; m > 0; m >>= 1) {
-    const unsigned long long o = __shfl_xor_sync(FULL, key, m);
-    key = o < key ? o : key;
-  }
-  if (key == ~0ull) { J = kInf; idx = 1 << 20; }
-  else { J = (long long)(key >> 5); idx = (int)(key & 31); }
+// (J < 2^58: SSE*256 of a 16x16 10-bit block is < 2^37); the 64-bit minimum is two hardware warp reductions (REDUX)
+__device__ __forceinline__ void warp_argmin(long long &J, int &idx) {
+  const unsigned long long key = J == kInf ? ~0ull : (((unsigned long long)J << 5) | (unsigned)(idx & 31));
+  const unsigned hi = (unsigned)(key >> 32);
+  const unsigned mh = __reduce_min_sync(FULL, hi);
+  const unsigned ml = __reduce_min_sync(FULL, hi == mh ? (unsigned)key : 0xffffffffu);
+  const unsigned long long best = ((unsigned long long)mh << 32) | ml;
+  if (best == ~0ull) { J = kInf; idx = 1 << 20; }
+  else { J = (long long)(best >> 5); idx = (int)(best & 31); }
 }
 
 // ---- edges (AV1 spec 7.11.2, intra edge filter disabled) from plane `r` (source in the analysis, reconstruction in
 // the final pass) into sh.above/left[slot]; top-right / bottom-left availability = static coding order predicate
-__device__ __noinline__ void build_edges(const TileCtx &t, Shared &sh, const uint16_t *r, int slot, int x, int y, int n, int &ha_out, int &hl_out) {
-  const B200Frame *f = t.f;
-  const int st = t.stride, lane = lane_id();
+// avail: bit0 have_above, bit1 have_left, bit2 have_above_right, bit3 have_below_left (block_avail(), once per block)
+__device__ __forceinline__ int block_avail(const TileCtx &t, int x, int y, int n) {
   const int mi_r = y >> 2, mi_c = x >> 2, n4 = n >> 2;
   const int ha = mi_r > t.tr0, hl = mi_c > t.tc0;
+  const int ar = ha && b200_unit_before(mi_r - 1, mi_c + n4, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
+  const int bl = hl && b200_unit_before(mi_r + n4, mi_c - 1, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
+  return ha | (hl << 1) | (ar << 2) | (bl << 3);
+}
+__device__ __noinline__ void build_edges(const TileCtx &t, Shared &sh, const uint16_t *r, int slot, int x, int y, int n, int avail) {
+  const B200Frame *f = t.f;
+  const int st = t.stride, lane = lane_id();
+  const int ha = avail & 1, hl = (avail >> 1) & 1, have_ar = (avail >> 2) & 1, have_bl = (avail >> 3) & 1;
   const int max_x = f->mi_cols * 4 - 1, max_y = f->mi_rows * 4 - 1;
   const int base = 1 << (f->bit_depth - 1);
-  const int have_ar = ha && b200_unit_before(mi_r - 1, mi_c + n4, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
-  const int have_bl = hl && b200_unit_before(mi_r + n4, mi_c - 1, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
   uint16_t *A = sh.above[slot] + EOFF, *L = sh.left[slot] + EOFF;
   for (int i = lane; i < 2 * n; i += 32) {
     uint16_t a, l;
@@ -152,7 +153,6 @@ __device__ __noinline__ void build_edges(const TileCtx &t, Shared &sh, const uin
     else tl = (uint16_t)base;
     A[-1] = tl; L[-1] = tl;
   }
-  ha_out = ha; hl_out = hl;
 }
 
 // ---- intra predictors (AV1 spec 7.11.2.x): value of pixel (i, j) of an n x n block ------------------
@@ -514,8 +514,8 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
 #pragma unroll 1
     for (int q = lane; q < N2; q += 32) sh.src[p][q] = t.src[p][(y + (q >> lg)) * t.stride + x + (q & (n - 1))];
   for (int i = lane; i < 200; i += 32) reinterpret_cast<uint32_t *>(sh.lev)[i] = 0;
-  int ha = 0, hl = 0;
-  for (int p = 0; p < planes; p++) build_edges(t, sh, t.src[p], p, x, y, n, ha, hl);
+  const int avail = block_avail(t, x, y, n), ha = avail & 1, hl = (avail >> 1) & 1;
+  for (int p = 0; p < planes; p++) build_edges(t, sh, t.src[p], p, x, y, n, avail);
   __syncwarp();
   // ---- ranking from the SATD table (context-0 mode rates)
   const uint16_t *ymode_cost = rt->y_mode[0][0];
@@ -620,8 +620,8 @@ __device__ __noinline__ void reconstruct_block(const TileCtx &t, Shared &sh, int
 #pragma unroll 1
     for (int q = lane; q < N2; q += 32) sh.src[p][q] = t.src[p][(y + (q >> lg)) * t.stride + x + (q & (n - 1))];
   for (int i = lane; i < 200; i += 32) reinterpret_cast<uint32_t *>(sh.lev)[i] = 0;
-  int ha = 0, hl = 0;
-  for (int p = 0; p < planes; p++) build_edges(t, sh, t.rec[p], p, x, y, n, ha, hl);
+  const int avail = block_avail(t, x, y, n), ha = avail & 1, hl = (avail >> 1) & 1;
+  for (int p = 0; p < planes; p++) build_edges(t, sh, t.rec[p], p, x, y, n, avail);
   __syncwarp();
   const long long coff = b200_coef_offset(f, mi_r, mi_c);
   int any = 0;

@@ -117,11 +117,11 @@ static inline B200_HD int b200_level_cols(const B200Frame *f, int lv) { return f
 static inline B200_HD int b200_level_rows(const B200Frame *f, int lv) { return f->mi_rows >> lv; }
 
 // z-order index (0..255) of the 4x4 unit (r, c) inside its 64x64 superblock, r,c in 0..15.
-static inline B200_HD int b200_zidx(int r, int c) {
-  int z = 0;
-  for (int i = 0; i < 4; i++) z |= (((c >> i) & 1) << (2 * i)) | (((r >> i) & 1) << (2 * i + 1));
-  return z;
+static inline B200_HD int b200_spread4(int v) {   // abcd -> 0a0b0c0d
+  v = (v | (v << 2)) & 0x33;
+  return (v | (v << 1)) & 0x55;
 }
+static inline B200_HD int b200_zidx(int r, int c) { return b200_spread4(c) | (b200_spread4(r) << 1); }
 // Is the 4x4 unit (ur, uc) reconstructed before the block whose top-left unit is (br, bc)?  Coding order is
 // static: superblocks in raster order inside the tile [tr0,tr1) x [tc0,tc1), z-order inside a superblock; any block
 // containing the unit lies entirely before or after the current block.  (AV1 top-right / bottom-left availability.)

@@ -86,6 +86,11 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   for (int l = 0; l < 32; l++) r |= (emu_exchange<int>(pred ? 1 : 0, l) ? 1u : 0u) << l;
   return r;
 }
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+  unsigned r = v;
+  for (int m = 16; m > 0; m >>= 1) { const unsigned o = emu_exchange(r, (int)((emu::g_threadIdx.x & 31) ^ m)); r = o < r ? o : r; }
+  return r;
+}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
