@@ -536,15 +536,21 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
   __syncwarp();
   long long bestJ = kInf;
   int bestC = 1 << 20, bestEob = 0;
+  bool skip_rest = false;      // every first-type trial quantised to all-zero: the other transform types are not tried
 #pragma unroll 1
-  for (int b = 0; b * G < 10; b++) {
+  for (int b = 0; b * G < 10 && !skip_rest; b++) {
     const int ci = b * G + g;
     const int ti = ci >> 1, k = ci & 1;
     const int m = k == 0 ? m0 : m1;
-    const bool ok = ti < 5 && m >= 0 && ((f->tx_type_mask >> ti) & 1) && (f->rdo_tx_decision || ti == first_t);
+    bool ok = ti < 5 && m >= 0 && ((f->tx_type_mask >> ti) & 1) && (f->rdo_tx_decision || ti == first_t);
     if (!__ballot_sync(FULL, ok)) continue;
     const TrialOut r = trial_batch<n, HBD>(t, sh, 0, sh.src[0], sh.pred + (ok ? k : 0) * 256, dv_tx_types[ok ? ti : 0],
                                            ok ? m : (m0 >= 0 ? m0 : 0));
+    const int gf = first_t * 2 - b * G;        // lane group of (rank 0, first type) in this batch, if it is here
+    if (f->rdo_tx_decision && gf >= 0 && gf < G) {
+      const int e0 = __shfl_sync(FULL, r.eob, gf << lg), e1 = __shfl_sync(FULL, r.eob, ((gf + 1) << lg) & 31);
+      if ((m0 < 0 || e0 == 0) && (m1 < 0 || e1 == 0)) { skip_rest = true; if (ti != first_t) ok = false; }
+    }
     long long wj = kInf;
     int wc = 1 << 20;
     if (ok) { wj = rd_cost(f, r.sse, r.rate + mode_rate(rt, ymode_cost, m, n)); wc = k * 5 + ti; }

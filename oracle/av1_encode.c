@@ -350,22 +350,31 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
   int first_tt = -1;
   for (int k = 0; k < 5; k++) if ((f->tx_type_mask >> k) & 1) { first_tt = k_tx_types[k]; break; }
   int64_t bestJ = INT64_MAX;
-  int best_mode = bm[0], best_tt = first_tt, eob_y = 0;
+  int best_mode = bm[0], best_tt = first_tt, eob_y = 0, best_c = 1 << 20;
   int16_t qc[1024];
   uint16_t recon[1024], eobv;
-  for (int k = 0; k < 2; k++) {
-    const int m = bm[k];
-    if (m < 0) continue;
-    orc_predict_intra(m, 0, n, A[0], L[0], ha, hl, f->bit_depth, pred);
-    const uint32_t mrate = mode_rate(rt, ymode_cost, m, n);
-    for (int t = 0; t < 5; t++) {
-      const int tt = k_tx_types[t];
-      if (!((f->tx_type_mask >> t) & 1)) continue;
-      if (!(f->rdo_tx_decision && n <= 16) && tt != first_tt) continue;
-      uint32_t rate;
-      const uint64_t d = trial_plane(e, 0, x, y, n, pred, tt, m, qc, &eobv, recon, &rate);
-      const int64_t J = rd_cost(f, d, rate + mrate);
-      if (J < bestJ) { bestJ = J; best_mode = m; best_tt = tt; eob_y = eobv; }
+  /* pass 0: the first allowed transform type on both ranked modes; pass 1: the other types - skipped when every
+   * first-type trial quantised to all-zero (nothing left for another transform to gain).  Winner = lowest J,
+   * ties -> lowest candidate index c = rank * 5 + type. */
+  int all_first_zero = 1;
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1 && (all_first_zero || !(f->rdo_tx_decision && n <= 16))) break;
+    for (int k = 0; k < 2; k++) {
+      const int m = bm[k];
+      if (m < 0) continue;
+      orc_predict_intra(m, 0, n, A[0], L[0], ha, hl, f->bit_depth, pred);
+      const uint32_t mrate = mode_rate(rt, ymode_cost, m, n);
+      for (int t = 0; t < 5; t++) {
+        const int tt = k_tx_types[t];
+        if (!((f->tx_type_mask >> t) & 1)) continue;
+        if ((pass == 0) != (tt == first_tt)) continue;
+        uint32_t rate;
+        const uint64_t d = trial_plane(e, 0, x, y, n, pred, tt, m, qc, &eobv, recon, &rate);
+        if (pass == 0 && eobv) all_first_zero = 0;
+        const int64_t J = rd_cost(f, d, rate + mrate);
+        const int c = k * 5 + t;
+        if (J < bestJ || (J == bestJ && c < best_c)) { bestJ = J; best_c = c; best_mode = m; best_tt = tt; eob_y = eobv; }
+      }
     }
   }
   int64_t total = bestJ;
