@@ -29,9 +29,14 @@ WORKLOADS = {
     "4k": dict(name="16x3840x2160 RGBA8 opaque, quality 80, speed 4, 10-bit (BASELINE configs[2])",
                n=16, w=3840, h=2160, quality=80.0, speed=4, depth=10),
 }
-# algorithmic bytes per pixel moved by the RDO kernel: 3 source planes read + 3 reconstructed planes
-# written + 3 coefficient planes written (all 16-bit samples) + 8 B mode info and 3 x 2 B eob per 4x4 unit
-RDO_BYTES_PER_PX = 3 * 2 + 3 * 2 + 3 * 2 + (8 + 6) / 16.0
+# Algorithmic bytes per pixel of the RDO stage group (SATD + analysis per level, partition decision, reconstruction
+# chain), 16-bit samples:
+#   analysis: 3 source planes read once per level by the SATD kernel and once by the trial kernel (3 levels)  2*3*3*2 = 36
+#             SATD tables written + read: 26 x 4 B per block at 3 levels                     2 * 104 * (1/16 + 1/64 + 1/256) = 17.1
+#             decisions written + read: 16 B per block at 3 levels                            2 * 16 * (1/16 + 1/64 + 1/256) = 2.6
+#   reconstruction: 3 source planes read, 3 reconstructed planes + 3 coefficient planes written, records      6 + 6 + 6 + 0.9 = 18.9
+RDO_BYTES_PER_PX = 36 + 17.1 + 2.6 + 18.9
+TRAFFIC_BYTES_PER_STEP = None     # filled from profiles/ (ncu dram__bytes_read.sum + dram__bytes_write.sum) when captured
 
 
 def make_images(wl, seed0=0):
@@ -263,8 +268,7 @@ def main():
             peak = json.load(open(peaks_path))["hbm_gbs"]; peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
-        rdo_launches = max(args.steps, 1)
-        rdo_ms = d["gpu_ms_rdo"] / rdo_launches
+        rdo_ms = d["gpu_ms_rdo"] / max(args.steps, 1)      # CUDA-event time of the RDO stage group, summed over the chunks of a step
         achieved = RDO_BYTES_PER_PX * px_per_step / 1e9 / (rdo_ms / 1e3) if rdo_ms > 0 else 0.0
         out = {
             "metric": "Mpixels/s encoded", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
@@ -273,17 +277,19 @@ def main():
             "config": {"workload": wl["name"], "images_per_gpu": wl["n"], "quality": wl["quality"], "speed": wl["speed"],
                        "depth": wl["depth"], "parallelism": "images sharded one batch per GPU, no data-path collective",
                        "l2": "inputs (%.0f MB/step) larger than L2, no flush needed" % (px_per_step * 4 / 1e6),
-                       "tools": "filters off (deblock/CDEF/LR not emitted yet), partitions 4..16, 13 intra modes, 5 tx types",
+                       "tools": "partitions 4..16 (square), 13 intra modes, 5 transform types, deblock + CDEF (per-SB strength search); LR / CFL / angle deltas not emitted",
                        "avif_bytes_per_step": out_bytes // max(args.steps, 1)},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "Mpixels/s", "h2d_bytes_per_step": d2["h2d_bytes"] // args.steps,
                     "d2h_bytes_per_step": d2["d2h_bytes"] // args.steps, "ms_per_step": ms2 / args.steps},
             "gpu_launches": int(d["kernel_launches"]),
-            "breakdown_ms_per_step": {"gpu_rdo_kernel": rdo_ms, "gpu_all": d["gpu_ms_total"] / args.steps,
-                                      "host_pack_mux": d["host_ms_pack"] / args.steps, "wall": wall * 1e3 / args.steps},
-            "roofline": {"bound": "hbm", "kernel": "b200_rdo_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "note": "RDO is dependency/ALU-bound, not DRAM-bound (SURVEY.md 8d); algorithmic bytes = %.2f B/px" % RDO_BYTES_PER_PX},
+            "breakdown_ms_per_step": {"gpu_rdo_stages": rdo_ms, "gpu_all_streams_summed": d["gpu_ms_total"] / args.steps,
+                                      "host_pack_mux_overlapped": d["host_ms_pack"] / args.steps, "wall": wall * 1e3 / args.steps},
+            "roofline": {"bound": "hbm", "kernel": "RDO stage group: b200_satd_kernel + b200_analyze_kernel<lv> x3 + b200_decide_kernel + b200_recon_kernel",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_STEP,
+                         "peak_source": peak_src,
+                         "note": "integer-ALU / latency bound by construction (small integer butterflies, SURVEY.md 8d), not DRAM-bound; "
+                                 "algorithmic bytes = %.1f B/px; traffic = ncu dram bytes of the group per step (profiles/), null if not captured" % RDO_BYTES_PER_PX},
             "cpu_baseline": cb,
         }
         print(json.dumps(out), flush=True)

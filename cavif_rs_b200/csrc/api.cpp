@@ -383,10 +383,11 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
   const int depth = enc.output_depth == 8 ? 8 : 10;
   const int mc = enc.color_model == B200AVIF_COLOR_YCBCR ? B200AVIF_MC_BT601 : B200AVIF_MC_IDENTITY;
 
-  // ---- host-side alpha pre-clean (av1encoder.rs:277-299)
-  for (ImageWork &im : imgs) {
+  // ---- host-side alpha pre-clean (av1encoder.rs:277-299), images in parallel on the host cores
+  parallel_for(imgs.size(), [&](size_t i) {
+    ImageWork &im = imgs[i];
     im.depth = depth;
-    if (im.raw || im.channels != 4 || im.on_device) continue;
+    if (im.raw || im.channels != 4 || im.on_device) return;
     if (enc.alpha_color_mode == B200AVIF_ALPHA_UNASSOCIATED_CLEAN) {
       im.cleaned.resize(im.w * im.h * 4);
       if (b200_blurred_dirty_alpha(im.pixels, im.w, im.h, im.stride, im.cleaned.data())) { im.pixels = im.cleaned.data(); im.stride = im.w; }
@@ -396,7 +397,7 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
       b200_premultiplied_branch(im.pixels, im.w, im.h, im.stride, im.cleaned.data());
       im.pixels = im.cleaned.data(); im.stride = im.w;
     }
-  }
+  });
   // ---- frame descriptions
   for (ImageWork &im : imgs) {
     const int cmc = im.raw ? im.raw_mc : mc;
