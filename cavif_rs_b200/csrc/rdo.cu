@@ -163,7 +163,7 @@ __device__ __forceinline__ int dc_value(int n, const uint16_t *A, const uint16_t
   return 1 << (bd - 1);
 }
 // A, L point at index 0 of the edge arrays (index -1 valid).  dc: precomputed DC value (used for DC_PRED only).
-__device__ __forceinline__ int pred_px(int mode, int n, int i, int j, const uint16_t *A, const uint16_t *L, int dc) {
+__device__ __forceinline__ int pred_px(int mode, int delta, int n, int i, int j, const uint16_t *A, const uint16_t *L, int dc) {
   if (mode == DC_PRED) return dc;
   if (mode == PAETH_PRED) {
     const int tl = A[-1], b = A[j] + L[i] - tl;
@@ -175,7 +175,7 @@ __device__ __forceinline__ int pred_px(int mode, int n, int i, int j, const uint
     const int v = w[i] * A[j] + (256 - w[i]) * L[n - 1], h = w[j] * L[i] + (256 - w[j]) * A[n - 1];
     return mode == SMOOTH_PRED ? (v + h + 256) >> 9 : (mode == SMOOTH_V_PRED ? (v + 128) >> 8 : (h + 128) >> 8);
   }
-  const int p_angle = dv_mode_to_angle[mode];
+  const int p_angle = dv_mode_to_angle[mode] + 3 * delta;
   if (p_angle == 90) return A[j];
   if (p_angle == 180) return L[i];
   if (p_angle > 90 && p_angle < 180) {
@@ -457,20 +457,20 @@ __device__ __forceinline__ long long rd_cost(const B200Frame *f, unsigned long l
   return (long long)(sse << 8) + (((long long)f->lambda_q8 * (long long)rate) >> 8);
 }
 __device__ __forceinline__ int chroma_tx_type(int uv_mode) { return dv_intra_mode_to_tx_type[uv_mode]; }
-__device__ __forceinline__ uint32_t mode_rate(const B200RateTables *rt, const uint16_t *cost_row, int m, int n) {
+__device__ __forceinline__ uint32_t mode_rate(const B200RateTables *rt, const uint16_t *cost_row, int m, int n, int delta) {
   uint32_t r = cost_row[m];
-  if (n >= 8 && m >= V_PRED && m <= D67_PRED) r += rt->angle_delta[m - V_PRED][3];
+  if (n >= 8 && m >= V_PRED && m <= D67_PRED) r += rt->angle_delta[m - V_PRED][delta + 3];
   return r;
 }
 
 // whole-block prediction into shared memory, pixels spread over the 32 lanes (the only place pred_px is expanded)
-__device__ __noinline__ void predict_block(int mode, int lg, const uint16_t *above, const uint16_t *left, int ha, int hl, int bd,
+__device__ __noinline__ void predict_block(int mode, int delta, int lg, const uint16_t *above, const uint16_t *left, int ha, int hl, int bd,
                                            uint16_t *dst) {
   const uint16_t *A = above + EOFF, *L = left + EOFF;
   const int n = 1 << lg;
   const int dc = mode == DC_PRED ? dc_value(n, A, L, ha, hl, bd) : 0;
 #pragma unroll 1
-  for (int p = lane_id(); p < n * n; p += 32) dst[p] = (uint16_t)pred_px(mode, n, p >> lg, p & (n - 1), A, L, dc);
+  for (int p = lane_id(); p < n * n; p += 32) dst[p] = (uint16_t)pred_px(mode, delta, n, p >> lg, p & (n - 1), A, L, dc);
 }
 
 // top-2 of 13 mode costs held by lanes 0..12 (kInf when not allowed): lowest cost first, ties -> lowest index
@@ -519,20 +519,24 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
   __syncwarp();
   // ---- ranking from the SATD table (context-0 mode rates)
   const uint16_t *ymode_cost = rt->y_mode[0][0];
+  const uint32_t wy = satd[13], wuv = f->planes > 1 ? satd[B200_SATD_WORDS + 13] : (255u | (3u << 8));      // refined directional mode | (delta + 3) << 8
+  const int md_y = wy & 255, dl_y = (int)(wy >> 8) - 3, md_uv = wuv & 255, dl_uv = (int)(wuv >> 8) - 3;
+#define DELTA_Y(m) ((m) == md_y ? dl_y : 0)
+#define DELTA_UV(m) ((m) == md_uv ? dl_uv : 0)
   long long my_ycost = kInf;
   uint32_t my_uvsatd = 0;
   if (lane < 13) {
     if ((f->y_mode_mask >> lane) & 1)
-      my_ycost = (long long)satd[lane] * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, lane, n)) >> 8);
-    my_uvsatd = satd[13 + lane];
+      my_ycost = (long long)satd[lane] * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, lane, n, DELTA_Y(lane))) >> 8);
+    my_uvsatd = satd[B200_SATD_WORDS + lane];
   }
   int m0, m1;
   rank_top2(my_ycost, m0, m1);
   // ---- luma full trials: candidate c = k * 5 + ti; lane batches pair the two modes on the same transform type
   int first_t = -1;
   for (int k = 0; k < 5; k++) if ((f->tx_type_mask >> k) & 1) { first_t = k; break; }
-  predict_block(m0 >= 0 ? m0 : 0, lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred);
-  predict_block(m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0), lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred + 256);
+  predict_block(m0 >= 0 ? m0 : 0, DELTA_Y(m0 >= 0 ? m0 : 0), lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred);
+  predict_block(m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0), DELTA_Y(m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0)), lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred + 256);
   __syncwarp();
   long long bestJ = kInf;
   int bestC = 1 << 20, bestEob = 0;
@@ -553,7 +557,7 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
     }
     long long wj = kInf;
     int wc = 1 << 20;
-    if (ok) { wj = rd_cost(f, r.sse, r.rate + mode_rate(rt, ymode_cost, m, n)); wc = k * 5 + ti; }
+    if (ok) { wj = rd_cost(f, r.sse, r.rate + mode_rate(rt, ymode_cost, m, n, DELTA_Y(m))); wc = k * 5 + ti; }
     warp_argmin(wj, wc);
     if (wj < bestJ || (wj == bestJ && wc < bestC)) {
       bestJ = wj; bestC = wc;
@@ -569,7 +573,7 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
     const uint16_t *uvcost = rt->uv_mode[1][best_mode];
     long long my_uvcost = kInf;
     if (lane < 13 && ((f->uv_mode_mask >> lane) & 1))
-      my_uvcost = (long long)my_uvsatd * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, uvcost, lane, n)) >> 8);
+      my_uvcost = (long long)my_uvsatd * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, uvcost, lane, n, DELTA_UV(lane))) >> 8);
     int u0, u1;
     rank_top2(my_uvcost, u0, u1);
     long long bestCj = kInf;
@@ -582,7 +586,7 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
 #pragma unroll 1
       for (int cc = b * G; cc < min((b + 1) * G, 4); cc++) {
         const int mm = (cc >> 1) == 0 ? u0 : u1, pp = 1 + (cc & 1);
-        predict_block(mm >= 0 ? mm : 0, lg, sh.above[pp], sh.left[pp], ha, hl, bd, sh.pred + (cc - b * G) * N2);
+        predict_block(mm >= 0 ? mm : 0, DELTA_UV(mm >= 0 ? mm : 0), lg, sh.above[pp], sh.left[pp], ha, hl, bd, sh.pred + (cc - b * G) * N2);
       }
       __syncwarp();
       const TrialOut r = trial_batch<n, HBD>(t, sh, p, sh.src[p], sh.pred + (ok ? g : 0) * N2, chroma_tx_type(m >= 0 ? m : 0), best_mode);
@@ -594,7 +598,7 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
         const int mm = kk == 0 ? u0 : u1;
         if (mm < 0) continue;
         const long long J = rd_cost(f, (unsigned long long)sh.taskD[cU] + sh.taskD[cV],
-                                    sh.taskR[cU] + sh.taskR[cV] + mode_rate(rt, uvcost, mm, n));
+                                    sh.taskR[cU] + sh.taskR[cV] + mode_rate(rt, uvcost, mm, n, DELTA_UV(mm)));
         if (J < bestCj) { bestCj = J; uv_best = mm; eobU = sh.taskE[cU]; eobV = sh.taskE[cV]; }
       }
       __syncwarp();
@@ -607,10 +611,13 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
     B200BlockDec d;
     d.cost = total; d.y_mode = (uint8_t)best_mode; d.tx_type = (uint8_t)best_tt; d.uv_mode = (uint8_t)uv_best;
     d.all_zero = (uint8_t)all_zero;
-    d.pad[0] = d.pad[1] = d.pad[2] = d.pad[3] = 0;
+    d.angle_y = (uint8_t)(DELTA_Y(best_mode) + 3); d.angle_uv = (uint8_t)(DELTA_UV(uv_best) + 3);
+    d.pad[0] = d.pad[1] = 0;
     *out = d;
   }
   __syncwarp();
+#undef DELTA_Y
+#undef DELTA_UV
 }
 
 // ---- stage C: closed-loop reconstruction of one decided block by one warp (oracle reconstruct_block) ----------------
@@ -635,7 +642,8 @@ __device__ __noinline__ void reconstruct_block(const TileCtx &t, Shared &sh, int
   for (int b = 0; b * G < planes; b++) {       // plane p = b * G + g handled by lane group g
 #pragma unroll 1
     for (int pp = b * G; pp < min((b + 1) * G, planes); pp++)
-      predict_block(pp == 0 ? m.y_mode : m.uv_mode, lg, sh.above[pp], sh.left[pp], ha, hl, bd, sh.pred + (pp - b * G) * N2);
+      predict_block(pp == 0 ? m.y_mode : m.uv_mode, (pp == 0 ? (m.angle & 15) : (m.angle >> 4)) - 3, lg, sh.above[pp], sh.left[pp], ha, hl, bd,
+                    sh.pred + (pp - b * G) * N2);
     __syncwarp();
     const int p = b * G + g;
     const bool ok = p < planes;
@@ -693,10 +701,9 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
 #pragma unroll
   for (int m = 0; m < 13; m++) acc[m] = 0;
   uint16_t Ab[EOFF + 34], Lb[EOFF + 34];
-#pragma unroll 1
-  for (int p = grp; p < (grp == 0 ? 1 : 3); p++) {
-    const uint16_t *r = job.src[p];
-    uint16_t *A = Ab + EOFF, *L = Lb + EOFF;
+  uint16_t *A = Ab + EOFF, *L = Lb + EOFF;
+  // source-neighbour edges of plane r (same rules as build_edges, one thread)
+  auto edges = [&](const uint16_t *r) {
 #pragma unroll 1
     for (int i = 0; i < 2 * n; i++) {
       uint16_t a, l;
@@ -708,14 +715,38 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
       else { int yy = (i < n || have_bl) ? y + i : y + n - 1; if (yy > max_y) yy = max_y; l = r[yy * st + x - 1]; }
       A[i] = a; L[i] = l;
     }
-    {
-      uint16_t tl;
-      if (ha && hl) tl = r[(y - 1) * st + x - 1];
-      else if (ha) tl = r[(y - 1) * st + x];
-      else if (hl) tl = r[y * st + x - 1];
-      else tl = (uint16_t)base;
-      A[-1] = tl; L[-1] = tl;
+    uint16_t tl;
+    if (ha && hl) tl = r[(y - 1) * st + x - 1];
+    else if (ha) tl = r[(y - 1) * st + x];
+    else if (hl) tl = r[y * st + x - 1];
+    else tl = (uint16_t)base;
+    A[-1] = tl; L[-1] = tl;
+  };
+  // 4x4 Hadamard SATD of one sub-block against mode m / delta
+  auto satd16 = [&](const int *s, int m, int delta, int sy, int sx, int dc) -> uint32_t {
+    int tt[16], d[16];
+#pragma unroll 1
+    for (int k = 0; k < 16; k++) sh_d[threadIdx.x * 17 + k] = s[k] - pred_px(m, delta, n, sy + (k >> 2), sx + (k & 3), A, L, dc);
+#pragma unroll
+    for (int k = 0; k < 16; k++) d[k] = sh_d[threadIdx.x * 17 + k];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int a = d[i * 4] + d[i * 4 + 1], b = d[i * 4] - d[i * 4 + 1], c = d[i * 4 + 2] + d[i * 4 + 3], e = d[i * 4 + 2] - d[i * 4 + 3];
+      tt[i * 4] = a + c; tt[i * 4 + 1] = b + e; tt[i * 4 + 2] = a - c; tt[i * 4 + 3] = b - e;
     }
+    uint32_t total = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int a = tt[j] + tt[4 + j], b = tt[j] - tt[4 + j], c = tt[8 + j] + tt[12 + j], e = tt[8 + j] - tt[12 + j];
+      total += (uint32_t)(abs(a + c) + abs(b + e) + abs(a - c) + abs(b - e));
+    }
+    return total;
+  };
+  const int p_end = grp == 0 ? 1 : 3;
+#pragma unroll 1
+  for (int p = grp; p < p_end; p++) {
+    const uint16_t *r = job.src[p];
+    edges(r);
     const int dc = dc_value(n, A, L, ha, hl, bd);
 #pragma unroll 1
     for (int sb = 0; sb < (n4 * n4); sb++) {
@@ -728,29 +759,57 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
 #pragma unroll 1
       for (int m = 0; m < 13; m++) {
         if (!((mask >> m) & 1)) continue;
-        int tt[16], d[16];
-#pragma unroll 1
-        for (int k = 0; k < 16; k++) sh_d[threadIdx.x * 17 + k] = s[k] - pred_px(m, n, sy + (k >> 2), sx + (k & 3), A, L, dc);
-#pragma unroll
-        for (int k = 0; k < 16; k++) d[k] = sh_d[threadIdx.x * 17 + k];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int a = d[i * 4] + d[i * 4 + 1], b = d[i * 4] - d[i * 4 + 1], c = d[i * 4 + 2] + d[i * 4 + 3], e = d[i * 4 + 2] - d[i * 4 + 3];
-          tt[i * 4] = a + c; tt[i * 4 + 1] = b + e; tt[i * 4 + 2] = a - c; tt[i * 4 + 3] = b - e;
-        }
-        uint32_t total = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int a = tt[j] + tt[4 + j], b = tt[j] - tt[4 + j], c = tt[8 + j] + tt[12 + j], e = tt[8 + j] - tt[12 + j];
-          total += (uint32_t)(abs(a + c) + abs(b + e) + abs(a - c) + abs(b - e));
-        }
-        acc[m] += total;
+        acc[m] += satd16(s, m, 0, sy, sx, dc);
       }
     }
   }
-  uint32_t *out = job.satd[lv] + ((size_t)blk * 2 + grp) * 13;
+  // angle refinement of the best directional mode (oracle refine_angle): deltas -3..3 by SATD + delta rate
+  uint32_t word = 255u | (3u << 8);
+  if (f->fine_directional_intra && n >= 8) {
+    int md = -1;
+    uint32_t smd = 0;
+#pragma unroll
+    for (int m = V_PRED; m <= D67_PRED; m++)
+      if (((mask >> m) & 1) && (md < 0 || acc[m] < smd)) { md = m; smd = acc[m]; }
+    if (md >= 0) {
+      uint32_t sv[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) sv[k] = 0;
+#pragma unroll 1
+      for (int p = grp; p < p_end; p++) {
+        const uint16_t *r = job.src[p];
+        if (p_end - grp > 1 || p != grp) edges(r);      // single-plane group: edges still hold this plane
+#pragma unroll 1
+        for (int sb = 0; sb < (n4 * n4); sb++) {
+          const int sy = (sb >> (lg - 2)) * 4, sx = (sb & (n4 - 1)) * 4;
+          int s[16];
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) s[i * 4 + j] = r[(y + sy + i) * st + x + sx + j];
+#pragma unroll
+          for (int k = 0; k < 6; k++) sv[k] += satd16(s, md, k < 3 ? k - 3 : k - 2, sy, sx, 0);
+        }
+      }
+      const uint16_t *drate = job.rate->angle_delta[md - V_PRED];
+      long long best = (long long)smd * 64 + (((long long)f->lambda_satd_q8 * drate[3]) >> 8);
+      int best_d = 0;
+      uint32_t best_s = smd;
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const int d = k < 3 ? k - 3 : k - 2;
+        const long long c = (long long)sv[k] * 64 + (((long long)f->lambda_satd_q8 * drate[d + 3]) >> 8);
+        if (c < best) { best = c; best_d = d; best_s = sv[k]; }
+      }
+#pragma unroll
+      for (int m = V_PRED; m <= D67_PRED; m++) if (m == md) acc[m] = best_s;
+      word = (uint32_t)md | ((uint32_t)(best_d + 3) << 8);
+    }
+  }
+  uint32_t *out = job.satd[lv] + ((size_t)blk * 2 + grp) * B200_SATD_WORDS;
 #pragma unroll
   for (int m = 0; m < 13; m++) out[m] = acc[m];
+  out[13] = word;
 }
 
 // ---- stage A.2: full trials.  One single-warp CTA loops over blocks of level lv (grid-stride), grid.y = job.
@@ -770,14 +829,14 @@ __global__ void __launch_bounds__(kThreads, LV == 0 ? 24 : (LV == 1 ? 24 : 16)) 
     if (LV == 0 && job.dec[1][((blk / cols) >> 1) * b200_level_cols(f, 1) + ((blk % cols) >> 1)].all_zero) {
       if (lane_id() == 0) {   // pruned by the 8x8 parent: never split
         B200BlockDec d;
-        d.cost = B200_COST_PRUNED; d.y_mode = 0; d.tx_type = 0; d.uv_mode = 0; d.all_zero = 0;
-        d.pad[0] = d.pad[1] = d.pad[2] = d.pad[3] = 0;
+        d.cost = B200_COST_PRUNED; d.y_mode = 0; d.tx_type = 0; d.uv_mode = 0; d.all_zero = 0; d.angle_y = 0; d.angle_uv = 0;
+        d.pad[0] = d.pad[1] = 0;
         job.dec[0][blk] = d;
       }
       continue;
     }
     tile_of_unit(f, y >> 2, x >> 2, t);
-    analyze_block<2 + LV, HBD>(t, sh, x, y, job.satd[lv] + (size_t)blk * 26, job.dec[lv] + blk);
+    analyze_block<2 + LV, HBD>(t, sh, x, y, job.satd[lv] + (size_t)blk * 2 * B200_SATD_WORDS, job.dec[lv] + blk);
   }
 }
 
@@ -792,7 +851,8 @@ __device__ __forceinline__ void set_mi(const B200RdoJob &job, int x, int y, int 
   const B200Frame *f = &job.frame;
   B200Mi m;
   m.bsize = (uint8_t)(n == 4 ? BLOCK_4X4 : n == 8 ? BLOCK_8X8 : BLOCK_16X16);
-  m.y_mode = d.y_mode; m.uv_mode = d.uv_mode; m.angle = 3 | (3 << 4);
+  m.y_mode = d.y_mode; m.uv_mode = d.uv_mode;
+  m.angle = (uint8_t)((d.angle_y ? d.angle_y : 3) | ((d.angle_uv ? d.angle_uv : 3) << 4));
   m.tx_size = (uint8_t)txs_of(n); m.tx_type = d.tx_type; m.flags = 0; m.cfl = 0;
   for (int i = 0; i < n / 4; i++)
     for (int j = 0; j < n / 4; j++) job.mi[((y >> 2) + i) * f->mi_cols + (x >> 2) + j] = m;

@@ -83,8 +83,12 @@ typedef struct B200BlockDec {
   int64_t cost;        // J = SSE*256 + lambda*R of the best (mode, transform type) per plane, + skip flag cost
   uint8_t y_mode, tx_type, uv_mode;
   uint8_t all_zero;    // every plane quantised to zero in the analysis (the block would be coded as "skip")
-  uint8_t pad[4];
+  uint8_t angle_y, angle_uv;   // angle_delta + 3 of the chosen luma / chroma mode (3 = no delta)
+  uint8_t pad[2];
 } B200BlockDec;
+// SATD table entry per (block, plane group): 13 mode SATDs + one word packing the refined directional mode and its
+// angle delta: (mode | (delta + 3) << 8), mode = 255 when no directional mode was refined.
+#define B200_SATD_WORDS 14
 // Early termination of the partition search: the four 4x4 children of an 8x8 block whose analysis quantised to
 // all-zero are not analysed; their cost is this sentinel so the split can never win.
 #define B200_COST_PRUNED ((int64_t)1 << 60)

@@ -312,37 +312,76 @@ static int chroma_tx_type(int uv_mode, int n) {
   return av1_intra_mode_to_tx_type[uv_mode];   /* DCT/ADST combinations are in every intra set up to 16x16 */
 }
 
-static uint32_t mode_rate(const B200RateTables *rt, const uint16_t *row, int m, int n) {
+static uint32_t mode_rate(const B200RateTables *rt, const uint16_t *row, int m, int n, int delta) {
   uint32_t r = row[m];
-  if (n >= 8 && m >= V_PRED && m <= D67_PRED) r += rt->angle_delta[m - V_PRED][3];
+  if (n >= 8 && m >= V_PRED && m <= D67_PRED) r += rt->angle_delta[m - V_PRED][delta + 3];
   return r;
+}
+
+/* fine_directional_intra (ravif: speed <= 6, av1encoder.rs:585): refine the angle of the best nominal directional
+ * mode of a plane group by SATD.  sat[]: nominal SATDs (updated in place for the refined mode); returns the packed
+ * (mode | (delta + 3) << 8) word, mode 255 = nothing refined.  Candidate order 0, -3, -2, -1, 1, 2, 3; strict '<'. */
+static uint32_t refine_angle(enc_t *e, int first_plane, int last_plane, int x, int y, int n, uint16_t A[3][EOFF + 66],
+                             uint16_t L[3][EOFF + 66], int ha, int hl, int mask, uint32_t sat[13]) {
+  const B200Frame *f = e->f;
+  if (!f->fine_directional_intra || n < 8) return 255u | (3u << 8);
+  int md = -1;
+  for (int m = V_PRED; m <= D67_PRED; m++)
+    if (((mask >> m) & 1) && (md < 0 || sat[m] < sat[md])) md = m;
+  if (md < 0) return 255u | (3u << 8);
+  uint16_t pred[32 * 32];
+  int best_d = 0;
+  int64_t best = (int64_t)sat[md] * 64 + (((int64_t)f->lambda_satd_q8 * e->rt->angle_delta[md - V_PRED][3]) >> 8);
+  uint32_t best_s = sat[md];
+  static const int order[6] = {-3, -2, -1, 1, 2, 3};
+  for (int k = 0; k < 6; k++) {
+    const int d = order[k];
+    uint32_t sv = 0;
+    for (int p = first_plane; p <= last_plane; p++) {
+      orc_predict_intra(md, d, n, A[p], L[p], ha, hl, f->bit_depth, pred);
+      sv += satd4(e->src[p] + y * e->stride + x, e->stride, pred, n);
+    }
+    const int64_t c = (int64_t)sv * 64 + (((int64_t)f->lambda_satd_q8 * e->rt->angle_delta[md - V_PRED][d + 3]) >> 8);
+    if (c < best) { best = c; best_d = d; best_s = sv; }
+  }
+  sat[md] = best_s;
+  return (uint32_t)md | ((uint32_t)(best_d + 3) << 8);
 }
 
 /* ---- stage A: open-loop analysis of one block.  Every prediction reads SOURCE neighbours, so all blocks of all
  * levels are independent of each other (one massively parallel kernel per level on the device).  Rate terms that
  * would depend on neighbouring decisions use the context-0 tables. */
-void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_t satd_y[13], uint32_t satd_uv[13]) {
+void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_t satd_y[14], uint32_t satd_uv[14]) {
   const B200Frame *f = e->f;
   const B200RateTables *rt = e->rt;
   uint16_t A[3][EOFF + 66], L[3][EOFF + 66], pred[32 * 32];
   int ha = 0, hl = 0;
   for (int p = 0; p < f->planes; p++) build_edges(e, e->src[p], x, y, n, A[p], L[p], &ha, &hl);
   const uint16_t *ymode_cost = rt->y_mode[0][0];
-  /* ranking: SATD + mode rate */
-  int64_t bc[2] = {INT64_MAX, INT64_MAX};
-  int bm[2] = {-1, -1};
+  /* SATD of the nominal modes (the device computes this table in b200_satd_kernel) */
   for (int m = 0; m < 13; m++) {
     satd_y[m] = 0; satd_uv[m] = 0;
     const int in_y = (f->y_mode_mask >> m) & 1, in_uv = f->planes > 1 && ((f->uv_mode_mask >> m) & 1);
-    if (!in_y && !in_uv) continue;
     for (int p = 0; p < f->planes; p++) {
       if (p == 0 ? !in_y : !in_uv) continue;
       orc_predict_intra(m, 0, n, A[p], L[p], ha, hl, f->bit_depth, pred);
       const uint32_t s = satd4(e->src[p] + y * e->stride + x, e->stride, pred, n);
       if (p == 0) satd_y[m] = s; else satd_uv[m] += s;
     }
-    if (!in_y) continue;
-    const int64_t c = (int64_t)satd_y[m] * 64 + (((int64_t)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, m, n)) >> 8);
+  }
+  satd_y[13] = refine_angle(e, 0, 0, x, y, n, A, L, ha, hl, f->y_mode_mask, satd_y);
+  satd_uv[13] = f->planes > 1 ? refine_angle(e, 1, 2, x, y, n, A, L, ha, hl, f->uv_mode_mask, satd_uv) : (255u | (3u << 8));
+  const int md_y = satd_y[13] & 255, dl_y = (int)(satd_y[13] >> 8) - 3;
+  const int md_uv = satd_uv[13] & 255, dl_uv = (int)(satd_uv[13] >> 8) - 3;
+  if (f->planes == 1) satd_uv[13] = 0;      /* the device has no chroma SATD thread for monochrome frames */
+#define DELTA_Y(m) ((m) == md_y ? dl_y : 0)
+#define DELTA_UV(m) ((m) == md_uv ? dl_uv : 0)
+  /* ranking: SATD + mode rate */
+  int64_t bc[2] = {INT64_MAX, INT64_MAX};
+  int bm[2] = {-1, -1};
+  for (int m = 0; m < 13; m++) {
+    if (!((f->y_mode_mask >> m) & 1)) continue;
+    const int64_t c = (int64_t)satd_y[m] * 64 + (((int64_t)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, m, n, DELTA_Y(m))) >> 8);
     if (c < bc[0]) { bc[1] = bc[0]; bm[1] = bm[0]; bc[0] = c; bm[0] = m; }
     else if (c < bc[1]) { bc[1] = c; bm[1] = m; }
   }
@@ -362,8 +401,8 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
     for (int k = 0; k < 2; k++) {
       const int m = bm[k];
       if (m < 0) continue;
-      orc_predict_intra(m, 0, n, A[0], L[0], ha, hl, f->bit_depth, pred);
-      const uint32_t mrate = mode_rate(rt, ymode_cost, m, n);
+      orc_predict_intra(m, DELTA_Y(m), n, A[0], L[0], ha, hl, f->bit_depth, pred);
+      const uint32_t mrate = mode_rate(rt, ymode_cost, m, n, DELTA_Y(m));
       for (int t = 0; t < 5; t++) {
         const int tt = k_tx_types[t];
         if (!((f->tx_type_mask >> t) & 1)) continue;
@@ -385,7 +424,7 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
     int um[2] = {-1, -1};
     for (int m = 0; m < 13; m++) {
       if (!((f->uv_mode_mask >> m) & 1)) continue;
-      const int64_t c = (int64_t)satd_uv[m] * 64 + (((int64_t)f->lambda_satd_q8 * mode_rate(rt, uvcost, m, n)) >> 8);
+      const int64_t c = (int64_t)satd_uv[m] * 64 + (((int64_t)f->lambda_satd_q8 * mode_rate(rt, uvcost, m, n, DELTA_UV(m))) >> 8);
       if (c < uc[0]) { uc[1] = uc[0]; um[1] = um[0]; uc[0] = c; um[0] = m; }
       else if (c < uc[1]) { uc[1] = c; um[1] = m; }
     }
@@ -396,11 +435,11 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
       const int ctt = chroma_tx_type(m, n);
       uint16_t e1, e2;
       uint32_t r1, r2;
-      orc_predict_intra(m, 0, n, A[1], L[1], ha, hl, f->bit_depth, pred);
+      orc_predict_intra(m, DELTA_UV(m), n, A[1], L[1], ha, hl, f->bit_depth, pred);
       uint64_t d = trial_plane(e, 1, x, y, n, pred, ctt, best_mode, qc, &e1, recon, &r1);
-      orc_predict_intra(m, 0, n, A[2], L[2], ha, hl, f->bit_depth, pred);
+      orc_predict_intra(m, DELTA_UV(m), n, A[2], L[2], ha, hl, f->bit_depth, pred);
       d += trial_plane(e, 2, x, y, n, pred, ctt, best_mode, qc, &e2, recon, &r2);
-      const int64_t J = rd_cost(f, d, r1 + r2 + mode_rate(rt, uvcost, m, n));
+      const int64_t J = rd_cost(f, d, r1 + r2 + mode_rate(rt, uvcost, m, n, DELTA_UV(m)));
       if (J < bestC) { bestC = J; uv_best = m; eob_u = e1; eob_v = e2; }
     }
     total += bestC;
@@ -411,6 +450,10 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
   out->cost = total;
   out->y_mode = (uint8_t)best_mode; out->tx_type = (uint8_t)best_tt; out->uv_mode = (uint8_t)uv_best;
   out->all_zero = (uint8_t)all_zero;
+  out->angle_y = (uint8_t)(DELTA_Y(best_mode) + 3);
+  out->angle_uv = (uint8_t)(DELTA_UV(uv_best) + 3);
+#undef DELTA_Y
+#undef DELTA_UV
 }
 
 /* ---- stage B: partition decision of one 16x16 region from the analysed costs (context-0 partition rates) */
@@ -423,7 +466,8 @@ static void set_mi(enc_t *e, int x, int y, int n, const B200BlockDec *d) {
   const B200Frame *f = e->f;
   B200Mi m;
   memset(&m, 0, sizeof(m));
-  m.bsize = (uint8_t)bsize_of(n); m.y_mode = d->y_mode; m.uv_mode = d->uv_mode; m.angle = 3 | (3 << 4);
+  m.bsize = (uint8_t)bsize_of(n); m.y_mode = d->y_mode; m.uv_mode = d->uv_mode;
+  m.angle = (uint8_t)((d->angle_y ? d->angle_y : 3) | ((d->angle_uv ? d->angle_uv : 3) << 4));
   m.tx_size = (uint8_t)txs_of(n); m.tx_type = d->tx_type;
   for (int i = 0; i < n / 4; i++)
     for (int j = 0; j < n / 4; j++) e->mi[((y >> 2) + i) * f->mi_cols + (x >> 2) + j] = m;
@@ -478,7 +522,7 @@ static void reconstruct_block(enc_t *e, int x, int y, int n) {
     build_edges(e, e->rec[p], x, y, n, A, L, &ha, &hl);
     const int mode = p == 0 ? m.y_mode : m.uv_mode;
     const int tt = p == 0 ? m.tx_type : chroma_tx_type(m.uv_mode, n);
-    orc_predict_intra(mode, 0, n, A, L, ha, hl, f->bit_depth, pred);
+    orc_predict_intra(mode, (p == 0 ? (m.angle & 15) : (m.angle >> 4)) - 3, n, A, L, ha, hl, f->bit_depth, pred);
     uint16_t eobv;
     uint32_t rate;
     trial_plane(e, p, x, y, n, pred, tt, m.y_mode, qc, &eobv, recon, &rate);
@@ -528,16 +572,16 @@ void orc_encode_frame(const B200Frame *f, const B200RateTables *rt, uint16_t *co
         int tr, tc;
         tile_of(f, by * (n / 4), bx * (n / 4), &tr, &tc);
         tile_bounds(&e, tr, tc);
-        uint32_t sy[13], suv[13];
+        uint32_t sy[14], suv[14];
         const size_t bi = (size_t)by * b200_level_cols(f, lv) + bx;
         if (lv == 0 && e.dec[1][(size_t)(by >> 1) * b200_level_cols(f, 1) + (bx >> 1)].all_zero) {
           memset(&e.dec[0][bi], 0, sizeof(B200BlockDec));
           e.dec[0][bi].cost = B200_COST_PRUNED;
-          if (satd_out && satd_out[0]) memset(satd_out[0] + bi * 26, 0, 26 * sizeof(uint32_t));
+          if (satd_out && satd_out[0]) memset(satd_out[0] + bi * 2 * B200_SATD_WORDS, 0, 2 * B200_SATD_WORDS * sizeof(uint32_t));
           continue;
         }
         orc_analyze_block(&e, bx * n, by * n, n, &e.dec[lv][bi], sy, suv);
-        if (satd_out && satd_out[lv]) { memcpy(satd_out[lv] + bi * 26, sy, sizeof(sy)); memcpy(satd_out[lv] + bi * 26 + 13, suv, sizeof(suv)); }
+        if (satd_out && satd_out[lv]) { memcpy(satd_out[lv] + bi * 2 * B200_SATD_WORDS, sy, sizeof(sy)); memcpy(satd_out[lv] + bi * 2 * B200_SATD_WORDS + B200_SATD_WORDS, suv, sizeof(suv)); }
       }
   }
   for (int y = 0; y < f->mi_rows * 4; y += 16)

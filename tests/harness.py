@@ -27,7 +27,8 @@ class B200Records(ctypes.Structure):
 RATE_TABLES_BYTES = 2 * (20 * 10 + 3 * 2 + 5 * 5 * 13 + 2 * 13 * 14 + 8 * 7 + 8 + 6 * 16 + 2 * 4 * 13 * 16 + 5 * 13 * 2 +
                          4 * 2 * 12 + 5 * 2 * 9 * 2 + 2 * 3 * 2 + 5 * 2 * 4 * 3 + 5 * 2 * 42 * 4 + 4 * 2 * 21 * 13)
 
-DEC_DTYPE = np.dtype([("cost", "<i8"), ("y_mode", "u1"), ("tx_type", "u1"), ("uv_mode", "u1"), ("all_zero", "u1"), ("pad", "u1", 4)])
+DEC_DTYPE = np.dtype([("cost", "<i8"), ("y_mode", "u1"), ("tx_type", "u1"), ("uv_mode", "u1"), ("all_zero", "u1"),
+                      ("angle_y", "u1"), ("angle_uv", "u1"), ("pad", "u1", 2)])
 MI_DTYPE = np.dtype([("bsize", "u1"), ("y_mode", "u1"), ("uv_mode", "u1"), ("angle", "u1"),
                      ("tx_size", "u1"), ("tx_type", "u1"), ("flags", "u1"), ("cfl", "u1")])
 
@@ -121,7 +122,7 @@ class Records:
         self.rec = [np.zeros((f.mi_rows * 4, f.mi_cols * 4), np.uint16) for _ in range(3)]
         # open-loop analysis outputs per level (0: 4x4, 1: 8x8, 2: 16x16)
         self.dec = [np.zeros((f.mi_rows >> lv) * (f.mi_cols >> lv), DEC_DTYPE) for lv in range(3)]
-        self.satd = [np.zeros(((f.mi_rows >> lv) * (f.mi_cols >> lv), 2, 13), np.uint32) for lv in range(3)]
+        self.satd = [np.zeros(((f.mi_rows >> lv) * (f.mi_cols >> lv), 2, 14), np.uint32) for lv in range(3)]
     def c_records(self):
         r = B200Records()
         r.mi = self.mi.ctypes.data
