@@ -77,6 +77,7 @@ extern "C" int b200av1_frame_setup(B200Frame *f, int width, int height, int bit_
   f->partition_min = 4; f->partition_max = 16;
   f->rdo_tx_decision = 1;
   f->fine_directional_intra = 1;
+  f->enable_cfl = 1;
   f->y_mode_mask = 0x1fff; f->uv_mode_mask = 0x1fff; f->tx_type_mask = 0x1f;
   // In-loop filter strengths: closed-form picks from the quantiser (encoder freedom; the filters themselves
   // are normative).  Deblock level: libaom's "pick from q" fit; CDEF: one frame-wide strength pair.

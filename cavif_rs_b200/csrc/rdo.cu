@@ -63,8 +63,9 @@ struct Shared {
   alignas(16) uint8_t lev[800];   // per group (N+4)^2 padded |level| map (rate contexts)
   int16_t qc[512];             // per group n*n quantised levels in scan order
   uint16_t rec[512];           // per group n*n reconstruction
-  uint32_t taskD[4], taskR[4];
-  uint16_t taskE[4];
+  int16_t ac[256];             // CFL: (luma << 3) - average of the block
+  uint32_t taskD[6], taskR[6];
+  uint16_t taskE[6];
 };
 
 struct TileCtx {
@@ -84,7 +85,7 @@ __device__ __forceinline__ int txs_of(int n) { return n == 4 ? 0 : n == 8 ? 1 : 
 __device__ __forceinline__ int scan_base(int n) { return n == 4 ? 0 : n == 8 ? 16 : 80; }
 __device__ __forceinline__ int ilog2_dev(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
   for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
   return v;
 }
@@ -456,7 +457,7 @@ __device__ __forceinline__ TrialOut trial_dispatch(int n, const TileCtx &t, Shar
 __device__ __forceinline__ long long rd_cost(const B200Frame *f, unsigned long long sse, uint32_t rate) {
   return (long long)(sse << 8) + (((long long)f->lambda_q8 * (long long)rate) >> 8);
 }
-__device__ __forceinline__ int chroma_tx_type(int uv_mode) { return dv_intra_mode_to_tx_type[uv_mode]; }
+__device__ __forceinline__ int chroma_tx_type(int uv_mode) { return uv_mode == UV_CFL_PRED ? 0 : dv_intra_mode_to_tx_type[uv_mode]; }
 __device__ __forceinline__ uint32_t mode_rate(const B200RateTables *rt, const uint16_t *cost_row, int m, int n, int delta) {
   uint32_t r = cost_row[m];
   if (n >= 8 && m >= V_PRED && m <= D67_PRED) r += rt->angle_delta[m - V_PRED][delta + 3];
@@ -471,6 +472,48 @@ __device__ __noinline__ void predict_block(int mode, int delta, int lg, const ui
   const int dc = mode == DC_PRED ? dc_value(n, A, L, ha, hl, bd) : 0;
 #pragma unroll 1
   for (int p = lane_id(); p < n * n; p += 32) dst[p] = (uint16_t)pred_px(mode, delta, n, p >> lg, p & (n - 1), A, L, dc);
+}
+
+// ---- chroma from luma (oracle cfl_ac / cfl_pick_alpha / cfl_predict), pixels spread over the 32 lanes
+__device__ __noinline__ void cfl_build_ac(const uint16_t *luma, int lg, int16_t *ac) {
+  const int N2 = 1 << (2 * lg);
+  long long sum = 0;
+#pragma unroll 1
+  for (int p = lane_id(); p < N2; p += 32) sum += luma[p] << 3;
+  const int avg = (int)((warp_sum_ll(sum) + (N2 >> 1)) >> (2 * lg));
+#pragma unroll 1
+  for (int p = lane_id(); p < N2; p += 32) ac[p] = (int16_t)((luma[p] << 3) - avg);
+  __syncwarp();
+}
+__device__ __noinline__ int cfl_pick_alpha(const int16_t *ac, const uint16_t *src, int N2, int dc) {
+  long long num = 0, den = 0;
+#pragma unroll 1
+  for (int p = lane_id(); p < N2; p += 32) {
+    const int a = ac[p];
+    num += (long long)a * ((int)src[p] - dc);
+    den += (long long)a * a;
+  }
+  num = warp_sum_ll(num); den = warp_sum_ll(den);
+  if (den == 0) return 0;
+  const unsigned long long mag = (((unsigned long long)(num < 0 ? -num : num) << 6) + (unsigned long long)(den >> 1)) / (unsigned long long)den;
+  const int a = mag > 16 ? 16 : (int)mag;
+  return num < 0 ? -a : a;
+}
+__device__ __noinline__ void cfl_predict_block(const int16_t *ac, int N2, int dc, int alpha, int bd, uint16_t *dst) {
+  const int mx = (1 << bd) - 1;
+#pragma unroll 1
+  for (int p = lane_id(); p < N2; p += 32) {
+    const int sc = alpha * ac[p];
+    const int v = dc + (sc < 0 ? -((-sc + 32) >> 6) : ((sc + 32) >> 6));
+    dst[p] = (uint16_t)(v < 0 ? 0 : (v > mx ? mx : v));
+  }
+}
+__device__ __forceinline__ uint32_t cfl_rate(const B200RateTables *rt, int au, int av) {
+  const int su = au == 0 ? 0 : (au < 0 ? 1 : 2), sv = av == 0 ? 0 : (av < 0 ? 1 : 2);
+  uint32_t r = rt->cfl_sign[su * 3 + sv - 1];
+  if (su) r += rt->cfl_alpha[(su - 1) * 3 + sv][abs(au) - 1];
+  if (sv) r += rt->cfl_alpha[(sv - 1) * 3 + su][abs(av) - 1];
+  return r;
 }
 
 // top-2 of 13 mode costs held by lanes 0..12 (kInf when not allowed): lowest cost first, ties -> lowest index
@@ -568,7 +611,7 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
   const int best_mode = bestC / 5 == 0 ? m0 : m1;
   const int best_tt = dv_tx_types[bestC % 5];
   long long total = bestJ;
-  int uv_best = DC_PRED, eobU = 0, eobV = 0;
+  int uv_best = DC_PRED, eobU = 0, eobV = 0, cfl_js = 0, cfl_idx = 0;
   if (planes > 1) {
     const uint16_t *uvcost = rt->uv_mode[1][best_mode];
     long long my_uvcost = kInf;
@@ -577,31 +620,52 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
     int u0, u1;
     rank_top2(my_uvcost, u0, u1);
     long long bestCj = kInf;
+    // third candidate: chroma from (source) luma, alpha = clamped integer least-squares fit per plane
+    int al_u = 0, al_v = 0, dc_u = 0, dc_v = 0;
+    if (f->enable_cfl) {
+      cfl_build_ac(sh.src[0], lg, sh.ac);
+      dc_u = dc_value(n, sh.above[1] + EOFF, sh.left[1] + EOFF, ha, hl, bd);
+      dc_v = dc_value(n, sh.above[2] + EOFF, sh.left[2] + EOFF, ha, hl, bd);
+      al_u = cfl_pick_alpha(sh.ac, sh.src[1], N2, dc_u);
+      al_v = cfl_pick_alpha(sh.ac, sh.src[2], N2, dc_v);
+    }
+    const bool cfl_ok = al_u != 0 || al_v != 0;
+    const int NC = cfl_ok ? 6 : 4;            // candidate = (k = ci >> 1: rank 0, rank 1, CFL; plane = 1 + (ci & 1))
 #pragma unroll 1
-    for (int b = 0; b * G < 4; b++) {
-      const int ci = b * G + g;               // candidate = (k = ci >> 1, plane = 1 + (ci & 1))
-      const int k = (ci >> 1) & 1, p = 1 + (ci & 1);
-      const int m = k == 0 ? u0 : u1;
-      const bool ok = ci < 4 && m >= 0;
+    for (int b = 0; b * G < NC; b++) {
+      const int ci = b * G + g;
+      const int k = ci >> 1, p = 1 + (ci & 1);
+      const int m = k == 0 ? u0 : (k == 1 ? u1 : UV_CFL_PRED);
+      const bool ok = ci < NC && m >= 0;
 #pragma unroll 1
-      for (int cc = b * G; cc < min((b + 1) * G, 4); cc++) {
-        const int mm = (cc >> 1) == 0 ? u0 : u1, pp = 1 + (cc & 1);
-        predict_block(mm >= 0 ? mm : 0, DELTA_UV(mm >= 0 ? mm : 0), lg, sh.above[pp], sh.left[pp], ha, hl, bd, sh.pred + (cc - b * G) * N2);
+      for (int cc = b * G; cc < min((b + 1) * G, NC); cc++) {
+        const int kk = cc >> 1, pp = 1 + (cc & 1);
+        uint16_t *dst = sh.pred + (cc - b * G) * N2;
+        if (kk == 2) cfl_predict_block(sh.ac, N2, pp == 1 ? dc_u : dc_v, pp == 1 ? al_u : al_v, bd, dst);
+        else {
+          const int mm = kk == 0 ? u0 : u1;
+          predict_block(mm >= 0 ? mm : 0, DELTA_UV(mm >= 0 ? mm : 0), lg, sh.above[pp], sh.left[pp], ha, hl, bd, dst);
+        }
       }
       __syncwarp();
-      const TrialOut r = trial_batch<n, HBD>(t, sh, p, sh.src[p], sh.pred + (ok ? g : 0) * N2, chroma_tx_type(m >= 0 ? m : 0), best_mode);
+      const TrialOut r = trial_batch<n, HBD>(t, sh, p, sh.src[p], sh.pred + (ok ? g : 0) * N2, chroma_tx_type(ok ? m : 0), best_mode);
       if (ok && (lane & (n - 1)) == 0) { sh.taskD[ci] = r.sse; sh.taskR[ci] = r.rate; sh.taskE[ci] = (uint16_t)r.eob; }
       __syncwarp();
-      for (int kk = 0; kk < 2; kk++) {
+      for (int kk = 0; kk < NC / 2; kk++) {
         const int cU = kk * 2, cV = kk * 2 + 1;
         if (cV < b * G || cV >= (b + 1) * G) continue;
-        const int mm = kk == 0 ? u0 : u1;
+        const int mm = kk == 0 ? u0 : (kk == 1 ? u1 : UV_CFL_PRED);
         if (mm < 0) continue;
-        const long long J = rd_cost(f, (unsigned long long)sh.taskD[cU] + sh.taskD[cV],
-                                    sh.taskR[cU] + sh.taskR[cV] + mode_rate(rt, uvcost, mm, n, DELTA_UV(mm)));
+        const uint32_t mr = kk == 2 ? uvcost[UV_CFL_PRED] + cfl_rate(rt, al_u, al_v) : mode_rate(rt, uvcost, mm, n, DELTA_UV(mm));
+        const long long J = rd_cost(f, (unsigned long long)sh.taskD[cU] + sh.taskD[cV], sh.taskR[cU] + sh.taskR[cV] + mr);
         if (J < bestCj) { bestCj = J; uv_best = mm; eobU = sh.taskE[cU]; eobV = sh.taskE[cV]; }
       }
       __syncwarp();
+    }
+    if (uv_best == UV_CFL_PRED) {
+      const int su = al_u == 0 ? 0 : (al_u < 0 ? 1 : 2), sv = al_v == 0 ? 0 : (al_v < 0 ? 1 : 2);
+      cfl_js = su * 3 + sv - 1;
+      cfl_idx = (al_u ? abs(al_u) - 1 : 0) | ((al_v ? abs(al_v) - 1 : 0) << 4);
     }
     total += bestCj;
   }
@@ -612,7 +676,7 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
     d.cost = total; d.y_mode = (uint8_t)best_mode; d.tx_type = (uint8_t)best_tt; d.uv_mode = (uint8_t)uv_best;
     d.all_zero = (uint8_t)all_zero;
     d.angle_y = (uint8_t)(DELTA_Y(best_mode) + 3); d.angle_uv = (uint8_t)(DELTA_UV(uv_best) + 3);
-    d.pad[0] = d.pad[1] = 0;
+    d.cfl_js = (uint8_t)cfl_js; d.cfl_alpha = (uint8_t)cfl_idx;
     *out = d;
   }
   __syncwarp();
@@ -638,15 +702,28 @@ __device__ __noinline__ void reconstruct_block(const TileCtx &t, Shared &sh, int
   __syncwarp();
   const long long coff = b200_coef_offset(f, mi_r, mi_c);
   int any = 0;
+  // CFL chroma needs the reconstructed luma of this block: luma goes alone first, then both chroma planes
+  const bool cfl = planes > 1 && m.uv_mode == UV_CFL_PRED;
+  int au = 0, av = 0;
+  if (cfl) {
+    const int js = (m.flags >> 1) & 7, su = (js + 1) / 3, sv = (js + 1) % 3;
+    au = su == 0 ? 0 : (su == 1 ? -1 : 1) * ((m.cfl & 15) + 1);
+    av = sv == 0 ? 0 : (sv == 1 ? -1 : 1) * ((m.cfl >> 4) + 1);
+  }
 #pragma unroll 1
-  for (int b = 0; b * G < planes; b++) {       // plane p = b * G + g handled by lane group g
+  for (int p0 = 0; p0 < planes;) {              // plane p = p0 + g handled by lane group g
+    const int cnt = (cfl && p0 == 0) ? 1 : min(G, planes - p0);
 #pragma unroll 1
-    for (int pp = b * G; pp < min((b + 1) * G, planes); pp++)
-      predict_block(pp == 0 ? m.y_mode : m.uv_mode, (pp == 0 ? (m.angle & 15) : (m.angle >> 4)) - 3, lg, sh.above[pp], sh.left[pp], ha, hl, bd,
-                    sh.pred + (pp - b * G) * N2);
+    for (int pp = p0; pp < p0 + cnt; pp++) {
+      uint16_t *dst = sh.pred + (pp - p0) * N2;
+      if (cfl && pp > 0)
+        cfl_predict_block(sh.ac, N2, dc_value(n, sh.above[pp] + EOFF, sh.left[pp] + EOFF, ha, hl, bd), pp == 1 ? au : av, bd, dst);
+      else
+        predict_block(pp == 0 ? m.y_mode : m.uv_mode, (pp == 0 ? (m.angle & 15) : (m.angle >> 4)) - 3, lg, sh.above[pp], sh.left[pp], ha, hl, bd, dst);
+    }
     __syncwarp();
-    const int p = b * G + g;
-    const bool ok = p < planes;
+    const int p = p0 + g;
+    const bool ok = g < cnt;
     const int pe = ok ? p : 0;
     const TrialOut r = trial_dispatch<HBD>(n, t, sh, pe, sh.src[pe], sh.pred + (ok ? g : 0) * N2,
                                            pe == 0 ? m.tx_type : chroma_tx_type(m.uv_mode), m.y_mode);
@@ -662,6 +739,8 @@ __device__ __noinline__ void reconstruct_block(const TileCtx &t, Shared &sh, int
     }
     any |= __ballot_sync(FULL, ok && r.eob != 0) != 0;
     __syncwarp();
+    if (cfl && p0 == 0) cfl_build_ac(sh.rec, lg, sh.ac);
+    p0 += cnt;
   }
   B200Mi mo = m;
   if (!any) mo.flags |= 1;
@@ -830,7 +909,7 @@ __global__ void __launch_bounds__(kThreads, LV == 0 ? 24 : (LV == 1 ? 24 : 16)) 
       if (lane_id() == 0) {   // pruned by the 8x8 parent: never split
         B200BlockDec d;
         d.cost = B200_COST_PRUNED; d.y_mode = 0; d.tx_type = 0; d.uv_mode = 0; d.all_zero = 0; d.angle_y = 0; d.angle_uv = 0;
-        d.pad[0] = d.pad[1] = 0;
+        d.cfl_js = 0; d.cfl_alpha = 0;
         job.dec[0][blk] = d;
       }
       continue;
@@ -854,6 +933,7 @@ __device__ __forceinline__ void set_mi(const B200RdoJob &job, int x, int y, int 
   m.y_mode = d.y_mode; m.uv_mode = d.uv_mode;
   m.angle = (uint8_t)((d.angle_y ? d.angle_y : 3) | ((d.angle_uv ? d.angle_uv : 3) << 4));
   m.tx_size = (uint8_t)txs_of(n); m.tx_type = d.tx_type; m.flags = 0; m.cfl = 0;
+  if (d.uv_mode == UV_CFL_PRED) { m.flags = (uint8_t)(d.cfl_js << 1); m.cfl = d.cfl_alpha; }
   for (int i = 0; i < n / 4; i++)
     for (int j = 0; j < n / 4; j++) job.mi[((y >> 2) + i) * f->mi_cols + (x >> 2) + j] = m;
 }

@@ -84,7 +84,7 @@ typedef struct B200BlockDec {
   uint8_t y_mode, tx_type, uv_mode;
   uint8_t all_zero;    // every plane quantised to zero in the analysis (the block would be coded as "skip")
   uint8_t angle_y, angle_uv;   // angle_delta + 3 of the chosen luma / chroma mode (3 = no delta)
-  uint8_t pad[2];
+  uint8_t cfl_js, cfl_alpha;   // uv_mode == UV_CFL_PRED: joint sign (0..7), alpha indices (u low nibble, v high nibble)
 } B200BlockDec;
 // SATD table entry per (block, plane group): 13 mode SATDs + one word packing the refined directional mode and its
 // angle delta: (mode | (delta + 3) << 8), mode = 255 when no directional mode was refined.

@@ -309,6 +309,7 @@ static const uint8_t k_tx_types[5] = {TX_DCT_DCT, TX_ADST_DCT, TX_DCT_ADST, TX_A
 static int chroma_tx_type(int uv_mode, int n) {
   if (uv_mode == UV_CFL_PRED) return TX_DCT_DCT;
   if (n >= 32) return TX_DCT_DCT;
+  if (uv_mode == 13) return TX_DCT_DCT;           /* UV_CFL_PRED */
   return av1_intra_mode_to_tx_type[uv_mode];   /* DCT/ADST combinations are in every intra set up to 16x16 */
 }
 
@@ -316,6 +317,56 @@ static uint32_t mode_rate(const B200RateTables *rt, const uint16_t *row, int m, 
   uint32_t r = row[m];
   if (n >= 8 && m >= V_PRED && m <= D67_PRED) r += rt->angle_delta[m - V_PRED][delta + 3];
   return r;
+}
+
+/* ---- chroma from luma (AV1 spec 7.11.5, 4:4:4 so no subsampling).  rav1e considers CFL for every intra chroma block
+ * whose size allows it (rdo.rs rdo_cfl_alpha); alpha is the integer least-squares fit, clamped to +-16. */
+static void cfl_ac(const uint16_t *luma, int stride, int n, int16_t *ac) {
+  int sum = 0;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) sum += luma[i * stride + j] << 3;
+  const int avg = (sum + ((n * n) >> 1)) >> (2 * ilog2(n));
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) ac[i * n + j] = (int16_t)((luma[i * stride + j] << 3) - avg);
+}
+static int cfl_pick_alpha(const int16_t *ac, const uint16_t *src, int stride, int n, int dc) {
+  int64_t num = 0, den = 0;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      const int a = ac[i * n + j];
+      num += (int64_t)a * ((int)src[i * stride + j] - dc);
+      den += (int64_t)a * a;
+    }
+  if (den == 0) return 0;
+  const uint64_t mag = (((uint64_t)(num < 0 ? -num : num) << 6) + (uint64_t)(den >> 1)) / (uint64_t)den;
+  const int a = mag > 16 ? 16 : (int)mag;
+  return num < 0 ? -a : a;
+}
+static void cfl_predict(const int16_t *ac, int n, int dc, int alpha, int bit_depth, uint16_t *pred) {
+  const int mx = (1 << bit_depth) - 1;
+  for (int i = 0; i < n * n; i++) {
+    const int sc = alpha * ac[i];
+    int v = dc + (sc < 0 ? -((-sc + 32) >> 6) : ((sc + 32) >> 6));
+    pred[i] = (uint16_t)(v < 0 ? 0 : (v > mx ? mx : v));
+  }
+}
+/* joint sign (0..7) and alpha indices of a signed alpha pair (not both zero) */
+static void cfl_code(int au, int av, int *js, int *idx) {
+  const int su = au == 0 ? 0 : (au < 0 ? 1 : 2), sv = av == 0 ? 0 : (av < 0 ? 1 : 2);
+  *js = su * 3 + sv - 1;
+  *idx = (au ? abs(au) - 1 : 0) | ((av ? abs(av) - 1 : 0) << 4);
+}
+static uint32_t cfl_rate(const B200RateTables *rt, int au, int av) {
+  const int su = au == 0 ? 0 : (au < 0 ? 1 : 2), sv = av == 0 ? 0 : (av < 0 ? 1 : 2);
+  uint32_t r = rt->cfl_sign[su * 3 + sv - 1];
+  if (su) r += rt->cfl_alpha[(su - 1) * 3 + sv][abs(au) - 1];
+  if (sv) r += rt->cfl_alpha[(sv - 1) * 3 + su][abs(av) - 1];
+  return r;
+}
+static void cfl_decode(int js, int idx, int *au, int *av) {
+  const int su = (js + 1) / 3, sv = (js + 1) % 3;
+  *au = su == 0 ? 0 : (su == 1 ? -1 : 1) * ((idx & 15) + 1);
+  *av = sv == 0 ? 0 : (sv == 1 ? -1 : 1) * ((idx >> 4) + 1);
 }
 
 /* fine_directional_intra (ravif: speed <= 6, av1encoder.rs:585): refine the angle of the best nominal directional
@@ -417,7 +468,7 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
     }
   }
   int64_t total = bestJ;
-  int uv_best = DC_PRED, eob_u = 0, eob_v = 0;
+  int uv_best = DC_PRED, eob_u = 0, eob_v = 0, cfl_js = 0, cfl_idx = 0;
   if (f->planes > 1) {
     const uint16_t *uvcost = rt->uv_mode[1][best_mode];
     int64_t uc[2] = {INT64_MAX, INT64_MAX};
@@ -442,6 +493,26 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
       const int64_t J = rd_cost(f, d, r1 + r2 + mode_rate(rt, uvcost, m, n, DELTA_UV(m)));
       if (J < bestC) { bestC = J; uv_best = m; eob_u = e1; eob_v = e2; }
     }
+    if (f->enable_cfl) {      /* third candidate: chroma from (source) luma */
+      int16_t ac[1024];
+      int al[2], dcv[2];
+      cfl_ac(e->src[0] + y * e->stride + x, e->stride, n, ac);
+      for (int p = 1; p < 3; p++) {
+        orc_predict_intra(DC_PRED, 0, n, A[p], L[p], ha, hl, f->bit_depth, pred);
+        dcv[p - 1] = pred[0];
+        al[p - 1] = cfl_pick_alpha(ac, e->src[p] + y * e->stride + x, e->stride, n, dcv[p - 1]);
+      }
+      if (al[0] || al[1]) {
+        uint16_t e1, e2;
+        uint32_t r1, r2;
+        cfl_predict(ac, n, dcv[0], al[0], f->bit_depth, pred);
+        uint64_t d = trial_plane(e, 1, x, y, n, pred, TX_DCT_DCT, best_mode, qc, &e1, recon, &r1);
+        cfl_predict(ac, n, dcv[1], al[1], f->bit_depth, pred);
+        d += trial_plane(e, 2, x, y, n, pred, TX_DCT_DCT, best_mode, qc, &e2, recon, &r2);
+        const int64_t J = rd_cost(f, d, r1 + r2 + uvcost[UV_CFL_PRED] + cfl_rate(rt, al[0], al[1]));
+        if (J < bestC) { bestC = J; uv_best = UV_CFL_PRED; eob_u = e1; eob_v = e2; cfl_code(al[0], al[1], &cfl_js, &cfl_idx); }
+      }
+    }
     total += bestC;
   }
   const int all_zero = eob_y == 0 && (f->planes == 1 || (eob_u == 0 && eob_v == 0));
@@ -452,6 +523,7 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
   out->all_zero = (uint8_t)all_zero;
   out->angle_y = (uint8_t)(DELTA_Y(best_mode) + 3);
   out->angle_uv = (uint8_t)(DELTA_UV(uv_best) + 3);
+  out->cfl_js = (uint8_t)cfl_js; out->cfl_alpha = (uint8_t)cfl_idx;
 #undef DELTA_Y
 #undef DELTA_UV
 }
@@ -469,6 +541,7 @@ static void set_mi(enc_t *e, int x, int y, int n, const B200BlockDec *d) {
   m.bsize = (uint8_t)bsize_of(n); m.y_mode = d->y_mode; m.uv_mode = d->uv_mode;
   m.angle = (uint8_t)((d->angle_y ? d->angle_y : 3) | ((d->angle_uv ? d->angle_uv : 3) << 4));
   m.tx_size = (uint8_t)txs_of(n); m.tx_type = d->tx_type;
+  if (d->uv_mode == UV_CFL_PRED) { m.flags = (uint8_t)(d->cfl_js << 1); m.cfl = d->cfl_alpha; }
   for (int i = 0; i < n / 4; i++)
     for (int j = 0; j < n / 4; j++) e->mi[((y >> 2) + i) * f->mi_cols + (x >> 2) + j] = m;
 }
@@ -522,7 +595,16 @@ static void reconstruct_block(enc_t *e, int x, int y, int n) {
     build_edges(e, e->rec[p], x, y, n, A, L, &ha, &hl);
     const int mode = p == 0 ? m.y_mode : m.uv_mode;
     const int tt = p == 0 ? m.tx_type : chroma_tx_type(m.uv_mode, n);
-    orc_predict_intra(mode, (p == 0 ? (m.angle & 15) : (m.angle >> 4)) - 3, n, A, L, ha, hl, f->bit_depth, pred);
+    if (p > 0 && mode == UV_CFL_PRED) {      /* DC + alpha * AC of the RECONSTRUCTED luma of this block */
+      int16_t ac[1024];
+      int au, av;
+      cfl_decode((m.flags >> 1) & 7, m.cfl, &au, &av);
+      cfl_ac(e->rec[0] + y * e->stride + x, e->stride, n, ac);
+      orc_predict_intra(DC_PRED, 0, n, A, L, ha, hl, f->bit_depth, pred);
+      cfl_predict(ac, n, pred[0], p == 1 ? au : av, f->bit_depth, pred);
+    } else {
+      orc_predict_intra(mode, (p == 0 ? (m.angle & 15) : (m.angle >> 4)) - 3, n, A, L, ha, hl, f->bit_depth, pred);
+    }
     uint16_t eobv;
     uint32_t rate;
     trial_plane(e, p, x, y, n, pred, tt, m.y_mode, qc, &eobv, recon, &rate);

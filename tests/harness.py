@@ -28,7 +28,7 @@ RATE_TABLES_BYTES = 2 * (20 * 10 + 3 * 2 + 5 * 5 * 13 + 2 * 13 * 14 + 8 * 7 + 8 
                          4 * 2 * 12 + 5 * 2 * 9 * 2 + 2 * 3 * 2 + 5 * 2 * 4 * 3 + 5 * 2 * 42 * 4 + 4 * 2 * 21 * 13)
 
 DEC_DTYPE = np.dtype([("cost", "<i8"), ("y_mode", "u1"), ("tx_type", "u1"), ("uv_mode", "u1"), ("all_zero", "u1"),
-                      ("angle_y", "u1"), ("angle_uv", "u1"), ("pad", "u1", 2)])
+                      ("angle_y", "u1"), ("angle_uv", "u1"), ("cfl_js", "u1"), ("cfl_alpha", "u1")])
 MI_DTYPE = np.dtype([("bsize", "u1"), ("y_mode", "u1"), ("uv_mode", "u1"), ("angle", "u1"),
                      ("tx_size", "u1"), ("tx_type", "u1"), ("flags", "u1"), ("cfl", "u1")])
 

@@ -45,7 +45,7 @@ def compare_analysis(ref, out, f):
         if n < min(f.partition_min, 8) or n > f.partition_max:
             continue
         assert np.array_equal(ref.satd[lv], out.satd[lv]), "SATD table level %d" % lv
-        for k in ("cost", "y_mode", "tx_type", "uv_mode", "all_zero", "angle_y", "angle_uv"):
+        for k in ("cost", "y_mode", "tx_type", "uv_mode", "all_zero", "angle_y", "angle_uv", "cfl_js", "cfl_alpha"):
             assert np.array_equal(ref.dec[lv][k], out.dec[lv][k]), "decision %s level %d" % (k, lv)
 
 
