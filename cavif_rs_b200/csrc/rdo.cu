@@ -85,7 +85,7 @@ __device__ __forceinline__ int txs_of(int n) { return n == 4 ? 0 : n == 8 ? 1 : 
 __device__ __forceinline__ int scan_base(int n) { return n == 4 ? 0 : n == 8 ? 16 : 80; }
 __device__ __forceinline__ int ilog2_dev(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
-__device__ __forceinline__ long long warp_sum_ll(long long v) {
+__device__ __noinline__ long long warp_sum_ll(long long v) {
   for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
   return v;
 }
@@ -114,7 +114,7 @@ __device__ __forceinline__ void warp_argmin(long long &J, int &idx) {
 // ---- edges (AV1 spec 7.11.2, intra edge filter disabled) from plane `r` (source in the analysis, reconstruction in
 // the final pass) into sh.above/left[slot]; top-right / bottom-left availability = static coding order predicate
 // avail: bit0 have_above, bit1 have_left, bit2 have_above_right, bit3 have_below_left (block_avail(), once per block)
-__device__ __forceinline__ int block_avail(const TileCtx &t, int x, int y, int n) {
+__device__ __noinline__ int block_avail(const TileCtx &t, int x, int y, int n) {
   const int mi_r = y >> 2, mi_c = x >> 2, n4 = n >> 2;
   const int ha = mi_r > t.tr0, hl = mi_c > t.tc0;
   const int ar = ha && b200_unit_before(mi_r - 1, mi_c + n4, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
@@ -157,11 +157,13 @@ __device__ __noinline__ void build_edges(const TileCtx &t, Shared &sh, const uin
 }
 
 // ---- intra predictors (AV1 spec 7.11.2.x): value of pixel (i, j) of an n x n block ------------------
-__device__ __forceinline__ int dc_value(int n, const uint16_t *A, const uint16_t *L, int ha, int hl, int bd) {
-  if (ha && hl) { int s = 0; for (int i = 0; i < n; i++) s += A[i] + L[i]; return (s + n) / (2 * n); }
-  if (hl) { int s = 0; for (int i = 0; i < n; i++) s += L[i]; return (s + (n >> 1)) / n; }
-  if (ha) { int s = 0; for (int i = 0; i < n; i++) s += A[i]; return (s + (n >> 1)) / n; }
-  return 1 << (bd - 1);
+__device__ __noinline__ int dc_value(int n, const uint16_t *A, const uint16_t *L, int ha, int hl, int bd) {
+  if (!ha && !hl) return 1 << (bd - 1);
+  const int lg = 31 - __clz(n);          // n is a power of two: the spec's divisions are shifts
+  int s = 0;
+#pragma unroll 1
+  for (int i = 0; i < n; i++) s += (ha ? A[i] : 0) + (hl ? L[i] : 0);
+  return (ha && hl) ? (s + n) >> (lg + 1) : (s + (n >> 1)) >> lg;
 }
 // A, L point at index 0 of the edge arrays (index -1 valid).  dc: precomputed DC value (used for DC_PRED only).
 __device__ __forceinline__ int pred_px(int mode, int delta, int n, int i, int j, const uint16_t *A, const uint16_t *L, int dc) {
@@ -508,7 +510,7 @@ __device__ __noinline__ void cfl_predict_block(const int16_t *ac, int N2, int dc
     dst[p] = (uint16_t)(v < 0 ? 0 : (v > mx ? mx : v));
   }
 }
-__device__ __forceinline__ uint32_t cfl_rate(const B200RateTables *rt, int au, int av) {
+__device__ __noinline__ uint32_t cfl_rate(const B200RateTables *rt, int au, int av) {
   const int su = au == 0 ? 0 : (au < 0 ? 1 : 2), sv = av == 0 ? 0 : (av < 0 ? 1 : 2);
   uint32_t r = rt->cfl_sign[su * 3 + sv - 1];
   if (su) r += rt->cfl_alpha[(su - 1) * 3 + sv][abs(au) - 1];
@@ -553,11 +555,14 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
   const int lane = lane_id(), g = lane >> lg;
   const int planes = f->planes, bd = f->bit_depth;
   // ---- stage source block and SOURCE edges; clear the padded level maps
+#pragma unroll 1
   for (int p = 0; p < planes; p++)
 #pragma unroll 1
     for (int q = lane; q < N2; q += 32) sh.src[p][q] = t.src[p][(y + (q >> lg)) * t.stride + x + (q & (n - 1))];
+#pragma unroll 1
   for (int i = lane; i < 200; i += 32) reinterpret_cast<uint32_t *>(sh.lev)[i] = 0;
   const int avail = block_avail(t, x, y, n), ha = avail & 1, hl = (avail >> 1) & 1;
+#pragma unroll 1
   for (int p = 0; p < planes; p++) build_edges(t, sh, t.src[p], p, x, y, n, avail);
   __syncwarp();
   // ---- ranking from the SATD table (context-0 mode rates)
@@ -651,6 +656,7 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
       const TrialOut r = trial_batch<n, HBD>(t, sh, p, sh.src[p], sh.pred + (ok ? g : 0) * N2, chroma_tx_type(ok ? m : 0), best_mode);
       if (ok && (lane & (n - 1)) == 0) { sh.taskD[ci] = r.sse; sh.taskR[ci] = r.rate; sh.taskE[ci] = (uint16_t)r.eob; }
       __syncwarp();
+#pragma unroll 1
       for (int kk = 0; kk < NC / 2; kk++) {
         const int cU = kk * 2, cV = kk * 2 + 1;
         if (cV < b * G || cV >= (b + 1) * G) continue;
@@ -693,11 +699,14 @@ __device__ __noinline__ void reconstruct_block(const TileCtx &t, Shared &sh, int
   const int planes = f->planes, bd = f->bit_depth;
   const int mi_r = y >> 2, mi_c = x >> 2, n4 = n >> 2;
   const B200Mi m = t.mi[mi_r * f->mi_cols + mi_c];
+#pragma unroll 1
   for (int p = 0; p < planes; p++)
 #pragma unroll 1
     for (int q = lane; q < N2; q += 32) sh.src[p][q] = t.src[p][(y + (q >> lg)) * t.stride + x + (q & (n - 1))];
+#pragma unroll 1
   for (int i = lane; i < 200; i += 32) reinterpret_cast<uint32_t *>(sh.lev)[i] = 0;
   const int avail = block_avail(t, x, y, n), ha = avail & 1, hl = (avail >> 1) & 1;
+#pragma unroll 1
   for (int p = 0; p < planes; p++) build_edges(t, sh, t.rec[p], p, x, y, n, avail);
   __syncwarp();
   const long long coff = b200_coef_offset(f, mi_r, mi_c);
@@ -776,117 +785,101 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
   const int have_bl = hl && b200_unit_before(mi_r + n4, mi_c - 1, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
   const int mask = grp == 0 ? f->y_mode_mask : f->uv_mode_mask;
   __shared__ int sh_d[128 * 17];     // per-thread 16 residuals (+1 pad: conflict-free), written by a rolled loop
-  uint32_t acc[13];
+  // acc[0..12]: SATD of the 13 nominal modes; acc[13..18]: the refined directional mode at deltas -3,-2,-1,1,2,3.
+  // Both passes run through ONE rolled copy of the edge / predictor / Hadamard code (instruction-cache footprint).
+  uint32_t acc[19];
 #pragma unroll
-  for (int m = 0; m < 13; m++) acc[m] = 0;
+  for (int m = 0; m < 19; m++) acc[m] = 0;
   uint16_t Ab[EOFF + 34], Lb[EOFF + 34];
   uint16_t *A = Ab + EOFF, *L = Lb + EOFF;
-  // source-neighbour edges of plane r (same rules as build_edges, one thread)
-  auto edges = [&](const uint16_t *r) {
-#pragma unroll 1
-    for (int i = 0; i < 2 * n; i++) {
-      uint16_t a, l;
-      if (!ha && hl) a = r[y * st + x - 1];
-      else if (!ha && !hl) a = (uint16_t)(base - 1);
-      else { int xx = (i < n || have_ar) ? x + i : x + n - 1; if (xx > max_x) xx = max_x; a = r[(y - 1) * st + xx]; }
-      if (!hl && ha) l = r[(y - 1) * st + x];
-      else if (!hl && !ha) l = (uint16_t)(base + 1);
-      else { int yy = (i < n || have_bl) ? y + i : y + n - 1; if (yy > max_y) yy = max_y; l = r[yy * st + x - 1]; }
-      A[i] = a; L[i] = l;
-    }
-    uint16_t tl;
-    if (ha && hl) tl = r[(y - 1) * st + x - 1];
-    else if (ha) tl = r[(y - 1) * st + x];
-    else if (hl) tl = r[y * st + x - 1];
-    else tl = (uint16_t)base;
-    A[-1] = tl; L[-1] = tl;
-  };
-  // 4x4 Hadamard SATD of one sub-block against mode m / delta
-  auto satd16 = [&](const int *s, int m, int delta, int sy, int sx, int dc) -> uint32_t {
-    int tt[16], d[16];
-#pragma unroll 1
-    for (int k = 0; k < 16; k++) sh_d[threadIdx.x * 17 + k] = s[k] - pred_px(m, delta, n, sy + (k >> 2), sx + (k & 3), A, L, dc);
-#pragma unroll
-    for (int k = 0; k < 16; k++) d[k] = sh_d[threadIdx.x * 17 + k];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int a = d[i * 4] + d[i * 4 + 1], b = d[i * 4] - d[i * 4 + 1], c = d[i * 4 + 2] + d[i * 4 + 3], e = d[i * 4 + 2] - d[i * 4 + 3];
-      tt[i * 4] = a + c; tt[i * 4 + 1] = b + e; tt[i * 4 + 2] = a - c; tt[i * 4 + 3] = b - e;
-    }
-    uint32_t total = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int a = tt[j] + tt[4 + j], b = tt[j] - tt[4 + j], c = tt[8 + j] + tt[12 + j], e = tt[8 + j] - tt[12 + j];
-      total += (uint32_t)(abs(a + c) + abs(b + e) + abs(a - c) + abs(b - e));
-    }
-    return total;
-  };
   const int p_end = grp == 0 ? 1 : 3;
+  int md = -1;
+  uint32_t smd = 0;
 #pragma unroll 1
-  for (int p = grp; p < p_end; p++) {
-    const uint16_t *r = job.src[p];
-    edges(r);
-    const int dc = dc_value(n, A, L, ha, hl, bd);
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1) {
+      // angle refinement of the best directional mode (oracle refine_angle)
+      if (!(f->fine_directional_intra && n >= 8)) break;
 #pragma unroll 1
-    for (int sb = 0; sb < (n4 * n4); sb++) {
-      const int sy = (sb >> (lg - 2)) * 4, sx = (sb & (n4 - 1)) * 4;
-      int s[16];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) s[i * 4 + j] = r[(y + sy + i) * st + x + sx + j];
-#pragma unroll 1
-      for (int m = 0; m < 13; m++) {
-        if (!((mask >> m) & 1)) continue;
-        acc[m] += satd16(s, m, 0, sy, sx, dc);
-      }
+      for (int m = V_PRED; m <= D67_PRED; m++)
+        if (((mask >> m) & 1) && (md < 0 || acc[m] < smd)) { md = m; smd = acc[m]; }
+      if (md < 0) break;
     }
-  }
-  // angle refinement of the best directional mode (oracle refine_angle): deltas -3..3 by SATD + delta rate
-  uint32_t word = 255u | (3u << 8);
-  if (f->fine_directional_intra && n >= 8) {
-    int md = -1;
-    uint32_t smd = 0;
-#pragma unroll
-    for (int m = V_PRED; m <= D67_PRED; m++)
-      if (((mask >> m) & 1) && (md < 0 || acc[m] < smd)) { md = m; smd = acc[m]; }
-    if (md >= 0) {
-      uint32_t sv[6];
-#pragma unroll
-      for (int k = 0; k < 6; k++) sv[k] = 0;
+    const int ncand = pass ? 6 : 13;
 #pragma unroll 1
-      for (int p = grp; p < p_end; p++) {
-        const uint16_t *r = job.src[p];
-        if (p_end - grp > 1 || p != grp) edges(r);      // single-plane group: edges still hold this plane
+    for (int p = grp; p < p_end; p++) {
+      const uint16_t *r = job.src[p];
+      if (pass == 0 || p_end - grp > 1) {     // single-plane group: the edges of pass 0 are still valid in pass 1
+        // source-neighbour edges (same rules as build_edges, one thread)
 #pragma unroll 1
-        for (int sb = 0; sb < (n4 * n4); sb++) {
-          const int sy = (sb >> (lg - 2)) * 4, sx = (sb & (n4 - 1)) * 4;
-          int s[16];
+        for (int i = 0; i < 2 * n; i++) {
+          uint16_t a, l;
+          if (!ha && hl) a = r[y * st + x - 1];
+          else if (!ha && !hl) a = (uint16_t)(base - 1);
+          else { int xx = (i < n || have_ar) ? x + i : x + n - 1; if (xx > max_x) xx = max_x; a = r[(y - 1) * st + xx]; }
+          if (!hl && ha) l = r[(y - 1) * st + x];
+          else if (!hl && !ha) l = (uint16_t)(base + 1);
+          else { int yy = (i < n || have_bl) ? y + i : y + n - 1; if (yy > max_y) yy = max_y; l = r[yy * st + x - 1]; }
+          A[i] = a; L[i] = l;
+        }
+        uint16_t tl;
+        if (ha && hl) tl = r[(y - 1) * st + x - 1];
+        else if (ha) tl = r[(y - 1) * st + x];
+        else if (hl) tl = r[y * st + x - 1];
+        else tl = (uint16_t)base;
+        A[-1] = tl; L[-1] = tl;
+      }
+      const int dc = dc_value(n, A, L, ha, hl, bd);
+#pragma unroll 1
+      for (int sb = 0; sb < (n4 * n4); sb++) {
+        const int sy = (sb >> (lg - 2)) * 4, sx = (sb & (n4 - 1)) * 4;
+        int s[16];
 #pragma unroll
-          for (int i = 0; i < 4; i++)
+        for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) s[i * 4 + j] = r[(y + sy + i) * st + x + sx + j];
+          for (int j = 0; j < 4; j++) s[i * 4 + j] = r[(y + sy + i) * st + x + sx + j];
+#pragma unroll 1
+        for (int c = 0; c < ncand; c++) {
+          if (pass == 0 && !((mask >> c) & 1)) continue;
+          const int m = pass ? md : c, delta = pass ? (c < 3 ? c - 3 : c - 2) : 0;
+          int tt[16], d[16];
+#pragma unroll 1
+          for (int k = 0; k < 16; k++) sh_d[threadIdx.x * 17 + k] = pred_px(m, delta, n, sy + (k >> 2), sx + (k & 3), A, L, dc);
 #pragma unroll
-          for (int k = 0; k < 6; k++) sv[k] += satd16(s, md, k < 3 ? k - 3 : k - 2, sy, sx, 0);
+          for (int k = 0; k < 16; k++) d[k] = s[k] - sh_d[threadIdx.x * 17 + k];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int a = d[i * 4] + d[i * 4 + 1], b = d[i * 4] - d[i * 4 + 1], c2 = d[i * 4 + 2] + d[i * 4 + 3], e = d[i * 4 + 2] - d[i * 4 + 3];
+            tt[i * 4] = a + c2; tt[i * 4 + 1] = b + e; tt[i * 4 + 2] = a - c2; tt[i * 4 + 3] = b - e;
+          }
+          uint32_t total = 0;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int a = tt[j] + tt[4 + j], b = tt[j] - tt[4 + j], c2 = tt[8 + j] + tt[12 + j], e = tt[8 + j] - tt[12 + j];
+            total += (uint32_t)(abs(a + c2) + abs(b + e) + abs(a - c2) + abs(b - e));
+          }
+          acc[pass * 13 + c] += total;
         }
       }
-      const uint16_t *drate = job.rate->angle_delta[md - V_PRED];
-      long long best = (long long)smd * 64 + (((long long)f->lambda_satd_q8 * drate[3]) >> 8);
-      int best_d = 0;
-      uint32_t best_s = smd;
-#pragma unroll
-      for (int k = 0; k < 6; k++) {
-        const int d = k < 3 ? k - 3 : k - 2;
-        const long long c = (long long)sv[k] * 64 + (((long long)f->lambda_satd_q8 * drate[d + 3]) >> 8);
-        if (c < best) { best = c; best_d = d; best_s = sv[k]; }
-      }
-#pragma unroll
-      for (int m = V_PRED; m <= D67_PRED; m++) if (m == md) acc[m] = best_s;
-      word = (uint32_t)md | ((uint32_t)(best_d + 3) << 8);
     }
   }
+  uint32_t word = 255u | (3u << 8);
+  if (md >= 0) {
+    const uint16_t *drate = job.rate->angle_delta[md - V_PRED];
+    long long best = (long long)smd * 64 + (((long long)f->lambda_satd_q8 * drate[3]) >> 8);
+    int best_d = 0;
+    uint32_t best_s = smd;
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+      const int d = k < 3 ? k - 3 : k - 2;
+      const long long c = (long long)acc[13 + k] * 64 + (((long long)f->lambda_satd_q8 * drate[d + 3]) >> 8);
+      if (c < best) { best = c; best_d = d; best_s = acc[13 + k]; }
+    }
+    acc[md] = best_s;
+    word = (uint32_t)md | ((uint32_t)(best_d + 3) << 8);
+  }
   uint32_t *out = job.satd[lv] + ((size_t)blk * 2 + grp) * B200_SATD_WORDS;
-#pragma unroll
+#pragma unroll 1
   for (int m = 0; m < 13; m++) out[m] = acc[m];
   out[13] = word;
 }
