@@ -361,7 +361,6 @@ struct ImageWork {
   // input
   const uint8_t *pixels = nullptr; bool on_device = false; int channels = 4;
   size_t w = 0, h = 0, stride = 0;
-  std::vector<uint8_t> cleaned;     // alpha-cleaned copy (host) if any
   // raw planes input (encode_raw_planes_*)
   bool raw = false; std::vector<uint16_t> raw_planes[3], raw_alpha; bool raw_has_alpha = false;
   int raw_range = 1, raw_mc = 6;
@@ -383,21 +382,7 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
   const int depth = enc.output_depth == 8 ? 8 : 10;
   const int mc = enc.color_model == B200AVIF_COLOR_YCBCR ? B200AVIF_MC_BT601 : B200AVIF_MC_IDENTITY;
 
-  // ---- host-side alpha pre-clean (av1encoder.rs:277-299), images in parallel on the host cores
-  parallel_for(imgs.size(), [&](size_t i) {
-    ImageWork &im = imgs[i];
-    im.depth = depth;
-    if (im.raw || im.channels != 4 || im.on_device) return;
-    if (enc.alpha_color_mode == B200AVIF_ALPHA_UNASSOCIATED_CLEAN) {
-      im.cleaned.resize(im.w * im.h * 4);
-      if (b200_blurred_dirty_alpha(im.pixels, im.w, im.h, im.stride, im.cleaned.data())) { im.pixels = im.cleaned.data(); im.stride = im.w; }
-      else im.cleaned.clear();
-    } else if (enc.alpha_color_mode == B200AVIF_ALPHA_PREMULTIPLIED) {
-      im.cleaned.resize(im.w * im.h * 4);
-      b200_premultiplied_branch(im.pixels, im.w, im.h, im.stride, im.cleaned.data());
-      im.pixels = im.cleaned.data(); im.stride = im.w;
-    }
-  });
+  for (ImageWork &im : imgs) im.depth = depth;
   // ---- frame descriptions
   for (ImageWork &im : imgs) {
     const int cmc = im.raw ? im.raw_mc : mc;
@@ -429,6 +414,7 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
       pin_bytes += job_pin_bytes(im.color) + job_pin_bytes(im.alpha);
       const size_t in_bytes = im.raw ? (im.w * im.h * 2 * 4) : (im.stride * im.h * im.channels);
       dev_bytes += align256(in_bytes) + 512;
+      if (!im.raw && im.channels == 4) dev_bytes += 2 * align256(im.w * im.h * 4) + 512;    // alpha pre-clean scratch
       if (!im.on_device) pin_bytes += align256(in_bytes) + 512;
     }
     if (c.dev.reserve(dev_bytes) || c.pin.reserve(pin_bytes)) return B200AVIF_ENCODING_ERROR;
@@ -478,7 +464,18 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
         h2d += bytes;
         d_in = d;
       }
-      if (int e = b200_convert_launch(d_in, im.channels, (int)im.w, (int)im.h, (int)im.stride, cw, chh, depth, enc.color_model,
+      size_t in_stride = im.stride;
+      if (im.channels == 4 && enc.alpha_color_mode != B200AVIF_ALPHA_UNASSOCIATED_DIRTY) {
+        // alpha pre-clean on the device (av1encoder.rs:277-299, dirtyalpha.rs): the converter reads the cleaned copy
+        const int mode = enc.alpha_color_mode == B200AVIF_ALPHA_PREMULTIPLIED ? 2 : 1;
+        uint8_t *d_tmp = c.dev.take<uint8_t>(im.w * im.h * 4), *d_clean = c.dev.take<uint8_t>(im.w * im.h * 4);
+        unsigned long long *d_acc = c.dev.take<unsigned long long>(4);
+        if (int e = b200_alpha_clean_launch(d_in, (int)im.w, (int)im.h, (int)im.stride, mode, d_tmp, d_clean, d_acc, c.stream))
+          return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
+        g_launches += mode == 2 ? 1 : 3;
+        d_in = d_clean; in_stride = im.w;
+      }
+      if (int e = b200_convert_launch(d_in, im.channels, (int)im.w, (int)im.h, (int)in_stride, cw, chh, depth, enc.color_model,
                                       im.color.d_src[0], im.color.d_src[1], im.color.d_src[2],
                                       im.channels == 4 ? im.alpha.d_src[0] : nullptr, im.channels == 4 ? d_flags + (i - ch.a) : nullptr, c.stream))
         return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
@@ -730,6 +727,27 @@ int b200av1_encode_planes(const b200av1_config *cfg, const uint16_t *const plane
 }
 
 // ---- test seam: colour conversion kernel on host pixels -> coded planes (mi-aligned, edge replicated)
+int b200av1_alpha_clean_run(const uint8_t *rgba, size_t w, size_t h, size_t stride_px, int mode, uint8_t *out) {
+  if (!rgba || !out || w == 0 || h == 0 || (mode != 1 && mode != 2)) return fail(B200AVIF_INVALID_ARGUMENT, "bad argument");
+  if (b200avif_device_count() <= 0) return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
+  std::unique_ptr<Context> ctx;
+  if (int e = acquire_context(-1, ctx)) return e;
+  Context &c = *ctx;
+  struct Release { std::unique_ptr<Context> &c; ~Release() { release_context(c); } } rel{ctx};
+  const size_t in_bytes = (stride_px * (h - 1) + w) * 4, img_bytes = w * h * 4;
+  if (c.dev.reserve(align256(in_bytes) + 2 * align256(img_bytes) + 8192) || c.pin.reserve(4096)) return B200AVIF_ENCODING_ERROR;
+  c.dev.reset(); c.pin.reset();
+  uint8_t *d_in = c.dev.take<uint8_t>(in_bytes + 16), *d_tmp = c.dev.take<uint8_t>(img_bytes), *d_out = c.dev.take<uint8_t>(img_bytes);
+  unsigned long long *d_acc = c.dev.take<unsigned long long>(4);
+  CU(cudaMemcpyAsync(d_in, rgba, in_bytes, cudaMemcpyHostToDevice, c.stream));
+  if (int e = b200_alpha_clean_launch(d_in, (int)w, (int)h, (int)stride_px, mode, d_tmp, d_out, d_acc, c.stream))
+    return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
+  g_launches += mode == 2 ? 1 : 3;
+  CU(cudaMemcpyAsync(out, d_out, img_bytes, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
 int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h, size_t stride_px, int depth, int color_model,
                         uint16_t *const planes[4] /* y,u,v,alpha (alpha may be NULL) */, int *any_alpha) {
   if (!pixels || !planes || w == 0 || h == 0) return fail(B200AVIF_INVALID_ARGUMENT, "null argument");

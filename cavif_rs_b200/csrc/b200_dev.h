@@ -10,9 +10,14 @@ extern "C" {
 int b200_convert_launch(const uint8_t *d_in, int channels, int width, int height, int stride_px, int cw, int ch, int depth,
                         int color_model, uint16_t *p0, uint16_t *p1, uint16_t *p2, uint16_t *alpha, int *any_alpha,
                         void *stream);
+// alpha_clean.cu: dirtyalpha.rs / premultiplied branch on the device (mode 1 = UnassociatedClean, 2 = Premultiplied)
+int b200_alpha_clean_launch(const uint8_t *d_in, int w, int h, int stride_px, int mode, uint8_t *d_tmp, uint8_t *d_out,
+                            unsigned long long *d_acc, void *stream);
 int b200_pad_plane_launch(const uint16_t *d_in, int width, int height, int in_stride, uint16_t *d_out, int cw, int ch,
                           void *stream);
 // Test seam: colour-conversion kernel.  planes[p]: (8*ceil(h/8)) x (8*ceil(w/8)) uint16 each.
+// test seam: runs the device alpha pre-clean on host pixels, returns the cleaned w*h RGBA8 image
+int b200av1_alpha_clean_run(const uint8_t *rgba, size_t w, size_t h, size_t stride_px, int mode, uint8_t *out);
 int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h, size_t stride_px, int depth, int color_model,
                         uint16_t *const planes[4], int *any_alpha);
 // Test seam: run the device hot path (RDO kernel, then deblock + CDEF search) on host-provided CODED planes

@@ -16,10 +16,6 @@ typedef struct B200SpeedTweaks {
 uint8_t b200_quality_to_quantizer(float quality);                       // av1encoder.rs:526-530
 void b200_speed_tweaks(int speed, int quantizer, B200SpeedTweaks *t);    // av1encoder.rs:555-605
 size_t b200_tile_target(size_t threads /*0 = None*/, size_t w, size_t h, size_t min_tile_size);   // :665-668
-// dirtyalpha.rs:17-41; out = w*h*4 tightly packed. returns 1 if the image was changed (Some), 0 for None.
-int b200_blurred_dirty_alpha(const uint8_t *rgba, size_t w, size_t h, size_t stride_px, uint8_t *out);
-// av1encoder.rs:282-297 (AlphaColorMode::Premultiplied branch, as coded)
-void b200_premultiplied_branch(const uint8_t *rgba, size_t w, size_t h, size_t stride_px, uint8_t *out);
 #ifdef __cplusplus
 }
 #endif

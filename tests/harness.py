@@ -82,8 +82,7 @@ def hostlib():
         _host.b200av1_convert_run.argtypes = [V, I, Z, Z, Z, I, I, V, V]
         _host.b200av1_seq_level_idx.argtypes = [V]
         _host.b200avif_mux.argtypes = [V, V, V]
-        _host.b200_blurred_dirty_alpha.argtypes = [V, Z, Z, Z, V]
-        _host.b200_premultiplied_branch.argtypes = [V, Z, Z, Z, V]
+        _host.b200av1_alpha_clean_run.argtypes = [V, Z, Z, Z, I, V]
         _host.b200_speed_tweaks.argtypes = [I, I, V]
         _host.b200avif_quality_to_quantizer.restype = ctypes.c_uint8
         _host.b200avif_quality_to_quantizer.argtypes = [ctypes.c_float]

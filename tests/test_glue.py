@@ -82,19 +82,18 @@ def test_speed_tweaks_table():
 
 
 @pytest.mark.parametrize("seed", [0, 1])
-def test_dirty_alpha_product_matches_oracle(seed):
-    L = _orc(); P = H.hostlib()
+def test_dirty_alpha_oracle_properties(seed):
+    """the oracle's dirtyalpha restatement (the device kernels are compared with it in tests/test_gpu_parity.py)"""
+    L = _orc()
     img = H.synth_image(97, 61, seed, alpha=True)
-    a = np.zeros_like(img); b = np.zeros_like(img)
-    ra = L.orc_blurred_dirty_alpha(img.ctypes.data, 97, 61, 97, a.ctypes.data)
-    ra = L.orc_blurred_dirty_alpha(img.ctypes.data, 97, 61, 97, a.ctypes.data)
-    rb = P.b200_blurred_dirty_alpha(img.ctypes.data, 97, 61, 97, b.ctypes.data)
-    assert ra == rb == 1 and np.array_equal(a, b)
+    a = np.zeros_like(img)
+    assert L.orc_blurred_dirty_alpha(img.ctypes.data, 97, 61, 97, a.ctypes.data) == 1
     assert np.array_equal(a[..., 3], img[..., 3])            # alpha untouched
     opaque = img[..., 3] == 255
     assert np.array_equal(a[opaque], img[opaque])            # opaque pixels untouched
+    assert not np.array_equal(a[img[..., 3] == 0], img[img[..., 3] == 0])
     op = img.copy(); op[..., 3] = 255
     assert L.orc_blurred_dirty_alpha(op.ctypes.data, 97, 61, 97, a.ctypes.data) == 0   # None for opaque images
     L.orc_premultiplied_branch(img.ctypes.data, 97, 61, 97, a.ctypes.data)
-    P.b200_premultiplied_branch(img.ctypes.data, 97, 61, 97, b.ctypes.data)
-    assert np.array_equal(a, b)
+    semi = (img[..., 3] != 0) & (img[..., 3] != 255)
+    assert not a[~semi].any()

@@ -76,6 +76,32 @@ def test_convert_kernel_bit_exact(depth, color_model):
     assert flag.value == 0
 
 
+@pytest.mark.parametrize("seed,w,h,stride", [(0, 97, 61, 97), (1, 333, 131, 340), (2, 1, 1, 1), (3, 5, 300, 8)])
+def test_alpha_clean_kernels_match_oracle(seed, w, h, stride):
+    """dirtyalpha.rs on the device (alpha_clean.cu) vs the oracle restatement: UnassociatedClean and Premultiplied"""
+    L = H.hostlib(); O = H.oracle()
+    rng = np.random.default_rng(seed)
+    img = np.zeros((h, stride, 4), np.uint8)
+    img[:, :w] = H.synth_image(w, h, seed, alpha=True)
+    # sprinkle every alpha class next to each other, including a = 1 (the u8 truncation case of premultiplied_minmax)
+    k = rng.integers(0, 4, (h, w))
+    img[:, :w, 3] = np.where(k == 0, 0, np.where(k == 1, 255, np.where(k == 2, 1, img[:, :w, 3])))
+    ref = np.zeros((h, w, 4), np.uint8); out = np.zeros((h, w, 4), np.uint8)
+    changed = O.orc_blurred_dirty_alpha(img.ctypes.data, w, h, stride, ref.ctypes.data)
+    if not changed:
+        ref = img[:, :w].copy()
+    assert L.b200av1_alpha_clean_run(img.ctypes.data, w, h, stride, 1, out.ctypes.data) == 0, L.b200avif_last_error_message()
+    assert np.array_equal(ref, out)
+    O.orc_premultiplied_branch(img.ctypes.data, w, h, stride, ref.ctypes.data)
+    assert L.b200av1_alpha_clean_run(img.ctypes.data, w, h, stride, 2, out.ctypes.data) == 0
+    assert np.array_equal(ref, out)
+    # an opaque image is passed through untouched (blurred_dirty_alpha() -> None)
+    img[..., 3] = 255
+    assert O.orc_blurred_dirty_alpha(img.ctypes.data, w, h, stride, ref.ctypes.data) == 0
+    assert L.b200av1_alpha_clean_run(img.ctypes.data, w, h, stride, 1, out.ctypes.data) == 0
+    assert np.array_equal(img[:, :w], out)
+
+
 @pytest.mark.parametrize("depth", [8, 10])
 def test_convert_exhaustive_2_24_colours(depth):
     L = _dev(); O = H.oracle()
