@@ -974,10 +974,21 @@ __global__ void __launch_bounds__(128) b200_decide_kernel(const B200RdoJob *jobs
   }
 }
 
-// ---- stage C: one single-warp CTA per tile walks its superblocks in raster order and the decided blocks in z-order
+// ---- stage C: one CTA per tile, kReconWarps warps on a superblock-row wavefront.  Warp w owns the tile's SB rows
+// w, w + W, ...; it walks a row left to right (the decided blocks of each SB in z-order) and may start SB (R, C) once
+// row R - 1 has finished SB C + 1: the above-right superblock is the furthest reconstruction any intra edge of this
+// SB can read (its bottom-left 64x64 neighbour is never decoded before it).  Progress counters live in shared memory.
+constexpr int kReconWarps = 4;
+constexpr int kMaxSbRows = 1024;     // 65536 / 64
+#ifdef B200_EMU
+#define B200_SPIN_WAIT() emu::yield()
+#else
+#define B200_SPIN_WAIT() __nanosleep(40)
+#endif
 template <bool HBD>
-__global__ void __launch_bounds__(kThreads, 16) b200_recon_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
-  __shared__ Shared sh;
+__global__ void __launch_bounds__(kThreads * kReconWarps, 4) b200_recon_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
+  __shared__ Shared shs[kReconWarps];
+  __shared__ volatile int sb_done[kMaxSbRows];      // superblocks finished in each SB row of this tile
   const B200TileRef tr = tiles[blockIdx.x];
   const B200RdoJob &job = jobs[tr.job];
   TileCtx t;
@@ -987,10 +998,23 @@ __global__ void __launch_bounds__(kThreads, 16) b200_recon_kernel(const B200RdoJ
   t.tr1 = min(f->tile_row_start_sb[tr.tile_row + 1] * 16, f->mi_rows);
   t.tc0 = f->tile_col_start_sb[tr.tile_col] * 16;
   t.tc1 = min(f->tile_col_start_sb[tr.tile_col + 1] * 16, f->mi_cols);
+  const int sb_rows = (t.tr1 - t.tr0 + 15) >> 4, sb_cols = (t.tc1 - t.tc0 + 15) >> 4;
+  for (int i = threadIdx.x; i < sb_rows; i += blockDim.x) sb_done[i] = 0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  Shared &sh = shs[warp];
 #pragma unroll 1
-  for (int r = t.tr0; r < t.tr1; r += 16)
+  for (int R = warp; R < sb_rows; R += kReconWarps) {
+    const int r = t.tr0 + R * 16;
 #pragma unroll 1
-    for (int c = t.tc0; c < t.tc1; c += 16)
+    for (int C = 0; C < sb_cols; C++) {
+      if (R > 0) {
+        const int need = min(C + 2, sb_cols);
+        while (sb_done[R - 1] < need) B200_SPIN_WAIT();
+        __syncwarp();
+        __threadfence_block();
+      }
+      const int c = t.tc0 + C * 16;
 #pragma unroll 1
       for (int z = 0; z < 256;) {          // 4x4 units of the superblock in z-order; skip over whole blocks
         int ur = 0, uc = 0;
@@ -1002,6 +1026,11 @@ __global__ void __launch_bounds__(kThreads, 16) b200_recon_kernel(const B200RdoJ
         reconstruct_block<HBD>(t, sh, mc * 4, mr * 4, lg);
         z += 1 << (2 * (lg - 2));           // a block covers (n/4)^2 consecutive z indices
       }
+      __threadfence_block();               // the reconstruction of this SB is visible before the counter moves
+      __syncwarp();
+      if (lane_id() == 0) sb_done[R] = C + 1;
+    }
+  }
 }
 
 #ifndef B200_EMU
@@ -1037,8 +1066,8 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
   }
   dim3 gd((max_blocks4 / 16 + 64 + 127) / 128, n_jobs);
   b200_decide_kernel<<<gd, 128, 0, st>>>(d_jobs);
-  if (high_bitdepth) b200_recon_kernel<true><<<n_tiles, kThreads, 0, st>>>(d_jobs, d_tiles);
-  else b200_recon_kernel<false><<<n_tiles, kThreads, 0, st>>>(d_jobs, d_tiles);
+  if (high_bitdepth) b200_recon_kernel<true><<<n_tiles, kThreads * kReconWarps, 0, st>>>(d_jobs, d_tiles);
+  else b200_recon_kernel<false><<<n_tiles, kThreads * kReconWarps, 0, st>>>(d_jobs, d_tiles);
   return (int)cudaGetLastError();
 }
 #else
@@ -1065,7 +1094,7 @@ extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *ti
     emu::launch(emu_analyze, nullptr, (unsigned)std::min(nblk, 7), kThreads);
   }
   emu::launch(emu_decide, nullptr, (unsigned)((nblk4 / 16 + 64 + 127) / 128), 128);
-  emu::launch(emu_recon, nullptr, (unsigned)n_tiles, kThreads);
+  emu::launch(emu_recon, nullptr, (unsigned)n_tiles, kThreads * kReconWarps);
   return 0;
 }
 #endif

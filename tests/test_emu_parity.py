@@ -53,6 +53,7 @@ def compare_analysis(ref, out, f):
     (64, 48, 8, 3, 1, {}),
     (40, 72, 10, 1, 2, dict(partition_min=8, rdo_tx_decision=0)),
     (72, 40, 8, 3, 1, dict(partition_min=16, partition_max=16, rdo_tx_decision=0)),   # forced 8x8 splits at the edges
+    (200, 136, 8, 3, 1, dict(partition_min=8)),      # 4 x 3 superblocks: the reconstruction wavefront waits on its neighbours
 ])
 def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
     E = emu_lib()
