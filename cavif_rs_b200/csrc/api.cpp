@@ -108,9 +108,11 @@ size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct Context {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // upload, conversion, open-loop analysis, partition decision
+  cudaStream_t stream_hi = nullptr;   // high priority: reconstruction chain, in-loop filters, record download
   Arena dev{false}, pin{true};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_analysis = nullptr;  // stages A + B of the current chunk are done
   std::map<int, B200RateTables *> d_rate;   // per base_q_idx
   ~Context() {}
 };
@@ -129,8 +131,12 @@ int acquire_context(int device, std::unique_ptr<Context> &out) {
   if (!out) {
     out.reset(new Context());
     out->device = device;
-    CU(cudaStreamCreateWithFlags(&out->stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU(cudaStreamCreateWithPriority(&out->stream, cudaStreamNonBlocking, prio_lo));
+    CU(cudaStreamCreateWithPriority(&out->stream_hi, cudaStreamNonBlocking, prio_hi));
     for (auto &e : out->ev) CU(cudaEventCreate(&e));
+    CU(cudaEventCreateWithFlags(&out->ev_analysis, cudaEventDisableTiming));
   }
   return 0;
 }
@@ -242,8 +248,12 @@ int rate_tables_for(Context &c, int qidx, B200RateTables **out) {
 
 // Issue (asynchronously, on c.stream) the RDO stages + in-loop filters for a set of jobs whose device buffers are
 // ready and sources filled, and the D2H copies of the block records.  finish_rdo() waits for it.
+// Stages A + B are queued on c.stream (behind `after_analysis_of`, the previous chunk's ev_analysis, so that the analyses
+// of successive chunks run back to back); stage C, the filters and the download go to the high-priority c.stream_hi and
+// overlap the next chunk's analysis.
 int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin, bool fetch_rec,
-              std::vector<std::vector<uint16_t>> *rec_out, std::vector<std::vector<uint16_t>> *pre_filter_rec = nullptr) {
+              std::vector<std::vector<uint16_t>> *rec_out, std::vector<std::vector<uint16_t>> *pre_filter_rec = nullptr,
+              cudaEvent_t after_analysis_of = nullptr) {
   std::vector<B200RdoJob> hj(jobs.size());
   std::vector<B200TileRef> tiles;
   for (size_t i = 0; i < jobs.size(); i++) {
@@ -269,22 +279,23 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
   B200TileRef *d_tiles = dev.take<B200TileRef>(tiles.size());
   CU(cudaMemcpyAsync(d_jobs, hj.data(), hj.size() * sizeof(B200RdoJob), cudaMemcpyHostToDevice, c.stream));
   CU(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(B200TileRef), cudaMemcpyHostToDevice, c.stream));
+  if (after_analysis_of) CU(cudaStreamWaitEvent(c.stream, after_analysis_of, 0));
   CU(cudaEventRecord(c.ev[1], c.stream));
   int max_blocks4 = 0;
   for (FrameJob *jp : jobs) max_blocks4 = std::max(max_blocks4, (int)jp->n_mi());
   const int le = b200_rdo_launch(d_jobs, (int)jobs.size(), d_tiles, (int)tiles.size(), max_blocks4, jobs[0]->f.bit_depth > 8,
-                                 c.stream);   // one bit depth per call
+                                 c.stream, c.stream_hi, c.ev_analysis);   // one bit depth per call
   if (le != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("RDO kernel launch failed: ") + cudaGetErrorString((cudaError_t)le));
   g_launches += 8;   // 3 x (SATD + analysis) + partition decision + reconstruction
-  CU(cudaEventRecord(c.ev[2], c.stream));
+  CU(cudaEventRecord(c.ev[2], c.stream_hi));
   if (pre_filter_rec) {   // test seam: reconstruction before the in-loop filters
     pre_filter_rec->clear();
     for (FrameJob *jp : jobs)
       for (int p = 0; p < jp->f.planes; p++) {
         pre_filter_rec->emplace_back(jp->n_px());
-        CU(cudaMemcpyAsync(pre_filter_rec->back().data(), jp->d_rec[p], jp->n_px() * 2, cudaMemcpyDeviceToHost, c.stream));
+        CU(cudaMemcpyAsync(pre_filter_rec->back().data(), jp->d_rec[p], jp->n_px() * 2, cudaMemcpyDeviceToHost, c.stream_hi));
       }
-    CU(cudaStreamSynchronize(c.stream));
+    CU(cudaStreamSynchronize(c.stream_hi));
   }
   {
     int max_edges = 0, max_sb = 0;
@@ -292,19 +303,19 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
       max_edges = std::max(max_edges, (int)(jp->n_mi() * 4 * jp->f.planes));
       max_sb = std::max(max_sb, (int)jp->n_sb());
     }
-    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_edges, max_sb, c.stream);
+    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_edges, max_sb, c.stream_hi);
     if (fe != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("filter kernel launch failed: ") + cudaGetErrorString((cudaError_t)fe));
     g_launches += 3;
   }
   uint64_t d2h = 0;
   for (FrameJob *jp : jobs) {
     FrameJob &j = *jp;
-    CU(cudaMemcpyAsync(j.h_mi, j.d_mi, j.n_mi() * sizeof(B200Mi), cudaMemcpyDeviceToHost, c.stream));
-    CU(cudaMemcpyAsync(j.h_cdef, j.d_cdef, j.n_sb(), cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaMemcpyAsync(j.h_mi, j.d_mi, j.n_mi() * sizeof(B200Mi), cudaMemcpyDeviceToHost, c.stream_hi));
+    CU(cudaMemcpyAsync(j.h_cdef, j.d_cdef, j.n_sb(), cudaMemcpyDeviceToHost, c.stream_hi));
     d2h += j.n_mi() * sizeof(B200Mi) + j.n_sb();
     for (int p = 0; p < j.f.planes; p++) {
-      CU(cudaMemcpyAsync(j.h_eob[p], j.d_eob[p], j.n_mi() * 2, cudaMemcpyDeviceToHost, c.stream));
-      CU(cudaMemcpyAsync(j.h_coef[p], j.d_coef[p], j.n_coef() * 2, cudaMemcpyDeviceToHost, c.stream));
+      CU(cudaMemcpyAsync(j.h_eob[p], j.d_eob[p], j.n_mi() * 2, cudaMemcpyDeviceToHost, c.stream_hi));
+      CU(cudaMemcpyAsync(j.h_coef[p], j.d_coef[p], j.n_coef() * 2, cudaMemcpyDeviceToHost, c.stream_hi));
       d2h += j.n_mi() * 2 + j.n_coef() * 2;
     }
   }
@@ -313,16 +324,17 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     for (FrameJob *jp : jobs)
       for (int p = 0; p < jp->f.planes; p++) {
         rec_out->emplace_back(jp->n_px());
-        CU(cudaMemcpyAsync(rec_out->back().data(), jp->d_rec[p], jp->n_px() * 2, cudaMemcpyDeviceToHost, c.stream));
+        CU(cudaMemcpyAsync(rec_out->back().data(), jp->d_rec[p], jp->n_px() * 2, cudaMemcpyDeviceToHost, c.stream_hi));
       }
   }
-  CU(cudaEventRecord(c.ev[3], c.stream));
+  CU(cudaEventRecord(c.ev[3], c.stream_hi));
   g_d2h += d2h;
   return 0;
 }
 
 // Wait for the device work issued by issue_rdo() on this context and account its CUDA-event times.
 int finish_rdo(Context &c) {
+  CU(cudaStreamSynchronize(c.stream_hi));
   CU(cudaStreamSynchronize(c.stream));
   float ms_rdo = 0, ms_tot = 0;
   cudaEventElapsedTime(&ms_rdo, c.ev[1], c.ev[2]);
@@ -394,11 +406,14 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
   //      upload/convert of chunk k+1 overlaps the RDO of chunk k, symbol packing (CPU threads) of chunk k overlaps
   //      the device work of chunk k+1.
   const size_t n_img = imgs.size();
-  const size_t n_chunks = n_img >= 16 ? 4 : (n_img >= 4 ? 2 : 1);
-  std::unique_ptr<Context> ctx2;
-  if (n_chunks > 1) { if (int e = acquire_context(enc.device, ctx2)) return e; }
-  struct Release2 { std::unique_ptr<Context> &c; ~Release2() { if (c) release_context(c); } } rel2{ctx2};
-  Context *cx[2] = {ctx.get(), n_chunks > 1 ? ctx2.get() : ctx.get()};
+  size_t n_chunks = n_img >= 32 ? 8 : (n_img >= 16 ? 4 : (n_img >= 4 ? 2 : 1));
+  if (const char *ev = getenv("B200AVIF_CHUNKS")) { const long v = atol(ev); if (v >= 1) n_chunks = std::min<size_t>((size_t)v, n_img); }
+  constexpr size_t NC = 3;            // contexts: two chunks in flight on the device + one being packed / refilled
+  std::unique_ptr<Context> ctx_extra[NC - 1];
+  for (size_t k = 1; k < std::min(NC, n_chunks); k++) { if (int e = acquire_context(enc.device, ctx_extra[k - 1])) return e; }
+  struct ReleaseExtra { std::unique_ptr<Context> *c; ~ReleaseExtra() { for (size_t k = 0; k < NC - 1; k++) if (c[k]) release_context(c[k]); } } rel2{ctx_extra};
+  Context *cx[NC];
+  for (size_t k = 0; k < NC; k++) cx[k] = (k == 0 || !ctx_extra[k - 1]) ? ctx.get() : ctx_extra[k - 1].get();
   struct Chunk { size_t a, b; int *h_flags = nullptr; std::vector<FrameJob *> jobs; std::thread packer; bool issued = false; };
   std::vector<Chunk> chunks(n_chunks);
   for (size_t k = 0; k < n_chunks; k++) { chunks[k].a = k * n_img / n_chunks; chunks[k].b = (k + 1) * n_img / n_chunks; }
@@ -486,7 +501,7 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
     ch.issued = true;
     return 0;
   };
-  auto phase2 = [&](Context &c, Chunk &ch) -> int {       // needs the alpha flags: RDO + filters + record D2H (async)
+  auto phase2 = [&](Context &c, Chunk &ch, cudaEvent_t prev_analysis) -> int {       // needs the alpha flags: RDO + filters + record D2H (async)
     CU(cudaStreamSynchronize(c.stream));
     for (size_t i = ch.a; i < ch.b; i++) {
       ImageWork &im = imgs[i];
@@ -496,7 +511,7 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
       if (im.use_alpha) ch.jobs.push_back(&im.alpha);
     }
     if (ch.jobs.empty()) return 0;
-    return issue_rdo(c, ch.jobs, c.dev, c.pin, false, nullptr);
+    return issue_rdo(c, ch.jobs, c.dev, c.pin, false, nullptr, nullptr, prev_analysis);
   };
   auto phase3 = [&](Context &c, Chunk &ch) -> int {       // wait for the device, hand the records to the packer thread
     if (ch.jobs.empty()) return 0;
@@ -504,14 +519,17 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
     ch.packer = std::thread([&ch]() { pack_jobs(ch.jobs); });
     return 0;
   };
+  cudaEvent_t prev_analysis = nullptr;
   for (size_t k = 0; k < n_chunks; k++) {
-    Context &c = *cx[k & 1];
-    if (k >= 2 && chunks[k - 2].packer.joinable()) chunks[k - 2].packer.join();   // its pinned arena is about to be reused
+    Context &c = *cx[k % NC];
+    if (k >= NC && chunks[k - NC].packer.joinable()) chunks[k - NC].packer.join();   // its pinned arena is about to be reused
     if (int e = phase1(c, chunks[k])) return e;
-    if (int e = phase2(c, chunks[k])) return e;           // queue this chunk's device work before waiting for the previous one
-    if (k >= 1) { if (int e = phase3(*cx[(k - 1) & 1], chunks[k - 1])) return e; }
+    if (int e = phase2(c, chunks[k], prev_analysis)) return e;      // queue this chunk's device work before waiting for older ones
+    if (!chunks[k].jobs.empty()) prev_analysis = c.ev_analysis;
+    if (k + 1 >= NC) { const size_t d = k + 1 - NC; if (int e = phase3(*cx[d % NC], chunks[d])) return e; }
   }
-  if (int e = phase3(*cx[(n_chunks - 1) & 1], chunks[n_chunks - 1])) return e;
+  for (size_t d = n_chunks >= NC ? n_chunks - NC + 1 : 0; d < n_chunks; d++)
+    if (int e = phase3(*cx[d % NC], chunks[d])) return e;
   join_all();
   // ---- mux
   const auto t0 = std::chrono::steady_clock::now();

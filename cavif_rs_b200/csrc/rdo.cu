@@ -1034,8 +1034,11 @@ __global__ void __launch_bounds__(kThreads * kReconWarps, 4) b200_recon_kernel(c
 }
 
 #ifndef B200_EMU
+// Stages A + B go to `stream`; stage C goes to `stream_recon` (may be the same stream) after `analysis_done` (an event
+// recorded behind stage B, may be null when both streams are the same).  The caller overlaps the low-parallelism
+// reconstruction chain of one chunk with the analysis of the next by giving stream_recon a higher priority.
 extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200TileRef *d_tiles, int n_tiles, int max_blocks4,
-                               int high_bitdepth, void *stream) {
+                               int high_bitdepth, void *stream, void *stream_recon, void *analysis_done) {
   if (n_tiles <= 0 || n_jobs <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   static bool configured = false;
@@ -1066,8 +1069,13 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
   }
   dim3 gd((max_blocks4 / 16 + 64 + 127) / 128, n_jobs);
   b200_decide_kernel<<<gd, 128, 0, st>>>(d_jobs);
-  if (high_bitdepth) b200_recon_kernel<true><<<n_tiles, kThreads * kReconWarps, 0, st>>>(d_jobs, d_tiles);
-  else b200_recon_kernel<false><<<n_tiles, kThreads * kReconWarps, 0, st>>>(d_jobs, d_tiles);
+  cudaStream_t sr = stream_recon ? (cudaStream_t)stream_recon : st;
+  if (analysis_done) {
+    cudaEventRecord((cudaEvent_t)analysis_done, st);
+    if (sr != st) cudaStreamWaitEvent(sr, (cudaEvent_t)analysis_done, 0);
+  }
+  if (high_bitdepth) b200_recon_kernel<true><<<n_tiles, kThreads * kReconWarps, 0, sr>>>(d_jobs, d_tiles);
+  else b200_recon_kernel<false><<<n_tiles, kThreads * kReconWarps, 0, sr>>>(d_jobs, d_tiles);
   return (int)cudaGetLastError();
 }
 #else

@@ -34,7 +34,7 @@ typedef struct B200TileRef {
 // All RDO stages for all jobs on `stream`: SATD + analysis per level, partition decision, reconstruction chain
 // (one warp per tile).  max_blocks4 = largest mi_rows*mi_cols over the jobs; high_bitdepth: all jobs are 10-bit.
 int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200TileRef *d_tiles, int n_tiles, int max_blocks4,
-                    int high_bitdepth, void *stream);
+                    int high_bitdepth, void *stream, void *stream_recon, void *analysis_done);
 // Deblock (2 launches) + CDEF search (1 launch) for all jobs: grid.y = job.
 int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, void *stream);
 
