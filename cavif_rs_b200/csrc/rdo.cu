@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
   if (gid >= cols * rows * groups) return;
   const int grp = gid / (cols * rows), blk = gid % (cols * rows);     // same group for neighbouring threads
   const int bx = blk % cols, by = blk / cols, x = bx * n, y = by * n;
-  if (lv == 0 && job.dec[1][(by >> 1) * b200_level_cols(f, 1) + (bx >> 1)].all_zero) return;   // pruned by the 8x8 parent
+  if (lv < 2 && b200_pruned_by_parent(f, lv, bx, by, job.dec[lv + 1])) return;   // top-down pruning
   TileCtx t;
   ctx_from_job(job, t);
   tile_of_unit(f, y >> 2, x >> 2, t);
@@ -898,12 +898,12 @@ __global__ void __launch_bounds__(kThreads, LV == 0 ? 24 : (LV == 1 ? 24 : 16)) 
 #pragma unroll 1
   for (int blk = blockIdx.x; blk < total; blk += gridDim.x) {
     const int x = (blk % cols) * n, y = (blk / cols) * n;
-    if (LV == 0 && job.dec[1][((blk / cols) >> 1) * b200_level_cols(f, 1) + ((blk % cols) >> 1)].all_zero) {
-      if (lane_id() == 0) {   // pruned by the 8x8 parent: never split
+    if (LV < 2 && b200_pruned_by_parent(f, lv, blk % cols, blk / cols, job.dec[LV < 2 ? LV + 1 : 2])) {
+      if (lane_id() == 0) {   // top-down pruning: never split down to this block
         B200BlockDec d;
         d.cost = B200_COST_PRUNED; d.y_mode = 0; d.tx_type = 0; d.uv_mode = 0; d.all_zero = 0; d.angle_y = 0; d.angle_uv = 0;
         d.cfl_js = 0; d.cfl_alpha = 0;
-        job.dec[0][blk] = d;
+        job.dec[lv][blk] = d;
       }
       continue;
     }

@@ -70,6 +70,9 @@ typedef struct B200Frame {
   int32_t lambda_satd_q8;                   // pre-ranking: J = satd * 64 + ((lambda_satd_q8 * R_q8) >> 8)
   int32_t y_mode_mask, uv_mode_mask;        // allowed intra modes (bit = mode index); conformance tests force single modes
   int32_t tx_type_mask;                     // allowed luma transform types: bit0 DCT_DCT 1 ADST_DCT 2 DCT_ADST 3 ADST_ADST 4 IDTX
+  // early termination of the partition search: the children of a block are not analysed when its own RD cost is at
+  // most split_gate_bits * lambda ([0]: 8x8 -> 4x4, [1]: 16x16 -> 8x8; 0 = exhaustive search)
+  int32_t split_gate_bits[2];
   // decisions of the in-loop filter stages
   int32_t lf_level[4];                      // y vertical, y horizontal, u, v
   int32_t lf_sharpness;
@@ -119,6 +122,22 @@ typedef struct B200RateTables {
 
 static inline B200_HD int b200_level_cols(const B200Frame *f, int lv) { return f->mi_cols >> lv; }
 static inline B200_HD int b200_level_rows(const B200Frame *f, int lv) { return f->mi_rows >> lv; }
+
+// Top-down pruning of the analysis (same rule in the oracle and in every device kernel): block (bx, by) of level
+// lv (0: 4x4, 1: 8x8) is not analysed when its parent at level lv + 1 was itself pruned, quantised to all-zero in
+// every plane, or is already cheap enough (split_gate_bits).  `parent` = the decision array of level lv + 1.
+static inline B200_HD int b200_pruned_by_parent(const B200Frame *f, int lv, int bx, int by, const B200BlockDec *parent) {
+  if (lv >= 2) return 0;
+  const int pn = 8 << lv;
+  const int pmin8 = f->partition_min < 8 ? f->partition_min : 8;
+  if (pn < pmin8 || pn > f->partition_max) return 0;                  /* the parent level is not analysed */
+  const int pc = b200_level_cols(f, lv + 1), pr = b200_level_rows(f, lv + 1);
+  if ((bx >> 1) >= pc || (by >> 1) >= pr) return 0;                   /* parent sticks out of the frame: forced split */
+  const B200BlockDec *d = parent + (size_t)(by >> 1) * pc + (bx >> 1);
+  if (d->cost >= B200_COST_PRUNED || d->all_zero) return 1;
+  const int gate = f->split_gate_bits[lv];
+  return gate > 0 && d->cost <= (int64_t)gate * f->lambda_q8;
+}
 
 // z-order index (0..255) of the 4x4 unit (r, c) inside its 64x64 superblock, r,c in 0..15.
 static inline B200_HD int b200_spread4(int v) {   // abcd -> 0a0b0c0d

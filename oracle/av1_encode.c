@@ -656,10 +656,10 @@ void orc_encode_frame(const B200Frame *f, const B200RateTables *rt, uint16_t *co
         tile_bounds(&e, tr, tc);
         uint32_t sy[14], suv[14];
         const size_t bi = (size_t)by * b200_level_cols(f, lv) + bx;
-        if (lv == 0 && e.dec[1][(size_t)(by >> 1) * b200_level_cols(f, 1) + (bx >> 1)].all_zero) {
-          memset(&e.dec[0][bi], 0, sizeof(B200BlockDec));
-          e.dec[0][bi].cost = B200_COST_PRUNED;
-          if (satd_out && satd_out[0]) memset(satd_out[0] + bi * 2 * B200_SATD_WORDS, 0, 2 * B200_SATD_WORDS * sizeof(uint32_t));
+        if (lv < 2 && b200_pruned_by_parent(f, lv, bx, by, e.dec[lv + 1])) {
+          memset(&e.dec[lv][bi], 0, sizeof(B200BlockDec));
+          e.dec[lv][bi].cost = B200_COST_PRUNED;
+          if (satd_out && satd_out[lv]) memset(satd_out[lv] + bi * 2 * B200_SATD_WORDS, 0, 2 * B200_SATD_WORDS * sizeof(uint32_t));
           continue;
         }
         orc_analyze_block(&e, bx * n, by * n, n, &e.dec[lv][bi], sy, suv);

@@ -15,6 +15,7 @@ class B200Frame(ctypes.Structure):
         "color_description_present", "color_primaries", "transfer_characteristics", "matrix_coefficients", "full_range",
         "partition_min", "partition_max", "rdo_tx_decision", "fine_directional_intra", "enable_cfl",
         "lambda_q8", "lambda_satd_q8", "y_mode_mask", "uv_mode_mask", "tx_type_mask")] + [
+        ("split_gate_bits", ctypes.c_int32 * 2),
         ("lf_level", ctypes.c_int32 * 4), ("lf_sharpness", ctypes.c_int32),
         ("cdef_damping", ctypes.c_int32), ("cdef_bits", ctypes.c_int32),
         ("cdef_y_strength", ctypes.c_int32 * 8), ("cdef_uv_strength", ctypes.c_int32 * 8),

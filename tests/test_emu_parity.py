@@ -53,13 +53,18 @@ def compare_analysis(ref, out, f):
     (64, 48, 8, 3, 1, {}),
     (40, 72, 10, 1, 2, dict(partition_min=8, rdo_tx_decision=0)),
     (72, 40, 8, 3, 1, dict(partition_min=16, partition_max=16, rdo_tx_decision=0)),   # forced 8x8 splits at the edges
-    (200, 136, 8, 3, 1, dict(partition_min=8)),      # 4 x 3 superblocks: the reconstruction wavefront waits on its neighbours
+    (200, 136, 8, 3, 1, dict(partition_min=8)),
+    (96, 80, 8, 3, 1, dict(split_gates=(44, 96))),       # early termination gates of the fast presets
+      # 4 x 3 superblocks: the reconstruction wavefront waits on its neighbours
 ])
 def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
     E = emu_lib()
     f = H.frame_setup(w, h, depth, planes, 121, tiles)
     for k, v in kw.items():
-        setattr(f, k, v)
+        if k == "split_gates":
+            f.split_gate_bits[0], f.split_gate_bits[1] = v
+        else:
+            setattr(f, k, v)
     rt = H.rate_tables(f.base_q_idx)
     img = H.synth_image(w, h, 3)
     src = H.pad_planes([img[..., c].astype(np.uint16) * (4 if depth == 10 else 1) for c in range(planes)], f)

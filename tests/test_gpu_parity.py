@@ -127,6 +127,8 @@ CASES = [
     (512, 512, 10, 3, 66, 16, {}),
     (256, 200, 8, 3, 199, 2, {}),
     (129, 101, 10, 3, 181, 1, dict(partition_min=16, partition_max=16, rdo_tx_decision=0, enable_cdef=0)),
+    (640, 360, 8, 3, 121, 4, dict(split_gates=(44, 96))),      # early-termination gates of the fast presets
+    (384, 256, 10, 3, 147, 2, dict(split_gates=(44, 96), partition_min=8)),
 ]
 
 
@@ -134,7 +136,10 @@ CASES = [
 def test_rdo_kernel_matches_oracle_and_dav1d(w, h, depth, planes, q, tiles, kw):
     f = H.frame_setup(w, h, depth, planes, q, tiles)
     for k, v in kw.items():
-        setattr(f, k, v)
+        if k == "split_gates":
+            f.split_gate_bits[0], f.split_gate_bits[1] = v
+        else:
+            setattr(f, k, v)
     rt = H.rate_tables(f.base_q_idx)
     img = H.synth_image(w, h, w + h)
     src = H.pad_planes([img[..., c].astype(np.uint16) * (4 if depth == 10 else 1) for c in range(planes)], f)
