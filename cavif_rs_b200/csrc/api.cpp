@@ -409,7 +409,7 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
   //      upload/convert of chunk k+1 overlaps the RDO of chunk k, symbol packing (CPU threads) of chunk k overlaps
   //      the device work of chunk k+1.
   const size_t n_img = imgs.size();
-  size_t n_chunks = n_img >= 32 ? 8 : (n_img >= 16 ? 4 : (n_img >= 4 ? 2 : 1));
+  size_t n_chunks = n_img >= 16 ? 4 : (n_img >= 4 ? 2 : 1);
   if (const char *ev = getenv("B200AVIF_CHUNKS")) { const long v = atol(ev); if (v >= 1) n_chunks = std::min<size_t>((size_t)v, n_img); }
   constexpr size_t NC = 3;            // contexts: two chunks in flight on the device + one being packed / refilled
   std::unique_ptr<Context> ctx_extra[NC - 1];

@@ -156,6 +156,7 @@ struct Cdfs {
   uint16_t coeff_base_eob[5][2][4][4];
   uint16_t coeff_base[5][2][42][5];
   uint16_t coeff_br[5][2][21][5];
+  uint16_t sgrproj_restore[3];
 
   void init(int base_q_idx) {
     const int q = base_q_idx <= 20 ? 0 : base_q_idx <= 60 ? 1 : base_q_idx <= 120 ? 2 : 3;
@@ -180,6 +181,7 @@ struct Cdfs {
     memcpy(coeff_base_eob, av1_default_coeff_base_eob_cdf[q], sizeof(coeff_base_eob));
     memcpy(coeff_base, av1_default_coeff_base_cdf[q], sizeof(coeff_base));
     memcpy(coeff_br, av1_default_coeff_br_cdf[q], sizeof(coeff_br));
+    memcpy(sgrproj_restore, av1_default_sgrproj_restore_cdf, sizeof(sgrproj_restore));
   }
 };
 
@@ -200,6 +202,7 @@ struct TilePacker {
   std::vector<uint8_t> above_level[3], above_dc[3];
   uint8_t left_level[3][16], left_dc[3][16];
   int8_t cdef_written = 0;   // per current 64x64: has cdef_idx been written?
+  int ref_sgr_xqd[3][2];     // RefSgrXqd (AV1 spec 5.11.58): previous unit's weights in this tile, per plane
 
   TilePacker(const B200Frame &fr, const B200Records &r) : f(fr), rec(r) {}
 
@@ -458,6 +461,48 @@ struct TilePacker {
     }
   }
 
+  // ---- loop restoration units (AV1 spec 5.11.57 read_lr / 5.11.58 read_lr_unit), coded at the start of the superblock
+  void write_literal(int v, int bits) { for (int i = bits - 1; i >= 0; i--) ec.literal_bit((v >> i) & 1); }
+  void write_ns(int n, int v) {                       // NS(n) in tile data
+    int w = 0; while ((1 << w) <= n) w++;
+    const int m = (1 << w) - n;
+    if (v < m) write_literal(v, w - 1);
+    else { write_literal((v + m) >> 1, w - 1); write_literal((v + m) & 1, 1); }
+  }
+  void write_subexp(int num_syms, int k, int v) {     // inverse of decode_subexp_bool
+    int i = 0, mk = 0;
+    for (;;) {
+      const int b2 = i ? k + i - 1 : k, a = 1 << b2;
+      if (num_syms <= mk + 3 * a) { write_ns(num_syms - mk, v - mk); return; }
+      const int more = v >= mk + a;
+      ec.literal_bit(more);
+      if (more) { i++; mk += a; } else { write_literal(v - mk, b2); return; }
+    }
+  }
+  static int recenter(int r, int v) { return v > 2 * r ? v : (v >= r ? (v - r) << 1 : ((r - v) << 1) - 1); }
+  void write_signed_subexp_with_ref(int lo, int hi, int k, int ref, int v) {   // value range [lo, hi)
+    const int mx = hi - lo, r = ref - lo, x = v - lo;
+    if ((r << 1) <= mx) write_subexp(mx, k, recenter(r, x));
+    else write_subexp(mx, k, recenter(mx - 1 - r, mx - 1 - x));
+  }
+  void write_lr_units(int r, int c) {
+    const int ur = r >> 4, uc = c >> 4;               // unit size 64 = superblock size: at most one unit per superblock
+    if (ur >= b200_lr_units(f.height) || uc >= b200_lr_units(f.width)) return;
+    for (int p = 0; p < f.planes; p++) {
+      if (!f.lr_type[p] || !rec.lr[p]) continue;
+      const B200LrUnit u = rec.lr[p][ur * b200_lr_units(f.width) + uc];
+      sym(u.use ? 1 : 0, cdf.sgrproj_restore, 2);
+      if (!u.use) continue;
+      write_literal(u.set, 4);
+      const int r0 = av1_sgr_params_tbl[u.set][0], r1 = av1_sgr_params_tbl[u.set][1];
+      int v0 = 0, v1;
+      if (r0) { v0 = u.xqd0; write_signed_subexp_with_ref(-96, 32, 4, ref_sgr_xqd[p][0], v0); }
+      if (r1) { v1 = u.xqd1; write_signed_subexp_with_ref(-32, 96, 4, ref_sgr_xqd[p][1], v1); }
+      else v1 = std::min(std::max(128 - v0, -32), 95);
+      ref_sgr_xqd[p][0] = v0; ref_sgr_xqd[p][1] = v1;
+    }
+  }
+
   void write_sb_tree(int r, int c, int lvl /*4: 64x64 ... 0: 4x4*/) {
     if (r >= f.mi_rows || c >= f.mi_cols) return;
     if (lvl == 0) { write_block(r, c); return; }
@@ -478,6 +523,7 @@ struct TilePacker {
     mi_col_start = f.tile_col_start_sb[tile_col] * 16;
     mi_col_end = std::min(f.tile_col_start_sb[tile_col + 1] * 16, f.mi_cols);
     cdf.init(f.base_q_idx);
+    for (int p = 0; p < 3; p++) { ref_sgr_xqd[p][0] = -32; ref_sgr_xqd[p][1] = 31; }     // Sgrproj_Xqd_Mid
     for (int p = 0; p < 3; p++) {
       above_level[p].assign(f.mi_cols + 32, 0);
       above_dc[p].assign(f.mi_cols + 32, 0);
@@ -487,6 +533,7 @@ struct TilePacker {
       memset(left_dc, 0, sizeof(left_dc));
       for (int c = mi_col_start; c < mi_col_end; c += 16) {
         cdef_written = 0;
+        write_lr_units(r, c);
         write_sb_tree(r, c, 4);
       }
     }
@@ -617,7 +664,10 @@ void write_frame_header(const B200Frame &f, BitWriter &b) {
   }
   // lr_params
   if (f.enable_restoration) {
-    for (int p = 0; p < f.planes; p++) b.put(0, 2);   // RESTORE_NONE for every plane
+    // lr_type: 0 -> RESTORE_NONE, 3 -> RESTORE_SGRPROJ (Remap_Lr_Type); lr_unit_shift = 0: 64x64 units; no lr_uv_shift in 4:4:4
+    int uses_lr = 0;
+    for (int p = 0; p < f.planes; p++) { b.put(f.lr_type[p] ? 3 : 0, 2); uses_lr |= f.lr_type[p] != 0; }
+    if (uses_lr) b.put(0, 1);
   }
   b.put(0, 1);   // tx_mode_select = 0 -> TX_MODE_LARGEST
   b.put(f.reduced_tx_set ? 1 : 0, 1);

@@ -15,6 +15,7 @@ typedef struct B200Records {
   const uint16_t *eob[3];    // per plane [mi_rows * mi_cols], valid at the top-left unit of each transform block
   const int16_t *coef[3];    // per plane [sb_rows * sb_cols * 4096], quantised levels in scan order (b200_coef_offset)
   const int8_t *cdef_idx;    // [sb_rows * sb_cols] or NULL
+  const B200LrUnit *lr[3];   // per plane [b200_lr_units(height) * b200_lr_units(width)]; read only where f->lr_type[plane] != 0
 } B200Records;
 
 // Fill geometry/derived fields of B200Frame (mi/sb sizes, uniform tile layout, quantiser steps, lambda).

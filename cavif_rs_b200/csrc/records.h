@@ -78,8 +78,22 @@ typedef struct B200Frame {
   int32_t lf_sharpness;
   int32_t cdef_damping, cdef_bits;
   int32_t cdef_y_strength[8], cdef_uv_strength[8];   // pri*4 + sec
-  int32_t lr_type[3];                       // 0 none (only value emitted for now)
+  int32_t lr_type[3];                       // per plane: 0 RESTORE_NONE, 1 RESTORE_SGRPROJ (64x64 units, lr_unit_shift 0)
 } B200Frame;
+
+// Loop restoration decision of one 64x64 restoration unit of one plane (self-guided filter, AV1 spec 5.11.58):
+// unit grid = b200_lr_units(height) rows x b200_lr_units(width) columns, row-major.
+typedef struct B200LrUnit {
+  int8_t use;          // use_sgrproj
+  int8_t set;          // lr_sgr_set 0..15
+  int8_t xqd0, xqd1;   // LrSgrXqd: -96..31, -32..95
+} B200LrUnit;
+static inline B200_HD int b200_lr_units(int size) { const int n = (size + 32) >> 6; return n < 1 ? 1 : n; }
+// encoder search: candidate parameter sets and the static cost (1/256 bit) of the use_sgrproj flag (default CDF 16855)
+#define B200_LR_CANDIDATES 4
+#define B200_LR_SETS 2, 6, 11, 14
+#define B200_LR_FLAG_COST0 246
+#define B200_LR_FLAG_COST1 267
 
 // Decision of the open-loop analysis for one block (analysis stage -> partition decision -> reconstruction).
 typedef struct B200BlockDec {

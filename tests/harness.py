@@ -23,13 +23,14 @@ class B200Frame(ctypes.Structure):
 
 class B200Records(ctypes.Structure):
     _fields_ = [("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3),
-                ("cdef_idx", ctypes.c_void_p)]
+                ("cdef_idx", ctypes.c_void_p), ("lr", ctypes.c_void_p * 3)]
 
 RATE_TABLES_BYTES = 2 * (20 * 10 + 3 * 2 + 5 * 5 * 13 + 2 * 13 * 14 + 8 * 7 + 8 + 6 * 16 + 2 * 4 * 13 * 16 + 5 * 13 * 2 +
                          4 * 2 * 12 + 5 * 2 * 9 * 2 + 2 * 3 * 2 + 5 * 2 * 4 * 3 + 5 * 2 * 42 * 4 + 4 * 2 * 21 * 13)
 
 DEC_DTYPE = np.dtype([("cost", "<i8"), ("y_mode", "u1"), ("tx_type", "u1"), ("uv_mode", "u1"), ("all_zero", "u1"),
                       ("angle_y", "u1"), ("angle_uv", "u1"), ("cfl_js", "u1"), ("cfl_alpha", "u1")])
+LR_DTYPE = np.dtype([("use", "i1"), ("set", "i1"), ("xqd0", "i1"), ("xqd1", "i1")])
 MI_DTYPE = np.dtype([("bsize", "u1"), ("y_mode", "u1"), ("uv_mode", "u1"), ("angle", "u1"),
                      ("tx_size", "u1"), ("tx_type", "u1"), ("flags", "u1"), ("cfl", "u1")])
 
@@ -37,6 +38,11 @@ def _run(cmd):
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT)
     if r.returncode != 0:
         raise RuntimeError("build failed: %s\n%s" % (" ".join(cmd), r.stderr[-4000:]))
+
+# libaom av1_sgr_params: (r0, r1, s0, s1) per set
+SGR_PARAMS = [(2, 1, 140, 3236), (2, 1, 112, 2158), (2, 1, 93, 1618), (2, 1, 80, 1438), (2, 1, 70, 1295), (2, 1, 58, 1177),
+              (2, 1, 47, 1079), (2, 1, 37, 996), (2, 1, 30, 925), (2, 1, 25, 863), (0, 1, -1, 2589), (0, 1, -1, 1618),
+              (0, 1, -1, 1177), (0, 1, -1, 925), (2, 0, 56, -1), (2, 0, 22, -1)]
 
 _oracle = None
 def oracle():
@@ -51,6 +57,9 @@ def oracle():
         L.orc_deblock_frame.argtypes = [V, V, V]
         L.orc_cdef_frame.argtypes = [V, V, V, V, V]
         L.orc_cdef_search_frame.argtypes = [V, V, V, V, V, V]
+        L.orc_sgr_region_plane.argtypes = [V, V] + [I] * 11 + [V, V]
+        L.orc_sgr_apply_region.argtypes = [V] + [I] * 11 + [V]
+        L.orc_lr_frame.argtypes = [V, V, V, V, V, V]
         L.orc_convert_image.argtypes = [V, I, Z, Z, Z, I, I, V, V, V, V]
         L.orc_any_alpha.argtypes = [V, Z, Z, Z]
         L.orc_blurred_dirty_alpha.argtypes = [V, Z, Z, Z, V]
@@ -111,6 +120,9 @@ def pad_planes(planes, f):
         out.append(np.ascontiguousarray(a))
     return out
 
+def lr_units(size):
+    return max((size + 32) // 64, 1)
+
 class Records:
     def __init__(self, f):
         n_mi = f.mi_rows * f.mi_cols
@@ -119,6 +131,7 @@ class Records:
         self.eob = [np.zeros(n_mi, np.uint16) for _ in range(3)]
         self.coef = [np.zeros(f.sb_rows * f.sb_cols * 4096, np.int16) for _ in range(3)]
         self.cdef_idx = np.zeros(f.sb_rows * f.sb_cols, np.int8)
+        self.lr = [np.zeros(lr_units(f.height) * lr_units(f.width), LR_DTYPE) for _ in range(3)]
         self.rec = [np.zeros((f.mi_rows * 4, f.mi_cols * 4), np.uint16) for _ in range(3)]
         # open-loop analysis outputs per level (0: 4x4, 1: 8x8, 2: 16x16)
         self.dec = [np.zeros((f.mi_rows >> lv) * (f.mi_cols >> lv), DEC_DTYPE) for lv in range(3)]
@@ -130,6 +143,8 @@ class Records:
             r.eob[p] = self.eob[p].ctypes.data
             r.coef[p] = self.coef[p].ctypes.data
         r.cdef_idx = self.cdef_idx.ctypes.data
+        for p in range(3):
+            r.lr[p] = self.lr[p].ctypes.data
         return r
 
 def ptr3(arrs):
@@ -153,6 +168,11 @@ def oracle_filters(f, rec, src):
     out = [np.zeros_like(r) for r in rec.rec]
     src3 = list(src) + [src[0]] * (3 - len(src))
     L.orc_cdef_search_frame(ctypes.byref(f), ptr3(deb), ptr3(src3), ptr3(out), rec.mi.ctypes.data, rec.cdef_idx.ctypes.data)
+    if any(f.lr_type[p] for p in range(f.planes)):      # loop restoration: search (fills rec.lr) + apply
+        fin = [np.zeros_like(r) for r in rec.rec]
+        L.orc_lr_frame(ctypes.byref(f), ptr3(src3), ptr3(deb), ptr3(out), ptr3(rec.lr), ptr3(fin))
+        rec.cdef_out = out
+        return fin, deb
     return out, deb
 
 
