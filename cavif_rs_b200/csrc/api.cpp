@@ -156,7 +156,9 @@ struct FrameJob {
   B200BlockDec *d_dec[3] = {nullptr, nullptr, nullptr};
   uint32_t *d_satd[3] = {nullptr, nullptr, nullptr};
   int8_t *d_cdef = nullptr;
-  uint16_t *d_fin[3] = {nullptr, nullptr, nullptr};   // only for the test seam
+  uint16_t *d_fin[3] = {nullptr, nullptr, nullptr};   // CDEF output: input of the loop-restoration search (and the test seam)
+  B200LrUnit *d_lr[3] = {nullptr, nullptr, nullptr}, *h_lr[3] = {nullptr, nullptr, nullptr};
+  uint16_t *d_lr_out[3] = {nullptr, nullptr, nullptr};   // restored planes: test seam only
   int8_t *h_cdef = nullptr;
   // pinned host
   B200Mi *h_mi = nullptr;
@@ -169,6 +171,8 @@ struct FrameJob {
   size_t n_coef() const { return (size_t)f.sb_rows * f.sb_cols * B200_SB_COEFS; }
   size_t n_sb() const { return (size_t)f.sb_rows * f.sb_cols; }
   size_t n_blk(int lv) const { return (size_t)(f.mi_rows >> lv) * (f.mi_cols >> lv); }
+  size_t n_lr() const { return (size_t)b200_lr_units(f.width) * b200_lr_units(f.height); }
+  bool uses_lr() const { return f.enable_restoration && (f.lr_type[0] || f.lr_type[1] || f.lr_type[2]); }
 };
 
 size_t job_dev_bytes(const FrameJob &j, bool own_src) {
@@ -181,11 +185,13 @@ size_t job_dev_bytes(const FrameJob &j, bool own_src) {
   b += P * align256(j.n_coef() * 2);
   b += align256(j.n_sb());
   for (int lv = 0; lv < 3; lv++) b += align256(j.n_blk(lv) * sizeof(B200BlockDec)) + align256(j.n_blk(lv) * 2 * B200_SATD_WORDS * 4);
+  if (j.uses_lr()) b += P * (align256(j.n_px() * 2) + align256(j.n_lr() * sizeof(B200LrUnit)));
   return b + 8192;
 }
 size_t job_pin_bytes(const FrameJob &j) {
   const int P = j.f.planes;
-  return align256(j.n_mi() * sizeof(B200Mi)) + P * align256(j.n_mi() * 2) + P * align256(j.n_coef() * 2) + align256(j.n_sb()) + 4096;
+  return align256(j.n_mi() * sizeof(B200Mi)) + P * align256(j.n_mi() * 2) + P * align256(j.n_coef() * 2) + align256(j.n_sb()) +
+         P * align256(j.n_lr() * sizeof(B200LrUnit)) + 4096;
 }
 void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
   const int P = j.f.planes;
@@ -204,6 +210,12 @@ void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
   }
   j.d_cdef = dev.take<int8_t>(j.n_sb());
   j.h_cdef = pin.take<int8_t>(j.n_sb());
+  if (j.uses_lr())
+    for (int p = 0; p < P; p++) {
+      if (!j.d_fin[p]) j.d_fin[p] = dev.take<uint16_t>(j.n_px());
+      j.d_lr[p] = dev.take<B200LrUnit>(j.n_lr());
+      j.h_lr[p] = pin.take<B200LrUnit>(j.n_lr());
+    }
   j.h_mi = pin.take<B200Mi>(j.n_mi());
 }
 
@@ -228,7 +240,8 @@ int configure_frame(B200Frame *f, size_t w, size_t h, int depth, bool mono, int 
   f->split_gate_bits[0] = speed <= 2 ? 0 : 44;
   f->split_gate_bits[1] = speed <= 2 ? 0 : 96;
   if (!tw.cdef) f->enable_cdef = 0;   // ravif: cdef = low_quality && speed <= 9 (av1encoder.rs:590)
-  f->enable_restoration = 0;          // loop restoration (lrf flag, :589) is not implemented: valid stream, LR off
+  f->enable_restoration = tw.lrf ? 1 : 0;     // loop restoration (lrf flag, av1encoder.rs:589): self-guided filter, 64x64 units
+  for (int p = 0; p < 3; p++) f->lr_type[p] = (tw.lrf && p < f->planes) ? 1 : 0;
   f->full_range = full_range;
   f->color_description_present = has_cd ? 1 : 0;
   if (has_cd) { f->color_primaries = 1; f->transfer_characteristics = 13; f->matrix_coefficients = mc; }
@@ -275,6 +288,7 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     for (int lv = 0; lv < 3; lv++) { r.dec[lv] = j.d_dec[lv]; r.satd[lv] = j.d_satd[lv]; }
     r.cdef_idx = j.d_cdef;
     for (int p = 0; p < 3; p++) r.fin[p] = j.d_fin[p < j.f.planes ? p : 0];
+    for (int p = 0; p < 3; p++) { r.lr[p] = p < j.f.planes ? j.d_lr[p] : nullptr; r.lr_out[p] = p < j.f.planes ? j.d_lr_out[p] : nullptr; }
     for (int tr = 0; tr < j.f.tile_rows; tr++)
       for (int tc = 0; tc < j.f.tile_cols; tc++) tiles.push_back(B200TileRef{(int32_t)i, (int16_t)tr, (int16_t)tc});
   }
@@ -306,9 +320,11 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
       max_edges = std::max(max_edges, (int)(jp->n_mi() * 4 * jp->f.planes));
       max_sb = std::max(max_sb, (int)jp->n_sb());
     }
-    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_edges, max_sb, c.stream_hi);
+    int with_lr = 0;
+    for (FrameJob *jp : jobs) with_lr |= jp->uses_lr();
+    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_edges, max_sb, with_lr, c.stream_hi);
     if (fe != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("filter kernel launch failed: ") + cudaGetErrorString((cudaError_t)fe));
-    g_launches += 3;
+    g_launches += 3 + with_lr;
   }
   uint64_t d2h = 0;
   for (FrameJob *jp : jobs) {
@@ -316,6 +332,11 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     CU(cudaMemcpyAsync(j.h_mi, j.d_mi, j.n_mi() * sizeof(B200Mi), cudaMemcpyDeviceToHost, c.stream_hi));
     CU(cudaMemcpyAsync(j.h_cdef, j.d_cdef, j.n_sb(), cudaMemcpyDeviceToHost, c.stream_hi));
     d2h += j.n_mi() * sizeof(B200Mi) + j.n_sb();
+    if (j.uses_lr())
+      for (int p = 0; p < j.f.planes; p++) {
+        CU(cudaMemcpyAsync(j.h_lr[p], j.d_lr[p], j.n_lr() * sizeof(B200LrUnit), cudaMemcpyDeviceToHost, c.stream_hi));
+        d2h += j.n_lr() * sizeof(B200LrUnit);
+      }
     for (int p = 0; p < j.f.planes; p++) {
       CU(cudaMemcpyAsync(j.h_eob[p], j.d_eob[p], j.n_mi() * 2, cudaMemcpyDeviceToHost, c.stream_hi));
       CU(cudaMemcpyAsync(j.h_coef[p], j.d_coef[p], j.n_coef() * 2, cudaMemcpyDeviceToHost, c.stream_hi));
@@ -361,6 +382,7 @@ void pack_jobs(std::vector<FrameJob *> &jobs) {
     memset(&rec, 0, sizeof(rec));
     rec.mi = j.h_mi;
     rec.cdef_idx = j.h_cdef;
+    for (int p = 0; p < j.f.planes; p++) rec.lr[p] = j.h_lr[p];
     for (int p = 0; p < j.f.planes; p++) { rec.eob[p] = j.h_eob[p]; rec.coef[p] = j.h_coef[p]; }
     uint8_t *out = nullptr;
     size_t len = 0;
@@ -803,7 +825,7 @@ int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h,
 // ---- test seam: run the device hot path on caller-provided coded planes and frame description -----
 int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi, uint16_t *const eob[3], int16_t *const coef[3],
                     uint16_t *const rec[3], uint16_t *const deblocked[3], uint16_t *const fin[3], int8_t *cdef_idx,
-                    B200BlockDec *const dec[3], uint32_t *const satd[3]) {
+                    B200BlockDec *const dec[3], uint32_t *const satd[3], B200LrUnit *const lr[3], uint16_t *const lr_out[3]) {
   if (!f || !src || !mi) return fail(B200AVIF_INVALID_ARGUMENT, "null argument");
   if (b200avif_device_count() <= 0) return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
   FrameJob job;
@@ -812,12 +834,13 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
   if (int e = acquire_context(-1, ctx)) return e;
   Context &c = *ctx;
   struct Release { std::unique_ptr<Context> &c; ~Release() { release_context(c); } } rel{ctx};
-  if (c.dev.reserve(job_dev_bytes(job, true) + 3 * align256(job.n_px() * 2) + (1 << 20)) || c.pin.reserve(job_pin_bytes(job) + (1 << 20))) return B200AVIF_ENCODING_ERROR;
+  if (c.dev.reserve(job_dev_bytes(job, true) + 6 * align256(job.n_px() * 2) + (1 << 20)) || c.pin.reserve(job_pin_bytes(job) + (1 << 20))) return B200AVIF_ENCODING_ERROR;
   c.dev.reset(); c.pin.reset();
   CU(cudaEventRecord(c.ev[0], c.stream));
   job_take(job, c.dev, c.pin, true);
   for (int p = 0; p < job.f.planes; p++) {
-    job.d_fin[p] = c.dev.take<uint16_t>(job.n_px());
+    if (!job.d_fin[p]) job.d_fin[p] = c.dev.take<uint16_t>(job.n_px());
+    if (job.uses_lr() && lr_out && lr_out[p]) job.d_lr_out[p] = c.dev.take<uint16_t>(job.n_px());
     CU(cudaMemcpyAsync(job.d_src[p], src[p], job.n_px() * 2, cudaMemcpyHostToDevice, c.stream));
     // test seam only: slots of blocks outside the frame are never written (and never read by the packer);
     // zero them so that whole-buffer comparisons against the oracle are meaningful
@@ -843,6 +866,8 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
     if (rec && rec[p]) memcpy(rec[p], pre[p].data(), job.n_px() * 2);
     if (deblocked && deblocked[p]) memcpy(deblocked[p], deb[p].data(), job.n_px() * 2);
     if (fin && fin[p]) CU(cudaMemcpy(fin[p], job.d_fin[p], job.n_px() * 2, cudaMemcpyDeviceToHost));
+    if (job.uses_lr() && lr && lr[p]) memcpy(lr[p], job.h_lr[p], job.n_lr() * sizeof(B200LrUnit));
+    if (job.d_lr_out[p]) CU(cudaMemcpy(lr_out[p], job.d_lr_out[p], job.n_px() * 2, cudaMemcpyDeviceToHost));
   }
   return 0;
 }

@@ -15,6 +15,10 @@
 #include "records.h"
 #include "rdo.h"
 
+#define AV1_TABLE(type, name, dims) __constant__ const type name dims
+#include "sgr_tables_dev.h"
+#undef AV1_TABLE
+
 namespace {
 
 __device__ __forceinline__ int iabs_d(int v) { return v < 0 ? -v : v; }
@@ -187,7 +191,239 @@ __device__ __forceinline__ int cdef_pixel(const uint16_t *I, int stride, int W, 
     }
   return clip3_d(mn, mx, x + ((8 + sum - (sum < 0)) >> 4));
 }
+// ---- loop restoration: self-guided filter parameter search (oracle/av1_restoration.c orc_lr_search_plane) ----------
+// One CTA (256 threads) per (restoration unit, plane); grid.y = job, grid.z = plane.  The unit is walked stripe by
+// stripe and in bands of 32 rows: a band's samples (CDEF output inside the stripe, deblocked rows outside it, AV1
+// spec 7.17.6) are staged once in shared memory and filtered with every candidate parameter set; the per-set normal
+// equations of the projection are accumulated in shared 64-bit counters, then one thread solves, quantises and scores
+// each set (quadratic form, no second filter pass).  When job.lr_out is set (tests), the winner is applied as well.
+constexpr int kLrBandH = 32, kLrMaxW = 96;
+constexpr int kLrSW = kLrMaxW + 6, kLrSH = kLrBandH + 6;        // staged samples: 3-sample border
+constexpr int kLrAW = kLrMaxW + 2, kLrAH = kLrBandH + 2;        // A / B: 1-entry border
+
+struct LrShared {
+  uint16_t S[kLrSH * kLrSW];
+  uint16_t A[kLrAH * kLrAW];
+  int32_t B[kLrAH * kLrAW];
+  uint16_t F0[kLrBandH * kLrMaxW];
+  unsigned long long acc[B200_LR_CANDIDATES][6];     // H00, H01, H11, C0, C1 (two's complement), S
+  B200LrUnit best;
+};
+
+__device__ __forceinline__ long long lr_round2(long long v, int n) { return n == 0 ? v : ((v + (1ll << (n - 1))) >> n); }
+
+// box sums of radius r around staged sample (sy, sx) -> a2 (A) and B entry
+__device__ __forceinline__ void lr_ab(const uint16_t *S, int sy, int sx, int r, int bd, uint32_t s, uint32_t one_by_n, int n, uint16_t *a_out,
+                                      int32_t *b_out) {
+  uint32_t a = 0, b = 0;
+  for (int dy = -r; dy <= r; dy++)
+    for (int dx = -r; dx <= r; dx++) {
+      const uint32_t v = S[(sy + dy) * kLrSW + sx + dx];
+      a += v * v; b += v;
+    }
+  const uint32_t a_s = (uint32_t)lr_round2(a, 2 * (bd - 8)), d = (uint32_t)lr_round2(b, bd - 8);
+  const long long pp = (long long)a_s * n - (long long)d * d;
+  const unsigned long long p = pp < 0 ? 0ull : (unsigned long long)pp;
+  const unsigned long long z = (p * s + (1u << 19)) >> 20;
+  const uint32_t a2 = dv_x_by_xplus1[z > 255 ? 255 : (int)z];
+  *a_out = (uint16_t)a2;
+  *b_out = (int32_t)lr_round2((long long)(256 - a2) * b * one_by_n, 12);
+}
+
+__device__ __forceinline__ long long lr_round_div(long long a, long long b) { return a >= 0 ? (a + b / 2) / b : -((-a + b / 2) / b); }
+__device__ __forceinline__ int lr_clamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ int lr_subexp_bits(int lo, int hi, int ref, int v) {      // oracle subexp_bits(), k = 4
+  const int mx = hi - lo, r = ref - lo, x = v - lo;
+  int t;
+  if ((r << 1) <= mx) t = x > 2 * r ? x : (x >= r ? (x - r) << 1 : ((r - x) << 1) - 1);
+  else { const int r2 = mx - 1 - r, x2 = mx - 1 - x; t = x2 > 2 * r2 ? x2 : (x2 >= r2 ? (x2 - r2) << 1 : ((r2 - x2) << 1) - 1); }
+  int i = 0, mk = 0, bits = 0;
+  for (;;) {
+    const int b2 = i ? 4 + i - 1 : 4, a = 1 << b2;
+    if (mx <= mk + 3 * a) {
+      const int nsym = mx - mk;
+      int w = 0; while ((1 << w) <= nsym) w++;
+      const int m = (1 << w) - nsym;
+      return bits + ((t - mk) < m ? w - 1 : w);
+    }
+    bits++;
+    if (t >= mk + a) { i++; mk += a; } else return bits + b2;
+  }
+}
 }  // namespace
+
+#ifdef B200_EMU
+static int g_f_plane;
+#endif
+__global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
+  __shared__ LrShared sh;
+  const B200RdoJob &job = jobs[blockIdx.y];
+  const B200Frame *f = &job.frame;
+#ifdef B200_EMU
+  const int plane = g_f_plane;       // the emulator launches one plane at a time
+#else
+  const int plane = blockIdx.z;
+#endif
+  if (plane >= f->planes || !f->lr_type[plane]) return;
+  const int nur = b200_lr_units(f->height), nuc = b200_lr_units(f->width);
+  if ((int)blockIdx.x >= nur * nuc) return;
+  const int ur = blockIdx.x / nuc, uc = blockIdx.x % nuc;
+  const int stride = f->mi_cols * 4, W = f->width, H = f->height, bd = f->bit_depth;
+  const int y0 = max(ur * 64 - 8, 0), y1 = ur == nur - 1 ? H : ur * 64 + 56;
+  const int x0 = uc * 64, x1 = uc == nuc - 1 ? W : uc * 64 + 64, w = x1 - x0;
+  const uint16_t *deb = job.rec[plane], *cdef = job.fin[plane], *src = job.src[plane];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < B200_LR_CANDIDATES * 6; i += 256) sh.acc[i / 6][i % 6] = 0;
+  __syncthreads();
+  const int8_t cand[B200_LR_CANDIDATES] = {B200_LR_SETS};
+  // pass over the unit: phase 0 accumulates the normal equations of every candidate set, phase 1 (tests only) applies
+  // the winner
+  for (int phase = 0; phase < 2; phase++) {
+    if (phase == 1 && !job.lr_out[plane]) break;
+    for (int ys = y0; ys < y1;) {
+      const int stripe = (ys + 8) >> 6, s_start = stripe * 64 - 8, s_end = stripe * 64 + 55;
+      const int ye = min(min(s_end + 1, y1), ys + kLrBandH), bh = ye - ys;
+      // stage the samples (AV1 spec 7.17.6 get_source_sample)
+      for (int i = tid; i < (bh + 6) * (w + 6); i += 256) {
+        const int sy = i / (w + 6), sx = i % (w + 6);
+        int y = ys + sy - 3, x = x0 + sx - 3;
+        x = min(max(x, 0), W - 1); y = min(max(y, 0), H - 1);
+        uint16_t v;
+        if (y < s_start) v = deb[max(y, s_start - 2) * stride + x];
+        else if (y > s_end) v = deb[min(y, s_end + 2) * stride + x];
+        else v = cdef[y * stride + x];
+        sh.S[sy * kLrSW + sx] = v;
+      }
+      __syncthreads();
+      const int ncand = phase == 0 ? B200_LR_CANDIDATES : 1;
+      for (int ci = 0; ci < ncand; ci++) {
+        const int set = phase == 0 ? cand[ci] : sh.best.set;
+        if (phase == 1 && !sh.best.use) {       // restoration off in this unit: the CDEF samples pass through
+          for (int i = tid; i < bh * w; i += 256) {
+            const int py = i / w, px = i % w;
+            job.lr_out[plane][(ys + py) * stride + x0 + px] = sh.S[(py + 3) * kLrSW + px + 3];
+          }
+          continue;
+        }
+        const int r0 = dv_sgr_params[set][0], r1 = dv_sgr_params[set][1];
+        long long h00 = 0, h01 = 0, h11 = 0, c0 = 0, c1 = 0, ss = 0;
+        for (int pass = 0; pass < 2; pass++) {
+          const int r = pass == 0 ? r0 : r1;
+          if (r) {
+            const uint32_t s = (uint32_t)dv_sgr_params[set][2 + pass];
+            const int n = (2 * r + 1) * (2 * r + 1);
+            const uint32_t one_by_n = dv_one_by_x[n - 1];
+            // A / B at rows -1..bh (pass 0: odd rows only), columns -1..w
+            const int rows = pass == 0 ? (bh + 3) / 2 : bh + 2;
+            for (int i = tid; i < rows * (w + 2); i += 256) {
+              const int ai = pass == 0 ? (i / (w + 2)) * 2 : i / (w + 2), aj = i % (w + 2);      // A row index = i + 1, i = -1, 1, 3, ...
+              lr_ab(sh.S, ai + 2, aj + 2, r, bd, s, one_by_n, n, &sh.A[ai * kLrAW + aj], &sh.B[ai * kLrAW + aj]);
+            }
+          }
+          __syncthreads();
+          for (int i = tid; i < bh * w; i += 256) {
+            const int py = i / w, px = i % w;
+            const int u_px = sh.S[(py + 3) * kLrSW + px + 3];
+            int32_t fv = 0;
+            if (r) {
+              long long a = 0, b = 0;
+              if (pass == 0) {
+                if (py & 1) {       // odd row: its own A / B row, weights 6 5 5
+                  const uint16_t *Ar = &sh.A[(py + 1) * kLrAW + px + 1]; const int32_t *Br = &sh.B[(py + 1) * kLrAW + px + 1];
+                  a = 6 * Ar[0] + 5 * (Ar[-1] + Ar[1]); b = 6ll * Br[0] + 5ll * ((long long)Br[-1] + Br[1]);
+                } else {
+                  const uint16_t *Au = &sh.A[py * kLrAW + px + 1], *Ad = &sh.A[(py + 2) * kLrAW + px + 1];
+                  const int32_t *Bu = &sh.B[py * kLrAW + px + 1], *Bd = &sh.B[(py + 2) * kLrAW + px + 1];
+                  a = 6 * (Au[0] + Ad[0]) + 5 * (Au[-1] + Au[1] + Ad[-1] + Ad[1]);
+                  b = 6ll * ((long long)Bu[0] + Bd[0]) + 5ll * ((long long)Bu[-1] + Bu[1] + Bd[-1] + Bd[1]);
+                }
+                fv = (int32_t)lr_round2(a * u_px + b, 8 + ((py & 1) ? 4 : 5) - 4);
+              } else {
+                for (int dy = -1; dy <= 1; dy++)
+                  for (int dx = -1; dx <= 1; dx++) {
+                    const int wt = (dx == 0 || dy == 0) ? 4 : 3;
+                    a += wt * sh.A[(py + 1 + dy) * kLrAW + px + 1 + dx];
+                    b += (long long)wt * sh.B[(py + 1 + dy) * kLrAW + px + 1 + dx];
+                  }
+                fv = (int32_t)lr_round2(a * u_px + b, 8 + 5 - 4);
+              }
+            }
+            if (pass == 0) { sh.F0[py * kLrMaxW + px] = (uint16_t)fv; continue; }
+            const int32_t f0 = sh.F0[py * kLrMaxW + px], f1 = fv;
+            if (phase == 0) {
+              const long long u = (long long)u_px << 4;
+              const long long sv = ((long long)src[(ys + py) * stride + x0 + px] << 4) - u;
+              const long long av = r0 ? f0 - u : 0, bv = r1 ? f1 - u : 0;
+              h00 += av * av; h01 += av * bv; h11 += bv * bv; c0 += av * sv; c1 += bv * sv; ss += sv * sv;
+            } else {
+              const int w0 = sh.best.xqd0, w1 = sh.best.xqd1, w2 = 128 - w0 - w1;
+              const long long u = (long long)u_px << 4;
+              long long v = w1 * u;
+              v += r0 ? (long long)w0 * f0 : w0 * u;
+              v += r1 ? (long long)w2 * f1 : w2 * u;
+              const long long o = lr_round2(v, 11);
+              const int mx = (1 << bd) - 1;
+              job.lr_out[plane][(ys + py) * stride + x0 + px] = (uint16_t)(o < 0 ? 0 : (o > mx ? mx : o));
+            }
+          }
+          __syncthreads();
+        }
+        if (phase == 0) {
+          long long v[6] = {h00, h01, h11, c0, c1, ss};
+#pragma unroll
+          for (int k = 0; k < 6; k++) {
+            for (int m = 16; m > 0; m >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], m);
+            if ((tid & 31) == 0 && v[k]) atomicAdd(&sh.acc[ci][k], (unsigned long long)v[k]);
+          }
+        }
+      }
+      __syncthreads();
+      ys = ye;
+    }
+    if (phase == 0) {
+      __syncthreads();
+      if (tid == 0) {
+        B200LrUnit best = {0, 0, 0, 0};
+        const long long S = (long long)sh.acc[0][5];
+        long long bestJ = ((S >> 8) << 8) + (((long long)f->lambda_q8 * B200_LR_FLAG_COST0) >> 8);
+        const long long npx = (long long)w * (y1 - y0);
+        for (int ci = 0; ci < B200_LR_CANDIDATES; ci++) {
+          const int set = cand[ci];
+          const int r0 = dv_sgr_params[set][0], r1 = dv_sgr_params[set][1];
+          const long long H00 = (long long)sh.acc[ci][0], H01 = (long long)sh.acc[ci][1], H11 = (long long)sh.acc[ci][2];
+          const long long C0 = (long long)sh.acc[ci][3], C1 = (long long)sh.acc[ci][4];
+          const long long h00 = H00 / npx, h01 = H01 / npx, h11 = H11 / npx, c0 = C0 / npx, c1 = C1 / npx;
+          long long xq0 = 0, xq1 = 0;
+          if (!r0) { if (h11 <= 0) continue; xq1 = lr_round_div(c1 * 128, h11); }
+          else if (!r1) { if (h00 <= 0) continue; xq0 = lr_round_div(c0 * 128, h00); }
+          else {
+            const long long det = h00 * h11 - h01 * h01;
+            if (det <= 0) continue;
+            xq0 = lr_round_div((c0 * h11 - c1 * h01) * 128, det);
+            xq1 = lr_round_div((c1 * h00 - c0 * h01) * 128, det);
+          }
+          xq0 = xq0 < -512 ? -512 : (xq0 > 512 ? 512 : xq0);
+          xq1 = xq1 < -512 ? -512 : (xq1 > 512 ? 512 : xq1);
+          int xqd0, xqd1;
+          if (!r0) { xqd0 = 0; xqd1 = lr_clamp(128 - (int)xq1, -32, 95); }
+          else if (!r1) { xqd0 = lr_clamp((int)xq0, -96, 31); xqd1 = lr_clamp(128 - xqd0, -32, 95); }
+          else { xqd0 = lr_clamp((int)xq0, -96, 31); xqd1 = lr_clamp(128 - xqd0 - (int)xq1, -32, 95); }
+          const long long e0 = r0 ? xqd0 : 0, e1 = r1 ? 128 - xqd0 - xqd1 : 0;
+          const long long E = S * 16384 - 256 * (e0 * C0 + e1 * C1) + e0 * e0 * H00 + 2 * e0 * e1 * H01 + e1 * e1 * H11;
+          const long long sse = E <= 0 ? 0 : (E >> 22);
+          int bits = 4;
+          if (r0) bits += lr_subexp_bits(-96, 32, -32, xqd0);
+          if (r1) bits += lr_subexp_bits(-32, 96, 31, xqd1);
+          const long long J = (sse << 8) + (((long long)f->lambda_q8 * (B200_LR_FLAG_COST1 + 256 * bits)) >> 8);
+          if (J < bestJ) { bestJ = J; best.use = 1; best.set = (int8_t)set; best.xqd0 = (int8_t)xqd0; best.xqd1 = (int8_t)xqd1; }
+        }
+        sh.best = best;
+        job.lr[plane][ur * nuc + uc] = best;
+      }
+      __syncthreads();
+    }
+  }
+}
 
 // One CTA (256 threads) per 64x64 superblock; grid.y = job.  Phase 1: direction/variance of the 64 8x8 blocks.
 // Phase 2: squared error of every strength index.  Phase 3: apply the winner into job.fin (if present).
@@ -289,7 +525,7 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
 }
 
 #ifndef B200_EMU
-extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, void *stream) {
+extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, int with_lr, void *stream) {
   if (n_jobs <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 g1((max_edge_threads + 255) / 256, n_jobs);
@@ -297,6 +533,10 @@ extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max
   b200_deblock_kernel<<<g1, 256, 0, st>>>(d_jobs, 1);
   dim3 g2(max_sb, n_jobs);
   b200_cdef_kernel<<<g2, 256, 0, st>>>(d_jobs);
+  if (with_lr) {
+    dim3 g3(max_sb, n_jobs, 3);       // restoration units <= superblocks
+    b200_lr_kernel<<<g3, 256, 0, st>>>(d_jobs);
+  }
   return (int)cudaGetLastError();
 }
 #else
@@ -304,10 +544,13 @@ static const B200RdoJob *g_f_jobs;
 static int g_f_pass;
 static void emu_deblock_entry(void *) { b200_deblock_kernel(g_f_jobs, g_f_pass); }
 static void emu_cdef_entry(void *) { b200_cdef_kernel(g_f_jobs); }
+static void emu_lr_entry(void *) { b200_lr_kernel(g_f_jobs); }
 extern "C" int b200_filters_launch_emu(const B200RdoJob *jobs, int max_edge_threads, int max_sb) {
   g_f_jobs = jobs;
   for (g_f_pass = 0; g_f_pass < 2; g_f_pass++) emu::launch(emu_deblock_entry, nullptr, (unsigned)((max_edge_threads + 255) / 256), 256);
   emu::launch(emu_cdef_entry, nullptr, (unsigned)max_sb, 256);
+  for (g_f_plane = 0; g_f_plane < jobs[0].frame.planes; g_f_plane++)
+    if (jobs[0].frame.lr_type[g_f_plane]) emu::launch(emu_lr_entry, nullptr, (unsigned)max_sb, 256);
   return 0;
 }
 #endif

@@ -23,6 +23,9 @@ typedef struct B200RdoJob {
   // strength index (-1: nothing coded in the superblock); fin (optional, may be NULL) receives the CDEF output.
   int8_t *cdef_idx;       // sb_rows*sb_cols
   uint16_t *fin[3];
+  // loop restoration (frame.lr_type[p] != 0; needs fin): per-unit decisions, and (optional, tests) the restored planes
+  B200LrUnit *lr[3];      // b200_lr_units(height) * b200_lr_units(width) per plane
+  uint16_t *lr_out[3];
 } B200RdoJob;
 
 typedef struct B200TileRef {
@@ -35,8 +38,8 @@ typedef struct B200TileRef {
 // (one warp per tile).  max_blocks4 = largest mi_rows*mi_cols over the jobs; high_bitdepth: all jobs are 10-bit.
 int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200TileRef *d_tiles, int n_tiles, int max_blocks4,
                     int high_bitdepth, void *stream, void *stream_recon, void *analysis_done);
-// Deblock (2 launches) + CDEF search (1 launch) for all jobs: grid.y = job.
-int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, void *stream);
+// Deblock (2 launches) + CDEF search (1 launch) + loop-restoration search (1 launch when with_lr) for all jobs: grid.y = job.
+int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, int with_lr, void *stream);
 
 #ifdef __cplusplus
 }

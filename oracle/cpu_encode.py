@@ -51,7 +51,9 @@ def configure(w, h, depth, planes, quantizer, speed, threads=None):
     f.split_gate_bits[0] = 0 if speed <= 2 else 44
     f.split_gate_bits[1] = 0 if speed <= 2 else 96
     f.enable_cdef = 1 if tw.cdef else 0
-    f.enable_restoration = 0
+    f.enable_restoration = 1 if tw.lrf else 0
+    for p in range(planes):
+        f.lr_type[p] = 1 if tw.lrf else 0
     return f
 
 

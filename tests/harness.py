@@ -88,7 +88,7 @@ def hostlib():
         _host.b200av1_pack_frame.argtypes = [ctypes.POINTER(B200Frame), ctypes.POINTER(B200Records),
                                              ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
         V, I, Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
-        _host.b200av1_rdo_run.argtypes = [V] * 11
+        _host.b200av1_rdo_run.argtypes = [V] * 13
         _host.b200av1_convert_run.argtypes = [V, I, Z, Z, Z, I, I, V, V]
         _host.b200av1_seq_level_idx.argtypes = [V]
         _host.b200avif_mux.argtypes = [V, V, V]

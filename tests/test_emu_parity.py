@@ -11,7 +11,8 @@ class RdoJob(ctypes.Structure):
     _fields_ = [("frame", H.B200Frame), ("rate", ctypes.c_void_p), ("src", ctypes.c_void_p * 3), ("rec", ctypes.c_void_p * 3),
                 ("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3),
                 ("dec", ctypes.c_void_p * 3), ("satd", ctypes.c_void_p * 3),
-                ("cdef_idx", ctypes.c_void_p), ("fin", ctypes.c_void_p * 3)]
+                ("cdef_idx", ctypes.c_void_p), ("fin", ctypes.c_void_p * 3),
+                ("lr", ctypes.c_void_p * 3), ("lr_out", ctypes.c_void_p * 3)]
 
 
 class TileRef(ctypes.Structure):
@@ -55,6 +56,8 @@ def compare_analysis(ref, out, f):
     (72, 40, 8, 3, 1, dict(partition_min=16, partition_max=16, rdo_tx_decision=0)),   # forced 8x8 splits at the edges
     (200, 136, 8, 3, 1, dict(partition_min=8)),
     (96, 80, 8, 3, 1, dict(split_gates=(44, 96))),       # early termination gates of the fast presets
+    (161, 100, 8, 3, 1, dict(lr=1, partition_min=8)),    # loop restoration: odd sizes, merged last unit row, two stripes
+    (95, 70, 10, 1, 1, dict(lr=1, partition_min=16)),    # one 95-wide unit, 10 bit, monochrome
       # 4 x 3 superblocks: the reconstruction wavefront waits on its neighbours
 ])
 def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
@@ -63,6 +66,10 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
     for k, v in kw.items():
         if k == "split_gates":
             f.split_gate_bits[0], f.split_gate_bits[1] = v
+        elif k == "lr":
+            f.enable_restoration = 1
+            for p in range(planes):
+                f.lr_type[p] = 1
         else:
             setattr(f, k, v)
     rt = H.rate_tables(f.base_q_idx)
@@ -86,6 +93,9 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
     for p in range(3):
         job.fin[p] = fin[p].ctypes.data
     job.cdef_idx = out.cdef_idx.ctypes.data
+    lr_out = [np.zeros_like(r) for r in out.rec]
+    for p in range(3):
+        job.lr[p] = out.lr[p].ctypes.data; job.lr_out[p] = lr_out[p].ctypes.data
     E.b200_rdo_launch_emu.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     E.b200_filters_launch_emu.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     E.b200_rdo_launch_emu(ctypes.byref(job), trs, nt)
@@ -94,7 +104,13 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
     # in-loop filter stage: deblock in place, CDEF strength search, CDEF output
     ref_fin, ref_deb = H.oracle_filters(f, ref, src)
     E.b200_filters_launch_emu(ctypes.byref(job), f.mi_rows * f.mi_cols * 4 * planes, f.sb_rows * f.sb_cols)
+    uses_lr = any(f.lr_type[p] for p in range(planes))
+    ref_cdef = ref.cdef_out if uses_lr else ref_fin
     for p in range(planes):
         assert np.array_equal(out.rec[p], ref_deb[p]), "deblocked plane %d" % p
-        assert np.array_equal(fin[p], ref_fin[p]), "CDEF output plane %d" % p
+        assert np.array_equal(fin[p], ref_cdef[p]), "CDEF output plane %d" % p
     assert np.array_equal(out.cdef_idx, ref.cdef_idx), "cdef index"
+    if uses_lr:
+        for p in range(planes):
+            assert np.array_equal(out.lr[p], ref.lr[p]), "restoration units plane %d" % p
+            assert np.array_equal(lr_out[p][:h, :w], ref_fin[p][:h, :w]), "restored plane %d" % p

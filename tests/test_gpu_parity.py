@@ -23,8 +23,10 @@ def device_rdo(f, src):
     out.deblocked = [np.zeros_like(r) for r in out.rec]
     out.final = [np.zeros_like(r) for r in out.rec]
     src3 = list(src) + [src[0]] * (3 - len(src))
+    out.lr_out = [np.zeros_like(r) for r in out.rec]
     rc = L.b200av1_rdo_run(ctypes.byref(f), H.ptr3(src3), out.mi.ctypes.data, H.ptr3(out.eob), H.ptr3(out.coef), H.ptr3(out.rec),
-                           H.ptr3(out.deblocked), H.ptr3(out.final), out.cdef_idx.ctypes.data, H.ptr3(out.dec), H.ptr3(out.satd))
+                           H.ptr3(out.deblocked), H.ptr3(out.final), out.cdef_idx.ctypes.data, H.ptr3(out.dec), H.ptr3(out.satd),
+                           H.ptr3(out.lr), H.ptr3(out.lr_out))
     assert rc == 0, L.b200avif_last_error_message()
     return out
 
@@ -46,6 +48,23 @@ def check_records(ref, out, planes):
         assert np.array_equal(ref.eob[p], out.eob[p]), "eob plane %d" % p
         assert np.array_equal(ref.coef[p], out.coef[p]), "coefficients plane %d" % p
     assert np.array_equal(ref.mi, out.mi), "mode info"
+
+
+def check_filters(f, ref, ref_fin, ref_deb, out, planes, w, h):
+    """in-loop filter stage: deblocked planes, CDEF index + output, restoration units + restored planes.
+    Returns the planes a decoder shows."""
+    uses_lr = any(f.lr_type[p] for p in range(planes))
+    ref_cdef = ref.cdef_out if uses_lr else ref_fin
+    for p in range(planes):
+        assert np.array_equal(out.deblocked[p], ref_deb[p]), "deblocked plane %d" % p
+        assert np.array_equal(out.final[p], ref_cdef[p]), "CDEF output plane %d" % p
+    assert np.array_equal(out.cdef_idx, ref.cdef_idx)
+    if not uses_lr:
+        return out.final
+    for p in range(planes):
+        assert np.array_equal(out.lr[p], ref.lr[p]), "restoration units plane %d" % p
+        assert np.array_equal(out.lr_out[p][:h, :w], ref_fin[p][:h, :w]), "restored plane %d" % p
+    return out.lr_out
 
 
 @pytest.mark.parametrize("depth", [8, 10])
@@ -129,6 +148,10 @@ CASES = [
     (129, 101, 10, 3, 181, 1, dict(partition_min=16, partition_max=16, rdo_tx_decision=0, enable_cdef=0)),
     (640, 360, 8, 3, 121, 4, dict(split_gates=(44, 96))),      # early-termination gates of the fast presets
     (384, 256, 10, 3, 147, 2, dict(split_gates=(44, 96), partition_min=8)),
+    (200, 136, 8, 3, 121, 1, dict(lr=1)),                      # loop restoration: merged last unit row
+    (161, 100, 10, 3, 147, 2, dict(lr=1)),                     # odd sizes, two tiles
+    (95, 95, 8, 1, 100, 1, dict(lr=1)),                        # one unit larger than 64 x 64, monochrome
+    (640, 360, 10, 3, 66, 4, dict(lr=1, split_gates=(44, 96))),
 ]
 
 
@@ -138,6 +161,10 @@ def test_rdo_kernel_matches_oracle_and_dav1d(w, h, depth, planes, q, tiles, kw):
     for k, v in kw.items():
         if k == "split_gates":
             f.split_gate_bits[0], f.split_gate_bits[1] = v
+        elif k == "lr":
+            f.enable_restoration = 1
+            for p in range(planes):
+                f.lr_type[p] = 1
         else:
             setattr(f, k, v)
     rt = H.rate_tables(f.base_q_idx)
@@ -148,14 +175,11 @@ def test_rdo_kernel_matches_oracle_and_dav1d(w, h, depth, planes, q, tiles, kw):
     out = device_rdo(f, src)
     check_analysis(ref, out, f)
     check_records(ref, out, planes)
-    for p in range(planes):
-        assert np.array_equal(out.deblocked[p], ref_deb[p]), "deblocked plane %d" % p
-        assert np.array_equal(out.final[p], ref_fin[p]), "CDEF output plane %d" % p
-    assert np.array_equal(out.cdef_idx, ref.cdef_idx)
+    shown = check_filters(f, ref, ref_fin, ref_deb, out, planes, w, h)
     obu = H.pack(f, out)
     dec, bpc, _ = dav1d.decode(obu)     # independent decoder, all in-loop filters on
     for p in range(planes):
-        assert np.array_equal(dec[p], out.final[p][:h, :w])
+        assert np.array_equal(dec[p], shown[p][:h, :w])
 
 
 def test_rdo_full_hd_frame_parity():
@@ -174,6 +198,4 @@ def test_rdo_full_hd_frame_parity():
     out = device_rdo(f, src)
     check_analysis(ref, out, f)
     check_records(ref, out, 3)
-    for p in range(3):
-        assert np.array_equal(out.final[p], ref_fin[p])
-    assert np.array_equal(out.cdef_idx, ref.cdef_idx)
+    check_filters(f, ref, ref_fin, ref_deb, out, 3, w, h)
