@@ -32,10 +32,10 @@ WORKLOADS = {
 # Algorithmic bytes per pixel of the RDO stage group (SATD + analysis per level, partition decision, reconstruction
 # chain), 16-bit samples:
 #   analysis: 3 source planes read once per level by the SATD kernel and once by the trial kernel (3 levels)  2*3*3*2 = 36
-#             SATD tables written + read: 26 x 4 B per block at 3 levels                     2 * 104 * (1/16 + 1/64 + 1/256) = 17.1
+#             SATD tables written + read: 28 x 4 B per block at 3 levels                     2 * 112 * (1/16 + 1/64 + 1/256) = 18.4
 #             decisions written + read: 16 B per block at 3 levels                            2 * 16 * (1/16 + 1/64 + 1/256) = 2.6
 #   reconstruction: 3 source planes read, 3 reconstructed planes + 3 coefficient planes written, records      6 + 6 + 6 + 0.9 = 18.9
-RDO_BYTES_PER_PX = 36 + 17.1 + 2.6 + 18.9
+RDO_BYTES_PER_PX = 36 + 18.4 + 2.6 + 18.9
 TRAFFIC_BYTES_PER_STEP = None     # filled from profiles/ (ncu dram__bytes_read.sum + dram__bytes_write.sum) when captured
 
 
@@ -278,7 +278,7 @@ def main():
             "config": {"workload": wl["name"], "images_per_gpu": wl["n"], "quality": wl["quality"], "speed": wl["speed"],
                        "depth": wl["depth"], "parallelism": "images sharded one batch per GPU, no data-path collective",
                        "l2": "inputs (%.0f MB/step) larger than L2, no flush needed" % (px_per_step * 4 / 1e6),
-                       "tools": "partitions 4..16 (square), 13 intra modes, 5 transform types, deblock + CDEF (per-SB strength search); LR / CFL / angle deltas not emitted",
+                       "tools": "partitions 4..16 (square, top-down early termination), 13 intra modes + angle deltas + CFL, 5 transform types, deblock + CDEF (per-SB strength search) + loop restoration (sgrproj, per-unit search)",
                        "avif_bytes_per_step": out_bytes // max(args.steps, 1)},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "Mpixels/s", "h2d_bytes_per_step": d2["h2d_bytes"] // args.steps,
