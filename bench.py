@@ -28,6 +28,12 @@ WORKLOADS = {
                   n=64, w=1920, h=1080, quality=80.0, speed=4, depth=8),
     "4k": dict(name="16x3840x2160 RGBA8 opaque, quality 80, speed 4, 10-bit (BASELINE configs[2])",
                n=16, w=3840, h=2160, quality=80.0, speed=4, depth=10),
+    # configs[3]: 256 images over 8 GPUs = 32 per GPU, real alpha (clean-up kernels + alpha frames), depth Auto -> 10-bit
+    "1080p-alpha": dict(name="32x1920x1080 RGBA8 with alpha per GPU, quality 60, speed 6, 10-bit, alpha quality 80 (BASELINE configs[3])",
+                        n=32, w=1920, h=1080, quality=60.0, speed=6, depth=10, alpha=True),
+    # configs[4]: one large RGB image, tile-parallel on one GPU (partition range clamped to 4..16)
+    "8k": dict(name="1x8192x8192 RGB8, quality 90, speed 2, 10-bit (BASELINE configs[4])",
+               n=1, w=8192, h=8192, quality=90.0, speed=2, depth=10, channels=3),
 }
 # Algorithmic bytes per pixel of the RDO stage group (SATD + analysis per level, partition decision, reconstruction
 # chain), 16-bit samples:
@@ -44,7 +50,9 @@ def make_images(wl, seed0=0):
     (distinct content, same statistics) to keep set-up time low."""
     import numpy as np
     import harness as H
-    base = [H.synth_image(wl["w"], wl["h"], seed0 + i) for i in range(min(8, wl["n"]))]
+    base = [H.synth_image(wl["w"], wl["h"], seed0 + i, alpha=bool(wl.get("alpha"))) for i in range(min(8, wl["n"]))]
+    if wl.get("channels", 4) == 3:
+        base = [np.ascontiguousarray(b[..., :3]) for b in base]
     imgs = []
     for i in range(wl["n"]):
         b = base[i % len(base)]
@@ -217,7 +225,9 @@ def main():
     imgs = make_images(wl, seed0=1000 * rank)     # every rank encodes its own batch (images are independent units)
     px_per_step = wl["n"] * wl["w"] * wl["h"]
     enc = (C.Encoder.new().with_quality(wl["quality"]).with_speed(wl["speed"]).with_bit_depth(wl["depth"])
-           .with_alpha_color_mode(C.AlphaColorMode.UnassociatedDirty).with_device(local_rank))
+           .with_alpha_color_mode(C.AlphaColorMode.UnassociatedClean if wl.get("alpha") else C.AlphaColorMode.UnassociatedDirty)
+           .with_device(local_rank))
+    nch = wl.get("channels", 4)
     d_imgs = [torch.from_numpy(a).to(dev) for a in imgs]                       # resident in HBM
     h_imgs = [torch.from_numpy(a).pin_memory() for a in imgs]                  # pinned host buffers for e2e
     h_np = [t.numpy() for t in h_imgs]
@@ -257,8 +267,8 @@ def main():
         delta = {k: s1[k] - s0[k] for k in s0}
         return ms, wall, delta, clocks, out_bytes
 
-    ms, wall, d, clocks, out_bytes = timed(lambda: enc.encode_batch(d_imgs), args.steps, args.warmup, True)
-    ms2, wall2, d2, _, _ = timed(lambda: enc.encode_batch(h_np), args.steps, max(1, args.warmup // 2), False)
+    ms, wall, d, clocks, out_bytes = timed(lambda: enc.encode_batch(d_imgs, nch), args.steps, args.warmup, True)
+    ms2, wall2, d2, _, _ = timed(lambda: enc.encode_batch(h_np, nch), args.steps, max(1, args.warmup // 2), False)
 
     if rank == 0:
         total_px = px_per_step * world * args.steps
@@ -277,7 +287,7 @@ def main():
             "vs_baseline": None, "dtype": "u16", "data": "synthetic",
             "config": {"workload": wl["name"], "images_per_gpu": wl["n"], "quality": wl["quality"], "speed": wl["speed"],
                        "depth": wl["depth"], "parallelism": "images sharded one batch per GPU, no data-path collective",
-                       "l2": "inputs (%.0f MB/step) larger than L2, no flush needed" % (px_per_step * 4 / 1e6),
+                       "l2": "inputs (%.0f MB/step) larger than L2, no flush needed" % (px_per_step * nch / 1e6),
                        "tools": "partitions 4..16 (square, top-down early termination), 13 intra modes + angle deltas + CFL, 5 transform types, deblock + CDEF (per-SB strength search) + loop restoration (sgrproj, per-unit search)",
                        "avif_bytes_per_step": out_bytes // max(args.steps, 1)},
             "clocks": clocks,

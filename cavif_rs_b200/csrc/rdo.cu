@@ -761,18 +761,52 @@ __device__ __noinline__ void reconstruct_block(const TileCtx &t, Shared &sh, int
 
 // ---- stage A.1: SATD of the 13 intra modes for every block of level lv, predicted from SOURCE neighbours.
 // One thread per (block, plane group): group 0 = luma, group 1 = U + V.  out: [block][2][13] uint32.
+// One item = (block, plane group) of level lv.  A CTA owns kSatdItems consecutive items: it first compacts the items
+// that survive the top-down pruning into shared memory, then its 128 threads walk the compacted list, so warps stay
+// full even when most of a level is pruned.
+constexpr int kSatdItems = 512;
+__device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid, int *sh_d);
+
 __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, int lv) {
+  __shared__ int sh_d[128 * 17];     // per-thread 16 residuals (+1 pad: conflict-free), written by a rolled loop
+  __shared__ uint16_t s_list[kSatdItems];
+  __shared__ int s_n;
   const B200RdoJob &job = jobs[blockIdx.y];
   const B200Frame *f = &job.frame;
-  const int n = 4 << lv, lg = 2 + lv;
+  const int n = 4 << lv;
   if (n < min(f->partition_min, 8) || n > f->partition_max) return;   // 8x8 always: forced splits at the frame edge
   const int cols = b200_level_cols(f, lv), rows = b200_level_rows(f, lv);
-  const int groups = f->planes > 1 ? 2 : 1;
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= cols * rows * groups) return;
+  const int groups = f->planes > 1 ? 2 : 1, total = cols * rows * groups;
+  const int base = blockIdx.x * kSatdItems;
+  if (base >= total) return;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+#pragma unroll 1
+  for (int k = 0; k < kSatdItems / 128; k++) {
+    const int it = k * 128 + threadIdx.x, gid = base + it;
+    bool active = gid < total;
+    if (active && lv < 2) {
+      const int blk = gid % (cols * rows);
+      active = !b200_pruned_by_parent(f, lv, blk % cols, blk / cols, job.dec[lv + 1]);   // top-down pruning
+    }
+    const unsigned m = __ballot_sync(FULL, active);
+    int off = 0;
+    if (lane_id() == 0 && m) off = atomicAdd(&s_n, __popc(m));
+    off = __shfl_sync(FULL, off, 0);
+    if (active) s_list[off + __popc(m & ((1u << lane_id()) - 1))] = (uint16_t)it;
+  }
+  __syncthreads();
+  const int cnt = s_n;
+#pragma unroll 1
+  for (int i = threadIdx.x; i < cnt; i += 128) satd_item(job, lv, base + s_list[i], sh_d);
+}
+
+__device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid, int *sh_d) {
+  const B200Frame *f = &job.frame;
+  const int n = 4 << lv, lg = 2 + lv;
+  const int cols = b200_level_cols(f, lv), rows = b200_level_rows(f, lv);
   const int grp = gid / (cols * rows), blk = gid % (cols * rows);     // same group for neighbouring threads
   const int bx = blk % cols, by = blk / cols, x = bx * n, y = by * n;
-  if (lv < 2 && b200_pruned_by_parent(f, lv, bx, by, job.dec[lv + 1])) return;   // top-down pruning
   TileCtx t;
   ctx_from_job(job, t);
   tile_of_unit(f, y >> 2, x >> 2, t);
@@ -784,7 +818,6 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
   const int have_ar = ha && b200_unit_before(mi_r - 1, mi_c + n4, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
   const int have_bl = hl && b200_unit_before(mi_r + n4, mi_c - 1, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
   const int mask = grp == 0 ? f->y_mode_mask : f->uv_mode_mask;
-  __shared__ int sh_d[128 * 17];     // per-thread 16 residuals (+1 pad: conflict-free), written by a rolled loop
   // acc[0..12]: SATD of the 13 nominal modes; acc[13..18]: the refined directional mode at deltas -3,-2,-1,1,2,3.
   // Both passes run through ONE rolled copy of the edge / predictor / Hadamard code (instruction-cache footprint).
   uint32_t acc[19];
@@ -1052,7 +1085,7 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
   }
   for (int lv = 2; lv >= 0; lv--) {   // large to small: 4x4 analysis is pruned by its 8x8 parent
     const int nblk = max_blocks4 >> (2 * lv);
-    dim3 gs((nblk * 2 + 127) / 128, n_jobs);
+    dim3 gs((nblk * 2 + kSatdItems - 1) / kSatdItems, n_jobs);
     b200_satd_kernel<<<gs, 128, 0, st>>>(d_jobs, lv);
     // enough single-warp CTAs to fill the machine several times over, grid-stride inside
     const int per_job = min(nblk, max(1, (148 * 16 * 4) / n_jobs));
@@ -1098,7 +1131,7 @@ extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *ti
   for (g_emu_lv = 2; g_emu_lv >= 0; g_emu_lv--) {
     const int nblk = (f->mi_rows >> g_emu_lv) * (f->mi_cols >> g_emu_lv);
     if (nblk == 0) continue;
-    emu::launch(emu_satd, nullptr, (unsigned)((nblk * 2 + 127) / 128), 128);
+    emu::launch(emu_satd, nullptr, (unsigned)((nblk * 2 + kSatdItems - 1) / kSatdItems), 128);
     emu::launch(emu_analyze, nullptr, (unsigned)std::min(nblk, 7), kThreads);
   }
   emu::launch(emu_decide, nullptr, (unsigned)((nblk4 / 16 + 64 + 127) / 128), 128);
