@@ -376,6 +376,11 @@ int run_rdo_and_fetch(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Are
 
 void pack_jobs(std::vector<FrameJob *> &jobs) {
   const auto t0 = std::chrono::steady_clock::now();
+  {   // few frames (one large image): spread each frame's tiles over the idle host threads
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    b200av1_pack_set_tile_threads(jobs.size() * 2 <= hw ? (int)(hw / std::max<size_t>(jobs.size(), 1)) : 1);
+  }
   parallel_for(jobs.size(), [&](size_t i) {
     FrameJob &j = *jobs[i];
     B200Records rec;

@@ -13,6 +13,8 @@
 #include <vector>
 #include <algorithm>
 
+#include <atomic>
+#include <thread>
 #include "av1_tables.h"
 #include "av1_tables_extra.h"
 
@@ -675,6 +677,10 @@ void write_frame_header(const B200Frame &f, BitWriter &b) {
 
 }  // namespace
 
+static std::atomic<int> g_tile_threads{1};
+// host threads b200av1_pack_frame may use for the tiles of ONE frame (default 1)
+extern "C" void b200av1_pack_set_tile_threads(int n) { g_tile_threads.store(n < 1 ? 1 : n); }
+
 extern "C" int b200av1_seq_level_idx(const B200Frame *f) { return level_for(*f); }
 
 extern "C" int b200av1_pack_frame(const B200Frame *fp, const B200Records *rec, uint8_t **out, size_t *out_len) {
@@ -700,11 +706,24 @@ extern "C" int b200av1_pack_frame(const B200Frame *fp, const B200Records *rec, u
       payload.push_back(0);   // tile_start_and_end_present_flag = 0 + byte alignment
     }
     std::vector<std::vector<uint8_t>> tiles(ntiles);
-    for (int tr = 0; tr < f.tile_rows; tr++)
-      for (int tc = 0; tc < f.tile_cols; tc++) {
-        TilePacker tp(f, *rec);
-        tiles[tr * f.tile_cols + tc] = tp.run(tr, tc);
+    // tiles are independent entropy-coding contexts: pack them on g_tile_threads host threads (one large image) or
+    // serially (batches, where the caller already runs one packer per frame)
+    {
+      const int nthreads = std::min(ntiles, std::max(1, g_tile_threads.load()));
+      std::atomic<int> next{0};
+      auto work = [&]() {
+        for (int t; (t = next.fetch_add(1)) < ntiles;) {
+          TilePacker tp(f, *rec);
+          tiles[t] = tp.run(t / f.tile_cols, t % f.tile_cols);
+        }
+      };
+      if (nthreads <= 1) work();
+      else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nthreads; k++) th.emplace_back(work);
+        for (auto &x : th) x.join();
       }
+    }
     for (int t = 0; t < ntiles; t++) {
       if (t != ntiles - 1) {
         const uint32_t sz = (uint32_t)tiles[t].size() - 1;

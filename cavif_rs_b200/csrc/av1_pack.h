@@ -27,6 +27,8 @@ int b200av1_frame_setup(B200Frame *f, int width, int height, int bit_depth, int 
 void b200av1_build_rate_tables(int base_q_idx, B200RateTables *t);
 
 // seq_level_idx_0 written into the sequence header (needed by the av1C box).
+// Host threads b200av1_pack_frame may use for the tiles of one frame (default 1; batches already pack one frame per thread).
+void b200av1_pack_set_tile_threads(int n);
 int b200av1_seq_level_idx(const B200Frame *f);
 
 // Pack one frame.  *out is malloc()ed; caller frees with free().  Returns 0 on success.

@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #endif
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "records.h"
 #include "rdo.h"
@@ -547,9 +548,14 @@ __device__ __forceinline__ void ctx_from_job(const B200RdoJob &job, TileCtx &t) 
 // ---- stage A: analysis of one block by one warp (oracle orc_analyze_block, minus the SATD table) ---------------
 // LG is a template parameter so that each per-level kernel contains only ITS transform size (instruction-cache
 // footprint: ~30 KB for 4x4, the level that dominates the block count).
-template <int LG, bool HBD>
+// SYNC: the warps of the CTA run their blocks in lock-step - a CTA barrier in front of every trial batch, with fixed trip
+// counts - so that they fetch the same instructions at the same time: the per-block code (~60 KB at 16x16) does not
+// fit the instruction cache and `stall_no_instruction` was the top stall of the free-running kernel (profiles/).
+// `out` == nullptr: a padding warp that repeats a valid block only to take part in the barriers.
+template <int LG, bool HBD, bool SYNC>
 __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int x, int y, const uint32_t *satd, B200BlockDec *out) {
   constexpr int lg = LG, n = 1 << LG, N2 = n * n, G = 32 >> LG;
+  if (SYNC) __syncthreads();
   const B200Frame *f = t.f;
   const B200RateTables *rt = t.rt;
   const int lane = lane_id(), g = lane >> lg;
@@ -590,7 +596,8 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
   int bestC = 1 << 20, bestEob = 0;
   bool skip_rest = false;      // every first-type trial quantised to all-zero: the other transform types are not tried
 #pragma unroll 1
-  for (int b = 0; b * G < 10 && !skip_rest; b++) {
+  for (int b = 0; b * G < 10 && (SYNC || !skip_rest); b++) {
+    if (SYNC) { __syncthreads(); if (skip_rest) continue; }
     const int ci = b * G + g;
     const int ti = ci >> 1, k = ci & 1;
     const int m = k == 0 ? m0 : m1;
@@ -637,7 +644,8 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
     const bool cfl_ok = al_u != 0 || al_v != 0;
     const int NC = cfl_ok ? 6 : 4;            // candidate = (k = ci >> 1: rank 0, rank 1, CFL; plane = 1 + (ci & 1))
 #pragma unroll 1
-    for (int b = 0; b * G < NC; b++) {
+    for (int b = 0; b * G < (SYNC ? 6 : NC); b++) {
+      if (SYNC) { __syncthreads(); if (b * G >= NC) continue; }
       const int ci = b * G + g;
       const int k = ci >> 1, p = 1 + (ci & 1);
       const int m = k == 0 ? u0 : (k == 1 ? u1 : UV_CFL_PRED);
@@ -675,7 +683,7 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
     }
     total += bestCj;
   }
-  if (lane == 0) {
+  if (lane == 0 && out) {
     const int all_zero = bestEob == 0 && (planes == 1 || (eobU == 0 && eobV == 0));
     total += ((long long)f->lambda_q8 * rt->skip[0][all_zero]) >> 8;
     B200BlockDec d;
@@ -767,7 +775,7 @@ __device__ __noinline__ void reconstruct_block(const TileCtx &t, Shared &sh, int
 constexpr int kSatdItems = 512;
 __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid, int *sh_d);
 
-__global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, int lv) {
+__global__ void __launch_bounds__(128, 8) b200_satd_kernel(const B200RdoJob *jobs, int lv, int items /* per CTA: 128 .. kSatdItems */) {
   __shared__ int sh_d[128 * 17];     // per-thread 16 residuals (+1 pad: conflict-free), written by a rolled loop
   __shared__ uint16_t s_list[kSatdItems];
   __shared__ int s_n;
@@ -777,12 +785,12 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
   if (n < min(f->partition_min, 8) || n > f->partition_max) return;   // 8x8 always: forced splits at the frame edge
   const int cols = b200_level_cols(f, lv), rows = b200_level_rows(f, lv);
   const int groups = f->planes > 1 ? 2 : 1, total = cols * rows * groups;
-  const int base = blockIdx.x * kSatdItems;
+  const int base = blockIdx.x * items;
   if (base >= total) return;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
 #pragma unroll 1
-  for (int k = 0; k < kSatdItems / 128; k++) {
+  for (int k = 0; k < items / 128; k++) {
     const int it = k * 128 + threadIdx.x, gid = base + it;
     bool active = gid < total;
     if (active && lv < 2) {
@@ -918,9 +926,13 @@ __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid
 }
 
 // ---- stage A.2: full trials.  One single-warp CTA loops over blocks of level lv (grid-stride), grid.y = job.
-template <int LV, bool HBD>
-__global__ void __launch_bounds__(kThreads, LV == 0 ? 24 : (LV == 1 ? 24 : 16)) b200_analyze_kernel(const B200RdoJob *jobs) {
-  __shared__ Shared sh;
+// W warps per CTA.  W == 1: free-running single-warp CTAs (grid-stride over the blocks).  W > 1 (the never-pruned top
+// level): the W warps of a CTA analyse W different blocks in lock-step (analyze_block<.., SYNC>).
+constexpr int kAnalyzeWarpsTop = 4;
+template <int LV, bool HBD, int W>
+__global__ void __launch_bounds__(kThreads * W, (LV == 2 ? 16 : 24) / W) b200_analyze_kernel(const B200RdoJob *jobs) {
+  __shared__ Shared shs[W];
+  Shared &sh = shs[threadIdx.x >> 5];
   const B200RdoJob &job = jobs[blockIdx.y];
   const B200Frame *f = &job.frame;
   constexpr int lv = LV, n = 4 << LV;
@@ -928,6 +940,18 @@ __global__ void __launch_bounds__(kThreads, LV == 0 ? 24 : (LV == 1 ? 24 : 16)) 
   TileCtx t;
   ctx_from_job(job, t);
   const int cols = b200_level_cols(f, lv), total = cols * b200_level_rows(f, lv);
+  if (W > 1) {
+    const int per_iter = gridDim.x * W, iters = (total + per_iter - 1) / per_iter;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+      const int want = (it * gridDim.x + blockIdx.x) * W + (threadIdx.x >> 5);
+      const int blk = want < total ? want : total - 1;             // padding warps repeat the last block, output discarded
+      const int x = (blk % cols) * n, y = (blk / cols) * n;
+      tile_of_unit(f, y >> 2, x >> 2, t);
+      analyze_block<2 + LV, HBD, true>(t, sh, x, y, job.satd[lv] + (size_t)blk * 2 * B200_SATD_WORDS, want < total ? job.dec[lv] + blk : nullptr);
+    }
+    return;
+  }
 #pragma unroll 1
   for (int blk = blockIdx.x; blk < total; blk += gridDim.x) {
     const int x = (blk % cols) * n, y = (blk / cols) * n;
@@ -941,7 +965,7 @@ __global__ void __launch_bounds__(kThreads, LV == 0 ? 24 : (LV == 1 ? 24 : 16)) 
       continue;
     }
     tile_of_unit(f, y >> 2, x >> 2, t);
-    analyze_block<2 + LV, HBD>(t, sh, x, y, job.satd[lv] + (size_t)blk * 2 * B200_SATD_WORDS, job.dec[lv] + blk);
+    analyze_block<2 + LV, HBD, false>(t, sh, x, y, job.satd[lv] + (size_t)blk * 2 * B200_SATD_WORDS, job.dec[lv] + blk);
   }
 }
 
@@ -1077,27 +1101,35 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
   static bool configured = false;
   if (!configured) {
 #define B200_CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
-    B200_CARVE((b200_analyze_kernel<0, false>)); B200_CARVE((b200_analyze_kernel<1, false>)); B200_CARVE((b200_analyze_kernel<2, false>));
-    B200_CARVE((b200_analyze_kernel<0, true>)); B200_CARVE((b200_analyze_kernel<1, true>)); B200_CARVE((b200_analyze_kernel<2, true>));
+    B200_CARVE((b200_analyze_kernel<0, false, 1>)); B200_CARVE((b200_analyze_kernel<1, false, 1>)); B200_CARVE((b200_analyze_kernel<2, false, 1>));
+    B200_CARVE((b200_analyze_kernel<0, true, 1>)); B200_CARVE((b200_analyze_kernel<1, true, 1>)); B200_CARVE((b200_analyze_kernel<2, true, 1>));
+    B200_CARVE((b200_analyze_kernel<2, false, kAnalyzeWarpsTop>)); B200_CARVE((b200_analyze_kernel<2, true, kAnalyzeWarpsTop>));
     cudaFuncSetAttribute(b200_recon_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(b200_recon_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   for (int lv = 2; lv >= 0; lv--) {   // large to small: 4x4 analysis is pruned by its 8x8 parent
     const int nblk = max_blocks4 >> (2 * lv);
-    dim3 gs((nblk * 2 + kSatdItems - 1) / kSatdItems, n_jobs);
-    b200_satd_kernel<<<gs, 128, 0, st>>>(d_jobs, lv);
-    // enough single-warp CTAs to fill the machine several times over, grid-stride inside
+    // the top level is never pruned: one item per thread; lower levels are mostly pruned: compact 512 items per CTA
+    const int items = lv == 2 ? 128 : kSatdItems;
+    dim3 gs((nblk * 2 + items - 1) / items, n_jobs);
+    b200_satd_kernel<<<gs, 128, 0, st>>>(d_jobs, lv, items);
+    // enough warps to fill the machine several times over, grid-stride inside
     const int per_job = min(nblk, max(1, (148 * 16 * 4) / n_jobs));
     dim3 ga(per_job, n_jobs);
-    if (high_bitdepth) {
-      if (lv == 0) b200_analyze_kernel<0, true><<<ga, kThreads, 0, st>>>(d_jobs);
-      else if (lv == 1) b200_analyze_kernel<1, true><<<ga, kThreads, 0, st>>>(d_jobs);
-      else b200_analyze_kernel<2, true><<<ga, kThreads, 0, st>>>(d_jobs);
+    static const int top_warps = getenv("B200AVIF_TOP_WARPS") ? atoi(getenv("B200AVIF_TOP_WARPS")) : kAnalyzeWarpsTop;
+    if (lv == 2 && top_warps > 1) {
+      dim3 gt((per_job + kAnalyzeWarpsTop - 1) / kAnalyzeWarpsTop, n_jobs);
+      if (high_bitdepth) b200_analyze_kernel<2, true, kAnalyzeWarpsTop><<<gt, kThreads * kAnalyzeWarpsTop, 0, st>>>(d_jobs);
+      else b200_analyze_kernel<2, false, kAnalyzeWarpsTop><<<gt, kThreads * kAnalyzeWarpsTop, 0, st>>>(d_jobs);
+    } else if (high_bitdepth) {
+      if (lv == 0) b200_analyze_kernel<0, true, 1><<<ga, kThreads, 0, st>>>(d_jobs);
+      else if (lv == 1) b200_analyze_kernel<1, true, 1><<<ga, kThreads, 0, st>>>(d_jobs);
+      else b200_analyze_kernel<2, true, 1><<<ga, kThreads, 0, st>>>(d_jobs);
     } else {
-      if (lv == 0) b200_analyze_kernel<0, false><<<ga, kThreads, 0, st>>>(d_jobs);
-      else if (lv == 1) b200_analyze_kernel<1, false><<<ga, kThreads, 0, st>>>(d_jobs);
-      else b200_analyze_kernel<2, false><<<ga, kThreads, 0, st>>>(d_jobs);
+      if (lv == 0) b200_analyze_kernel<0, false, 1><<<ga, kThreads, 0, st>>>(d_jobs);
+      else if (lv == 1) b200_analyze_kernel<1, false, 1><<<ga, kThreads, 0, st>>>(d_jobs);
+      else b200_analyze_kernel<2, false, 1><<<ga, kThreads, 0, st>>>(d_jobs);
     }
   }
   dim3 gd((max_blocks4 / 16 + 64 + 127) / 128, n_jobs);
@@ -1115,12 +1147,12 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
 static const B200RdoJob *g_emu_jobs;
 static const B200TileRef *g_emu_tiles;
 static int g_emu_lv;
-static void emu_satd(void *) { b200_satd_kernel(g_emu_jobs, g_emu_lv); }
+static void emu_satd(void *) { b200_satd_kernel(g_emu_jobs, g_emu_lv, g_emu_lv == 2 ? 128 : kSatdItems); }
 static void emu_analyze(void *) {
   const bool hbd = g_emu_jobs[0].frame.bit_depth > 8;
-  if (g_emu_lv == 0) { if (hbd) b200_analyze_kernel<0, true>(g_emu_jobs); else b200_analyze_kernel<0, false>(g_emu_jobs); }
-  else if (g_emu_lv == 1) { if (hbd) b200_analyze_kernel<1, true>(g_emu_jobs); else b200_analyze_kernel<1, false>(g_emu_jobs); }
-  else { if (hbd) b200_analyze_kernel<2, true>(g_emu_jobs); else b200_analyze_kernel<2, false>(g_emu_jobs); }
+  if (g_emu_lv == 0) { if (hbd) b200_analyze_kernel<0, true, 1>(g_emu_jobs); else b200_analyze_kernel<0, false, 1>(g_emu_jobs); }
+  else if (g_emu_lv == 1) { if (hbd) b200_analyze_kernel<1, true, 1>(g_emu_jobs); else b200_analyze_kernel<1, false, 1>(g_emu_jobs); }
+  else { if (hbd) b200_analyze_kernel<2, true, kAnalyzeWarpsTop>(g_emu_jobs); else b200_analyze_kernel<2, false, kAnalyzeWarpsTop>(g_emu_jobs); }
 }
 static void emu_decide(void *) { b200_decide_kernel(g_emu_jobs); }
 static void emu_recon(void *) { if (g_emu_jobs[0].frame.bit_depth > 8) b200_recon_kernel<true>(g_emu_jobs, g_emu_tiles); else b200_recon_kernel<false>(g_emu_jobs, g_emu_tiles); }
@@ -1131,8 +1163,8 @@ extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *ti
   for (g_emu_lv = 2; g_emu_lv >= 0; g_emu_lv--) {
     const int nblk = (f->mi_rows >> g_emu_lv) * (f->mi_cols >> g_emu_lv);
     if (nblk == 0) continue;
-    emu::launch(emu_satd, nullptr, (unsigned)((nblk * 2 + kSatdItems - 1) / kSatdItems), 128);
-    emu::launch(emu_analyze, nullptr, (unsigned)std::min(nblk, 7), kThreads);
+    emu::launch(emu_satd, nullptr, (unsigned)((nblk * 2 + (g_emu_lv == 2 ? 128 : kSatdItems) - 1) / (g_emu_lv == 2 ? 128 : kSatdItems)), 128);
+    emu::launch(emu_analyze, nullptr, (unsigned)std::min(nblk, g_emu_lv == 2 ? 3 : 7), g_emu_lv == 2 ? kThreads * kAnalyzeWarpsTop : kThreads);
   }
   emu::launch(emu_decide, nullptr, (unsigned)((nblk4 / 16 + 64 + 127) / 128), 128);
   emu::launch(emu_recon, nullptr, (unsigned)n_tiles, kThreads * kReconWarps);
