@@ -193,11 +193,11 @@ __device__ __forceinline__ int cdef_pixel(const uint16_t *I, int stride, int W, 
 }
 // ---- loop restoration: self-guided filter parameter search (oracle/av1_restoration.c orc_lr_search_plane) ----------
 // One CTA (256 threads) per (restoration unit, plane); grid.y = job, grid.z = plane.  The unit is walked stripe by
-// stripe and in bands of 32 rows: a band's samples (CDEF output inside the stripe, deblocked rows outside it, AV1
+// stripe and in bands of 16 rows: a band's samples (CDEF output inside the stripe, deblocked rows outside it, AV1
 // spec 7.17.6) are staged once in shared memory and filtered with every candidate parameter set; the per-set normal
 // equations of the projection are accumulated in shared 64-bit counters, then one thread solves, quantises and scores
 // each set (quadratic form, no second filter pass).  When job.lr_out is set (tests), the winner is applied as well.
-constexpr int kLrBandH = 32, kLrMaxW = 96;
+constexpr int kLrBandH = 16, kLrMaxW = 96;
 constexpr int kLrSW = kLrMaxW + 6, kLrSH = kLrBandH + 6;        // staged samples: 3-sample border
 constexpr int kLrAW = kLrMaxW + 2, kLrAH = kLrBandH + 2;        // A / B: 1-entry border
 
@@ -206,21 +206,27 @@ struct LrShared {
   uint16_t A[kLrAH * kLrAW];
   int32_t B[kLrAH * kLrAW];
   uint16_t F0[kLrBandH * kLrMaxW];
+  // raw box sums of the band, shared by every candidate set: 3x3 at all A/B rows, 5x5 at the odd rows only
+  uint32_t R3a[kLrAH * kLrAW], R5a[((kLrAH + 1) / 2) * kLrAW];
+  uint16_t R3b[kLrAH * kLrAW], R5b[((kLrAH + 1) / 2) * kLrAW];
   unsigned long long acc[B200_LR_CANDIDATES][6];     // H00, H01, H11, C0, C1 (two's complement), S
   B200LrUnit best;
 };
 
 __device__ __forceinline__ long long lr_round2(long long v, int n) { return n == 0 ? v : ((v + (1ll << (n - 1))) >> n); }
 
-// box sums of radius r around staged sample (sy, sx) -> a2 (A) and B entry
-__device__ __forceinline__ void lr_ab(const uint16_t *S, int sy, int sx, int r, int bd, uint32_t s, uint32_t one_by_n, int n, uint16_t *a_out,
-                                      int32_t *b_out) {
+// box sums of radius r around staged sample (sy, sx)
+__device__ __forceinline__ void lr_box(const uint16_t *S, int sy, int sx, int r, uint32_t *a_out, uint32_t *b_out) {
   uint32_t a = 0, b = 0;
   for (int dy = -r; dy <= r; dy++)
     for (int dx = -r; dx <= r; dx++) {
       const uint32_t v = S[(sy + dy) * kLrSW + sx + dx];
       a += v * v; b += v;
     }
+  *a_out = a; *b_out = b;
+}
+// box sums -> a2 (A entry) and B entry for one parameter set (AV1 spec 7.17.4)
+__device__ __forceinline__ void lr_ab(uint32_t a, uint32_t b, int bd, uint32_t s, uint32_t one_by_n, int n, uint16_t *a_out, int32_t *b_out) {
   const uint32_t a_s = (uint32_t)lr_round2(a, 2 * (bd - 8)), d = (uint32_t)lr_round2(b, bd - 8);
   const long long pp = (long long)a_s * n - (long long)d * d;
   const unsigned long long p = pp < 0 ? 0ull : (unsigned long long)pp;
@@ -295,6 +301,20 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
         sh.S[sy * kLrSW + sx] = v;
       }
       __syncthreads();
+      // raw box sums, once per band
+      for (int i = tid; i < (bh + 2) * (w + 2); i += 256) {
+        const int ai = i / (w + 2), aj = i % (w + 2);
+        uint32_t a, b;
+        lr_box(sh.S, ai + 2, aj + 2, 1, &a, &b);
+        sh.R3a[ai * kLrAW + aj] = a; sh.R3b[ai * kLrAW + aj] = (uint16_t)b;
+      }
+      for (int i = tid; i < ((bh + 3) / 2) * (w + 2); i += 256) {
+        const int ri = i / (w + 2), aj = i % (w + 2);          // A row index 2 * ri <-> i = -1, 1, 3, ...
+        uint32_t a, b;
+        lr_box(sh.S, 2 * ri + 2, aj + 2, 2, &a, &b);
+        sh.R5a[ri * kLrAW + aj] = a; sh.R5b[ri * kLrAW + aj] = (uint16_t)b;
+      }
+      __syncthreads();
       const int ncand = phase == 0 ? B200_LR_CANDIDATES : 1;
       for (int ci = 0; ci < ncand; ci++) {
         const int set = phase == 0 ? cand[ci] : sh.best.set;
@@ -316,8 +336,11 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
             // A / B at rows -1..bh (pass 0: odd rows only), columns -1..w
             const int rows = pass == 0 ? (bh + 3) / 2 : bh + 2;
             for (int i = tid; i < rows * (w + 2); i += 256) {
-              const int ai = pass == 0 ? (i / (w + 2)) * 2 : i / (w + 2), aj = i % (w + 2);      // A row index = i + 1, i = -1, 1, 3, ...
-              lr_ab(sh.S, ai + 2, aj + 2, r, bd, s, one_by_n, n, &sh.A[ai * kLrAW + aj], &sh.B[ai * kLrAW + aj]);
+              const int ri = i / (w + 2), aj = i % (w + 2);
+              const int ai = pass == 0 ? ri * 2 : ri;             // A row index = i + 1, i = -1, 1, 3, ... in the r = 2 pass
+              const uint32_t a = pass == 0 ? sh.R5a[ri * kLrAW + aj] : sh.R3a[ri * kLrAW + aj];
+              const uint32_t b = pass == 0 ? sh.R5b[ri * kLrAW + aj] : sh.R3b[ri * kLrAW + aj];
+              lr_ab(a, b, bd, s, one_by_n, n, &sh.A[ai * kLrAW + aj], &sh.B[ai * kLrAW + aj]);
             }
           }
           __syncthreads();

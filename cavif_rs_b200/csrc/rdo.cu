@@ -775,7 +775,7 @@ __device__ __noinline__ void reconstruct_block(const TileCtx &t, Shared &sh, int
 constexpr int kSatdItems = 512;
 __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid, int *sh_d);
 
-__global__ void __launch_bounds__(128, 8) b200_satd_kernel(const B200RdoJob *jobs, int lv, int items /* per CTA: 128 .. kSatdItems */) {
+__global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, int lv, int items /* per CTA: 128 .. kSatdItems */) {
   __shared__ int sh_d[128 * 17];     // per-thread 16 residuals (+1 pad: conflict-free), written by a rolled loop
   __shared__ uint16_t s_list[kSatdItems];
   __shared__ int s_n;
@@ -807,6 +807,23 @@ __global__ void __launch_bounds__(128, 8) b200_satd_kernel(const B200RdoJob *job
   const int cnt = s_n;
 #pragma unroll 1
   for (int i = threadIdx.x; i < cnt; i += 128) satd_item(job, lv, base + s_list[i], sh_d);
+}
+
+// never-pruned top level: one item per thread, no compaction
+__global__ void __launch_bounds__(128) b200_satd_direct_kernel(const B200RdoJob *jobs, int lv) {
+  __shared__ int sh_d[128 * 17];
+  const B200RdoJob &job = jobs[blockIdx.y];
+  const B200Frame *f = &job.frame;
+  const int n = 4 << lv;
+  if (n < min(f->partition_min, 8) || n > f->partition_max) return;
+  const int total = b200_level_cols(f, lv) * b200_level_rows(f, lv) * (f->planes > 1 ? 2 : 1);
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  if (lv < 2) {
+    const int cols = b200_level_cols(f, lv), blk = gid % (cols * b200_level_rows(f, lv));
+    if (b200_pruned_by_parent(f, lv, blk % cols, blk / cols, job.dec[lv + 1])) return;
+  }
+  satd_item(job, lv, gid, sh_d);
 }
 
 __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid, int *sh_d) {
@@ -1111,9 +1128,15 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
   for (int lv = 2; lv >= 0; lv--) {   // large to small: 4x4 analysis is pruned by its 8x8 parent
     const int nblk = max_blocks4 >> (2 * lv);
     // the top level is never pruned: one item per thread; lower levels are mostly pruned: compact 512 items per CTA
-    const int items = lv == 2 ? 128 : kSatdItems;
-    dim3 gs((nblk * 2 + items - 1) / items, n_jobs);
-    b200_satd_kernel<<<gs, 128, 0, st>>>(d_jobs, lv, items);
+    static const int satd_mode = getenv("B200AVIF_SATD_MODE") ? atoi(getenv("B200AVIF_SATD_MODE")) : 0;    // experiments
+    if ((lv == 2 && satd_mode != 1) || satd_mode == 2) {
+      dim3 gs((nblk * 2 + 127) / 128, n_jobs);
+      b200_satd_direct_kernel<<<gs, 128, 0, st>>>(d_jobs, lv);
+    } else {
+      const int items = lv == 2 ? 128 : kSatdItems;
+      dim3 gs((nblk * 2 + items - 1) / items, n_jobs);
+      b200_satd_kernel<<<gs, 128, 0, st>>>(d_jobs, lv, items);
+    }
     // enough warps to fill the machine several times over, grid-stride inside
     const int per_job = min(nblk, max(1, (148 * 16 * 4) / n_jobs));
     dim3 ga(per_job, n_jobs);
