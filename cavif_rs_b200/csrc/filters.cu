@@ -233,7 +233,7 @@ __device__ __forceinline__ void lr_ab(uint32_t a, uint32_t b, int bd, uint32_t s
   const unsigned long long z = (p * s + (1u << 19)) >> 20;
   const uint32_t a2 = dv_x_by_xplus1[z > 255 ? 255 : (int)z];
   *a_out = (uint16_t)a2;
-  *b_out = (int32_t)lr_round2((long long)(256 - a2) * b * one_by_n, 12);
+  *b_out = (int32_t)(((256u - a2) * b * one_by_n + (1u << 11)) >> 12);      // (256 - a2) * b * one_by_n < 2^31 for r = 1 and r = 2
 }
 
 __device__ __forceinline__ long long lr_round_div(long long a, long long b) { return a >= 0 ? (a + b / 2) / b : -((-a + b / 2) / b); }
@@ -349,34 +349,35 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
             const int u_px = sh.S[(py + 3) * kLrSW + px + 3];
             int32_t fv = 0;
             if (r) {
-              long long a = 0, b = 0;
+              int a = 0, b = 0;       // a <= 32 * 256, b <= 32 * 2^18: a * u + b < 2^31
               if (pass == 0) {
                 if (py & 1) {       // odd row: its own A / B row, weights 6 5 5
                   const uint16_t *Ar = &sh.A[(py + 1) * kLrAW + px + 1]; const int32_t *Br = &sh.B[(py + 1) * kLrAW + px + 1];
-                  a = 6 * Ar[0] + 5 * (Ar[-1] + Ar[1]); b = 6ll * Br[0] + 5ll * ((long long)Br[-1] + Br[1]);
+                  a = 6 * Ar[0] + 5 * (Ar[-1] + Ar[1]); b = 6 * Br[0] + 5 * (Br[-1] + Br[1]);
                 } else {
                   const uint16_t *Au = &sh.A[py * kLrAW + px + 1], *Ad = &sh.A[(py + 2) * kLrAW + px + 1];
                   const int32_t *Bu = &sh.B[py * kLrAW + px + 1], *Bd = &sh.B[(py + 2) * kLrAW + px + 1];
                   a = 6 * (Au[0] + Ad[0]) + 5 * (Au[-1] + Au[1] + Ad[-1] + Ad[1]);
-                  b = 6ll * ((long long)Bu[0] + Bd[0]) + 5ll * ((long long)Bu[-1] + Bu[1] + Bd[-1] + Bd[1]);
+                  b = 6 * (Bu[0] + Bd[0]) + 5 * (Bu[-1] + Bu[1] + Bd[-1] + Bd[1]);
                 }
-                fv = (int32_t)lr_round2(a * u_px + b, 8 + ((py & 1) ? 4 : 5) - 4);
+                { const int sh_f = 8 + ((py & 1) ? 4 : 5) - 4; fv = (a * u_px + b + (1 << (sh_f - 1))) >> sh_f; }
               } else {
                 for (int dy = -1; dy <= 1; dy++)
                   for (int dx = -1; dx <= 1; dx++) {
                     const int wt = (dx == 0 || dy == 0) ? 4 : 3;
                     a += wt * sh.A[(py + 1 + dy) * kLrAW + px + 1 + dx];
-                    b += (long long)wt * sh.B[(py + 1 + dy) * kLrAW + px + 1 + dx];
+                    b += wt * sh.B[(py + 1 + dy) * kLrAW + px + 1 + dx];
                   }
-                fv = (int32_t)lr_round2(a * u_px + b, 8 + 5 - 4);
+                fv = (a * u_px + b + (1 << 8)) >> 9;
               }
             }
             if (pass == 0) { sh.F0[py * kLrMaxW + px] = (uint16_t)fv; continue; }
             const int32_t f0 = sh.F0[py * kLrMaxW + px], f1 = fv;
             if (phase == 0) {
-              const long long u = (long long)u_px << 4;
-              const long long sv = ((long long)src[(ys + py) * stride + x0 + px] << 4) - u;
-              const long long av = r0 ? f0 - u : 0, bv = r1 ? f1 - u : 0;
+              // |av|, |bv|, |sv| < 2^15: the products fit 32 bits, only the sums are 64-bit
+              const int u = u_px << 4;
+              const int sv = ((int)src[(ys + py) * stride + x0 + px] << 4) - u;
+              const int av = r0 ? f0 - u : 0, bv = r1 ? f1 - u : 0;
               h00 += av * av; h01 += av * bv; h11 += bv * bv; c0 += av * sv; c1 += bv * sv; ss += sv * sv;
             } else {
               const int w0 = sh.best.xqd0, w1 = sh.best.xqd1, w2 = 128 - w0 - w1;
