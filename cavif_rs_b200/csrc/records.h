@@ -71,8 +71,8 @@ typedef struct B200Frame {
   int32_t y_mode_mask, uv_mode_mask;        // allowed intra modes (bit = mode index); conformance tests force single modes
   int32_t tx_type_mask;                     // allowed luma transform types: bit0 DCT_DCT 1 ADST_DCT 2 DCT_ADST 3 ADST_ADST 4 IDTX
   // early termination of the partition search: the children of a block are not analysed when its own RD cost is at
-  // most split_gate_bits * lambda ([0]: 8x8 -> 4x4, [1]: 16x16 -> 8x8; 0 = exhaustive search)
-  int32_t split_gate_bits[2];
+  // most split_gate_bits * lambda ([0]: 8x8 -> 4x4, [1]: 16x16 -> 8x8, [2]: 32x32 -> 16x16; 0 = exhaustive search)
+  int32_t split_gate_bits[3];
   // decisions of the in-loop filter stages
   int32_t lf_level[4];                      // y vertical, y horizontal, u, v
   int32_t lf_sharpness;
@@ -106,6 +106,8 @@ typedef struct B200BlockDec {
 // SATD table entry per (block, plane group): 13 mode SATDs + one word packing the refined directional mode and its
 // angle delta: (mode | (delta + 3) << 8), mode = 255 when no directional mode was refined.
 #define B200_SATD_WORDS 14
+// analysis levels: 0: 4x4, 1: 8x8, 2: 16x16, 3: 32x32 (block size 4 << lv)
+#define B200_LEVELS 4
 // Early termination of the partition search: the four 4x4 children of an 8x8 block whose analysis quantised to
 // all-zero are not analysed; their cost is this sentinel so the split can never win.
 #define B200_COST_PRUNED ((int64_t)1 << 60)
@@ -138,10 +140,10 @@ static inline B200_HD int b200_level_cols(const B200Frame *f, int lv) { return f
 static inline B200_HD int b200_level_rows(const B200Frame *f, int lv) { return f->mi_rows >> lv; }
 
 // Top-down pruning of the analysis (same rule in the oracle and in every device kernel): block (bx, by) of level
-// lv (0: 4x4, 1: 8x8) is not analysed when its parent at level lv + 1 was itself pruned, quantised to all-zero in
+// lv (0: 4x4, 1: 8x8, 2: 16x16) is not analysed when its parent at level lv + 1 was itself pruned, quantised to all-zero in
 // every plane, or is already cheap enough (split_gate_bits).  `parent` = the decision array of level lv + 1.
 static inline B200_HD int b200_pruned_by_parent(const B200Frame *f, int lv, int bx, int by, const B200BlockDec *parent) {
-  if (lv >= 2) return 0;
+  if (lv >= B200_LEVELS - 1) return 0;
   const int pn = 8 << lv;
   const int pmin8 = f->partition_min < 8 ? f->partition_min : 8;
   if (pn < pmin8 || pn > f->partition_max) return 0;                  /* the parent level is not analysed */

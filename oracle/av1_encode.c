@@ -35,7 +35,7 @@ typedef struct {
   B200Mi *mi;
   uint16_t *eob[3];
   int16_t *coef[3];
-  B200BlockDec *dec[3];     /* analysis decisions per level (0: 4x4, 1: 8x8, 2: 16x16) */
+  B200BlockDec *dec[B200_LEVELS];     /* analysis decisions per level (0: 4x4, 1: 8x8, 2: 16x16, 3: 32x32) */
   int tr0, tr1, tc0, tc1;   /* current tile bounds in mi units */
 } enc_t;
 
@@ -437,8 +437,10 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
     else if (c < bc[1]) { bc[1] = c; bm[1] = m; }
   }
   /* luma trials: top-2 modes x allowed transform types; order (mode rank, type index), strict '<' keeps the earliest */
+  /* 32x32: the intra transform set is DCT only (AV1 spec get_tx_set: no tx_type is coded) */
+  const int tx_mask = n == 32 ? 1 : f->tx_type_mask;
   int first_tt = -1;
-  for (int k = 0; k < 5; k++) if ((f->tx_type_mask >> k) & 1) { first_tt = k_tx_types[k]; break; }
+  for (int k = 0; k < 5; k++) if ((tx_mask >> k) & 1) { first_tt = k_tx_types[k]; break; }
   int64_t bestJ = INT64_MAX;
   int best_mode = bm[0], best_tt = first_tt, eob_y = 0, best_c = 1 << 20;
   int16_t qc[1024];
@@ -456,7 +458,7 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
       const uint32_t mrate = mode_rate(rt, ymode_cost, m, n, DELTA_Y(m));
       for (int t = 0; t < 5; t++) {
         const int tt = k_tx_types[t];
-        if (!((f->tx_type_mask >> t) & 1)) continue;
+        if (!((tx_mask >> t) & 1)) continue;
         if ((pass == 0) != (tt == first_tt)) continue;
         uint32_t rate;
         const uint64_t d = trial_plane(e, 0, x, y, n, pred, tt, m, qc, &eobv, recon, &rate);
@@ -549,38 +551,32 @@ static const B200BlockDec *dec_at(const enc_t *e, int lv, int x, int y) {
   const int n = 4 << lv;
   return &e->dec[lv][(y / n) * b200_level_cols(e->f, lv) + (x / n)];
 }
-void orc_decide_region(enc_t *e, int x, int y) {
+/* Best RD cost of the block (level lv, top-left x, y): PARTITION_NONE against PARTITION_SPLIT into four blocks of the
+ * level below, recursively; blocks that stick out of the (8-pixel aligned) frame must split.  commit != 0 also writes
+ * the winning decisions into the mode-info array.  Ties keep the larger block. */
+static int64_t decide_block(enc_t *e, int lv, int x, int y, int commit) {
   const B200Frame *f = e->f;
-  const int W = f->mi_cols * 4, H = f->mi_rows * 4;
-  if (x >= W || y >= H) return;
-  const int inside = (x + 16 <= W) && (y + 16 <= H);
-  const int can_none = inside && f->partition_max >= 16;
-  const int can_split = f->partition_min < 16 || !inside;
-  int64_t j_split = part_cost(f, e->rt, y >> 2, x >> 2, 16, 1);
-  int split8[4] = {0, 0, 0, 0};
-  for (int k = 0; k < 4; k++) {
-    const int xx = x + (k & 1) * 8, yy = y + (k >> 1) * 8;
-    if (xx >= W || yy >= H) continue;
-    const int64_t j8 = dec_at(e, 1, xx, yy)->cost + part_cost(f, e->rt, yy >> 2, xx >> 2, 8, 0);
-    int64_t best = j8;
-    if (f->partition_min < 8) {
-      int64_t j4 = part_cost(f, e->rt, yy >> 2, xx >> 2, 8, 1);
-      for (int q = 0; q < 4; q++) j4 += dec_at(e, 0, xx + (q & 1) * 4, yy + (q >> 1) * 4)->cost;
-      if (!(j8 <= j4)) { best = j4; split8[k] = 1; }
-    }
-    j_split += best;
+  const int W = f->mi_cols * 4, H = f->mi_rows * 4, n = 4 << lv;
+  if (x >= W || y >= H) return 0;
+  const int inside = (x + n <= W) && (y + n <= H);
+  const int can_none = inside && n <= f->partition_max;
+  const int can_split = lv > 0 && (f->partition_min < n || !inside);
+  int64_t j_none = 0, j_split = 0;
+  if (can_none) j_none = dec_at(e, lv, x, y)->cost + (lv > 0 ? part_cost(f, e->rt, y >> 2, x >> 2, n, 0) : 0);
+  if (can_split) {
+    j_split = part_cost(f, e->rt, y >> 2, x >> 2, n, 1);
+    for (int k = 0; k < 4; k++) j_split += decide_block(e, lv - 1, x + (k & 1) * (n >> 1), y + (k >> 1) * (n >> 1), 0);
   }
-  if (can_none && (!can_split || dec_at(e, 2, x, y)->cost + part_cost(f, e->rt, y >> 2, x >> 2, 16, 0) <= j_split)) {
-    set_mi(e, x, y, 16, dec_at(e, 2, x, y));
-    return;
+  const int none = can_none && (!can_split || j_none <= j_split);
+  if (commit) {
+    if (none) set_mi(e, x, y, n, dec_at(e, lv, x, y));
+    else for (int k = 0; k < 4; k++) decide_block(e, lv - 1, x + (k & 1) * (n >> 1), y + (k >> 1) * (n >> 1), 1);
   }
-  for (int k = 0; k < 4; k++) {
-    const int xx = x + (k & 1) * 8, yy = y + (k >> 1) * 8;
-    if (xx >= W || yy >= H) continue;
-    if (!split8[k]) set_mi(e, xx, yy, 8, dec_at(e, 1, xx, yy));
-    else for (int q = 0; q < 4; q++) set_mi(e, xx + (q & 1) * 4, yy + (q >> 1) * 4, 4, dec_at(e, 0, xx + (q & 1) * 4, yy + (q >> 1) * 4));
-  }
+  return none ? j_none : j_split;
 }
+/* root regions: 32x32 when the partition range reaches it, else 16x16 */
+static int root_level(const B200Frame *f) { return f->partition_max >= 32 ? 3 : 2; }
+void orc_decide_region(enc_t *e, int x, int y) { decide_block(e, root_level(e->f), x, y, 1); }
 
 /* ---- stage C: closed-loop reconstruction of one decided block (the only stage that needs reconstructed neighbours) */
 static void reconstruct_block(enc_t *e, int x, int y, int n) {
@@ -635,17 +631,17 @@ static void tile_of(const B200Frame *f, int mi_r, int mi_c, int *tr, int *tc) {
 /* Whole frame: analysis of every block at every allowed level, partition decision, reconstruction chain.
  * dec[lv] (may be NULL): receives the analysis decisions, satd (may be NULL): [lv][block][2][13] for tests. */
 void orc_encode_frame(const B200Frame *f, const B200RateTables *rt, uint16_t *const src[3], uint16_t *const rec[3],
-                      B200Mi *mi, uint16_t *const eob[3], int16_t *const coef[3], B200BlockDec *const dec_out[3],
-                      uint32_t *const satd_out[3]) {
+                      B200Mi *mi, uint16_t *const eob[3], int16_t *const coef[3], B200BlockDec *const dec_out[B200_LEVELS],
+                      uint32_t *const satd_out[B200_LEVELS]) {
   enc_t e;
   memset(&e, 0, sizeof(e));
   e.f = f; e.rt = rt; e.stride = f->mi_cols * 4; e.mi = mi;
   for (int p = 0; p < 3; p++) { e.src[p] = src[p]; e.rec[p] = rec[p]; e.eob[p] = eob[p]; e.coef[p] = coef[p]; }
-  for (int lv = 0; lv < 3; lv++) {
+  for (int lv = 0; lv < B200_LEVELS; lv++) {
     const size_t nblk = (size_t)b200_level_rows(f, lv) * b200_level_cols(f, lv);
     e.dec[lv] = (dec_out && dec_out[lv]) ? dec_out[lv] : (B200BlockDec *)calloc(nblk ? nblk : 1, sizeof(B200BlockDec));
   }
-  for (int lv = 2; lv >= 0; lv--) {     /* large to small: 4x4 analysis is pruned by its 8x8 parent */
+  for (int lv = B200_LEVELS - 1; lv >= 0; lv--) {     /* large to small: a level is pruned by its parent level */
     const int n = 4 << lv;
     /* 8x8 is always analysed: 16x16 regions that stick out of the frame are forced to split down to 8x8 */
     if (n < (f->partition_min < 8 ? f->partition_min : 8) || n > f->partition_max) continue;
@@ -656,7 +652,7 @@ void orc_encode_frame(const B200Frame *f, const B200RateTables *rt, uint16_t *co
         tile_bounds(&e, tr, tc);
         uint32_t sy[14], suv[14];
         const size_t bi = (size_t)by * b200_level_cols(f, lv) + bx;
-        if (lv < 2 && b200_pruned_by_parent(f, lv, bx, by, e.dec[lv + 1])) {
+        if (lv < B200_LEVELS - 1 && b200_pruned_by_parent(f, lv, bx, by, e.dec[lv + 1])) {
           memset(&e.dec[lv][bi], 0, sizeof(B200BlockDec));
           e.dec[lv][bi].cost = B200_COST_PRUNED;
           if (satd_out && satd_out[lv]) memset(satd_out[lv] + bi * 2 * B200_SATD_WORDS, 0, 2 * B200_SATD_WORDS * sizeof(uint32_t));
@@ -666,8 +662,9 @@ void orc_encode_frame(const B200Frame *f, const B200RateTables *rt, uint16_t *co
         if (satd_out && satd_out[lv]) { memcpy(satd_out[lv] + bi * 2 * B200_SATD_WORDS, sy, sizeof(sy)); memcpy(satd_out[lv] + bi * 2 * B200_SATD_WORDS + B200_SATD_WORDS, suv, sizeof(suv)); }
       }
   }
-  for (int y = 0; y < f->mi_rows * 4; y += 16)
-    for (int x = 0; x < f->mi_cols * 4; x += 16) orc_decide_region(&e, x, y);
+  const int rn = 4 << root_level(f);
+  for (int y = 0; y < f->mi_rows * 4; y += rn)
+    for (int x = 0; x < f->mi_cols * 4; x += rn) orc_decide_region(&e, x, y);
   for (int tr = 0; tr < f->tile_rows; tr++)
     for (int tc = 0; tc < f->tile_cols; tc++) {
       tile_bounds(&e, tr, tc);
@@ -683,5 +680,5 @@ void orc_encode_frame(const B200Frame *f, const B200RateTables *rt, uint16_t *co
             reconstruct_block(&e, mc * 4, mr * 4, n);
           }
     }
-  for (int lv = 0; lv < 3; lv++) if (!(dec_out && dec_out[lv])) free(e.dec[lv]);
+  for (int lv = 0; lv < B200_LEVELS; lv++) if (!(dec_out && dec_out[lv])) free(e.dec[lv]);
 }

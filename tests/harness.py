@@ -15,7 +15,7 @@ class B200Frame(ctypes.Structure):
         "color_description_present", "color_primaries", "transfer_characteristics", "matrix_coefficients", "full_range",
         "partition_min", "partition_max", "rdo_tx_decision", "fine_directional_intra", "enable_cfl",
         "lambda_q8", "lambda_satd_q8", "y_mode_mask", "uv_mode_mask", "tx_type_mask")] + [
-        ("split_gate_bits", ctypes.c_int32 * 2),
+        ("split_gate_bits", ctypes.c_int32 * 3),
         ("lf_level", ctypes.c_int32 * 4), ("lf_sharpness", ctypes.c_int32),
         ("cdef_damping", ctypes.c_int32), ("cdef_bits", ctypes.c_int32),
         ("cdef_y_strength", ctypes.c_int32 * 8), ("cdef_uv_strength", ctypes.c_int32 * 8),
@@ -134,8 +134,8 @@ class Records:
         self.lr = [np.zeros(lr_units(f.height) * lr_units(f.width), LR_DTYPE) for _ in range(3)]
         self.rec = [np.zeros((f.mi_rows * 4, f.mi_cols * 4), np.uint16) for _ in range(3)]
         # open-loop analysis outputs per level (0: 4x4, 1: 8x8, 2: 16x16)
-        self.dec = [np.zeros((f.mi_rows >> lv) * (f.mi_cols >> lv), DEC_DTYPE) for lv in range(3)]
-        self.satd = [np.zeros(((f.mi_rows >> lv) * (f.mi_cols >> lv), 2, 14), np.uint32) for lv in range(3)]
+        self.dec = [np.zeros(max((f.mi_rows >> lv) * (f.mi_cols >> lv), 1), DEC_DTYPE) for lv in range(LEVELS)]
+        self.satd = [np.zeros((max((f.mi_rows >> lv) * (f.mi_cols >> lv), 1), 2, 14), np.uint32) for lv in range(LEVELS)]
     def c_records(self):
         r = B200Records()
         r.mi = self.mi.ctypes.data
@@ -147,6 +147,11 @@ class Records:
             r.lr[p] = self.lr[p].ctypes.data
         return r
 
+LEVELS = 4     # analysis levels: 4x4, 8x8, 16x16, 32x32 (records.h B200_LEVELS)
+
+def ptrn(arrs):
+    return (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
 def ptr3(arrs):
     return (ctypes.c_void_p * 3)(*[a.ctypes.data for a in arrs])
 
@@ -156,7 +161,7 @@ def oracle_encode(f, rt, src):
     rec = Records(f)
     src3 = list(src) + [src[0]] * (3 - len(src))
     L.orc_encode_frame(ctypes.byref(f), rt.ctypes.data, ptr3(src3), ptr3(rec.rec), rec.mi.ctypes.data,
-                       ptr3(rec.eob), ptr3(rec.coef), ptr3(rec.dec), ptr3(rec.satd))
+                       ptr3(rec.eob), ptr3(rec.coef), ptrn(rec.dec), ptrn(rec.satd))
     return rec
 
 def oracle_filters(f, rec, src):

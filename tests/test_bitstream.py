@@ -95,3 +95,15 @@ def test_rate_increases_with_quality():
     s_lo, p_lo = roundtrip(256, 192, q=180)
     s_hi, p_hi = roundtrip(256, 192, q=60)
     assert s_hi > s_lo and p_hi > p_lo
+
+
+@pytest.mark.parametrize("w,h,depth,planes,q,tiles", [
+    (256, 256, 8, 3, 180, 1), (200, 136, 10, 3, 150, 2), (95, 95, 8, 1, 100, 1), (384, 320, 8, 3, 220, 4), (130, 70, 10, 3, 199, 1),
+])
+def test_32x32_partitions(w, h, depth, planes, q, tiles):
+    """partition range 4..32 (ravif speed <= 2): BLOCK_32X32 / TX_32X32 (DCT only), forced splits at the frame edges"""
+    n, psnr = roundtrip(w, h, depth=depth, planes=planes, q=q, tiles=tiles, pmax=32, seed=w)
+    assert n > 0
+    n8, _ = roundtrip(w, h, depth=depth, planes=planes, q=q, tiles=tiles, pmin=8, pmax=32, seed=w)
+    n16, _ = roundtrip(w, h, depth=depth, planes=planes, q=q, tiles=tiles, pmin=16, pmax=32, rdo_tx=0, seed=w)
+    assert n8 > 0 and n16 > 0
