@@ -153,8 +153,8 @@ struct FrameJob {
   B200Mi *d_mi = nullptr;
   uint16_t *d_eob[3] = {nullptr, nullptr, nullptr};
   int16_t *d_coef[3] = {nullptr, nullptr, nullptr};
-  B200BlockDec *d_dec[3] = {nullptr, nullptr, nullptr};
-  uint32_t *d_satd[3] = {nullptr, nullptr, nullptr};
+  B200BlockDec *d_dec[B200_LEVELS] = {};
+  uint32_t *d_satd[B200_LEVELS] = {};
   int8_t *d_cdef = nullptr;
   uint16_t *d_fin[3] = {nullptr, nullptr, nullptr};   // CDEF output: input of the loop-restoration search (and the test seam)
   B200LrUnit *d_lr[3] = {nullptr, nullptr, nullptr}, *h_lr[3] = {nullptr, nullptr, nullptr};
@@ -184,7 +184,7 @@ size_t job_dev_bytes(const FrameJob &j, bool own_src) {
   b += P * align256(j.n_mi() * 2);
   b += P * align256(j.n_coef() * 2);
   b += align256(j.n_sb());
-  for (int lv = 0; lv < 3; lv++) b += align256(j.n_blk(lv) * sizeof(B200BlockDec)) + align256(j.n_blk(lv) * 2 * B200_SATD_WORDS * 4);
+  for (int lv = 0; lv < B200_LEVELS; lv++) b += align256(j.n_blk(lv) * sizeof(B200BlockDec)) + align256(j.n_blk(lv) * 2 * B200_SATD_WORDS * 4) + 512;
   if (j.uses_lr()) b += P * (align256(j.n_px() * 2) + align256(j.n_lr() * sizeof(B200LrUnit)));
   return b + 8192;
 }
@@ -204,7 +204,7 @@ void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
     j.h_coef[p] = pin.take<int16_t>(j.n_coef());
   }
   j.d_mi = dev.take<B200Mi>(j.n_mi());
-  for (int lv = 0; lv < 3; lv++) {
+  for (int lv = 0; lv < B200_LEVELS; lv++) {
     j.d_dec[lv] = dev.take<B200BlockDec>(j.n_blk(lv));
     j.d_satd[lv] = dev.take<uint32_t>(j.n_blk(lv) * 2 * B200_SATD_WORDS);
   }
@@ -233,12 +233,13 @@ int configure_frame(B200Frame *f, size_t w, size_t h, int depth, bool mono, int 
   f->partition_min = tw.partition_min;
   // The device RDO currently searches square partitions up to 16x16 (ravif reaches 32x32/64x64 only at
   // speed <= 2 with low quantizers, av1encoder.rs:563-570); larger maxima are clamped.
-  f->partition_max = std::min(tw.partition_max, 16);
+  f->partition_max = std::min(tw.partition_max, 32);      // 64x64 blocks (speed 1) are clamped to 32x32
   f->partition_min = std::min(f->partition_min, f->partition_max);
   f->fine_directional_intra = tw.fine_directional_intra;
   // early termination of the partition search (records.h split_gate_bits): exhaustive at the slow presets
   f->split_gate_bits[0] = speed <= 2 ? 0 : 44;
   f->split_gate_bits[1] = speed <= 2 ? 0 : 96;
+  f->split_gate_bits[2] = speed <= 2 ? 0 : 200;
   if (!tw.cdef) f->enable_cdef = 0;   // ravif: cdef = low_quality && speed <= 9 (av1encoder.rs:590)
   f->enable_restoration = tw.lrf ? 1 : 0;     // loop restoration (lrf flag, av1encoder.rs:589): self-guided filter, 64x64 units
   for (int p = 0; p < 3; p++) f->lr_type[p] = (tw.lrf && p < f->planes) ? 1 : 0;
@@ -285,7 +286,7 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
       r.src[p] = j.d_src[q]; r.rec[p] = j.d_rec[q]; r.eob[p] = j.d_eob[q]; r.coef[p] = j.d_coef[q];
     }
     r.mi = j.d_mi;
-    for (int lv = 0; lv < 3; lv++) { r.dec[lv] = j.d_dec[lv]; r.satd[lv] = j.d_satd[lv]; }
+    for (int lv = 0; lv < B200_LEVELS; lv++) { r.dec[lv] = j.d_dec[lv]; r.satd[lv] = j.d_satd[lv]; }
     r.cdef_idx = j.d_cdef;
     for (int p = 0; p < 3; p++) r.fin[p] = j.d_fin[p < j.f.planes ? p : 0];
     for (int p = 0; p < 3; p++) { r.lr[p] = p < j.f.planes ? j.d_lr[p] : nullptr; r.lr_out[p] = p < j.f.planes ? j.d_lr_out[p] : nullptr; }
@@ -298,10 +299,10 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
   CU(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(B200TileRef), cudaMemcpyHostToDevice, c.stream));
   if (after_analysis_of) CU(cudaStreamWaitEvent(c.stream, after_analysis_of, 0));
   CU(cudaEventRecord(c.ev[1], c.stream));
-  int max_blocks4 = 0;
-  for (FrameJob *jp : jobs) max_blocks4 = std::max(max_blocks4, (int)jp->n_mi());
+  int max_blocks4 = 0, top_level = 2;
+  for (FrameJob *jp : jobs) { max_blocks4 = std::max(max_blocks4, (int)jp->n_mi()); if (jp->f.partition_max >= 32) top_level = 3; }
   const int le = b200_rdo_launch(d_jobs, (int)jobs.size(), d_tiles, (int)tiles.size(), max_blocks4, jobs[0]->f.bit_depth > 8,
-                                 c.stream, c.stream_hi, c.ev_analysis);   // one bit depth per call
+                                 top_level, c.stream, c.stream_hi, c.ev_analysis);   // one bit depth per call
   if (le != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("RDO kernel launch failed: ") + cudaGetErrorString((cudaError_t)le));
   g_launches += 8;   // 3 x (SATD + analysis) + partition decision + reconstruction
   CU(cudaEventRecord(c.ev[2], c.stream_hi));
@@ -830,7 +831,7 @@ int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h,
 // ---- test seam: run the device hot path on caller-provided coded planes and frame description -----
 int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi, uint16_t *const eob[3], int16_t *const coef[3],
                     uint16_t *const rec[3], uint16_t *const deblocked[3], uint16_t *const fin[3], int8_t *cdef_idx,
-                    B200BlockDec *const dec[3], uint32_t *const satd[3], B200LrUnit *const lr[3], uint16_t *const lr_out[3]) {
+                    B200BlockDec *const dec[B200_LEVELS], uint32_t *const satd[B200_LEVELS], B200LrUnit *const lr[3], uint16_t *const lr_out[3]) {
   if (!f || !src || !mi) return fail(B200AVIF_INVALID_ARGUMENT, "null argument");
   if (b200avif_device_count() <= 0) return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
   FrameJob job;
@@ -852,7 +853,7 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
     CU(cudaMemsetAsync(job.d_coef[p], 0, job.n_coef() * 2, c.stream));
     CU(cudaMemsetAsync(job.d_eob[p], 0, job.n_mi() * 2, c.stream));
   }
-  for (int lv = 0; lv < 3; lv++) {   // levels outside the partition range are not analysed: keep them comparable
+  for (int lv = 0; lv < B200_LEVELS; lv++) {   // levels outside the partition range are not analysed: keep them comparable
     CU(cudaMemsetAsync(job.d_dec[lv], 0, job.n_blk(lv) * sizeof(B200BlockDec), c.stream));
     CU(cudaMemsetAsync(job.d_satd[lv], 0, job.n_blk(lv) * 2 * B200_SATD_WORDS * 4, c.stream));
   }
@@ -861,7 +862,7 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
   if (int e = run_rdo_and_fetch(c, jobs, c.dev, c.pin, true, &deb, &pre)) return e;
   memcpy(mi, job.h_mi, job.n_mi() * sizeof(B200Mi));
   if (cdef_idx) memcpy(cdef_idx, job.h_cdef, job.n_sb());
-  for (int lv = 0; lv < 3; lv++) {
+  for (int lv = 0; lv < B200_LEVELS; lv++) {
     if (dec && dec[lv]) CU(cudaMemcpy(dec[lv], job.d_dec[lv], job.n_blk(lv) * sizeof(B200BlockDec), cudaMemcpyDeviceToHost));
     if (satd && satd[lv]) CU(cudaMemcpy(satd[lv], job.d_satd[lv], job.n_blk(lv) * 2 * B200_SATD_WORDS * 4, cudaMemcpyDeviceToHost));
   }

@@ -43,7 +43,7 @@ namespace {
 
 constexpr int kThreads = 32;
 constexpr int EOFF = 16;          // edge arrays: index -1 .. 2n-1 stored at EOFF-1 ..
-constexpr int kEdge = EOFF + 34;  // n <= 16
+constexpr int kEdge = EOFF + 34;  // n <= 16 (per-thread edge arrays of the SATD kernel use EOFF + 66 at the 32x32 level)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr long long kInf = 0x7fffffffffffffffll;
 
@@ -52,22 +52,32 @@ constexpr long long kInf = 0x7fffffffffffffffll;
 __device__ const uint8_t dv_iscan_g[336] = {
 #include "iscan_init.inc"
 };
-__constant__ const uint8_t dv_sm_weights[4 + 8 + 16] = {255, 149, 85, 64, 255, 197, 146, 105, 73, 50, 37, 32,
-                                                        255, 225, 196, 170, 145, 123, 102, 84, 68, 54, 43, 33, 26, 20, 17, 16};
+__device__ const uint16_t dv_iscan32_g[1024] = {
+#include "iscan32_init.inc"
+};
+__constant__ const uint8_t dv_sm_weights[4 + 8 + 16 + 32] = {255, 149, 85, 64, 255, 197, 146, 105, 73, 50, 37, 32,
+                                                             255, 225, 196, 170, 145, 123, 102, 84, 68, 54, 43, 33, 26, 20, 17, 16,
+                                                             255, 240, 225, 210, 196, 182, 169, 157, 145, 133, 122, 111, 101, 92, 83, 74,
+                                                             66, 59, 52, 45, 39, 34, 29, 25, 21, 17, 14, 12, 10, 9, 8, 8};
 __constant__ const uint8_t dv_tx_types[5] = {TX_DCT_DCT, TX_ADST_DCT, TX_DCT_ADST, TX_ADST_ADST, TX_IDTX};
 
-struct Shared {
-  uint16_t src[3][256];
-  uint16_t above[3][kEdge], left[3][kEdge];
-  uint16_t pred[512];          // luma: predictions of the two ranked modes; chroma: up to four (mode rank, plane) predictions
-  int32_t buf[32 * 17];        // G groups x N rows x (N+1): transform transpose staging
-  alignas(16) uint8_t lev[800];   // per group (N+4)^2 padded |level| map (rate contexts)
-  int16_t qc[512];             // per group n*n quantised levels in scan order
-  uint16_t rec[512];           // per group n*n reconstruction
-  int16_t ac[256];             // CFL: (luma << 3) - average of the block
+// Per-warp working set.  NMAX = largest block size the kernel instance handles (16: 8.7 KB, 32: 22.9 KB).
+template <int NMAX>
+struct SharedT {
+  static constexpr int kMaxN = NMAX;
+  static constexpr int kPredStride = NMAX * NMAX;          // one prediction slot (luma: two ranked modes, two slots)
+  uint16_t src[3][NMAX * NMAX];
+  uint16_t above[3][EOFF + 2 * NMAX + 2], left[3][EOFF + 2 * NMAX + 2];
+  uint16_t pred[2 * NMAX * NMAX];   // luma: predictions of the two ranked modes; chroma: up to G (mode rank, plane) predictions
+  int32_t buf[32 * (NMAX + 1)];     // G groups x N rows x (N+1): transform transpose staging
+  alignas(16) uint8_t lev[NMAX == 32 ? 1296 : 800];   // per group (N+4)^2 padded |level| map (rate contexts)
+  int16_t qc[NMAX == 32 ? 1024 : 512];                // per group n*n quantised levels in scan order
+  uint16_t rec[NMAX == 32 ? 1024 : 512];              // per group n*n reconstruction
+  int16_t ac[NMAX * NMAX];          // CFL: (luma << 3) - average of the block
   uint32_t taskD[6], taskR[6];
   uint16_t taskE[6];
 };
+typedef SharedT<16> Shared;
 
 struct TileCtx {
   const B200Frame *f;
@@ -84,6 +94,11 @@ struct TileCtx {
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int txs_of(int n) { return n == 4 ? 0 : n == 8 ? 1 : n == 16 ? 2 : 3; }
 __device__ __forceinline__ int scan_base(int n) { return n == 4 ? 0 : n == 8 ? 16 : 80; }
+// position -> scan index (tables in global memory, L1 resident: the index diverges per lane)
+template <int N> __device__ __forceinline__ int iscan_at(int pos) {
+  if (N == 32) return __ldg(&dv_iscan32_g[pos]);
+  return __ldg(&dv_iscan_g[scan_base(N) + pos]);
+}
 __device__ __forceinline__ int ilog2_dev(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
 __device__ __noinline__ long long warp_sum_ll(long long v) {
@@ -122,7 +137,8 @@ __device__ __noinline__ int block_avail(const TileCtx &t, int x, int y, int n) {
   const int bl = hl && b200_unit_before(mi_r + n4, mi_c - 1, mi_r, mi_c, t.tr0, t.tr1, t.tc0, t.tc1);
   return ha | (hl << 1) | (ar << 2) | (bl << 3);
 }
-__device__ __noinline__ void build_edges(const TileCtx &t, Shared &sh, const uint16_t *r, int slot, int x, int y, int n, int avail) {
+template <class SH>
+__device__ __noinline__ void build_edges(const TileCtx &t, SH &sh, const uint16_t *r, int slot, int x, int y, int n, int avail) {
   const B200Frame *f = t.f;
   const int st = t.stride, lane = lane_id();
   const int ha = avail & 1, hl = (avail >> 1) & 1, have_ar = (avail >> 2) & 1, have_bl = (avail >> 3) & 1;
@@ -175,7 +191,7 @@ __device__ __forceinline__ int pred_px(int mode, int delta, int n, int i, int j,
     return (pl <= pt && pl <= ptl) ? L[i] : (pt <= ptl ? A[j] : tl);
   }
   if (mode >= SMOOTH_PRED) {   // SMOOTH, SMOOTH_V, SMOOTH_H share the two half sums
-    const uint8_t *w = dv_sm_weights + (n == 4 ? 0 : n == 8 ? 4 : 12);
+    const uint8_t *w = dv_sm_weights + (n == 4 ? 0 : n == 8 ? 4 : n == 16 ? 12 : 28);
     const int v = w[i] * A[j] + (256 - w[i]) * L[n - 1], h = w[j] * L[i] + (256 - w[j]) * A[n - 1];
     return mode == SMOOTH_PRED ? (v + h + 256) >> 9 : (mode == SMOOTH_V_PRED ? (v + 128) >> 8 : (h + 128) >> 8);
   }
@@ -235,7 +251,8 @@ __device__ __forceinline__ void identity_dev(const int32_t *in, int32_t *out) {
   for (int i = 0; i < N; i++) {
     if (N == 4) out[i] = round_shift64((long long)in[i] * 5793, 12);
     else if (N == 8) out[i] = in[i] * 2;
-    else out[i] = round_shift64((long long)in[i] * 2 * 5793, 12);
+    else if (N == 16) out[i] = round_shift64((long long)in[i] * 2 * 5793, 12);
+    else out[i] = in[i] * 4;
   }
 }
 // HBD = false (8-bit video): every half-butterfly w0*a + w1*b fits int32 (DESIGN.md "int32 butterflies"), so the
@@ -244,6 +261,7 @@ template <int N, bool HBD>
 __device__ __forceinline__ void fwd1d(int kind, const int32_t *in, int32_t *out, int bit) {
   const int32_t *c = dv_cospi_arr[bit - 10];
   if (kind == K_IDT) { identity_dev<N>(in, out); return; }
+  if (N == 32) { gen_fdct32(in, out, c, bit); return; }      // 32x32 is DCT (or identity) only
   if (kind == K_DCT) {
     if (HBD) { if (N == 4) gen_fdct4(in, out, c, bit); else if (N == 8) gen_fdct8(in, out, c, bit); else gen_fdct16(in, out, c, bit); }
     else { if (N == 4) gen_fdct4_w32(in, out, c, bit); else if (N == 8) gen_fdct8_w32(in, out, c, bit); else gen_fdct16_w32(in, out, c, bit); }
@@ -258,6 +276,7 @@ __device__ __forceinline__ void inv1d(int kind, const int32_t *in, int32_t *out)
   const int bit = 12;
   const int32_t *c = dv_cospi_arr[bit - 10];
   if (kind == K_IDT) { identity_dev<N>(in, out); return; }
+  if (N == 32) { gen_idct32(in, out, c, bit); return; }
   if (kind == K_DCT) {
     if (HBD) { if (N == 4) gen_idct4(in, out, c, bit); else if (N == 8) gen_idct8(in, out, c, bit); else gen_idct16(in, out, c, bit); }
     else { if (N == 4) gen_idct4_w32(in, out, c, bit); else if (N == 8) gen_idct8_w32(in, out, c, bit); else gen_idct16_w32(in, out, c, bit); }
@@ -285,12 +304,14 @@ __device__ __forceinline__ int32_t clamp_bits(int32_t v, int bits) {
 // each 1-D transform kernel appears once (two-pass loops), and the per-coefficient loops are rolled.
 struct TrialOut { int eob; uint32_t rate, sse; };
 
-template <int N, bool HBD>
-__device__ __noinline__ TrialOut trial_batch(const TileCtx &t, Shared &sh, int plane, const uint16_t *src, const uint16_t *pred,
+template <int N, bool HBD, class SH>
+__device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane, const uint16_t *src, const uint16_t *pred,
                                              int tx_type, int y_mode) {
+  static_assert(N <= SH::kMaxN, "working set too small for this transform size");
   constexpr int S = N + 1, N2 = N * N, LS = N + 4;
-  constexpr int shift1 = N == 4 ? 0 : (N == 8 ? 1 : 2);   // -fwd_shift[1]
-  constexpr int row_shift = N == 4 ? 0 : (N == 8 ? 1 : 2);
+  constexpr int shift1 = N == 4 ? 0 : (N == 8 ? 1 : (N == 16 ? 2 : 4));   // -fwd_shift[1] (libaom fwd_txfm_shift_ls)
+  constexpr int row_shift = N == 4 ? 0 : (N == 8 ? 1 : 2);                // inverse: shift after the row pass
+  constexpr int qshift = N == 32 ? 1 : 0;                                 // 32x32: coefficients are coded at half scale
   const B200Frame *f = t.f;
   const B200RateTables *rt = t.rt;
   const int lane = lane_id(), g = lane / N, l = lane % N;
@@ -298,7 +319,6 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, Shared &sh, int p
   uint8_t *lev = sh.lev + g * LS * LS;
   int16_t *qc = sh.qc + g * N2;
   uint16_t *rec = sh.rec + g * N2;
-  const uint8_t *iscan = dv_iscan_g + scan_base(N);   // position -> scan index (global memory, L1 resident)
   int vert, horz;
   tx_kernels(tx_type, vert, horz);
   const int bd = f->bit_depth;
@@ -314,7 +334,7 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, Shared &sh, int p
 #pragma unroll
       for (int c = 0; c < N; c++) x[c] = buf[l * S + c];
     }
-    fwd1d<N, HBD>(pass == 0 ? vert : horz, x, o, (pass == 1 && N == 16) ? 12 : 13);
+    fwd1d<N, HBD>(pass == 0 ? vert : horz, x, o, (N == 32 || (pass == 1 && N == 16)) ? 12 : 13);   // fwd_cos_bit_col / _row
     if (pass == 0) {
 #pragma unroll
       for (int r = 0; r < N; r++) buf[r * S + l] = rshift_round(o[r], shift1);
@@ -335,14 +355,14 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, Shared &sh, int p
       const uint32_t q = pos == 0 ? dc_q : ac_q, rcp = pos == 0 ? dc_rcp : ac_rcp;
       const uint32_t off = pos == 0 ? (q * 109) >> 8 : (q * 98) >> 8;
       const int32_t cf = buf[l * S + c];
-      const uint32_t a = (uint32_t)(cf < 0 ? -cf : cf) + off;
+      const uint32_t a = ((uint32_t)(cf < 0 ? -cf : cf) << qshift) + off;
       uint32_t lv = __umulhi(a, rcp);           // floor(a / q) or one/two less
       uint32_t rem = a - lv * q;
       if (rem >= q) { lv++; rem -= q; }
       if (rem >= q) lv++;
       if (lv > 32767) lv = 32767;
-      const int32_t dqa = (int32_t)((lv * q) & 0xFFFFFF);
-      const int si = __ldg(&iscan[pos]);
+      const int32_t dqa = (int32_t)((lv * q) & 0xFFFFFF) >> qshift;
+      const int si = iscan_at<N>(pos);
       qc[si] = (int16_t)(cf < 0 ? -(int)lv : (int)lv);
       buf[l * S + c] = cf < 0 ? -dqa : dqa;
       lev[l * LS + c] = (uint8_t)(lv > 127 ? 127 : lv);
@@ -360,7 +380,7 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, Shared &sh, int p
   } else {
     if (l == 0) {
       rate = rt->txb_skip[txs][skip_ctx][0];
-      if (plane == 0) rate += rt->intra_tx[(f->reduced_tx_set || N == 16) ? 1 : 0][txs][y_mode][tx_type];
+      if (plane == 0 && N <= 16) rate += rt->intra_tx[(f->reduced_tx_set || N == 16) ? 1 : 0][txs][y_mode][tx_type];
       int tg = 0;
       while (tg < 11 && (tg == 0 ? 1 : (tg == 1 ? 2 : (1 << (tg - 1)) + 1)) <= eob) tg++;   // group_start[tg + 1] <= eob
       const int gstart = tg < 3 ? tg : (1 << (tg - 2)) + 1;                                 // group_start[tg]
@@ -375,7 +395,7 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, Shared &sh, int p
 #pragma unroll 1
     for (int c = 0; c < N; c++) {
       const int pos = l * N + c;
-      const int si = __ldg(&iscan[pos]);
+      const int si = iscan_at<N>(pos);
       if (si >= eob) continue;
       const int level = abs((int)qc[si]);
       const uint8_t *L = lev + l * LS + c;
@@ -449,11 +469,12 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, Shared &sh, int p
   return o;
 }
 
-template <bool HBD>
-__device__ __forceinline__ TrialOut trial_dispatch(int n, const TileCtx &t, Shared &sh, int plane, const uint16_t *src,
+template <bool HBD, class SH>
+__device__ __forceinline__ TrialOut trial_dispatch(int n, const TileCtx &t, SH &sh, int plane, const uint16_t *src,
                                                    const uint16_t *pred, int tx_type, int y_mode) {
   if (n == 4) return trial_batch<4, HBD>(t, sh, plane, src, pred, tx_type, y_mode);
   if (n == 8) return trial_batch<8, HBD>(t, sh, plane, src, pred, tx_type, y_mode);
+  if (SH::kMaxN >= 32 && n == 32) return trial_batch<(SH::kMaxN >= 32 ? 32 : 16), HBD>(t, sh, plane, src, pred, tx_type, y_mode);
   return trial_batch<16, HBD>(t, sh, plane, src, pred, tx_type, y_mode);
 }
 
@@ -552,9 +573,9 @@ __device__ __forceinline__ void ctx_from_job(const B200RdoJob &job, TileCtx &t) 
 // counts - so that they fetch the same instructions at the same time: the per-block code (~60 KB at 16x16) does not
 // fit the instruction cache and `stall_no_instruction` was the top stall of the free-running kernel (profiles/).
 // `out` == nullptr: a padding warp that repeats a valid block only to take part in the barriers.
-template <int LG, bool HBD, bool SYNC>
-__device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int x, int y, const uint32_t *satd, B200BlockDec *out) {
-  constexpr int lg = LG, n = 1 << LG, N2 = n * n, G = 32 >> LG;
+template <int LG, bool HBD, bool SYNC, class SH>
+__device__ __forceinline__ void analyze_block(const TileCtx &t, SH &sh, int x, int y, const uint32_t *satd, B200BlockDec *out) {
+  constexpr int lg = LG, n = 1 << LG, N2 = n * n, G = 32 >> LG, PS = SH::kPredStride;
   if (SYNC) __syncthreads();
   const B200Frame *f = t.f;
   const B200RateTables *rt = t.rt;
@@ -566,7 +587,7 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
 #pragma unroll 1
     for (int q = lane; q < N2; q += 32) sh.src[p][q] = t.src[p][(y + (q >> lg)) * t.stride + x + (q & (n - 1))];
 #pragma unroll 1
-  for (int i = lane; i < 200; i += 32) reinterpret_cast<uint32_t *>(sh.lev)[i] = 0;
+  for (int i = lane; i < (int)sizeof(sh.lev) / 4; i += 32) reinterpret_cast<uint32_t *>(sh.lev)[i] = 0;
   const int avail = block_avail(t, x, y, n), ha = avail & 1, hl = (avail >> 1) & 1;
 #pragma unroll 1
   for (int p = 0; p < planes; p++) build_edges(t, sh, t.src[p], p, x, y, n, avail);
@@ -587,10 +608,11 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
   int m0, m1;
   rank_top2(my_ycost, m0, m1);
   // ---- luma full trials: candidate c = k * 5 + ti; lane batches pair the two modes on the same transform type
+  const int tx_mask = n == 32 ? 1 : f->tx_type_mask;      // 32x32: the intra transform set is DCT only
   int first_t = -1;
-  for (int k = 0; k < 5; k++) if ((f->tx_type_mask >> k) & 1) { first_t = k; break; }
+  for (int k = 0; k < 5; k++) if ((tx_mask >> k) & 1) { first_t = k; break; }
   predict_block(m0 >= 0 ? m0 : 0, DELTA_Y(m0 >= 0 ? m0 : 0), lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred);
-  predict_block(m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0), DELTA_Y(m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0)), lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred + 256);
+  predict_block(m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0), DELTA_Y(m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0)), lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred + PS);
   __syncwarp();
   long long bestJ = kInf;
   int bestC = 1 << 20, bestEob = 0;
@@ -601,12 +623,12 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
     const int ci = b * G + g;
     const int ti = ci >> 1, k = ci & 1;
     const int m = k == 0 ? m0 : m1;
-    bool ok = ti < 5 && m >= 0 && ((f->tx_type_mask >> ti) & 1) && (f->rdo_tx_decision || ti == first_t);
+    bool ok = ti < 5 && m >= 0 && ((tx_mask >> ti) & 1) && (f->rdo_tx_decision || ti == first_t);
     if (!__ballot_sync(FULL, ok)) continue;
-    const TrialOut r = trial_batch<n, HBD>(t, sh, 0, sh.src[0], sh.pred + (ok ? k : 0) * 256, dv_tx_types[ok ? ti : 0],
+    const TrialOut r = trial_batch<n, HBD>(t, sh, 0, sh.src[0], sh.pred + (ok ? k : 0) * PS, dv_tx_types[ok ? ti : 0],
                                            ok ? m : (m0 >= 0 ? m0 : 0));
     const int gf = first_t * 2 - b * G;        // lane group of (rank 0, first type) in this batch, if it is here
-    if (f->rdo_tx_decision && gf >= 0 && gf < G) {
+    if (G >= 2 && f->rdo_tx_decision && gf >= 0 && gf < G) {
       const int e0 = __shfl_sync(FULL, r.eob, gf << lg), e1 = __shfl_sync(FULL, r.eob, ((gf + 1) << lg) & 31);
       if ((m0 < 0 || e0 == 0) && (m1 < 0 || e1 == 0)) { skip_rest = true; if (ti != first_t) ok = false; }
     }
@@ -699,8 +721,8 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, Shared &sh, int 
 }
 
 // ---- stage C: closed-loop reconstruction of one decided block by one warp (oracle reconstruct_block) ----------------
-template <bool HBD>
-__device__ __noinline__ void reconstruct_block(const TileCtx &t, Shared &sh, int x, int y, int lg) {
+template <bool HBD, class SH>
+__device__ __noinline__ void reconstruct_block(const TileCtx &t, SH &sh, int x, int y, int lg) {
   const int n = 1 << lg, N2 = n * n, G = 32 >> lg;
   const B200Frame *f = t.f;
   const int lane = lane_id(), g = lane >> lg;
@@ -712,7 +734,7 @@ __device__ __noinline__ void reconstruct_block(const TileCtx &t, Shared &sh, int
 #pragma unroll 1
     for (int q = lane; q < N2; q += 32) sh.src[p][q] = t.src[p][(y + (q >> lg)) * t.stride + x + (q & (n - 1))];
 #pragma unroll 1
-  for (int i = lane; i < 200; i += 32) reinterpret_cast<uint32_t *>(sh.lev)[i] = 0;
+  for (int i = lane; i < (int)sizeof(sh.lev) / 4; i += 32) reinterpret_cast<uint32_t *>(sh.lev)[i] = 0;
   const int avail = block_avail(t, x, y, n), ha = avail & 1, hl = (avail >> 1) & 1;
 #pragma unroll 1
   for (int p = 0; p < planes; p++) build_edges(t, sh, t.rec[p], p, x, y, n, avail);
@@ -793,7 +815,7 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
   for (int k = 0; k < items / 128; k++) {
     const int it = k * 128 + threadIdx.x, gid = base + it;
     bool active = gid < total;
-    if (active && lv < 2) {
+    if (active && lv < B200_LEVELS - 1) {
       const int blk = gid % (cols * rows);
       active = !b200_pruned_by_parent(f, lv, blk % cols, blk / cols, job.dec[lv + 1]);   // top-down pruning
     }
@@ -819,7 +841,7 @@ __global__ void __launch_bounds__(128) b200_satd_direct_kernel(const B200RdoJob 
   const int total = b200_level_cols(f, lv) * b200_level_rows(f, lv) * (f->planes > 1 ? 2 : 1);
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
-  if (lv < 2) {
+  if (lv < B200_LEVELS - 1) {
     const int cols = b200_level_cols(f, lv), blk = gid % (cols * b200_level_rows(f, lv));
     if (b200_pruned_by_parent(f, lv, blk % cols, blk / cols, job.dec[lv + 1])) return;
   }
@@ -848,7 +870,7 @@ __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid
   uint32_t acc[19];
 #pragma unroll
   for (int m = 0; m < 19; m++) acc[m] = 0;
-  uint16_t Ab[EOFF + 34], Lb[EOFF + 34];
+  uint16_t Ab[EOFF + 66], Lb[EOFF + 66];       // n <= 32
   uint16_t *A = Ab + EOFF, *L = Lb + EOFF;
   const int p_end = grp == 0 ? 1 : 3;
   int md = -1;
@@ -945,11 +967,13 @@ __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid
 // ---- stage A.2: full trials.  One single-warp CTA loops over blocks of level lv (grid-stride), grid.y = job.
 // W warps per CTA.  W == 1: free-running single-warp CTAs (grid-stride over the blocks).  W > 1 (the never-pruned top
 // level): the W warps of a CTA analyse W different blocks in lock-step (analyze_block<.., SYNC>).
-constexpr int kAnalyzeWarpsTop = 4;
+constexpr int kAnalyzeWarpsTop = 4;      // 16x16 as the top level
+constexpr int kAnalyzeWarpsTop32 = 2;    // 32x32 as the top level (22.9 KB of shared memory per warp)
 template <int LV, bool HBD, int W>
-__global__ void __launch_bounds__(kThreads * W, (LV == 2 ? 16 : 24) / W) b200_analyze_kernel(const B200RdoJob *jobs) {
-  __shared__ Shared shs[W];
-  Shared &sh = shs[threadIdx.x >> 5];
+__global__ void __launch_bounds__(kThreads * W, LV == 3 ? 4 : (LV == 2 ? 16 : 24) / W) b200_analyze_kernel(const B200RdoJob *jobs) {
+  typedef SharedT<(LV == 3 ? 32 : 16)> SH;
+  __shared__ SH shs[W];
+  SH &sh = shs[threadIdx.x >> 5];
   const B200RdoJob &job = jobs[blockIdx.y];
   const B200Frame *f = &job.frame;
   constexpr int lv = LV, n = 4 << LV;
@@ -972,7 +996,7 @@ __global__ void __launch_bounds__(kThreads * W, (LV == 2 ? 16 : 24) / W) b200_an
 #pragma unroll 1
   for (int blk = blockIdx.x; blk < total; blk += gridDim.x) {
     const int x = (blk % cols) * n, y = (blk / cols) * n;
-    if (LV < 2 && b200_pruned_by_parent(f, lv, blk % cols, blk / cols, job.dec[LV < 2 ? LV + 1 : 2])) {
+    if (LV < B200_LEVELS - 1 && b200_pruned_by_parent(f, lv, blk % cols, blk / cols, job.dec[LV < B200_LEVELS - 1 ? LV + 1 : LV])) {
       if (lane_id() == 0) {   // top-down pruning: never split down to this block
         B200BlockDec d;
         d.cost = B200_COST_PRUNED; d.y_mode = 0; d.tx_type = 0; d.uv_mode = 0; d.all_zero = 0; d.angle_y = 0; d.angle_uv = 0;
@@ -996,7 +1020,7 @@ __device__ __forceinline__ long long part_cost0(const B200Frame *f, const B200Ra
 __device__ __forceinline__ void set_mi(const B200RdoJob &job, int x, int y, int n, const B200BlockDec &d) {
   const B200Frame *f = &job.frame;
   B200Mi m;
-  m.bsize = (uint8_t)(n == 4 ? BLOCK_4X4 : n == 8 ? BLOCK_8X8 : BLOCK_16X16);
+  m.bsize = (uint8_t)(n == 4 ? BLOCK_4X4 : n == 8 ? BLOCK_8X8 : n == 16 ? BLOCK_16X16 : BLOCK_32X32);
   m.y_mode = d.y_mode; m.uv_mode = d.uv_mode;
   m.angle = (uint8_t)((d.angle_y ? d.angle_y : 3) | ((d.angle_uv ? d.angle_uv : 3) << 4));
   m.tx_size = (uint8_t)txs_of(n); m.tx_type = d.tx_type; m.flags = 0; m.cfl = 0;
@@ -1010,42 +1034,47 @@ __device__ __forceinline__ const B200BlockDec &dec_at(const B200RdoJob &job, int
 }
 }  // namespace
 
-__global__ void __launch_bounds__(128) b200_decide_kernel(const B200RdoJob *jobs) {
-  const B200RdoJob &job = jobs[blockIdx.y];
+// oracle decide_block(): best RD cost of block (LV, x, y), NONE against SPLIT recursively; commit writes the decisions
+template <int LV>
+__device__ long long decide_block(const B200RdoJob &job, int x, int y, bool commit) {
   const B200Frame *f = &job.frame;
   const B200RateTables *rt = job.rate;
   const int W = f->mi_cols * 4, H = f->mi_rows * 4;
-  const int rcols = (W + 15) >> 4, rrows = (H + 15) >> 4;
+  constexpr int n = 4 << LV;
+  if (x >= W || y >= H) return 0;
+  const bool inside = (x + n <= W) && (y + n <= H);
+  const bool can_none = inside && n <= f->partition_max;
+  const bool can_split = LV > 0 && (f->partition_min < n || !inside);
+  long long j_none = 0, j_split = 0;
+  if (can_none) j_none = dec_at(job, LV, x, y).cost + (LV > 0 ? part_cost0(f, rt, y >> 2, x >> 2, n, 0) : 0);
+  if (LV > 0 && can_split) {
+    j_split = part_cost0(f, rt, y >> 2, x >> 2, n, 1);
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) j_split += decide_block<(LV > 0 ? LV - 1 : 0)>(job, x + (k & 1) * (n >> 1), y + (k >> 1) * (n >> 1), false);
+  }
+  const bool none = can_none && (!can_split || j_none <= j_split);
+  if (commit) {
+    if (none) set_mi(job, x, y, n, dec_at(job, LV, x, y));
+    else if (LV > 0) {
+#pragma unroll 1
+      for (int k = 0; k < 4; k++) decide_block<(LV > 0 ? LV - 1 : 0)>(job, x + (k & 1) * (n >> 1), y + (k >> 1) * (n >> 1), true);
+    }
+  }
+  return none ? j_none : j_split;
+}
+
+// one thread per root region: 32x32 when the partition range reaches it, else 16x16
+__global__ void __launch_bounds__(128) b200_decide_kernel(const B200RdoJob *jobs) {
+  const B200RdoJob &job = jobs[blockIdx.y];
+  const B200Frame *f = &job.frame;
+  const int W = f->mi_cols * 4, H = f->mi_rows * 4;
+  const int root = f->partition_max >= 32 ? 3 : 2, rn = 4 << root;
+  const int rcols = (W + rn - 1) / rn, rrows = (H + rn - 1) / rn;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= rcols * rrows) return;
-  const int x = (gid % rcols) * 16, y = (gid / rcols) * 16;
-  const bool inside = (x + 16 <= W) && (y + 16 <= H);
-  const bool can_none = inside && f->partition_max >= 16;
-  const bool can_split = f->partition_min < 16 || !inside;
-  long long j_split = part_cost0(f, rt, y >> 2, x >> 2, 16, 1);
-  int split8 = 0;
-  for (int k = 0; k < 4; k++) {
-    const int xx = x + (k & 1) * 8, yy = y + (k >> 1) * 8;
-    if (xx >= W || yy >= H) continue;
-    const long long j8 = dec_at(job, 1, xx, yy).cost + part_cost0(f, rt, yy >> 2, xx >> 2, 8, 0);
-    long long best = j8;
-    if (f->partition_min < 8) {
-      long long j4 = part_cost0(f, rt, yy >> 2, xx >> 2, 8, 1);
-      for (int q = 0; q < 4; q++) j4 += dec_at(job, 0, xx + (q & 1) * 4, yy + (q >> 1) * 4).cost;
-      if (!(j8 <= j4)) { best = j4; split8 |= 1 << k; }
-    }
-    j_split += best;
-  }
-  if (can_none && (!can_split || dec_at(job, 2, x, y).cost + part_cost0(f, rt, y >> 2, x >> 2, 16, 0) <= j_split)) {
-    set_mi(job, x, y, 16, dec_at(job, 2, x, y));
-    return;
-  }
-  for (int k = 0; k < 4; k++) {
-    const int xx = x + (k & 1) * 8, yy = y + (k >> 1) * 8;
-    if (xx >= W || yy >= H) continue;
-    if (!((split8 >> k) & 1)) set_mi(job, xx, yy, 8, dec_at(job, 1, xx, yy));
-    else for (int q = 0; q < 4; q++) set_mi(job, xx + (q & 1) * 4, yy + (q >> 1) * 4, 4, dec_at(job, 0, xx + (q & 1) * 4, yy + (q >> 1) * 4));
-  }
+  const int x = (gid % rcols) * rn, y = (gid / rcols) * rn;
+  if (root == 3) decide_block<3>(job, x, y, true);
+  else decide_block<2>(job, x, y, true);
 }
 
 // ---- stage C: one CTA per tile, kReconWarps warps on a superblock-row wavefront.  Warp w owns the tile's SB rows
@@ -1059,10 +1088,13 @@ constexpr int kMaxSbRows = 1024;     // 65536 / 64
 #else
 #define B200_SPIN_WAIT() __nanosleep(40)
 #endif
-template <bool HBD>
-__global__ void __launch_bounds__(kThreads * kReconWarps, 4) b200_recon_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
-  __shared__ Shared shs[kReconWarps];
-  __shared__ volatile int sb_done[kMaxSbRows];      // superblocks finished in each SB row of this tile
+// NMAX = 32 (partition range up to 32x32): 2 warps per tile, 22.9 KB of shared memory each
+template <bool HBD, int NMAX>
+__global__ void __launch_bounds__(kThreads * (NMAX == 32 ? 2 : kReconWarps), NMAX == 32 ? 4 : 4) b200_recon_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
+  constexpr int kWarps = NMAX == 32 ? 2 : kReconWarps;
+  typedef SharedT<NMAX> SH;
+  __shared__ SH shs[kWarps];
+  __shared__ volatile unsigned short sb_done[kMaxSbRows];      // superblocks finished in each SB row of this tile (<= 1024 columns)
   const B200TileRef tr = tiles[blockIdx.x];
   const B200RdoJob &job = jobs[tr.job];
   TileCtx t;
@@ -1076,15 +1108,15 @@ __global__ void __launch_bounds__(kThreads * kReconWarps, 4) b200_recon_kernel(c
   for (int i = threadIdx.x; i < sb_rows; i += blockDim.x) sb_done[i] = 0;
   __syncthreads();
   const int warp = threadIdx.x >> 5;
-  Shared &sh = shs[warp];
+  SH &sh = shs[warp];
 #pragma unroll 1
-  for (int R = warp; R < sb_rows; R += kReconWarps) {
+  for (int R = warp; R < sb_rows; R += kWarps) {
     const int r = t.tr0 + R * 16;
 #pragma unroll 1
     for (int C = 0; C < sb_cols; C++) {
       if (R > 0) {
         const int need = min(C + 2, sb_cols);
-        while (sb_done[R - 1] < need) B200_SPIN_WAIT();
+        while ((int)sb_done[R - 1] < need) B200_SPIN_WAIT();
         __syncwarp();
         __threadfence_block();
       }
@@ -1096,13 +1128,13 @@ __global__ void __launch_bounds__(kThreads * kReconWarps, 4) b200_recon_kernel(c
         const int mr = r + ur, mc = c + uc;
         if (mr >= f->mi_rows || mc >= f->mi_cols) { z++; continue; }
         const int bs = t.mi[mr * f->mi_cols + mc].bsize;
-        const int lg = bs == BLOCK_4X4 ? 2 : (bs == BLOCK_8X8 ? 3 : 4);
+        const int lg = bs == BLOCK_4X4 ? 2 : (bs == BLOCK_8X8 ? 3 : (bs == BLOCK_16X16 ? 4 : 5));
         reconstruct_block<HBD>(t, sh, mc * 4, mr * 4, lg);
         z += 1 << (2 * (lg - 2));           // a block covers (n/4)^2 consecutive z indices
       }
       __threadfence_block();               // the reconstruction of this SB is visible before the counter moves
       __syncwarp();
-      if (lane_id() == 0) sb_done[R] = C + 1;
+      if (lane_id() == 0) sb_done[R] = (unsigned short)(C + 1);
     }
   }
 }
@@ -1112,7 +1144,7 @@ __global__ void __launch_bounds__(kThreads * kReconWarps, 4) b200_recon_kernel(c
 // recorded behind stage B, may be null when both streams are the same).  The caller overlaps the low-parallelism
 // reconstruction chain of one chunk with the analysis of the next by giving stream_recon a higher priority.
 extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200TileRef *d_tiles, int n_tiles, int max_blocks4,
-                               int high_bitdepth, void *stream, void *stream_recon, void *analysis_done) {
+                               int high_bitdepth, int top_level, void *stream, void *stream_recon, void *analysis_done) {
   if (n_tiles <= 0 || n_jobs <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   static bool configured = false;
@@ -1121,39 +1153,38 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     B200_CARVE((b200_analyze_kernel<0, false, 1>)); B200_CARVE((b200_analyze_kernel<1, false, 1>)); B200_CARVE((b200_analyze_kernel<2, false, 1>));
     B200_CARVE((b200_analyze_kernel<0, true, 1>)); B200_CARVE((b200_analyze_kernel<1, true, 1>)); B200_CARVE((b200_analyze_kernel<2, true, 1>));
     B200_CARVE((b200_analyze_kernel<2, false, kAnalyzeWarpsTop>)); B200_CARVE((b200_analyze_kernel<2, true, kAnalyzeWarpsTop>));
-    cudaFuncSetAttribute(b200_recon_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(b200_recon_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    B200_CARVE((b200_analyze_kernel<3, false, kAnalyzeWarpsTop32>)); B200_CARVE((b200_analyze_kernel<3, true, kAnalyzeWarpsTop32>));
+    B200_CARVE((b200_recon_kernel<false, 16>)); B200_CARVE((b200_recon_kernel<true, 16>));
+    B200_CARVE((b200_recon_kernel<false, 32>)); B200_CARVE((b200_recon_kernel<true, 32>));
     configured = true;
   }
-  for (int lv = 2; lv >= 0; lv--) {   // large to small: 4x4 analysis is pruned by its 8x8 parent
+  const int top = top_level >= 3 ? 3 : 2;
+  for (int lv = top; lv >= 0; lv--) {   // large to small: every level is pruned by its parent level
     const int nblk = max_blocks4 >> (2 * lv);
+    if (nblk == 0) continue;
     // the top level is never pruned: one item per thread; lower levels are mostly pruned: compact 512 items per CTA
-    static const int satd_mode = getenv("B200AVIF_SATD_MODE") ? atoi(getenv("B200AVIF_SATD_MODE")) : 0;    // experiments
-    if ((lv == 2 && satd_mode != 1) || satd_mode == 2) {
+    if (lv == top) {
       dim3 gs((nblk * 2 + 127) / 128, n_jobs);
       b200_satd_direct_kernel<<<gs, 128, 0, st>>>(d_jobs, lv);
     } else {
-      const int items = lv == 2 ? 128 : kSatdItems;
-      dim3 gs((nblk * 2 + items - 1) / items, n_jobs);
-      b200_satd_kernel<<<gs, 128, 0, st>>>(d_jobs, lv, items);
+      dim3 gs((nblk * 2 + kSatdItems - 1) / kSatdItems, n_jobs);
+      b200_satd_kernel<<<gs, 128, 0, st>>>(d_jobs, lv, kSatdItems);
     }
     // enough warps to fill the machine several times over, grid-stride inside
     const int per_job = min(nblk, max(1, (148 * 16 * 4) / n_jobs));
     dim3 ga(per_job, n_jobs);
-    static const int top_warps = getenv("B200AVIF_TOP_WARPS") ? atoi(getenv("B200AVIF_TOP_WARPS")) : kAnalyzeWarpsTop;
-    if (lv == 2 && top_warps > 1) {
+#define B200_ANALYZE(LV, W, GRID) \
+    do { if (high_bitdepth) b200_analyze_kernel<LV, true, W><<<GRID, kThreads * W, 0, st>>>(d_jobs); \
+         else b200_analyze_kernel<LV, false, W><<<GRID, kThreads * W, 0, st>>>(d_jobs); } while (0)
+    if (lv == 3) {
+      dim3 gt((per_job + kAnalyzeWarpsTop32 - 1) / kAnalyzeWarpsTop32, n_jobs);
+      B200_ANALYZE(3, kAnalyzeWarpsTop32, gt);
+    } else if (lv == 2 && top == 2) {      // never pruned: lock-step CTAs
       dim3 gt((per_job + kAnalyzeWarpsTop - 1) / kAnalyzeWarpsTop, n_jobs);
-      if (high_bitdepth) b200_analyze_kernel<2, true, kAnalyzeWarpsTop><<<gt, kThreads * kAnalyzeWarpsTop, 0, st>>>(d_jobs);
-      else b200_analyze_kernel<2, false, kAnalyzeWarpsTop><<<gt, kThreads * kAnalyzeWarpsTop, 0, st>>>(d_jobs);
-    } else if (high_bitdepth) {
-      if (lv == 0) b200_analyze_kernel<0, true, 1><<<ga, kThreads, 0, st>>>(d_jobs);
-      else if (lv == 1) b200_analyze_kernel<1, true, 1><<<ga, kThreads, 0, st>>>(d_jobs);
-      else b200_analyze_kernel<2, true, 1><<<ga, kThreads, 0, st>>>(d_jobs);
-    } else {
-      if (lv == 0) b200_analyze_kernel<0, false, 1><<<ga, kThreads, 0, st>>>(d_jobs);
-      else if (lv == 1) b200_analyze_kernel<1, false, 1><<<ga, kThreads, 0, st>>>(d_jobs);
-      else b200_analyze_kernel<2, false, 1><<<ga, kThreads, 0, st>>>(d_jobs);
-    }
+      B200_ANALYZE(2, kAnalyzeWarpsTop, gt);
+    } else if (lv == 2) B200_ANALYZE(2, 1, ga);
+    else if (lv == 1) B200_ANALYZE(1, 1, ga);
+    else B200_ANALYZE(0, 1, ga);
   }
   dim3 gd((max_blocks4 / 16 + 64 + 127) / 128, n_jobs);
   b200_decide_kernel<<<gd, 128, 0, st>>>(d_jobs);
@@ -1162,35 +1193,53 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     cudaEventRecord((cudaEvent_t)analysis_done, st);
     if (sr != st) cudaStreamWaitEvent(sr, (cudaEvent_t)analysis_done, 0);
   }
-  if (high_bitdepth) b200_recon_kernel<true><<<n_tiles, kThreads * kReconWarps, 0, sr>>>(d_jobs, d_tiles);
-  else b200_recon_kernel<false><<<n_tiles, kThreads * kReconWarps, 0, sr>>>(d_jobs, d_tiles);
+  if (top == 3) {
+    if (high_bitdepth) b200_recon_kernel<true, 32><<<n_tiles, kThreads * 2, 0, sr>>>(d_jobs, d_tiles);
+    else b200_recon_kernel<false, 32><<<n_tiles, kThreads * 2, 0, sr>>>(d_jobs, d_tiles);
+  } else {
+    if (high_bitdepth) b200_recon_kernel<true, 16><<<n_tiles, kThreads * kReconWarps, 0, sr>>>(d_jobs, d_tiles);
+    else b200_recon_kernel<false, 16><<<n_tiles, kThreads * kReconWarps, 0, sr>>>(d_jobs, d_tiles);
+  }
   return (int)cudaGetLastError();
 }
 #else
 static const B200RdoJob *g_emu_jobs;
 static const B200TileRef *g_emu_tiles;
-static int g_emu_lv;
-static void emu_satd(void *) { b200_satd_kernel(g_emu_jobs, g_emu_lv, g_emu_lv == 2 ? 128 : kSatdItems); }
+static int g_emu_lv, g_emu_top;
+static void emu_satd(void *) {
+  if (g_emu_lv == g_emu_top) b200_satd_direct_kernel(g_emu_jobs, g_emu_lv);
+  else b200_satd_kernel(g_emu_jobs, g_emu_lv, kSatdItems);
+}
 static void emu_analyze(void *) {
   const bool hbd = g_emu_jobs[0].frame.bit_depth > 8;
-  if (g_emu_lv == 0) { if (hbd) b200_analyze_kernel<0, true, 1>(g_emu_jobs); else b200_analyze_kernel<0, false, 1>(g_emu_jobs); }
-  else if (g_emu_lv == 1) { if (hbd) b200_analyze_kernel<1, true, 1>(g_emu_jobs); else b200_analyze_kernel<1, false, 1>(g_emu_jobs); }
-  else { if (hbd) b200_analyze_kernel<2, true, kAnalyzeWarpsTop>(g_emu_jobs); else b200_analyze_kernel<2, false, kAnalyzeWarpsTop>(g_emu_jobs); }
+#define EMU_ANALYZE(LV, W) do { if (hbd) b200_analyze_kernel<LV, true, W>(g_emu_jobs); else b200_analyze_kernel<LV, false, W>(g_emu_jobs); } while (0)
+  if (g_emu_lv == 0) EMU_ANALYZE(0, 1);
+  else if (g_emu_lv == 1) EMU_ANALYZE(1, 1);
+  else if (g_emu_lv == 2 && g_emu_top == 2) EMU_ANALYZE(2, kAnalyzeWarpsTop);
+  else if (g_emu_lv == 2) EMU_ANALYZE(2, 1);
+  else EMU_ANALYZE(3, kAnalyzeWarpsTop32);
 }
 static void emu_decide(void *) { b200_decide_kernel(g_emu_jobs); }
-static void emu_recon(void *) { if (g_emu_jobs[0].frame.bit_depth > 8) b200_recon_kernel<true>(g_emu_jobs, g_emu_tiles); else b200_recon_kernel<false>(g_emu_jobs, g_emu_tiles); }
+static void emu_recon(void *) {
+  const bool hbd = g_emu_jobs[0].frame.bit_depth > 8;
+  if (g_emu_top == 3) { if (hbd) b200_recon_kernel<true, 32>(g_emu_jobs, g_emu_tiles); else b200_recon_kernel<false, 32>(g_emu_jobs, g_emu_tiles); }
+  else { if (hbd) b200_recon_kernel<true, 16>(g_emu_jobs, g_emu_tiles); else b200_recon_kernel<false, 16>(g_emu_jobs, g_emu_tiles); }
+}
 extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *tiles, int n_tiles) {
   g_emu_jobs = jobs; g_emu_tiles = tiles;
   const B200Frame *f = &jobs[0].frame;
   const int nblk4 = f->mi_rows * f->mi_cols;
-  for (g_emu_lv = 2; g_emu_lv >= 0; g_emu_lv--) {
+  g_emu_top = f->partition_max >= 32 ? 3 : 2;
+  for (g_emu_lv = g_emu_top; g_emu_lv >= 0; g_emu_lv--) {
     const int nblk = (f->mi_rows >> g_emu_lv) * (f->mi_cols >> g_emu_lv);
     if (nblk == 0) continue;
-    emu::launch(emu_satd, nullptr, (unsigned)((nblk * 2 + (g_emu_lv == 2 ? 128 : kSatdItems) - 1) / (g_emu_lv == 2 ? 128 : kSatdItems)), 128);
-    emu::launch(emu_analyze, nullptr, (unsigned)std::min(nblk, g_emu_lv == 2 ? 3 : 7), g_emu_lv == 2 ? kThreads * kAnalyzeWarpsTop : kThreads);
+    const int items = g_emu_lv == g_emu_top ? 128 : kSatdItems;
+    emu::launch(emu_satd, nullptr, (unsigned)((nblk * 2 + items - 1) / items), 128);
+    const int w = g_emu_lv == 3 ? kAnalyzeWarpsTop32 : ((g_emu_lv == 2 && g_emu_top == 2) ? kAnalyzeWarpsTop : 1);
+    emu::launch(emu_analyze, nullptr, (unsigned)std::min(nblk, w > 1 ? 3 : 7), kThreads * w);
   }
   emu::launch(emu_decide, nullptr, (unsigned)((nblk4 / 16 + 64 + 127) / 128), 128);
-  emu::launch(emu_recon, nullptr, (unsigned)n_tiles, kThreads * kReconWarps);
+  emu::launch(emu_recon, nullptr, (unsigned)n_tiles, kThreads * (g_emu_top == 3 ? 2 : kReconWarps));
   return 0;
 }
 #endif

@@ -17,8 +17,8 @@ typedef struct B200RdoJob {
   B200Mi *mi;
   uint16_t *eob[3];
   int16_t *coef[3];
-  B200BlockDec *dec[3];   // analysis decisions per level (0: 4x4, 1: 8x8, 2: 16x16), b200_level_rows*cols entries
-  uint32_t *satd[3];      // SATD tables per level: [block][2 (Y, U+V)][13 modes]
+  B200BlockDec *dec[B200_LEVELS];   // analysis decisions per level (0: 4x4 .. 3: 32x32), b200_level_rows*cols entries
+  uint32_t *satd[B200_LEVELS];      // SATD tables per level: [block][2 (Y, U+V)][14 words]
   // in-loop filter stage (filters.cu): rec is deblocked IN PLACE; cdef_idx receives the per-superblock
   // strength index (-1: nothing coded in the superblock); fin (optional, may be NULL) receives the CDEF output.
   int8_t *cdef_idx;       // sb_rows*sb_cols
@@ -37,7 +37,7 @@ typedef struct B200TileRef {
 // All RDO stages for all jobs on `stream`: SATD + analysis per level, partition decision, reconstruction chain
 // (one warp per tile).  max_blocks4 = largest mi_rows*mi_cols over the jobs; high_bitdepth: all jobs are 10-bit.
 int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200TileRef *d_tiles, int n_tiles, int max_blocks4,
-                    int high_bitdepth, void *stream, void *stream_recon, void *analysis_done);
+                    int high_bitdepth, int top_level /* 2: 16x16, 3: 32x32 */, void *stream, void *stream_recon, void *analysis_done);
 // Deblock (2 launches) + CDEF search (1 launch) + loop-restoration search (1 launch when with_lr) for all jobs: grid.y = job.
 int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, int with_lr, void *stream);
 

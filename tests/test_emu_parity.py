@@ -10,7 +10,7 @@ import harness as H
 class RdoJob(ctypes.Structure):
     _fields_ = [("frame", H.B200Frame), ("rate", ctypes.c_void_p), ("src", ctypes.c_void_p * 3), ("rec", ctypes.c_void_p * 3),
                 ("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3),
-                ("dec", ctypes.c_void_p * 3), ("satd", ctypes.c_void_p * 3),
+                ("dec", ctypes.c_void_p * H.LEVELS), ("satd", ctypes.c_void_p * H.LEVELS),
                 ("cdef_idx", ctypes.c_void_p), ("fin", ctypes.c_void_p * 3),
                 ("lr", ctypes.c_void_p * 3), ("lr_out", ctypes.c_void_p * 3)]
 
@@ -41,7 +41,7 @@ def compare(ref, out, planes):
 
 def compare_analysis(ref, out, f):
     """stage A outputs: SATD tables and per-block decisions of every analysed level"""
-    for lv in range(3):
+    for lv in range(H.LEVELS):
         n = 4 << lv
         if n < min(f.partition_min, 8) or n > f.partition_max:
             continue
@@ -58,6 +58,8 @@ def compare_analysis(ref, out, f):
     (96, 80, 8, 3, 1, dict(split_gates=(44, 96))),       # early termination gates of the fast presets
     (161, 100, 8, 3, 1, dict(lr=1, partition_min=8)),    # loop restoration: odd sizes, merged last unit row, two stripes
     (95, 70, 10, 1, 1, dict(lr=1, partition_min=16)),    # one 95-wide unit, 10 bit, monochrome
+    (136, 104, 8, 3, 1, dict(partition_max=32)),         # 32x32 level on top (partition range of speed <= 2)
+    (96, 64, 10, 3, 1, dict(partition_max=32, partition_min=8, lr=1)),
       # 4 x 3 superblocks: the reconstruction wavefront waits on its neighbours
 ])
 def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
@@ -83,7 +85,7 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
         job.src[p] = src3[p].ctypes.data; job.rec[p] = out.rec[p].ctypes.data
         job.eob[p] = out.eob[p].ctypes.data; job.coef[p] = out.coef[p].ctypes.data
     job.mi = out.mi.ctypes.data
-    for lv in range(3):
+    for lv in range(H.LEVELS):
         job.dec[lv] = out.dec[lv].ctypes.data; job.satd[lv] = out.satd[lv].ctypes.data
     nt = f.tile_cols * f.tile_rows
     trs = (TileRef * nt)()

@@ -25,7 +25,7 @@ def device_rdo(f, src):
     src3 = list(src) + [src[0]] * (3 - len(src))
     out.lr_out = [np.zeros_like(r) for r in out.rec]
     rc = L.b200av1_rdo_run(ctypes.byref(f), H.ptr3(src3), out.mi.ctypes.data, H.ptr3(out.eob), H.ptr3(out.coef), H.ptr3(out.rec),
-                           H.ptr3(out.deblocked), H.ptr3(out.final), out.cdef_idx.ctypes.data, H.ptr3(out.dec), H.ptr3(out.satd),
+                           H.ptr3(out.deblocked), H.ptr3(out.final), out.cdef_idx.ctypes.data, H.ptrn(out.dec), H.ptrn(out.satd),
                            H.ptr3(out.lr), H.ptr3(out.lr_out))
     assert rc == 0, L.b200avif_last_error_message()
     return out
@@ -33,7 +33,7 @@ def device_rdo(f, src):
 
 def check_analysis(ref, out, f):
     """stage A: SATD tables and per-block decisions (cost, modes, transform type) of every analysed level"""
-    for lv in range(3):
+    for lv in range(H.LEVELS):
         n = 4 << lv
         if n < min(f.partition_min, 8) or n > f.partition_max:
             continue
@@ -152,6 +152,9 @@ CASES = [
     (161, 100, 10, 3, 147, 2, dict(lr=1)),                     # odd sizes, two tiles
     (95, 95, 8, 1, 100, 1, dict(lr=1)),                        # one unit larger than 64 x 64, monochrome
     (640, 360, 10, 3, 66, 4, dict(lr=1, split_gates=(44, 96))),
+    (256, 256, 8, 3, 180, 1, dict(partition_max=32)),           # 32x32 level (speed <= 2)
+    (200, 136, 10, 3, 150, 2, dict(partition_max=32, lr=1)),
+    (384, 320, 8, 3, 220, 4, dict(partition_max=32, partition_min=8)),
 ]
 
 
