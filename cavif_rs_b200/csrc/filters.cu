@@ -191,6 +191,39 @@ __device__ __forceinline__ int cdef_pixel(const uint16_t *I, int stride, int W, 
     }
   return clip3_d(mn, mx, x + ((8 + sum - (sum < 0)) >> 4));
 }
+// Same filter on a staged (64 + 4)^2 tile of the superblock (kCdefTW samples per row, 2-sample border, kCdefNA marks
+// samples outside the frame): lx, ly = position inside the superblock.
+constexpr int kCdefTW = 68;
+constexpr uint16_t kCdefNA = 0xFFFF;
+__device__ __forceinline__ int cdef_pixel_tile(const uint16_t *T, int lx, int ly, int pri, int sec, int dir, int damping, int cshift) {
+  const uint16_t *c = T + (ly + 2) * kCdefTW + lx + 2;
+  const int x = *c;
+  if (!pri && !sec) return x;
+  const int pt0 = ((pri >> cshift) & 1) ? 3 : 4, pt1 = ((pri >> cshift) & 1) ? 3 : 2;
+  int sum = 0, mx = x, mn = x;
+#pragma unroll
+  for (int k = 0; k < 2; k++)
+#pragma unroll
+    for (int sgn = -1; sgn <= 1; sgn += 2) {
+      {
+        const int v = c[sgn * (dv_cdef_dir[dir][k][0] * kCdefTW + dv_cdef_dir[dir][k][1])];
+        if (v != kCdefNA) {
+          sum += (k == 0 ? pt0 : pt1) * constrain_d(v - x, pri, damping);
+          mx = max(mx, v); mn = min(mn, v);
+        }
+      }
+#pragma unroll
+      for (int doff = -2; doff <= 2; doff += 4) {
+        const int d2 = (dir + doff) & 7;
+        const int v = c[sgn * (dv_cdef_dir[d2][k][0] * kCdefTW + dv_cdef_dir[d2][k][1])];
+        if (v != kCdefNA) {
+          sum += (k == 0 ? 2 : 1) * constrain_d(v - x, sec, damping);
+          mx = max(mx, v); mn = min(mn, v);
+        }
+      }
+    }
+  return clip3_d(mn, mx, x + ((8 + sum - (sum < 0)) >> 4));
+}
 // ---- loop restoration: self-guided filter parameter search (oracle/av1_restoration.c orc_lr_search_plane) ----------
 // One CTA (256 threads) per (restoration unit, plane); grid.y = job, grid.z = plane.  The unit is walked stripe by
 // stripe and in bands of 16 rows: a band's samples (CDEF output inside the stripe, deblocked rows outside it, AV1
@@ -462,8 +495,14 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
   __shared__ int s_dir[64], s_var[64], s_skip[64], s_any;
   __shared__ unsigned long long s_sse[8];
   __shared__ int s_best;
+  __shared__ uint16_t s_px[3][kCdefTW * kCdefTW];     // deblocked samples of the superblock + 2-sample border, per plane
   if (tid == 0) s_any = 0;
   if (tid < 8) s_sse[tid] = 0;
+  for (int p = 0; p < f->planes; p++)
+    for (int i = tid; i < kCdefTW * kCdefTW; i += 256) {
+      const int yy = sbr * 64 + i / kCdefTW - 2, xx = sbc * 64 + i % kCdefTW - 2;
+      s_px[p][i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? job.rec[p][yy * stride + xx] : kCdefNA;
+    }
   __syncthreads();
   if (tid < 64) {
     const int r = sbr * 16 + (tid >> 3) * 2, c = sbc * 16 + (tid & 7) * 2;
@@ -471,7 +510,7 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
     if (r < f->mi_rows && c < f->mi_cols) {
       const B200Mi *m = &job.mi[r * f->mi_cols + c];
       skip = (m[0].flags & 1) && (m[1].flags & 1) && (m[f->mi_cols].flags & 1) && (m[f->mi_cols + 1].flags & 1);
-      if (!skip) { cdef_direction(job.rec[0] + r * 4 * stride + c * 4, stride, bd, &s_dir[tid], &s_var[tid]); s_any = 1; }
+      if (!skip) { cdef_direction(&s_px[0][((tid >> 3) * 8 + 2) * kCdefTW + (tid & 7) * 8 + 2], kCdefTW, bd, &s_dir[tid], &s_var[tid]); s_any = 1; }
     }
     s_skip[tid] = skip;
   }
@@ -508,7 +547,7 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
       if (sec == 3) sec = 4;
       sec <<= cshift;
       const int damping = f->cdef_damping + cshift - (p > 0);
-      const uint16_t *I = job.rec[p];
+      const uint16_t *T = s_px[p];
       const uint16_t *S = job.src[p];
       for (int i = tid; i < 4096; i += 256) {
         const int ly = i >> 6, lx = i & 63;
@@ -516,7 +555,7 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
         if (y0 >= H || x0 >= W) continue;
         const int b = (ly >> 3) * 8 + (lx >> 3);
         int v;
-        if (s_skip[b]) v = I[y0 * stride + x0];
+        if (s_skip[b]) v = T[(ly + 2) * kCdefTW + lx + 2];
         else {
           int pri = pri0;
           const int dir = pri == 0 ? 0 : s_dir[b];
@@ -525,7 +564,7 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
             const int ii = (var >> 6) ? min(floor_log2_d((unsigned)(var >> 6)), 12) : 0;
             pri = var ? (pri * (4 + ii) + 8) >> 4 : 0;
           }
-          v = cdef_pixel(I, stride, W, H, x0, y0, pri, sec, dir, damping, cshift);
+          v = cdef_pixel_tile(T, lx, ly, pri, sec, dir, damping, cshift);
           const int d = v - (int)S[y0 * stride + x0];
           sse += (unsigned long long)(d * d);
         }

@@ -304,7 +304,8 @@ __device__ __forceinline__ int32_t clamp_bits(int32_t v, int bits) {
 // each 1-D transform kernel appears once (two-pass loops), and the per-coefficient loops are rolled.
 struct TrialOut { int eob; uint32_t rate, sse; };
 
-template <int N, bool HBD, class SH>
+// RATE = false (reconstruction stage): the coefficient-rate model is skipped, TrialOut.rate is 0.
+template <int N, bool HBD, class SH, bool RATE = true>
 __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane, const uint16_t *src, const uint16_t *pred,
                                              int tx_type, int y_mode) {
   static_assert(N <= SH::kMaxN, "working set too small for this transform size");
@@ -375,7 +376,8 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
   const int txs = txs_of(N), ptype = plane > 0;
   const int skip_ctx = plane == 0 ? 0 : 7;
   uint32_t rate = 0;
-  if (eob == 0) {
+  if (!RATE) {
+  } else if (eob == 0) {
     if (l == 0) rate = rt->txb_skip[txs][skip_ctx][1];
   } else {
     if (l == 0) {
@@ -419,7 +421,7 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
       if (level) rate += (si == 0) ? rt->dc_sign[ptype][0][qc[si] < 0] : 256u;
     }
   }
-  rate = group_sum<N>(rate);
+  if (RATE) rate = group_sum<N>(rate);
   // ---- inverse (AV1 spec 7.13.3): pass 0 = row l (buf -> buf), pass 1 = column l -> reconstruction + SSE
   uint32_t sse = 0;
   if (eob) {
@@ -472,10 +474,11 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
 template <bool HBD, class SH>
 __device__ __forceinline__ TrialOut trial_dispatch(int n, const TileCtx &t, SH &sh, int plane, const uint16_t *src,
                                                    const uint16_t *pred, int tx_type, int y_mode) {
-  if (n == 4) return trial_batch<4, HBD>(t, sh, plane, src, pred, tx_type, y_mode);
-  if (n == 8) return trial_batch<8, HBD>(t, sh, plane, src, pred, tx_type, y_mode);
-  if (SH::kMaxN >= 32 && n == 32) return trial_batch<(SH::kMaxN >= 32 ? 32 : 16), HBD>(t, sh, plane, src, pred, tx_type, y_mode);
-  return trial_batch<16, HBD>(t, sh, plane, src, pred, tx_type, y_mode);
+  // only the reconstruction stage dispatches on a run-time size, and it does not need the rate
+  if (n == 4) return trial_batch<4, HBD, SH, false>(t, sh, plane, src, pred, tx_type, y_mode);
+  if (n == 8) return trial_batch<8, HBD, SH, false>(t, sh, plane, src, pred, tx_type, y_mode);
+  if (SH::kMaxN >= 32 && n == 32) return trial_batch<(SH::kMaxN >= 32 ? 32 : 16), HBD, SH, false>(t, sh, plane, src, pred, tx_type, y_mode);
+  return trial_batch<16, HBD, SH, false>(t, sh, plane, src, pred, tx_type, y_mode);
 }
 
 __device__ __forceinline__ long long rd_cost(const B200Frame *f, unsigned long long sse, uint32_t rate) {

@@ -91,6 +91,10 @@ def encode_rgba(rgba, quality=80.0, speed=4, depth=10, alpha_quality=80.0, color
         out = np.zeros_like(a)
         if L.orc_blurred_dirty_alpha(a.ctypes.data, w, h, w, out.ctypes.data):
             a = out
+    elif ch == 4 and alpha_mode == 2:      # AlphaColorMode::Premultiplied (av1encoder.rs:277-299)
+        out = np.zeros_like(a)
+        L.orc_premultiplied_branch(a.ctypes.data, w, h, w, out.ctypes.data)
+        a = out
     q = L.orc_quality_to_quantizer(quality)
     aq = L.orc_quality_to_quantizer(alpha_quality)
     planes, alpha, anya = convert(a, depth, color_model)

@@ -83,7 +83,9 @@ def test_testimage_like_cli_config_1():   # BASELINE config #1: 128x85 opaque, q
     assert 10 * np.log10(255 ** 2 / mse) > 30
 
 
-@pytest.mark.parametrize("depth,alpha,speed,quality", [(8, False, 4, 80.0), (10, True, 6, 60.0), (10, False, 4, 90.0)])
+@pytest.mark.parametrize("depth,alpha,speed,quality", [(8, False, 4, 80.0), (10, True, 6, 60.0), (10, False, 4, 90.0),
+                                                       (10, False, 2, 90.0),      # speed 2: partition range 4..32, exhaustive
+                                                       (8, True, 1, 70.0), (8, False, 10, 40.0)])
 def test_api_payload_identical_to_cpu_pipeline(depth, alpha, speed, quality):
     """Same input through (device path via C ABI) and (oracle hot path + host packer): identical AV1 payload bytes."""
     import cpu_encode as CE
@@ -98,6 +100,32 @@ def test_api_payload_identical_to_cpu_pipeline(depth, alpha, speed, quality):
         assert al == ref["alpha_obu"]
     else:
         assert al is None
+
+
+def test_premultiplied_mode_matches_cpu_pipeline():
+    import cpu_encode as CE
+    m = C()
+    img = H.synth_image(200, 136, 4, alpha=True)
+    r = m.Encoder.new().with_quality(70).with_speed(6).with_alpha_color_mode(m.AlphaColorMode.Premultiplied).encode_rgba(img)
+    ref = CE.encode_rgba(img, 70.0, 6, 10, alpha_mode=2)
+    col, al = payloads(r.avif_file)
+    assert col == ref["color_obu"] and al == ref["alpha_obu"]
+
+
+def test_concurrent_calls_share_one_encoder():
+    """N OS threads call encode_rgba on the same Encoder at once (cavif: rayon par_iter over files, src/main.rs:223)"""
+    import threading
+    m = C()
+    enc = m.Encoder.new().with_quality(65).with_speed(6)
+    imgs = [H.synth_image(160 + 16 * i, 96 + 8 * i, 20 + i, alpha=(i % 3 == 0)) for i in range(8)]
+    serial = [enc.encode_rgba(im).avif_file for im in imgs]
+    out = [None] * len(imgs)
+    def work(i):
+        out[i] = enc.encode_rgba(imgs[i]).avif_file
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(imgs))]
+    for t in th: t.start()
+    for t in th: t.join()
+    assert out == serial
 
 
 def test_batch_matches_single_and_isolates_errors():
