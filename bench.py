@@ -42,7 +42,10 @@ WORKLOADS = {
 #             decisions written + read: 16 B per block at 3 levels                            2 * 16 * (1/16 + 1/64 + 1/256) = 2.6
 #   reconstruction: 3 source planes read, 3 reconstructed planes + 3 coefficient planes written, records      6 + 6 + 6 + 0.9 = 18.9
 RDO_BYTES_PER_PX = 36 + 18.4 + 2.6 + 18.9
-TRAFFIC_BYTES_PER_STEP = None     # filled from profiles/ (ncu dram__bytes_read.sum + dram__bytes_write.sum) when captured
+# ncu dram__bytes_read.sum + dram__bytes_write.sum of the RDO stage group over one 64-image step (profiles/r01_v8_dram_bytes.csv:
+# 19.73 GB read + 7.72 GB written over the 4 steps of that run); below the algorithmic figure because pruned levels are not
+# read and the 126 MB L2 serves most of the second read of the source planes
+TRAFFIC_BYTES_PER_STEP = {"1080p": 6.86e9}
 
 
 def make_images(wl, seed0=0):
@@ -297,7 +300,7 @@ def main():
             "breakdown_ms_per_step": {"gpu_rdo_stages": rdo_ms, "gpu_all_streams_summed": d["gpu_ms_total"] / args.steps,
                                       "host_pack_mux_overlapped": d["host_ms_pack"] / args.steps, "wall": wall * 1e3 / args.steps},
             "roofline": {"bound": "hbm", "kernel": "RDO stage group: b200_satd_kernel + b200_analyze_kernel<lv> x3 + b200_decide_kernel + b200_recon_kernel",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_STEP,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_STEP.get(args.workload) if args.images == 0 else None,
                          "peak_source": peak_src,
                          "note": "integer-ALU / latency bound by construction (small integer butterflies, SURVEY.md 8d), not DRAM-bound; "
                                  "algorithmic bytes = %.1f B/px; traffic = ncu dram bytes of the group per step (profiles/), null if not captured" % RDO_BYTES_PER_PX},
