@@ -138,40 +138,50 @@ def _cpu_encode(args):
     return img.shape[0] * img.shape[1]
 
 
-def cpu_baseline(wl, images_per_core=1):
-    """Oracle port (oracle/ hot path + host packer) on all host cores: one process per core, each encoding
-    `images_per_core` frames of the workload; process start-up and image synthesis are outside the timed region."""
+def _sample_size(wl):
+    """Bounded CPU sample: the upper half of a workload frame (full width, height / 2 rounded up to 8 rows)."""
+    return wl["w"], min(wl["h"], ((wl["h"] // 2 + 7) // 8) * 8)
+
+
+def cpu_steps(wl, n_steps):
+    """Oracle port (oracle/ hot path + host packer) on all host cores: one process per core, each encoding one sample
+    frame per step; process start-up and image synthesis are outside the timed regions.  Returns per-step dicts."""
     from concurrent.futures import ProcessPoolExecutor
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     import harness as H
     H.oracle(); H.hostlib()          # build once in the parent
+    sw, sh = _sample_size(wl)
+    out = []
     with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn"), initializer=_cpu_init,
-                             initargs=(wl["w"], wl["h"])) as ex:
+                             initargs=(sw, sh)) as ex:
         pids = set(ex.map(_cpu_wait, [1.5] * cores))          # all workers up and initialised
         pids |= set(ex.map(_cpu_wait, [0.01] * cores))
-        n = cores * images_per_core
-        t0 = time.perf_counter()
-        px = sum(ex.map(_cpu_encode, [(wl["quality"], wl["speed"], wl["depth"])] * n))
-        dt = time.perf_counter() - t0
-    return {"value": px / 1e6 / dt, "unit": "Mpixels/s", "cores": cores, "kind": "port",
-            "sample": "%d frames of %dx%d on %d worker processes, encode-only wall %.1f s; "
-                      "reference rav1e CPU path: not runnable in this environment" % (n, wl["w"], wl["h"], len(pids), dt)}
+        for _ in range(n_steps):
+            t0 = time.perf_counter()
+            px = sum(ex.map(_cpu_encode, [(wl["quality"], wl["speed"], wl["depth"])] * cores))
+            dt = time.perf_counter() - t0
+            out.append({"value": px / 1e6 / dt, "unit": "Mpixels/s", "cores": cores, "kind": "port", "px": px,
+                        "sample": "%d half frames of %dx%d (of the %dx%d workload frames) on %d worker processes, encode-only "
+                                  "wall %.1f s per step; reference rav1e CPU path: not runnable in this environment"
+                                  % (cores, sw, sh, wl["w"], wl["h"], len(pids), dt)})
+    return out
+
+
+def cpu_baseline(wl):
+    r = cpu_steps(wl, 1)[0]
+    r.pop("px")
+    return r
 
 
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    cb = None
-    for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(wl)
-        if i >= args.warmup:
-            vals.append(cb["value"])
-    v = sum(vals) / len(vals)
+    steps = cpu_steps(wl, args.warmup + args.steps)[args.warmup:]
+    v = sum(s["value"] for s in steps) / len(steps)
+    cb = dict(steps[-1]); px = cb.pop("px")
     cb["value"] = v
-    px = (os.cpu_count() or 1) * wl["w"] * wl["h"]
     out = {"impl": "reference", "metric": "Mpixels/s encoded", "value": v, "unit": "Mpixels/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": px / 1e6 / v * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
