@@ -226,7 +226,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line (NCCL prints its version at VERSION/INFO)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL logs (its version banner) must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
         # north_star: NCCL only to broadcast the quantiser/rate tables (rank 0 -> all), once per batch
         import harness as H
