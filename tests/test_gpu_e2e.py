@@ -102,6 +102,21 @@ def test_api_payload_identical_to_cpu_pipeline(depth, alpha, speed, quality):
         assert al is None
 
 
+@pytest.mark.parametrize("w,h", [(1, 1), (3, 5), (17, 9), (65, 63), (8, 520), (2049, 16), (130, 97)])
+def test_odd_sizes_match_cpu_pipeline(w, h):
+    """tiny / odd / extreme aspect-ratio frames: padding, single partial superblock, many forced splits"""
+    import cpu_encode as CE
+    m = C()
+    img = H.synth_image(w, h, w * 7 + h, alpha=(w % 2 == 1))
+    r = m.Encoder.new().with_quality(72).with_speed(5).encode_rgba(img)
+    ref = CE.encode_rgba(img, 72.0, 5, 10)
+    col, al = payloads(r.avif_file)
+    assert col == ref["color_obu"]
+    assert al == ref["alpha_obu"]
+    im = Image.open(io.BytesIO(r.avif_file))
+    assert im.size == (w, h)
+
+
 def test_premultiplied_mode_matches_cpu_pipeline():
     import cpu_encode as CE
     m = C()
