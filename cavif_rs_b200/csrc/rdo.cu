@@ -1097,7 +1097,9 @@ __global__ void __launch_bounds__(kThreads * (NMAX == 32 ? 2 : kReconWarps), NMA
   constexpr int kWarps = NMAX == 32 ? 2 : kReconWarps;
   typedef SharedT<NMAX> SH;
   __shared__ SH shs[kWarps];
-  __shared__ volatile unsigned short sb_done[kMaxSbRows];      // superblocks finished in each SB row of this tile (<= 1024 columns)
+  // superblocks finished in each SB row of this tile: 16-bit counters (<= 1024 columns), two per word, touched only by
+  // shared-memory atomics (release: fence + atomicAdd by the producer warp, acquire: atomic read + fence by the consumer)
+  __shared__ unsigned int sb_done[kMaxSbRows / 2];
   const B200TileRef tr = tiles[blockIdx.x];
   const B200RdoJob &job = jobs[tr.job];
   TileCtx t;
@@ -1108,7 +1110,7 @@ __global__ void __launch_bounds__(kThreads * (NMAX == 32 ? 2 : kReconWarps), NMA
   t.tc0 = f->tile_col_start_sb[tr.tile_col] * 16;
   t.tc1 = min(f->tile_col_start_sb[tr.tile_col + 1] * 16, f->mi_cols);
   const int sb_rows = (t.tr1 - t.tr0 + 15) >> 4, sb_cols = (t.tc1 - t.tc0 + 15) >> 4;
-  for (int i = threadIdx.x; i < sb_rows; i += blockDim.x) sb_done[i] = 0;
+  for (int i = threadIdx.x; i < (sb_rows + 1) / 2; i += blockDim.x) sb_done[i] = 0;
   __syncthreads();
   const int warp = threadIdx.x >> 5;
   SH &sh = shs[warp];
@@ -1119,7 +1121,7 @@ __global__ void __launch_bounds__(kThreads * (NMAX == 32 ? 2 : kReconWarps), NMA
     for (int C = 0; C < sb_cols; C++) {
       if (R > 0) {
         const int need = min(C + 2, sb_cols);
-        while ((int)sb_done[R - 1] < need) B200_SPIN_WAIT();
+        while ((int)((atomicAdd(&sb_done[(R - 1) >> 1], 0u) >> (16 * ((R - 1) & 1))) & 0xffffu) < need) B200_SPIN_WAIT();
         __syncwarp();
         __threadfence_block();
       }
@@ -1137,7 +1139,7 @@ __global__ void __launch_bounds__(kThreads * (NMAX == 32 ? 2 : kReconWarps), NMA
       }
       __threadfence_block();               // the reconstruction of this SB is visible before the counter moves
       __syncwarp();
-      if (lane_id() == 0) sb_done[R] = (unsigned short)(C + 1);
+      if (lane_id() == 0) atomicAdd(&sb_done[R >> 1], 1u << (16 * (R & 1)));
     }
   }
 }
