@@ -37,11 +37,11 @@ WORKLOADS = {
 }
 # Algorithmic bytes per pixel of the RDO stage group (SATD + analysis per level, partition decision, reconstruction
 # chain), 16-bit samples:
-#   analysis: 3 source planes read once per level by the SATD kernel and once by the trial kernel (3 levels)  2*3*3*2 = 36
-#             SATD tables written + read: 28 x 4 B per block at 3 levels                     2 * 112 * (1/16 + 1/64 + 1/256) = 18.4
+#   analysis: per level the SATD kernel reads the luma source plane and the trial kernel reads the 3 source planes   3 * (2 + 6) = 24
+#             SATD tables written + read: 14 x 4 B per block at 3 levels                      2 * 56 * (1/16 + 1/64 + 1/256) = 9.2
 #             decisions written + read: 16 B per block at 3 levels                            2 * 16 * (1/16 + 1/64 + 1/256) = 2.6
 #   reconstruction: 3 source planes read, 3 reconstructed planes + 3 coefficient planes written, records      6 + 6 + 6 + 0.9 = 18.9
-RDO_BYTES_PER_PX = 36 + 18.4 + 2.6 + 18.9
+RDO_BYTES_PER_PX = 24 + 9.2 + 2.6 + 18.9
 # ncu dram__bytes_read.sum + dram__bytes_write.sum of the RDO stage group over one 64-image step (profiles/r01_v8_dram_bytes.csv:
 # 19.73 GB read + 7.72 GB written over the 4 steps of that run); below the algorithmic figure because pruned levels are not
 # read and the 126 MB L2 serves most of the second read of the source planes

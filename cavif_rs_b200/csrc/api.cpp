@@ -184,7 +184,7 @@ size_t job_dev_bytes(const FrameJob &j, bool own_src) {
   b += P * align256(j.n_mi() * 2);
   b += P * align256(j.n_coef() * 2);
   b += align256(j.n_sb());
-  for (int lv = 0; lv < B200_LEVELS; lv++) b += align256(j.n_blk(lv) * sizeof(B200BlockDec)) + align256(j.n_blk(lv) * 2 * B200_SATD_WORDS * 4) + 512;
+  for (int lv = 0; lv < B200_LEVELS; lv++) b += align256(j.n_blk(lv) * sizeof(B200BlockDec)) + align256(j.n_blk(lv) * B200_SATD_WORDS * 4) + 512;
   if (j.uses_lr()) b += P * (align256(j.n_px() * 2) + align256(j.n_lr() * sizeof(B200LrUnit)));
   return b + 8192;
 }
@@ -206,7 +206,7 @@ void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
   j.d_mi = dev.take<B200Mi>(j.n_mi());
   for (int lv = 0; lv < B200_LEVELS; lv++) {
     j.d_dec[lv] = dev.take<B200BlockDec>(j.n_blk(lv));
-    j.d_satd[lv] = dev.take<uint32_t>(j.n_blk(lv) * 2 * B200_SATD_WORDS);
+    j.d_satd[lv] = dev.take<uint32_t>(j.n_blk(lv) * B200_SATD_WORDS);
   }
   j.d_cdef = dev.take<int8_t>(j.n_sb());
   j.h_cdef = pin.take<int8_t>(j.n_sb());
@@ -855,7 +855,7 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
   }
   for (int lv = 0; lv < B200_LEVELS; lv++) {   // levels outside the partition range are not analysed: keep them comparable
     CU(cudaMemsetAsync(job.d_dec[lv], 0, job.n_blk(lv) * sizeof(B200BlockDec), c.stream));
-    CU(cudaMemsetAsync(job.d_satd[lv], 0, job.n_blk(lv) * 2 * B200_SATD_WORDS * 4, c.stream));
+    CU(cudaMemsetAsync(job.d_satd[lv], 0, job.n_blk(lv) * B200_SATD_WORDS * 4, c.stream));
   }
   std::vector<FrameJob *> jobs{&job};
   std::vector<std::vector<uint16_t>> deb, pre;
@@ -864,7 +864,7 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
   if (cdef_idx) memcpy(cdef_idx, job.h_cdef, job.n_sb());
   for (int lv = 0; lv < B200_LEVELS; lv++) {
     if (dec && dec[lv]) CU(cudaMemcpy(dec[lv], job.d_dec[lv], job.n_blk(lv) * sizeof(B200BlockDec), cudaMemcpyDeviceToHost));
-    if (satd && satd[lv]) CU(cudaMemcpy(satd[lv], job.d_satd[lv], job.n_blk(lv) * 2 * B200_SATD_WORDS * 4, cudaMemcpyDeviceToHost));
+    if (satd && satd[lv]) CU(cudaMemcpy(satd[lv], job.d_satd[lv], job.n_blk(lv) * B200_SATD_WORDS * 4, cudaMemcpyDeviceToHost));
   }
   for (int p = 0; p < job.f.planes; p++) {
     if (eob && eob[p]) memcpy(eob[p], job.h_eob[p], job.n_mi() * 2);

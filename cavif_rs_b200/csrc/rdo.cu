@@ -597,17 +597,13 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, SH &sh, int x, i
   __syncwarp();
   // ---- ranking from the SATD table (context-0 mode rates)
   const uint16_t *ymode_cost = rt->y_mode[0][0];
-  const uint32_t wy = satd[13], wuv = f->planes > 1 ? satd[B200_SATD_WORDS + 13] : (255u | (3u << 8));      // refined directional mode | (delta + 3) << 8
-  const int md_y = wy & 255, dl_y = (int)(wy >> 8) - 3, md_uv = wuv & 255, dl_uv = (int)(wuv >> 8) - 3;
+  const uint32_t wy = satd[13];      // refined directional mode | (delta + 3) << 8
+  const int md_y = wy & 255, dl_y = (int)(wy >> 8) - 3;
 #define DELTA_Y(m) ((m) == md_y ? dl_y : 0)
-#define DELTA_UV(m) ((m) == md_uv ? dl_uv : 0)
+#define DELTA_UV(m) ((m) == best_mode ? DELTA_Y(m) : 0)
   long long my_ycost = kInf;
-  uint32_t my_uvsatd = 0;
-  if (lane < 13) {
-    if ((f->y_mode_mask >> lane) & 1)
-      my_ycost = (long long)satd[lane] * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, lane, n, DELTA_Y(lane))) >> 8);
-    my_uvsatd = satd[B200_SATD_WORDS + lane];
-  }
+  if (lane < 13 && ((f->y_mode_mask >> lane) & 1))
+    my_ycost = (long long)satd[lane] * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, lane, n, DELTA_Y(lane))) >> 8);
   int m0, m1;
   rank_top2(my_ycost, m0, m1);
   // ---- luma full trials: candidate c = k * 5 + ti; lane batches pair the two modes on the same transform type
@@ -651,11 +647,11 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, SH &sh, int x, i
   int uv_best = DC_PRED, eobU = 0, eobV = 0, cfl_js = 0, cfl_idx = 0;
   if (planes > 1) {
     const uint16_t *uvcost = rt->uv_mode[1][best_mode];
-    long long my_uvcost = kInf;
-    if (lane < 13 && ((f->uv_mode_mask >> lane) & 1))
-      my_uvcost = (long long)my_uvsatd * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, uvcost, lane, n, DELTA_UV(lane))) >> 8);
-    int u0, u1;
-    rank_top2(my_uvcost, u0, u1);
+    // chroma candidates (oracle): the chosen luma mode with its angle delta, DC_PRED, chroma-from-luma
+    int u0 = -1, u1 = -1;
+    if ((f->uv_mode_mask >> best_mode) & 1) u0 = best_mode;
+    if (best_mode != DC_PRED && (f->uv_mode_mask & 1)) { if (u0 < 0) u0 = DC_PRED; else u1 = DC_PRED; }
+    if (u0 < 0) u0 = __ffs(f->uv_mode_mask & 0x1fff) - 1;       // forced single modes (conformance tests)
     long long bestCj = kInf;
     // third candidate: chroma from (source) luma, alpha = clamped integer least-squares fit per plane
     int al_u = 0, al_v = 0, dc_u = 0, dc_v = 0;
@@ -794,7 +790,7 @@ __device__ __noinline__ void reconstruct_block(const TileCtx &t, SH &sh, int x, 
 
 // ---- stage A.1: SATD of the 13 intra modes for every block of level lv, predicted from SOURCE neighbours.
 // One thread per (block, plane group): group 0 = luma, group 1 = U + V.  out: [block][2][13] uint32.
-// One item = (block, plane group) of level lv.  A CTA owns kSatdItems consecutive items: it first compacts the items
+// One item = one block of level lv (luma SATD of the 13 modes + angle refinement).  A CTA owns kSatdItems consecutive items: it first compacts the items
 // that survive the top-down pruning into shared memory, then its 128 threads walk the compacted list, so warps stay
 // full even when most of a level is pruned.
 constexpr int kSatdItems = 512;
@@ -809,7 +805,7 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
   const int n = 4 << lv;
   if (n < min(f->partition_min, 8) || n > f->partition_max) return;   // 8x8 always: forced splits at the frame edge
   const int cols = b200_level_cols(f, lv), rows = b200_level_rows(f, lv);
-  const int groups = f->planes > 1 ? 2 : 1, total = cols * rows * groups;
+  const int total = cols * rows;
   const int base = blockIdx.x * items;
   if (base >= total) return;
   if (threadIdx.x == 0) s_n = 0;
@@ -841,7 +837,7 @@ __global__ void __launch_bounds__(128) b200_satd_direct_kernel(const B200RdoJob 
   const B200Frame *f = &job.frame;
   const int n = 4 << lv;
   if (n < min(f->partition_min, 8) || n > f->partition_max) return;
-  const int total = b200_level_cols(f, lv) * b200_level_rows(f, lv) * (f->planes > 1 ? 2 : 1);
+  const int total = b200_level_cols(f, lv) * b200_level_rows(f, lv);
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
   if (lv < B200_LEVELS - 1) {
@@ -854,8 +850,9 @@ __global__ void __launch_bounds__(128) b200_satd_direct_kernel(const B200RdoJob 
 __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid, int *sh_d) {
   const B200Frame *f = &job.frame;
   const int n = 4 << lv, lg = 2 + lv;
-  const int cols = b200_level_cols(f, lv), rows = b200_level_rows(f, lv);
-  const int grp = gid / (cols * rows), blk = gid % (cols * rows);     // same group for neighbouring threads
+  const int cols = b200_level_cols(f, lv);
+  constexpr int grp = 0;            // luma only: the chroma candidates are derived from the luma decision
+  const int blk = gid;
   const int bx = blk % cols, by = blk / cols, x = bx * n, y = by * n;
   TileCtx t;
   ctx_from_job(job, t);
@@ -961,7 +958,7 @@ __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid
     acc[md] = best_s;
     word = (uint32_t)md | ((uint32_t)(best_d + 3) << 8);
   }
-  uint32_t *out = job.satd[lv] + ((size_t)blk * 2 + grp) * B200_SATD_WORDS;
+  uint32_t *out = job.satd[lv] + (size_t)blk * B200_SATD_WORDS;
 #pragma unroll 1
   for (int m = 0; m < 13; m++) out[m] = acc[m];
   out[13] = word;
@@ -992,7 +989,7 @@ __global__ void __launch_bounds__(kThreads * W, LV == 3 ? 4 : (LV == 2 ? 16 : 24
       const int blk = want < total ? want : total - 1;             // padding warps repeat the last block, output discarded
       const int x = (blk % cols) * n, y = (blk / cols) * n;
       tile_of_unit(f, y >> 2, x >> 2, t);
-      analyze_block<2 + LV, HBD, true>(t, sh, x, y, job.satd[lv] + (size_t)blk * 2 * B200_SATD_WORDS, want < total ? job.dec[lv] + blk : nullptr);
+      analyze_block<2 + LV, HBD, true>(t, sh, x, y, job.satd[lv] + (size_t)blk * B200_SATD_WORDS, want < total ? job.dec[lv] + blk : nullptr);
     }
     return;
   }
@@ -1009,7 +1006,7 @@ __global__ void __launch_bounds__(kThreads * W, LV == 3 ? 4 : (LV == 2 ? 16 : 24
       continue;
     }
     tile_of_unit(f, y >> 2, x >> 2, t);
-    analyze_block<2 + LV, HBD, false>(t, sh, x, y, job.satd[lv] + (size_t)blk * 2 * B200_SATD_WORDS, job.dec[lv] + blk);
+    analyze_block<2 + LV, HBD, false>(t, sh, x, y, job.satd[lv] + (size_t)blk * B200_SATD_WORDS, job.dec[lv] + blk);
   }
 }
 
@@ -1169,10 +1166,10 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     if (nblk == 0) continue;
     // the top level is never pruned: one item per thread; lower levels are mostly pruned: compact 512 items per CTA
     if (lv == top) {
-      dim3 gs((nblk * 2 + 127) / 128, n_jobs);
+      dim3 gs((nblk + 127) / 128, n_jobs);
       b200_satd_direct_kernel<<<gs, 128, 0, st>>>(d_jobs, lv);
     } else {
-      dim3 gs((nblk * 2 + kSatdItems - 1) / kSatdItems, n_jobs);
+      dim3 gs((nblk + kSatdItems - 1) / kSatdItems, n_jobs);
       b200_satd_kernel<<<gs, 128, 0, st>>>(d_jobs, lv, kSatdItems);
     }
     // enough warps to fill the machine several times over, grid-stride inside
@@ -1239,7 +1236,7 @@ extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *ti
     const int nblk = (f->mi_rows >> g_emu_lv) * (f->mi_cols >> g_emu_lv);
     if (nblk == 0) continue;
     const int items = g_emu_lv == g_emu_top ? 128 : kSatdItems;
-    emu::launch(emu_satd, nullptr, (unsigned)((nblk * 2 + items - 1) / items), 128);
+    emu::launch(emu_satd, nullptr, (unsigned)((nblk + items - 1) / items), 128);
     const int w = g_emu_lv == 3 ? kAnalyzeWarpsTop32 : ((g_emu_lv == 2 && g_emu_top == 2) ? kAnalyzeWarpsTop : 1);
     emu::launch(emu_analyze, nullptr, (unsigned)std::min(nblk, w > 1 ? 3 : 7), kThreads * w);
   }

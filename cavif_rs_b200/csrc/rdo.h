@@ -18,7 +18,7 @@ typedef struct B200RdoJob {
   uint16_t *eob[3];
   int16_t *coef[3];
   B200BlockDec *dec[B200_LEVELS];   // analysis decisions per level (0: 4x4 .. 3: 32x32), b200_level_rows*cols entries
-  uint32_t *satd[B200_LEVELS];      // SATD tables per level: [block][2 (Y, U+V)][14 words]
+  uint32_t *satd[B200_LEVELS];      // luma SATD tables per level: [block][14 words]
   // in-loop filter stage (filters.cu): rec is deblocked IN PLACE; cdef_idx receives the per-superblock
   // strength index (-1: nothing coded in the superblock); fin (optional, may be NULL) receives the CDEF output.
   int8_t *cdef_idx;       // sb_rows*sb_cols

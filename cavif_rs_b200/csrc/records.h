@@ -103,7 +103,7 @@ typedef struct B200BlockDec {
   uint8_t angle_y, angle_uv;   // angle_delta + 3 of the chosen luma / chroma mode (3 = no delta)
   uint8_t cfl_js, cfl_alpha;   // uv_mode == UV_CFL_PRED: joint sign (0..7), alpha indices (u low nibble, v high nibble)
 } B200BlockDec;
-// SATD table entry per (block, plane group): 13 mode SATDs + one word packing the refined directional mode and its
+// SATD table entry per block (luma): 13 mode SATDs + one word packing the refined directional mode and its
 // angle delta: (mode | (delta + 3) << 8), mode = 255 when no directional mode was refined.
 #define B200_SATD_WORDS 14
 // analysis levels: 0: 4x4, 1: 8x8, 2: 16x16, 3: 32x32 (block size 4 << lv)

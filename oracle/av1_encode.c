@@ -402,31 +402,26 @@ static uint32_t refine_angle(enc_t *e, int first_plane, int last_plane, int x, i
 /* ---- stage A: open-loop analysis of one block.  Every prediction reads SOURCE neighbours, so all blocks of all
  * levels are independent of each other (one massively parallel kernel per level on the device).  Rate terms that
  * would depend on neighbouring decisions use the context-0 tables. */
-void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_t satd_y[14], uint32_t satd_uv[14]) {
+void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_t satd_y[14]) {
   const B200Frame *f = e->f;
   const B200RateTables *rt = e->rt;
   uint16_t A[3][EOFF + 66], L[3][EOFF + 66], pred[32 * 32];
   int ha = 0, hl = 0;
   for (int p = 0; p < f->planes; p++) build_edges(e, e->src[p], x, y, n, A[p], L[p], &ha, &hl);
   const uint16_t *ymode_cost = rt->y_mode[0][0];
-  /* SATD of the nominal modes (the device computes this table in b200_satd_kernel) */
+  /* luma SATD of the nominal modes (the device computes this table in the SATD kernels) */
   for (int m = 0; m < 13; m++) {
-    satd_y[m] = 0; satd_uv[m] = 0;
-    const int in_y = (f->y_mode_mask >> m) & 1, in_uv = f->planes > 1 && ((f->uv_mode_mask >> m) & 1);
-    for (int p = 0; p < f->planes; p++) {
-      if (p == 0 ? !in_y : !in_uv) continue;
-      orc_predict_intra(m, 0, n, A[p], L[p], ha, hl, f->bit_depth, pred);
-      const uint32_t s = satd4(e->src[p] + y * e->stride + x, e->stride, pred, n);
-      if (p == 0) satd_y[m] = s; else satd_uv[m] += s;
-    }
+    satd_y[m] = 0;
+    if (!((f->y_mode_mask >> m) & 1)) continue;
+    orc_predict_intra(m, 0, n, A[0], L[0], ha, hl, f->bit_depth, pred);
+    satd_y[m] = satd4(e->src[0] + y * e->stride + x, e->stride, pred, n);
   }
   satd_y[13] = refine_angle(e, 0, 0, x, y, n, A, L, ha, hl, f->y_mode_mask, satd_y);
-  satd_uv[13] = f->planes > 1 ? refine_angle(e, 1, 2, x, y, n, A, L, ha, hl, f->uv_mode_mask, satd_uv) : (255u | (3u << 8));
   const int md_y = satd_y[13] & 255, dl_y = (int)(satd_y[13] >> 8) - 3;
-  const int md_uv = satd_uv[13] & 255, dl_uv = (int)(satd_uv[13] >> 8) - 3;
-  if (f->planes == 1) satd_uv[13] = 0;      /* the device has no chroma SATD thread for monochrome frames */
 #define DELTA_Y(m) ((m) == md_y ? dl_y : 0)
-#define DELTA_UV(m) ((m) == md_uv ? dl_uv : 0)
+  /* chroma follows rav1e's candidate structure (rdo.rs rdo_mode_decision): the chosen luma mode (with its angle
+   * delta), DC_PRED, and chroma-from-luma - no chroma SATD ranking */
+#define DELTA_UV(m) ((m) == best_mode ? DELTA_Y(m) : 0)
   /* ranking: SATD + mode rate */
   int64_t bc[2] = {INT64_MAX, INT64_MAX};
   int bm[2] = {-1, -1};
@@ -473,14 +468,11 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
   int uv_best = DC_PRED, eob_u = 0, eob_v = 0, cfl_js = 0, cfl_idx = 0;
   if (f->planes > 1) {
     const uint16_t *uvcost = rt->uv_mode[1][best_mode];
-    int64_t uc[2] = {INT64_MAX, INT64_MAX};
     int um[2] = {-1, -1};
-    for (int m = 0; m < 13; m++) {
-      if (!((f->uv_mode_mask >> m) & 1)) continue;
-      const int64_t c = (int64_t)satd_uv[m] * 64 + (((int64_t)f->lambda_satd_q8 * mode_rate(rt, uvcost, m, n, DELTA_UV(m))) >> 8);
-      if (c < uc[0]) { uc[1] = uc[0]; um[1] = um[0]; uc[0] = c; um[0] = m; }
-      else if (c < uc[1]) { uc[1] = c; um[1] = m; }
-    }
+    if ((f->uv_mode_mask >> best_mode) & 1) um[0] = best_mode;
+    if (best_mode != DC_PRED && (f->uv_mode_mask & 1)) { if (um[0] < 0) um[0] = DC_PRED; else um[1] = DC_PRED; }
+    if (um[0] < 0)      /* neither is allowed (conformance tests force single modes): the lowest allowed mode */
+      for (int m = 0; m < 13; m++) if ((f->uv_mode_mask >> m) & 1) { um[0] = m; break; }
     int64_t bestC = INT64_MAX;
     for (int k = 0; k < 2; k++) {
       const int m = um[k];
@@ -650,16 +642,16 @@ void orc_encode_frame(const B200Frame *f, const B200RateTables *rt, uint16_t *co
         int tr, tc;
         tile_of(f, by * (n / 4), bx * (n / 4), &tr, &tc);
         tile_bounds(&e, tr, tc);
-        uint32_t sy[14], suv[14];
+        uint32_t sy[14];
         const size_t bi = (size_t)by * b200_level_cols(f, lv) + bx;
         if (lv < B200_LEVELS - 1 && b200_pruned_by_parent(f, lv, bx, by, e.dec[lv + 1])) {
           memset(&e.dec[lv][bi], 0, sizeof(B200BlockDec));
           e.dec[lv][bi].cost = B200_COST_PRUNED;
-          if (satd_out && satd_out[lv]) memset(satd_out[lv] + bi * 2 * B200_SATD_WORDS, 0, 2 * B200_SATD_WORDS * sizeof(uint32_t));
+          if (satd_out && satd_out[lv]) memset(satd_out[lv] + bi * B200_SATD_WORDS, 0, B200_SATD_WORDS * sizeof(uint32_t));
           continue;
         }
-        orc_analyze_block(&e, bx * n, by * n, n, &e.dec[lv][bi], sy, suv);
-        if (satd_out && satd_out[lv]) { memcpy(satd_out[lv] + bi * 2 * B200_SATD_WORDS, sy, sizeof(sy)); memcpy(satd_out[lv] + bi * 2 * B200_SATD_WORDS + B200_SATD_WORDS, suv, sizeof(suv)); }
+        orc_analyze_block(&e, bx * n, by * n, n, &e.dec[lv][bi], sy);
+        if (satd_out && satd_out[lv]) memcpy(satd_out[lv] + bi * B200_SATD_WORDS, sy, sizeof(sy));
       }
   }
   const int rn = 4 << root_level(f);

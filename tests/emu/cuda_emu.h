@@ -92,6 +92,7 @@ static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
   return r;
 }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }

@@ -135,7 +135,7 @@ class Records:
         self.rec = [np.zeros((f.mi_rows * 4, f.mi_cols * 4), np.uint16) for _ in range(3)]
         # open-loop analysis outputs per level (0: 4x4, 1: 8x8, 2: 16x16)
         self.dec = [np.zeros(max((f.mi_rows >> lv) * (f.mi_cols >> lv), 1), DEC_DTYPE) for lv in range(LEVELS)]
-        self.satd = [np.zeros((max((f.mi_rows >> lv) * (f.mi_cols >> lv), 1), 2, 14), np.uint32) for lv in range(LEVELS)]
+        self.satd = [np.zeros((max((f.mi_rows >> lv) * (f.mi_cols >> lv), 1), 14), np.uint32) for lv in range(LEVELS)]
     def c_records(self):
         r = B200Records()
         r.mi = self.mi.ctypes.data
