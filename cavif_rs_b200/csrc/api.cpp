@@ -237,8 +237,8 @@ int configure_frame(B200Frame *f, size_t w, size_t h, int depth, bool mono, int 
   f->partition_min = std::min(f->partition_min, f->partition_max);
   f->fine_directional_intra = tw.fine_directional_intra;
   // early termination of the partition search (records.h split_gate_bits): exhaustive at the slow presets
-  f->split_gate_bits[0] = speed <= 2 ? 0 : 44;
-  f->split_gate_bits[1] = speed <= 2 ? 0 : 96;
+  f->split_gate_bits[0] = speed <= 2 ? 0 : 60;
+  f->split_gate_bits[1] = speed <= 2 ? 0 : 120;
   f->split_gate_bits[2] = speed <= 2 ? 0 : 200;
   if (!tw.cdef) f->enable_cdef = 0;   // ravif: cdef = low_quality && speed <= 9 (av1encoder.rs:590)
   f->enable_restoration = tw.lrf ? 1 : 0;     // loop restoration (lrf flag, av1encoder.rs:589): self-guided filter, 64x64 units

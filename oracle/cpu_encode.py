@@ -48,8 +48,8 @@ def configure(w, h, depth, planes, quantizer, speed, threads=None):
     f.partition_max = min(tw.partition_max, 32)
     f.partition_min = min(tw.partition_min, f.partition_max)
     f.fine_directional_intra = tw.fine_directional_intra
-    f.split_gate_bits[0] = 0 if speed <= 2 else 44
-    f.split_gate_bits[1] = 0 if speed <= 2 else 96
+    f.split_gate_bits[0] = 0 if speed <= 2 else 60
+    f.split_gate_bits[1] = 0 if speed <= 2 else 120
     f.split_gate_bits[2] = 0 if speed <= 2 else 200
     f.enable_cdef = 1 if tw.cdef else 0
     f.enable_restoration = 1 if tw.lrf else 0
