@@ -60,6 +60,7 @@ def compare_analysis(ref, out, f):
     (95, 70, 10, 1, 1, dict(lr=1, partition_min=16)),    # one 95-wide unit, 10 bit, monochrome
     (136, 104, 8, 3, 1, dict(partition_max=32)),         # 32x32 level on top (partition range of speed <= 2)
     (96, 64, 10, 3, 1, dict(partition_max=32, partition_min=8, lr=1)),
+    (120, 88, 10, 1, 2, dict(split_gates=(60, 120), partition_min=8, lr=1)),   # monochrome (alpha) frame of the fast presets
       # 4 x 3 superblocks: the reconstruction wavefront waits on its neighbours
 ])
 def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):

@@ -185,6 +185,28 @@ def test_rdo_kernel_matches_oracle_and_dav1d(w, h, depth, planes, q, tiles, kw):
         assert np.array_equal(dec[p], shown[p][:h, :w])
 
 
+@pytest.mark.parametrize("speed,quantizer", [(6, 121), (4, 121), (8, 66)])
+def test_alpha_frame_of_the_fast_presets(speed, quantizer):
+    """the monochrome alpha frame exactly as encode_rgba() configures it (real alpha plane: large flat areas, heavy pruning)"""
+    import sys, os
+    sys.path.insert(0, os.path.join(H.ROOT, "oracle"))
+    import cpu_encode as CE
+    w, h = 360, 240
+    img = H.synth_image(w, h, 7, alpha=True)
+    _, alpha, anya = CE.convert(img, 10)
+    assert anya
+    f = CE.configure(w, h, 10, 1, quantizer, speed)
+    f.full_range = 1
+    src = H.pad_planes([alpha], f)
+    ref = H.oracle_encode(f, H.rate_tables(f.base_q_idx), src)
+    ref_fin, ref_deb = H.oracle_filters(f, ref, src)
+    out = device_rdo(f, src)
+    check_analysis(ref, out, f)
+    check_records(ref, out, 1)
+    check_filters(f, ref, ref_fin, ref_deb, out, 1, w, h)
+    assert H.pack(f, out) == H.pack(f, ref)
+
+
 def test_rdo_full_hd_frame_parity():
     """BASELINE.json config #2 geometry (1920x1080, q80 -> quantizer 121, speed 4, 8-bit, 31 tiles)."""
     import sys, os
