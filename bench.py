@@ -226,14 +226,25 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL logs (its version banner) must not share stdout with the JSON line
-        dist.init_process_group("nccl", device_id=dev)
-        # north_star: NCCL only to broadcast the quantiser/rate tables (rank 0 -> all), once per batch
-        import harness as H
-        q = C.quality_to_quantizer(wl["quality"])
-        tbl = torch.from_numpy(H.rate_tables(max(q, 1)).astype(np.int32)).to(dev) if rank == 0 else \
-            torch.zeros(H.RATE_TABLES_BYTES // 2, dtype=torch.int32, device=dev)
-        dist.broadcast(tbl, src=0)
+        # NCCL prints its version banner to stdout when the communicator is created: keep fd 1 pointed at stderr until the
+        # first collective is through, so that rank 0's stdout carries exactly the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            # north_star: NCCL only to broadcast the quantiser/rate tables (rank 0 -> all), once per batch
+            import harness as H
+            q = C.quality_to_quantizer(wl["quality"])
+            tbl = torch.from_numpy(H.rate_tables(max(q, 1)).astype(np.int32)).to(dev) if rank == 0 else \
+                torch.zeros(H.RATE_TABLES_BYTES // 2, dtype=torch.int32, device=dev)
+            dist.broadcast(tbl, src=0)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     imgs = make_images(wl, seed0=1000 * rank)     # every rank encodes its own batch (images are independent units)
     px_per_step = wl["n"] * wl["w"] * wl["h"]
