@@ -45,6 +45,11 @@ constexpr int kThreads = 32;
 constexpr int EOFF = 16;          // edge arrays: index -1 .. 2n-1 stored at EOFF-1 ..
 constexpr int kEdge = EOFF + 34;  // n <= 16 (per-thread edge arrays of the SATD kernel use EOFF + 66 at the 32x32 level)
 constexpr unsigned FULL = 0xffffffffu;
+#ifdef B200_EMU
+#define B200_PREFETCH_L2(p) ((void)(p))
+#else
+#define B200_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#endif
 constexpr long long kInf = 0x7fffffffffffffffll;
 
 // inverse scan tables (4x4 | 8x8 | 16x16) in GLOBAL memory: indexed per lane (divergent), which the constant
@@ -181,6 +186,13 @@ __device__ __noinline__ int dc_value(int n, const uint16_t *A, const uint16_t *L
 #pragma unroll 1
   for (int i = 0; i < n; i++) s += (ha ? A[i] : 0) + (hl ? L[i] : 0);
   return (ha && hl) ? (s + n) >> (lg + 1) : (s + (n >> 1)) >> lg;
+}
+// the same value computed by the whole warp (edges in shared memory): lane i adds sample i (n <= 32), one REDUX
+__device__ __noinline__ int dc_value_warp(int n, const uint16_t *A, const uint16_t *L, int ha, int hl, int bd) {
+  if (!ha && !hl) return 1 << (bd - 1);
+  const int lg = 31 - __clz(n), i = lane_id();
+  const unsigned s = __reduce_add_sync(FULL, i < n ? (unsigned)((ha ? A[i] : 0) + (hl ? L[i] : 0)) : 0u);
+  return (ha && hl) ? (int)(s + n) >> (lg + 1) : (int)(s + (n >> 1)) >> lg;
 }
 // A, L point at index 0 of the edge arrays (index -1 valid).  dc: precomputed DC value (used for DC_PRED only).
 __device__ __forceinline__ int pred_px(int mode, int delta, int n, int i, int j, const uint16_t *A, const uint16_t *L, int dc) {
@@ -496,7 +508,7 @@ __device__ __noinline__ void predict_block(int mode, int delta, int lg, const ui
                                            uint16_t *dst) {
   const uint16_t *A = above + EOFF, *L = left + EOFF;
   const int n = 1 << lg;
-  const int dc = mode == DC_PRED ? dc_value(n, A, L, ha, hl, bd) : 0;
+  const int dc = mode == DC_PRED ? dc_value_warp(n, A, L, ha, hl, bd) : 0;
 #pragma unroll 1
   for (int p = lane_id(); p < n * n; p += 32) dst[p] = (uint16_t)pred_px(mode, delta, n, p >> lg, p & (n - 1), A, L, dc);
 }
@@ -657,8 +669,8 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, SH &sh, int x, i
     int al_u = 0, al_v = 0, dc_u = 0, dc_v = 0;
     if (f->enable_cfl) {
       cfl_build_ac(sh.src[0], lg, sh.ac);
-      dc_u = dc_value(n, sh.above[1] + EOFF, sh.left[1] + EOFF, ha, hl, bd);
-      dc_v = dc_value(n, sh.above[2] + EOFF, sh.left[2] + EOFF, ha, hl, bd);
+      dc_u = dc_value_warp(n, sh.above[1] + EOFF, sh.left[1] + EOFF, ha, hl, bd);
+      dc_v = dc_value_warp(n, sh.above[2] + EOFF, sh.left[2] + EOFF, ha, hl, bd);
       al_u = cfl_pick_alpha(sh.ac, sh.src[1], N2, dc_u);
       al_v = cfl_pick_alpha(sh.ac, sh.src[2], N2, dc_v);
     }
@@ -755,7 +767,7 @@ __device__ __noinline__ void reconstruct_block(const TileCtx &t, SH &sh, int x, 
     for (int pp = p0; pp < p0 + cnt; pp++) {
       uint16_t *dst = sh.pred + (pp - p0) * N2;
       if (cfl && pp > 0)
-        cfl_predict_block(sh.ac, N2, dc_value(n, sh.above[pp] + EOFF, sh.left[pp] + EOFF, ha, hl, bd), pp == 1 ? au : av, bd, dst);
+        cfl_predict_block(sh.ac, N2, dc_value_warp(n, sh.above[pp] + EOFF, sh.left[pp] + EOFF, ha, hl, bd), pp == 1 ? au : av, bd, dst);
       else
         predict_block(pp == 0 ? m.y_mode : m.uv_mode, (pp == 0 ? (m.angle & 15) : (m.angle >> 4)) - 3, lg, sh.above[pp], sh.left[pp], ha, hl, bd, dst);
     }
@@ -988,6 +1000,13 @@ __global__ void __launch_bounds__(kThreads * W, LV == 3 ? 4 : (LV == 2 ? 16 : 24
       const int want = (it * gridDim.x + blockIdx.x) * W + (threadIdx.x >> 5);
       const int blk = want < total ? want : total - 1;             // padding warps repeat the last block, output discarded
       const int x = (blk % cols) * n, y = (blk / cols) * n;
+      {   // the next block of this warp: pull its source rows into L2 while this one is analysed
+        const int nxt = want + per_iter;
+        if (nxt < total) {
+          const int nx = (nxt % cols) * n, ny = (nxt / cols) * n;
+          for (int i = lane_id(); i < n * f->planes; i += 32) B200_PREFETCH_L2(t.src[i / n] + (size_t)(ny + i % n) * t.stride + nx);
+        }
+      }
       tile_of_unit(f, y >> 2, x >> 2, t);
       analyze_block<2 + LV, HBD, true>(t, sh, x, y, job.satd[lv] + (size_t)blk * B200_SATD_WORDS, want < total ? job.dec[lv] + blk : nullptr);
     }
@@ -1088,6 +1107,19 @@ constexpr int kMaxSbRows = 1024;     // 65536 / 64
 #else
 #define B200_SPIN_WAIT() __nanosleep(40)
 #endif
+// The chain stalls on the first touch of every block's source samples (profiles/: 27 % of the active samples of the
+// reconstruction kernel): pull the source rows of superblock (mi row r, mi col c) into L2 ahead of time, one 128-byte
+// line per lane and iteration (64 samples of 2 bytes = one line per row and plane).
+__device__ __forceinline__ void prefetch_sb_source(const TileCtx &t, int r, int c) {
+  const B200Frame *f = t.f;
+  if (r >= t.tr1 || c >= t.tc1) return;
+  const int rows = min(64, (f->mi_rows - r) * 4);
+#pragma unroll 1
+  for (int i = lane_id(); i < rows * f->planes; i += 32) {
+    const int p = i / rows, y = r * 4 + i % rows;
+    B200_PREFETCH_L2(t.src[p] + (size_t)y * t.stride + c * 4);
+  }
+}
 // NMAX = 32 (partition range up to 32x32): 2 warps per tile, 22.9 KB of shared memory each
 template <bool HBD, int NMAX>
 __global__ void __launch_bounds__(kThreads * (NMAX == 32 ? 2 : kReconWarps), NMAX == 32 ? 4 : 4) b200_recon_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
@@ -1114,8 +1146,10 @@ __global__ void __launch_bounds__(kThreads * (NMAX == 32 ? 2 : kReconWarps), NMA
 #pragma unroll 1
   for (int R = warp; R < sb_rows; R += kWarps) {
     const int r = t.tr0 + R * 16;
+    prefetch_sb_source(t, r, t.tc0);
 #pragma unroll 1
     for (int C = 0; C < sb_cols; C++) {
+      prefetch_sb_source(t, r, t.tc0 + (C + 1) * 16);        // the next superblock of this row, while this one is coded
       if (R > 0) {
         const int need = min(C + 2, sb_cols);
         while ((int)((atomicAdd(&sb_done[(R - 1) >> 1], 0u) >> (16 * ((R - 1) & 1))) & 0xffffu) < need) B200_SPIN_WAIT();

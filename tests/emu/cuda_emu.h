@@ -91,6 +91,11 @@ static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
   for (int m = 16; m > 0; m >>= 1) { const unsigned o = emu_exchange(r, (int)((emu::g_threadIdx.x & 31) ^ m)); r = o < r ? o : r; }
   return r;
 }
+static inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+  unsigned r = v;
+  for (int m = 16; m > 0; m >>= 1) r += emu_exchange(r, (int)((emu::g_threadIdx.x & 31) ^ m));
+  return r;
+}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
