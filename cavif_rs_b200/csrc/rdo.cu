@@ -1143,8 +1143,9 @@ __global__ void __launch_bounds__(kThreads * (NMAX == 32 ? 2 : kReconWarps), NMA
   __syncthreads();
   const int warp = threadIdx.x >> 5;
   SH &sh = shs[warp];
+  const int n_warps = blockDim.x >> 5;       // <= kWarps (1 when the wavefront is switched off for debugging)
 #pragma unroll 1
-  for (int R = warp; R < sb_rows; R += kWarps) {
+  for (int R = warp; R < sb_rows; R += n_warps) {
     const int r = t.tr0 + R * 16;
     prefetch_sb_source(t, r, t.tc0);
 #pragma unroll 1
@@ -1229,12 +1230,15 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     cudaEventRecord((cudaEvent_t)analysis_done, st);
     if (sr != st) cudaStreamWaitEvent(sr, (cudaEvent_t)analysis_done, 0);
   }
+  static const bool serial_chain = getenv("B200AVIF_DEBUG_SERIAL_RECON") != nullptr;      // debugging aid: one warp per tile
   if (top == 3) {
-    if (high_bitdepth) b200_recon_kernel<true, 32><<<n_tiles, kThreads * 2, 0, sr>>>(d_jobs, d_tiles);
-    else b200_recon_kernel<false, 32><<<n_tiles, kThreads * 2, 0, sr>>>(d_jobs, d_tiles);
+    const int bt = kThreads * (serial_chain ? 1 : 2);
+    if (high_bitdepth) b200_recon_kernel<true, 32><<<n_tiles, bt, 0, sr>>>(d_jobs, d_tiles);
+    else b200_recon_kernel<false, 32><<<n_tiles, bt, 0, sr>>>(d_jobs, d_tiles);
   } else {
-    if (high_bitdepth) b200_recon_kernel<true, 16><<<n_tiles, kThreads * kReconWarps, 0, sr>>>(d_jobs, d_tiles);
-    else b200_recon_kernel<false, 16><<<n_tiles, kThreads * kReconWarps, 0, sr>>>(d_jobs, d_tiles);
+    const int bt = kThreads * (serial_chain ? 1 : kReconWarps);
+    if (high_bitdepth) b200_recon_kernel<true, 16><<<n_tiles, bt, 0, sr>>>(d_jobs, d_tiles);
+    else b200_recon_kernel<false, 16><<<n_tiles, bt, 0, sr>>>(d_jobs, d_tiles);
   }
   return (int)cudaGetLastError();
 }
