@@ -1,0 +1,26 @@
+"""Repeat the concurrent-encode scenario of tests/test_gpu_e2e.py and report WHAT differs (colour / alpha payload, sizes)."""
+import os, sys, threading
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cavif_rs_b200 as C
+import harness as H
+from test_gpu_e2e import payloads
+
+enc = C.Encoder.new().with_quality(65).with_speed(6)
+imgs = [H.synth_image(160 + 16 * i, 96 + 8 * i, 20 + i, alpha=(i % 3 == 0)) for i in range(8)]
+serial = [enc.encode_rgba(im).avif_file for im in imgs]
+again = [enc.encode_rgba(im).avif_file for im in imgs]
+print("serial repeat identical:", again == serial)
+for rnd in range(10):
+    out = [None] * len(imgs)
+    def work(i):
+        out[i] = enc.encode_rgba(imgs[i]).avif_file
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(imgs))]
+    for t in th: t.start()
+    for t in th: t.join()
+    for i in range(len(imgs)):
+        if out[i] != serial[i]:
+            c0, a0 = payloads(serial[i]); c1, a1 = payloads(out[i])
+            print("round", rnd, "image", i, "colour differs" if c0 != c1 else "colour same", len(c0), len(c1),
+                  "alpha differs" if a0 != a1 else "alpha same", None if a0 is None else len(a0), None if a1 is None else len(a1))
+print("done")
