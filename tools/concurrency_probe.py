@@ -6,12 +6,16 @@ import cavif_rs_b200 as C
 import harness as H
 from test_gpu_e2e import payloads
 
-enc = C.Encoder.new().with_quality(65).with_speed(6)
+enc = C.Encoder.new().with_quality(65).with_speed(int(os.environ.get('PROBE_SPEED', '6')))
+if os.environ.get('PROBE_DIRTY'):
+    enc = enc.with_alpha_color_mode(C.AlphaColorMode.UnassociatedDirty)
+if os.environ.get('PROBE_DEPTH'):
+    enc = enc.with_bit_depth(int(os.environ['PROBE_DEPTH']))
 imgs = [H.synth_image(160 + 16 * i, 96 + 8 * i, 20 + i, alpha=(i % 3 == 0)) for i in range(8)]
 serial = [enc.encode_rgba(im).avif_file for im in imgs]
 again = [enc.encode_rgba(im).avif_file for im in imgs]
 print("serial repeat identical:", again == serial)
-for rnd in range(10):
+for rnd in range(int(os.environ.get('PROBE_ROUNDS', '20'))):
     out = [None] * len(imgs)
     def work(i):
         out[i] = enc.encode_rgba(imgs[i]).avif_file
@@ -23,4 +27,4 @@ for rnd in range(10):
             c0, a0 = payloads(serial[i]); c1, a1 = payloads(out[i])
             print("round", rnd, "image", i, "colour differs" if c0 != c1 else "colour same", len(c0), len(c1),
                   "alpha differs" if a0 != a1 else "alpha same", None if a0 is None else len(a0), None if a1 is None else len(a1))
-print("done")
+print("done", {k: os.environ[k] for k in os.environ if k.startswith("PROBE") or k.startswith("B200AVIF")})
