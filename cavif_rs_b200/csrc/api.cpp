@@ -257,7 +257,12 @@ int rate_tables_for(Context &c, int qidx, B200RateTables **out) {
   b200av1_build_rate_tables(qidx, &host);
   B200RateTables *d = nullptr;
   CU(cudaMalloc((void **)&d, sizeof(host)));
-  CU(cudaMemcpy(d, &host, sizeof(host), cudaMemcpyHostToDevice));
+  // Stream-ordered upload + wait.  A plain cudaMemcpy from pageable memory returns once the data is STAGED: the DMA into
+  // `d` is ordered only against the legacy default stream, not against this context's non-blocking streams, so kernels
+  // launched right after could read the table before it arrived (seen as rare payload differences when concurrent calls
+  // make a context build a table it had not cached yet).
+  CU(cudaMemcpyAsync(d, &host, sizeof(host), cudaMemcpyHostToDevice, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
   c.d_rate[qidx] = d;
   *out = d;
   return 0;
