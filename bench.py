@@ -43,9 +43,9 @@ WORKLOADS = {
 #   reconstruction: 3 source planes read, 3 reconstructed planes + 3 coefficient planes written, records      6 + 6 + 6 + 0.9 = 18.9
 RDO_BYTES_PER_PX = 24 + 9.2 + 2.6 + 18.9
 # ncu dram__bytes_read.sum + dram__bytes_write.sum of the RDO stage group over one 64-image step
-# (profiles/r01_final_kernel_times_and_dram.txt: 12.27 GB read + 6.76 GB written over the 4 steps of that run); below the
+# (profiles/r01_final_kernel_times_and_dram.txt: 14.05 GB read + 6.79 GB written over the 4 steps of that run); below the
 # algorithmic figure because pruned levels are not read and the 126 MB L2 serves most re-reads of the source planes
-TRAFFIC_BYTES_PER_STEP = {"1080p": 4.76e9}
+TRAFFIC_BYTES_PER_STEP = {"1080p": 5.21e9}
 
 
 def make_images(wl, seed0=0):
