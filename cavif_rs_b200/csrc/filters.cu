@@ -161,37 +161,8 @@ __device__ void cdef_direction(const uint16_t *img, int stride, int bd, int *dir
   *var_out = (bc - cost[(best + 4) & 7]) >> 10;
 }
 
-// CDEF output of one pixel (plane p, position x0,y0) of a non-skip 8x8 block for strength pair (pri, sec)
-__device__ __forceinline__ int cdef_pixel(const uint16_t *I, int stride, int W, int H, int x0, int y0, int pri, int sec, int dir,
-                                          int damping, int cshift) {
-  const int x = I[y0 * stride + x0];
-  if (!pri && !sec) return x;
-  const int pt0 = ((pri >> cshift) & 1) ? 3 : 4, pt1 = ((pri >> cshift) & 1) ? 3 : 2;
-  int sum = 0, mx = x, mn = x;
-#pragma unroll
-  for (int k = 0; k < 2; k++)
-#pragma unroll
-    for (int sgn = -1; sgn <= 1; sgn += 2) {
-      int yy = y0 + sgn * dv_cdef_dir[dir][k][0], xx = x0 + sgn * dv_cdef_dir[dir][k][1];
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-        const int v = I[yy * stride + xx];
-        sum += (k == 0 ? pt0 : pt1) * constrain_d(v - x, pri, damping);
-        mx = max(mx, v); mn = min(mn, v);
-      }
-#pragma unroll
-      for (int doff = -2; doff <= 2; doff += 4) {
-        const int d2 = (dir + doff) & 7;
-        yy = y0 + sgn * dv_cdef_dir[d2][k][0]; xx = x0 + sgn * dv_cdef_dir[d2][k][1];
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-          const int v = I[yy * stride + xx];
-          sum += (k == 0 ? 2 : 1) * constrain_d(v - x, sec, damping);
-          mx = max(mx, v); mn = min(mn, v);
-        }
-      }
-    }
-  return clip3_d(mn, mx, x + ((8 + sum - (sum < 0)) >> 4));
-}
-// Same filter on a staged (64 + 4)^2 tile of the superblock (kCdefTW samples per row, 2-sample border, kCdefNA marks
+// CDEF output of one pixel of a non-skip 8x8 block for strength pair (pri, sec) (AV1 spec 7.15.2), read from a
+// staged (64 + 4)^2 tile of the superblock (kCdefTW samples per row, 2-sample border, kCdefNA marks
 // samples outside the frame): lx, ly = position inside the superblock.
 constexpr int kCdefTW = 68;
 constexpr uint16_t kCdefNA = 0xFFFF;

@@ -1,14 +1,19 @@
-// AV1 intra rate-distortion search on the device, in three stages (v4):
+// AV1 intra rate-distortion search on the device, in three stages:
 //
-//   A. ANALYSIS (open loop, embarrassingly parallel).  Every block of every level (4x4, 8x8, 16x16) of every image is
-//      analysed independently, predicting from SOURCE neighbours: SATD ranking of the 13 intra modes
-//      (b200_satd_kernel: one thread per (block, plane group)), then full trials of the top-2 modes x transform types
-//      and of the top-2 chroma modes (b200_analyze_kernel: one warp per block, lane-batched candidates: lane group
-//      g = lane / N owns one candidate, lane l = lane % N owns column l / row l of its transform; butterflies in
-//      registers, transpose through shared memory, quantiser / rate / dequantiser on the row, SSE by shuffles).
-//   B. PARTITION DECISION (b200_decide_kernel: one thread per 16x16 region) from the analysed RD costs.
-//   C. RECONSTRUCTION (closed loop, b200_recon_kernel: one warp per TILE): the only stage that needs reconstructed
-//      neighbours; one trial per decided block and plane, Y/U/V batched over the lane groups.
+//   A. ANALYSIS (open loop, embarrassingly parallel).  Every block of every level (4x4, 8x8, 16x16, 32x32 when the
+//      partition range reaches it) of every image is analysed independently, predicting from SOURCE neighbours, from
+//      the largest level down so that a level can be pruned by its parent (b200_pruned_by_parent, records.h):
+//      luma SATD ranking of the 13 intra modes + angle refinement (b200_satd_direct_kernel for the never-pruned top
+//      level, b200_satd_kernel with per-CTA compaction of the surviving blocks below it: one thread per block), then
+//      full trials of the top-2 luma modes x transform types and of the chroma candidates {luma mode, DC, CFL}
+//      (b200_analyze_kernel: one warp per block, lane-batched candidates: lane group g = lane / N owns one candidate,
+//      lane l = lane % N owns column l / row l of its transform; butterflies in registers, transpose through shared
+//      memory, quantiser / rate / dequantiser on the row, SSE by shuffles; the top level runs its warps in lock-step
+//      CTAs for instruction-cache locality).
+//   B. PARTITION DECISION (b200_decide_kernel: one thread per root region, NONE vs SPLIT recursively).
+//   C. RECONSTRUCTION (closed loop, b200_recon_kernel: one CTA per TILE, warps on a superblock-row wavefront): the only
+//      stage that needs reconstructed neighbours; one trial per decided block and plane, Y/U/V batched over the lane
+//      groups, CFL chroma after its luma.
 //
 // Only stage C is a serial chain (a tile's blocks depend on their left/top reconstruction); stages A/B carry >95 % of
 // the arithmetic and scale with the number of blocks in the batch.
@@ -19,7 +24,7 @@
 // (encoder freedom; the bitstream and the reconstruction stay exact).  The bit-exact CPU restatement of THIS file is
 // oracle/av1_encode.c; tests/test_gpu_parity.py compares every stage.
 //
-// No tensor cores on purpose: the work is 4..16-point integer butterflies with normative rounding at every stage
+// No tensor cores on purpose: the work is 4..32-point integer butterflies with normative rounding at every stage
 // (BASELINE.json north_star).
 #ifdef B200_EMU
 #include "cuda_emu.h"
