@@ -570,7 +570,7 @@ void write_sequence_header(const B200Frame &f, BitWriter &b) {
   b.put(f.height - 1, hb);
   b.put(0, 1);   // use_128x128_superblock
   b.put(0, 1);   // enable_filter_intra
-  b.put(0, 1);   // enable_intra_edge_filter
+  b.put(f.enable_intra_edge_filter ? 1 : 0, 1);   // enable_intra_edge_filter
   b.put(0, 1);   // enable_superres
   b.put(f.enable_cdef ? 1 : 0, 1);
   b.put(f.enable_restoration ? 1 : 0, 1);

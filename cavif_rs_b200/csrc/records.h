@@ -66,6 +66,7 @@ typedef struct B200Frame {
   int32_t rdo_tx_decision;                  // search transform type per block
   int32_t fine_directional_intra;           // angle_delta search
   int32_t enable_cfl;
+  int32_t enable_intra_edge_filter;          // sequence-header tool: edge smoothing / upsampling of directional predictors (AV1 spec 7.11.2.4)
   int32_t lambda_q8;                        // RD multiplier: J = (SSE << 8) + ((lambda_q8 * R_q8) >> 8), R in 1/256 bit
   int32_t lambda_satd_q8;                   // pre-ranking: J = satd * 64 + ((lambda_satd_q8 * R_q8) >> 8)
   int32_t y_mode_mask, uv_mode_mask;        // allowed intra modes (bit = mode index); conformance tests force single modes

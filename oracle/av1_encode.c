@@ -97,9 +97,126 @@ static const uint8_t *sm_weights(int n) {
 }
 
 /* AV1 spec 7.11.2.x intra predictors for an n x n block. angle_delta in -3..3. */
+/* ---- intra edge filter and upsampling of the directional predictors (AV1 spec 7.11.2.7 - 7.11.2.12), applied on
+ * private copies of the edges.  filter_type: 0 / 1 = get_filter_type() (a smooth-mode neighbour above or left). */
+static int ief_strength(int blk_wh, int filter_type, int delta) {                 /* 7.11.2.9 */
+  const int d = abs(delta);
+  int s = 0;
+  if (filter_type == 0) {
+    if (blk_wh <= 8) { if (d >= 56) s = 1; }
+    else if (blk_wh <= 16) { if (d >= 40) s = 1; }
+    else if (blk_wh <= 24) { if (d >= 8) s = 1; if (d >= 16) s = 2; if (d >= 32) s = 3; }
+    else if (blk_wh <= 32) { if (d >= 1) s = 1; if (d >= 4) s = 2; if (d >= 32) s = 3; }
+    else { if (d >= 1) s = 3; }
+  } else {
+    if (blk_wh <= 8) { if (d >= 40) s = 1; if (d >= 64) s = 2; }
+    else if (blk_wh <= 16) { if (d >= 20) s = 1; if (d >= 48) s = 2; }
+    else if (blk_wh <= 24) { if (d >= 4) s = 3; }
+    else { if (d >= 1) s = 3; }
+  }
+  return s;
+}
+static int ief_upsample(int blk_wh, int filter_type, int delta) {                 /* 7.11.2.10 */
+  const int d = abs(delta);
+  if (d <= 0 || d >= 40) return 0;
+  return filter_type == 0 ? blk_wh <= 16 : blk_wh <= 8;
+}
+static void ief_filter(uint16_t *buf /* index -1 .. sz-2 */, int sz, int strength) {   /* 7.11.2.12 */
+  static const int kern[3][5] = {{0, 4, 8, 4, 0}, {0, 5, 6, 5, 0}, {2, 4, 4, 4, 2}};
+  if (!strength) return;
+  uint16_t edge[160];
+  for (int i = 0; i < sz; i++) edge[i] = buf[i - 1];
+  for (int i = 1; i < sz; i++) {
+    int sum = 0;
+    for (int j = 0; j < 5; j++) {
+      int k = i - 2 + j;
+      k = k < 0 ? 0 : (k > sz - 1 ? sz - 1 : k);
+      sum += kern[strength - 1][j] * edge[k];
+    }
+    buf[i - 1] = (uint16_t)((sum + 8) >> 4);
+  }
+}
+static void ief_upsample_edge(uint16_t *buf /* index -2 .. 2*num_px-2 */, int num_px, int bd) {   /* 7.11.2.11 */
+  int dup[160];
+  dup[0] = buf[-1];
+  for (int i = -1; i < num_px; i++) dup[i + 2] = buf[i];
+  dup[num_px + 2] = buf[num_px - 1];
+  buf[-2] = (uint16_t)dup[0];
+  const int mx = (1 << bd) - 1;
+  for (int i = 0; i < num_px; i++) {
+    int v = -dup[i] + 9 * dup[i + 1] + 9 * dup[i + 2] - dup[i + 3];
+    v = (v + 8) >> 4;
+    buf[2 * i - 1] = (uint16_t)(v < 0 ? 0 : (v > mx ? mx : v));
+    buf[2 * i] = (uint16_t)dup[i + 2];
+  }
+}
+/* directional prediction with the edge filter enabled (spec 7.11.2.4) */
+static void predict_directional_ief(int p_angle, int n, const uint16_t *A0, const uint16_t *L0, int have_above, int have_left,
+                                    int bit_depth, int filter_type, uint16_t *pred) {
+  uint16_t Ab[EOFF + 160], Lb[EOFF + 160];
+  uint16_t *A = Ab + EOFF, *L = Lb + EOFF;
+  for (int i = -1; i < 2 * n; i++) { A[i] = A0[i]; L[i] = L0[i]; }
+  int up_a = 0, up_l = 0;
+  if (p_angle != 90 && p_angle != 180) {
+    if (p_angle > 90 && p_angle < 180 && 2 * n >= 24) {          /* 7.11.2.7 corner filter */
+      const int c = (L[0] * 5 + A[-1] * 6 + A[0] * 5 + 8) >> 4;
+      A[-1] = L[-1] = (uint16_t)c;
+    }
+    if (have_above) ief_filter(A, n + (p_angle < 90 ? n : 0) + 1, ief_strength(2 * n, filter_type, p_angle - 90));
+    if (have_left) ief_filter(L, n + (p_angle > 180 ? n : 0) + 1, ief_strength(2 * n, filter_type, p_angle - 180));
+  }
+  up_a = ief_upsample(2 * n, filter_type, p_angle - 90);
+  if (up_a) ief_upsample_edge(A, n + (p_angle < 90 ? n : 0), bit_depth);
+  up_l = ief_upsample(2 * n, filter_type, p_angle - 180);
+  if (up_l) ief_upsample_edge(L, n + (p_angle > 180 ? n : 0), bit_depth);
+  if (p_angle == 90) { for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) pred[i * n + j] = A[j]; return; }
+  if (p_angle == 180) { for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) pred[i * n + j] = L[i]; return; }
+  if (p_angle < 90) {
+    const int dx = av1_dr_intra_derivative[p_angle], max_base = (2 * n - 1) << up_a;
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        const int idx = (i + 1) * dx, base = (idx >> (6 - up_a)) + (j << up_a), shift = ((idx << up_a) >> 1) & 31;
+        pred[i * n + j] = base < max_base ? (uint16_t)((A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5) : A[max_base];
+      }
+  } else if (p_angle < 180) {
+    const int dx = av1_dr_intra_derivative[180 - p_angle], dy = av1_dr_intra_derivative[p_angle - 90];
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        int idx = (j << 6) - (i + 1) * dx, base = idx >> (6 - up_a);
+        if (base >= -(1 << up_a)) {
+          const int shift = ((idx << up_a) >> 1) & 31;
+          pred[i * n + j] = (uint16_t)((A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5);
+        } else {
+          idx = (i << 6) - (j + 1) * dy; base = idx >> (6 - up_l);
+          const int shift = ((idx << up_l) >> 1) & 31;
+          pred[i * n + j] = (uint16_t)((L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5);
+        }
+      }
+  } else {
+    const int dy = av1_dr_intra_derivative[270 - p_angle];
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        const int idx = (j + 1) * dy, base = (idx >> (6 - up_l)) + (i << up_l), shift = ((idx << up_l) >> 1) & 31;
+        pred[i * n + j] = (uint16_t)((L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5);
+      }
+  }
+}
+
+void orc_predict_intra_ef(int mode, int angle_delta, int n, const uint16_t *above, const uint16_t *left, int have_above,
+                          int have_left, int bit_depth, int filter_type, uint16_t *pred);
+/* edge filter disabled (sequence header enable_intra_edge_filter = 0; also the SATD pre-ranking of every frame) */
 void orc_predict_intra(int mode, int angle_delta, int n, const uint16_t *above, const uint16_t *left, int have_above,
                        int have_left, int bit_depth, uint16_t *pred /* n*n */) {
+  orc_predict_intra_ef(mode, angle_delta, n, above, left, have_above, have_left, bit_depth, -1, pred);
+}
+/* filter_type: -1 = edge filter off, 0 / 1 = on with that get_filter_type() result */
+void orc_predict_intra_ef(int mode, int angle_delta, int n, const uint16_t *above, const uint16_t *left, int have_above,
+                          int have_left, int bit_depth, int filter_type, uint16_t *pred /* n*n */) {
   const uint16_t *A = above + EOFF, *L = left + EOFF;
+  if (filter_type >= 0 && mode >= V_PRED && mode <= D67_PRED) {
+    predict_directional_ief(av1_mode_to_angle[mode] + angle_delta * 3, n, A, L, have_above, have_left, bit_depth, filter_type, pred);
+    return;
+  }
   if (mode == DC_PRED) {
     int v;
     if (have_above && have_left) { int s = 0; for (int i = 0; i < n; i++) s += A[i] + L[i]; v = (s + n) / (2 * n); }
@@ -409,6 +526,9 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
   int ha = 0, hl = 0;
   for (int p = 0; p < f->planes; p++) build_edges(e, e->src[p], x, y, n, A[p], L[p], &ha, &hl);
   const uint16_t *ymode_cost = rt->y_mode[0][0];
+  /* open loop: the neighbours' modes are not known yet, the trials assume get_filter_type() = 0; the SATD pre-ranking
+   * and the angle refinement use the unfiltered edges */
+  const int ief = f->enable_intra_edge_filter ? 0 : -1;
   /* luma SATD of the nominal modes (the device computes this table in the SATD kernels) */
   for (int m = 0; m < 13; m++) {
     satd_y[m] = 0;
@@ -449,7 +569,7 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
     for (int k = 0; k < 2; k++) {
       const int m = bm[k];
       if (m < 0) continue;
-      orc_predict_intra(m, DELTA_Y(m), n, A[0], L[0], ha, hl, f->bit_depth, pred);
+      orc_predict_intra_ef(m, DELTA_Y(m), n, A[0], L[0], ha, hl, f->bit_depth, ief, pred);
       const uint32_t mrate = mode_rate(rt, ymode_cost, m, n, DELTA_Y(m));
       for (int t = 0; t < 5; t++) {
         const int tt = k_tx_types[t];
@@ -480,9 +600,9 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
       const int ctt = chroma_tx_type(m, n);
       uint16_t e1, e2;
       uint32_t r1, r2;
-      orc_predict_intra(m, DELTA_UV(m), n, A[1], L[1], ha, hl, f->bit_depth, pred);
+      orc_predict_intra_ef(m, DELTA_UV(m), n, A[1], L[1], ha, hl, f->bit_depth, ief, pred);
       uint64_t d = trial_plane(e, 1, x, y, n, pred, ctt, best_mode, qc, &e1, recon, &r1);
-      orc_predict_intra(m, DELTA_UV(m), n, A[2], L[2], ha, hl, f->bit_depth, pred);
+      orc_predict_intra_ef(m, DELTA_UV(m), n, A[2], L[2], ha, hl, f->bit_depth, ief, pred);
       d += trial_plane(e, 2, x, y, n, pred, ctt, best_mode, qc, &e2, recon, &r2);
       const int64_t J = rd_cost(f, d, r1 + r2 + mode_rate(rt, uvcost, m, n, DELTA_UV(m)));
       if (J < bestC) { bestC = J; uv_best = m; eob_u = e1; eob_v = e2; }
@@ -591,7 +711,17 @@ static void reconstruct_block(enc_t *e, int x, int y, int n) {
       orc_predict_intra(DC_PRED, 0, n, A, L, ha, hl, f->bit_depth, pred);
       cfl_predict(ac, n, pred[0], p == 1 ? au : av, f->bit_depth, pred);
     } else {
-      orc_predict_intra(mode, (p == 0 ? (m.angle & 15) : (m.angle >> 4)) - 3, n, A, L, ha, hl, f->bit_depth, pred);
+      int ief = -1;
+      if (f->enable_intra_edge_filter) {      /* get_filter_type (spec 7.11.2.8): a smooth mode above or to the left */
+        ief = 0;
+        for (int side = 0; side < 2; side++) {
+          if (side == 0 ? !ha : !hl) continue;
+          const B200Mi *nb = &e->mi[(side == 0 ? mi_r - 1 : mi_r) * f->mi_cols + (side == 0 ? mi_c : mi_c - 1)];
+          const int nm = p == 0 ? nb->y_mode : nb->uv_mode;
+          if (nm == SMOOTH_PRED || nm == SMOOTH_V_PRED || nm == SMOOTH_H_PRED) ief = 1;
+        }
+      }
+      orc_predict_intra_ef(mode, (p == 0 ? (m.angle & 15) : (m.angle >> 4)) - 3, n, A, L, ha, hl, f->bit_depth, ief, pred);
     }
     uint16_t eobv;
     uint32_t rate;

@@ -13,7 +13,7 @@ class B200Frame(ctypes.Structure):
         (n, ctypes.c_int32) for n in (
         "base_q_idx", "dc_q", "ac_q", "reduced_tx_set", "enable_cdef", "enable_restoration",
         "color_description_present", "color_primaries", "transfer_characteristics", "matrix_coefficients", "full_range",
-        "partition_min", "partition_max", "rdo_tx_decision", "fine_directional_intra", "enable_cfl",
+        "partition_min", "partition_max", "rdo_tx_decision", "fine_directional_intra", "enable_cfl", "enable_intra_edge_filter",
         "lambda_q8", "lambda_satd_q8", "y_mode_mask", "uv_mode_mask", "tx_type_mask")] + [
         ("split_gate_bits", ctypes.c_int32 * 3),
         ("lf_level", ctypes.c_int32 * 4), ("lf_sharpness", ctypes.c_int32),

@@ -10,10 +10,11 @@ pytestmark = pytest.mark.skipif(not dav1d.available(), reason="dav1d not availab
 
 
 def roundtrip(w, h, depth=8, planes=3, q=121, tiles=1, ymask=0x1fff, uvmask=0x1fff, txmask=0x1f, pmin=4, pmax=16, rdo_tx=1,
-              seed=0, reduced=1):
+              seed=0, reduced=1, ief=0):
     f = H.frame_setup(w, h, depth, planes, q, tiles)
     f.y_mode_mask = ymask; f.uv_mode_mask = uvmask; f.tx_type_mask = txmask
     f.partition_min = pmin; f.partition_max = pmax; f.rdo_tx_decision = rdo_tx; f.reduced_tx_set = reduced
+    f.enable_intra_edge_filter = ief
     rt = H.rate_tables(f.base_q_idx)
     img = H.synth_image(w, h, seed)
     pl = [img[..., c].astype(np.uint16) * (4 if depth == 10 else 1) for c in range(planes)]
@@ -107,3 +108,23 @@ def test_32x32_partitions(w, h, depth, planes, q, tiles):
     n8, _ = roundtrip(w, h, depth=depth, planes=planes, q=q, tiles=tiles, pmin=8, pmax=32, seed=w)
     n16, _ = roundtrip(w, h, depth=depth, planes=planes, q=q, tiles=tiles, pmin=16, pmax=32, rdo_tx=0, seed=w)
     assert n8 > 0 and n16 > 0
+
+
+@pytest.mark.parametrize("mode", range(1, 9))
+@pytest.mark.parametrize("size", [4, 8, 16, 32])
+def test_intra_edge_filter_each_directional_mode_and_size(mode, size):
+    """enable_intra_edge_filter = 1: every directional mode (with its refined angle deltas) at every block size, so that
+    every strength class, the corner filter (>= 16x16) and the edge upsampling (<= 8x8) are decoded by dav1d"""
+    pmin = min(size, 8) if size >= 8 else 4
+    for depth, q in ((8, 100), (10, 160)):
+        n, _ = roundtrip(136, 104, depth=depth, q=q, ymask=(1 << mode) | 1, uvmask=0x1fff, pmin=pmin if size < 16 else size, pmax=size,
+                         rdo_tx=0, seed=mode * 10 + size, ief=1)
+        assert n > 0
+
+
+@pytest.mark.parametrize("w,h,depth,planes,q,tiles,pmax", [(200, 136, 8, 3, 121, 2, 16), (161, 100, 10, 3, 147, 1, 32), (95, 95, 8, 1, 100, 1, 16),
+                                                        (256, 192, 8, 3, 60, 4, 32)])
+def test_intra_edge_filter_full_search(w, h, depth, planes, q, tiles, pmax):
+    """all tools on (smooth neighbours change the filter type of the closed-loop reconstruction)"""
+    n, _ = roundtrip(w, h, depth=depth, planes=planes, q=q, tiles=tiles, pmax=pmax, seed=w, ief=1)
+    assert n > 0
