@@ -236,6 +236,7 @@ int configure_frame(B200Frame *f, size_t w, size_t h, int depth, bool mono, int 
   f->partition_max = std::min(tw.partition_max, 32);      // 64x64 blocks (speed 1) are clamped to 32x32
   f->partition_min = std::min(f->partition_min, f->partition_max);
   f->fine_directional_intra = tw.fine_directional_intra;
+  f->enable_intra_edge_filter = 1;     // rav1e's sequence headers always enable the intra edge filter [EXT]
   // early termination of the partition search (records.h split_gate_bits): exhaustive at the slow presets
   f->split_gate_bits[0] = speed <= 2 ? 0 : 60;
   f->split_gate_bits[1] = speed <= 2 ? 0 : 120;

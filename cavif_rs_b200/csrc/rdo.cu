@@ -78,6 +78,7 @@ struct SharedT {
   static constexpr int kPredStride = NMAX * NMAX;          // one prediction slot (luma: two ranked modes, two slots)
   uint16_t src[3][NMAX * NMAX];
   uint16_t above[3][EOFF + 2 * NMAX + 2], left[3][EOFF + 2 * NMAX + 2];
+  uint16_t ef[2][EOFF + 2 * NMAX + 8];   // intra edge filter: filtered / upsampled private copy of one plane's edges
   uint16_t pred[2 * NMAX * NMAX];   // luma: predictions of the two ranked modes; chroma: up to G (mode rank, plane) predictions
   int32_t buf[32 * (NMAX + 1)];     // G groups x N rows x (N+1): transform transpose staging
   alignas(16) uint8_t lev[NMAX == 32 ? 1296 : 800];   // per group (N+4)^2 padded |level| map (rate contexts)
@@ -508,6 +509,116 @@ __device__ __forceinline__ uint32_t mode_rate(const B200RateTables *rt, const ui
   return r;
 }
 
+// ---- intra edge filter / upsampling (AV1 spec 7.11.2.7 - 7.11.2.12; oracle predict_directional_ief), warp-cooperative
+__device__ __forceinline__ int ief_strength(int blk_wh, int filter_type, int delta) {
+  const int d = abs(delta);
+  int s = 0;
+  if (filter_type == 0) {
+    if (blk_wh <= 8) { if (d >= 56) s = 1; }
+    else if (blk_wh <= 16) { if (d >= 40) s = 1; }
+    else if (blk_wh <= 24) { if (d >= 8) s = 1; if (d >= 16) s = 2; if (d >= 32) s = 3; }
+    else if (blk_wh <= 32) { if (d >= 1) s = 1; if (d >= 4) s = 2; if (d >= 32) s = 3; }
+    else { if (d >= 1) s = 3; }
+  } else {
+    if (blk_wh <= 8) { if (d >= 40) s = 1; if (d >= 64) s = 2; }
+    else if (blk_wh <= 16) { if (d >= 20) s = 1; if (d >= 48) s = 2; }
+    else if (blk_wh <= 24) { if (d >= 4) s = 3; }
+    else { if (d >= 1) s = 3; }
+  }
+  return s;
+}
+__device__ __forceinline__ int ief_use_upsample(int blk_wh, int filter_type, int delta) {
+  const int d = abs(delta);
+  if (d <= 0 || d >= 40) return 0;
+  return filter_type == 0 ? blk_wh <= 16 : blk_wh <= 8;
+}
+// buf: index -1 .. sz-2 filtered in place (entries 0 .. sz-2 change), sz <= 65
+__device__ __forceinline__ void ief_filter_edge(uint16_t *buf, int sz, int strength) {
+  if (strength) {
+    const int k0 = strength == 3 ? 2 : 0, k1 = strength == 1 ? 4 : (strength == 2 ? 5 : 4), k2 = strength == 1 ? 8 : (strength == 2 ? 6 : 4);
+    uint16_t o[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const int i = 1 + lane_id() + 32 * r;
+      int sum = 0;
+      if (i < sz) {
+        const int e0 = buf[max(i - 2, 0) - 1], e1 = buf[i - 2], e2 = buf[i - 1], e3 = buf[min(i + 1, sz - 1) - 1], e4 = buf[min(i + 2, sz - 1) - 1];
+        sum = k0 * (e0 + e4) + k1 * (e1 + e3) + k2 * e2;
+      }
+      o[r] = (uint16_t)((sum + 8) >> 4);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 3; r++) { const int i = 1 + lane_id() + 32 * r; if (i < sz) buf[i - 1] = o[r]; }
+  }
+  __syncwarp();
+}
+// buf: index -2 .. 2 * num_px - 2 after the call, num_px <= 16
+__device__ __forceinline__ void ief_upsample_edge(uint16_t *buf, int num_px, int bd) {
+  const int i = lane_id();
+  int v = 0, m = 0;
+  const int corner = buf[-1];
+  if (i < num_px) {
+    const int d0 = i == 0 ? corner : buf[i - 2], d1 = buf[i - 1], d2 = buf[i], d3 = buf[min(i + 1, num_px - 1)];
+    v = (-d0 + 9 * d1 + 9 * d2 - d3 + 8) >> 4;
+    const int mx = (1 << bd) - 1;
+    v = v < 0 ? 0 : (v > mx ? mx : v);
+    m = d2;
+  }
+  __syncwarp();
+  if (i < num_px) { buf[2 * i - 1] = (uint16_t)v; buf[2 * i] = (uint16_t)m; }
+  if (i == 0) buf[-2] = (uint16_t)corner;
+  __syncwarp();
+}
+__device__ __forceinline__ int pred_dir_px(int p_angle, int n, int i, int j, const uint16_t *A, const uint16_t *L, int up_a, int up_l) {
+  if (p_angle == 90) return A[j];
+  if (p_angle == 180) return L[i];
+  if (p_angle < 90) {
+    const int dx = dv_dr_intra_derivative[p_angle], max_base = (2 * n - 1) << up_a;
+    const int idx = (i + 1) * dx, base = (idx >> (6 - up_a)) + (j << up_a), shift = ((idx << up_a) >> 1) & 31;
+    return base < max_base ? (A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5 : A[max_base];
+  }
+  if (p_angle < 180) {
+    const int dx = dv_dr_intra_derivative[180 - p_angle], dy = dv_dr_intra_derivative[p_angle - 90];
+    int idx = (j << 6) - (i + 1) * dx, base = idx >> (6 - up_a);
+    if (base >= -(1 << up_a)) {
+      const int shift = ((idx << up_a) >> 1) & 31;
+      return (A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5;
+    }
+    idx = (i << 6) - (j + 1) * dy; base = idx >> (6 - up_l);
+    const int shift = ((idx << up_l) >> 1) & 31;
+    return (L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5;
+  }
+  const int dy = dv_dr_intra_derivative[270 - p_angle];
+  const int idx = (j + 1) * dy, base = (idx >> (6 - up_l)) + (i << up_l), shift = ((idx << up_l) >> 1) & 31;
+  return (L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5;
+}
+// directional mode with the edge filter on: ef[0] / ef[1] receive the private copies of the edges
+__device__ __noinline__ void predict_block_ief(int mode, int delta, int lg, const uint16_t *above, const uint16_t *left, int ha, int hl,
+                                               int bd, int ftype, uint16_t *ef_a, uint16_t *ef_l, uint16_t *dst) {
+  const int n = 1 << lg, p_angle = dv_mode_to_angle[mode] + 3 * delta;
+  uint16_t *A = ef_a + EOFF, *L = ef_l + EOFF;
+#pragma unroll 1
+  for (int i = lane_id() - 1; i < 2 * n; i += 32) { A[i] = above[EOFF + i]; L[i] = left[EOFF + i]; }
+  __syncwarp();
+  if (p_angle != 90 && p_angle != 180) {
+    if (p_angle > 90 && p_angle < 180 && n >= 16) {
+      const int c = (L[0] * 5 + A[-1] * 6 + A[0] * 5 + 8) >> 4;
+      __syncwarp();
+      if (lane_id() == 0) { A[-1] = (uint16_t)c; L[-1] = (uint16_t)c; }
+      __syncwarp();
+    }
+    if (ha) ief_filter_edge(A, n + (p_angle < 90 ? n : 0) + 1, ief_strength(2 * n, ftype, p_angle - 90));
+    if (hl) ief_filter_edge(L, n + (p_angle > 180 ? n : 0) + 1, ief_strength(2 * n, ftype, p_angle - 180));
+  }
+  const int up_a = ief_use_upsample(2 * n, ftype, p_angle - 90), up_l = ief_use_upsample(2 * n, ftype, p_angle - 180);
+  if (up_a) ief_upsample_edge(A, n + (p_angle < 90 ? n : 0), bd);
+  if (up_l) ief_upsample_edge(L, n + (p_angle > 180 ? n : 0), bd);
+#pragma unroll 1
+  for (int p = lane_id(); p < n * n; p += 32) dst[p] = (uint16_t)pred_dir_px(p_angle, n, p >> lg, p & (n - 1), A, L, up_a, up_l);
+  __syncwarp();
+}
+
 // whole-block prediction into shared memory, pixels spread over the 32 lanes (the only place pred_px is expanded)
 __device__ __noinline__ void predict_block(int mode, int delta, int lg, const uint16_t *above, const uint16_t *left, int ha, int hl, int bd,
                                            uint16_t *dst) {
@@ -516,6 +627,14 @@ __device__ __noinline__ void predict_block(int mode, int delta, int lg, const ui
   const int dc = mode == DC_PRED ? dc_value_warp(n, A, L, ha, hl, bd) : 0;
 #pragma unroll 1
   for (int p = lane_id(); p < n * n; p += 32) dst[p] = (uint16_t)pred_px(mode, delta, n, p >> lg, p & (n - 1), A, L, dc);
+}
+
+// ftype: -1 = intra edge filter off, 0 / 1 = on with that filter type
+template <class SH>
+__device__ __forceinline__ void predict_any(SH &sh, int ftype, int mode, int delta, int lg, const uint16_t *above, const uint16_t *left, int ha,
+                                            int hl, int bd, uint16_t *dst) {
+  if (ftype >= 0 && mode >= V_PRED && mode <= D67_PRED) predict_block_ief(mode, delta, lg, above, left, ha, hl, bd, ftype, sh.ef[0], sh.ef[1], dst);
+  else predict_block(mode, delta, lg, above, left, ha, hl, bd, dst);
 }
 
 // ---- chroma from luma (oracle cfl_ac / cfl_pick_alpha / cfl_predict), pixels spread over the 32 lanes
@@ -627,8 +746,10 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, SH &sh, int x, i
   const int tx_mask = n == 32 ? 1 : f->tx_type_mask;      // 32x32: the intra transform set is DCT only
   int first_t = -1;
   for (int k = 0; k < 5; k++) if ((tx_mask >> k) & 1) { first_t = k; break; }
-  predict_block(m0 >= 0 ? m0 : 0, DELTA_Y(m0 >= 0 ? m0 : 0), lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred);
-  predict_block(m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0), DELTA_Y(m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0)), lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred + PS);
+  // open loop: the neighbours' modes are not decided yet, the trials assume filter type 0 (oracle)
+  const int ief = f->enable_intra_edge_filter ? 0 : -1;
+  predict_any(sh, ief, m0 >= 0 ? m0 : 0, DELTA_Y(m0 >= 0 ? m0 : 0), lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred);
+  predict_any(sh, ief, m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0), DELTA_Y(m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0)), lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred + PS);
   __syncwarp();
   long long bestJ = kInf;
   int bestC = 1 << 20, bestEob = 0;
@@ -695,7 +816,7 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, SH &sh, int x, i
         if (kk == 2) cfl_predict_block(sh.ac, N2, pp == 1 ? dc_u : dc_v, pp == 1 ? al_u : al_v, bd, dst);
         else {
           const int mm = kk == 0 ? u0 : u1;
-          predict_block(mm >= 0 ? mm : 0, DELTA_UV(mm >= 0 ? mm : 0), lg, sh.above[pp], sh.left[pp], ha, hl, bd, dst);
+          predict_any(sh, ief, mm >= 0 ? mm : 0, DELTA_UV(mm >= 0 ? mm : 0), lg, sh.above[pp], sh.left[pp], ha, hl, bd, dst);
         }
       }
       __syncwarp();
@@ -774,7 +895,15 @@ __device__ __noinline__ void reconstruct_block(const TileCtx &t, SH &sh, int x, 
       if (cfl && pp > 0)
         cfl_predict_block(sh.ac, N2, dc_value_warp(n, sh.above[pp] + EOFF, sh.left[pp] + EOFF, ha, hl, bd), pp == 1 ? au : av, bd, dst);
       else
-        predict_block(pp == 0 ? m.y_mode : m.uv_mode, (pp == 0 ? (m.angle & 15) : (m.angle >> 4)) - 3, lg, sh.above[pp], sh.left[pp], ha, hl, bd, dst);
+      {
+        int ief = -1;
+        if (f->enable_intra_edge_filter) {     // get_filter_type (spec 7.11.2.8): a smooth mode above or to the left
+          ief = 0;
+          if (ha) { const B200Mi nb = t.mi[(mi_r - 1) * f->mi_cols + mi_c]; const int nm = pp == 0 ? nb.y_mode : nb.uv_mode; if (nm >= SMOOTH_PRED && nm <= SMOOTH_H_PRED) ief = 1; }
+          if (hl) { const B200Mi nb = t.mi[mi_r * f->mi_cols + mi_c - 1]; const int nm = pp == 0 ? nb.y_mode : nb.uv_mode; if (nm >= SMOOTH_PRED && nm <= SMOOTH_H_PRED) ief = 1; }
+        }
+        predict_any(sh, ief, pp == 0 ? m.y_mode : m.uv_mode, (pp == 0 ? (m.angle & 15) : (m.angle >> 4)) - 3, lg, sh.above[pp], sh.left[pp], ha, hl, bd, dst);
+      }
     }
     __syncwarp();
     const int p = p0 + g;

@@ -48,6 +48,7 @@ def configure(w, h, depth, planes, quantizer, speed, threads=None):
     f.partition_max = min(tw.partition_max, 32)
     f.partition_min = min(tw.partition_min, f.partition_max)
     f.fine_directional_intra = tw.fine_directional_intra
+    f.enable_intra_edge_filter = 1
     f.split_gate_bits[0] = 0 if speed <= 2 else 60
     f.split_gate_bits[1] = 0 if speed <= 2 else 120
     f.split_gate_bits[2] = 0 if speed <= 2 else 200

@@ -155,6 +155,9 @@ CASES = [
     (256, 256, 8, 3, 180, 1, dict(partition_max=32)),           # 32x32 level (speed <= 2)
     (200, 136, 10, 3, 150, 2, dict(partition_max=32, lr=1)),
     (384, 320, 8, 3, 220, 4, dict(partition_max=32, partition_min=8)),
+    (200, 136, 8, 3, 121, 2, dict(enable_intra_edge_filter=1)),         # intra edge filter / upsampling
+    (256, 192, 10, 3, 100, 1, dict(enable_intra_edge_filter=1, partition_max=32, lr=1)),
+    (136, 104, 8, 3, 150, 1, dict(enable_intra_edge_filter=1, y_mode_mask=0x1fe)),       # directional luma modes only
 ]
 
 
