@@ -804,3 +804,9 @@ void orc_encode_frame(const B200Frame *f, const B200RateTables *rt, uint16_t *co
     }
   for (int lv = 0; lv < B200_LEVELS; lv++) if (!(dec_out && dec_out[lv])) free(e.dec[lv]);
 }
+
+/* test hooks: the 1-D edge operations on a caller buffer whose element [off] is the corner sample (index -1) */
+void orc_ief_filter_hook(uint16_t *buf, int off, int sz, int strength) { ief_filter(buf + off + 1, sz, strength); }
+void orc_ief_upsample_hook(uint16_t *buf, int off, int num_px, int bd) { ief_upsample_edge(buf + off + 1, num_px, bd); }
+int orc_ief_strength_hook(int blk_wh, int filter_type, int delta) { return ief_strength(blk_wh, filter_type, delta); }
+int orc_ief_use_upsample_hook(int blk_wh, int filter_type, int delta) { return ief_upsample(blk_wh, filter_type, delta); }
