@@ -36,10 +36,42 @@ static inline int lr_sample(const lr_t *c, int x, int y) {
 }
 static inline int64_t round2s(int64_t v, int n) { return n == 0 ? v : ((v + ((int64_t)1 << (n - 1))) >> n); }
 
-/* box filter process (spec 7.17.4) of both passes over the region [x0, x0+w) x [y0, y0+h), which lies inside ONE
- * stripe (c->stripe_*).  flt0 / flt1: w*h outputs (left untouched when the set's radius is 0). */
-void orc_sgr_region(const lr_t *c, int x0, int y0, int w, int h, int set, int32_t *flt0, int32_t *flt1) {
-  const int aw = w + 2;
+/* Raw box sums of the region [x0, x0+w) x [y0, y0+h) (inside ONE stripe): sum and sum of squares over the (2r+1)^2
+ * window around every A / B position (-1 .. h) x (-1 .. w), r = 1 at every row, r = 2 at the odd rows only (the r = 2
+ * pass of spec 7.17.4 reads no other row).  They do not depend on the parameter set, so the search computes them once. */
+typedef struct { uint32_t *a3, *b3, *a5, *b5; int aw; } sgr_sums_t;
+static void sgr_box_sums(const lr_t *c, int x0, int y0, int w, int h, sgr_sums_t *s) {
+  const int aw = w + 2, sw = w + 6, sh = h + 6;
+  s->aw = aw;
+  s->a3 = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)aw * (h + 2)); s->b3 = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)aw * (h + 2));
+  s->a5 = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)aw * (h + 2)); s->b5 = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)aw * (h + 2));
+  uint16_t *S = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)sw * sh);       /* samples with the 3-sample border */
+  for (int i = 0; i < sh; i++)
+    for (int j = 0; j < sw; j++) S[i * sw + j] = (uint16_t)lr_sample(c, x0 + j - 3, y0 + i - 3);
+  for (int i = -1; i <= h; i++)
+    for (int j = -1; j <= w; j++) {
+      const uint16_t *ctr = S + (i + 3) * sw + j + 3;
+      uint32_t a = 0, b = 0;
+      for (int dy = -1; dy <= 1; dy++)
+        for (int dx = -1; dx <= 1; dx++) { const uint32_t v = ctr[dy * sw + dx]; a += v * v; b += v; }
+      s->a3[(i + 1) * aw + j + 1] = a; s->b3[(i + 1) * aw + j + 1] = b;
+      if (i & 1) {
+        for (int dy = -2; dy <= 2; dy++)
+          for (int dx = -2; dx <= 2; dx++) {
+            if (dy >= -1 && dy <= 1 && dx >= -1 && dx <= 1) continue;
+            const uint32_t v = ctr[dy * sw + dx]; a += v * v; b += v;
+          }
+        s->a5[(i + 1) * aw + j + 1] = a; s->b5[(i + 1) * aw + j + 1] = b;
+      }
+    }
+  free(S);
+}
+static void sgr_sums_free(sgr_sums_t *s) { free(s->a3); free(s->b3); free(s->a5); free(s->b5); }
+
+/* box filter process (spec 7.17.4) of both passes for one parameter set from the raw sums.  flt0 / flt1: w*h outputs
+ * (left untouched when the set's radius is 0). */
+static void sgr_from_sums(const lr_t *c, const sgr_sums_t *bs, int x0, int y0, int w, int h, int set, int32_t *flt0, int32_t *flt1) {
+  const int aw = bs->aw;
   int32_t *A = (int32_t *)malloc(sizeof(int32_t) * (size_t)aw * (h + 2));
   int32_t *B = (int32_t *)malloc(sizeof(int32_t) * (size_t)aw * (h + 2));
   for (int pass = 0; pass < 2; pass++) {
@@ -51,19 +83,15 @@ void orc_sgr_region(const lr_t *c, int x0, int y0, int w, int h, int set, int32_
     for (int i = -1; i <= h; i++) {
       if (pass == 0 && !(i & 1)) continue;                 /* the r = 2 pass only reads the odd rows of A / B */
       for (int j = -1; j <= w; j++) {
-        uint32_t a = 0, b = 0;
-        for (int dy = -r; dy <= r; dy++)
-          for (int dx = -r; dx <= r; dx++) {
-            const uint32_t v = (uint32_t)lr_sample(c, x0 + j + dx, y0 + i + dy);
-            a += v * v; b += v;
-          }
+        const int k = (i + 1) * aw + j + 1;
+        const uint32_t a = pass == 0 ? bs->a5[k] : bs->a3[k], b = pass == 0 ? bs->b5[k] : bs->b3[k];
         const uint32_t a_s = (uint32_t)round2s(a, 2 * (c->bd - 8)), d = (uint32_t)round2s(b, c->bd - 8);
         const int64_t pp = (int64_t)a_s * n - (int64_t)d * d;
         const uint64_t p = pp < 0 ? 0 : (uint64_t)pp;
         const uint64_t z = (p * s + (1u << 19)) >> 20;
         const uint32_t a2 = (uint32_t)av1_x_by_xplus1_tbl[z > 255 ? 255 : z];
-        A[(i + 1) * aw + j + 1] = (int32_t)a2;
-        B[(i + 1) * aw + j + 1] = (int32_t)round2s((int64_t)(256 - a2) * b * one_by_n, 12);
+        A[k] = (int32_t)a2;
+        B[k] = (int32_t)round2s((int64_t)(256 - a2) * b * one_by_n, 12);
       }
     }
     int32_t *F = pass == 0 ? flt0 : flt1;
@@ -86,6 +114,12 @@ void orc_sgr_region(const lr_t *c, int x0, int y0, int w, int h, int set, int32_
     }
   }
   free(A); free(B);
+}
+void orc_sgr_region(const lr_t *c, int x0, int y0, int w, int h, int set, int32_t *flt0, int32_t *flt1) {
+  sgr_sums_t bs;
+  sgr_box_sums(c, x0, y0, w, h, &bs);
+  sgr_from_sums(c, &bs, x0, y0, w, h, set, flt0, flt1);
+  sgr_sums_free(&bs);
 }
 
 /* test hook: filter one region of a plane whose rows all belong to one stripe */
@@ -158,16 +192,27 @@ void orc_lr_search_plane(const B200Frame *f, int plane, const uint16_t *src, con
       B200LrUnit best = {0, 0, 0, 0};
       int64_t bestJ = 0;
       int have = 0;
+      /* stripes of this unit and their raw box sums, shared by every candidate set */
+      int n_reg = 0, reg_y[4], reg_h[4];
+      lr_t reg_c[4];
+      sgr_sums_t reg_s[4];
+      for (int ys = y0; ys < y1;) {
+        const int stripe = (ys + 8) >> 6;
+        lr_t c = {deb, cdef, stride, f->width, f->height, f->bit_depth, stripe * 64 - 8, stripe * 64 + 55};
+        const int ye = c.stripe_end + 1 < y1 ? c.stripe_end + 1 : y1;
+        reg_c[n_reg] = c; reg_y[n_reg] = ys; reg_h[n_reg] = ye - ys;
+        sgr_box_sums(&c, x0, ys, w, ye - ys, &reg_s[n_reg]);
+        n_reg++;
+        ys = ye;
+      }
       for (int ci = 0; ci < B200_LR_CANDIDATES; ci++) {
         const int set = orc_lr_candidate_sets[ci];
         const int r0 = av1_sgr_params_tbl[set][0], r1 = av1_sgr_params_tbl[set][1];
         int64_t H00 = 0, H01 = 0, H11 = 0, C0 = 0, C1 = 0, S = 0;
-        for (int ys = y0; ys < y1;) {              /* stripe by stripe */
-          const int stripe = (ys + 8) >> 6;
-          lr_t c = {deb, cdef, stride, f->width, f->height, f->bit_depth, stripe * 64 - 8, stripe * 64 + 55};
-          const int ye = c.stripe_end + 1 < y1 ? c.stripe_end + 1 : y1, h = ye - ys;
+        for (int rg = 0; rg < n_reg; rg++) {
+          const int ys = reg_y[rg], h = reg_h[rg];
           int32_t *f0 = (int32_t *)calloc((size_t)w * h, sizeof(int32_t)), *f1 = (int32_t *)calloc((size_t)w * h, sizeof(int32_t));
-          orc_sgr_region(&c, x0, ys, w, h, set, f0, f1);
+          sgr_from_sums(&reg_c[rg], &reg_s[rg], x0, ys, w, h, set, f0, f1);
           for (int i = 0; i < h; i++)
             for (int j = 0; j < w; j++) {
               const int64_t u = (int64_t)cdef[(ys + i) * stride + x0 + j] << 4;
@@ -176,7 +221,6 @@ void orc_lr_search_plane(const B200Frame *f, int plane, const uint16_t *src, con
               H00 += a * a; H01 += a * b; H11 += b * b; C0 += a * s; C1 += b * s; S += s * s;
             }
           free(f0); free(f1);
-          ys = ye;
         }
         if (!have) {     /* "no restoration": distortion of the CDEF output, cost of the use_sgrproj = 0 flag */
           bestJ = ((S >> 8) << 8) + (((int64_t)f->lambda_q8 * B200_LR_FLAG_COST0) >> 8);
@@ -209,6 +253,7 @@ void orc_lr_search_plane(const B200Frame *f, int plane, const uint16_t *src, con
         const int64_t J = (sse << 8) + (((int64_t)f->lambda_q8 * (B200_LR_FLAG_COST1 + 256 * bits)) >> 8);
         if (J < bestJ) { bestJ = J; best.use = 1; best.set = (int8_t)set; best.xqd0 = (int8_t)xqd0; best.xqd1 = (int8_t)xqd1; }
       }
+      for (int rg = 0; rg < n_reg; rg++) sgr_sums_free(&reg_s[rg]);
       units[ur * nuc + uc] = best;
     }
 }
