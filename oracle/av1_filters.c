@@ -230,8 +230,10 @@ void orc_cdef_frame(const B200Frame *f, uint16_t *const in[3], uint16_t *const o
  * has at least one non-skip 8x8 block, pick the strength index (0 .. 2^cdef_bits - 1) minimising the
  * squared error of the CDEF output against the source over all planes (ties -> lowest index).
  * Writes cdef_idx[] (-1 where the superblock is entirely skipped) and the filtered planes. */
+/* dirvar: optional cache of (direction, variance) per 8x8 block of this superblock (64 entries x 2, dir = -1: not yet
+ * computed) - the strength search calls this once per candidate index and the directions do not depend on it */
 static uint64_t cdef_sb_sse(const B200Frame *f, uint16_t *const in[3], uint16_t *const src[3], uint16_t *const out[3],
-                            const B200Mi *mi, int sbr, int sbc, int idx, int write) {
+                            const B200Mi *mi, int sbr, int sbc, int idx, int write, int *dirvar) {
   const int stride = f->mi_cols * 4, bd = f->bit_depth, cshift = bd - 8;
   const int W = f->mi_cols * 4, H = f->mi_rows * 4;
   uint64_t sse = 0;
@@ -241,7 +243,12 @@ static uint64_t cdef_sb_sse(const B200Frame *f, uint16_t *const in[3], uint16_t 
       const int skip = (m[0].flags & 1) && (m[1].flags & 1) && (m[f->mi_cols].flags & 1) && (m[f->mi_cols + 1].flags & 1);
       if (skip) continue;
       int ydir, var;
-      orc_cdef_direction(in[0] + r * 4 * stride + c * 4, stride, bd, &ydir, &var);
+      int *dv = dirvar ? dirvar + 2 * ((((r >> 1) & 7) << 3) | ((c >> 1) & 7)) : NULL;
+      if (dv && dv[0] >= 0) { ydir = dv[0]; var = dv[1]; }
+      else {
+        orc_cdef_direction(in[0] + r * 4 * stride + c * 4, stride, bd, &ydir, &var);
+        if (dv) { dv[0] = ydir; dv[1] = var; }
+      }
       for (int p = 0; p < f->planes; p++) {
         const int str = p == 0 ? f->cdef_y_strength[idx] : f->cdef_uv_strength[idx];
         int pri = (str >> 2) << cshift, sec = str & 3;
@@ -306,11 +313,13 @@ void orc_cdef_search_frame(const B200Frame *f, uint16_t *const in[3], uint16_t *
       if (!any || !f->enable_cdef) { cdef_idx[sbr * f->sb_cols + sbc] = -1; continue; }
       int best = 0;
       uint64_t bs = UINT64_MAX;
+      int dirvar[128];
+      for (int k = 0; k < 128; k++) dirvar[k] = -1;
       for (int idx = 0; idx < (1 << f->cdef_bits); idx++) {
-        const uint64_t s = cdef_sb_sse(f, in, src, out, mi, sbr, sbc, idx, 0);
+        const uint64_t s = cdef_sb_sse(f, in, src, out, mi, sbr, sbc, idx, 0, dirvar);
         if (s < bs) { bs = s; best = idx; }
       }
       cdef_idx[sbr * f->sb_cols + sbc] = (int8_t)best;
-      cdef_sb_sse(f, in, src, out, mi, sbr, sbc, best, 1);
+      cdef_sb_sse(f, in, src, out, mi, sbr, sbc, best, 1, dirvar);
     }
 }
