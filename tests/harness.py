@@ -35,7 +35,15 @@ MI_DTYPE = np.dtype([("bsize", "u1"), ("y_mode", "u1"), ("uv_mode", "u1"), ("ang
                      ("tx_size", "u1"), ("tx_type", "u1"), ("flags", "u1"), ("cfl", "u1")])
 
 def _run(cmd):
-    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT)
+    """run a (make) command under an exclusive file lock: several ranks / xdist workers may import this module at once and
+    two concurrent builds must never write the same shared library"""
+    import fcntl
+    with open(os.path.join(ROOT, ".build.lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
     if r.returncode != 0:
         raise RuntimeError("build failed: %s\n%s" % (" ".join(cmd), r.stderr[-4000:]))
 
