@@ -61,12 +61,14 @@ def filter_inputs(images, quiet, err=sys.stderr):
             continue
         ext = os.path.splitext(s)[1].lower()
         if ext == ".avif":
-            if os.path.exists(s):
-                if not quiet:
-                    print("warning: ignoring %s, because it's already an AVIF" % s, file=err)
+            # main.rs:144-156: with --quiet every .avif argument is dropped; otherwise an existing one is ignored with a
+            # warning and a missing one is kept (with the "-o" hint)
+            if quiet:
                 continue
-            if not quiet:
-                print("warning: Did you mean to use -o %s?" % s, file=err)
+            if os.path.exists(s):
+                print("warning: ignoring %s, because it's already an AVIF" % s, file=err)
+                continue
+            print("warning: Did you mean to use -o %s?" % s, file=err)
         keep.append(s)
     return keep
 
@@ -144,12 +146,12 @@ def main(argv=None, stdin=None, stdout=None, stderr=None):
     if work:
         try:
             results = enc.encode_batch([w[2] for w in work])            # one device pass for every file
-        except Error:
+        except (Error, ValueError, AssertionError):                     # status 4 maps to ValueError, bad buffers assert
             results = []
             for name, out, px in work:                                  # isolate the failing image(s)
                 try:
                     results.append(enc.encode_rgba(px))
-                except Error as e:
+                except (Error, ValueError, AssertionError) as e:
                     results.append(None)
                     failures.append("%s: error: %s" % (name, e))
     for (name, out, _), res in zip(work, results):

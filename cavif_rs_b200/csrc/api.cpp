@@ -50,6 +50,7 @@ namespace {
 
 thread_local std::string g_err;
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define ARENA_CHECK(c) do { if ((c).dev.overflow || (c).pin.overflow) return fail(B200AVIF_ENCODING_ERROR, "internal error: work arena too small for this batch"); } while (0)
 
 std::atomic<uint64_t> g_launches{0}, g_h2d{0}, g_d2h{0};
 std::mutex g_stat_mu;
@@ -96,9 +97,13 @@ struct Arena {
     if (base) { if (host) cudaFreeHost(base); else cudaFree(base); }
     base = nullptr; cap = 0;
   }
-  void reset() { used = 0; }
+  void reset() { used = 0; overflow = false; }
+  // Bump allocation.  A request past the reserved capacity does NOT hand out memory beyond the arena: it sets
+  // `overflow` (checked by the callers before any device work is queued) and returns the arena base.
+  bool overflow = false;
   template <typename T> T *take(size_t count) {
     used = (used + 255) & ~(size_t)255;
+    if (used + count * sizeof(T) > cap) { overflow = true; return (T *)base; }
     T *p = (T *)(base + used);
     used += count * sizeof(T);
     return p;
@@ -114,7 +119,22 @@ struct Context {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_analysis = nullptr;  // stages A + B of the current chunk are done
   std::map<int, B200RateTables *> d_rate;   // per base_q_idx
-  ~Context() {}
+  // Queued work is drained before anything is freed.  Contexts are destroyed by b200avif_shutdown() or when a call
+  // drops a context after an error; NOT from a static destructor at process exit (the CUDA runtime may already be gone).
+  void drain() { if (stream) cudaStreamSynchronize(stream); if (stream_hi) cudaStreamSynchronize(stream_hi); }
+  ~Context() {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaSetDevice(device);
+    drain();
+    for (auto &kv : d_rate) cudaFree(kv.second);
+    dev.release(); pin.release();
+    for (auto &e : ev) if (e) cudaEventDestroy(e);
+    if (ev_analysis) cudaEventDestroy(ev_analysis);
+    if (stream) cudaStreamDestroy(stream);
+    if (stream_hi) cudaStreamDestroy(stream_hi);
+    cudaSetDevice(cur);
+  }
 };
 std::mutex g_ctx_mu;
 std::vector<std::unique_ptr<Context>> g_ctx_free;
@@ -129,21 +149,33 @@ int acquire_context(int device, std::unique_ptr<Context> &out) {
   }
   CU(cudaSetDevice(device));
   if (!out) {
-    out.reset(new Context());
-    out->device = device;
+    std::unique_ptr<Context> c(new Context());      // destroyed (streams / events released) if any step below fails
+    c->device = device;
     int prio_lo = 0, prio_hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    CU(cudaStreamCreateWithPriority(&out->stream, cudaStreamNonBlocking, prio_lo));
-    CU(cudaStreamCreateWithPriority(&out->stream_hi, cudaStreamNonBlocking, prio_hi));
-    for (auto &e : out->ev) CU(cudaEventCreate(&e));
-    CU(cudaEventCreateWithFlags(&out->ev_analysis, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
+    CU(cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, prio_hi));
+    for (auto &e : c->ev) CU(cudaEventCreate(&e));
+    CU(cudaEventCreateWithFlags(&c->ev_analysis, cudaEventDisableTiming));
+    out = std::move(c);
   }
   return 0;
 }
-void release_context(std::unique_ptr<Context> &c) {
+// ok == false (the call failed part-way): the context may still have copies / kernels in flight that read its arenas;
+// drain it before the next user can reset those arenas.
+void release_context(std::unique_ptr<Context> &c, bool ok = true) {
+  if (!c) return;
+  if (!ok) c->drain();
   std::lock_guard<std::mutex> lk(g_ctx_mu);
   g_ctx_free.push_back(std::move(c));
 }
+
+// RAII lease of a pooled context: handed back drained unless the call marked itself successful.
+struct CtxLease {
+  std::unique_ptr<Context> c;
+  bool ok = false;
+  ~CtxLease() { release_context(c, ok); }
+};
 
 // ---- one AV1 frame to encode (colour or alpha of an image) ------------------------------------------
 struct FrameJob {
@@ -186,6 +218,8 @@ size_t job_dev_bytes(const FrameJob &j, bool own_src) {
   b += align256(j.n_sb());
   for (int lv = 0; lv < B200_LEVELS; lv++) b += align256(j.n_blk(lv) * sizeof(B200BlockDec)) + align256(j.n_blk(lv) * B200_SATD_WORDS * 4) + 512;
   if (j.uses_lr()) b += P * (align256(j.n_px() * 2) + align256(j.n_lr() * sizeof(B200LrUnit)));
+  // the job descriptor and tile list issue_rdo() uploads (one entry per job / tile)
+  b += align256(sizeof(B200RdoJob)) + align256((size_t)j.f.tile_rows * j.f.tile_cols * sizeof(B200TileRef)) + 512;
   return b + 8192;
 }
 size_t job_pin_bytes(const FrameJob &j) {
@@ -301,16 +335,23 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
   }
   B200RdoJob *d_jobs = dev.take<B200RdoJob>(hj.size());
   B200TileRef *d_tiles = dev.take<B200TileRef>(tiles.size());
+  if (dev.overflow || pin.overflow) return fail(B200AVIF_ENCODING_ERROR, "internal error: work arena too small for this batch");
   CU(cudaMemcpyAsync(d_jobs, hj.data(), hj.size() * sizeof(B200RdoJob), cudaMemcpyHostToDevice, c.stream));
   CU(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(B200TileRef), cudaMemcpyHostToDevice, c.stream));
   if (after_analysis_of) CU(cudaStreamWaitEvent(c.stream, after_analysis_of, 0));
   CU(cudaEventRecord(c.ev[1], c.stream));
   int max_blocks4 = 0, top_level = 2;
   for (FrameJob *jp : jobs) { max_blocks4 = std::max(max_blocks4, (int)jp->n_mi()); if (jp->f.partition_max >= 32) top_level = 3; }
-  const int le = b200_rdo_launch(d_jobs, (int)jobs.size(), d_tiles, (int)tiles.size(), max_blocks4, jobs[0]->f.bit_depth > 8,
-                                 top_level, c.stream, c.stream_hi, c.ev_analysis);   // one bit depth per call
+  int max_regions = 0;       // root regions of the partition decision: every job decides with ITS root size (16 or 32)
+  for (FrameJob *jp : jobs) {
+    const int rn4 = jp->f.partition_max >= 32 ? 8 : 4;
+    max_regions = std::max(max_regions, ((jp->f.mi_cols + rn4 - 1) / rn4) * ((jp->f.mi_rows + rn4 - 1) / rn4));
+  }
+  int n_launched = 0;
+  const int le = b200_rdo_launch(d_jobs, (int)jobs.size(), d_tiles, (int)tiles.size(), max_blocks4, max_regions, jobs[0]->f.bit_depth > 8,
+                                 top_level, c.stream, c.stream_hi, c.ev_analysis, &n_launched);   // one bit depth per call
   if (le != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("RDO kernel launch failed: ") + cudaGetErrorString((cudaError_t)le));
-  g_launches += 8;   // 3 x (SATD + analysis) + partition decision + reconstruction
+  g_launches += (uint64_t)n_launched;   // counted by the launcher: (SATD + analysis) per level + partition decision + reconstruction
   CU(cudaEventRecord(c.ev[2], c.stream_hi));
   if (pre_filter_rec) {   // test seam: reconstruction before the in-loop filters
     pre_filter_rec->clear();
@@ -329,9 +370,9 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     }
     int with_lr = 0;
     for (FrameJob *jp : jobs) with_lr |= jp->uses_lr();
-    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_edges, max_sb, with_lr, c.stream_hi);
+    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_edges, max_sb, with_lr, c.stream_hi, &n_launched);
     if (fe != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("filter kernel launch failed: ") + cudaGetErrorString((cudaError_t)fe));
-    g_launches += 3 + with_lr;
+    g_launches += (uint64_t)n_launched;
   }
   uint64_t d2h = 0;
   for (FrameJob *jp : jobs) {
@@ -423,11 +464,14 @@ struct ImageWork {
 };
 
 int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b200avif_image *outs, int *status) {
+  // every output is defined on every return path: a caller may b200avif_image_free() a failed call's images
+  for (size_t i = 0; i < imgs.size(); i++) { memset(&outs[i], 0, sizeof(outs[i])); if (status) status[i] = B200AVIF_ENCODING_ERROR; }
   if (b200avif_device_count() <= 0)
     return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
-  std::unique_ptr<Context> ctx;
-  if (int e = acquire_context(enc.device, ctx)) return e;
-  struct Release { std::unique_ptr<Context> &c; ~Release() { release_context(c); } } rel{ctx};
+  constexpr size_t NC = 3;            // contexts: two chunks in flight on the device + one being packed / refilled
+  CtxLease lease[NC];                 // destroyed last: after the packer threads were joined (Joiner below)
+  if (int e = acquire_context(enc.device, lease[0].c)) return e;
+  std::unique_ptr<Context> &ctx = lease[0].c;
   const int depth = enc.output_depth == 8 ? 8 : 10;
   const int mc = enc.color_model == B200AVIF_COLOR_YCBCR ? B200AVIF_MC_BT601 : B200AVIF_MC_IDENTITY;
 
@@ -445,12 +489,9 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
   const size_t n_img = imgs.size();
   size_t n_chunks = n_img >= 16 ? 4 : (n_img >= 4 ? 2 : 1);
   if (const char *ev = getenv("B200AVIF_CHUNKS")) { const long v = atol(ev); if (v >= 1) n_chunks = std::min<size_t>((size_t)v, n_img); }
-  constexpr size_t NC = 3;            // contexts: two chunks in flight on the device + one being packed / refilled
-  std::unique_ptr<Context> ctx_extra[NC - 1];
-  for (size_t k = 1; k < std::min(NC, n_chunks); k++) { if (int e = acquire_context(enc.device, ctx_extra[k - 1])) return e; }
-  struct ReleaseExtra { std::unique_ptr<Context> *c; ~ReleaseExtra() { for (size_t k = 0; k < NC - 1; k++) if (c[k]) release_context(c[k]); } } rel2{ctx_extra};
+  for (size_t k = 1; k < std::min(NC, n_chunks); k++) { if (int e = acquire_context(enc.device, lease[k].c)) return e; }
   Context *cx[NC];
-  for (size_t k = 0; k < NC; k++) cx[k] = (k == 0 || !ctx_extra[k - 1]) ? ctx.get() : ctx_extra[k - 1].get();
+  for (size_t k = 0; k < NC; k++) cx[k] = lease[k].c ? lease[k].c.get() : ctx.get();
   struct Chunk { size_t a, b; int *h_flags = nullptr; std::vector<FrameJob *> jobs; std::thread packer; bool issued = false; };
   std::vector<Chunk> chunks(n_chunks);
   for (size_t k = 0; k < n_chunks; k++) { chunks[k].a = k * n_img / n_chunks; chunks[k].b = (k + 1) * n_img / n_chunks; }
@@ -482,14 +523,16 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
       if (im.status) continue;
       job_take(im.color, c.dev, c.pin, true);
       job_take(im.alpha, c.dev, c.pin, true);
+      ARENA_CHECK(c);
       const int cw = im.color.f.mi_cols * 4, chh = im.color.f.mi_rows * 4;
       if (im.raw) {
         for (int p = 0; p < 4; p++) {
           if (p == 3 && !im.raw_has_alpha) break;
           const std::vector<uint16_t> &srcv = p < 3 ? im.raw_planes[p] : im.raw_alpha;
           uint16_t *stage = c.pin.take<uint16_t>(im.w * im.h);
-          memcpy(stage, srcv.data(), im.w * im.h * 2);
           uint16_t *d = c.dev.take<uint16_t>(im.w * im.h);
+          ARENA_CHECK(c);
+          memcpy(stage, srcv.data(), im.w * im.h * 2);
           CU(cudaMemcpyAsync(d, stage, im.w * im.h * 2, cudaMemcpyHostToDevice, c.stream));
           if (int e = b200_pad_plane_launch(d, (int)im.w, (int)im.h, (int)im.w, p < 3 ? im.color.d_src[p] : im.alpha.d_src[0], cw, chh, c.stream))
             return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
@@ -506,12 +549,13 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
         const bool pinned = cudaPointerGetAttributes(&attr, im.pixels) == cudaSuccess && attr.type == cudaMemoryTypeHost;
         if (!pinned) cudaGetLastError();
         const uint8_t *from = im.pixels;
+        uint8_t *stage = pinned ? nullptr : c.pin.take<uint8_t>(bytes);
+        uint8_t *d = c.dev.take<uint8_t>(bytes + 16);
+        ARENA_CHECK(c);
         if (!pinned) {
-          uint8_t *stage = c.pin.take<uint8_t>(bytes);
           memcpy(stage, im.pixels, bytes);
           from = stage;
         }
-        uint8_t *d = c.dev.take<uint8_t>(bytes + 16);
         CU(cudaMemcpyAsync(d, from, bytes, cudaMemcpyHostToDevice, c.stream));
         h2d += bytes;
         d_in = d;
@@ -522,6 +566,7 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
         const int mode = enc.alpha_color_mode == B200AVIF_ALPHA_PREMULTIPLIED ? 2 : 1;
         uint8_t *d_tmp = c.dev.take<uint8_t>(im.w * im.h * 4), *d_clean = c.dev.take<uint8_t>(im.w * im.h * 4);
         unsigned long long *d_acc = c.dev.take<unsigned long long>(4);
+        ARENA_CHECK(c);
         if (int e = b200_alpha_clean_launch(d_in, (int)im.w, (int)im.h, (int)im.stride, mode, d_tmp, d_clean, d_acc, c.stream))
           return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
         g_launches += mode == 2 ? 1 : 3;
@@ -571,9 +616,9 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
   // ---- mux
   const auto t0 = std::chrono::steady_clock::now();
   int first_err = 0;
+  for (size_t k = 0; k < NC; k++) lease[k].ok = true;      // all device work of this call has been waited for
   for (size_t i = 0; i < imgs.size(); i++) {
     ImageWork &im = imgs[i];
-    memset(&outs[i], 0, sizeof(outs[i]));
     if (!im.status && (im.color.status || (im.use_alpha && im.alpha.status))) im.status = B200AVIF_ENCODING_ERROR;
     if (!im.status) {
       B200AvifMuxInput mi;
@@ -653,6 +698,18 @@ int b200avif_encoder_with_quality(b200avif_encoder *enc, float q) {
 int b200avif_encoder_with_alpha_quality(b200avif_encoder *enc, float q) {
   if (!enc || !(q >= 1.f && q <= 100.f)) return fail(B200AVIF_INVALID_ARGUMENT, "alpha quality must be in 1..=100");
   enc->alpha_quantizer = b200_quality_to_quantizer(q);
+  return 0;
+}
+// The reference struct stores the QUANTIZERS (av1encoder.rs:67-71: quantizer, alpha_quantizer: u8), not the qualities:
+// a binding that mirrors the struct field by field uses these two.
+int b200avif_encoder_with_quantizer(b200avif_encoder *enc, uint8_t quantizer) {
+  if (!enc) return fail(B200AVIF_INVALID_ARGUMENT, "null encoder");
+  enc->quantizer = quantizer;
+  return 0;
+}
+int b200avif_encoder_with_alpha_quantizer(b200avif_encoder *enc, uint8_t quantizer) {
+  if (!enc) return fail(B200AVIF_INVALID_ARGUMENT, "null encoder");
+  enc->alpha_quantizer = quantizer;
   return 0;
 }
 int b200avif_encoder_with_speed(b200avif_encoder *enc, uint8_t s) {
@@ -738,6 +795,14 @@ int b200avif_device_count(void) {
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
+size_t b200avif_default_num_threads(void) { return b200_host_threads(); }
+// Release every pooled context (streams, events, arenas, cached rate tables).  Safe to call at any quiet point; the next
+// encode call rebuilds what it needs.  Not registered with atexit(): the CUDA runtime may be torn down first.
+void b200avif_shutdown(void) {
+  std::vector<std::unique_ptr<Context>> drop;
+  { std::lock_guard<std::mutex> lk(g_ctx_mu); drop.swap(g_ctx_free); }
+  drop.clear();
+}
 void b200avif_get_stats(b200avif_stats *out) {
   if (!out) return;
   std::lock_guard<std::mutex> lk(g_stat_mu);
@@ -752,10 +817,9 @@ int b200av1_encode_planes(const b200av1_config *cfg, const uint16_t *const plane
   FrameJob job;
   if (int e = configure_frame(&job.f, cfg->width, cfg->height, cfg->bit_depth, cfg->monochrome != 0, cfg->quantizer, cfg->speed,
                               cfg->threads, cfg->pixel_range, cfg->has_color_description != 0, cfg->matrix_coefficients)) return e;
-  std::unique_ptr<Context> ctx;
-  if (int e = acquire_context(-1, ctx)) return e;
-  Context &c = *ctx;
-  struct Release { std::unique_ptr<Context> &c; ~Release() { release_context(c); } } rel{ctx};
+  CtxLease lease;
+  if (int e = acquire_context(-1, lease.c)) return e;
+  Context &c = *lease.c;
   const size_t w = cfg->width, h = cfg->height;
   if (c.dev.reserve(job_dev_bytes(job, true) + job.f.planes * align256(w * h * 2) + (1 << 20)) ||
       c.pin.reserve(job_pin_bytes(job) + job.f.planes * align256(w * h * 2) + (1 << 20))) return B200AVIF_ENCODING_ERROR;
@@ -765,8 +829,9 @@ int b200av1_encode_planes(const b200av1_config *cfg, const uint16_t *const plane
   const int cw = job.f.mi_cols * 4, ch = job.f.mi_rows * 4;
   for (int p = 0; p < job.f.planes; p++) {
     uint16_t *stage = c.pin.take<uint16_t>(w * h);
-    for (size_t y = 0; y < h; y++) memcpy(stage + y * w, planes[p] + y * strides[p], w * 2);
     uint16_t *d = c.dev.take<uint16_t>(w * h);
+    ARENA_CHECK(c);
+    for (size_t y = 0; y < h; y++) memcpy(stage + y * w, planes[p] + y * strides[p], w * 2);
     CU(cudaMemcpyAsync(d, stage, w * h * 2, cudaMemcpyHostToDevice, c.stream));
     if (int e = b200_pad_plane_launch(d, (int)w, (int)h, (int)w, job.d_src[p], cw, ch, c.stream)) return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
     g_launches++; g_h2d += w * h * 2;
@@ -778,6 +843,7 @@ int b200av1_encode_planes(const b200av1_config *cfg, const uint16_t *const plane
   *obu = (uint8_t *)malloc(job.obu.size());
   memcpy(*obu, job.obu.data(), job.obu.size());
   *obu_len = job.obu.size();
+  lease.ok = true;
   return 0;
 }
 
@@ -785,10 +851,9 @@ int b200av1_encode_planes(const b200av1_config *cfg, const uint16_t *const plane
 int b200av1_alpha_clean_run(const uint8_t *rgba, size_t w, size_t h, size_t stride_px, int mode, uint8_t *out) {
   if (!rgba || !out || w == 0 || h == 0 || (mode != 1 && mode != 2)) return fail(B200AVIF_INVALID_ARGUMENT, "bad argument");
   if (b200avif_device_count() <= 0) return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
-  std::unique_ptr<Context> ctx;
-  if (int e = acquire_context(-1, ctx)) return e;
-  Context &c = *ctx;
-  struct Release { std::unique_ptr<Context> &c; ~Release() { release_context(c); } } rel{ctx};
+  CtxLease lease;
+  if (int e = acquire_context(-1, lease.c)) return e;
+  Context &c = *lease.c;
   const size_t in_bytes = (stride_px * (h - 1) + w) * 4, img_bytes = w * h * 4;
   if (c.dev.reserve(align256(in_bytes) + 2 * align256(img_bytes) + 8192) || c.pin.reserve(4096)) return B200AVIF_ENCODING_ERROR;
   c.dev.reset(); c.pin.reset();
@@ -800,6 +865,7 @@ int b200av1_alpha_clean_run(const uint8_t *rgba, size_t w, size_t h, size_t stri
   g_launches += mode == 2 ? 1 : 3;
   CU(cudaMemcpyAsync(out, d_out, img_bytes, cudaMemcpyDeviceToHost, c.stream));
   CU(cudaStreamSynchronize(c.stream));
+  lease.ok = true;
   return 0;
 }
 
@@ -807,10 +873,9 @@ int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h,
                         uint16_t *const planes[4] /* y,u,v,alpha (alpha may be NULL) */, int *any_alpha) {
   if (!pixels || !planes || w == 0 || h == 0) return fail(B200AVIF_INVALID_ARGUMENT, "null argument");
   if (b200avif_device_count() <= 0) return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
-  std::unique_ptr<Context> ctx;
-  if (int e = acquire_context(-1, ctx)) return e;
-  Context &c = *ctx;
-  struct Release { std::unique_ptr<Context> &c; ~Release() { release_context(c); } } rel{ctx};
+  CtxLease lease;
+  if (int e = acquire_context(-1, lease.c)) return e;
+  Context &c = *lease.c;
   const int cw = 8 * (int)((w + 7) >> 3), ch = 8 * (int)((h + 7) >> 3);
   const size_t npx = (size_t)cw * ch, in_bytes = (stride_px * (h - 1) + w) * channels;
   if (c.dev.reserve(4 * align256(npx * 2) + align256(in_bytes) + 8192) || c.pin.reserve(4096)) return B200AVIF_ENCODING_ERROR;
@@ -831,6 +896,7 @@ int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h,
   CU(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   CU(cudaStreamSynchronize(c.stream));
   if (any_alpha) *any_alpha = flag;
+  lease.ok = true;
   return 0;
 }
 
@@ -842,10 +908,9 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
   if (b200avif_device_count() <= 0) return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
   FrameJob job;
   job.f = *f;
-  std::unique_ptr<Context> ctx;
-  if (int e = acquire_context(-1, ctx)) return e;
-  Context &c = *ctx;
-  struct Release { std::unique_ptr<Context> &c; ~Release() { release_context(c); } } rel{ctx};
+  CtxLease lease;
+  if (int e = acquire_context(-1, lease.c)) return e;
+  Context &c = *lease.c;
   if (c.dev.reserve(job_dev_bytes(job, true) + 6 * align256(job.n_px() * 2) + (1 << 20)) || c.pin.reserve(job_pin_bytes(job) + (1 << 20))) return B200AVIF_ENCODING_ERROR;
   c.dev.reset(); c.pin.reset();
   CU(cudaEventRecord(c.ev[0], c.stream));
@@ -881,6 +946,7 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
     if (job.uses_lr() && lr && lr[p]) memcpy(lr[p], job.h_lr[p], job.n_lr() * sizeof(B200LrUnit));
     if (job.d_lr_out[p]) CU(cudaMemcpy(lr_out[p], job.d_lr_out[p], job.n_px() * 2, cudaMemcpyDeviceToHost));
   }
+  lease.ok = true;
   return 0;
 }
 

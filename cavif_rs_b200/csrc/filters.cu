@@ -559,7 +559,8 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
 }
 
 #ifndef B200_EMU
-extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, int with_lr, void *stream) {
+extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, int with_lr, void *stream, int *launched) {
+  if (launched) *launched = 0;
   if (n_jobs <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 g1((max_edge_threads + 255) / 256, n_jobs);
@@ -571,6 +572,7 @@ extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max
     dim3 g3(max_sb, n_jobs, 3);       // restoration units <= superblocks
     b200_lr_kernel<<<g3, 256, 0, st>>>(d_jobs);
   }
+  if (launched) *launched = 3 + (with_lr ? 1 : 0);
   return (int)cudaGetLastError();
 }
 #else

@@ -5,7 +5,11 @@
 #include "ravif_settings.h"
 
 #include <math.h>
+#include <sched.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include <algorithm>
 #include <vector>
 
@@ -42,9 +46,33 @@ extern "C" void b200_speed_tweaks(int speed, int quantizer, B200SpeedTweaks *t) 
   t->min_tile_size = (speed <= 4 ? mts[speed] : 128) * (high_quality ? 2 : 1);
 }
 
+// rayon::current_num_threads() of the global pool (what `threads: None` means, av1encoder.rs:413-415, :666):
+// RAYON_NUM_THREADS when set to a positive number, else std::thread::available_parallelism(), which on Linux is the
+// size of the affinity mask bounded by the cgroup CPU quota.
+extern "C" size_t b200_host_threads(void) {
+  if (const char *ev = getenv("RAYON_NUM_THREADS")) { const long v = atol(ev); if (v > 0) return (size_t)v; }
+  size_t n = 0;
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) n = (size_t)CPU_COUNT(&set);
+  if (n == 0) { const long v = sysconf(_SC_NPROCESSORS_ONLN); n = v > 0 ? (size_t)v : 1; }
+  // cgroup v2 quota: "max 100000" or "<quota> <period>"; v1: cpu.cfs_quota_us / cpu.cfs_period_us
+  long long quota = -1, period = 0;
+  if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+    char q[32] = {0};
+    if (fscanf(f, "%31s %lld", q, &period) == 2 && strcmp(q, "max") != 0) quota = atoll(q);
+    fclose(f);
+  } else {
+    if (FILE *fq = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) { if (fscanf(fq, "%lld", &quota) != 1) quota = -1; fclose(fq); }
+    if (FILE *fp = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(fp, "%lld", &period) != 1) period = 0; fclose(fp); }
+  }
+  if (quota > 0 && period > 0) n = std::min(n, (size_t)std::max<long long>(quota / period, 1));
+  return std::max<size_t>(n, 1);
+}
+
 extern "C" size_t b200_tile_target(size_t threads, size_t w, size_t h, size_t min_tile_size) {
   const size_t cap = (w * h) / (min_tile_size * min_tile_size);
-  // threads == 0 is ravif's `None` ("all threads of the pool"); the device always has more lanes than the
-  // cap, so None resolves to the cap itself (state `threads` explicitly for byte parity).
-  return threads == 0 ? cap : std::min(threads, cap);
+  // av1encoder.rs:665-668: tiles = threads.min(cap); threads == 0 is ravif's `None` = the global pool size (:413-415).
+  // Like the reference, default-config output therefore depends on the host: callers that need
+  // reproducible bytes pass with_num_threads(n); n >= cap gives the most tiles (most device parallelism).
+  return std::min(threads == 0 ? b200_host_threads() : threads, cap);
 }

@@ -15,6 +15,7 @@ typedef struct B200SpeedTweaks {
 } B200SpeedTweaks;
 uint8_t b200_quality_to_quantizer(float quality);                       // av1encoder.rs:526-530
 void b200_speed_tweaks(int speed, int quantizer, B200SpeedTweaks *t);    // av1encoder.rs:555-605
+size_t b200_host_threads(void);                                        // rayon::current_num_threads() (:413-415)
 size_t b200_tile_target(size_t threads /*0 = None*/, size_t w, size_t h, size_t min_tile_size);   // :665-668
 #ifdef __cplusplus
 }

@@ -33,6 +33,9 @@
 #endif
 #include <stdint.h>
 #include <stdlib.h>
+#ifndef B200_EMU
+#include <mutex>
+#endif
 
 #include "records.h"
 #include "rdo.h"
@@ -1315,10 +1318,17 @@ __global__ void __launch_bounds__(kThreads * (NMAX == 32 ? 2 : kReconWarps), NMA
 // recorded behind stage B, may be null when both streams are the same).  The caller overlaps the low-parallelism
 // reconstruction chain of one chunk with the analysis of the next by giving stream_recon a higher priority.
 extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200TileRef *d_tiles, int n_tiles, int max_blocks4,
-                               int high_bitdepth, int top_level, void *stream, void *stream_recon, void *analysis_done) {
+                               int max_regions, int high_bitdepth, int top_level, void *stream, void *stream_recon, void *analysis_done, int *launched) {
   if (n_tiles <= 0 || n_jobs <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool configured = false;
+  int n_launch = 0;
+  // function attributes are per device: set them once per device, under a lock (concurrent callers, several GPUs)
+  static std::mutex cfg_mu;
+  static bool cfg_done[64] = {};
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  std::lock_guard<std::mutex> cfg_lock(cfg_mu);
+  bool &configured = cfg_done[cur_dev & 63];
   if (!configured) {
 #define B200_CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
     B200_CARVE((b200_analyze_kernel<0, false, 1>)); B200_CARVE((b200_analyze_kernel<1, false, 1>)); B200_CARVE((b200_analyze_kernel<2, false, 1>));
@@ -1337,9 +1347,11 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     if (lv == top) {
       dim3 gs((nblk + 127) / 128, n_jobs);
       b200_satd_direct_kernel<<<gs, 128, 0, st>>>(d_jobs, lv);
+      n_launch++;
     } else {
       dim3 gs((nblk + kSatdItems - 1) / kSatdItems, n_jobs);
       b200_satd_kernel<<<gs, 128, 0, st>>>(d_jobs, lv, kSatdItems);
+      n_launch++;
     }
     // enough warps to fill the machine several times over, grid-stride inside
     const int per_job = min(nblk, max(1, (148 * 16 * 4) / n_jobs));
@@ -1356,9 +1368,13 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     } else if (lv == 2) B200_ANALYZE(2, 1, ga);
     else if (lv == 1) B200_ANALYZE(1, 1, ga);
     else B200_ANALYZE(0, 1, ga);
+    n_launch++;
   }
-  dim3 gd((max_blocks4 / 16 + 64 + 127) / 128, n_jobs);
+  // one thread per ROOT REGION: ceil(W / rn) * ceil(H / rn) per job (larger than n_mi / 16 when the coded size is
+  // 8 mod 16), computed by the caller over all jobs
+  dim3 gd((max_regions + 127) / 128, n_jobs);
   b200_decide_kernel<<<gd, 128, 0, st>>>(d_jobs);
+  n_launch += 2;      // partition decision + the reconstruction chain below
   cudaStream_t sr = stream_recon ? (cudaStream_t)stream_recon : st;
   if (analysis_done) {
     cudaEventRecord((cudaEvent_t)analysis_done, st);
@@ -1374,6 +1390,7 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     if (high_bitdepth) b200_recon_kernel<true, 16><<<n_tiles, bt, 0, sr>>>(d_jobs, d_tiles);
     else b200_recon_kernel<false, 16><<<n_tiles, bt, 0, sr>>>(d_jobs, d_tiles);
   }
+  if (launched) *launched = n_launch;
   return (int)cudaGetLastError();
 }
 #else
@@ -1402,7 +1419,6 @@ static void emu_recon(void *) {
 extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *tiles, int n_tiles) {
   g_emu_jobs = jobs; g_emu_tiles = tiles;
   const B200Frame *f = &jobs[0].frame;
-  const int nblk4 = f->mi_rows * f->mi_cols;
   g_emu_top = f->partition_max >= 32 ? 3 : 2;
   for (g_emu_lv = g_emu_top; g_emu_lv >= 0; g_emu_lv--) {
     const int nblk = (f->mi_rows >> g_emu_lv) * (f->mi_cols >> g_emu_lv);
@@ -1412,7 +1428,9 @@ extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *ti
     const int w = g_emu_lv == 3 ? kAnalyzeWarpsTop32 : ((g_emu_lv == 2 && g_emu_top == 2) ? kAnalyzeWarpsTop : 1);
     emu::launch(emu_analyze, nullptr, (unsigned)std::min(nblk, w > 1 ? 3 : 7), kThreads * w);
   }
-  emu::launch(emu_decide, nullptr, (unsigned)((nblk4 / 16 + 64 + 127) / 128), 128);
+  const int rn4 = g_emu_top == 3 ? 8 : 4;
+  const int regions = ((f->mi_cols + rn4 - 1) / rn4) * ((f->mi_rows + rn4 - 1) / rn4);
+  emu::launch(emu_decide, nullptr, (unsigned)((regions + 127) / 128), 128);
   emu::launch(emu_recon, nullptr, (unsigned)n_tiles, kThreads * (g_emu_top == 3 ? 2 : kReconWarps));
   return 0;
 }

@@ -37,9 +37,10 @@ typedef struct B200TileRef {
 // All RDO stages for all jobs on `stream`: SATD + analysis per level, partition decision, reconstruction chain
 // (one warp per tile).  max_blocks4 = largest mi_rows*mi_cols over the jobs; high_bitdepth: all jobs are 10-bit.
 int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200TileRef *d_tiles, int n_tiles, int max_blocks4,
-                    int high_bitdepth, int top_level /* 2: 16x16, 3: 32x32 */, void *stream, void *stream_recon, void *analysis_done);
+                    int max_regions /* largest root-region count (ceil(W/rn) * ceil(H/rn), rn = 16 or 32) over the jobs */, int high_bitdepth, int top_level /* 2: 16x16, 3: 32x32 */, void *stream, void *stream_recon, void *analysis_done,
+                    int *launched /* out, may be NULL: kernels launched by this call */);
 // Deblock (2 launches) + CDEF search (1 launch) + loop-restoration search (1 launch when with_lr) for all jobs: grid.y = job.
-int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, int with_lr, void *stream);
+int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, int with_lr, void *stream, int *launched);
 
 #ifdef __cplusplus
 }

@@ -115,6 +115,9 @@ def lib():
         L.b200avif_encoder_free.argtypes = [ctypes.c_void_p]
         L.b200avif_encoder_with_quality.argtypes = [ctypes.c_void_p, ctypes.c_float]
         L.b200avif_encoder_with_alpha_quality.argtypes = [ctypes.c_void_p, ctypes.c_float]
+        L.b200avif_encoder_with_quantizer.argtypes = [ctypes.c_void_p, ctypes.c_uint8]
+        L.b200avif_encoder_with_alpha_quantizer.argtypes = [ctypes.c_void_p, ctypes.c_uint8]
+        L.b200avif_default_num_threads.restype = ctypes.c_size_t
         L.b200avif_encoder_with_speed.argtypes = [ctypes.c_void_p, ctypes.c_uint8]
         L.b200avif_encoder_with_bit_depth.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.b200avif_encoder_with_internal_color_model.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -143,6 +146,16 @@ def device_count():
 
 def quality_to_quantizer(q):
     return lib().b200avif_quality_to_quantizer(q)
+
+
+def default_num_threads():
+    """What `with_num_threads(None)` resolves to on this host (rayon::current_num_threads(), av1encoder.rs:413-415)."""
+    return lib().b200avif_default_num_threads()
+
+
+def shutdown():
+    """Release the pooled device contexts of this process."""
+    lib().b200avif_shutdown()
 
 
 def stats():

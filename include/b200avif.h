@@ -6,6 +6,7 @@
  *
  *   b200avif_encoder_new / _clone / _free      Encoder::new(), #[derive(Clone)]   ravif/src/av1encoder.rs:66-110
  *   b200avif_encoder_with_quality              Encoder::with_quality              :112-120  (assert -> B200AVIF_INVALID_ARGUMENT)
+ *   b200avif_encoder_with_quantizer/_alpha_quantizer   the stored fields     :67-71 (quantizer, alpha_quantizer: u8)
  *   b200avif_encoder_with_bit_depth            Encoder::with_bit_depth            :136-140
  *   b200avif_encoder_with_alpha_quality        Encoder::with_alpha_quality        :142-150
  *   b200avif_encoder_with_speed                Encoder::with_speed                :152-163
@@ -74,11 +75,18 @@ void b200avif_encoder_free(b200avif_encoder *enc);
 
 int b200avif_encoder_with_quality(b200avif_encoder *enc, float quality);              /* 1..=100 */
 int b200avif_encoder_with_alpha_quality(b200avif_encoder *enc, float quality);        /* 1..=100 */
+/* raw struct fields (av1encoder.rs:67-71 stores quantizer / alpha_quantizer: u8; with_quality converts, :112-120) */
+int b200avif_encoder_with_quantizer(b200avif_encoder *enc, uint8_t quantizer);        /* 0..=255 */
+int b200avif_encoder_with_alpha_quantizer(b200avif_encoder *enc, uint8_t quantizer);  /* 0..=255 */
 int b200avif_encoder_with_speed(b200avif_encoder *enc, uint8_t speed);                /* 1..=10 */
 int b200avif_encoder_with_bit_depth(b200avif_encoder *enc, int depth);                /* 0 auto(=10) | 8 | 10 */
 int b200avif_encoder_with_internal_color_model(b200avif_encoder *enc, int color_model);
 int b200avif_encoder_with_alpha_color_mode(b200avif_encoder *enc, int mode);
-int b200avif_encoder_with_num_threads(b200avif_encoder *enc, size_t num_threads);     /* 0 = None */
+/* 0 = None = rayon::current_num_threads() of the host (av1encoder.rs:413-415,666): RAYON_NUM_THREADS, else the
+ * usable cores.  It only sets the AV1 tile count, min(threads, area / min_tile_size^2), so like the reference the
+ * default output depends on the host; pass n >= the cap for the most tiles (most device parallelism). */
+int b200avif_encoder_with_num_threads(b200avif_encoder *enc, size_t num_threads);
+size_t b200avif_default_num_threads(void);   /* what 0 / None resolves to on this host */
 int b200avif_encoder_set_exif(b200avif_encoder *enc, const uint8_t *exif, size_t len);/* copied */
 int b200avif_encoder_set_device(b200avif_encoder *enc, int cuda_device);              /* default: current device */
 
@@ -131,6 +139,8 @@ typedef struct b200avif_stats {
   double host_ms_pack;          /* accumulated wall time of symbol packing + muxing */
 } b200avif_stats;
 void b200avif_get_stats(b200avif_stats *out);
+/* Releases the pooled device contexts (streams, arenas, cached rate tables) of this process. */
+void b200avif_shutdown(void);
 int b200avif_device_count(void);   /* 0 when no CUDA device is usable */
 
 #ifdef __cplusplus

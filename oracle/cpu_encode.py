@@ -40,7 +40,11 @@ def configure(w, h, depth, planes, quantizer, speed, threads=None):
     tw = SpeedTweaks()
     L.orc_speed_tweaks_from_my_preset(speed, quantizer, ctypes.byref(tw))
     cap = (w * h) // (tw.min_tile_size ** 2)
-    tiles = cap if threads is None else min(threads, cap)
+    if threads is None:      # ravif `None` = rayon::current_num_threads() of this host (av1encoder.rs:413-415, :666)
+        hl = H.hostlib()
+        hl.b200avif_default_num_threads.restype = ctypes.c_size_t
+        threads = hl.b200avif_default_num_threads()
+    tiles = min(threads, cap)
     tiles = min(max(tiles, 1), 4096)
     f = H.frame_setup(w, h, depth, planes, quantizer, tiles)
     f.reduced_tx_set = tw.reduced_tx_set

@@ -34,6 +34,8 @@ extern "C" {
     pub fn b200avif_encoder_free(enc: *mut b200avif_encoder);
     pub fn b200avif_encoder_with_quality(enc: *mut b200avif_encoder, quality: f32) -> c_int;
     pub fn b200avif_encoder_with_alpha_quality(enc: *mut b200avif_encoder, quality: f32) -> c_int;
+    pub fn b200avif_encoder_with_quantizer(enc: *mut b200avif_encoder, quantizer: u8) -> c_int;
+    pub fn b200avif_encoder_with_alpha_quantizer(enc: *mut b200avif_encoder, quantizer: u8) -> c_int;
     pub fn b200avif_encoder_with_speed(enc: *mut b200avif_encoder, speed: u8) -> c_int;
     pub fn b200avif_encoder_with_bit_depth(enc: *mut b200avif_encoder, depth: c_int) -> c_int;
     pub fn b200avif_encoder_with_internal_color_model(enc: *mut b200avif_encoder, model: c_int) -> c_int;
@@ -69,9 +71,9 @@ pub fn to_error(code: c_int) -> crate::Error {
 // impl Encoder<'_> {
 //     fn native(&self) -> *mut b200avif_encoder { unsafe {
 //         let e = b200avif_encoder_new();
-//         // the builder stores quantizers; the C ABI takes qualities, so keep the f32 the user passed
-//         b200avif_encoder_with_quality(e, self.quality);
-//         b200avif_encoder_with_alpha_quality(e, self.alpha_quality);
+//         // the struct stores the quantizers (av1encoder.rs:67-71), already converted by with_quality (:112-120)
+//         b200avif_encoder_with_quantizer(e, self.quantizer);
+//         b200avif_encoder_with_alpha_quantizer(e, self.alpha_quantizer);
 //         b200avif_encoder_with_speed(e, self.speed);
 //         b200avif_encoder_with_bit_depth(e, match self.output_depth { BitDepth::Eight => 8, BitDepth::Ten => 10, BitDepth::Auto => 0 });
 //         b200avif_encoder_with_internal_color_model(e, self.color_model as c_int);

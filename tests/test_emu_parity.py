@@ -63,6 +63,8 @@ def compare_analysis(ref, out, f):
     (120, 88, 10, 1, 2, dict(split_gates=(60, 120), partition_min=8, lr=1)),   # monochrome (alpha) frame of the fast presets
     (136, 104, 8, 3, 1, dict(enable_intra_edge_filter=1)),                     # intra edge filter / upsampling
     (96, 96, 10, 3, 1, dict(enable_intra_edge_filter=1, partition_max=32, y_mode_mask=0x1fe)),   # directional modes only, up to 32x32
+    # coded size 8 mod 16 and wide: the root-region count (129) exceeds n_mi / 16 + 64 (128); every region must be decided
+    (2056, 8, 8, 1, 1, dict(partition_min=8, rdo_tx_decision=0)),
       # 4 x 3 superblocks: the reconstruction wavefront waits on its neighbours
 ])
 def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
