@@ -53,3 +53,33 @@ def test_mux_is_parsed_by_libavif(with_alpha):
     assert np.array_equal(arr[..., 0], r) and np.array_equal(arr[..., 1], g) and np.array_equal(arr[..., 2], b)
     if with_alpha:
         assert np.array_equal(arr[..., 3], arec.final[0][:h, :w])
+
+
+def test_exif_item_round_trips_through_libavif():
+    """Encoder::with_exif / set_exif (av1encoder.rs:206-219) -> Aviffy::set_exif (:470-472): the Exif item written by the
+    muxer is found and returned byte-for-byte by libavif (Pillow), and the picture still decodes."""
+    w, h = 64, 48
+    img = H.synth_image(w, h, 11)
+    col, rec, f = encode_obu([img[..., 1], img[..., 2], img[..., 0]], w, h, 8, q=60)
+    # a minimal TIFF-structured Exif payload: little-endian header, one IFD0 entry (Software = "b20", inline ASCII);
+    # (an Orientation tag would be rewritten by Pillow, which takes the orientation from irot / imir)
+    exif = b"II*\x00\x08\x00\x00\x00" + b"\x01\x00" + b"\x31\x01\x02\x00\x04\x00\x00\x00b20\x00" + b"\x00\x00\x00\x00"
+    mi = MuxIn()
+    cb = ctypes.create_string_buffer(col, len(col)); eb = ctypes.create_string_buffer(exif, len(exif))
+    mi.color = ctypes.addressof(cb); mi.color_len = len(col)
+    mi.exif = ctypes.addressof(eb); mi.exif_len = len(exif)
+    mi.width = w; mi.height = h; mi.depth = 8; mi.matrix_coefficients = 0
+    L = H.hostlib()
+    mi.color_level_idx = L.b200av1_seq_level_idx(ctypes.byref(f)); mi.alpha_level_idx = mi.color_level_idx
+    out = ctypes.c_void_p(); n = ctypes.c_size_t()
+    assert L.b200avif_mux(ctypes.byref(mi), ctypes.byref(out), ctypes.byref(n)) == 0
+    data = ctypes.string_at(out.value, n.value)
+    assert b"Exif" in data and exif in data
+    im = Image.open(io.BytesIO(data))
+    assert im.size == (w, h)
+    got = im.info.get("exif")
+    assert got is not None and bytes(got).endswith(exif), "libavif did not return the Exif item"
+    assert im.getexif().get(0x0131) == "b20"
+    arr = np.asarray(im.convert("RGB"))
+    # Pillow applies no orientation by itself: the decoded samples are the reconstruction
+    assert np.array_equal(arr[..., 1], rec.final[0][:h, :w])

@@ -218,7 +218,7 @@ def test_rdo_full_hd_frame_parity():
     w, h = 1920, 1080
     img = H.synth_image(w, h, 0)
     planes, _, _ = CE.convert(img, 8)
-    f = CE.configure(w, h, 8, 3, 121, 4)
+    f = CE.configure(w, h, 8, 3, 121, 4, threads=64)
     assert f.tile_cols * f.tile_rows >= 31
     src = H.pad_planes(planes, f)
     ref = H.oracle_encode(f, H.rate_tables(f.base_q_idx), src)
