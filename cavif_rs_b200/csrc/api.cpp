@@ -181,16 +181,17 @@ struct CtxLease {
 struct FrameJob {
   B200Frame f;
   // device
-  uint16_t *d_src[3] = {nullptr, nullptr, nullptr}, *d_rec[3] = {nullptr, nullptr, nullptr};
+  // sample planes at the native width: uint8_t for 8-bit frames, uint16_t for 10-bit; stride() samples per row
+  void *d_src[3] = {nullptr, nullptr, nullptr}, *d_rec[3] = {nullptr, nullptr, nullptr};
   B200Mi *d_mi = nullptr;
   uint16_t *d_eob[3] = {nullptr, nullptr, nullptr};
   int16_t *d_coef[3] = {nullptr, nullptr, nullptr};
   B200BlockDec *d_dec[B200_LEVELS] = {};
   uint32_t *d_satd[B200_LEVELS] = {};
   int8_t *d_cdef = nullptr;
-  uint16_t *d_fin[3] = {nullptr, nullptr, nullptr};   // CDEF output: input of the loop-restoration search (and the test seam)
+  void *d_fin[3] = {nullptr, nullptr, nullptr};   // CDEF output: input of the loop-restoration search (and the test seam)
   B200LrUnit *d_lr[3] = {nullptr, nullptr, nullptr}, *h_lr[3] = {nullptr, nullptr, nullptr};
-  uint16_t *d_lr_out[3] = {nullptr, nullptr, nullptr};   // restored planes: test seam only
+  void *d_lr_out[3] = {nullptr, nullptr, nullptr};   // restored planes: test seam only
   int8_t *h_cdef = nullptr;
   // pinned host
   B200Mi *h_mi = nullptr;
@@ -200,6 +201,9 @@ struct FrameJob {
   int status = 0;
   size_t n_mi() const { return (size_t)f.mi_rows * f.mi_cols; }
   size_t n_px() const { return n_mi() * 16; }
+  size_t bps() const { return f.bit_depth > 8 ? 2 : 1; }                         // bytes per sample
+  size_t stride() const { return ((size_t)f.mi_cols * 4 + 63) & ~(size_t)63; }   // samples per plane row: 64-sample aligned rows
+  size_t plane_bytes() const { return stride() * f.mi_rows * 4 * bps(); }
   size_t n_coef() const { return (size_t)f.sb_rows * f.sb_cols * B200_SB_COEFS; }
   size_t n_sb() const { return (size_t)f.sb_rows * f.sb_cols; }
   size_t n_blk(int lv) const { return (size_t)(f.mi_rows >> lv) * (f.mi_cols >> lv); }
@@ -210,14 +214,14 @@ struct FrameJob {
 size_t job_dev_bytes(const FrameJob &j, bool own_src) {
   const int P = j.f.planes;
   size_t b = 0;
-  if (own_src) b += P * align256(j.n_px() * 2);
-  b += P * align256(j.n_px() * 2);                 // rec
+  if (own_src) b += P * align256(j.plane_bytes());
+  b += P * align256(j.plane_bytes());                 // rec
   b += align256(j.n_mi() * sizeof(B200Mi));
   b += P * align256(j.n_mi() * 2);
   b += P * align256(j.n_coef() * 2);
   b += align256(j.n_sb());
   for (int lv = 0; lv < B200_LEVELS; lv++) b += align256(j.n_blk(lv) * sizeof(B200BlockDec)) + align256(j.n_blk(lv) * B200_SATD_WORDS * 4) + 512;
-  if (j.uses_lr()) b += P * (align256(j.n_px() * 2) + align256(j.n_lr() * sizeof(B200LrUnit)));
+  if (j.uses_lr()) b += P * (align256(j.plane_bytes()) + align256(j.n_lr() * sizeof(B200LrUnit)));
   // the job descriptor and tile list issue_rdo() uploads (one entry per job / tile)
   b += align256(sizeof(B200RdoJob)) + align256((size_t)j.f.tile_rows * j.f.tile_cols * sizeof(B200TileRef)) + 512;
   return b + 8192;
@@ -230,8 +234,8 @@ size_t job_pin_bytes(const FrameJob &j) {
 void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
   const int P = j.f.planes;
   for (int p = 0; p < P; p++) {
-    if (own_src) j.d_src[p] = dev.take<uint16_t>(j.n_px());
-    j.d_rec[p] = dev.take<uint16_t>(j.n_px());
+    if (own_src) j.d_src[p] = dev.take<uint8_t>(j.plane_bytes());
+    j.d_rec[p] = dev.take<uint8_t>(j.plane_bytes());
     j.d_eob[p] = dev.take<uint16_t>(j.n_mi());
     j.d_coef[p] = dev.take<int16_t>(j.n_coef());
     j.h_eob[p] = pin.take<uint16_t>(j.n_mi());
@@ -246,7 +250,7 @@ void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
   j.h_cdef = pin.take<int8_t>(j.n_sb());
   if (j.uses_lr())
     for (int p = 0; p < P; p++) {
-      if (!j.d_fin[p]) j.d_fin[p] = dev.take<uint16_t>(j.n_px());
+      if (!j.d_fin[p]) j.d_fin[p] = dev.take<uint8_t>(j.plane_bytes());
       j.d_lr[p] = dev.take<B200LrUnit>(j.n_lr());
       j.h_lr[p] = pin.take<B200LrUnit>(j.n_lr());
     }
@@ -309,7 +313,7 @@ int rate_tables_for(Context &c, int qidx, B200RateTables **out) {
 // of successive chunks run back to back); stage C, the filters and the download go to the high-priority c.stream_hi and
 // overlap the next chunk's analysis.
 int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin, bool fetch_rec,
-              std::vector<std::vector<uint16_t>> *rec_out, std::vector<std::vector<uint16_t>> *pre_filter_rec = nullptr,
+              std::vector<std::vector<uint8_t>> *rec_out, std::vector<std::vector<uint8_t>> *pre_filter_rec = nullptr,
               cudaEvent_t after_analysis_of = nullptr) {
   std::vector<B200RdoJob> hj(jobs.size());
   std::vector<B200TileRef> tiles;
@@ -318,6 +322,7 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     B200RdoJob &r = hj[i];
     memset(&r, 0, sizeof(r));
     r.frame = j.f;
+    r.stride = (int32_t)j.stride();
     B200RateTables *rt;
     if (int e = rate_tables_for(c, j.f.base_q_idx, &rt)) return e;
     r.rate = rt;
@@ -357,8 +362,8 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     pre_filter_rec->clear();
     for (FrameJob *jp : jobs)
       for (int p = 0; p < jp->f.planes; p++) {
-        pre_filter_rec->emplace_back(jp->n_px());
-        CU(cudaMemcpyAsync(pre_filter_rec->back().data(), jp->d_rec[p], jp->n_px() * 2, cudaMemcpyDeviceToHost, c.stream_hi));
+        pre_filter_rec->emplace_back(jp->plane_bytes());
+        CU(cudaMemcpyAsync(pre_filter_rec->back().data(), jp->d_rec[p], jp->plane_bytes(), cudaMemcpyDeviceToHost, c.stream_hi));
       }
     CU(cudaStreamSynchronize(c.stream_hi));
   }
@@ -370,7 +375,7 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     }
     int with_lr = 0;
     for (FrameJob *jp : jobs) with_lr |= jp->uses_lr();
-    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_edges, max_sb, with_lr, c.stream_hi, &n_launched);
+    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_edges, max_sb, with_lr, jobs[0]->f.bit_depth > 8, c.stream_hi, &n_launched);
     if (fe != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("filter kernel launch failed: ") + cudaGetErrorString((cudaError_t)fe));
     g_launches += (uint64_t)n_launched;
   }
@@ -395,8 +400,8 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     rec_out->clear();
     for (FrameJob *jp : jobs)
       for (int p = 0; p < jp->f.planes; p++) {
-        rec_out->emplace_back(jp->n_px());
-        CU(cudaMemcpyAsync(rec_out->back().data(), jp->d_rec[p], jp->n_px() * 2, cudaMemcpyDeviceToHost, c.stream_hi));
+        rec_out->emplace_back(jp->plane_bytes());
+        CU(cudaMemcpyAsync(rec_out->back().data(), jp->d_rec[p], jp->plane_bytes(), cudaMemcpyDeviceToHost, c.stream_hi));
       }
   }
   CU(cudaEventRecord(c.ev[3], c.stream_hi));
@@ -417,7 +422,7 @@ int finish_rdo(Context &c) {
 }
 
 int run_rdo_and_fetch(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin, bool fetch_rec,
-                      std::vector<std::vector<uint16_t>> *rec_out, std::vector<std::vector<uint16_t>> *pre_filter_rec = nullptr) {
+                      std::vector<std::vector<uint8_t>> *rec_out, std::vector<std::vector<uint8_t>> *pre_filter_rec = nullptr) {
   if (int e = issue_rdo(c, jobs, dev, pin, fetch_rec, rec_out, pre_filter_rec)) return e;
   return finish_rdo(c);
 }
@@ -459,7 +464,6 @@ struct ImageWork {
   int depth = 10;
   bool use_alpha = false;
   FrameJob color, alpha;
-  uint16_t *d_alpha_src = nullptr;
   int status = 0;
 };
 
@@ -534,7 +538,7 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
           ARENA_CHECK(c);
           memcpy(stage, srcv.data(), im.w * im.h * 2);
           CU(cudaMemcpyAsync(d, stage, im.w * im.h * 2, cudaMemcpyHostToDevice, c.stream));
-          if (int e = b200_pad_plane_launch(d, (int)im.w, (int)im.h, (int)im.w, p < 3 ? im.color.d_src[p] : im.alpha.d_src[0], cw, chh, c.stream))
+          if (int e = b200_pad_plane_launch(d, (int)im.w, (int)im.h, (int)im.w, p < 3 ? im.color.d_src[p] : im.alpha.d_src[0], cw, chh, (int)im.color.stride(), depth, c.stream))
             return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
           g_launches++; h2d += im.w * im.h * 2;
         }
@@ -572,7 +576,7 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
         g_launches += mode == 2 ? 1 : 3;
         d_in = d_clean; in_stride = im.w;
       }
-      if (int e = b200_convert_launch(d_in, im.channels, (int)im.w, (int)im.h, (int)in_stride, cw, chh, depth, enc.color_model,
+      if (int e = b200_convert_launch(d_in, im.channels, (int)im.w, (int)im.h, (int)in_stride, cw, chh, (int)im.color.stride(), depth, enc.color_model,
                                       im.color.d_src[0], im.color.d_src[1], im.color.d_src[2],
                                       im.channels == 4 ? im.alpha.d_src[0] : nullptr, im.channels == 4 ? d_flags + (i - ch.a) : nullptr, c.stream))
         return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
@@ -833,7 +837,7 @@ int b200av1_encode_planes(const b200av1_config *cfg, const uint16_t *const plane
     ARENA_CHECK(c);
     for (size_t y = 0; y < h; y++) memcpy(stage + y * w, planes[p] + y * strides[p], w * 2);
     CU(cudaMemcpyAsync(d, stage, w * h * 2, cudaMemcpyHostToDevice, c.stream));
-    if (int e = b200_pad_plane_launch(d, (int)w, (int)h, (int)w, job.d_src[p], cw, ch, c.stream)) return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
+    if (int e = b200_pad_plane_launch(d, (int)w, (int)h, (int)w, job.d_src[p], cw, ch, (int)job.stride(), job.f.bit_depth, c.stream)) return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
     g_launches++; g_h2d += w * h * 2;
   }
   std::vector<FrameJob *> jobs{&job};
@@ -845,6 +849,20 @@ int b200av1_encode_planes(const b200av1_config *cfg, const uint16_t *const plane
   *obu_len = job.obu.size();
   lease.ok = true;
   return 0;
+}
+
+// test seams exchange uint16 planes with a contiguous stride; the device holds native-width samples with its own stride
+static void widen_plane(const uint8_t *dev_copy, size_t bps, size_t dstride, uint16_t *out, size_t w, size_t h) {
+  for (size_t y = 0; y < h; y++)
+    for (size_t x = 0; x < w; x++)
+      out[y * w + x] = bps == 2 ? reinterpret_cast<const uint16_t *>(dev_copy)[y * dstride + x] : dev_copy[y * dstride + x];
+}
+static void narrow_plane(const uint16_t *in, size_t w, size_t h, size_t bps, size_t dstride, uint8_t *out) {
+  for (size_t y = 0; y < h; y++)
+    for (size_t x = 0; x < dstride; x++) {
+      const uint16_t v = in[y * w + (x < w ? x : w - 1)];
+      if (bps == 2) reinterpret_cast<uint16_t *>(out)[y * dstride + x] = v; else out[y * dstride + x] = (uint8_t)v;
+    }
 }
 
 // ---- test seam: colour conversion kernel on host pixels -> coded planes (mi-aligned, edge replicated)
@@ -881,20 +899,23 @@ int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h,
   if (c.dev.reserve(4 * align256(npx * 2) + align256(in_bytes) + 8192) || c.pin.reserve(4096)) return B200AVIF_ENCODING_ERROR;
   c.dev.reset(); c.pin.reset();
   uint8_t *d_in = c.dev.take<uint8_t>(in_bytes + 16);
-  uint16_t *d_p[4];
-  for (int p = 0; p < 4; p++) d_p[p] = c.dev.take<uint16_t>(npx);
+  const size_t bps = depth > 8 ? 2 : 1;
+  uint8_t *d_p[4];
+  for (int p = 0; p < 4; p++) d_p[p] = c.dev.take<uint8_t>(npx * bps);
   int *d_flag = c.dev.take<int>(1);
   CU(cudaMemcpyAsync(d_in, pixels, in_bytes, cudaMemcpyHostToDevice, c.stream));
   CU(cudaMemsetAsync(d_flag, 0, sizeof(int), c.stream));
-  if (int e = b200_convert_launch(d_in, channels, (int)w, (int)h, (int)stride_px, cw, ch, depth, color_model, d_p[0], d_p[1], d_p[2],
+  if (int e = b200_convert_launch(d_in, channels, (int)w, (int)h, (int)stride_px, cw, ch, cw, depth, color_model, d_p[0], d_p[1], d_p[2],
                                   channels == 4 ? d_p[3] : nullptr, channels == 4 ? d_flag : nullptr, c.stream))
     return fail(B200AVIF_ENCODING_ERROR, cudaGetErrorString((cudaError_t)e));
   g_launches++;
+  std::vector<uint8_t> host[4];
   for (int p = 0; p < 4; p++)
-    if (planes[p] && (p < 3 || channels == 4)) CU(cudaMemcpyAsync(planes[p], d_p[p], npx * 2, cudaMemcpyDeviceToHost, c.stream));
+    if (planes[p] && (p < 3 || channels == 4)) { host[p].resize(npx * bps); CU(cudaMemcpyAsync(host[p].data(), d_p[p], npx * bps, cudaMemcpyDeviceToHost, c.stream)); }
   int flag = 0;
   CU(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   CU(cudaStreamSynchronize(c.stream));
+  for (int p = 0; p < 4; p++) if (!host[p].empty()) widen_plane(host[p].data(), bps, (size_t)cw, planes[p], (size_t)cw, (size_t)ch);
   if (any_alpha) *any_alpha = flag;
   lease.ok = true;
   return 0;
@@ -911,14 +932,17 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
   CtxLease lease;
   if (int e = acquire_context(-1, lease.c)) return e;
   Context &c = *lease.c;
-  if (c.dev.reserve(job_dev_bytes(job, true) + 6 * align256(job.n_px() * 2) + (1 << 20)) || c.pin.reserve(job_pin_bytes(job) + (1 << 20))) return B200AVIF_ENCODING_ERROR;
+  if (c.dev.reserve(job_dev_bytes(job, true) + 6 * align256(job.plane_bytes()) + (1 << 20)) || c.pin.reserve(job_pin_bytes(job) + 3 * align256(job.plane_bytes()) + (1 << 20))) return B200AVIF_ENCODING_ERROR;
   c.dev.reset(); c.pin.reset();
   CU(cudaEventRecord(c.ev[0], c.stream));
   job_take(job, c.dev, c.pin, true);
   for (int p = 0; p < job.f.planes; p++) {
-    if (!job.d_fin[p]) job.d_fin[p] = c.dev.take<uint16_t>(job.n_px());
-    if (job.uses_lr() && lr_out && lr_out[p]) job.d_lr_out[p] = c.dev.take<uint16_t>(job.n_px());
-    CU(cudaMemcpyAsync(job.d_src[p], src[p], job.n_px() * 2, cudaMemcpyHostToDevice, c.stream));
+    if (!job.d_fin[p]) job.d_fin[p] = c.dev.take<uint8_t>(job.plane_bytes());
+    if (job.uses_lr() && lr_out && lr_out[p]) job.d_lr_out[p] = c.dev.take<uint8_t>(job.plane_bytes());
+    uint8_t *stage = c.pin.take<uint8_t>(job.plane_bytes());
+    ARENA_CHECK(c);
+    narrow_plane(src[p], (size_t)job.f.mi_cols * 4, (size_t)job.f.mi_rows * 4, job.bps(), job.stride(), stage);
+    CU(cudaMemcpyAsync(job.d_src[p], stage, job.plane_bytes(), cudaMemcpyHostToDevice, c.stream));
     // test seam only: slots of blocks outside the frame are never written (and never read by the packer);
     // zero them so that whole-buffer comparisons against the oracle are meaningful
     CU(cudaMemsetAsync(job.d_coef[p], 0, job.n_coef() * 2, c.stream));
@@ -929,7 +953,7 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
     CU(cudaMemsetAsync(job.d_satd[lv], 0, job.n_blk(lv) * B200_SATD_WORDS * 4, c.stream));
   }
   std::vector<FrameJob *> jobs{&job};
-  std::vector<std::vector<uint16_t>> deb, pre;
+  std::vector<std::vector<uint8_t>> deb, pre;
   if (int e = run_rdo_and_fetch(c, jobs, c.dev, c.pin, true, &deb, &pre)) return e;
   memcpy(mi, job.h_mi, job.n_mi() * sizeof(B200Mi));
   if (cdef_idx) memcpy(cdef_idx, job.h_cdef, job.n_sb());
@@ -940,11 +964,13 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
   for (int p = 0; p < job.f.planes; p++) {
     if (eob && eob[p]) memcpy(eob[p], job.h_eob[p], job.n_mi() * 2);
     if (coef && coef[p]) memcpy(coef[p], job.h_coef[p], job.n_coef() * 2);
-    if (rec && rec[p]) memcpy(rec[p], pre[p].data(), job.n_px() * 2);
-    if (deblocked && deblocked[p]) memcpy(deblocked[p], deb[p].data(), job.n_px() * 2);
-    if (fin && fin[p]) CU(cudaMemcpy(fin[p], job.d_fin[p], job.n_px() * 2, cudaMemcpyDeviceToHost));
+    const size_t cw = (size_t)job.f.mi_cols * 4, chh = (size_t)job.f.mi_rows * 4;
+    std::vector<uint8_t> tmp(job.plane_bytes());
+    if (rec && rec[p]) widen_plane(pre[p].data(), job.bps(), job.stride(), rec[p], cw, chh);
+    if (deblocked && deblocked[p]) widen_plane(deb[p].data(), job.bps(), job.stride(), deblocked[p], cw, chh);
+    if (fin && fin[p]) { CU(cudaMemcpy(tmp.data(), job.d_fin[p], job.plane_bytes(), cudaMemcpyDeviceToHost)); widen_plane(tmp.data(), job.bps(), job.stride(), fin[p], cw, chh); }
     if (job.uses_lr() && lr && lr[p]) memcpy(lr[p], job.h_lr[p], job.n_lr() * sizeof(B200LrUnit));
-    if (job.d_lr_out[p]) CU(cudaMemcpy(lr_out[p], job.d_lr_out[p], job.n_px() * 2, cudaMemcpyDeviceToHost));
+    if (job.d_lr_out[p]) { CU(cudaMemcpy(tmp.data(), job.d_lr_out[p], job.plane_bytes(), cudaMemcpyDeviceToHost)); widen_plane(tmp.data(), job.bps(), job.stride(), lr_out[p], cw, chh); }
   }
   lease.ok = true;
   return 0;

@@ -7,14 +7,15 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
-int b200_convert_launch(const uint8_t *d_in, int channels, int width, int height, int stride_px, int cw, int ch, int depth,
-                        int color_model, uint16_t *p0, uint16_t *p1, uint16_t *p2, uint16_t *alpha, int *any_alpha,
+// output planes: native sample width (uint8_t for depth 8, uint16_t for depth 10), out_stride samples per row
+int b200_convert_launch(const uint8_t *d_in, int channels, int width, int height, int stride_px, int cw, int ch, int out_stride, int depth,
+                        int color_model, void *p0, void *p1, void *p2, void *alpha, int *any_alpha,
                         void *stream);
 // alpha_clean.cu: dirtyalpha.rs / premultiplied branch on the device (mode 1 = UnassociatedClean, 2 = Premultiplied)
 int b200_alpha_clean_launch(const uint8_t *d_in, int w, int h, int stride_px, int mode, uint8_t *d_tmp, uint8_t *d_out,
                             unsigned long long *d_acc, void *stream);
-int b200_pad_plane_launch(const uint16_t *d_in, int width, int height, int in_stride, uint16_t *d_out, int cw, int ch,
-                          void *stream);
+int b200_pad_plane_launch(const uint16_t *d_in, int width, int height, int in_stride, void *d_out, int cw, int ch, int out_stride,
+                          int depth, void *stream);
 // Test seam: colour-conversion kernel.  planes[p]: (8*ceil(h/8)) x (8*ceil(w/8)) uint16 each.
 // test seam: runs the device alpha pre-clean on host pixels, returns the cleaned w*h RGBA8 image
 int b200av1_alpha_clean_run(const uint8_t *rgba, size_t w, size_t h, size_t stride_px, int mode, uint8_t *out);

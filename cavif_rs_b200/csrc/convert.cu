@@ -1,5 +1,6 @@
 // RGBA8 / RGB8 (interleaved, strided) -> planar 8/10-bit Y,Cb,Cr (or G,B,R) + alpha plane,
-// written as uint16 samples into 8-pixel-aligned, edge-replicated coded planes, plus an
+// written at the NATIVE sample width (uint8_t planes for 8-bit, uint16_t for 10-bit) into 8-pixel-aligned,
+// edge-replicated coded planes (row stride `out_stride` samples), plus an
 // "any pixel with a != 255" flag.  One streaming pass, HBM-bound.
 //
 // Bit-exact restatement of the reference's per-pixel arithmetic:
@@ -21,9 +22,10 @@ struct ConvParams {
   int width, height;      // visible
   int stride_px;          // input row stride in pixels
   int cw, ch;             // coded (padded) plane size
+  int out_stride;         // samples per row of the output planes (>= cw, multiple of 4)
   int depth;              // 8 | 10
   int color_model;        // 0 YCbCr(BT601) 1 RGB (planes G,B,R)
-  uint16_t *p0, *p1, *p2, *alpha;   // alpha may be null
+  void *p0, *p1, *p2, *alpha;   // alpha may be null; uint8_t (depth 8) or uint16_t (depth 10) samples
   int *any_alpha;         // device flag (may be null)
 };
 
@@ -49,53 +51,86 @@ __device__ __forceinline__ void convert_px(uint8_t r, uint8_t g, uint8_t b, int 
   for (int k = 0; k < 3; k++) o[k] = (uint16_t)(v[k] <= 0.f ? 0.f : (v[k] >= hi ? hi : v[k]));
 }
 
-// one thread per coded pixel; threads beyond the visible area replicate the last column/row
+template <class PIX> struct Vec4;
+template <> struct Vec4<uint8_t> { typedef uchar4 type; };
+template <> struct Vec4<uint16_t> { typedef ushort4 type; };
+
+// One thread per FOUR horizontally adjacent coded pixels (the coded width is a multiple of 8): one 16-byte load of
+// RGBA8 where the row is 16-byte aligned, one 4- or 8-byte store per plane.  Threads beyond the visible area replicate
+// the last column / row.
+template <class PIX>
 __global__ void __launch_bounds__(256) convert_kernel(ConvParams p) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y;
-  if (x >= p.cw) return;
-  const int sx = min(x, p.width - 1), sy = min(y, p.height - 1);
-  const uint8_t *px = p.in + ((size_t)sy * p.stride_px + sx) * p.channels;
-  uint8_t r, g, b, a = 255;
-  if (p.channels == 4) {
-    const uchar4 v = *reinterpret_cast<const uchar4 *>(px);
-    r = v.x; g = v.y; b = v.z; a = v.w;
+  if (x4 >= p.cw) return;
+  const int sy = min(y, p.height - 1);
+  uint8_t r[4], g[4], b[4], a[4];
+  const uint8_t *row = p.in + (size_t)sy * p.stride_px * p.channels;
+  if (p.channels == 4 && x4 + 3 < p.width && ((reinterpret_cast<uintptr_t>(row) + (size_t)x4 * 4) & 15) == 0) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(row + (size_t)x4 * 4);
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) { r[k] = w[k] & 255; g[k] = (w[k] >> 8) & 255; b[k] = (w[k] >> 16) & 255; a[k] = w[k] >> 24; }
   } else {
-    r = px[0]; g = px[1]; b = px[2];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint8_t *px = row + (size_t)min(x4 + k, p.width - 1) * p.channels;
+      if (p.channels == 4) {
+        const uchar4 v = *reinterpret_cast<const uchar4 *>(px);
+        r[k] = v.x; g[k] = v.y; b[k] = v.z; a[k] = v.w;
+      } else {
+        r[k] = px[0]; g[k] = px[1]; b[k] = px[2]; a[k] = 255;
+      }
+    }
   }
-  uint16_t o[3];
-  convert_px(r, g, b, p.depth, p.color_model, o);
-  const size_t idx = (size_t)y * p.cw + x;
-  p.p0[idx] = o[0]; p.p1[idx] = o[1]; p.p2[idx] = o[2];
-  if (p.alpha) p.alpha[idx] = p.depth == 8 ? (uint16_t)a : to_ten(a);
-  if (p.any_alpha && x < p.width && y < p.height) {
-    const unsigned m = __ballot_sync(__activemask(), a != 255);
+  uint16_t o[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; k++) convert_px(r[k], g[k], b[k], p.depth, p.color_model, o[k]);
+  typedef typename Vec4<PIX>::type V4;
+  const size_t idx = ((size_t)y * p.out_stride + x4) >> 2;
+  V4 v;
+  v.x = (PIX)o[0][0]; v.y = (PIX)o[1][0]; v.z = (PIX)o[2][0]; v.w = (PIX)o[3][0]; reinterpret_cast<V4 *>(p.p0)[idx] = v;
+  v.x = (PIX)o[0][1]; v.y = (PIX)o[1][1]; v.z = (PIX)o[2][1]; v.w = (PIX)o[3][1]; reinterpret_cast<V4 *>(p.p1)[idx] = v;
+  v.x = (PIX)o[0][2]; v.y = (PIX)o[1][2]; v.z = (PIX)o[2][2]; v.w = (PIX)o[3][2]; reinterpret_cast<V4 *>(p.p2)[idx] = v;
+  if (p.alpha) {
+    if (sizeof(PIX) == 1) { v.x = (PIX)a[0]; v.y = (PIX)a[1]; v.z = (PIX)a[2]; v.w = (PIX)a[3]; }
+    else { v.x = (PIX)to_ten(a[0]); v.y = (PIX)to_ten(a[1]); v.z = (PIX)to_ten(a[2]); v.w = (PIX)to_ten(a[3]); }
+    reinterpret_cast<V4 *>(p.alpha)[idx] = v;
+  }
+  if (p.any_alpha && y < p.height) {
+    bool t = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) t |= (x4 + k < p.width) && a[k] != 255;
+    const unsigned m = __ballot_sync(__activemask(), t);
     if (m && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicOr(p.any_alpha, 1);
   }
 }
 
-// raw planar input (encode_raw_planes_*): copy + edge-replicate into the coded plane
-__global__ void __launch_bounds__(256) pad_plane_kernel(const uint16_t *in, int width, int height, int in_stride, uint16_t *out, int cw) {
+// raw planar input (encode_raw_planes_*): copy + edge-replicate into the coded plane (narrowing to the native width)
+template <class PIX>
+__global__ void __launch_bounds__(256) pad_plane_kernel(const uint16_t *in, int width, int height, int in_stride, PIX *out, int cw, int out_stride) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   if (x >= cw) return;
-  out[(size_t)y * cw + x] = in[(size_t)min(y, height - 1) * in_stride + min(x, width - 1)];
+  out[(size_t)y * out_stride + x] = (PIX)in[(size_t)min(y, height - 1) * in_stride + min(x, width - 1)];
 }
 
 }  // namespace
 
-extern "C" int b200_convert_launch(const uint8_t *d_in, int channels, int width, int height, int stride_px, int cw, int ch,
-                                   int depth, int color_model, uint16_t *p0, uint16_t *p1, uint16_t *p2, uint16_t *alpha,
+extern "C" int b200_convert_launch(const uint8_t *d_in, int channels, int width, int height, int stride_px, int cw, int ch, int out_stride,
+                                   int depth, int color_model, void *p0, void *p1, void *p2, void *alpha,
                                    int *any_alpha, void *stream) {
-  ConvParams p{d_in, channels, width, height, stride_px, cw, ch, depth, color_model, p0, p1, p2, alpha, any_alpha};
-  dim3 grid((cw + 255) / 256, ch);
-  convert_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  ConvParams p{d_in, channels, width, height, stride_px, cw, ch, out_stride, depth, color_model, p0, p1, p2, alpha, any_alpha};
+  dim3 grid((cw / 4 + 255) / 256, ch);
+  if (depth > 8) convert_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else convert_kernel<uint8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 }
 
-extern "C" int b200_pad_plane_launch(const uint16_t *d_in, int width, int height, int in_stride, uint16_t *d_out, int cw, int ch,
-                                     void *stream) {
+extern "C" int b200_pad_plane_launch(const uint16_t *d_in, int width, int height, int in_stride, void *d_out, int cw, int ch, int out_stride,
+                                     int depth, void *stream) {
   dim3 grid((cw + 255) / 256, ch);
-  pad_plane_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, width, height, in_stride, d_out, cw);
+  if (depth > 8) pad_plane_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, width, height, in_stride, (uint16_t *)d_out, cw, out_stride);
+  else pad_plane_kernel<uint8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, width, height, in_stride, (uint8_t *)d_out, cw, out_stride);
   return (int)cudaGetLastError();
 }

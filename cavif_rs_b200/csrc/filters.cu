@@ -25,7 +25,8 @@ __device__ __forceinline__ int iabs_d(int v) { return v < 0 ? -v : v; }
 __device__ __forceinline__ int clip3_d(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // one edge sample; px -> q0, step = tap distance
-__device__ void deblock_sample(uint16_t *px, int step, int filter_len, int lvl, int sharp, int bd) {
+template <class PIX>
+__device__ void deblock_sample(PIX *px, int step, int filter_len, int lvl, int sharp, int bd) {
   const int shift = sharp > 4 ? 2 : (sharp > 0 ? 1 : 0);
   int limit = sharp > 0 ? clip3_d(1, 9 - sharp, lvl >> shift) : max(1, lvl >> shift);
   const int blimit = (2 * (lvl + 2) + limit) << (bd - 8);
@@ -56,12 +57,12 @@ __device__ void deblock_sample(uint16_t *px, int step, int filter_len, int lvl, 
     int f = hev ? clip3_d(lo, hi, ps1 - qs1) : 0;
     f = clip3_d(lo, hi, f + 3 * (qs0 - ps0));
     const int f1 = clip3_d(lo, hi, f + 4) >> 3, f2 = clip3_d(lo, hi, f + 3) >> 3;
-    px[0] = (uint16_t)(clip3_d(lo, hi, qs0 - f1) + off);
-    px[-step] = (uint16_t)(clip3_d(lo, hi, ps0 + f2) + off);
+    px[0] = (PIX)(clip3_d(lo, hi, qs0 - f1) + off);
+    px[-step] = (PIX)(clip3_d(lo, hi, ps0 + f2) + off);
     if (!hev) {
       const int f3 = (f1 + 1) >> 1;
-      px[step] = (uint16_t)(clip3_d(lo, hi, qs1 - f3) + off);
-      px[-2 * step] = (uint16_t)(clip3_d(lo, hi, ps1 + f3) + off);
+      px[step] = (PIX)(clip3_d(lo, hi, qs1 - f3) + off);
+      px[-2 * step] = (PIX)(clip3_d(lo, hi, ps1 + f3) + off);
     }
     return;
   }
@@ -80,13 +81,14 @@ __device__ void deblock_sample(uint16_t *px, int step, int filter_len, int lvl, 
     }
     o[i + n] = (t + (1 << (lg - 1))) >> lg;
   }
-  for (int i = -n; i < n; i++) px[i * step] = (uint16_t)o[i + n];
+  for (int i = -n; i < n; i++) px[i * step] = (PIX)o[i + n];
 }
 
 }  // namespace
 
 // grid.y = job, grid.x covers planes * (4 * mi_rows * mi_cols) edge samples.  In place: edges of one pass
 // never overlap (filter length is bounded by the smaller transform on either side).
+template <class PIX>
 __global__ void __launch_bounds__(256) b200_deblock_kernel(const B200RdoJob *jobs, int pass) {
   const B200RdoJob &job = jobs[blockIdx.y];
   const B200Frame *f = &job.frame;
@@ -96,10 +98,10 @@ __global__ void __launch_bounds__(256) b200_deblock_kernel(const B200RdoJob *job
   const int plane = gid / per_plane, e = gid % per_plane;
   const int lvl = plane == 0 ? f->lf_level[pass] : f->lf_level[plane + 1];
   if (!lvl) return;
-  const int stride = f->mi_cols * 4;
+  const int stride = job.stride, estride = f->mi_cols * 4;
   int r, c, i;
   if (pass == 0) { c = e % f->mi_cols; const int y = e / f->mi_cols; r = y >> 2; i = y & 3; }   // consecutive threads: consecutive edges of a row
-  else { const int x = e % stride; r = e / stride; c = x >> 2; i = x & 3; }                       // consecutive threads: consecutive columns
+  else { const int x = e % estride; r = e / estride; c = x >> 2; i = x & 3; }                       // consecutive threads: consecutive columns
   const int x = c * 4, y = r * 4;
   if (x >= f->width || y >= f->height) return;
   if (pass == 0 ? c == 0 : r == 0) return;
@@ -109,8 +111,8 @@ __global__ void __launch_bounds__(256) b200_deblock_kernel(const B200RdoJob *job
   const int base = min(tx, ptx);
   int flen = plane == 0 ? min(base, 16) : min(base, 8);
   if (plane > 0 && flen == 8) flen = 6;
-  uint16_t *P = job.rec[plane];
-  uint16_t *px = pass == 0 ? P + (y + i) * stride + x : P + y * stride + x + i;
+  PIX *P = (PIX *)job.rec[plane];
+  PIX *px = pass == 0 ? P + (y + i) * stride + x : P + y * stride + x + i;
   deblock_sample(px, pass == 0 ? 1 : stride, flen, lvl, f->lf_sharpness, f->bit_depth);
 }
 
@@ -265,6 +267,7 @@ __device__ int lr_subexp_bits(int lo, int hi, int ref, int v) {      // oracle s
 #ifdef B200_EMU
 static int g_f_plane;
 #endif
+template <class PIX>
 __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
   __shared__ LrShared sh;
   const B200RdoJob &job = jobs[blockIdx.y];
@@ -278,10 +281,11 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
   const int nur = b200_lr_units(f->height), nuc = b200_lr_units(f->width);
   if ((int)blockIdx.x >= nur * nuc) return;
   const int ur = blockIdx.x / nuc, uc = blockIdx.x % nuc;
-  const int stride = f->mi_cols * 4, W = f->width, H = f->height, bd = f->bit_depth;
+  const int stride = job.stride, W = f->width, H = f->height, bd = f->bit_depth;
   const int y0 = max(ur * 64 - 8, 0), y1 = ur == nur - 1 ? H : ur * 64 + 56;
   const int x0 = uc * 64, x1 = uc == nuc - 1 ? W : uc * 64 + 64, w = x1 - x0;
-  const uint16_t *deb = job.rec[plane], *cdef = job.fin[plane], *src = job.src[plane];
+  const PIX *deb = (const PIX *)job.rec[plane], *cdef = (const PIX *)job.fin[plane], *src = (const PIX *)job.src[plane];
+  PIX *lr_out = (PIX *)job.lr_out[plane];
   const int tid = threadIdx.x;
   for (int i = tid; i < B200_LR_CANDIDATES * 6; i += 256) sh.acc[i / 6][i % 6] = 0;
   __syncthreads();
@@ -289,7 +293,7 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
   // pass over the unit: phase 0 accumulates the normal equations of every candidate set, phase 1 (tests only) applies
   // the winner
   for (int phase = 0; phase < 2; phase++) {
-    if (phase == 1 && !job.lr_out[plane]) break;
+    if (phase == 1 && !lr_out) break;
     for (int ys = y0; ys < y1;) {
       const int stripe = (ys + 8) >> 6, s_start = stripe * 64 - 8, s_end = stripe * 64 + 55;
       const int ye = min(min(s_end + 1, y1), ys + kLrBandH), bh = ye - ys;
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
         if (phase == 1 && !sh.best.use) {       // restoration off in this unit: the CDEF samples pass through
           for (int i = tid; i < bh * w; i += 256) {
             const int py = i / w, px = i % w;
-            job.lr_out[plane][(ys + py) * stride + x0 + px] = sh.S[(py + 3) * kLrSW + px + 3];
+            lr_out[(ys + py) * stride + x0 + px] = (PIX)sh.S[(py + 3) * kLrSW + px + 3];
           }
           continue;
         }
@@ -391,7 +395,7 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
               v += r1 ? (long long)w2 * f1 : w2 * u;
               const long long o = lr_round2(v, 11);
               const int mx = (1 << bd) - 1;
-              job.lr_out[plane][(ys + py) * stride + x0 + px] = (uint16_t)(o < 0 ? 0 : (o > mx ? mx : o));
+              lr_out[(ys + py) * stride + x0 + px] = (PIX)(o < 0 ? 0 : (o > mx ? mx : o));
             }
           }
           __syncthreads();
@@ -455,13 +459,14 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
 
 // One CTA (256 threads) per 64x64 superblock; grid.y = job.  Phase 1: direction/variance of the 64 8x8 blocks.
 // Phase 2: squared error of every strength index.  Phase 3: apply the winner into job.fin (if present).
+template <class PIX>
 __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) {
   const B200RdoJob &job = jobs[blockIdx.y];
   const B200Frame *f = &job.frame;
   const int nsb = f->sb_rows * f->sb_cols;
   if ((int)blockIdx.x >= nsb) return;
   const int sbr = blockIdx.x / f->sb_cols, sbc = blockIdx.x % f->sb_cols;
-  const int stride = f->mi_cols * 4, W = stride, H = f->mi_rows * 4, bd = f->bit_depth, cshift = bd - 8;
+  const int stride = job.stride, W = f->mi_cols * 4, H = f->mi_rows * 4, bd = f->bit_depth, cshift = bd - 8;
   const int tid = threadIdx.x;
   __shared__ int s_dir[64], s_var[64], s_skip[64], s_any;
   __shared__ unsigned long long s_sse[8];
@@ -472,7 +477,7 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
   for (int p = 0; p < f->planes; p++)
     for (int i = tid; i < kCdefTW * kCdefTW; i += 256) {
       const int yy = sbr * 64 + i / kCdefTW - 2, xx = sbc * 64 + i % kCdefTW - 2;
-      s_px[p][i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? job.rec[p][yy * stride + xx] : kCdefNA;
+      s_px[p][i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (uint16_t)((const PIX *)job.rec[p])[yy * stride + xx] : kCdefNA;
     }
   __syncthreads();
   if (tid < 64) {
@@ -501,7 +506,7 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
       for (int p = 0; p < f->planes; p++)
         for (int i = tid; i < 4096; i += 256) {
           const int y0 = sbr * 64 + (i >> 6), x0 = sbc * 64 + (i & 63);
-          if (y0 < H && x0 < W) job.fin[p][y0 * stride + x0] = job.rec[p][y0 * stride + x0];
+          if (y0 < H && x0 < W) ((PIX *)job.fin[p])[y0 * stride + x0] = ((const PIX *)job.rec[p])[y0 * stride + x0];
         }
     return;
   }
@@ -519,7 +524,7 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
       sec <<= cshift;
       const int damping = f->cdef_damping + cshift - (p > 0);
       const uint16_t *T = s_px[p];
-      const uint16_t *S = job.src[p];
+      const PIX *S = (const PIX *)job.src[p];
       for (int i = tid; i < 4096; i += 256) {
         const int ly = i >> 6, lx = i & 63;
         const int y0 = sbr * 64 + ly, x0 = sbc * 64 + lx;
@@ -539,7 +544,7 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
           const int d = v - (int)S[y0 * stride + x0];
           sse += (unsigned long long)(d * d);
         }
-        if (apply) job.fin[p][y0 * stride + x0] = (uint16_t)v;
+        if (apply) ((PIX *)job.fin[p])[y0 * stride + x0] = (PIX)v;
       }
     }
     if (!apply) {
@@ -559,18 +564,22 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
 }
 
 #ifndef B200_EMU
-extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, int with_lr, void *stream, int *launched) {
+extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, int with_lr, int high_bitdepth, void *stream, int *launched) {
   if (launched) *launched = 0;
   if (n_jobs <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 g1((max_edge_threads + 255) / 256, n_jobs);
-  b200_deblock_kernel<<<g1, 256, 0, st>>>(d_jobs, 0);
-  b200_deblock_kernel<<<g1, 256, 0, st>>>(d_jobs, 1);
-  dim3 g2(max_sb, n_jobs);
-  b200_cdef_kernel<<<g2, 256, 0, st>>>(d_jobs);
-  if (with_lr) {
-    dim3 g3(max_sb, n_jobs, 3);       // restoration units <= superblocks
-    b200_lr_kernel<<<g3, 256, 0, st>>>(d_jobs);
+  dim3 g2(max_sb, n_jobs), g3(max_sb, n_jobs, 3);       // restoration units <= superblocks
+  if (high_bitdepth) {
+    b200_deblock_kernel<uint16_t><<<g1, 256, 0, st>>>(d_jobs, 0);
+    b200_deblock_kernel<uint16_t><<<g1, 256, 0, st>>>(d_jobs, 1);
+    b200_cdef_kernel<uint16_t><<<g2, 256, 0, st>>>(d_jobs);
+    if (with_lr) b200_lr_kernel<uint16_t><<<g3, 256, 0, st>>>(d_jobs);
+  } else {
+    b200_deblock_kernel<uint8_t><<<g1, 256, 0, st>>>(d_jobs, 0);
+    b200_deblock_kernel<uint8_t><<<g1, 256, 0, st>>>(d_jobs, 1);
+    b200_cdef_kernel<uint8_t><<<g2, 256, 0, st>>>(d_jobs);
+    if (with_lr) b200_lr_kernel<uint8_t><<<g3, 256, 0, st>>>(d_jobs);
   }
   if (launched) *launched = 3 + (with_lr ? 1 : 0);
   return (int)cudaGetLastError();
@@ -578,9 +587,10 @@ extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max
 #else
 static const B200RdoJob *g_f_jobs;
 static int g_f_pass;
-static void emu_deblock_entry(void *) { b200_deblock_kernel(g_f_jobs, g_f_pass); }
-static void emu_cdef_entry(void *) { b200_cdef_kernel(g_f_jobs); }
-static void emu_lr_entry(void *) { b200_lr_kernel(g_f_jobs); }
+static bool emu_hbd() { return g_f_jobs[0].frame.bit_depth > 8; }
+static void emu_deblock_entry(void *) { if (emu_hbd()) b200_deblock_kernel<uint16_t>(g_f_jobs, g_f_pass); else b200_deblock_kernel<uint8_t>(g_f_jobs, g_f_pass); }
+static void emu_cdef_entry(void *) { if (emu_hbd()) b200_cdef_kernel<uint16_t>(g_f_jobs); else b200_cdef_kernel<uint8_t>(g_f_jobs); }
+static void emu_lr_entry(void *) { if (emu_hbd()) b200_lr_kernel<uint16_t>(g_f_jobs); else b200_lr_kernel<uint8_t>(g_f_jobs); }
 extern "C" int b200_filters_launch_emu(const B200RdoJob *jobs, int max_edge_threads, int max_sb) {
   g_f_jobs = jobs;
   for (g_f_pass = 0; g_f_pass < 2; g_f_pass++) emu::launch(emu_deblock_entry, nullptr, (unsigned)((max_edge_threads + 255) / 256), 256);

@@ -8,12 +8,15 @@ extern "C" {
 #endif
 
 // One AV1 frame to encode (the colour planes of an image, or its alpha plane): all pointers are
-// device pointers.  Planes are uint16 samples, row stride mi_cols*4, mi_rows*4 rows.
+// device pointers.  Planes hold samples at their NATIVE width - uint8_t for 8-bit video (frame.bit_depth == 8),
+// uint16_t for 10-bit - with `stride` samples per row (>= mi_cols*4) and mi_rows*4 rows.
 typedef struct B200RdoJob {
   B200Frame frame;
   const B200RateTables *rate;
-  const uint16_t *src[3];
-  uint16_t *rec[3];
+  int32_t stride;          // samples per row of src / rec / fin / lr_out
+  int32_t reserved_;
+  const void *src[3];
+  void *rec[3];
   B200Mi *mi;
   uint16_t *eob[3];
   int16_t *coef[3];
@@ -22,10 +25,10 @@ typedef struct B200RdoJob {
   // in-loop filter stage (filters.cu): rec is deblocked IN PLACE; cdef_idx receives the per-superblock
   // strength index (-1: nothing coded in the superblock); fin (optional, may be NULL) receives the CDEF output.
   int8_t *cdef_idx;       // sb_rows*sb_cols
-  uint16_t *fin[3];
+  void *fin[3];
   // loop restoration (frame.lr_type[p] != 0; needs fin): per-unit decisions, and (optional, tests) the restored planes
   B200LrUnit *lr[3];      // b200_lr_units(height) * b200_lr_units(width) per plane
-  uint16_t *lr_out[3];
+  void *lr_out[3];
 } B200RdoJob;
 
 typedef struct B200TileRef {
@@ -40,7 +43,7 @@ int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200TileRef *d_t
                     int max_regions /* largest root-region count (ceil(W/rn) * ceil(H/rn), rn = 16 or 32) over the jobs */, int high_bitdepth, int top_level /* 2: 16x16, 3: 32x32 */, void *stream, void *stream_recon, void *analysis_done,
                     int *launched /* out, may be NULL: kernels launched by this call */);
 // Deblock (2 launches) + CDEF search (1 launch) + loop-restoration search (1 launch when with_lr) for all jobs: grid.y = job.
-int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, int with_lr, void *stream, int *launched);
+int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, int with_lr, int high_bitdepth, void *stream, int *launched);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,8 @@ import harness as H
 
 
 class RdoJob(ctypes.Structure):
-    _fields_ = [("frame", H.B200Frame), ("rate", ctypes.c_void_p), ("src", ctypes.c_void_p * 3), ("rec", ctypes.c_void_p * 3),
+    _fields_ = [("frame", H.B200Frame), ("rate", ctypes.c_void_p), ("stride", ctypes.c_int32), ("reserved_", ctypes.c_int32),
+                ("src", ctypes.c_void_p * 3), ("rec", ctypes.c_void_p * 3),
                 ("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3),
                 ("dec", ctypes.c_void_p * H.LEVELS), ("satd", ctypes.c_void_p * H.LEVELS),
                 ("cdef_idx", ctypes.c_void_p), ("fin", ctypes.c_void_p * 3),
@@ -22,7 +23,7 @@ class TileRef(ctypes.Structure):
 def emu_lib():
     out = os.path.join(H.ROOT, "build", "libemu.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    src = [os.path.join(H.ROOT, p) for p in ("tests/emu/emu_main.cpp", "tests/emu/cuda_emu.h", "cavif_rs_b200/csrc/rdo.cu",
+    src = [os.path.join(H.ROOT, p) for p in ("tests/emu/emu_main.cpp", "tests/emu/cuda_emu.h", "cavif_rs_b200/csrc/rdo.cu", "cavif_rs_b200/csrc/av1_dev.cuh",
                                              "cavif_rs_b200/csrc/filters.cu", "cavif_rs_b200/csrc/rdo.h", "cavif_rs_b200/csrc/records.h")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in src):
         r = subprocess.run(["g++", "-O1", "-std=c++17", "-DB200_EMU", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-Itests/emu",
@@ -85,7 +86,11 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
     ref = H.oracle_encode(f, rt, src)
     out = H.Records(f)
     job = RdoJob(); job.frame = f; job.rate = rt.ctypes.data
-    src3 = list(src) + [src[0]] * (3 - len(src))
+    # the kernels work on planes of the native sample width: uint8 for 8-bit video, uint16 for 10-bit
+    pix = np.uint8 if depth == 8 else np.uint16
+    job.stride = f.mi_cols * 4
+    src3 = [np.ascontiguousarray(a.astype(pix)) for a in (list(src) + [src[0]] * (3 - len(src)))]
+    out.rec = [np.zeros(r.shape, pix) for r in out.rec]
     for p in range(3):
         job.src[p] = src3[p].ctypes.data; job.rec[p] = out.rec[p].ctypes.data
         job.eob[p] = out.eob[p].ctypes.data; job.coef[p] = out.coef[p].ctypes.data
