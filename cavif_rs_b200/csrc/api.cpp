@@ -119,6 +119,8 @@ struct Context {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_analysis = nullptr;  // stages A + B of the current chunk are done
   std::map<int, B200RateTables *> d_rate;   // per base_q_idx
+  const uint32_t *stream_total = nullptr;   // last issue_rdo(): total levels gathered (pinned, valid after the streams are drained)
+  size_t stream_capacity = 0;
   // Queued work is drained before anything is freed.  Contexts are destroyed by b200avif_shutdown() or when a call
   // drops a context after an error; NOT from a static destructor at process exit (the CUDA runtime may already be gone).
   void drain() { if (stream) cudaStreamSynchronize(stream); if (stream_hi) cudaStreamSynchronize(stream_hi); }
@@ -185,7 +187,8 @@ struct FrameJob {
   void *d_src[3] = {nullptr, nullptr, nullptr}, *d_rec[3] = {nullptr, nullptr, nullptr};
   B200Mi *d_mi = nullptr;
   uint16_t *d_eob[3] = {nullptr, nullptr, nullptr};
-  int16_t *d_coef[3] = {nullptr, nullptr, nullptr};
+  int16_t *d_coef[3] = {nullptr, nullptr, nullptr};      // backing store of the compact level streams (dense capacity)
+  uint32_t *d_stream_len[3] = {nullptr, nullptr, nullptr};   // per (frame superblock row, tile column) region
   B200BlockDec *d_dec[B200_LEVELS] = {};
   uint32_t *d_satd[B200_LEVELS] = {};
   int8_t *d_cdef = nullptr;
@@ -196,7 +199,8 @@ struct FrameJob {
   // pinned host
   B200Mi *h_mi = nullptr;
   uint16_t *h_eob[3] = {nullptr, nullptr, nullptr};
-  int16_t *h_coef[3] = {nullptr, nullptr, nullptr};
+  const int16_t *h_stream_base = nullptr;                 // gathered level streams of the chunk (pinned)
+  const uint32_t *h_stream_off[3] = {nullptr, nullptr, nullptr};   // per plane: offset of every region into h_stream_base
   std::vector<uint8_t> obu;
   int status = 0;
   size_t n_mi() const { return (size_t)f.mi_rows * f.mi_cols; }
@@ -207,6 +211,7 @@ struct FrameJob {
   size_t n_coef() const { return (size_t)f.sb_rows * f.sb_cols * B200_SB_COEFS; }
   size_t n_sb() const { return (size_t)f.sb_rows * f.sb_cols; }
   size_t n_blk(int lv) const { return (size_t)(f.mi_rows >> lv) * (f.mi_cols >> lv); }
+  size_t n_regions() const { return (size_t)f.sb_rows * f.tile_cols; }
   size_t n_lr() const { return (size_t)b200_lr_units(f.width) * b200_lr_units(f.height); }
   bool uses_lr() const { return f.enable_restoration && (f.lr_type[0] || f.lr_type[1] || f.lr_type[2]); }
 };
@@ -219,6 +224,7 @@ size_t job_dev_bytes(const FrameJob &j, bool own_src) {
   b += align256(j.n_mi() * sizeof(B200Mi));
   b += P * align256(j.n_mi() * 2);
   b += P * align256(j.n_coef() * 2);
+  b += P * (align256(j.n_regions() * 4) + j.n_regions() * (sizeof(B200StreamRegionH) + 4) + 512);   // stream lengths, gather regions + offsets
   b += align256(j.n_sb());
   for (int lv = 0; lv < B200_LEVELS; lv++) b += align256(j.n_blk(lv) * sizeof(B200BlockDec)) + align256(j.n_blk(lv) * B200_SATD_WORDS * 4) + 512;
   if (j.uses_lr()) b += P * (align256(j.plane_bytes()) + align256(j.n_lr() * sizeof(B200LrUnit)));
@@ -228,8 +234,8 @@ size_t job_dev_bytes(const FrameJob &j, bool own_src) {
 }
 size_t job_pin_bytes(const FrameJob &j) {
   const int P = j.f.planes;
-  return align256(j.n_mi() * sizeof(B200Mi)) + P * align256(j.n_mi() * 2) + P * align256(j.n_coef() * 2) + align256(j.n_sb()) +
-         P * align256(j.n_lr() * sizeof(B200LrUnit)) + 4096;
+  return align256(j.n_mi() * sizeof(B200Mi)) + P * align256(j.n_mi() * 2) + P * align256(j.n_coef() * 2) /* share of the chunk's stream buffer */ +
+         P * (j.n_regions() * 4 + 256) + align256(j.n_sb()) + P * align256(j.n_lr() * sizeof(B200LrUnit)) + 4096;
 }
 void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
   const int P = j.f.planes;
@@ -238,8 +244,8 @@ void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
     j.d_rec[p] = dev.take<uint8_t>(j.plane_bytes());
     j.d_eob[p] = dev.take<uint16_t>(j.n_mi());
     j.d_coef[p] = dev.take<int16_t>(j.n_coef());
+    j.d_stream_len[p] = dev.take<uint32_t>(j.n_regions());
     j.h_eob[p] = pin.take<uint16_t>(j.n_mi());
-    j.h_coef[p] = pin.take<int16_t>(j.n_coef());
   }
   j.d_mi = dev.take<B200Mi>(j.n_mi());
   for (int lv = 0; lv < B200_LEVELS; lv++) {
@@ -328,7 +334,7 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     r.rate = rt;
     for (int p = 0; p < 3; p++) {
       const int q = p < j.f.planes ? p : 0;
-      r.src[p] = j.d_src[q]; r.rec[p] = j.d_rec[q]; r.eob[p] = j.d_eob[q]; r.coef[p] = j.d_coef[q];
+      r.src[p] = j.d_src[q]; r.rec[p] = j.d_rec[q]; r.eob[p] = j.d_eob[q]; r.coef[p] = j.d_coef[q]; r.stream_len[p] = j.d_stream_len[q];
     }
     r.mi = j.d_mi;
     for (int lv = 0; lv < B200_LEVELS; lv++) { r.dec[lv] = j.d_dec[lv]; r.satd[lv] = j.d_satd[lv]; }
@@ -352,9 +358,27 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     const int rn4 = jp->f.partition_max >= 32 ? 8 : 4;
     max_regions = std::max(max_regions, ((jp->f.mi_cols + rn4 - 1) / rn4) * ((jp->f.mi_rows + rn4 - 1) / rn4));
   }
+  // superblock-row slots of the reconstruction chain: as many as keep every tile of the launch resident at once
+  int recon_rows = 4;
+  {
+    int dev_id = 0, sms = 148, smem_sm = 227 * 1024;
+    cudaGetDevice(&dev_id);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev_id);
+    int max_tile_rows = 1;
+    for (FrameJob *jp : jobs)
+      for (int tr = 0; tr < jp->f.tile_rows; tr++) max_tile_rows = std::max(max_tile_rows, jp->f.tile_row_start_sb[tr + 1] - jp->f.tile_row_start_sb[tr]);
+    while (recon_rows > 1) {
+      const size_t need = b200_recon_smem_bytes(jobs[0]->f.bit_depth > 8, top_level, recon_rows) + 1024;
+      const size_t per_sm = need ? (size_t)smem_sm / need : 0;
+      if (recon_rows <= max_tile_rows && per_sm * (size_t)sms >= tiles.size()) break;
+      recon_rows >>= 1;
+    }
+    if (const char *ev = getenv("B200AVIF_RECON_ROWS")) { const int v = atoi(ev); if (v == 1 || v == 2 || v == 4) recon_rows = v; }
+  }
   int n_launched = 0;
   const int le = b200_rdo_launch(d_jobs, (int)jobs.size(), d_tiles, (int)tiles.size(), max_blocks4, max_regions, jobs[0]->f.bit_depth > 8,
-                                 top_level, c.stream, c.stream_hi, c.ev_analysis, &n_launched);   // one bit depth per call
+                                 top_level, recon_rows, c.stream, c.stream_hi, c.ev_analysis, &n_launched);   // one bit depth per call
   if (le != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("RDO kernel launch failed: ") + cudaGetErrorString((cudaError_t)le));
   g_launches += (uint64_t)n_launched;   // counted by the launcher: (SATD + analysis) per level + partition decision + reconstruction
   CU(cudaEventRecord(c.ev[2], c.stream_hi));
@@ -392,9 +416,41 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
       }
     for (int p = 0; p < j.f.planes; p++) {
       CU(cudaMemcpyAsync(j.h_eob[p], j.d_eob[p], j.n_mi() * 2, cudaMemcpyDeviceToHost, c.stream_hi));
-      CU(cudaMemcpyAsync(j.h_coef[p], j.d_coef[p], j.n_coef() * 2, cudaMemcpyDeviceToHost, c.stream_hi));
-      d2h += j.n_mi() * 2 + j.n_coef() * 2;
+      d2h += j.n_mi() * 2;
     }
+  }
+  {
+    // Quantised levels: the reconstruction chain wrote compact streams (eob levels per transform block) at the start of
+    // every (frame superblock row, tile column) region of the coefficient planes.  One scan + one gather kernel pack all
+    // regions of the chunk back to back straight into pinned host memory (the used bytes only cross PCIe), the packer
+    // gets the offsets.
+    std::vector<B200StreamRegionH> regs;
+    size_t capacity = 0;
+    for (FrameJob *jp : jobs)
+      for (int p = 0; p < jp->f.planes; p++) {
+        capacity += jp->n_coef();
+        for (int sbr = 0; sbr < jp->f.sb_rows; sbr++)
+          for (int tc = 0; tc < jp->f.tile_cols; tc++)
+            regs.push_back(B200StreamRegionH{jp->d_coef[p] + ((size_t)sbr * jp->f.sb_cols + jp->f.tile_col_start_sb[tc]) * B200_SB_COEFS,
+                                             jp->d_stream_len[p] + (size_t)sbr * jp->f.tile_cols + tc});
+      }
+    capacity = std::min<size_t>(capacity, 0xfffffff0u);
+    B200StreamRegionH *d_regs = dev.take<B200StreamRegionH>(regs.size());
+    uint32_t *d_off = dev.take<uint32_t>(regs.size() + 1);
+    uint32_t *h_off = pin.take<uint32_t>(regs.size() + 1);
+    int16_t *h_stream = pin.take<int16_t>(capacity);
+    if (dev.overflow || pin.overflow) return fail(B200AVIF_ENCODING_ERROR, "internal error: work arena too small for this batch");
+    CU(cudaMemcpyAsync(d_regs, regs.data(), regs.size() * sizeof(B200StreamRegionH), cudaMemcpyHostToDevice, c.stream_hi));
+    const int ge = b200_stream_gather_launch(d_regs, (int)regs.size(), d_off, h_stream, (uint32_t)capacity, c.stream_hi);
+    if (ge != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("stream gather launch failed: ") + cudaGetErrorString((cudaError_t)ge));
+    g_launches += 2;
+    CU(cudaMemcpyAsync(h_off, d_off, (regs.size() + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream_hi));
+    d2h += (regs.size() + 1) * sizeof(uint32_t);
+    size_t k = 0;
+    for (FrameJob *jp : jobs)
+      for (int p = 0; p < jp->f.planes; p++) { jp->h_stream_base = h_stream; jp->h_stream_off[p] = h_off + k; k += jp->n_regions(); }
+    c.stream_total = h_off + regs.size();
+    c.stream_capacity = capacity;
   }
   if (fetch_rec && rec_out) {
     rec_out->clear();
@@ -413,6 +469,11 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
 int finish_rdo(Context &c) {
   CU(cudaStreamSynchronize(c.stream_hi));
   CU(cudaStreamSynchronize(c.stream));
+  if (c.stream_total) {
+    if (*c.stream_total > c.stream_capacity) return fail(B200AVIF_ENCODING_ERROR, "internal error: level stream larger than its buffer");
+    g_d2h += (uint64_t)*c.stream_total * 2;
+    c.stream_total = nullptr;
+  }
   float ms_rdo = 0, ms_tot = 0;
   cudaEventElapsedTime(&ms_rdo, c.ev[1], c.ev[2]);
   cudaEventElapsedTime(&ms_tot, c.ev[0], c.ev[3]);
@@ -441,7 +502,8 @@ void pack_jobs(std::vector<FrameJob *> &jobs) {
     rec.mi = j.h_mi;
     rec.cdef_idx = j.h_cdef;
     for (int p = 0; p < j.f.planes; p++) rec.lr[p] = j.h_lr[p];
-    for (int p = 0; p < j.f.planes; p++) { rec.eob[p] = j.h_eob[p]; rec.coef[p] = j.h_coef[p]; }
+    for (int p = 0; p < j.f.planes; p++) { rec.eob[p] = j.h_eob[p]; rec.stream_off[p] = j.h_stream_off[p]; }
+    rec.stream_base = j.h_stream_base;
     uint8_t *out = nullptr;
     size_t len = 0;
     j.status = b200av1_pack_frame(&j.f, &rec, &out, &len);
@@ -851,6 +913,33 @@ int b200av1_encode_planes(const b200av1_config *cfg, const uint16_t *const plane
   return 0;
 }
 
+// test seam: compact level streams of one plane -> the dense per-block layout of records.h (what the oracle writes)
+static void expand_stream_plane(const FrameJob &j, int p, int16_t *dense) {
+  const B200Frame &f = j.f;
+  memset(dense, 0, j.n_coef() * 2);
+  for (int tr = 0; tr < f.tile_rows; tr++)
+    for (int tc = 0; tc < f.tile_cols; tc++) {
+      const int r0 = f.tile_row_start_sb[tr] * 16, r1 = std::min(f.tile_row_start_sb[tr + 1] * 16, f.mi_rows);
+      const int c0 = f.tile_col_start_sb[tc] * 16, c1 = std::min(f.tile_col_start_sb[tc + 1] * 16, f.mi_cols);
+      for (int sr = r0; sr < r1; sr += 16) {
+        const int16_t *cur = j.h_stream_base + j.h_stream_off[p][(size_t)(sr >> 4) * f.tile_cols + tc];
+        for (int sc = c0; sc < c1; sc += 16)
+          for (int z = 0; z < 256; z++) {
+            int ur = 0, uc = 0;
+            for (int b = 0; b < 4; b++) { uc |= ((z >> (2 * b)) & 1) << b; ur |= ((z >> (2 * b + 1)) & 1) << b; }
+            const int mr = sr + ur, mc = sc + uc;
+            if (mr >= f.mi_rows || mc >= f.mi_cols) continue;
+            const int bs = j.h_mi[(size_t)mr * f.mi_cols + mc].bsize;
+            const int n4 = bs == BLOCK_4X4 ? 1 : (bs == BLOCK_8X8 ? 2 : (bs == BLOCK_16X16 ? 4 : 8));
+            if ((mr & (n4 - 1)) || (mc & (n4 - 1))) continue;
+            const int e = j.h_eob[p][(size_t)mr * f.mi_cols + mc];
+            memcpy(dense + b200_coef_offset(&f, mr, mc), cur, (size_t)e * 2);
+            cur += e;
+          }
+      }
+    }
+}
+
 // test seams exchange uint16 planes with a contiguous stride; the device holds native-width samples with its own stride
 static void widen_plane(const uint8_t *dev_copy, size_t bps, size_t dstride, uint16_t *out, size_t w, size_t h) {
   for (size_t y = 0; y < h; y++)
@@ -963,7 +1052,7 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
   }
   for (int p = 0; p < job.f.planes; p++) {
     if (eob && eob[p]) memcpy(eob[p], job.h_eob[p], job.n_mi() * 2);
-    if (coef && coef[p]) memcpy(coef[p], job.h_coef[p], job.n_coef() * 2);
+    if (coef && coef[p]) expand_stream_plane(job, p, coef[p]);
     const size_t cw = (size_t)job.f.mi_cols * 4, chh = (size_t)job.f.mi_rows * 4;
     std::vector<uint8_t> tmp(job.plane_bytes());
     if (rec && rec[p]) widen_plane(pre[p].data(), job.bps(), job.stride(), rec[p], cw, chh);

@@ -83,6 +83,7 @@ struct TileCtx {
   int16_t *coef[3];
   int stride;
   int tr0, tr1, tc0, tc1;
+  int tile_col;           // tile column index (reconstruction stage: stream bookkeeping)
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

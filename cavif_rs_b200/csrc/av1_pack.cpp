@@ -267,7 +267,11 @@ struct TilePacker {
     const int ptype = plane > 0;
     const int txs_ctx = txs;          // square transforms
     const int eob = rec.eob[plane][(size_t)mi_r * f.mi_cols + mi_c];
-    const int16_t *qc = rec.coef[plane] + b200_coef_offset(&f, mi_r, mi_c);
+    // dense layout (oracle): the block's slot range; compact streams (device): the plane's cursor, blocks arrive in
+    // coding order
+    const int16_t *qc;
+    if (rec.stream_base) { qc = stream_cur[plane]; stream_cur[plane] += eob; }
+    else qc = rec.coef[plane] + b200_coef_offset(&f, mi_r, mi_c);
     // --- all_zero context
     int ctx;
     {
@@ -519,6 +523,7 @@ struct TilePacker {
     write_sb_tree(r + hbs, c + hbs, lvl - 1);
   }
 
+  const int16_t *stream_cur[3] = {nullptr, nullptr, nullptr};
   std::vector<uint8_t> run(int tile_row, int tile_col) {
     mi_row_start = f.tile_row_start_sb[tile_row] * 16;
     mi_row_end = std::min(f.tile_row_start_sb[tile_row + 1] * 16, f.mi_rows);
@@ -531,6 +536,8 @@ struct TilePacker {
       above_dc[p].assign(f.mi_cols + 32, 0);
     }
     for (int r = mi_row_start; r < mi_row_end; r += 16) {
+      if (rec.stream_base)
+        for (int p = 0; p < f.planes; p++) stream_cur[p] = rec.stream_base + rec.stream_off[p][(size_t)(r >> 4) * f.tile_cols + tile_col];
       memset(left_level, 0, sizeof(left_level));
       memset(left_dc, 0, sizeof(left_dc));
       for (int c = mi_col_start; c < mi_col_end; c += 16) {

@@ -14,6 +14,11 @@ typedef struct B200Records {
   const B200Mi *mi;          // [mi_rows * mi_cols]
   const uint16_t *eob[3];    // per plane [mi_rows * mi_cols], valid at the top-left unit of each transform block
   const int16_t *coef[3];    // per plane [sb_rows * sb_cols * 4096], quantised levels in scan order (b200_coef_offset)
+  // Compact level streams (device path, recon.cu); when stream_base != NULL `coef` is not read.  The eob levels of every
+  // transform block (scan order) of region (plane p, frame superblock row r, tile column c), appended in coding order,
+  // start at stream_base + stream_off[p][r * tile_cols + c].
+  const int16_t *stream_base;
+  const uint32_t *stream_off[3];
   const int8_t *cdef_idx;    // [sb_rows * sb_cols] or NULL
   const B200LrUnit *lr[3];   // per plane [b200_lr_units(height) * b200_lr_units(width)]; read only where f->lr_type[plane] != 0
 } B200Records;

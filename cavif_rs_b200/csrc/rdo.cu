@@ -186,82 +186,6 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, SH &sh, int x, i
 #undef DELTA_UV
 }
 
-// ---- stage C: closed-loop reconstruction of one decided block by one warp (oracle reconstruct_block) ----------------
-template <bool HBD, class SH>
-__device__ __noinline__ void reconstruct_block(const TileCtx &t, SH &sh, int x, int y, int lg) {
-  const int n = 1 << lg, N2 = n * n, G = 32 >> lg;
-  const B200Frame *f = t.f;
-  const int lane = lane_id(), g = lane >> lg;
-  const int planes = f->planes, bd = f->bit_depth;
-  const int mi_r = y >> 2, mi_c = x >> 2, n4 = n >> 2;
-  typedef typename SH::Pix PIX;
-  const B200Mi m = t.mi[mi_r * f->mi_cols + mi_c];
-#pragma unroll 1
-  for (int p = 0; p < planes; p++)
-#pragma unroll 1
-    for (int q = lane; q < N2; q += 32) sh.src[p][q] = ((const PIX *)t.src[p])[(y + (q >> lg)) * t.stride + x + (q & (n - 1))];
-#pragma unroll 1
-  for (int i = lane; i < (int)sizeof(sh.lev) / 4; i += 32) reinterpret_cast<uint32_t *>(sh.lev)[i] = 0;
-  const int avail = block_avail(t, x, y, n), ha = avail & 1, hl = (avail >> 1) & 1;
-#pragma unroll 1
-  for (int p = 0; p < planes; p++) build_edges(t, sh, (const PIX *)t.rec[p], p, x, y, n, avail);
-  __syncwarp();
-  const long long coff = b200_coef_offset(f, mi_r, mi_c);
-  int any = 0;
-  // CFL chroma needs the reconstructed luma of this block: luma goes alone first, then both chroma planes
-  const bool cfl = planes > 1 && m.uv_mode == UV_CFL_PRED;
-  int au = 0, av = 0;
-  if (cfl) {
-    const int js = (m.flags >> 1) & 7, su = (js + 1) / 3, sv = (js + 1) % 3;
-    au = su == 0 ? 0 : (su == 1 ? -1 : 1) * ((m.cfl & 15) + 1);
-    av = sv == 0 ? 0 : (sv == 1 ? -1 : 1) * ((m.cfl >> 4) + 1);
-  }
-#pragma unroll 1
-  for (int p0 = 0; p0 < planes;) {              // plane p = p0 + g handled by lane group g
-    const int cnt = (cfl && p0 == 0) ? 1 : min(G, planes - p0);
-#pragma unroll 1
-    for (int pp = p0; pp < p0 + cnt; pp++) {
-      PIX *dst = sh.pred + (pp - p0) * N2;
-      if (cfl && pp > 0)
-        cfl_predict_block(sh.ac, N2, dc_value_warp(n, sh.above[pp] + EOFF, sh.left[pp] + EOFF, ha, hl, bd), pp == 1 ? au : av, bd, dst);
-      else
-      {
-        int ief = -1;
-        if (f->enable_intra_edge_filter) {     // get_filter_type (spec 7.11.2.8): a smooth mode above or to the left
-          ief = 0;
-          if (ha) { const B200Mi nb = t.mi[(mi_r - 1) * f->mi_cols + mi_c]; const int nm = pp == 0 ? nb.y_mode : nb.uv_mode; if (nm >= SMOOTH_PRED && nm <= SMOOTH_H_PRED) ief = 1; }
-          if (hl) { const B200Mi nb = t.mi[mi_r * f->mi_cols + mi_c - 1]; const int nm = pp == 0 ? nb.y_mode : nb.uv_mode; if (nm >= SMOOTH_PRED && nm <= SMOOTH_H_PRED) ief = 1; }
-        }
-        predict_any(sh, ief, pp == 0 ? m.y_mode : m.uv_mode, (pp == 0 ? (m.angle & 15) : (m.angle >> 4)) - 3, lg, sh.above[pp], sh.left[pp], ha, hl, bd, dst);
-      }
-    }
-    __syncwarp();
-    const int p = p0 + g;
-    const bool ok = g < cnt;
-    const int pe = ok ? p : 0;
-    const TrialOut r = trial_dispatch<HBD>(n, t, sh, pe, sh.src[pe], sh.pred + (ok ? g : 0) * N2,
-                                           pe == 0 ? m.tx_type : chroma_tx_type(m.uv_mode), m.y_mode);
-    if (ok) {
-      // every lane of the group writes its share of the block: reconstruction and scan-ordered levels
-      const int l = lane & (n - 1);
-#pragma unroll 1
-      for (int q = l; q < N2; q += n) {
-        ((PIX *)t.rec[p])[(y + (q >> lg)) * t.stride + x + (q & (n - 1))] = sh.rec[g * N2 + q];
-        t.coef[p][coff + q] = sh.qc[g * N2 + q];
-      }
-      if (l == 0) t.eob[p][mi_r * f->mi_cols + mi_c] = (uint16_t)r.eob;
-    }
-    any |= __ballot_sync(FULL, ok && r.eob != 0) != 0;
-    __syncwarp();
-    if (cfl && p0 == 0) cfl_build_ac(sh.rec, lg, sh.ac);
-    p0 += cnt;
-  }
-  B200Mi mo = m;
-  if (!any) mo.flags |= 1;
-  for (int i = lane; i < n4 * n4; i += 32) t.mi[(mi_r + (i >> (lg - 2))) * f->mi_cols + mi_c + (i & (n4 - 1))] = mo;
-  __syncwarp();
-}
-
 }  // namespace
 
 // ---- stage A.1: SATD of the 13 intra modes for every block of level lv, predicted from SOURCE neighbours.
@@ -564,94 +488,12 @@ __global__ void __launch_bounds__(128) b200_decide_kernel(const B200RdoJob *jobs
   else decide_block<2>(job, x, y, true);
 }
 
-// ---- stage C: one CTA per tile, kReconWarps warps on a superblock-row wavefront.  Warp w owns the tile's SB rows
-// w, w + W, ...; it walks a row left to right (the decided blocks of each SB in z-order) and may start SB (R, C) once
-// row R - 1 has finished SB C + 1: the above-right superblock is the furthest reconstruction any intra edge of this
-// SB can read (its bottom-left 64x64 neighbour is never decoded before it).  Progress counters live in shared memory.
-constexpr int kReconWarps = 4;
-constexpr int kMaxSbRows = 1024;     // 65536 / 64
-#ifdef B200_EMU
-#define B200_SPIN_WAIT() emu::yield()
-#else
-#define B200_SPIN_WAIT() __nanosleep(40)
-#endif
-// The chain stalls on the first touch of every block's source samples (profiles/: 27 % of the active samples of the
-// reconstruction kernel): pull the source rows of superblock (mi row r, mi col c) into L2 ahead of time, one 128-byte
-// line per lane and iteration (64 samples of 2 bytes = one line per row and plane).
-template <class PIX>
-__device__ __forceinline__ void prefetch_sb_source(const TileCtx &t, int r, int c) {
-  const B200Frame *f = t.f;
-  if (r >= t.tr1 || c >= t.tc1) return;
-  const int rows = min(64, (f->mi_rows - r) * 4);
-#pragma unroll 1
-  for (int i = lane_id(); i < rows * f->planes; i += 32) {
-    const int p = i / rows, y = r * 4 + i % rows;
-    B200_PREFETCH_L2((const PIX *)t.src[p] + (size_t)y * t.stride + c * 4);
-  }
-}
-// NMAX = 32 (partition range up to 32x32): 2 warps per tile, 22.9 KB of shared memory each
-template <bool HBD, int NMAX>
-__global__ void __launch_bounds__(kThreads * (NMAX == 32 ? 2 : kReconWarps), NMAX == 32 ? 4 : 4) b200_recon_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
-  constexpr int kWarps = NMAX == 32 ? 2 : kReconWarps;
-  typedef typename PixOf<HBD>::type PIX;
-  typedef SharedT<NMAX, PIX> SH;
-  __shared__ SH shs[kWarps];
-  // superblocks finished in each SB row of this tile: 16-bit counters (<= 1024 columns), two per word, touched only by
-  // shared-memory atomics (release: fence + atomicAdd by the producer warp, acquire: atomic read + fence by the consumer)
-  __shared__ unsigned int sb_done[kMaxSbRows / 2];
-  const B200TileRef tr = tiles[blockIdx.x];
-  const B200RdoJob &job = jobs[tr.job];
-  TileCtx t;
-  ctx_from_job(job, t);
-  const B200Frame *f = t.f;
-  t.tr0 = f->tile_row_start_sb[tr.tile_row] * 16;
-  t.tr1 = min(f->tile_row_start_sb[tr.tile_row + 1] * 16, f->mi_rows);
-  t.tc0 = f->tile_col_start_sb[tr.tile_col] * 16;
-  t.tc1 = min(f->tile_col_start_sb[tr.tile_col + 1] * 16, f->mi_cols);
-  const int sb_rows = (t.tr1 - t.tr0 + 15) >> 4, sb_cols = (t.tc1 - t.tc0 + 15) >> 4;
-  for (int i = threadIdx.x; i < (sb_rows + 1) / 2; i += blockDim.x) sb_done[i] = 0;
-  __syncthreads();
-  const int warp = threadIdx.x >> 5;
-  SH &sh = shs[warp];
-  const int n_warps = blockDim.x >> 5;       // <= kWarps (1 when the wavefront is switched off for debugging)
-#pragma unroll 1
-  for (int R = warp; R < sb_rows; R += n_warps) {
-    const int r = t.tr0 + R * 16;
-    prefetch_sb_source<PIX>(t, r, t.tc0);
-#pragma unroll 1
-    for (int C = 0; C < sb_cols; C++) {
-      prefetch_sb_source<PIX>(t, r, t.tc0 + (C + 1) * 16);        // the next superblock of this row, while this one is coded
-      if (R > 0) {
-        const int need = min(C + 2, sb_cols);
-        while ((int)((atomicAdd(&sb_done[(R - 1) >> 1], 0u) >> (16 * ((R - 1) & 1))) & 0xffffu) < need) B200_SPIN_WAIT();
-        __syncwarp();
-        __threadfence_block();
-      }
-      const int c = t.tc0 + C * 16;
-#pragma unroll 1
-      for (int z = 0; z < 256;) {          // 4x4 units of the superblock in z-order; skip over whole blocks
-        int ur = 0, uc = 0;
-        for (int b = 0; b < 4; b++) { uc |= ((z >> (2 * b)) & 1) << b; ur |= ((z >> (2 * b + 1)) & 1) << b; }
-        const int mr = r + ur, mc = c + uc;
-        if (mr >= f->mi_rows || mc >= f->mi_cols) { z++; continue; }
-        const int bs = t.mi[mr * f->mi_cols + mc].bsize;
-        const int lg = bs == BLOCK_4X4 ? 2 : (bs == BLOCK_8X8 ? 3 : (bs == BLOCK_16X16 ? 4 : 5));
-        reconstruct_block<HBD>(t, sh, mc * 4, mr * 4, lg);
-        z += 1 << (2 * (lg - 2));           // a block covers (n/4)^2 consecutive z indices
-      }
-      __threadfence_block();               // the reconstruction of this SB is visible before the counter moves
-      __syncwarp();
-      if (lane_id() == 0) atomicAdd(&sb_done[R >> 1], 1u << (16 * (R & 1)));
-    }
-  }
-}
-
 #ifndef B200_EMU
 // Stages A + B go to `stream`; stage C goes to `stream_recon` (may be the same stream) after `analysis_done` (an event
 // recorded behind stage B, may be null when both streams are the same).  The caller overlaps the low-parallelism
 // reconstruction chain of one chunk with the analysis of the next by giving stream_recon a higher priority.
 extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200TileRef *d_tiles, int n_tiles, int max_blocks4,
-                               int max_regions, int high_bitdepth, int top_level, void *stream, void *stream_recon, void *analysis_done, int *launched) {
+                               int max_regions, int high_bitdepth, int top_level, int recon_rows, void *stream, void *stream_recon, void *analysis_done, int *launched) {
   if (n_tiles <= 0 || n_jobs <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   int n_launch = 0;
@@ -668,8 +510,6 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     B200_CARVE((b200_analyze_kernel<0, true, 1>)); B200_CARVE((b200_analyze_kernel<1, true, 1>)); B200_CARVE((b200_analyze_kernel<2, true, 1>));
     B200_CARVE((b200_analyze_kernel<2, false, kAnalyzeWarpsTop>)); B200_CARVE((b200_analyze_kernel<2, true, kAnalyzeWarpsTop>));
     B200_CARVE((b200_analyze_kernel<3, false, kAnalyzeWarpsTop32>)); B200_CARVE((b200_analyze_kernel<3, true, kAnalyzeWarpsTop32>));
-    B200_CARVE((b200_recon_kernel<false, 16>)); B200_CARVE((b200_recon_kernel<true, 16>));
-    B200_CARVE((b200_recon_kernel<false, 32>)); B200_CARVE((b200_recon_kernel<true, 32>));
     configured = true;
   }
   const int top = top_level >= 3 ? 3 : 2;
@@ -715,15 +555,9 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     cudaEventRecord((cudaEvent_t)analysis_done, st);
     if (sr != st) cudaStreamWaitEvent(sr, (cudaEvent_t)analysis_done, 0);
   }
-  static const bool serial_chain = getenv("B200AVIF_DEBUG_SERIAL_RECON") != nullptr;      // debugging aid: one warp per tile
-  if (top == 3) {
-    const int bt = kThreads * (serial_chain ? 1 : 2);
-    if (high_bitdepth) b200_recon_kernel<true, 32><<<n_tiles, bt, 0, sr>>>(d_jobs, d_tiles);
-    else b200_recon_kernel<false, 32><<<n_tiles, bt, 0, sr>>>(d_jobs, d_tiles);
-  } else {
-    const int bt = kThreads * (serial_chain ? 1 : kReconWarps);
-    if (high_bitdepth) b200_recon_kernel<true, 16><<<n_tiles, bt, 0, sr>>>(d_jobs, d_tiles);
-    else b200_recon_kernel<false, 16><<<n_tiles, bt, 0, sr>>>(d_jobs, d_tiles);
+  {
+    const int re = b200_recon_launch(d_jobs, d_tiles, n_tiles, high_bitdepth, top, recon_rows, sr);
+    if (re) return re;
   }
   if (launched) *launched = n_launch;
   return (int)cudaGetLastError();
@@ -747,12 +581,8 @@ static void emu_analyze(void *) {
   else EMU_ANALYZE(3, kAnalyzeWarpsTop32);
 }
 static void emu_decide(void *) { b200_decide_kernel(g_emu_jobs); }
-static void emu_recon(void *) {
-  const bool hbd = g_emu_jobs[0].frame.bit_depth > 8;
-  if (g_emu_top == 3) { if (hbd) b200_recon_kernel<true, 32>(g_emu_jobs, g_emu_tiles); else b200_recon_kernel<false, 32>(g_emu_jobs, g_emu_tiles); }
-  else { if (hbd) b200_recon_kernel<true, 16>(g_emu_jobs, g_emu_tiles); else b200_recon_kernel<false, 16>(g_emu_jobs, g_emu_tiles); }
-}
-extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *tiles, int n_tiles) {
+extern "C" int b200_recon_launch_emu(const B200RdoJob *jobs, const B200TileRef *tiles, int n_tiles, int rows);
+extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *tiles, int n_tiles, int recon_rows) {
   g_emu_jobs = jobs; g_emu_tiles = tiles;
   const B200Frame *f = &jobs[0].frame;
   g_emu_top = f->partition_max >= 32 ? 3 : 2;
@@ -767,7 +597,7 @@ extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *ti
   const int rn4 = g_emu_top == 3 ? 8 : 4;
   const int regions = ((f->mi_cols + rn4 - 1) / rn4) * ((f->mi_rows + rn4 - 1) / rn4);
   emu::launch(emu_decide, nullptr, (unsigned)((regions + 127) / 128), 128);
-  emu::launch(emu_recon, nullptr, (unsigned)n_tiles, kThreads * (g_emu_top == 3 ? 2 : kReconWarps));
+  b200_recon_launch_emu(jobs, tiles, n_tiles, recon_rows);
   return 0;
 }
 #endif

@@ -20,6 +20,9 @@ typedef struct B200RdoJob {
   B200Mi *mi;
   uint16_t *eob[3];
   int16_t *coef[3];
+  // compact level streams (recon.cu): length of the stream of every (frame superblock row, tile column) region per plane,
+  // [sb_rows * tile_cols]; the stream itself starts at the region's first slot of coef[plane]
+  uint32_t *stream_len[3];
   B200BlockDec *dec[B200_LEVELS];   // analysis decisions per level (0: 4x4 .. 3: 32x32), b200_level_rows*cols entries
   uint32_t *satd[B200_LEVELS];      // luma SATD tables per level: [block][14 words]
   // in-loop filter stage (filters.cu): rec is deblocked IN PLACE; cdef_idx receives the per-superblock
@@ -40,8 +43,13 @@ typedef struct B200TileRef {
 // All RDO stages for all jobs on `stream`: SATD + analysis per level, partition decision, reconstruction chain
 // (one warp per tile).  max_blocks4 = largest mi_rows*mi_cols over the jobs; high_bitdepth: all jobs are 10-bit.
 int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200TileRef *d_tiles, int n_tiles, int max_blocks4,
-                    int max_regions /* largest root-region count (ceil(W/rn) * ceil(H/rn), rn = 16 or 32) over the jobs */, int high_bitdepth, int top_level /* 2: 16x16, 3: 32x32 */, void *stream, void *stream_recon, void *analysis_done,
+                    int max_regions /* largest root-region count (ceil(W/rn) * ceil(H/rn), rn = 16 or 32) over the jobs */, int high_bitdepth, int top_level /* 2: 16x16, 3: 32x32 */, int recon_rows /* superblock-row slots per tile: 1, 2, 4 */, void *stream, void *stream_recon, void *analysis_done,
                     int *launched /* out, may be NULL: kernels launched by this call */);
+// recon.cu: the reconstruction chain (one CTA per tile) and the gather of the compact level streams
+int b200_recon_launch(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int n_tiles, int high_bitdepth, int top_level, int rows, void *stream);
+size_t b200_recon_smem_bytes(int high_bitdepth, int top_level, int rows);
+typedef struct B200StreamRegionH { const int16_t *src; const uint32_t *len; } B200StreamRegionH;   // device pointers
+int b200_stream_gather_launch(const void *d_regions, int n_regions, uint32_t *d_offsets /* n + 1 */, int16_t *out, uint32_t capacity, void *stream);
 // Deblock (2 launches) + CDEF search (1 launch) + loop-restoration search (1 launch when with_lr) for all jobs: grid.y = job.
 int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, int with_lr, int high_bitdepth, void *stream, int *launched);
 

@@ -23,6 +23,7 @@ class B200Frame(ctypes.Structure):
 
 class B200Records(ctypes.Structure):
     _fields_ = [("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3),
+                ("stream_base", ctypes.c_void_p), ("stream_off", ctypes.c_void_p * 3),
                 ("cdef_idx", ctypes.c_void_p), ("lr", ctypes.c_void_p * 3)]
 
 RATE_TABLES_BYTES = 2 * (20 * 10 + 3 * 2 + 5 * 5 * 13 + 2 * 13 * 14 + 8 * 7 + 8 + 6 * 16 + 2 * 4 * 13 * 16 + 5 * 13 * 2 +
@@ -230,3 +231,54 @@ def synth_image(w, h, seed=0, alpha=False):
             x0 = int(rng.integers(0, max(1, w - rw))); y0 = int(rng.integers(0, max(1, h - rh)))
             img[y0:y0 + rh, x0:x0 + rw, 3] = 0
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def _zunits():
+    out = []
+    for z in range(256):
+        ur = uc = 0
+        for b in range(4):
+            uc |= ((z >> (2 * b)) & 1) << b
+            ur |= ((z >> (2 * b + 1)) & 1) << b
+        out.append((ur, uc))
+    return out
+
+_ZU = _zunits()
+_BW4 = {0: 1, 3: 2, 6: 4, 9: 8}      # BLOCK_4X4, 8X8, 16X16, 32X32 -> size in 4x4 units
+
+
+def expand_streams(f, mi, eob, backing, planes):
+    """Compact level streams (recon.cu: per (tile superblock row, plane), appended in coding order at the row's first slot of
+    the coefficient plane) -> the dense per-block layout of records.h (b200_coef_offset), for comparisons with the oracle.
+    Returns (dense planes, stream lengths per plane as {(sb row, tile col): n})."""
+    dense = [np.zeros_like(b) for b in backing]
+    lens = [dict() for _ in range(planes)]
+    mi2 = mi.reshape(f.mi_rows, f.mi_cols)
+    for tr in range(f.tile_rows):
+        for tc in range(f.tile_cols):
+            r0, r1 = f.tile_row_start_sb[tr] * 16, min(f.tile_row_start_sb[tr + 1] * 16, f.mi_rows)
+            c0, c1 = f.tile_col_start_sb[tc] * 16, min(f.tile_col_start_sb[tc + 1] * 16, f.mi_cols)
+            for sr in range(r0, r1, 16):
+                start = ((sr >> 4) * f.sb_cols + (c0 >> 4)) * 4096
+                cur = [start] * planes
+                for sc in range(c0, c1, 16):
+                    for (ur, uc) in _ZU:
+                        mr, mc = sr + ur, sc + uc
+                        if mr >= f.mi_rows or mc >= f.mi_cols:
+                            continue
+                        n4 = _BW4[int(mi2[mr, mc]["bsize"])]
+                        if (mr % n4) or (mc % n4):
+                            continue
+                        sb = (mr >> 4) * f.sb_cols + (mc >> 4)
+                        zi = 0
+                        for b in range(4):
+                            zi |= (((mc & 15) >> b) & 1) << (2 * b)
+                            zi |= (((mr & 15) >> b) & 1) << (2 * b + 1)
+                        off = sb * 4096 + zi * 16
+                        for p in range(planes):
+                            e = int(eob[p][mr * f.mi_cols + mc])
+                            dense[p][off:off + e] = backing[p][cur[p]:cur[p] + e]
+                            cur[p] += e
+                for p in range(planes):
+                    lens[p][(sr >> 4, tc)] = cur[p] - start
+    return dense, lens

@@ -10,7 +10,7 @@ import harness as H
 class RdoJob(ctypes.Structure):
     _fields_ = [("frame", H.B200Frame), ("rate", ctypes.c_void_p), ("stride", ctypes.c_int32), ("reserved_", ctypes.c_int32),
                 ("src", ctypes.c_void_p * 3), ("rec", ctypes.c_void_p * 3),
-                ("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3),
+                ("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3), ("stream_len", ctypes.c_void_p * 3),
                 ("dec", ctypes.c_void_p * H.LEVELS), ("satd", ctypes.c_void_p * H.LEVELS),
                 ("cdef_idx", ctypes.c_void_p), ("fin", ctypes.c_void_p * 3),
                 ("lr", ctypes.c_void_p * 3), ("lr_out", ctypes.c_void_p * 3)]
@@ -23,7 +23,7 @@ class TileRef(ctypes.Structure):
 def emu_lib():
     out = os.path.join(H.ROOT, "build", "libemu.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    src = [os.path.join(H.ROOT, p) for p in ("tests/emu/emu_main.cpp", "tests/emu/cuda_emu.h", "cavif_rs_b200/csrc/rdo.cu", "cavif_rs_b200/csrc/av1_dev.cuh",
+    src = [os.path.join(H.ROOT, p) for p in ("tests/emu/emu_main.cpp", "tests/emu/cuda_emu.h", "cavif_rs_b200/csrc/rdo.cu", "cavif_rs_b200/csrc/recon.cu", "cavif_rs_b200/csrc/av1_dev.cuh",
                                              "cavif_rs_b200/csrc/filters.cu", "cavif_rs_b200/csrc/rdo.h", "cavif_rs_b200/csrc/records.h")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in src):
         r = subprocess.run(["g++", "-O1", "-std=c++17", "-DB200_EMU", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-Itests/emu",
@@ -51,6 +51,7 @@ def compare_analysis(ref, out, f):
             assert np.array_equal(ref.dec[lv][k], out.dec[lv][k]), "decision %s level %d" % (k, lv)
 
 
+@pytest.mark.parametrize("rows", [1, 2, 4])
 @pytest.mark.parametrize("w,h,depth,planes,tiles,kw", [
     (64, 48, 8, 3, 1, {}),
     (40, 72, 10, 1, 2, dict(partition_min=8, rdo_tx_decision=0)),
@@ -68,7 +69,7 @@ def compare_analysis(ref, out, f):
     (2056, 8, 8, 1, 1, dict(partition_min=8, rdo_tx_decision=0)),
       # 4 x 3 superblocks: the reconstruction wavefront waits on its neighbours
 ])
-def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
+def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw, rows):
     E = emu_lib()
     f = H.frame_setup(w, h, depth, planes, 121, tiles)
     for k, v in kw.items():
@@ -94,6 +95,9 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
     for p in range(3):
         job.src[p] = src3[p].ctypes.data; job.rec[p] = out.rec[p].ctypes.data
         job.eob[p] = out.eob[p].ctypes.data; job.coef[p] = out.coef[p].ctypes.data
+    slen = [np.zeros(f.sb_rows * f.tile_cols, np.uint32) for _ in range(3)]
+    for p in range(3):
+        job.stream_len[p] = slen[p].ctypes.data
     job.mi = out.mi.ctypes.data
     for lv in range(H.LEVELS):
         job.dec[lv] = out.dec[lv].ctypes.data; job.satd[lv] = out.satd[lv].ctypes.data
@@ -108,10 +112,15 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw):
     lr_out = [np.zeros_like(r) for r in out.rec]
     for p in range(3):
         job.lr[p] = out.lr[p].ctypes.data; job.lr_out[p] = lr_out[p].ctypes.data
-    E.b200_rdo_launch_emu.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    E.b200_rdo_launch_emu.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     E.b200_filters_launch_emu.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
-    E.b200_rdo_launch_emu(ctypes.byref(job), trs, nt)
+    E.b200_rdo_launch_emu(ctypes.byref(job), trs, nt, rows)
     compare_analysis(ref, out, f)
+    # the reconstruction chain emits compact level streams: expand them to the dense per-block layout of the oracle
+    out.coef, lens = H.expand_streams(f, out.mi, out.eob, out.coef, planes)
+    for p in range(planes):
+        for (sbr, tc), n in lens[p].items():
+            assert slen[p][sbr * f.tile_cols + tc] == n, "stream length plane %d region %d,%d" % (p, sbr, tc)
     compare(ref, out, planes)
     # in-loop filter stage: deblock in place, CDEF strength search, CDEF output
     ref_fin, ref_deb = H.oracle_filters(f, ref, src)
