@@ -195,6 +195,8 @@ struct FrameJob {
   void *d_fin[3] = {nullptr, nullptr, nullptr};   // CDEF output: input of the loop-restoration search (and the test seam)
   B200LrUnit *d_lr[3] = {nullptr, nullptr, nullptr}, *h_lr[3] = {nullptr, nullptr, nullptr};
   void *d_lr_out[3] = {nullptr, nullptr, nullptr};   // restored planes: test seam only
+  void *d_dbrows[3] = {nullptr, nullptr, nullptr};   // deblocked rows 54..57 of every superblock row (loop restoration input)
+  void *d_deb_full[3] = {nullptr, nullptr, nullptr}; // whole deblocked planes: test seam only
   int8_t *h_cdef = nullptr;
   // pinned host
   B200Mi *h_mi = nullptr;
@@ -208,6 +210,7 @@ struct FrameJob {
   size_t bps() const { return f.bit_depth > 8 ? 2 : 1; }                         // bytes per sample
   size_t stride() const { return ((size_t)f.mi_cols * 4 + 63) & ~(size_t)63; }   // samples per plane row: 64-sample aligned rows
   size_t plane_bytes() const { return stride() * f.mi_rows * 4 * bps(); }
+  size_t dbrows_bytes() const { return stride() * (size_t)f.sb_rows * 4 * bps(); }
   size_t n_coef() const { return (size_t)f.sb_rows * f.sb_cols * B200_SB_COEFS; }
   size_t n_sb() const { return (size_t)f.sb_rows * f.sb_cols; }
   size_t n_blk(int lv) const { return (size_t)(f.mi_rows >> lv) * (f.mi_cols >> lv); }
@@ -227,7 +230,7 @@ size_t job_dev_bytes(const FrameJob &j, bool own_src) {
   b += P * (align256(j.n_regions() * 4) + j.n_regions() * (sizeof(B200StreamRegionH) + 4) + 512);   // stream lengths, gather regions + offsets
   b += align256(j.n_sb());
   for (int lv = 0; lv < B200_LEVELS; lv++) b += align256(j.n_blk(lv) * sizeof(B200BlockDec)) + align256(j.n_blk(lv) * B200_SATD_WORDS * 4) + 512;
-  if (j.uses_lr()) b += P * (align256(j.plane_bytes()) + align256(j.n_lr() * sizeof(B200LrUnit)));
+  if (j.uses_lr()) b += P * (align256(j.plane_bytes()) + align256(j.dbrows_bytes()) + align256(j.n_lr() * sizeof(B200LrUnit)));
   // the job descriptor and tile list issue_rdo() uploads (one entry per job / tile)
   b += align256(sizeof(B200RdoJob)) + align256((size_t)j.f.tile_rows * j.f.tile_cols * sizeof(B200TileRef)) + 512;
   return b + 8192;
@@ -257,6 +260,7 @@ void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
   if (j.uses_lr())
     for (int p = 0; p < P; p++) {
       if (!j.d_fin[p]) j.d_fin[p] = dev.take<uint8_t>(j.plane_bytes());
+      j.d_dbrows[p] = dev.take<uint8_t>(j.dbrows_bytes());
       j.d_lr[p] = dev.take<B200LrUnit>(j.n_lr());
       j.h_lr[p] = pin.take<B200LrUnit>(j.n_lr());
     }
@@ -339,7 +343,7 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     r.mi = j.d_mi;
     for (int lv = 0; lv < B200_LEVELS; lv++) { r.dec[lv] = j.d_dec[lv]; r.satd[lv] = j.d_satd[lv]; }
     r.cdef_idx = j.d_cdef;
-    for (int p = 0; p < 3; p++) r.fin[p] = j.d_fin[p < j.f.planes ? p : 0];
+    for (int p = 0; p < 3; p++) { r.fin[p] = j.d_fin[p < j.f.planes ? p : 0]; r.dbrows[p] = p < j.f.planes ? j.d_dbrows[p] : nullptr; r.deb_full[p] = p < j.f.planes ? j.d_deb_full[p] : nullptr; }
     for (int p = 0; p < 3; p++) { r.lr[p] = p < j.f.planes ? j.d_lr[p] : nullptr; r.lr_out[p] = p < j.f.planes ? j.d_lr_out[p] : nullptr; }
     for (int tr = 0; tr < j.f.tile_rows; tr++)
       for (int tc = 0; tc < j.f.tile_cols; tc++) tiles.push_back(B200TileRef{(int32_t)i, (int16_t)tr, (int16_t)tc});
@@ -392,14 +396,11 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     CU(cudaStreamSynchronize(c.stream_hi));
   }
   {
-    int max_edges = 0, max_sb = 0;
-    for (FrameJob *jp : jobs) {
-      max_edges = std::max(max_edges, (int)(jp->n_mi() * 4 * jp->f.planes));
-      max_sb = std::max(max_sb, (int)jp->n_sb());
-    }
+    int max_sb = 0;
+    for (FrameJob *jp : jobs) max_sb = std::max(max_sb, (int)jp->n_sb());
     int with_lr = 0;
     for (FrameJob *jp : jobs) with_lr |= jp->uses_lr();
-    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_edges, max_sb, with_lr, jobs[0]->f.bit_depth > 8, c.stream_hi, &n_launched);
+    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_sb, with_lr, jobs[0]->f.bit_depth > 8, c.stream_hi, &n_launched);
     if (fe != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("filter kernel launch failed: ") + cudaGetErrorString((cudaError_t)fe));
     g_launches += (uint64_t)n_launched;
   }
@@ -457,7 +458,7 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     for (FrameJob *jp : jobs)
       for (int p = 0; p < jp->f.planes; p++) {
         rec_out->emplace_back(jp->plane_bytes());
-        CU(cudaMemcpyAsync(rec_out->back().data(), jp->d_rec[p], jp->plane_bytes(), cudaMemcpyDeviceToHost, c.stream_hi));
+        CU(cudaMemcpyAsync(rec_out->back().data(), jp->d_deb_full[p] ? jp->d_deb_full[p] : jp->d_rec[p], jp->plane_bytes(), cudaMemcpyDeviceToHost, c.stream_hi));
       }
   }
   CU(cudaEventRecord(c.ev[3], c.stream_hi));
@@ -1021,12 +1022,13 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
   CtxLease lease;
   if (int e = acquire_context(-1, lease.c)) return e;
   Context &c = *lease.c;
-  if (c.dev.reserve(job_dev_bytes(job, true) + 6 * align256(job.plane_bytes()) + (1 << 20)) || c.pin.reserve(job_pin_bytes(job) + 3 * align256(job.plane_bytes()) + (1 << 20))) return B200AVIF_ENCODING_ERROR;
+  if (c.dev.reserve(job_dev_bytes(job, true) + 9 * align256(job.plane_bytes()) + (1 << 20)) || c.pin.reserve(job_pin_bytes(job) + 3 * align256(job.plane_bytes()) + (1 << 20))) return B200AVIF_ENCODING_ERROR;
   c.dev.reset(); c.pin.reset();
   CU(cudaEventRecord(c.ev[0], c.stream));
   job_take(job, c.dev, c.pin, true);
   for (int p = 0; p < job.f.planes; p++) {
     if (!job.d_fin[p]) job.d_fin[p] = c.dev.take<uint8_t>(job.plane_bytes());
+    job.d_deb_full[p] = c.dev.take<uint8_t>(job.plane_bytes());
     if (job.uses_lr() && lr_out && lr_out[p]) job.d_lr_out[p] = c.dev.take<uint8_t>(job.plane_bytes());
     uint8_t *stage = c.pin.take<uint8_t>(job.plane_bytes());
     ARENA_CHECK(c);

@@ -21,6 +21,8 @@
 
 namespace {
 
+// slot of frame row y in job.dbrows (the deblocked rows 54..57 of every superblock row, kept for the loop restoration)
+__device__ __forceinline__ int db_row_slot(int y) { return (y >> 6) * 4 + ((y & 63) - 54); }
 __device__ __forceinline__ int iabs_d(int v) { return v < 0 ? -v : v; }
 __device__ __forceinline__ int clip3_d(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -86,36 +88,6 @@ __device__ void deblock_sample(PIX *px, int step, int filter_len, int lvl, int s
 
 }  // namespace
 
-// grid.y = job, grid.x covers planes * (4 * mi_rows * mi_cols) edge samples.  In place: edges of one pass
-// never overlap (filter length is bounded by the smaller transform on either side).
-template <class PIX>
-__global__ void __launch_bounds__(256) b200_deblock_kernel(const B200RdoJob *jobs, int pass) {
-  const B200RdoJob &job = jobs[blockIdx.y];
-  const B200Frame *f = &job.frame;
-  const int per_plane = f->mi_rows * f->mi_cols * 4;
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= per_plane * f->planes) return;
-  const int plane = gid / per_plane, e = gid % per_plane;
-  const int lvl = plane == 0 ? f->lf_level[pass] : f->lf_level[plane + 1];
-  if (!lvl) return;
-  const int stride = job.stride, estride = f->mi_cols * 4;
-  int r, c, i;
-  if (pass == 0) { c = e % f->mi_cols; const int y = e / f->mi_cols; r = y >> 2; i = y & 3; }   // consecutive threads: consecutive edges of a row
-  else { const int x = e % estride; r = e / estride; c = x >> 2; i = x & 3; }                       // consecutive threads: consecutive columns
-  const int x = c * 4, y = r * 4;
-  if (x >= f->width || y >= f->height) return;
-  if (pass == 0 ? c == 0 : r == 0) return;
-  const int tx = 4 << job.mi[r * f->mi_cols + c].tx_size;
-  if (pass == 0 ? (x & (tx - 1)) : (y & (tx - 1))) return;
-  const int ptx = 4 << (pass == 0 ? job.mi[r * f->mi_cols + c - 1].tx_size : job.mi[(r - 1) * f->mi_cols + c].tx_size);
-  const int base = min(tx, ptx);
-  int flen = plane == 0 ? min(base, 16) : min(base, 8);
-  if (plane > 0 && flen == 8) flen = 6;
-  PIX *P = (PIX *)job.rec[plane];
-  PIX *px = pass == 0 ? P + (y + i) * stride + x : P + y * stride + x + i;
-  deblock_sample(px, pass == 0 ? 1 : stride, flen, lvl, f->lf_sharpness, f->bit_depth);
-}
-
 namespace {
 __constant__ const int8_t dv_cdef_dir[8][2][2] = {{{-1, 1}, {-2, 2}}, {{0, 1}, {-1, 2}}, {{0, 1}, {0, 2}}, {{0, 1}, {1, 2}},
                                                   {{1, 1}, {2, 2}},   {{1, 0}, {2, 1}},  {{1, 0}, {2, 0}}, {{1, 0}, {2, -1}}};
@@ -166,10 +138,12 @@ __device__ void cdef_direction(const uint16_t *img, int stride, int bd, int *dir
 // CDEF output of one pixel of a non-skip 8x8 block for strength pair (pri, sec) (AV1 spec 7.15.2), read from a
 // staged (64 + 4)^2 tile of the superblock (kCdefTW samples per row, 2-sample border, kCdefNA marks
 // samples outside the frame): lx, ly = position inside the superblock.
-constexpr int kCdefTW = 68;
+constexpr int kFH = 7;                   // halo of the staged region: the deblocking filters reach 7 samples past an edge
+constexpr int kFW = 64 + 2 * kFH;        // staged rows / columns
+constexpr int kCdefTW = 80;              // row stride of the staged region in shared memory
 constexpr uint16_t kCdefNA = 0xFFFF;
 __device__ __forceinline__ int cdef_pixel_tile(const uint16_t *T, int lx, int ly, int pri, int sec, int dir, int damping, int cshift) {
-  const uint16_t *c = T + (ly + 2) * kCdefTW + lx + 2;
+  const uint16_t *c = T + (ly + kFH) * kCdefTW + lx + kFH;
   const int x = *c;
   if (!pri && !sec) return x;
   const int pt0 = ((pri >> cshift) & 1) ? 3 : 4, pt1 = ((pri >> cshift) & 1) ? 3 : 2;
@@ -284,7 +258,8 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
   const int stride = job.stride, W = f->width, H = f->height, bd = f->bit_depth;
   const int y0 = max(ur * 64 - 8, 0), y1 = ur == nur - 1 ? H : ur * 64 + 56;
   const int x0 = uc * 64, x1 = uc == nuc - 1 ? W : uc * 64 + 64, w = x1 - x0;
-  const PIX *deb = (const PIX *)job.rec[plane], *cdef = (const PIX *)job.fin[plane], *src = (const PIX *)job.src[plane];
+  // deb: the deblocked rows 54..57 of every superblock row kept by the fused kernel (the only ones read: spec 7.17.6)
+  const PIX *deb = (const PIX *)job.dbrows[plane], *cdef = (const PIX *)job.fin[plane], *src = (const PIX *)job.src[plane];
   PIX *lr_out = (PIX *)job.lr_out[plane];
   const int tid = threadIdx.x;
   for (int i = tid; i < B200_LR_CANDIDATES * 6; i += 256) sh.acc[i / 6][i % 6] = 0;
@@ -303,8 +278,8 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
         int y = ys + sy - 3, x = x0 + sx - 3;
         x = min(max(x, 0), W - 1); y = min(max(y, 0), H - 1);
         uint16_t v;
-        if (y < s_start) v = deb[max(y, s_start - 2) * stride + x];
-        else if (y > s_end) v = deb[min(y, s_end + 2) * stride + x];
+        if (y < s_start) v = deb[(size_t)db_row_slot(max(y, s_start - 2)) * stride + x];
+        else if (y > s_end) v = deb[(size_t)db_row_slot(min(y, s_end + 2)) * stride + x];
         else v = cdef[y * stride + x];
         sh.S[sy * kLrSW + sx] = v;
       }
@@ -457,10 +432,21 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
   }
 }
 
-// One CTA (256 threads) per 64x64 superblock; grid.y = job.  Phase 1: direction/variance of the 64 8x8 blocks.
-// Phase 2: squared error of every strength index.  Phase 3: apply the winner into job.fin (if present).
+// ---- fused deblocking + CDEF: one CTA (256 threads) per 64x64 superblock, all planes; grid.y = job -------------------
+// The reconstruction of the superblock and a 7-sample halo is staged ONCE in shared memory; both deblocking passes
+// (vertical edges, then horizontal edges: AV1 spec 7.14) run on the staged copy - redundantly on the halo, so that the
+// superblock plus the 2-sample border CDEF reads hold the final deblocked samples without any exchange between CTAs -
+// then the CDEF direction search, the strength search against the source and the winning filter run on the same copy
+// (spec 7.15).  The frame is read once (reconstruction, source) and written once (CDEF output); of the deblocked frame
+// only the four rows per superblock row that loop restoration reads across stripe boundaries (spec 7.17.6) are kept
+// (job.dbrows).  Why 7: an edge filter modifies at most 6 samples on either side and reads 7; edges of one pass never
+// overlap (the filter length is bounded by the smaller transform on either side), so a sample of the inner region
+// depends on the edges within 6 samples of it and on 7 samples beyond those edges at most.
+// Phase 1: stage + deblock.  Phase 2: direction / variance of the 64 8x8 blocks.  Phase 3: squared error of every
+// strength index.  Phase 4: apply the winner into job.fin (if present).
+
 template <class PIX>
-__global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) {
+__global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs) {
   const B200RdoJob &job = jobs[blockIdx.y];
   const B200Frame *f = &job.frame;
   const int nsb = f->sb_rows * f->sb_cols;
@@ -468,34 +454,78 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
   const int sbr = blockIdx.x / f->sb_cols, sbc = blockIdx.x % f->sb_cols;
   const int stride = job.stride, W = f->mi_cols * 4, H = f->mi_rows * 4, bd = f->bit_depth, cshift = bd - 8;
   const int tid = threadIdx.x;
+  const int x0 = sbc * 64, y0 = sbr * 64;
   __shared__ int s_dir[64], s_var[64], s_skip[64], s_any;
   __shared__ unsigned long long s_sse[8];
   __shared__ int s_best;
-  __shared__ uint16_t s_px[3][kCdefTW * kCdefTW];     // deblocked samples of the superblock + 2-sample border, per plane
+  __shared__ uint16_t s_px[3][kFW * kCdefTW];     // staged samples: rows y0-7 .. y0+70, columns x0-7 .. x0+70 (kCdefNA outside the frame)
+  __shared__ uint8_t s_txs[20 * 20];              // tx_size of the 4x4 units (sbr*16 - 2 .. +17) x (sbc*16 - 2 .. +17)
   if (tid == 0) s_any = 0;
   if (tid < 8) s_sse[tid] = 0;
-  for (int p = 0; p < f->planes; p++)
-    for (int i = tid; i < kCdefTW * kCdefTW; i += 256) {
-      const int yy = sbr * 64 + i / kCdefTW - 2, xx = sbc * 64 + i % kCdefTW - 2;
-      s_px[p][i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (uint16_t)((const PIX *)job.rec[p])[yy * stride + xx] : kCdefNA;
+  for (int p = 0; p < f->planes; p++) {
+    const PIX *R = (const PIX *)job.rec[p];
+    for (int i = tid; i < kFW * kFW; i += 256) {
+      const int ty = i / kFW, tx = i % kFW;
+      const int yy = y0 - kFH + ty, xx = x0 - kFH + tx;
+      s_px[p][ty * kCdefTW + tx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (uint16_t)R[(size_t)yy * stride + xx] : kCdefNA;
     }
+  }
+  for (int i = tid; i < 400; i += 256) {
+    const int r = sbr * 16 - 2 + i / 20, c = sbc * 16 - 2 + i % 20;
+    s_txs[i] = (r >= 0 && r < f->mi_rows && c >= 0 && c < f->mi_cols) ? job.mi[r * f->mi_cols + c].tx_size : 0;
+  }
   __syncthreads();
+#define TXS_AT(r, c) s_txs[((r) - (sbr * 16 - 2)) * 20 + ((c) - (sbc * 16 - 2))]
+  // ---- deblocking: pass 0 = vertical edges x0 + 4k (k = 0..16) on every staged row, pass 1 = horizontal edges y0 + 4k on
+  // the columns x0-2 .. x0+65.  Same edge rules as the frame-level filter of the oracle (orc_deblock_frame).
+  for (int pass = 0; pass < 2; pass++) {
+    const int span = pass == 0 ? kFW : 68;
+    for (int i = tid; i < f->planes * 17 * span; i += 256) {
+      const int plane = i / (17 * span), k = (i / span) % 17, j = i % span;
+      const int lvl = plane == 0 ? f->lf_level[pass] : f->lf_level[plane + 1];
+      if (!lvl) continue;
+      int x, y;
+      if (pass == 0) { x = x0 + 4 * k; y = y0 - kFH + j; } else { x = x0 - 2 + j; y = y0 + 4 * k; }
+      if (x < 0 || y < 0 || (x & ~3) >= f->width || (y & ~3) >= f->height) continue;     // 4x4 units that start inside the visible frame
+      const int r = y >> 2, c = x >> 2;
+      if (pass == 0 ? c == 0 : r == 0) continue;
+      const int tx = 4 << TXS_AT(r, c);
+      if (pass == 0 ? (x & (tx - 1)) : (y & (tx - 1))) continue;
+      const int ptx = 4 << (pass == 0 ? TXS_AT(r, c - 1) : TXS_AT(r - 1, c));
+      const int base = min(tx, ptx);
+      int flen = plane == 0 ? min(base, 16) : min(base, 8);
+      if (plane > 0 && flen == 8) flen = 6;
+      deblock_sample<uint16_t>(&s_px[plane][(y - (y0 - kFH)) * kCdefTW + (x - (x0 - kFH))], pass == 0 ? 1 : kCdefTW, flen, lvl, f->lf_sharpness, bd);
+    }
+    __syncthreads();
+  }
+#undef TXS_AT
+  // ---- keep what later stages read of the deblocked frame: rows 54..57 of the superblock (stripe boundaries of the loop
+  // restoration), and the whole superblock when a full plane was asked for (test seam)
+  for (int p = 0; p < f->planes; p++) {
+    PIX *DR = (PIX *)job.dbrows[p], *DF = (PIX *)job.deb_full[p];
+    if (DR)
+      for (int i = tid; i < 4 * 64; i += 256) {
+        const int ly = 54 + (i >> 6), lx = i & 63;
+        if (y0 + ly < H && x0 + lx < W) DR[(size_t)db_row_slot(y0 + ly) * stride + x0 + lx] = (PIX)s_px[p][(ly + kFH) * kCdefTW + lx + kFH];
+      }
+    if (DF)
+      for (int i = tid; i < 4096; i += 256) {
+        const int ly = i >> 6, lx = i & 63;
+        if (y0 + ly < H && x0 + lx < W) DF[(size_t)(y0 + ly) * stride + x0 + lx] = (PIX)s_px[p][(ly + kFH) * kCdefTW + lx + kFH];
+      }
+  }
   if (tid < 64) {
     const int r = sbr * 16 + (tid >> 3) * 2, c = sbc * 16 + (tid & 7) * 2;
     int skip = 1;
     if (r < f->mi_rows && c < f->mi_cols) {
       const B200Mi *m = &job.mi[r * f->mi_cols + c];
       skip = (m[0].flags & 1) && (m[1].flags & 1) && (m[f->mi_cols].flags & 1) && (m[f->mi_cols + 1].flags & 1);
-      if (!skip) { cdef_direction(&s_px[0][((tid >> 3) * 8 + 2) * kCdefTW + (tid & 7) * 8 + 2], kCdefTW, bd, &s_dir[tid], &s_var[tid]); s_any = 1; }
+      if (!skip) cdef_direction(&s_px[0][((tid >> 3) * 8 + kFH) * kCdefTW + (tid & 7) * 8 + kFH], kCdefTW, bd, &s_dir[tid], &s_var[tid]);
     }
     s_skip[tid] = skip;
   }
-  __syncthreads();
-  // "any non-skip 4x4" (oracle) == "any non-skip 8x8 group": a group is skipped only if all four units are
-  // skipped; but the oracle counts single units.  Recompute exactly:
-  if (tid == 0) s_any = 0;
-  __syncthreads();
-  {
+  {   // any non-skip 4x4 unit in the superblock (oracle)
     const int r = sbr * 16 + (tid >> 4), c = sbc * 16 + (tid & 15);
     if (r < f->mi_rows && c < f->mi_cols && !(job.mi[r * f->mi_cols + c].flags & 1)) s_any = 1;
   }
@@ -505,8 +535,8 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
     if (job.fin[0])
       for (int p = 0; p < f->planes; p++)
         for (int i = tid; i < 4096; i += 256) {
-          const int y0 = sbr * 64 + (i >> 6), x0 = sbc * 64 + (i & 63);
-          if (y0 < H && x0 < W) ((PIX *)job.fin[p])[y0 * stride + x0] = ((const PIX *)job.rec[p])[y0 * stride + x0];
+          const int ly = i >> 6, lx = i & 63;
+          if (y0 + ly < H && x0 + lx < W) ((PIX *)job.fin[p])[(size_t)(y0 + ly) * stride + x0 + lx] = (PIX)s_px[p][(ly + kFH) * kCdefTW + lx + kFH];
         }
     return;
   }
@@ -527,11 +557,11 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
       const PIX *S = (const PIX *)job.src[p];
       for (int i = tid; i < 4096; i += 256) {
         const int ly = i >> 6, lx = i & 63;
-        const int y0 = sbr * 64 + ly, x0 = sbc * 64 + lx;
-        if (y0 >= H || x0 >= W) continue;
+        const int yy = y0 + ly, xx = x0 + lx;
+        if (yy >= H || xx >= W) continue;
         const int b = (ly >> 3) * 8 + (lx >> 3);
         int v;
-        if (s_skip[b]) v = T[(ly + 2) * kCdefTW + lx + 2];
+        if (s_skip[b]) v = T[(ly + kFH) * kCdefTW + lx + kFH];
         else {
           int pri = pri0;
           const int dir = pri == 0 ? 0 : s_dir[b];
@@ -541,10 +571,10 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
             pri = var ? (pri * (4 + ii) + 8) >> 4 : 0;
           }
           v = cdef_pixel_tile(T, lx, ly, pri, sec, dir, damping, cshift);
-          const int d = v - (int)S[y0 * stride + x0];
+          const int d = v - (int)S[(size_t)yy * stride + xx];
           sse += (unsigned long long)(d * d);
         }
-        if (apply) ((PIX *)job.fin[p])[y0 * stride + x0] = (PIX)v;
+        if (apply) ((PIX *)job.fin[p])[(size_t)yy * stride + xx] = (PIX)v;
       }
     }
     if (!apply) {
@@ -564,36 +594,28 @@ __global__ void __launch_bounds__(256) b200_cdef_kernel(const B200RdoJob *jobs) 
 }
 
 #ifndef B200_EMU
-extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, int with_lr, int high_bitdepth, void *stream, int *launched) {
+extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_sb, int with_lr, int high_bitdepth, void *stream, int *launched) {
   if (launched) *launched = 0;
   if (n_jobs <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 g1((max_edge_threads + 255) / 256, n_jobs);
   dim3 g2(max_sb, n_jobs), g3(max_sb, n_jobs, 3);       // restoration units <= superblocks
   if (high_bitdepth) {
-    b200_deblock_kernel<uint16_t><<<g1, 256, 0, st>>>(d_jobs, 0);
-    b200_deblock_kernel<uint16_t><<<g1, 256, 0, st>>>(d_jobs, 1);
-    b200_cdef_kernel<uint16_t><<<g2, 256, 0, st>>>(d_jobs);
+    b200_dbcdef_kernel<uint16_t><<<g2, 256, 0, st>>>(d_jobs);
     if (with_lr) b200_lr_kernel<uint16_t><<<g3, 256, 0, st>>>(d_jobs);
   } else {
-    b200_deblock_kernel<uint8_t><<<g1, 256, 0, st>>>(d_jobs, 0);
-    b200_deblock_kernel<uint8_t><<<g1, 256, 0, st>>>(d_jobs, 1);
-    b200_cdef_kernel<uint8_t><<<g2, 256, 0, st>>>(d_jobs);
+    b200_dbcdef_kernel<uint8_t><<<g2, 256, 0, st>>>(d_jobs);
     if (with_lr) b200_lr_kernel<uint8_t><<<g3, 256, 0, st>>>(d_jobs);
   }
-  if (launched) *launched = 3 + (with_lr ? 1 : 0);
+  if (launched) *launched = 1 + (with_lr ? 1 : 0);
   return (int)cudaGetLastError();
 }
 #else
 static const B200RdoJob *g_f_jobs;
-static int g_f_pass;
 static bool emu_hbd() { return g_f_jobs[0].frame.bit_depth > 8; }
-static void emu_deblock_entry(void *) { if (emu_hbd()) b200_deblock_kernel<uint16_t>(g_f_jobs, g_f_pass); else b200_deblock_kernel<uint8_t>(g_f_jobs, g_f_pass); }
-static void emu_cdef_entry(void *) { if (emu_hbd()) b200_cdef_kernel<uint16_t>(g_f_jobs); else b200_cdef_kernel<uint8_t>(g_f_jobs); }
+static void emu_cdef_entry(void *) { if (emu_hbd()) b200_dbcdef_kernel<uint16_t>(g_f_jobs); else b200_dbcdef_kernel<uint8_t>(g_f_jobs); }
 static void emu_lr_entry(void *) { if (emu_hbd()) b200_lr_kernel<uint16_t>(g_f_jobs); else b200_lr_kernel<uint8_t>(g_f_jobs); }
-extern "C" int b200_filters_launch_emu(const B200RdoJob *jobs, int max_edge_threads, int max_sb) {
+extern "C" int b200_filters_launch_emu(const B200RdoJob *jobs, int max_sb) {
   g_f_jobs = jobs;
-  for (g_f_pass = 0; g_f_pass < 2; g_f_pass++) emu::launch(emu_deblock_entry, nullptr, (unsigned)((max_edge_threads + 255) / 256), 256);
   emu::launch(emu_cdef_entry, nullptr, (unsigned)max_sb, 256);
   for (g_f_plane = 0; g_f_plane < jobs[0].frame.planes; g_f_plane++)
     if (jobs[0].frame.lr_type[g_f_plane]) emu::launch(emu_lr_entry, nullptr, (unsigned)max_sb, 256);

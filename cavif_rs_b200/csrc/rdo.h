@@ -25,10 +25,12 @@ typedef struct B200RdoJob {
   uint32_t *stream_len[3];
   B200BlockDec *dec[B200_LEVELS];   // analysis decisions per level (0: 4x4 .. 3: 32x32), b200_level_rows*cols entries
   uint32_t *satd[B200_LEVELS];      // luma SATD tables per level: [block][14 words]
-  // in-loop filter stage (filters.cu): rec is deblocked IN PLACE; cdef_idx receives the per-superblock
+  // in-loop filter stage (filters.cu): rec is read only (deblocking happens on a staged copy); cdef_idx receives the per-superblock
   // strength index (-1: nothing coded in the superblock); fin (optional, may be NULL) receives the CDEF output.
   int8_t *cdef_idx;       // sb_rows*sb_cols
   void *fin[3];
+  void *dbrows[3];        // deblocked rows 54..57 of every superblock row (4 * sb_rows rows of `stride` samples): loop restoration input
+  void *deb_full[3];      // optional (tests): the whole deblocked planes
   // loop restoration (frame.lr_type[p] != 0; needs fin): per-unit decisions, and (optional, tests) the restored planes
   B200LrUnit *lr[3];      // b200_lr_units(height) * b200_lr_units(width) per plane
   void *lr_out[3];
@@ -50,8 +52,8 @@ int b200_recon_launch(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int 
 size_t b200_recon_smem_bytes(int high_bitdepth, int top_level, int rows);
 typedef struct B200StreamRegionH { const int16_t *src; const uint32_t *len; } B200StreamRegionH;   // device pointers
 int b200_stream_gather_launch(const void *d_regions, int n_regions, uint32_t *d_offsets /* n + 1 */, int16_t *out, uint32_t capacity, void *stream);
-// Deblock (2 launches) + CDEF search (1 launch) + loop-restoration search (1 launch when with_lr) for all jobs: grid.y = job.
-int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_edge_threads, int max_sb, int with_lr, int high_bitdepth, void *stream, int *launched);
+// Fused deblocking + CDEF search (1 launch) + loop-restoration search (1 launch when with_lr) for all jobs: grid.y = job.
+int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_sb, int with_lr, int high_bitdepth, void *stream, int *launched);
 
 #ifdef __cplusplus
 }

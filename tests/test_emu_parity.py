@@ -12,7 +12,7 @@ class RdoJob(ctypes.Structure):
                 ("src", ctypes.c_void_p * 3), ("rec", ctypes.c_void_p * 3),
                 ("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3), ("stream_len", ctypes.c_void_p * 3),
                 ("dec", ctypes.c_void_p * H.LEVELS), ("satd", ctypes.c_void_p * H.LEVELS),
-                ("cdef_idx", ctypes.c_void_p), ("fin", ctypes.c_void_p * 3),
+                ("cdef_idx", ctypes.c_void_p), ("fin", ctypes.c_void_p * 3), ("dbrows", ctypes.c_void_p * 3), ("deb_full", ctypes.c_void_p * 3),
                 ("lr", ctypes.c_void_p * 3), ("lr_out", ctypes.c_void_p * 3)]
 
 
@@ -113,7 +113,7 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw, rows):
     for p in range(3):
         job.lr[p] = out.lr[p].ctypes.data; job.lr_out[p] = lr_out[p].ctypes.data
     E.b200_rdo_launch_emu.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
-    E.b200_filters_launch_emu.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    E.b200_filters_launch_emu.argtypes = [ctypes.c_void_p, ctypes.c_int]
     E.b200_rdo_launch_emu(ctypes.byref(job), trs, nt, rows)
     compare_analysis(ref, out, f)
     # the reconstruction chain emits compact level streams: expand them to the dense per-block layout of the oracle
@@ -124,11 +124,15 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw, rows):
     compare(ref, out, planes)
     # in-loop filter stage: deblock in place, CDEF strength search, CDEF output
     ref_fin, ref_deb = H.oracle_filters(f, ref, src)
-    E.b200_filters_launch_emu(ctypes.byref(job), f.mi_rows * f.mi_cols * 4 * planes, f.sb_rows * f.sb_cols)
+    deb = [np.zeros_like(r) for r in out.rec]
+    dbrows = [np.zeros((f.sb_rows * 4, f.mi_cols * 4), pix) for _ in range(3)]
+    for p in range(3):
+        job.deb_full[p] = deb[p].ctypes.data; job.dbrows[p] = dbrows[p].ctypes.data
+    E.b200_filters_launch_emu(ctypes.byref(job), f.sb_rows * f.sb_cols)
     uses_lr = any(f.lr_type[p] for p in range(planes))
     ref_cdef = ref.cdef_out if uses_lr else ref_fin
     for p in range(planes):
-        assert np.array_equal(out.rec[p], ref_deb[p]), "deblocked plane %d" % p
+        assert np.array_equal(deb[p], ref_deb[p]), "deblocked plane %d" % p
         assert np.array_equal(fin[p], ref_cdef[p]), "CDEF output plane %d" % p
     assert np.array_equal(out.cdef_idx, ref.cdef_idx), "cdef index"
     if uses_lr:
