@@ -20,6 +20,14 @@ $(LIB): $(CU) $(CPP) $(HDR)
 $(ORACLE): $(OSRC) $(HDR) $(wildcard oracle/*.h)
 	gcc -O2 -ffp-contract=off -Wall -Wno-missing-braces -Wno-unused-function -Wno-misleading-indentation -shared -fPIC -o $@ $(OSRC) -lm
 
+# CPU-baseline build of the oracle for the machine it runs on (bench.py builds it ON the box: -march=native code must not
+# travel between hosts); same sources, same results, -O3.
+ORACLE_NATIVE := oracle/_native/liboracle_native.so
+oracle-native: $(ORACLE_NATIVE)
+$(ORACLE_NATIVE): $(OSRC) $(HDR) $(wildcard oracle/*.h)
+	mkdir -p oracle/_native
+	gcc -O3 -march=native -ffp-contract=off -Wall -Wno-missing-braces -Wno-unused-function -Wno-misleading-indentation -Wno-maybe-uninitialized -shared -fPIC -o $@ $(OSRC) -lm
+
 clean:
 	rm -f $(LIB) $(ORACLE)
-.PHONY: all lib oracle clean
+.PHONY: all lib oracle oracle-native clean

@@ -6,8 +6,8 @@ kernels inside cavif_rs_b200/libcavif_b200.so; there is no CPU fallback.
 """
 from .encoder import (Encoder, EncodedImage, ColorModel, AlphaColorMode, BitDepth, PixelRange, MatrixCoefficients,
                       Error, TooFewPixels, Unsupported, EncodingError, lib, build, stats, device_count,
-                      quality_to_quantizer, default_num_threads, shutdown)
+                      quality_to_quantizer, default_num_threads, shutdown, set_profiling, stage_times)
 
 __all__ = ["Encoder", "EncodedImage", "ColorModel", "AlphaColorMode", "BitDepth", "PixelRange", "MatrixCoefficients",
            "Error", "TooFewPixels", "Unsupported", "EncodingError", "lib", "build", "stats", "device_count",
-           "quality_to_quantizer", "default_num_threads", "shutdown"]
+           "quality_to_quantizer", "default_num_threads", "shutdown", "set_profiling", "stage_times"]

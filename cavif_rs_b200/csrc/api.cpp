@@ -119,6 +119,10 @@ struct Context {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_analysis = nullptr;  // stages A + B of the current chunk are done
   std::map<int, B200RateTables *> d_rate;   // per base_q_idx
+  struct Mark { const char *name; cudaStream_t stream; cudaEvent_t ev; };
+  std::vector<Mark> marks;                  // this issue's marks, resolved by finish_rdo()
+  std::vector<cudaEvent_t> mark_pool;
+  size_t mark_used = 0;
   const uint32_t *stream_total = nullptr;   // last issue_rdo(): total levels gathered (pinned, valid after the streams are drained)
   size_t stream_capacity = 0;
   // Queued work is drained before anything is freed.  Contexts are destroyed by b200avif_shutdown() or when a call
@@ -132,6 +136,7 @@ struct Context {
     for (auto &kv : d_rate) cudaFree(kv.second);
     dev.release(); pin.release();
     for (auto &e : ev) if (e) cudaEventDestroy(e);
+    for (auto &e : mark_pool) cudaEventDestroy(e);
     if (ev_analysis) cudaEventDestroy(ev_analysis);
     if (stream) cudaStreamDestroy(stream);
     if (stream_hi) cudaStreamDestroy(stream_hi);
@@ -139,6 +144,11 @@ struct Context {
   }
 };
 std::mutex g_ctx_mu;
+// ---- per-kernel timing (b200avif_set_profiling): CUDA events between the kernels of a stream -----------------------
+std::atomic<int> g_profiling{0};
+struct StageStat { double ms = 0; uint64_t launches = 0; };
+std::map<std::string, StageStat> g_stage;      // guarded by g_stat_mu
+thread_local Context *tl_mark_ctx = nullptr;   // the context whose work the calling thread is issuing
 std::vector<std::unique_ptr<Context>> g_ctx_free;
 
 int acquire_context(int device, std::unique_ptr<Context> &out) {
@@ -298,8 +308,18 @@ int configure_frame(B200Frame *f, size_t w, size_t h, int depth, bool mono, int 
   return 0;
 }
 
+// Rate tables installed from device memory (b200avif_install_rate_tables: the multi-GPU driver broadcasts rank 0's tables
+// over NCCL and every rank installs its received copy), per (device, base_q_idx).  Owned by the library.
+std::mutex g_installed_mu;
+std::map<std::pair<int, int>, B200RateTables *> g_installed_rate;
+
 // Upload (cached) rate tables for this frame's quantiser.
 int rate_tables_for(Context &c, int qidx, B200RateTables **out) {
+  {
+    std::lock_guard<std::mutex> lk(g_installed_mu);
+    auto gi = g_installed_rate.find(std::make_pair(c.device, qidx));
+    if (gi != g_installed_rate.end()) { *out = gi->second; return 0; }
+  }
   auto it = c.d_rate.find(qidx);
   if (it != c.d_rate.end()) { *out = it->second; return 0; }
   B200RateTables host;
@@ -325,6 +345,7 @@ int rate_tables_for(Context &c, int qidx, B200RateTables **out) {
 int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin, bool fetch_rec,
               std::vector<std::vector<uint8_t>> *rec_out, std::vector<std::vector<uint8_t>> *pre_filter_rec = nullptr,
               cudaEvent_t after_analysis_of = nullptr) {
+  struct MarkScope { MarkScope(Context *c) { tl_mark_ctx = c; c->marks.clear(); c->mark_used = 0; } ~MarkScope() { tl_mark_ctx = nullptr; } } mark_scope(&c);
   std::vector<B200RdoJob> hj(jobs.size());
   std::vector<B200TileRef> tiles;
   for (size_t i = 0; i < jobs.size(); i++) {
@@ -400,6 +421,7 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     for (FrameJob *jp : jobs) max_sb = std::max(max_sb, (int)jp->n_sb());
     int with_lr = 0;
     for (FrameJob *jp : jobs) with_lr |= jp->uses_lr();
+    b200_mark(nullptr, c.stream_hi);
     const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_sb, with_lr, jobs[0]->f.bit_depth > 8, c.stream_hi, &n_launched);
     if (fe != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("filter kernel launch failed: ") + cudaGetErrorString((cudaError_t)fe));
     g_launches += (uint64_t)n_launched;
@@ -474,6 +496,19 @@ int finish_rdo(Context &c) {
     if (*c.stream_total > c.stream_capacity) return fail(B200AVIF_ENCODING_ERROR, "internal error: level stream larger than its buffer");
     g_d2h += (uint64_t)*c.stream_total * 2;
     c.stream_total = nullptr;
+  }
+  if (!c.marks.empty()) {       // time between consecutive marks of a stream -> the kernel launched in between
+    std::map<cudaStream_t, cudaEvent_t> last;
+    std::lock_guard<std::mutex> lk(g_stat_mu);
+    for (const Context::Mark &m : c.marks) {
+      auto it = last.find(m.stream);
+      if (m.name && it != last.end()) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, it->second, m.ev) == cudaSuccess) { StageStat &st = g_stage[m.name]; st.ms += ms; st.launches++; }
+      }
+      last[m.stream] = m.ev;
+    }
+    c.marks.clear();
   }
   float ms_rdo = 0, ms_tot = 0;
   cudaEventElapsedTime(&ms_rdo, c.ev[1], c.ev[2]);
@@ -863,6 +898,53 @@ int b200avif_device_count(void) {
   return n;
 }
 size_t b200avif_default_num_threads(void) { return b200_host_threads(); }
+void b200_mark(const char *name, void *stream) {
+  Context *c = tl_mark_ctx;
+  if (!c || !g_profiling.load(std::memory_order_relaxed)) return;
+  if (c->mark_used == c->mark_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    c->mark_pool.push_back(e);
+  }
+  cudaEvent_t e = c->mark_pool[c->mark_used++];
+  if (cudaEventRecord(e, (cudaStream_t)stream) != cudaSuccess) return;
+  c->marks.push_back(Context::Mark{name, (cudaStream_t)stream, e});
+}
+size_t b200avif_rate_tables_bytes(void) { return sizeof(B200RateTables); }
+int b200avif_build_rate_tables(int base_q_idx, void *host_out) {
+  if (!host_out || base_q_idx < 1 || base_q_idx > 255) return fail(B200AVIF_INVALID_ARGUMENT, "bad argument");
+  b200av1_build_rate_tables(base_q_idx, (B200RateTables *)host_out);
+  return 0;
+}
+int b200avif_install_rate_tables(int device, int base_q_idx, const void *device_tables, size_t bytes) {
+  if (!device_tables || bytes != sizeof(B200RateTables) || base_q_idx < 1 || base_q_idx > 255) return fail(B200AVIF_INVALID_ARGUMENT, "bad argument");
+  int cur = 0;
+  if (device < 0) { CU(cudaGetDevice(&cur)); device = cur; }
+  CU(cudaSetDevice(device));
+  B200RateTables *d = nullptr;
+  CU(cudaMalloc((void **)&d, sizeof(B200RateTables)));
+  CU(cudaMemcpy(d, device_tables, sizeof(B200RateTables), cudaMemcpyDeviceToDevice));
+  CU(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_installed_mu);
+  auto key = std::make_pair(device, base_q_idx);
+  auto it = g_installed_rate.find(key);
+  if (it != g_installed_rate.end()) { cudaFree(it->second); it->second = d; } else g_installed_rate[key] = d;
+  return 0;
+}
+void b200avif_set_profiling(int on) { g_profiling.store(on ? 1 : 0); }
+size_t b200avif_get_stage_times(b200avif_stage_time *out, size_t cap) {
+  std::lock_guard<std::mutex> lk(g_stat_mu);
+  size_t n = 0;
+  for (const auto &kv : g_stage) {
+    if (out && n < cap) {
+      memset(&out[n], 0, sizeof(out[n]));
+      strncpy(out[n].name, kv.first.c_str(), sizeof(out[n].name) - 1);
+      out[n].ms = kv.second.ms; out[n].launches = kv.second.launches;
+    }
+    n++;
+  }
+  return n;
+}
 // Release every pooled context (streams, events, arenas, cached rate tables).  Safe to call at any quiet point; the next
 // encode call rebuilds what it needs.  Not registered with atexit(): the CUDA runtime may be torn down first.
 void b200avif_shutdown(void) {

@@ -16,6 +16,11 @@
 
 #include "records.h"
 #include "rdo.h"
+#ifdef B200_EMU
+#define B200_MARK(name, st) ((void)0)
+#else
+#define B200_MARK(name, st) b200_mark(name, (void *)(st))
+#endif
 
 #define AV1_TABLE(type, name, dims) __constant__ const type name dims
 #include "av1_tables_dev.h"

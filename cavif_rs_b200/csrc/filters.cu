@@ -14,6 +14,11 @@
 
 #include "records.h"
 #include "rdo.h"
+#ifdef B200_EMU
+#define B200_MARK_F(name, st) ((void)0)
+#else
+#define B200_MARK_F(name, st) b200_mark(name, (void *)(st))
+#endif
 
 #define AV1_TABLE(type, name, dims) __constant__ const type name dims
 #include "sgr_tables_dev.h"
@@ -601,10 +606,12 @@ extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max
   dim3 g2(max_sb, n_jobs), g3(max_sb, n_jobs, 3);       // restoration units <= superblocks
   if (high_bitdepth) {
     b200_dbcdef_kernel<uint16_t><<<g2, 256, 0, st>>>(d_jobs);
-    if (with_lr) b200_lr_kernel<uint16_t><<<g3, 256, 0, st>>>(d_jobs);
+    B200_MARK_F("deblock_cdef", st);
+    if (with_lr) { b200_lr_kernel<uint16_t><<<g3, 256, 0, st>>>(d_jobs); B200_MARK_F("lr_search", st); }
   } else {
     b200_dbcdef_kernel<uint8_t><<<g2, 256, 0, st>>>(d_jobs);
-    if (with_lr) b200_lr_kernel<uint8_t><<<g3, 256, 0, st>>>(d_jobs);
+    B200_MARK_F("deblock_cdef", st);
+    if (with_lr) { b200_lr_kernel<uint8_t><<<g3, 256, 0, st>>>(d_jobs); B200_MARK_F("lr_search", st); }
   }
   if (launched) *launched = 1 + (with_lr ? 1 : 0);
   return (int)cudaGetLastError();

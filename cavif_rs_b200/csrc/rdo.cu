@@ -513,6 +513,7 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     configured = true;
   }
   const int top = top_level >= 3 ? 3 : 2;
+  B200_MARK(nullptr, st);
   for (int lv = top; lv >= 0; lv--) {   // large to small: every level is pruned by its parent level
     const int nblk = max_blocks4 >> (2 * lv);
     if (nblk == 0) continue;
@@ -521,11 +522,13 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
       dim3 gs((nblk + 127) / 128, n_jobs);
       if (high_bitdepth) b200_satd_direct_kernel<uint16_t><<<gs, 128, 0, st>>>(d_jobs, lv);
       else b200_satd_direct_kernel<uint8_t><<<gs, 128, 0, st>>>(d_jobs, lv);
+      B200_MARK(lv == 3 ? "satd_32x32" : "satd_16x16", st);
       n_launch++;
     } else {
       dim3 gs((nblk + kSatdItems - 1) / kSatdItems, n_jobs);
       if (high_bitdepth) b200_satd_kernel<uint16_t><<<gs, 128, 0, st>>>(d_jobs, lv, kSatdItems);
       else b200_satd_kernel<uint8_t><<<gs, 128, 0, st>>>(d_jobs, lv, kSatdItems);
+      B200_MARK(lv == 2 ? "satd_16x16" : (lv == 1 ? "satd_8x8" : "satd_4x4"), st);
       n_launch++;
     }
     // enough warps to fill the machine several times over, grid-stride inside
@@ -543,12 +546,14 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     } else if (lv == 2) B200_ANALYZE(2, 1, ga);
     else if (lv == 1) B200_ANALYZE(1, 1, ga);
     else B200_ANALYZE(0, 1, ga);
+    B200_MARK(lv == 3 ? "analyze_32x32" : (lv == 2 ? "analyze_16x16" : (lv == 1 ? "analyze_8x8" : "analyze_4x4")), st);
     n_launch++;
   }
   // one thread per ROOT REGION: ceil(W / rn) * ceil(H / rn) per job (larger than n_mi / 16 when the coded size is
   // 8 mod 16), computed by the caller over all jobs
   dim3 gd((max_regions + 127) / 128, n_jobs);
   b200_decide_kernel<<<gd, 128, 0, st>>>(d_jobs);
+  B200_MARK("decide", st);
   n_launch += 2;      // partition decision + the reconstruction chain below
   cudaStream_t sr = stream_recon ? (cudaStream_t)stream_recon : st;
   if (analysis_done) {
@@ -556,7 +561,9 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     if (sr != st) cudaStreamWaitEvent(sr, (cudaEvent_t)analysis_done, 0);
   }
   {
+    B200_MARK(nullptr, sr);
     const int re = b200_recon_launch(d_jobs, d_tiles, n_tiles, high_bitdepth, top, recon_rows, sr);
+    B200_MARK("recon_chain", sr);
     if (re) return re;
   }
   if (launched) *launched = n_launch;

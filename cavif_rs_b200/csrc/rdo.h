@@ -47,6 +47,10 @@ typedef struct B200TileRef {
 int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200TileRef *d_tiles, int n_tiles, int max_blocks4,
                     int max_regions /* largest root-region count (ceil(W/rn) * ceil(H/rn), rn = 16 or 32) over the jobs */, int high_bitdepth, int top_level /* 2: 16x16, 3: 32x32 */, int recon_rows /* superblock-row slots per tile: 1, 2, 4 */, void *stream, void *stream_recon, void *analysis_done,
                     int *launched /* out, may be NULL: kernels launched by this call */);
+// Per-kernel timing hook (api.cpp): the launchers call it after every kernel; when profiling is on it records a CUDA event
+// on that stream, and the time between consecutive marks of a stream is accumulated under `name`
+// (b200avif_get_stage_times).  name == NULL opens an interval without closing one.
+void b200_mark(const char *name, void *stream);
 // recon.cu: the reconstruction chain (one CTA per tile) and the gather of the compact level streams
 int b200_recon_launch(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int n_tiles, int high_bitdepth, int top_level, int rows, void *stream);
 size_t b200_recon_smem_bytes(int high_bitdepth, int top_level, int rows);

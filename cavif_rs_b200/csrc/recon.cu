@@ -592,6 +592,7 @@ extern "C" int b200_stream_gather_launch(const void *d_regions, int n_regions, u
   cudaStream_t st = (cudaStream_t)stream;
   b200_stream_scan_kernel<<<1, 1024, 0, st>>>((const B200StreamRegion *)d_regions, n_regions, d_offsets);
   b200_stream_gather_kernel<<<n_regions, 256, 0, st>>>((const B200StreamRegion *)d_regions, d_offsets, out, capacity);
+  B200_MARK("stream_gather", st);
   return (int)cudaGetLastError();
 }
 #else

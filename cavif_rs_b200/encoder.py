@@ -80,6 +80,10 @@ class _Stats(ctypes.Structure):
                 ("gpu_ms_rdo", ctypes.c_double), ("gpu_ms_total", ctypes.c_double), ("host_ms_pack", ctypes.c_double)]
 
 
+class _StageTime(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 48), ("ms", ctypes.c_double), ("launches", ctypes.c_uint64)]
+
+
 class EncodedImage:
     """EncodedImage (av1encoder.rs:52-61)"""
     __slots__ = ("avif_file", "color_byte_size", "alpha_byte_size")
@@ -136,6 +140,12 @@ def lib():
         L.b200avif_quality_to_quantizer.restype = ctypes.c_uint8
         L.b200avif_quality_to_quantizer.argtypes = [ctypes.c_float]
         L.b200avif_get_stats.argtypes = [ctypes.POINTER(_Stats)]
+        L.b200avif_set_profiling.argtypes = [ctypes.c_int]
+        L.b200avif_get_stage_times.restype = ctypes.c_size_t
+        L.b200avif_get_stage_times.argtypes = [ctypes.POINTER(_StageTime), ctypes.c_size_t]
+        L.b200avif_rate_tables_bytes.restype = ctypes.c_size_t
+        L.b200avif_build_rate_tables.argtypes = [ctypes.c_int, ctypes.c_void_p]
+        L.b200avif_install_rate_tables.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
         _lib = L
     return _lib
 
@@ -156,6 +166,18 @@ def default_num_threads():
 def shutdown():
     """Release the pooled device contexts of this process."""
     lib().b200avif_shutdown()
+
+
+def set_profiling(on):
+    """Per-kernel CUDA-event timing on/off (stage_times())."""
+    lib().b200avif_set_profiling(1 if on else 0)
+
+
+def stage_times():
+    """{kernel stage: (accumulated ms between CUDA events on the launching stream, launches)} since process start."""
+    buf = (_StageTime * 64)()
+    n = lib().b200avif_get_stage_times(buf, 64)
+    return {buf[i].name.decode(): (buf[i].ms, buf[i].launches) for i in range(min(n, 64))}
 
 
 def stats():

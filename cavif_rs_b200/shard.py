@@ -31,3 +31,32 @@ def gather_stats(values, device=None):
     out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
     dist.all_gather(out, t)
     return [o.cpu().tolist() for o in out]
+
+
+def broadcast_and_install_rate_tables(qidxs, rank, device):
+    """The one collective of a multi-GPU batch (BASELINE.json north_star): rank 0 builds the quantiser / rate tables of every
+    base_q_idx the batch uses, ONE broadcast (NCCL over NVLink when `device` is a CUDA device) carries them to every rank,
+    and every rank installs the copy it received - straight from device memory - into the encoder
+    (b200avif_install_rate_tables), which then never builds tables of its own for those quantisers.
+    Returns the bytes broadcast."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from . import encoder
+    L = encoder.lib()
+    nb = L.b200avif_rate_tables_bytes()
+    host = torch.zeros(len(qidxs) * nb, dtype=torch.uint8)
+    if rank == 0:
+        for k, q in enumerate(qidxs):
+            buf = (ctypes.c_uint8 * nb)()
+            assert L.b200avif_build_rate_tables(int(q), buf) == 0
+            host[k * nb:(k + 1) * nb] = torch.frombuffer(buf, dtype=torch.uint8)
+    t = host.to(device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(t, src=0)
+    if t.is_cuda:
+        torch.cuda.synchronize(t.device)
+        for k, q in enumerate(qidxs):
+            rc = L.b200avif_install_rate_tables(t.device.index, int(q), ctypes.c_void_p(t.data_ptr() + k * nb), nb)
+            assert rc == 0, L.b200avif_last_error_message()
+    return t.numel()

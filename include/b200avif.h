@@ -139,6 +139,18 @@ typedef struct b200avif_stats {
   double host_ms_pack;          /* accumulated wall time of symbol packing + muxing */
 } b200avif_stats;
 void b200avif_get_stats(b200avif_stats *out);
+/* Per-kernel CUDA-event times (accumulated since process start while profiling is on): the time between consecutive
+ * events on the launching stream, i.e. the duration of the kernel launched in between. */
+typedef struct b200avif_stage_time { char name[48]; double ms; uint64_t launches; } b200avif_stage_time;
+void b200avif_set_profiling(int on);
+size_t b200avif_get_stage_times(b200avif_stage_time *out, size_t cap);   /* returns the number of stages */
+/* Multi-GPU batches (one process per GPU): the quantiser / rate tables of a batch are built ONCE (rank 0,
+ * b200avif_build_rate_tables into rate_tables_bytes() of host memory), broadcast over NCCL, and installed by every rank
+ * from the DEVICE buffer it received; encodes on that device with that base_q_idx then use the installed copy instead of
+ * building their own.  (BASELINE.json north_star: "NCCL only to broadcast quantizer tables".) */
+size_t b200avif_rate_tables_bytes(void);
+int b200avif_build_rate_tables(int base_q_idx, void *host_out);
+int b200avif_install_rate_tables(int cuda_device, int base_q_idx, const void *device_tables, size_t bytes);
 /* Releases the pooled device contexts (streams, arenas, cached rate tables) of this process. */
 void b200avif_shutdown(void);
 int b200avif_device_count(void);   /* 0 when no CUDA device is usable */

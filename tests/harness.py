@@ -58,8 +58,12 @@ def oracle():
     """gcc-built CPU restatement (oracle/)."""
     global _oracle
     if _oracle is None:
-        _run(["make", "-s", "oracle"])
-        L = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+        if os.environ.get("B200_ORACLE_NATIVE") == "1":      # bench.py CPU arm: -O3 -march=native build made on this host
+            _run(["make", "-s", "oracle-native"])
+            L = ctypes.CDLL(os.path.join(ROOT, "oracle", "_native", "liboracle_native.so"))
+        else:
+            _run(["make", "-s", "oracle"])
+            L = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
         V, I, Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
         # NB: without argtypes ctypes passes Python ints as 32-bit C ints and truncates pointers.
         L.orc_encode_frame.argtypes = [V, V, V, V, V, V, V, V, V]
