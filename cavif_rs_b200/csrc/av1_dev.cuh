@@ -65,7 +65,7 @@ struct SharedT {
   typedef PIX Pix;
   static constexpr int kMaxN = NMAX;
   static constexpr int kPredStride = NMAX * NMAX;          // one prediction slot (luma: two ranked modes, two slots)
-  PIX src[3][NMAX * NMAX];
+  alignas(16) PIX src[3][NMAX * NMAX];
   PIX above[3][EOFF + 2 * NMAX + 2], left[3][EOFF + 2 * NMAX + 2];
   PIX ef[2][EOFF + 2 * NMAX + 8];   // intra edge filter: filtered / upsampled private copy of one plane's edges
   PIX pred[2 * NMAX * NMAX];   // luma: predictions of the two ranked modes; chroma: up to G (mode rank, plane) predictions
@@ -706,6 +706,41 @@ __device__ __forceinline__ void ctx_from_job(const B200RdoJob &job, TileCtx &t) 
   for (int p = 0; p < 3; p++) { t.src[p] = job.src[p]; t.rec[p] = job.rec[p]; t.eob[p] = job.eob[p]; t.coef[p] = job.coef[p]; }
   t.mi = job.mi; t.stride = job.stride;
 }
+
+// ---- vectorised staging of a source block: global -> registers -> shared memory --------------------------------------
+// source block (n x n at frame position x, y) -> registers: one row segment of up to 16 bytes per lane
+template <class PIX>
+struct SrcRegs { uint4 v; };
+template <class PIX>
+__device__ __forceinline__ void src_fetch(const PIX *plane, int stride, int x, int y, int n, SrcRegs<PIX> &o, int half /*u16 n=32 second half etc.*/) {
+  // bytes per row = n * sizeof(PIX); segments of 16 bytes (or the whole row when shorter)
+  const int row_bytes = n * (int)sizeof(PIX), seg = row_bytes < 16 ? row_bytes : 16, segs_per_row = row_bytes / seg;
+  const int idx = lane_id() + 32 * half, r = idx / segs_per_row, s = idx % segs_per_row;
+  o.v = make_uint4(0, 0, 0, 0);
+  if (r >= n) return;
+  const char *p = reinterpret_cast<const char *>(plane + (size_t)(y + r) * stride + x) + s * seg;
+  if (seg == 16) {
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) o.v = *reinterpret_cast<const uint4 *>(p);
+    else { const uint2 a = *reinterpret_cast<const uint2 *>(p), b = *reinterpret_cast<const uint2 *>(p + 8); o.v = make_uint4(a.x, a.y, b.x, b.y); }
+  } else if (seg == 8) { const uint2 a = *reinterpret_cast<const uint2 *>(p); o.v.x = a.x; o.v.y = a.y; }
+  else o.v.x = *reinterpret_cast<const uint32_t *>(p);
+}
+template <class PIX>
+__device__ __forceinline__ void src_store(PIX *dst /* n x n row-major, 16-byte aligned */, int n, const SrcRegs<PIX> &o, int half) {
+  const int row_bytes = n * (int)sizeof(PIX), seg = row_bytes < 16 ? row_bytes : 16, segs_per_row = row_bytes / seg;
+  const int idx = lane_id() + 32 * half, r = idx / segs_per_row, s = idx % segs_per_row;
+  if (r >= n) return;
+  char *p = reinterpret_cast<char *>(dst) + r * row_bytes + s * seg;
+  if (seg == 16) *reinterpret_cast<uint4 *>(p) = o.v;
+  else if (seg == 8) *reinterpret_cast<uint2 *>(p) = make_uint2(o.v.x, o.v.y);
+  else *reinterpret_cast<uint32_t *>(p) = o.v.x;
+}
+// number of 32-lane fetch rounds a block of n x n samples needs
+template <class PIX> __device__ __forceinline__ int src_rounds(int n) {
+  const int row_bytes = n * (int)sizeof(PIX), seg = row_bytes < 16 ? row_bytes : 16;
+  return (n * (row_bytes / seg) + 31) / 32;
+}
+
 
 }  // namespace
 #endif  // B200_AV1_DEV_CUH_

@@ -176,6 +176,60 @@ __device__ __forceinline__ int cdef_pixel_tile(const uint16_t *T, int lx, int ly
     }
   return clip3_d(mn, mx, x + ((8 + sum - (sum < 0)) >> 4));
 }
+// The strength search evaluates several (primary, secondary) strength pairs on the SAME taps: the 4 primary and 8 secondary
+// tap samples of a pixel depend only on the block's direction.  They are loaded once; a tap outside the frame is replaced by
+// the centre sample (difference 0, no effect on the clipping range - the same as skipping it, spec 7.15.2).
+struct CdefTaps { int x, p[4], s[8]; };
+__device__ __forceinline__ void cdef_load_taps(const uint16_t *c, const int16_t *off /* [8][2]: dy * stride + dx */, int dir, CdefTaps &t) {
+  t.x = *c;
+  const int da = (dir - 2) & 7, db = (dir + 2) & 7;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int op = off[dir * 2 + k], oa = off[da * 2 + k], ob = off[db * 2 + k];
+    int v;
+    v = c[-op]; t.p[2 * k] = v == kCdefNA ? t.x : v;
+    v = c[op]; t.p[2 * k + 1] = v == kCdefNA ? t.x : v;
+    v = c[-oa]; t.s[4 * k] = v == kCdefNA ? t.x : v;
+    v = c[oa]; t.s[4 * k + 1] = v == kCdefNA ? t.x : v;
+    v = c[-ob]; t.s[4 * k + 2] = v == kCdefNA ? t.x : v;
+    v = c[ob]; t.s[4 * k + 3] = v == kCdefNA ? t.x : v;
+  }
+}
+__device__ __forceinline__ int constrain_adj(int diff, int threshold, int adj) {
+  const int mag = iabs_d(diff);
+  const int v = max(0, min(mag, threshold - (mag >> adj)));
+  return diff < 0 ? -v : v;
+}
+// one strength pair on loaded taps.  With only one of the two strengths the result provably stays inside the range of the
+// taps it used (total tap weight 12/16), so the spec's clip to [min, max] is the identity and is skipped.
+__device__ __forceinline__ int cdef_eval(const CdefTaps &t, int pri, int sec, int damping, int cshift) {
+  const int x = t.x;
+  if (!pri && !sec) return x;
+  int sum = 0;
+  if (pri) {
+    const int adj = max(0, damping - floor_log2_d((unsigned)pri));
+    const int w0 = ((pri >> cshift) & 1) ? 3 : 4, w1 = ((pri >> cshift) & 1) ? 3 : 2;
+    sum += w0 * (constrain_adj(t.p[0] - x, pri, adj) + constrain_adj(t.p[1] - x, pri, adj)) +
+           w1 * (constrain_adj(t.p[2] - x, pri, adj) + constrain_adj(t.p[3] - x, pri, adj));
+  }
+  if (sec) {
+    const int adj = max(0, damping - floor_log2_d((unsigned)sec));
+    int s0 = 0, s1 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { s0 += constrain_adj(t.s[i] - x, sec, adj); s1 += constrain_adj(t.s[4 + i] - x, sec, adj); }
+    sum += 2 * s0 + s1;
+  }
+  int y = x + ((8 + sum - (sum < 0)) >> 4);
+  if (pri && sec) {
+    int mn = x, mx = x;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { mn = min(mn, t.p[i]); mx = max(mx, t.p[i]); }
+#pragma unroll
+    for (int i = 0; i < 8; i++) { mn = min(mn, t.s[i]); mx = max(mx, t.s[i]); }
+    y = clip3_d(mn, mx, y);
+  }
+  return y;
+}
 // ---- loop restoration: self-guided filter parameter search (oracle/av1_restoration.c orc_lr_search_plane) ----------
 // One CTA (256 threads) per (restoration unit, plane); grid.y = job, grid.z = plane.  The unit is walked stripe by
 // stripe and in bands of 16 rows: a band's samples (CDEF output inside the stripe, deblocked rows outside it, AV1
@@ -465,6 +519,8 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
   __shared__ int s_best;
   __shared__ uint16_t s_px[3][kFW * kCdefTW];     // staged samples: rows y0-7 .. y0+70, columns x0-7 .. x0+70 (kCdefNA outside the frame)
   __shared__ uint8_t s_txs[20 * 20];              // tx_size of the 4x4 units (sbr*16 - 2 .. +17) x (sbc*16 - 2 .. +17)
+  __shared__ int16_t s_off[8][2];                 // CDEF tap offsets in the staged region per direction
+  if (tid < 16) s_off[tid >> 1][tid & 1] = (int16_t)(dv_cdef_dir[tid >> 1][tid & 1][0] * kCdefTW + dv_cdef_dir[tid >> 1][tid & 1][1]);
   if (tid == 0) s_any = 0;
   if (tid < 8) s_sse[tid] = 0;
   for (int p = 0; p < f->planes; p++) {
@@ -545,19 +601,17 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
         }
     return;
   }
-  const int nidx = 1 << f->cdef_bits;
-  for (int pass = 0; pass <= nidx; pass++) {     // passes 0..nidx-1: measure; pass nidx: apply the winner
-    const bool apply = pass == nidx;
-    const int idx = apply ? s_best : pass;
+  // ---- strength search: every pixel loads its taps once and evaluates all strength indices on them (squared error
+  // against the source per index), then the winner is applied.  Skipped 8x8 blocks are not filtered and do not count.
+  const int nidx = 1 << f->cdef_bits;              // <= 8
+  for (int pass = 0; pass < 2; pass++) {           // 0: measure every index, 1: apply the winner
+    const bool apply = pass == 1;
     if (apply && !job.fin[0]) break;
-    unsigned long long sse = 0;
+    const int best = apply ? s_best : 0;
+    unsigned int sse[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int p = 0; p < f->planes; p++) {
-      const int str = p == 0 ? f->cdef_y_strength[idx] : f->cdef_uv_strength[idx];
-      const int pri0 = (str >> 2) << cshift;
-      int sec = str & 3;
-      if (sec == 3) sec = 4;
-      sec <<= cshift;
       const int damping = f->cdef_damping + cshift - (p > 0);
+      const int32_t *strengths = p == 0 ? f->cdef_y_strength : f->cdef_uv_strength;
       const uint16_t *T = s_px[p];
       const PIX *S = (const PIX *)job.src[p];
       for (int i = tid; i < 4096; i += 256) {
@@ -565,33 +619,54 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
         const int yy = y0 + ly, xx = x0 + lx;
         if (yy >= H || xx >= W) continue;
         const int b = (ly >> 3) * 8 + (lx >> 3);
-        int v;
-        if (s_skip[b]) v = T[(ly + kFH) * kCdefTW + lx + kFH];
-        else {
-          int pri = pri0;
-          const int dir = pri == 0 ? 0 : s_dir[b];
-          if (p == 0 && pri) {
-            const int var = s_var[b];
-            const int ii = (var >> 6) ? min(floor_log2_d((unsigned)(var >> 6)), 12) : 0;
-            pri = var ? (pri * (4 + ii) + 8) >> 4 : 0;
-          }
-          v = cdef_pixel_tile(T, lx, ly, pri, sec, dir, damping, cshift);
-          const int d = v - (int)S[(size_t)yy * stride + xx];
-          sse += (unsigned long long)(d * d);
+        const uint16_t *c = T + (ly + kFH) * kCdefTW + lx + kFH;
+        if (s_skip[b]) {
+          if (apply) ((PIX *)job.fin[p])[(size_t)yy * stride + xx] = (PIX)*c;
+          continue;
         }
-        if (apply) ((PIX *)job.fin[p])[(size_t)yy * stride + xx] = (PIX)v;
+        CdefTaps taps;
+        cdef_load_taps(c, &s_off[0][0], s_dir[b], taps);
+        int vscale = -1;                            // luma: primary strength scaled by the block variance (spec 7.15.2)
+        if (p == 0) {
+          const int var = s_var[b];
+          vscale = var ? 4 + ((var >> 6) ? min(floor_log2_d((unsigned)(var >> 6)), 12) : 0) : 0;
+        }
+        const int src = apply ? 0 : (int)S[(size_t)yy * stride + xx];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          if (k >= nidx || (apply && k != best)) continue;
+          const int str = strengths[k];
+          const int pri0 = (str >> 2) << cshift;
+          int sec = str & 3;
+          if (sec == 3) sec = 4;
+          sec <<= cshift;
+          int v;
+          if (pri0 == 0 && sec != 0) v = cdef_pixel_tile(T, lx, ly, 0, sec, 0, damping, cshift);      // direction 0 when the primary strength is zero
+          else {
+            int pri = pri0;
+            if (p == 0 && pri) pri = vscale ? (pri * vscale + 8) >> 4 : 0;
+            v = cdef_eval(taps, pri, sec, damping, cshift);
+          }
+          if (apply) ((PIX *)job.fin[p])[(size_t)yy * stride + xx] = (PIX)v;
+          else { const int d = v - src; sse[k] += (unsigned)(d * d); }
+        }
       }
     }
     if (!apply) {
-      for (int m = 16; m > 0; m >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, m);
-      if ((tid & 31) == 0) atomicAdd(&s_sse[idx], sse);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (k >= nidx) continue;
+        unsigned long long v = sse[k];
+        for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if ((tid & 31) == 0) atomicAdd(&s_sse[k], v);
+      }
       __syncthreads();
-      if (pass == nidx - 1 && tid == 0) {
-        int best = 0;
+      if (tid == 0) {
+        int bi = 0;
         unsigned long long bs = s_sse[0];
-        for (int k = 1; k < nidx; k++) if (s_sse[k] < bs) { bs = s_sse[k]; best = k; }
-        s_best = best;
-        job.cdef_idx[blockIdx.x] = (int8_t)best;
+        for (int k = 1; k < nidx; k++) if (s_sse[k] < bs) { bs = s_sse[k]; bi = k; }
+        s_best = bi;
+        job.cdef_idx[blockIdx.x] = (int8_t)bi;
       }
       __syncthreads();
     }

@@ -204,46 +204,13 @@ __device__ __forceinline__ void edges_from_tile(const PIX *T, const PIX *AB, con
   __syncwarp();
 }
 
-// source block (n x n at frame position x, y) -> registers: one row segment of up to 16 bytes per lane
-template <class PIX>
-struct SrcRegs { uint4 v; };
-template <class PIX>
-__device__ __forceinline__ void src_fetch(const PIX *plane, int stride, int x, int y, int n, SrcRegs<PIX> &o, int half /*u16 n=32 second half etc.*/) {
-  // bytes per row = n * sizeof(PIX); segments of 16 bytes (or the whole row when shorter)
-  const int row_bytes = n * (int)sizeof(PIX), seg = row_bytes < 16 ? row_bytes : 16, segs_per_row = row_bytes / seg;
-  const int idx = lane_id() + 32 * half, r = idx / segs_per_row, s = idx % segs_per_row;
-  o.v = make_uint4(0, 0, 0, 0);
-  if (r >= n) return;
-  const char *p = reinterpret_cast<const char *>(plane + (size_t)(y + r) * stride + x) + s * seg;
-  if (seg == 16) {
-    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) o.v = *reinterpret_cast<const uint4 *>(p);
-    else { const uint2 a = *reinterpret_cast<const uint2 *>(p), b = *reinterpret_cast<const uint2 *>(p + 8); o.v = make_uint4(a.x, a.y, b.x, b.y); }
-  } else if (seg == 8) { const uint2 a = *reinterpret_cast<const uint2 *>(p); o.v.x = a.x; o.v.y = a.y; }
-  else o.v.x = *reinterpret_cast<const uint32_t *>(p);
-}
-template <class PIX>
-__device__ __forceinline__ void src_store(PIX *dst /* n x n row-major, 16-byte aligned */, int n, const SrcRegs<PIX> &o, int half) {
-  const int row_bytes = n * (int)sizeof(PIX), seg = row_bytes < 16 ? row_bytes : 16, segs_per_row = row_bytes / seg;
-  const int idx = lane_id() + 32 * half, r = idx / segs_per_row, s = idx % segs_per_row;
-  if (r >= n) return;
-  char *p = reinterpret_cast<char *>(dst) + r * row_bytes + s * seg;
-  if (seg == 16) *reinterpret_cast<uint4 *>(p) = o.v;
-  else if (seg == 8) *reinterpret_cast<uint2 *>(p) = make_uint2(o.v.x, o.v.y);
-  else *reinterpret_cast<uint32_t *>(p) = o.v.x;
-}
-// number of 32-lane fetch rounds a block of n x n samples needs
-template <class PIX> __device__ __forceinline__ int src_rounds(int n) {
-  const int row_bytes = n * (int)sizeof(PIX), seg = row_bytes < 16 ? row_bytes : 16;
-  return (n * (row_bytes / seg) + 31) / 32;
-}
-
-template <bool HBD, class PIX>
+template <bool HBD, int NMAX, class PIX>
 __device__ __forceinline__ int recon_tx_any(int n, const B200Frame *f, bool active, const PIX *src, const PIX *pred, PIX *rec, int32_t *buf,
                                             int16_t *qc, int tx_type) {
   if (n == 4) return recon_tx<4, HBD, PIX>(f, active, src, pred, rec, buf, qc, tx_type);
   if (n == 8) return recon_tx<8, HBD, PIX>(f, active, src, pred, rec, buf, qc, tx_type);
-  if (n == 16) return recon_tx<16, HBD, PIX>(f, active, src, pred, rec, buf, qc, tx_type);
-  return recon_tx<32, HBD, PIX>(f, active, src, pred, rec, buf, qc, tx_type);
+  if (NMAX == 16 || n == 16) return recon_tx<16, HBD, PIX>(f, active, src, pred, rec, buf, qc, tx_type);
+  return recon_tx<(NMAX == 32 ? 32 : 16), HBD, PIX>(f, active, src, pred, rec, buf, qc, tx_type);
 }
 
 struct BlockInfo { B200Mi m; uint8_t mode_above, mode_left; };
@@ -407,14 +374,14 @@ __device__ void recon_sb_row(const B200RdoJob &job, const TileCtx &t, ReconWarp<
         const int g = lane >> lg;
         const bool active = g < np;
         const int k = active ? g : 0;
-        const int e = recon_tx_any<HBD, PIX>(n, f, active, w.srcb[k], w.pred[k], (k == 0 ? T0 : T1) + by * kTS + bx,
+        const int e = recon_tx_any<HBD, NMAX, PIX>(n, f, active, w.srcb[k], w.pred[k], (k == 0 ? T0 : T1) + by * kTS + bx,
                                              w.buf + k * n * (n + 1), w.qc[k], tx_type);
         eobs[0] = __shfl_sync(FULL, e, 0);
         if (np == 2) eobs[1] = __shfl_sync(FULL, e, n & 31);
       } else {
 #pragma unroll 1
         for (int k = 0; k < 2; k++)
-          eobs[k] = recon_tx_any<HBD, PIX>(n, f, true, w.srcb[k], w.pred[k], (k == 0 ? T0 : T1) + by * kTS + bx, w.buf, w.qc[k], tx_type);
+          eobs[k] = recon_tx_any<HBD, NMAX, PIX>(n, f, true, w.srcb[k], w.pred[k], (k == 0 ? T0 : T1) + by * kTS + bx, w.buf, w.qc[k], tx_type);
       }
       // ---- records: eob per plane, levels appended to the compact stream
 #pragma unroll 1
@@ -481,8 +448,11 @@ struct ReconShared {
   ReconSync<ROWS> sy;
 };
 
+// Register budget: the chain is latency-bound, so what matters is that EVERY tile of a launch is resident at once (one
+// wave) while leaving room for the throughput kernels of the next chunk on the same SMs: <= 128 registers per thread
+// (16x16 transforms hold 3 x 16 values per lane); the 32x32 instances need the full budget.
 template <bool HBD, int NMAX, int ROWS>
-__global__ void __launch_bounds__(64 * ROWS) b200_recon_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
+__global__ void __launch_bounds__(64 * ROWS, NMAX == 32 ? 1 : (ROWS == 1 ? 8 : (ROWS == 2 ? 4 : 2))) b200_recon_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
   typedef typename PixOf<HBD>::type PIX;
   typedef ReconShared<HBD, NMAX, ROWS> SH;
   B200_RECON_SMEM(SH, sh);
@@ -563,6 +533,7 @@ int recon_launch_t(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int n_t
     std::lock_guard<std::mutex> lk(mu);
     if (!done[dev & 63]) {
       cudaFuncSetAttribute(b200_recon_kernel<HBD, NMAX, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SH));
+      cudaFuncSetAttribute(b200_recon_kernel<HBD, NMAX, ROWS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       done[dev & 63] = true;
     }
   }
