@@ -46,10 +46,10 @@ template <> struct PixOf<false> { typedef uint8_t type; };
 
 // inverse scan tables (4x4 | 8x8 | 16x16) in GLOBAL memory: indexed per lane (divergent), which the constant
 // cache would serialise; __ldg keeps them L1 resident.
-__device__ const uint8_t dv_iscan_g[336] = {
+__device__ __align__(16) const uint8_t dv_iscan_g[336] = {
 #include "iscan_init.inc"
 };
-__device__ const uint16_t dv_iscan32_g[1024] = {
+__device__ __align__(16) const uint16_t dv_iscan32_g[1024] = {
 #include "iscan32_init.inc"
 };
 __constant__ const uint8_t dv_sm_weights[4 + 8 + 16 + 32] = {255, 149, 85, 64, 255, 197, 146, 105, 73, 50, 37, 32,
@@ -98,6 +98,24 @@ __device__ __forceinline__ int scan_base(int n) { return n == 4 ? 0 : n == 8 ? 1
 template <int N> __device__ __forceinline__ int iscan_at(int pos) {
   if (N == 32) return __ldg(&dv_iscan32_g[pos]);
   return __ldg(&dv_iscan_g[scan_base(N) + pos]);
+}
+// scan indices of ROW l of an N x N block, packed: N <= 16: bytes of words w[0..N/4-1]; N == 32: halfwords of w[0..15].
+// One vector load per row; SCAN_AT(c) extracts entry c with a compile-time shift when c is a constant.
+template <int N> struct ScanRow { uint32_t w[N == 32 ? 16 : (N >= 4 ? N / 4 : 1)]; };
+template <int N> __device__ __forceinline__ void scan_row_load(int l, ScanRow<N> &r) {
+  if (N == 4) r.w[0] = __ldg(reinterpret_cast<const uint32_t *>(dv_iscan_g + l * 4));
+  else if (N == 8) { const uint2 v = __ldg(reinterpret_cast<const uint2 *>(dv_iscan_g + 16 + l * 8)); r.w[0] = v.x; r.w[1] = v.y; }
+  else if (N == 16) { const uint4 v = __ldg(reinterpret_cast<const uint4 *>(dv_iscan_g + 80 + l * 16)); r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w; }
+  else {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(dv_iscan32_g + l * 32) + k);
+      r.w[4 * k] = v.x; r.w[4 * k + 1] = v.y; r.w[4 * k + 2] = v.z; r.w[4 * k + 3] = v.w;
+    }
+  }
+}
+template <int N> __device__ __forceinline__ int scan_row_at(const ScanRow<N> &r, int c) {
+  return N == 32 ? (int)((r.w[c >> 1] >> (16 * (c & 1))) & 0xffffu) : (int)((r.w[c >> 2] >> (8 * (c & 3))) & 0xffu);
 }
 __device__ __forceinline__ int ilog2_dev(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
@@ -300,6 +318,12 @@ __device__ __forceinline__ void inv1d(int kind, const int32_t *in, int32_t *out)
 __device__ __forceinline__ int32_t rshift_round(int32_t v, int bit) {   // bit > 0: rounding right shift; <= 0: left shift
   return bit <= 0 ? (int32_t)((uint32_t)v << (-bit)) : (int32_t)(((long long)v + (1ll << (bit - 1))) >> bit);
 }
+// 8-bit video: every value this is applied to is below 2^30 in magnitude (DESIGN.md "int32 butterflies"), so the rounding
+// add cannot overflow 32 bits; 10-bit keeps the 64-bit form
+template <bool HBD> __device__ __forceinline__ int32_t rshift_round_t(int32_t v, int bit) {
+  if (HBD) return rshift_round(v, bit);
+  return bit <= 0 ? (int32_t)((uint32_t)v << (-bit)) : (v + (1 << (bit - 1))) >> bit;
+}
 __device__ __forceinline__ int32_t clamp_bits(int32_t v, int bits) {
   const int32_t mx = (1 << (bits - 1)) - 1, mn = -(1 << (bits - 1));
   return v < mn ? mn : (v > mx ? mx : v);
@@ -350,23 +374,25 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
     fwd1d<N, HBD>(pass == 0 ? vert : horz, x, o, (N == 32 || (pass == 1 && N == 16)) ? 12 : 13);   // fwd_cos_bit_col / _row
     if (pass == 0) {
 #pragma unroll
-      for (int r = 0; r < N; r++) buf[r * S + l] = rshift_round(o[r], shift1);
+      for (int r = 0; r < N; r++) buf[r * S + l] = rshift_round_t<HBD>(o[r], shift1);
       __syncwarp();
     } else {
 #pragma unroll
       for (int c = 0; c < N; c++) buf[l * S + c] = o[c];
     }
   }
-  // ---- quantise / dequantise row l in place (oracle quantize()); exact division by reciprocal multiplication
+  // ---- quantise / dequantise row l in place (oracle quantize()); exact division by reciprocal multiplication.
+  // Unrolled: the scan indices of the row come from one vector load, only coefficient 0 of lane 0 uses the DC step.
   int eob = 0;
+  ScanRow<N> srow;
+  scan_row_load<N>(l, srow);
   {
     const uint32_t dc_q = (uint32_t)f->dc_q, ac_q = (uint32_t)f->ac_q;
-    const uint32_t dc_rcp = 0xffffffffu / dc_q, ac_rcp = 0xffffffffu / ac_q;
-#pragma unroll 1
+    const uint32_t ac_rcp = 0xffffffffu / ac_q, ac_off = (ac_q * 98) >> 8;
+#pragma unroll
     for (int c = 0; c < N; c++) {
-      const int pos = l * N + c;
-      const uint32_t q = pos == 0 ? dc_q : ac_q, rcp = pos == 0 ? dc_rcp : ac_rcp;
-      const uint32_t off = pos == 0 ? (q * 109) >> 8 : (q * 98) >> 8;
+      uint32_t q = ac_q, rcp = ac_rcp, off = ac_off;
+      if (c == 0 && l == 0) { q = dc_q; rcp = 0xffffffffu / dc_q; off = (dc_q * 109) >> 8; }
       const int32_t cf = buf[l * S + c];
       const uint32_t a = ((uint32_t)(cf < 0 ? -cf : cf) << qshift) + off;
       uint32_t lv = __umulhi(a, rcp);           // floor(a / q) or one/two less
@@ -375,7 +401,7 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
       if (rem >= q) lv++;
       if (lv > 32767) lv = 32767;
       const int32_t dqa = (int32_t)((lv * q) & 0xFFFFFF) >> qshift;
-      const int si = iscan_at<N>(pos);
+      const int si = scan_row_at<N>(srow, c);
       qc[si] = (int16_t)(cf < 0 ? -(int)lv : (int)lv);
       buf[l * S + c] = cf < 0 ? -dqa : dqa;
       lev[l * LS + c] = (uint8_t)(lv > 127 ? 127 : lv);
@@ -407,30 +433,43 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
       }
     }
 #pragma unroll 1
-    for (int c = 0; c < N; c++) {
-      const int pos = l * N + c;
-      const int si = iscan_at<N>(pos);
-      if (si >= eob) continue;
-      const int level = abs((int)qc[si]);
-      const uint8_t *L = lev + l * LS + c;
-      if (si == eob - 1) {
-        const int c4 = si == 0 ? 0 : (si <= N2 / 8 ? 1 : (si <= N2 / 4 ? 2 : 3));
-        rate += rt->coeff_base_eob[txs][ptype][c4][min(level, 3) - 1];
+    for (int c0 = 0; c0 < N; c0 += 4) {
+      // the four scan indices of this step: one (N <= 16) or two (N == 32) packed words selected by the loop counter
+      uint32_t wa = 0, wb = 0;
+      if (N == 32) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (c0 == 4 * k) { wa = srow.w[2 * k]; wb = srow.w[2 * k + 1]; }
       } else {
-        const int mag = min((int)L[1], 3) + min((int)L[LS], 3) + min((int)L[LS + 1], 3) + min((int)L[2], 3) + min((int)L[2 * LS], 3);
-        int ctx = min((mag + 1) >> 1, 4);
-        if (l == 0 && c == 0) ctx = 0;
-        else ctx += (l + c < 2) ? 1 : ((l + c < 4) ? 6 : 21);
-        rate += rt->coeff_base[txs][ptype][ctx][min(level, 3)];
+#pragma unroll
+        for (int k = 0; k < (N >= 4 ? N / 4 : 1); k++) if (c0 == 4 * k) wa = srow.w[k];
       }
-      if (level > 2) {
-        int mag = min((int)L[1], 15) + min((int)L[LS], 15) + min((int)L[LS + 1], 15);
-        mag = min((mag + 1) >> 1, 6);
-        const int bctx = (l == 0 && c == 0) ? mag : ((l < 2 && c < 2) ? mag + 7 : mag + 14);
-        rate += rt->coeff_br[txs][ptype][bctx][min(level - 3, 12)];
-        if (level > 14) rate += 256u * (uint32_t)(2 * (32 - __clz(level - 14)) - 1);   // golomb(level - 15)
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) {
+        const int c = c0 + cc;
+        const int si = N == 32 ? (int)(((cc < 2 ? wa : wb) >> (16 * (cc & 1))) & 0xffffu) : (int)((wa >> (8 * cc)) & 0xffu);
+        if (si >= eob) continue;
+        const int qv = qc[si];
+        const int level = abs(qv);
+        const uint8_t *L = lev + l * LS + c;
+        if (si == eob - 1) {
+          const int c4 = si == 0 ? 0 : (si <= N2 / 8 ? 1 : (si <= N2 / 4 ? 2 : 3));
+          rate += rt->coeff_base_eob[txs][ptype][c4][min(level, 3) - 1];
+        } else {
+          const int mag = min((int)L[1], 3) + min((int)L[LS], 3) + min((int)L[LS + 1], 3) + min((int)L[2], 3) + min((int)L[2 * LS], 3);
+          int ctx = min((mag + 1) >> 1, 4);
+          if (l == 0 && c == 0) ctx = 0;
+          else ctx += (l + c < 2) ? 1 : ((l + c < 4) ? 6 : 21);
+          rate += rt->coeff_base[txs][ptype][ctx][min(level, 3)];
+        }
+        if (level > 2) {
+          int mag = min((int)L[1], 15) + min((int)L[LS], 15) + min((int)L[LS + 1], 15);
+          mag = min((mag + 1) >> 1, 6);
+          const int bctx = (l == 0 && c == 0) ? mag : ((l < 2 && c < 2) ? mag + 7 : mag + 14);
+          rate += rt->coeff_br[txs][ptype][bctx][min(level - 3, 12)];
+          if (level > 14) rate += 256u * (uint32_t)(2 * (32 - __clz(level - 14)) - 1);   // golomb(level - 15)
+        }
+        if (level) rate += (si == 0) ? rt->dc_sign[ptype][0][qv < 0] : 256u;
       }
-      if (level) rate += (si == 0) ? rt->dc_sign[ptype][0][qc[si] < 0] : 256u;
     }
   }
   if (RATE) rate = group_sum<N>(rate);
@@ -452,11 +491,11 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
       inv1d<N, HBD>(pass == 0 ? horz : vert, x, o);
       if (pass == 0) {
 #pragma unroll
-        for (int c = 0; c < N; c++) buf[l * S + c] = rshift_round(o[c], row_shift);
+        for (int c = 0; c < N; c++) buf[l * S + c] = rshift_round_t<HBD>(o[c], row_shift);
       } else {
 #pragma unroll
         for (int r = 0; r < N; r++) {
-          int v = (int)pred[r * N + l] + rshift_round(o[r], 4);
+          int v = (int)pred[r * N + l] + rshift_round_t<HBD>(o[r], 4);
           v = v < 0 ? 0 : (v > mx ? mx : v);
           rec[r * N + l] = (PIX)v;
           const int d = (int)src[r * N + l] - v;

@@ -377,8 +377,9 @@ __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid
   out[13] = word;
 }
 
-// ---- stage A.2: full trials of the never-pruned TOP level; grid.y = job.  The W warps of a CTA analyse W consecutive
-// blocks in lock-step (analyze_block<.., SYNC>), CTAs walk the level grid-stride.
+// ---- stage A.2: full trials.  One single-warp CTA loops over blocks of level lv (grid-stride), grid.y = job.
+// W warps per CTA.  W == 1: free-running single-warp CTAs (grid-stride over the blocks).  W > 1 (the never-pruned top
+// level): the W warps of a CTA analyse W different blocks in lock-step (analyze_block<.., SYNC>).
 constexpr int kAnalyzeWarpsTop = 4;      // 16x16 as the top level
 constexpr int kAnalyzeWarpsTop32 = 2;    // 32x32 as the top level (22.9 KB of shared memory per warp)
 template <int LV, bool HBD, int W>
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(kThreads * W, LV == 3 ? 4 : (LV == 2 ? 16 : 24
   TileCtx t;
   ctx_from_job(job, t);
   const int cols = b200_level_cols(f, lv), total = cols * b200_level_rows(f, lv);
-  {
+  if (W > 1) {
     const int per_iter = gridDim.x * W, iters = (total + per_iter - 1) / per_iter;
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
@@ -411,65 +412,22 @@ __global__ void __launch_bounds__(kThreads * W, LV == 3 ? 4 : (LV == 2 ? 16 : 24
       tile_of_unit(f, y >> 2, x >> 2, t);
       analyze_block<2 + LV, HBD, true>(t, sh, x, y, job.satd[lv] + (size_t)blk * B200_SATD_WORDS, want < total ? job.dec[lv] + blk : nullptr);
     }
+    return;
   }
-}
-
-// Pruned levels (everything below the top level): most blocks are not analysed at all, and free-running single-warp CTAs
-// lose their issue slots to instruction fetch (ncu: stall_no_instruction 6.3 warps per issue at the 8x8 level - every warp
-// walks ~60 KB of code on its own).  This variant gives a CTA of W warps a SEGMENT of kListItems consecutive blocks: the
-// threads first mark the pruned ones and compact the survivors into shared memory, then the W warps analyse W survivors at a
-// time in lock-step (analyze_block<.., SYNC>: a CTA barrier in front of every trial batch) so that they share the
-// instruction stream.  Segments are walked grid-stride.
-constexpr int kListWarps = 4;
-constexpr int kListItems = 256;
-template <int LV, bool HBD>
-__global__ void __launch_bounds__(kThreads * kListWarps, (LV == 2 ? 16 : 24) / kListWarps) b200_analyze_list_kernel(const B200RdoJob *jobs) {
-  typedef typename PixOf<HBD>::type PIX;
-  typedef SharedT<16, PIX> SH;
-  constexpr int W = kListWarps;
-  __shared__ SH shs[W];
-  __shared__ uint16_t s_list[kListItems];
-  __shared__ int s_n;
-  SH &sh = shs[threadIdx.x >> 5];
-  const B200RdoJob &job = jobs[blockIdx.y];
-  const B200Frame *f = &job.frame;
-  constexpr int lv = LV, n = 4 << LV;
-  if (n < min(f->partition_min, 8) || n > f->partition_max) return;   // 8x8 always: forced splits at the frame edge
-  TileCtx t;
-  ctx_from_job(job, t);
-  const int cols = b200_level_cols(f, lv), total = cols * b200_level_rows(f, lv);
 #pragma unroll 1
-  for (int base = blockIdx.x * kListItems; base < total; base += gridDim.x * kListItems) {
-    __syncthreads();                       // the previous segment's list is no longer read
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-#pragma unroll 1
-    for (int k = 0; k < kListItems / (kThreads * W); k++) {
-      const int it = k * kThreads * W + threadIdx.x, blk = base + it;
-      bool active = blk < total;
-      if (active && b200_pruned_by_parent(f, lv, blk % cols, blk / cols, job.dec[LV + 1])) {
-        B200BlockDec d;                    // top-down pruning: never split down to this block
+  for (int blk = blockIdx.x; blk < total; blk += gridDim.x) {
+    const int x = (blk % cols) * n, y = (blk / cols) * n;
+    if (LV < B200_LEVELS - 1 && b200_pruned_by_parent(f, lv, blk % cols, blk / cols, job.dec[LV < B200_LEVELS - 1 ? LV + 1 : LV])) {
+      if (lane_id() == 0) {   // top-down pruning: never split down to this block
+        B200BlockDec d;
         d.cost = B200_COST_PRUNED; d.y_mode = 0; d.tx_type = 0; d.uv_mode = 0; d.all_zero = 0; d.angle_y = 0; d.angle_uv = 0;
         d.cfl_js = 0; d.cfl_alpha = 0;
         job.dec[lv][blk] = d;
-        active = false;
       }
-      const unsigned m = __ballot_sync(FULL, active);
-      int off = 0;
-      if (lane_id() == 0 && m) off = atomicAdd(&s_n, __popc(m));
-      off = __shfl_sync(FULL, off, 0);
-      if (active) s_list[off + __popc(m & ((1u << lane_id()) - 1))] = (uint16_t)it;
+      continue;
     }
-    __syncthreads();
-    const int cnt = s_n;
-#pragma unroll 1
-    for (int i0 = 0; i0 < cnt; i0 += W) {
-      const int i = i0 + (threadIdx.x >> 5);
-      const int blk = base + s_list[i < cnt ? i : cnt - 1];        // padding warps repeat the last survivor, output discarded
-      const int x = (blk % cols) * n, y = (blk / cols) * n;
-      tile_of_unit(f, y >> 2, x >> 2, t);
-      analyze_block<2 + LV, HBD, true>(t, sh, x, y, job.satd[lv] + (size_t)blk * B200_SATD_WORDS, i < cnt ? job.dec[lv] + blk : nullptr);
-    }
+    tile_of_unit(f, y >> 2, x >> 2, t);
+    analyze_block<2 + LV, HBD, false>(t, sh, x, y, job.satd[lv] + (size_t)blk * B200_SATD_WORDS, job.dec[lv] + blk);
   }
 }
 
@@ -560,8 +518,8 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
 #define B200_CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
     B200_CARVE((b200_analyze_kernel<2, false, kAnalyzeWarpsTop>)); B200_CARVE((b200_analyze_kernel<2, true, kAnalyzeWarpsTop>));
     B200_CARVE((b200_analyze_kernel<3, false, kAnalyzeWarpsTop32>)); B200_CARVE((b200_analyze_kernel<3, true, kAnalyzeWarpsTop32>));
-    B200_CARVE((b200_analyze_list_kernel<0, false>)); B200_CARVE((b200_analyze_list_kernel<1, false>)); B200_CARVE((b200_analyze_list_kernel<2, false>));
-    B200_CARVE((b200_analyze_list_kernel<0, true>)); B200_CARVE((b200_analyze_list_kernel<1, true>)); B200_CARVE((b200_analyze_list_kernel<2, true>));
+    B200_CARVE((b200_analyze_kernel<0, false, 1>)); B200_CARVE((b200_analyze_kernel<1, false, 1>)); B200_CARVE((b200_analyze_kernel<2, false, 1>));
+    B200_CARVE((b200_analyze_kernel<0, true, 1>)); B200_CARVE((b200_analyze_kernel<1, true, 1>)); B200_CARVE((b200_analyze_kernel<2, true, 1>));
     configured = true;
   }
   const int top = top_level >= 3 ? 3 : 2;
@@ -585,6 +543,7 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     }
     // enough warps to fill the machine several times over, grid-stride inside
     const int per_job = min(nblk, max(1, (148 * 16 * 4) / n_jobs));
+    dim3 ga(per_job, n_jobs);
 #define B200_ANALYZE(LV, W, GRID) \
     do { if (high_bitdepth) b200_analyze_kernel<LV, true, W><<<GRID, kThreads * W, 0, st>>>(d_jobs); \
          else b200_analyze_kernel<LV, false, W><<<GRID, kThreads * W, 0, st>>>(d_jobs); } while (0)
@@ -594,16 +553,9 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     } else if (lv == 2 && top == 2) {      // never pruned: lock-step CTAs
       dim3 gt((per_job + kAnalyzeWarpsTop - 1) / kAnalyzeWarpsTop, n_jobs);
       B200_ANALYZE(2, kAnalyzeWarpsTop, gt);
-    } else {                               // pruned levels: segments of kListItems blocks, survivors in lock-step
-      const int segs = (nblk + kListItems - 1) / kListItems;
-      dim3 gl(min(segs, max(1, (148 * 16) / n_jobs)), n_jobs);
-#define B200_ANALYZE_LIST(LV) \
-      do { if (high_bitdepth) b200_analyze_list_kernel<LV, true><<<gl, kThreads * kListWarps, 0, st>>>(d_jobs); \
-           else b200_analyze_list_kernel<LV, false><<<gl, kThreads * kListWarps, 0, st>>>(d_jobs); } while (0)
-      if (lv == 2) B200_ANALYZE_LIST(2);
-      else if (lv == 1) B200_ANALYZE_LIST(1);
-      else B200_ANALYZE_LIST(0);
-    }
+    } else if (lv == 2) B200_ANALYZE(2, 1, ga);
+    else if (lv == 1) B200_ANALYZE(1, 1, ga);
+    else B200_ANALYZE(0, 1, ga);
     B200_MARK(lv == 3 ? "analyze_32x32" : (lv == 2 ? "analyze_16x16" : (lv == 1 ? "analyze_8x8" : "analyze_4x4")), st);
     n_launch++;
   }
@@ -639,11 +591,11 @@ static void emu_satd(void *) {
 static void emu_analyze(void *) {
   const bool hbd = g_emu_jobs[0].frame.bit_depth > 8;
 #define EMU_ANALYZE(LV, W) do { if (hbd) b200_analyze_kernel<LV, true, W>(g_emu_jobs); else b200_analyze_kernel<LV, false, W>(g_emu_jobs); } while (0)
-#define EMU_ANALYZE_LIST(LV) do { if (hbd) b200_analyze_list_kernel<LV, true>(g_emu_jobs); else b200_analyze_list_kernel<LV, false>(g_emu_jobs); } while (0)
-  if (g_emu_lv == g_emu_top) { if (g_emu_top == 3) EMU_ANALYZE(3, kAnalyzeWarpsTop32); else EMU_ANALYZE(2, kAnalyzeWarpsTop); }
-  else if (g_emu_lv == 2) EMU_ANALYZE_LIST(2);
-  else if (g_emu_lv == 1) EMU_ANALYZE_LIST(1);
-  else EMU_ANALYZE_LIST(0);
+  if (g_emu_lv == 0) EMU_ANALYZE(0, 1);
+  else if (g_emu_lv == 1) EMU_ANALYZE(1, 1);
+  else if (g_emu_lv == 2 && g_emu_top == 2) EMU_ANALYZE(2, kAnalyzeWarpsTop);
+  else if (g_emu_lv == 2) EMU_ANALYZE(2, 1);
+  else EMU_ANALYZE(3, kAnalyzeWarpsTop32);
 }
 static void emu_decide(void *) { b200_decide_kernel(g_emu_jobs); }
 extern "C" int b200_recon_launch_emu(const B200RdoJob *jobs, const B200TileRef *tiles, int n_tiles, int rows);
@@ -656,7 +608,7 @@ extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *ti
     if (nblk == 0) continue;
     const int items = g_emu_lv == g_emu_top ? 128 : kSatdItems;
     emu::launch(emu_satd, nullptr, (unsigned)((nblk + items - 1) / items), 128);
-    const int w = g_emu_lv == g_emu_top ? (g_emu_top == 3 ? kAnalyzeWarpsTop32 : kAnalyzeWarpsTop) : kListWarps;
+    const int w = g_emu_lv == 3 ? kAnalyzeWarpsTop32 : ((g_emu_lv == 2 && g_emu_top == 2) ? kAnalyzeWarpsTop : 1);
     emu::launch(emu_analyze, nullptr, (unsigned)std::min(nblk, w > 1 ? 3 : 7), kThreads * w);
   }
   const int rn4 = g_emu_top == 3 ? 8 : 4;

@@ -76,9 +76,32 @@ __device__ __forceinline__ void publish_add(unsigned *p) {
 }
 
 // ---- single-candidate transform path of the reconstruction: lane group g (N lanes) codes one plane ---------------
+// The chain is bound by INSTRUCTION FETCH, not by arithmetic (ncu: stall_no_instruction 5.6 warps per issue with every
+// 1-D transform inlined at each of its four call sites: 190 KB of code, a different 20 KB slice per block and warp).  Each
+// 1-D transform therefore exists ONCE per size, behind a call, with its data in thread-local memory; forward column / row
+// passes and inverse row / column passes share those copies, and the hot set of the whole kernel stays cache resident.
+template <int N, bool HBD>
+__device__ __noinline__ void fwd1d_call(int kind, int32_t *v /* in/out */, int bit) {
+  int32_t x[N], o[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) x[i] = v[i];
+  fwd1d<N, HBD>(kind, x, o, bit);
+#pragma unroll
+  for (int i = 0; i < N; i++) v[i] = o[i];
+}
+template <int N, bool HBD>
+__device__ __noinline__ void inv1d_call(int kind, int32_t *v /* in/out */) {
+  int32_t x[N], o[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) x[i] = v[i];
+  inv1d<N, HBD>(kind, x, o);
+#pragma unroll
+  for (int i = 0; i < N; i++) v[i] = o[i];
+}
+
 // src: n x n row-major (stride N); pred: n x n (stride N); rec: destination inside the superblock tile (stride kTS).
 // Same arithmetic as trial_batch() in av1_dev.cuh (forward: libaom design; quantiser dead zone 109/256 DC, 98/256 AC;
-// inverse: AV1 spec 7.13.3) without the rate model; the dequantised row feeds the inverse row pass from registers.
+// inverse: AV1 spec 7.13.3) without the rate model.
 template <int N, bool HBD, class PIX>
 __device__ __noinline__ int recon_tx(const B200Frame *f, bool active, const PIX *src, const PIX *pred, PIX *rec, int32_t *buf,
                                      int16_t *qc, int tx_type) {
@@ -90,32 +113,31 @@ __device__ __noinline__ int recon_tx(const B200Frame *f, bool active, const PIX 
   const int bd = f->bit_depth;
   int vert, horz;
   tx_kernels(tx_type, vert, horz);
+  int32_t v[N];
   // forward column pass
   if (active) {
-    int32_t x[N], o[N];
 #pragma unroll
-    for (int r = 0; r < N; r++) x[r] = ((int)src[r * N + l] - (int)pred[r * N + l]) * 4;
-    fwd1d<N, HBD>(vert, x, o, N == 32 ? 12 : 13);
+    for (int r = 0; r < N; r++) v[r] = ((int)src[r * N + l] - (int)pred[r * N + l]) * 4;
+    fwd1d_call<N, HBD>(vert, v, N == 32 ? 12 : 13);
 #pragma unroll
-    for (int r = 0; r < N; r++) buf[r * S + l] = rshift_round(o[r], shift1);
+    for (int r = 0; r < N; r++) buf[r * S + l] = rshift_round_t<HBD>(v[r], shift1);
   }
   __syncwarp();
-  // forward row pass, quantiser, dequantiser, inverse row pass
+  // forward row pass, quantiser, dequantiser
   int eob = 0;
-  int32_t dq[N];
   if (active) {
-    int32_t x[N];
 #pragma unroll
-    for (int c = 0; c < N; c++) x[c] = buf[l * S + c];
-    fwd1d<N, HBD>(horz, x, dq, (N == 32 || N == 16) ? 12 : 13);
+    for (int c = 0; c < N; c++) v[c] = buf[l * S + c];
+    fwd1d_call<N, HBD>(horz, v, (N == 32 || N == 16) ? 12 : 13);
     const uint32_t dc_q = (uint32_t)f->dc_q, ac_q = (uint32_t)f->ac_q;
     const uint32_t ac_rcp = 0xffffffffu / ac_q, ac_off = (ac_q * 98) >> 8;
+    ScanRow<N> srow;
+    scan_row_load<N>(l, srow);
 #pragma unroll
     for (int c = 0; c < N; c++) {
-      const int pos = l * N + c;
       uint32_t q = ac_q, rcp = ac_rcp, off = ac_off;
       if (c == 0 && l == 0) { q = dc_q; rcp = 0xffffffffu / dc_q; off = (dc_q * 109) >> 8; }
-      const int32_t cf = dq[c];
+      const int32_t cf = v[c];
       const uint32_t a = ((uint32_t)(cf < 0 ? -cf : cf) << qshift) + off;
       uint32_t lv = __umulhi(a, rcp);
       uint32_t rem = a - lv * q;
@@ -123,35 +145,32 @@ __device__ __noinline__ int recon_tx(const B200Frame *f, bool active, const PIX 
       if (rem >= q) lv++;
       if (lv > 32767) lv = 32767;
       const int32_t dqa = (int32_t)((lv * q) & 0xFFFFFF) >> qshift;
-      const int si = iscan_at<N>(pos);
+      const int si = scan_row_at<N>(srow, c);
       qc[si] = (int16_t)(cf < 0 ? -(int)lv : (int)lv);
-      dq[c] = cf < 0 ? -dqa : dqa;
+      v[c] = clamp_bits(cf < 0 ? -dqa : dqa, bd + 8);
       if (lv) eob = max(eob, si + 1);
     }
   }
   eob = group_max<N>(eob);
+  // inverse row pass
   if (active && eob) {
-    int32_t x[N], o[N];
+    inv1d_call<N, HBD>(horz, v);
 #pragma unroll
-    for (int c = 0; c < N; c++) x[c] = clamp_bits(dq[c], bd + 8);
-    inv1d<N, HBD>(horz, x, o);
-#pragma unroll
-    for (int c = 0; c < N; c++) buf[l * S + c] = rshift_round(o[c], row_shift);
+    for (int c = 0; c < N; c++) buf[l * S + c] = rshift_round_t<HBD>(v[c], row_shift);
   }
   __syncwarp();
   if (active) {
     if (eob) {
       const int col_clamp = bd + 6 > 16 ? bd + 6 : 16;
       const int mx = (1 << bd) - 1;
-      int32_t x[N], o[N];
 #pragma unroll
-      for (int r = 0; r < N; r++) x[r] = clamp_bits(buf[r * S + l], col_clamp);
-      inv1d<N, HBD>(vert, x, o);
+      for (int r = 0; r < N; r++) v[r] = clamp_bits(buf[r * S + l], col_clamp);
+      inv1d_call<N, HBD>(vert, v);
 #pragma unroll
       for (int r = 0; r < N; r++) {
-        int v = (int)pred[r * N + l] + rshift_round(o[r], 4);
-        v = v < 0 ? 0 : (v > mx ? mx : v);
-        rec[r * kTS + l] = (PIX)v;
+        int y = (int)pred[r * N + l] + rshift_round_t<HBD>(v[r], 4);
+        y = y < 0 ? 0 : (y > mx ? mx : y);
+        rec[r * kTS + l] = (PIX)y;
       }
     } else {
 #pragma unroll

@@ -23,6 +23,7 @@
 #define __constant__ static
 #define __restrict__
 #define __launch_bounds__(...)
+#define __align__(n) alignas(n)
 
 struct emu_dim3 { unsigned x, y, z; };
 namespace emu {
