@@ -11,6 +11,7 @@
 // unavailable.
 #include "../../include/b200avif.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -182,6 +183,30 @@ void release_context(std::unique_ptr<Context> &c, bool ok = true) {
   g_ctx_free.push_back(std::move(c));
 }
 
+// ---- TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no link against libcuda) --------
+typedef CUresult (*TmapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = []() -> TmapEncodeFn {
+    if (getenv("B200AVIF_NO_TMA")) return nullptr;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+    return (TmapEncodeFn)p;
+  }();
+  return fn;
+}
+// 2-D map of one sample plane (coded width x height, `stride` samples per row), box = box_w x box_h samples, zero fill
+bool encode_plane_tmap(CUtensorMap *out, void *base, size_t bps, size_t cw, size_t ch, size_t stride, int box_w, int box_h) {
+  TmapEncodeFn fn = tmap_encoder();
+  if (!fn || ((uintptr_t)base & 15) || ((stride * bps) & 15)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cw, (cuuint64_t)ch};
+  const cuuint64_t strides[1] = {(cuuint64_t)(stride * bps)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, estr[2] = {1, 1};
+  return fn(out, bps == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // RAII lease of a pooled context: handed back drained unless the call marked itself successful.
 struct CtxLease {
   std::unique_ptr<Context> c;
@@ -242,7 +267,7 @@ size_t job_dev_bytes(const FrameJob &j, bool own_src) {
   for (int lv = 0; lv < B200_LEVELS; lv++) b += align256(j.n_blk(lv) * sizeof(B200BlockDec)) + align256(j.n_blk(lv) * B200_SATD_WORDS * 4) + 512;
   if (j.uses_lr()) b += P * (align256(j.plane_bytes()) + align256(j.dbrows_bytes()) + align256(j.n_lr() * sizeof(B200LrUnit)));
   // the job descriptor and tile list issue_rdo() uploads (one entry per job / tile)
-  b += align256(sizeof(B200RdoJob)) + align256((size_t)j.f.tile_rows * j.f.tile_cols * sizeof(B200TileRef)) + 512;
+  b += align256(sizeof(B200RdoJob)) + align256((size_t)j.f.tile_rows * j.f.tile_cols * sizeof(B200TileRef)) + 512 + 3 * sizeof(CUtensorMap) + 256;
   return b + 8192;
 }
 size_t job_pin_bytes(const FrameJob &j) {
@@ -421,8 +446,28 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     for (FrameJob *jp : jobs) max_sb = std::max(max_sb, (int)jp->n_sb());
     int with_lr = 0;
     for (FrameJob *jp : jobs) with_lr |= jp->uses_lr();
+    // tensor maps of the reconstruction planes for the TMA loads of the fused filter kernel (one per job and plane)
+    const void *d_tmaps = nullptr;
+    {
+      int bw = 0, bh = 0;
+      b200_filters_tmap_box(&bw, &bh);
+      std::vector<CUtensorMap> maps(jobs.size() * 3);
+      bool ok = tmap_encoder() != nullptr;
+      for (size_t i = 0; ok && i < jobs.size(); i++)
+        for (int p = 0; ok && p < 3; p++) {
+          FrameJob &j = *jobs[i];
+          const int q = p < j.f.planes ? p : 0;
+          ok = encode_plane_tmap(&maps[i * 3 + p], j.d_rec[q], j.bps(), (size_t)j.f.mi_cols * 4, (size_t)j.f.mi_rows * 4, j.stride(), bw, bh);
+        }
+      if (ok) {
+        CUtensorMap *d = dev.take<CUtensorMap>(maps.size());
+        if (dev.overflow) return fail(B200AVIF_ENCODING_ERROR, "internal error: work arena too small for this batch");
+        CU(cudaMemcpyAsync(d, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, c.stream_hi));
+        d_tmaps = d;
+      }
+    }
     b200_mark(nullptr, c.stream_hi);
-    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_sb, with_lr, jobs[0]->f.bit_depth > 8, c.stream_hi, &n_launched);
+    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_sb, with_lr, jobs[0]->f.bit_depth > 8, d_tmaps, c.stream_hi, &n_launched);
     if (fe != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("filter kernel launch failed: ") + cudaGetErrorString((cudaError_t)fe));
     g_launches += (uint64_t)n_launched;
   }

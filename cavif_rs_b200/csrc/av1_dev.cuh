@@ -381,18 +381,16 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
       for (int c = 0; c < N; c++) buf[l * S + c] = o[c];
     }
   }
-  // ---- quantise / dequantise row l in place (oracle quantize()); exact division by reciprocal multiplication.
-  // Unrolled: the scan indices of the row come from one vector load, only coefficient 0 of lane 0 uses the DC step.
+  // ---- quantise / dequantise row l in place (oracle quantize()); exact division by reciprocal multiplication
   int eob = 0;
-  ScanRow<N> srow;
-  scan_row_load<N>(l, srow);
   {
     const uint32_t dc_q = (uint32_t)f->dc_q, ac_q = (uint32_t)f->ac_q;
-    const uint32_t ac_rcp = 0xffffffffu / ac_q, ac_off = (ac_q * 98) >> 8;
-#pragma unroll
+    const uint32_t dc_rcp = 0xffffffffu / dc_q, ac_rcp = 0xffffffffu / ac_q;
+#pragma unroll 1
     for (int c = 0; c < N; c++) {
-      uint32_t q = ac_q, rcp = ac_rcp, off = ac_off;
-      if (c == 0 && l == 0) { q = dc_q; rcp = 0xffffffffu / dc_q; off = (dc_q * 109) >> 8; }
+      const int pos = l * N + c;
+      const uint32_t q = pos == 0 ? dc_q : ac_q, rcp = pos == 0 ? dc_rcp : ac_rcp;
+      const uint32_t off = pos == 0 ? (q * 109) >> 8 : (q * 98) >> 8;
       const int32_t cf = buf[l * S + c];
       const uint32_t a = ((uint32_t)(cf < 0 ? -cf : cf) << qshift) + off;
       uint32_t lv = __umulhi(a, rcp);           // floor(a / q) or one/two less
@@ -401,7 +399,7 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
       if (rem >= q) lv++;
       if (lv > 32767) lv = 32767;
       const int32_t dqa = (int32_t)((lv * q) & 0xFFFFFF) >> qshift;
-      const int si = scan_row_at<N>(srow, c);
+      const int si = iscan_at<N>(pos);
       qc[si] = (int16_t)(cf < 0 ? -(int)lv : (int)lv);
       buf[l * S + c] = cf < 0 ? -dqa : dqa;
       lev[l * LS + c] = (uint8_t)(lv > 127 ? 127 : lv);
@@ -433,43 +431,30 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
       }
     }
 #pragma unroll 1
-    for (int c0 = 0; c0 < N; c0 += 4) {
-      // the four scan indices of this step: one (N <= 16) or two (N == 32) packed words selected by the loop counter
-      uint32_t wa = 0, wb = 0;
-      if (N == 32) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) if (c0 == 4 * k) { wa = srow.w[2 * k]; wb = srow.w[2 * k + 1]; }
+    for (int c = 0; c < N; c++) {
+      const int pos = l * N + c;
+      const int si = iscan_at<N>(pos);
+      if (si >= eob) continue;
+      const int level = abs((int)qc[si]);
+      const uint8_t *L = lev + l * LS + c;
+      if (si == eob - 1) {
+        const int c4 = si == 0 ? 0 : (si <= N2 / 8 ? 1 : (si <= N2 / 4 ? 2 : 3));
+        rate += rt->coeff_base_eob[txs][ptype][c4][min(level, 3) - 1];
       } else {
-#pragma unroll
-        for (int k = 0; k < (N >= 4 ? N / 4 : 1); k++) if (c0 == 4 * k) wa = srow.w[k];
+        const int mag = min((int)L[1], 3) + min((int)L[LS], 3) + min((int)L[LS + 1], 3) + min((int)L[2], 3) + min((int)L[2 * LS], 3);
+        int ctx = min((mag + 1) >> 1, 4);
+        if (l == 0 && c == 0) ctx = 0;
+        else ctx += (l + c < 2) ? 1 : ((l + c < 4) ? 6 : 21);
+        rate += rt->coeff_base[txs][ptype][ctx][min(level, 3)];
       }
-#pragma unroll
-      for (int cc = 0; cc < 4; cc++) {
-        const int c = c0 + cc;
-        const int si = N == 32 ? (int)(((cc < 2 ? wa : wb) >> (16 * (cc & 1))) & 0xffffu) : (int)((wa >> (8 * cc)) & 0xffu);
-        if (si >= eob) continue;
-        const int qv = qc[si];
-        const int level = abs(qv);
-        const uint8_t *L = lev + l * LS + c;
-        if (si == eob - 1) {
-          const int c4 = si == 0 ? 0 : (si <= N2 / 8 ? 1 : (si <= N2 / 4 ? 2 : 3));
-          rate += rt->coeff_base_eob[txs][ptype][c4][min(level, 3) - 1];
-        } else {
-          const int mag = min((int)L[1], 3) + min((int)L[LS], 3) + min((int)L[LS + 1], 3) + min((int)L[2], 3) + min((int)L[2 * LS], 3);
-          int ctx = min((mag + 1) >> 1, 4);
-          if (l == 0 && c == 0) ctx = 0;
-          else ctx += (l + c < 2) ? 1 : ((l + c < 4) ? 6 : 21);
-          rate += rt->coeff_base[txs][ptype][ctx][min(level, 3)];
-        }
-        if (level > 2) {
-          int mag = min((int)L[1], 15) + min((int)L[LS], 15) + min((int)L[LS + 1], 15);
-          mag = min((mag + 1) >> 1, 6);
-          const int bctx = (l == 0 && c == 0) ? mag : ((l < 2 && c < 2) ? mag + 7 : mag + 14);
-          rate += rt->coeff_br[txs][ptype][bctx][min(level - 3, 12)];
-          if (level > 14) rate += 256u * (uint32_t)(2 * (32 - __clz(level - 14)) - 1);   // golomb(level - 15)
-        }
-        if (level) rate += (si == 0) ? rt->dc_sign[ptype][0][qv < 0] : 256u;
+      if (level > 2) {
+        int mag = min((int)L[1], 15) + min((int)L[LS], 15) + min((int)L[LS + 1], 15);
+        mag = min((mag + 1) >> 1, 6);
+        const int bctx = (l == 0 && c == 0) ? mag : ((l < 2 && c < 2) ? mag + 7 : mag + 14);
+        rate += rt->coeff_br[txs][ptype][bctx][min(level - 3, 12)];
+        if (level > 14) rate += 256u * (uint32_t)(2 * (32 - __clz(level - 14)) - 1);   // golomb(level - 15)
       }
+      if (level) rate += (si == 0) ? rt->dc_sign[ptype][0][qc[si] < 0] : 256u;
     }
   }
   if (RATE) rate = group_sum<N>(rate);

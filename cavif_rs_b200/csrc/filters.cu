@@ -14,6 +14,9 @@
 
 #include "records.h"
 #include "rdo.h"
+#ifndef B200_EMU
+#include <mutex>
+#endif
 #ifdef B200_EMU
 #define B200_MARK_F(name, st) ((void)0)
 #else
@@ -147,6 +150,29 @@ constexpr int kFH = 7;                   // halo of the staged region: the deblo
 constexpr int kFW = 64 + 2 * kFH;        // staged rows / columns
 constexpr int kCdefTW = 80;              // row stride of the staged region in shared memory
 constexpr uint16_t kCdefNA = 0xFFFF;
+#ifndef B200_EMU
+// ---- TMA (cp.async.bulk.tensor) + mbarrier: the tensor-memory-access unit moves the (64 + 14)^2 region of a plane from
+// HBM / L2 into shared memory on its own - no address arithmetic, no load instructions, no registers of the SM - and signals
+// an mbarrier with the byte count when the tile has landed.  Out-of-frame parts of the box arrive as zeros.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(void *bar, uint32_t phase) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, int y, void *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+#endif
+constexpr int kTmaBoxW = 80, kTmaBoxH = kFW;   // box of the tensor map: 80 x 78 samples starting at (x0 - 8, y0 - 7)
 __device__ __forceinline__ int cdef_pixel_tile(const uint16_t *T, int lx, int ly, int pri, int sec, int dir, int damping, int cshift) {
   const uint16_t *c = T + (ly + kFH) * kCdefTW + lx + kFH;
   const int x = *c;
@@ -505,7 +531,7 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
 // strength index.  Phase 4: apply the winner into job.fin (if present).
 
 template <class PIX>
-__global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs) {
+__global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs, const unsigned char *tmaps /* CUtensorMap[job][3] of the rec planes, or null */) {
   const B200RdoJob &job = jobs[blockIdx.y];
   const B200Frame *f = &job.frame;
   const int nsb = f->sb_rows * f->sb_cols;
@@ -517,20 +543,55 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
   __shared__ int s_dir[64], s_var[64], s_skip[64], s_any;
   __shared__ unsigned long long s_sse[8];
   __shared__ int s_best;
-  __shared__ uint16_t s_px[3][kFW * kCdefTW];     // staged samples: rows y0-7 .. y0+70, columns x0-7 .. x0+70 (kCdefNA outside the frame)
+#ifdef B200_EMU
+  static uint16_t s_px[3][kFW * kCdefTW];         // staged samples: rows y0-7 .. y0+70, columns x0-7 .. x0+70 (kCdefNA outside the frame)
+#else
+  // dynamic shared memory: [3 planes] TMA landing zone (PIX, 80 x 78, 128-byte aligned) | [3 planes] working copy (uint16)
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  constexpr int kLand = ((kTmaBoxW * kTmaBoxH * (int)sizeof(PIX) + 127) / 128) * 128;
+  uint16_t (*s_px)[kFW * kCdefTW] = reinterpret_cast<uint16_t (*)[kFW * kCdefTW]>(dyn_smem + 3 * kLand);
+  __shared__ __align__(8) unsigned long long s_bar;
+#endif
   __shared__ uint8_t s_txs[20 * 20];              // tx_size of the 4x4 units (sbr*16 - 2 .. +17) x (sbc*16 - 2 .. +17)
   __shared__ int16_t s_off[8][2];                 // CDEF tap offsets in the staged region per direction
   if (tid < 16) s_off[tid >> 1][tid & 1] = (int16_t)(dv_cdef_dir[tid >> 1][tid & 1][0] * kCdefTW + dv_cdef_dir[tid >> 1][tid & 1][1]);
   if (tid == 0) s_any = 0;
   if (tid < 8) s_sse[tid] = 0;
-  for (int p = 0; p < f->planes; p++) {
-    const PIX *R = (const PIX *)job.rec[p];
-    for (int i = tid; i < kFW * kFW; i += 256) {
-      const int ty = i / kFW, tx = i % kFW;
-      const int yy = y0 - kFH + ty, xx = x0 - kFH + tx;
-      s_px[p][ty * kCdefTW + tx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (uint16_t)R[(size_t)yy * stride + xx] : kCdefNA;
+  bool staged = false;
+#ifndef B200_EMU
+  if (tmaps) {
+    // one thread arms the barrier with the byte count of the boxes and issues one tensor load per plane
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&s_bar, (uint32_t)(f->planes * kTmaBoxW * kTmaBoxH * (int)sizeof(PIX)));
+      for (int p = 0; p < f->planes; p++)
+        tma_load_2d(dyn_smem + p * kLand, tmaps + ((size_t)blockIdx.y * 3 + p) * 128, x0 - 8, y0 - kFH, &s_bar);
     }
+    // everybody waits for the bytes (bounded: a tile that never lands is a bug, not a hang)
+    unsigned spins = 0;
+    while (!mbar_try_wait(&s_bar, 0)) { if (++spins > (1u << 24)) __trap(); }
+    // landing zone (native width, zeros outside the frame) -> working copy (uint16, kCdefNA outside the frame)
+    for (int p = 0; p < f->planes; p++) {
+      const PIX *Lz = reinterpret_cast<const PIX *>(dyn_smem + p * kLand);
+      for (int i = tid; i < kFW * kFW; i += 256) {
+        const int ty = i / kFW, tx = i % kFW;
+        const int yy = y0 - kFH + ty, xx = x0 - kFH + tx;
+        s_px[p][ty * kCdefTW + tx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (uint16_t)Lz[ty * kTmaBoxW + tx + 1] : kCdefNA;
+      }
+    }
+    staged = true;
   }
+#endif
+  if (!staged)
+    for (int p = 0; p < f->planes; p++) {
+      const PIX *R = (const PIX *)job.rec[p];
+      for (int i = tid; i < kFW * kFW; i += 256) {
+        const int ty = i / kFW, tx = i % kFW;
+        const int yy = y0 - kFH + ty, xx = x0 - kFH + tx;
+        s_px[p][ty * kCdefTW + tx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (uint16_t)R[(size_t)yy * stride + xx] : kCdefNA;
+      }
+    }
   for (int i = tid; i < 400; i += 256) {
     const int r = sbr * 16 - 2 + i / 20, c = sbc * 16 - 2 + i % 20;
     s_txs[i] = (r >= 0 && r < f->mi_rows && c >= 0 && c < f->mi_cols) ? job.mi[r * f->mi_cols + c].tx_size : 0;
@@ -674,27 +735,49 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
 }
 
 #ifndef B200_EMU
-extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_sb, int with_lr, int high_bitdepth, void *stream, int *launched) {
+namespace {
+template <class PIX> size_t dbcdef_smem_bytes() {
+  return 3 * (size_t)(((kTmaBoxW * kTmaBoxH * (int)sizeof(PIX) + 127) / 128) * 128) + 3 * sizeof(uint16_t) * kFW * kCdefTW;
+}
+template <class PIX> void dbcdef_configure() {
+  static std::mutex mu;
+  static bool done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (done[dev & 63]) return;
+  cudaFuncSetAttribute(b200_dbcdef_kernel<PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dbcdef_smem_bytes<PIX>());
+  cudaFuncSetAttribute(b200_dbcdef_kernel<PIX>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  done[dev & 63] = true;
+}
+}  // namespace
+// d_tmaps: device array of CUtensorMap[n_jobs][3] describing the rec planes with an 80 x 78 box (b200_filters_tmap_box),
+// or NULL: the fused kernel then stages its region with ordinary loads.
+extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_sb, int with_lr, int high_bitdepth, const void *d_tmaps, void *stream,
+                                   int *launched) {
   if (launched) *launched = 0;
   if (n_jobs <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 g2(max_sb, n_jobs), g3(max_sb, n_jobs, 3);       // restoration units <= superblocks
   if (high_bitdepth) {
-    b200_dbcdef_kernel<uint16_t><<<g2, 256, 0, st>>>(d_jobs);
+    dbcdef_configure<uint16_t>();
+    b200_dbcdef_kernel<uint16_t><<<g2, 256, dbcdef_smem_bytes<uint16_t>(), st>>>(d_jobs, (const unsigned char *)d_tmaps);
     B200_MARK_F("deblock_cdef", st);
     if (with_lr) { b200_lr_kernel<uint16_t><<<g3, 256, 0, st>>>(d_jobs); B200_MARK_F("lr_search", st); }
   } else {
-    b200_dbcdef_kernel<uint8_t><<<g2, 256, 0, st>>>(d_jobs);
+    dbcdef_configure<uint8_t>();
+    b200_dbcdef_kernel<uint8_t><<<g2, 256, dbcdef_smem_bytes<uint8_t>(), st>>>(d_jobs, (const unsigned char *)d_tmaps);
     B200_MARK_F("deblock_cdef", st);
     if (with_lr) { b200_lr_kernel<uint8_t><<<g3, 256, 0, st>>>(d_jobs); B200_MARK_F("lr_search", st); }
   }
   if (launched) *launched = 1 + (with_lr ? 1 : 0);
   return (int)cudaGetLastError();
 }
+extern "C" void b200_filters_tmap_box(int *box_w, int *box_h) { *box_w = kTmaBoxW; *box_h = kTmaBoxH; }
 #else
 static const B200RdoJob *g_f_jobs;
 static bool emu_hbd() { return g_f_jobs[0].frame.bit_depth > 8; }
-static void emu_cdef_entry(void *) { if (emu_hbd()) b200_dbcdef_kernel<uint16_t>(g_f_jobs); else b200_dbcdef_kernel<uint8_t>(g_f_jobs); }
+static void emu_cdef_entry(void *) { if (emu_hbd()) b200_dbcdef_kernel<uint16_t>(g_f_jobs, nullptr); else b200_dbcdef_kernel<uint8_t>(g_f_jobs, nullptr); }
 static void emu_lr_entry(void *) { if (emu_hbd()) b200_lr_kernel<uint16_t>(g_f_jobs); else b200_lr_kernel<uint8_t>(g_f_jobs); }
 extern "C" int b200_filters_launch_emu(const B200RdoJob *jobs, int max_sb) {
   g_f_jobs = jobs;

@@ -57,7 +57,9 @@ size_t b200_recon_smem_bytes(int high_bitdepth, int top_level, int rows);
 typedef struct B200StreamRegionH { const int16_t *src; const uint32_t *len; } B200StreamRegionH;   // device pointers
 int b200_stream_gather_launch(const void *d_regions, int n_regions, uint32_t *d_offsets /* n + 1 */, int16_t *out, uint32_t capacity, void *stream);
 // Fused deblocking + CDEF search (1 launch) + loop-restoration search (1 launch when with_lr) for all jobs: grid.y = job.
-int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_sb, int with_lr, int high_bitdepth, void *stream, int *launched);
+// d_tmaps: CUtensorMap[n_jobs][3] of the rec planes (box from b200_filters_tmap_box; coordinates in samples), or NULL
+int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_sb, int with_lr, int high_bitdepth, const void *d_tmaps, void *stream, int *launched);
+void b200_filters_tmap_box(int *box_w, int *box_h);
 
 #ifdef __cplusplus
 }
