@@ -56,7 +56,7 @@ __constant__ const uint8_t dv_sm_weights[4 + 8 + 16 + 32] = {255, 149, 85, 64, 2
                                                              255, 225, 196, 170, 145, 123, 102, 84, 68, 54, 43, 33, 26, 20, 17, 16,
                                                              255, 240, 225, 210, 196, 182, 169, 157, 145, 133, 122, 111, 101, 92, 83, 74,
                                                              66, 59, 52, 45, 39, 34, 29, 25, 21, 17, 14, 12, 10, 9, 8, 8};
-__constant__ const uint8_t dv_tx_types[5] = {TX_DCT_DCT, TX_ADST_DCT, TX_DCT_ADST, TX_ADST_ADST, TX_IDTX};
+__constant__ const uint8_t dv_tx_types[B200_TX_TYPES] = {B200_TX_TYPE_LIST};
 
 // Per-warp working set.  NMAX = largest block size the kernel instance handles; PIX = sample type of the planes
 // (uint8_t for 8-bit video, uint16_t for 10-bit): 16 / u8: 6.6 KB, 16 / u16: 8.7 KB, 32 / u8: 16.1 KB, 32 / u16: 22.9 KB.
@@ -116,6 +116,11 @@ template <int N> __device__ __forceinline__ void scan_row_load(int l, ScanRow<N>
 }
 template <int N> __device__ __forceinline__ int scan_row_at(const ScanRow<N> &r, int c) {
   return N == 32 ? (int)((r.w[c >> 1] >> (16 * (c & 1))) & 0xffffu) : (int)((r.w[c >> 2] >> (8 * (c & 3))) & 0xffu);
+}
+// scan index of coefficient (row l, column c) [pos = l * N + c] for a transform class: default scan for the 2-D class, row by
+// row for TX_CLASS_VERT (mrow), column by column for TX_CLASS_HORIZ (mcol): AV1 spec get_scan(), oracle scan_pos()
+template <int N> __device__ __forceinline__ int scan_index(int txc, int pos, int l, int c) {
+  return txc == 0 ? iscan_at<N>(pos) : (txc == 2 ? pos : c * N + l);
 }
 __device__ __forceinline__ int ilog2_dev(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
@@ -246,8 +251,9 @@ __device__ __forceinline__ int pred_px(int mode, int delta, int n, int i, int j,
 // ---- 1-D transforms on register arrays -----------------------------------------------------
 enum { K_DCT = 0, K_ADST = 1, K_IDT = 2 };
 __device__ __forceinline__ void tx_kernels(int tx_type, int &vert, int &horz) {
-  vert = (tx_type == TX_ADST_DCT || tx_type == TX_ADST_ADST) ? K_ADST : (tx_type == TX_IDTX ? K_IDT : K_DCT);
-  horz = (tx_type == TX_DCT_ADST || tx_type == TX_ADST_ADST) ? K_ADST : (tx_type == TX_IDTX ? K_IDT : K_DCT);
+  // V_DCT: DCT down the columns, identity along the rows; H_DCT: the other way round
+  vert = (tx_type == TX_ADST_DCT || tx_type == TX_ADST_ADST) ? K_ADST : ((tx_type == TX_IDTX || tx_type == TX_H_DCT) ? K_IDT : K_DCT);
+  horz = (tx_type == TX_DCT_ADST || tx_type == TX_ADST_ADST) ? K_ADST : ((tx_type == TX_IDTX || tx_type == TX_V_DCT) ? K_IDT : K_DCT);
 }
 __device__ __forceinline__ int32_t round_shift64(long long v, int bit) { return (int32_t)((v + (1ll << (bit - 1))) >> bit); }
 
@@ -383,6 +389,7 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
   }
   // ---- quantise / dequantise row l in place (oracle quantize()); exact division by reciprocal multiplication
   int eob = 0;
+  const int txc = plane == 0 ? b200_tx_class(tx_type) : 0;      // transform class: scan order and coefficient contexts
   {
     const uint32_t dc_q = (uint32_t)f->dc_q, ac_q = (uint32_t)f->ac_q;
     const uint32_t dc_rcp = 0xffffffffu / dc_q, ac_rcp = 0xffffffffu / ac_q;
@@ -399,7 +406,7 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
       if (rem >= q) lv++;
       if (lv > 32767) lv = 32767;
       const int32_t dqa = (int32_t)((lv * q) & 0xFFFFFF) >> qshift;
-      const int si = iscan_at<N>(pos);
+      const int si = scan_index<N>(txc, pos, l, c);
       qc[si] = (int16_t)(cf < 0 ? -(int)lv : (int)lv);
       buf[l * S + c] = cf < 0 ? -dqa : dqa;
       lev[l * LS + c] = (uint8_t)(lv > 127 ? 127 : lv);
@@ -422,7 +429,7 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
       int tg = 0;
       while (tg < 11 && (tg == 0 ? 1 : (tg == 1 ? 2 : (1 << (tg - 1)) + 1)) <= eob) tg++;   // group_start[tg + 1] <= eob
       const int gstart = tg < 3 ? tg : (1 << (tg - 2)) + 1;                                 // group_start[tg]
-      rate += rt->eob_pt[txs][ptype][tg - 1];
+      rate += rt->eob_pt[txs][ptype][txc != 0][tg - 1];
       const int nb = tg < 3 ? 0 : tg - 2;
       if (nb > 0) {
         const int extra = eob - gstart;
@@ -433,7 +440,7 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
 #pragma unroll 1
     for (int c = 0; c < N; c++) {
       const int pos = l * N + c;
-      const int si = iscan_at<N>(pos);
+      const int si = scan_index<N>(txc, pos, l, c);
       if (si >= eob) continue;
       const int level = abs((int)qc[si]);
       const uint8_t *L = lev + l * LS + c;
@@ -441,16 +448,23 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
         const int c4 = si == 0 ? 0 : (si <= N2 / 8 ? 1 : (si <= N2 / 4 ? 2 : 3));
         rate += rt->coeff_base_eob[txs][ptype][c4][min(level, 3) - 1];
       } else {
-        const int mag = min((int)L[1], 3) + min((int)L[LS], 3) + min((int)L[LS + 1], 3) + min((int)L[2], 3) + min((int)L[2 * LS], 3);
+        // neighbourhood and offset by transform class (AV1 spec Sig_Ref_Diff_Offset / Coeff_Base_Pos_Ctx_Offset; oracle coef_rate)
+        int mag = min((int)L[1], 3) + min((int)L[LS], 3);
+        if (txc == 0) mag += min((int)L[LS + 1], 3) + min((int)L[2], 3) + min((int)L[2 * LS], 3);
+        else if (txc == 1) mag += min((int)L[2], 3) + min((int)L[3], 3) + min((int)L[4], 3);
+        else mag += min((int)L[2 * LS], 3) + min((int)L[3 * LS], 3) + min((int)L[4 * LS], 3);
         int ctx = min((mag + 1) >> 1, 4);
-        if (l == 0 && c == 0) ctx = 0;
-        else ctx += (l + c < 2) ? 1 : ((l + c < 4) ? 6 : 21);
+        if (txc == 0) {
+          if (l == 0 && c == 0) ctx = 0;
+          else ctx += (l + c < 2) ? 1 : ((l + c < 4) ? 6 : 21);
+        } else ctx += 26 + 5 * min(txc == 2 ? l : c, 2);
         rate += rt->coeff_base[txs][ptype][ctx][min(level, 3)];
       }
       if (level > 2) {
-        int mag = min((int)L[1], 15) + min((int)L[LS], 15) + min((int)L[LS + 1], 15);
+        int mag = min((int)L[1], 15) + min((int)L[LS], 15) + min((int)(txc == 0 ? L[LS + 1] : (txc == 1 ? L[2] : L[2 * LS])), 15);
         mag = min((mag + 1) >> 1, 6);
-        const int bctx = (l == 0 && c == 0) ? mag : ((l < 2 && c < 2) ? mag + 7 : mag + 14);
+        const bool near = txc == 0 ? (l < 2 && c < 2) : (txc == 1 ? c == 0 : l == 0);
+        const int bctx = (l == 0 && c == 0) ? mag : (near ? mag + 7 : mag + 14);
         rate += rt->coeff_br[txs][ptype][bctx][min(level - 3, 12)];
         if (level > 14) rate += 256u * (uint32_t)(2 * (32 - __clz(level - 14)) - 1);   // golomb(level - 15)
       }

@@ -78,7 +78,7 @@ extern "C" int b200av1_frame_setup(B200Frame *f, int width, int height, int bit_
   f->rdo_tx_decision = 1;
   f->fine_directional_intra = 1;
   f->enable_cfl = 1;
-  f->y_mode_mask = 0x1fff; f->uv_mode_mask = 0x1fff; f->tx_type_mask = 0x1f;
+  f->y_mode_mask = 0x1fff; f->uv_mode_mask = 0x1fff; f->tx_type_mask = 0x7f;
   // In-loop filter strengths: closed-form picks from the quantiser (encoder freedom; the filters themselves
   // are normative).  Deblock level: libaom's "pick from q" fit; CDEF: one frame-wide strength pair.
   {
@@ -149,10 +149,12 @@ extern "C" void b200av1_build_rate_tables(int base_q_idx, B200RateTables *t) {
   }
   for (int s = 0; s < 5; s++) for (int c = 0; c < 13; c++) cdf_costs(av1_default_txb_skip_cdf[q][s][c], 2, t->txb_skip[s][c]);
   for (int p = 0; p < 2; p++) {
-    cdf_costs(av1_default_eob_multi16_cdf[q][p][0], 5, t->eob_pt[0][p]);
-    cdf_costs(av1_default_eob_multi64_cdf[q][p][0], 7, t->eob_pt[1][p]);
-    cdf_costs(av1_default_eob_multi256_cdf[q][p][0], 9, t->eob_pt[2][p]);
-    cdf_costs(av1_default_eob_multi1024_cdf[q][p][0], 11, t->eob_pt[3][p]);
+    for (int c = 0; c < 2; c++) {
+      cdf_costs(av1_default_eob_multi16_cdf[q][p][c], 5, t->eob_pt[0][p][c]);
+      cdf_costs(av1_default_eob_multi64_cdf[q][p][c], 7, t->eob_pt[1][p][c]);
+      cdf_costs(av1_default_eob_multi256_cdf[q][p][c], 9, t->eob_pt[2][p][c]);
+      cdf_costs(av1_default_eob_multi1024_cdf[q][p][c], 11, t->eob_pt[3][p][c]);
+    }
   }
   for (int s = 0; s < 5; s++) for (int p = 0; p < 2; p++) for (int c = 0; c < 9; c++)
     cdf_costs(av1_default_eob_extra_cdf[q][s][p][c], 2, t->eob_extra[s][p][c]);

@@ -329,7 +329,8 @@ struct TilePacker {
       eob_pt = t;   // eob 1 -> 1, 2 -> 2, 3..4 -> 3, ...
       eob_extra = eob - group_start[t];
     }
-    const int eob_multi_ctx = 0;   // 2-D transform class only
+    const int txc = plane == 0 ? b200_tx_class(tx_type) : 0;      // transform class (spec get_tx_class): 0 2-D, 1 HORIZ, 2 VERT
+    const int eob_multi_ctx = txc != 0;
     switch (txs) {
       case TX_4X4: sym(eob_pt - 1, cdf.eob_multi16[ptype][eob_multi_ctx], 5); break;
       case TX_8X8: sym(eob_pt - 1, cdf.eob_multi64[ptype][eob_multi_ctx], 7); break;
@@ -351,32 +352,40 @@ struct TilePacker {
     const int stride = n + 4;
     uint8_t levels[(32 + 4) * (32 + 4)];
     memset(levels, 0, (size_t)stride * (n + 4));
+    // scan (spec get_scan): default for the 2-D class, row by row (mrow) for TX_CLASS_VERT, column by column (mcol) for HORIZ
+    auto scan_pos = [&](int i) -> int { return txc == 0 ? scan[i] : (txc == 2 ? i : (i % n) * n + i / n); };
     for (int i = 0; i < eob; i++) {
-      const int pos = scan[i], r = pos / n, c = pos % n;
+      const int pos = scan_pos(i), r = pos / n, c = pos % n;
       const int a = abs(qc[i]);
       levels[r * stride + c] = (uint8_t)std::min(a, 127);
     }
     const int log2n = 2 + txs;
     // --- base levels, reverse scan
     for (int i = eob - 1; i >= 0; i--) {
-      const int pos = scan[i], r = pos >> log2n, c = pos & (n - 1);
+      const int pos = scan_pos(i), r = pos >> log2n, c = pos & (n - 1);
       const int level = abs(qc[i]);
       const uint8_t *L = levels + r * stride + c;
       if (i == eob - 1) {
         const int c4 = i == 0 ? 0 : (i <= (n * n) / 8 ? 1 : (i <= (n * n) / 4 ? 2 : 3));
         sym(std::min(level, 3) - 1, cdf.coeff_base_eob[txs_ctx][ptype][c4], 3);
       } else {
-        int mag = std::min<int>(L[1], 3) + std::min<int>(L[stride], 3) + std::min<int>(L[stride + 1], 3) +
-                  std::min<int>(L[2], 3) + std::min<int>(L[2 * stride], 3);
+        // neighbourhood / offset by transform class (spec Sig_Ref_Diff_Offset, Coeff_Base_Ctx_Offset, Coeff_Base_Pos_Ctx_Offset)
+        int mag = std::min<int>(L[1], 3) + std::min<int>(L[stride], 3);
+        if (txc == 0) mag += std::min<int>(L[stride + 1], 3) + std::min<int>(L[2], 3) + std::min<int>(L[2 * stride], 3);
+        else if (txc == 1) mag += std::min<int>(L[2], 3) + std::min<int>(L[3], 3) + std::min<int>(L[4], 3);
+        else mag += std::min<int>(L[2 * stride], 3) + std::min<int>(L[3 * stride], 3) + std::min<int>(L[4 * stride], 3);
         int cctx = std::min((mag + 1) >> 1, 4);
-        if (r == 0 && c == 0) cctx = 0;
-        else cctx += (r + c < 2) ? 1 : (r + c < 4) ? 6 : 21;
+        if (txc == 0) {
+          if (r == 0 && c == 0) cctx = 0;
+          else cctx += (r + c < 2) ? 1 : (r + c < 4) ? 6 : 21;
+        } else cctx += 26 + 5 * std::min(txc == 2 ? r : c, 2);
         sym(std::min(level, 3), cdf.coeff_base[txs_ctx][ptype][cctx], 4);
       }
       if (level > 2) {
-        int mag = std::min<int>(L[1], 15) + std::min<int>(L[stride], 15) + std::min<int>(L[stride + 1], 15);
+        int mag = std::min<int>(L[1], 15) + std::min<int>(L[stride], 15) + std::min<int>(txc == 0 ? L[stride + 1] : (txc == 1 ? L[2] : L[2 * stride]), 15);
         mag = std::min((mag + 1) >> 1, 6);
-        int bctx = (r == 0 && c == 0) ? mag : ((r < 2 && c < 2) ? mag + 7 : mag + 14);
+        const bool near = txc == 0 ? (r < 2 && c < 2) : (txc == 1 ? c == 0 : r == 0);
+        int bctx = (r == 0 && c == 0) ? mag : (near ? mag + 7 : mag + 14);
         uint16_t *bc = cdf.coeff_br[std::min(txs_ctx, 3)][ptype][bctx];
         const int base_range = level - 1 - 2;
         for (int idx = 0; idx < 12; idx += 3) {

@@ -167,6 +167,11 @@ __device__ __forceinline__ bool mbar_try_wait(void *bar, uint32_t phase) {
   asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
   return ok != 0;
 }
+// A tensor map that lives in GLOBAL memory is read through the tensor-map proxy, which caches descriptors by address: the
+// arena re-uses addresses from call to call with new contents, so the issuing thread first acquires the 128 bytes.
+__device__ __forceinline__ void tmap_acquire(const void *tmap) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, int y, void *bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
@@ -565,8 +570,11 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
     __syncthreads();
     if (tid == 0) {
       mbar_expect_tx(&s_bar, (uint32_t)(f->planes * kTmaBoxW * kTmaBoxH * (int)sizeof(PIX)));
-      for (int p = 0; p < f->planes; p++)
-        tma_load_2d(dyn_smem + p * kLand, tmaps + ((size_t)blockIdx.y * 3 + p) * 128, x0 - 8, y0 - kFH, &s_bar);
+      for (int p = 0; p < f->planes; p++) {
+        const unsigned char *tm = tmaps + ((size_t)blockIdx.y * 3 + p) * 128;
+        tmap_acquire(tm);
+        tma_load_2d(dyn_smem + p * kLand, tm, x0 - 8, y0 - kFH, &s_bar);
+      }
     }
     // everybody waits for the bytes (bounded: a tile that never lands is a bug, not a hang)
     unsigned spins = 0;

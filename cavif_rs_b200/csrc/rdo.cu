@@ -81,10 +81,10 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, SH &sh, int x, i
     my_ycost = (long long)satd[lane] * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, lane, n, DELTA_Y(lane))) >> 8);
   int m0, m1;
   rank_top2(my_ycost, m0, m1);
-  // ---- luma full trials: candidate c = k * 5 + ti; lane batches pair the two modes on the same transform type
-  const int tx_mask = n == 32 ? 1 : f->tx_type_mask;      // 32x32: the intra transform set is DCT only
+  // ---- luma full trials: candidate c = k * B200_TX_TYPES + ti; lane batches pair the two modes on the same transform type
+  const int tx_mask = b200_tx_mask_for(f->tx_type_mask, f->reduced_tx_set, n);      // 32x32: DCT only; 1-D DCTs: 7-type set only
   int first_t = -1;
-  for (int k = 0; k < 5; k++) if ((tx_mask >> k) & 1) { first_t = k; break; }
+  for (int k = 0; k < B200_TX_TYPES; k++) if ((tx_mask >> k) & 1) { first_t = k; break; }
   // open loop: the neighbours' modes are not decided yet, the trials assume filter type 0 (oracle)
   const int ief = f->enable_intra_edge_filter ? 0 : -1;
   predict_any(sh, ief, m0 >= 0 ? m0 : 0, DELTA_Y(m0 >= 0 ? m0 : 0), lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred);
@@ -94,12 +94,12 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, SH &sh, int x, i
   int bestC = 1 << 20, bestEob = 0;
   bool skip_rest = false;      // every first-type trial quantised to all-zero: the other transform types are not tried
 #pragma unroll 1
-  for (int b = 0; b * G < 10 && (SYNC || !skip_rest); b++) {
+  for (int b = 0; b * G < 2 * B200_TX_TYPES && (SYNC || !skip_rest); b++) {
     if (SYNC) { __syncthreads(); if (skip_rest) continue; }
     const int ci = b * G + g;
     const int ti = ci >> 1, k = ci & 1;
     const int m = k == 0 ? m0 : m1;
-    bool ok = ti < 5 && m >= 0 && ((tx_mask >> ti) & 1) && (f->rdo_tx_decision || ti == first_t);
+    bool ok = ti < B200_TX_TYPES && m >= 0 && ((tx_mask >> ti) & 1) && (f->rdo_tx_decision || ti == first_t);
     if (!__ballot_sync(FULL, ok)) continue;
     const TrialOut r = trial_batch<n, HBD>(t, sh, 0, sh.src[0], sh.pred + (ok ? k : 0) * PS, dv_tx_types[ok ? ti : 0],
                                            ok ? m : (m0 >= 0 ? m0 : 0));
@@ -110,16 +110,16 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, SH &sh, int x, i
     }
     long long wj = kInf;
     int wc = 1 << 20;
-    if (ok) { wj = rd_cost(f, r.sse, r.rate + mode_rate(rt, ymode_cost, m, n, DELTA_Y(m))); wc = k * 5 + ti; }
+    if (ok) { wj = rd_cost(f, r.sse, r.rate + mode_rate(rt, ymode_cost, m, n, DELTA_Y(m))); wc = k * B200_TX_TYPES + ti; }
     warp_argmin(wj, wc);
     if (wj < bestJ || (wj == bestJ && wc < bestC)) {
       bestJ = wj; bestC = wc;
-      const int wg = (wc % 5) * 2 + wc / 5 - b * G;
+      const int wg = (wc % B200_TX_TYPES) * 2 + wc / B200_TX_TYPES - b * G;
       bestEob = __shfl_sync(FULL, r.eob, wg << lg);
     }
   }
-  const int best_mode = bestC / 5 == 0 ? m0 : m1;
-  const int best_tt = dv_tx_types[bestC % 5];
+  const int best_mode = bestC / B200_TX_TYPES == 0 ? m0 : m1;
+  const int best_tt = dv_tx_types[bestC % B200_TX_TYPES];
   long long total = bestJ;
   int uv_best = DC_PRED, eobU = 0, eobV = 0, cfl_js = 0, cfl_idx = 0;
   if (planes > 1) {

@@ -133,6 +133,7 @@ __device__ __noinline__ int recon_tx(const B200Frame *f, bool active, const PIX 
     const uint32_t ac_rcp = 0xffffffffu / ac_q, ac_off = (ac_q * 98) >> 8;
     ScanRow<N> srow;
     scan_row_load<N>(l, srow);
+    const int txc = b200_tx_class(tx_type);      // chroma never uses the 1-D types (tx type derived from the uv mode)
 #pragma unroll
     for (int c = 0; c < N; c++) {
       uint32_t q = ac_q, rcp = ac_rcp, off = ac_off;
@@ -145,7 +146,7 @@ __device__ __noinline__ int recon_tx(const B200Frame *f, bool active, const PIX 
       if (rem >= q) lv++;
       if (lv > 32767) lv = 32767;
       const int32_t dqa = (int32_t)((lv * q) & 0xFFFFFF) >> qshift;
-      const int si = scan_row_at<N>(srow, c);
+      const int si = txc == 0 ? scan_row_at<N>(srow, c) : (txc == 2 ? l * N + c : c * N + l);
       qc[si] = (int16_t)(cf < 0 ? -(int)lv : (int)lv);
       v[c] = clamp_bits(cf < 0 ? -dqa : dqa, bd + 8);
       if (lv) eob = max(eob, si + 1);

@@ -27,7 +27,18 @@ enum {
   DC_PRED = 0, V_PRED, H_PRED, D45_PRED, D135_PRED, D113_PRED, D157_PRED, D203_PRED, D67_PRED,
   SMOOTH_PRED, SMOOTH_V_PRED, SMOOTH_H_PRED, PAETH_PRED, UV_CFL_PRED = 13
 };
-enum { TX_DCT_DCT = 0, TX_ADST_DCT = 1, TX_DCT_ADST = 2, TX_ADST_ADST = 3, TX_IDTX = 9 };
+enum { TX_DCT_DCT = 0, TX_ADST_DCT = 1, TX_DCT_ADST = 2, TX_ADST_ADST = 3, TX_IDTX = 9, TX_V_DCT = 10, TX_H_DCT = 11 };
+// searched luma transform types in candidate order (bit k of B200Frame.tx_type_mask enables entry k).  Entries 5 and 6 (the
+// 1-D DCTs) exist only in the 7-type intra set: transforms up to 8x8 when reduced_tx_set is off (AV1 spec get_tx_set).
+#define B200_TX_TYPES 7
+#define B200_TX_TYPE_LIST TX_DCT_DCT, TX_ADST_DCT, TX_DCT_ADST, TX_ADST_ADST, TX_IDTX, TX_V_DCT, TX_H_DCT
+// transform class of a type (AV1 spec get_tx_class): 0 = 2-D, 1 = TX_CLASS_HORIZ (H_DCT: identity vertically), 2 = TX_CLASS_VERT
+static inline B200_HD int b200_tx_class(int tx_type) { return tx_type == TX_H_DCT ? 1 : (tx_type == TX_V_DCT ? 2 : 0); }
+// luma transform types a block of size n may use: the frame's mask, minus the 1-D DCTs where the 5-type set applies
+static inline B200_HD int b200_tx_mask_for(int tx_type_mask, int reduced_tx_set, int n) {
+  if (n >= 32) return 1;
+  return (reduced_tx_set || n >= 16) ? (tx_type_mask & 0x1f) : tx_type_mask;
+}
 
 #define B200_MAX_TILE_COLS 64
 #define B200_MAX_TILE_ROWS 64
@@ -70,7 +81,7 @@ typedef struct B200Frame {
   int32_t lambda_q8;                        // RD multiplier: J = (SSE << 8) + ((lambda_q8 * R_q8) >> 8), R in 1/256 bit
   int32_t lambda_satd_q8;                   // pre-ranking: J = satd * 64 + ((lambda_satd_q8 * R_q8) >> 8)
   int32_t y_mode_mask, uv_mode_mask;        // allowed intra modes (bit = mode index); conformance tests force single modes
-  int32_t tx_type_mask;                     // allowed luma transform types: bit0 DCT_DCT 1 ADST_DCT 2 DCT_ADST 3 ADST_ADST 4 IDTX
+  int32_t tx_type_mask;                     // allowed luma transform types: bit0 DCT_DCT 1 ADST_DCT 2 DCT_ADST 3 ADST_ADST 4 IDTX 5 V_DCT 6 H_DCT
   // early termination of the partition search: the children of a block are not analysed when its own RD cost is at
   // most split_gate_bits * lambda ([0]: 8x8 -> 4x4, [1]: 16x16 -> 8x8, [2]: 32x32 -> 16x16; 0 = exhaustive search)
   int32_t split_gate_bits[3];
@@ -129,7 +140,7 @@ typedef struct B200RateTables {
   uint16_t cfl_alpha[6][16];
   uint16_t intra_tx[2][4][13][16];          // [0: 7-type set, 1: 5-type set][tx size][y mode][tx_type]
   uint16_t txb_skip[5][13][2];
-  uint16_t eob_pt[4][2][12];                // [TX_4X4..TX_32X32][plane type][eob_pt - 1]
+  uint16_t eob_pt[4][2][2][12];             // [TX_4X4..TX_32X32][plane type][0: 2-D transform class, 1: 1-D class][eob_pt - 1]
   uint16_t eob_extra[5][2][9][2];
   uint16_t dc_sign[2][3][2];
   uint16_t coeff_base_eob[5][2][4][3];

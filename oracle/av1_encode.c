@@ -306,13 +306,18 @@ static uint32_t satd4(const uint16_t *src, int sstride, const uint16_t *pred, in
 }
 
 /* quantise -> levels in scan order + eob; dequantise -> dq (row-major).  Levels clamped to int16. */
-static int quantize(const B200Frame *f, const int32_t *coef, int n, int16_t *qc_scan, int32_t *dq) {
+/* coefficient position (row-major) of scan index i: default zig-zag-like scan for the 2-D transform class, row by row
+ * (mrow) for TX_CLASS_VERT (V_DCT), column by column (mcol) for TX_CLASS_HORIZ (H_DCT): AV1 spec get_scan() */
+static inline int scan_pos(const uint16_t *scan, int n, int tx_class, int i) {
+  return tx_class == 0 ? scan[i] : (tx_class == 2 ? i : (i % n) * n + i / n);
+}
+static int quantize(const B200Frame *f, const int32_t *coef, int n, int tx_type, int16_t *qc_scan, int32_t *dq) {
   const uint16_t *scan = scan_for(n);
-  const int n2 = n * n;
+  const int n2 = n * n, txc = b200_tx_class(tx_type);
   int eob = 0;
   const int shift = n == 32 ? 1 : 0;   /* 32x32: forward scale is half, dequant >> 1 */
   for (int i = 0; i < n2; i++) {
-    const int pos = scan[i];
+    const int pos = scan_pos(scan, n, txc, i);
     const int q = pos == 0 ? f->dc_q : f->ac_q;
     const int off = pos == 0 ? (q * 109) >> 8 : (q * 98) >> 8;
     const int32_t c = coef[pos];
@@ -339,7 +344,8 @@ static uint32_t coef_rate(const enc_t *e, int plane, int n, int tx_type, int y_m
   static const int8_t offset_bits[12] = {0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9};
   int t = 0;
   while (t < 11 && group_start[t + 1] <= eob) t++;
-  r += rt->eob_pt[txs][ptype][t - 1];
+  const int txc = b200_tx_class(tx_type);
+  r += rt->eob_pt[txs][ptype][txc != 0][t - 1];
   if (offset_bits[t] > 0) {
     const int extra = eob - group_start[t], nb = offset_bits[t];
     r += rt->eob_extra[txs][ptype][t - 3][(extra >> (nb - 1)) & 1];
@@ -350,12 +356,12 @@ static uint32_t coef_rate(const enc_t *e, int plane, int n, int tx_type, int y_m
   uint8_t lev[36 * 36];
   memset(lev, 0, (size_t)stride * (n + 4));
   for (int i = 0; i < eob; i++) {
-    const int pos = scan[i];
+    const int pos = scan_pos(scan, n, txc, i);
     const int a = abs(qc[i]);
     lev[(pos / n) * stride + pos % n] = (uint8_t)(a > 127 ? 127 : a);
   }
   for (int i = eob - 1; i >= 0; i--) {
-    const int pos = scan[i], rr = pos / n, cc = pos % n;
+    const int pos = scan_pos(scan, n, txc, i), rr = pos / n, cc = pos % n;
     const int level = abs(qc[i]);
     const uint8_t *L = lev + rr * stride + cc;
 #define M3(v) ((v) > 3 ? 3 : (v))
@@ -364,18 +370,28 @@ static uint32_t coef_rate(const enc_t *e, int plane, int n, int tx_type, int y_m
       const int c4 = i == 0 ? 0 : (i <= (n * n) / 8 ? 1 : (i <= (n * n) / 4 ? 2 : 3));
       r += rt->coeff_base_eob[txs][ptype][c4][M3(level) - 1];
     } else {
-      const int mag = M3(L[1]) + M3(L[stride]) + M3(L[stride + 1]) + M3(L[2]) + M3(L[2 * stride]);
+      /* neighbourhood and offset by transform class (AV1 spec Sig_Ref_Diff_Offset / Coeff_Base_Pos_Ctx_Offset) */
+      int mag = M3(L[1]) + M3(L[stride]);
+      if (txc == 0) mag += M3(L[stride + 1]) + M3(L[2]) + M3(L[2 * stride]);
+      else if (txc == 1) mag += M3(L[2]) + M3(L[3]) + M3(L[4]);
+      else mag += M3(L[2 * stride]) + M3(L[3 * stride]) + M3(L[4 * stride]);
       int ctx = (mag + 1) >> 1;
       if (ctx > 4) ctx = 4;
-      if (rr == 0 && cc == 0) ctx = 0;
-      else ctx += (rr + cc < 2) ? 1 : (rr + cc < 4) ? 6 : 21;
+      if (txc == 0) {
+        if (rr == 0 && cc == 0) ctx = 0;
+        else ctx += (rr + cc < 2) ? 1 : (rr + cc < 4) ? 6 : 21;
+      } else {
+        const int idx = txc == 2 ? rr : cc;
+        ctx += 26 + 5 * (idx > 2 ? 2 : idx);
+      }
       r += rt->coeff_base[txs][ptype][ctx][M3(level)];
     }
     if (level > 2) {
-      int mag = M15(L[1]) + M15(L[stride]) + M15(L[stride + 1]);
+      int mag = M15(L[1]) + M15(L[stride]) + M15(txc == 0 ? L[stride + 1] : (txc == 1 ? L[2] : L[2 * stride]));
       mag = (mag + 1) >> 1;
       if (mag > 6) mag = 6;
-      const int bctx = (rr == 0 && cc == 0) ? mag : ((rr < 2 && cc < 2) ? mag + 7 : mag + 14);
+      const int near = txc == 0 ? (rr < 2 && cc < 2) : (txc == 1 ? cc == 0 : rr == 0);
+      const int bctx = (rr == 0 && cc == 0) ? mag : (near ? mag + 7 : mag + 14);
       const int br = level - 3;
       r += rt->coeff_br[txs > 3 ? 3 : txs][ptype][bctx][br > 12 ? 12 : br];
       if (level > 14) {   /* golomb(level - 15): 2*len - 1 bits */
@@ -407,7 +423,7 @@ static uint64_t trial_plane(const enc_t *e, int plane, int x, int y, int n, cons
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++) resid[i * n + j] = (int16_t)((int)src[i * e->stride + j] - (int)pred[i * n + j]);
   orc_fwd_txfm2d(resid, n, coef, n, tx_type);
-  const int eob = quantize(f, coef, n, qc, dq);
+  const int eob = quantize(f, coef, n, tx_type, qc, dq);
   memcpy(recon, pred, sizeof(uint16_t) * n * n);
   if (eob) orc_inv_txfm2d_add(dq, recon, n, n, tx_type, f->bit_depth);
   *eob_out = (uint16_t)eob;
@@ -419,7 +435,7 @@ static inline int64_t rd_cost(const B200Frame *f, uint64_t sse, uint32_t rate) {
   return (int64_t)(sse << 8) + (((int64_t)f->lambda_q8 * (int64_t)rate) >> 8);
 }
 
-static const uint8_t k_tx_types[5] = {TX_DCT_DCT, TX_ADST_DCT, TX_DCT_ADST, TX_ADST_ADST, TX_IDTX};
+static const uint8_t k_tx_types[B200_TX_TYPES] = {B200_TX_TYPE_LIST};
 
 /* chroma transform type derived from the uv mode (AV1 spec get_tx_type for intra chroma),
  * restricted to what the (reduced) intra set allows for this size */
@@ -553,16 +569,16 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
   }
   /* luma trials: top-2 modes x allowed transform types; order (mode rank, type index), strict '<' keeps the earliest */
   /* 32x32: the intra transform set is DCT only (AV1 spec get_tx_set: no tx_type is coded) */
-  const int tx_mask = n == 32 ? 1 : f->tx_type_mask;
+  const int tx_mask = b200_tx_mask_for(f->tx_type_mask, f->reduced_tx_set, n);
   int first_tt = -1;
-  for (int k = 0; k < 5; k++) if ((tx_mask >> k) & 1) { first_tt = k_tx_types[k]; break; }
+  for (int k = 0; k < B200_TX_TYPES; k++) if ((tx_mask >> k) & 1) { first_tt = k_tx_types[k]; break; }
   int64_t bestJ = INT64_MAX;
   int best_mode = bm[0], best_tt = first_tt, eob_y = 0, best_c = 1 << 20;
   int16_t qc[1024];
   uint16_t recon[1024], eobv;
   /* pass 0: the first allowed transform type on both ranked modes; pass 1: the other types - skipped when every
    * first-type trial quantised to all-zero (nothing left for another transform to gain).  Winner = lowest J,
-   * ties -> lowest candidate index c = rank * 5 + type. */
+   * ties -> lowest candidate index c = rank * B200_TX_TYPES + type. */
   int all_first_zero = 1;
   for (int pass = 0; pass < 2; pass++) {
     if (pass == 1 && (all_first_zero || !(f->rdo_tx_decision && n <= 16))) break;
@@ -571,7 +587,7 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
       if (m < 0) continue;
       orc_predict_intra_ef(m, DELTA_Y(m), n, A[0], L[0], ha, hl, f->bit_depth, ief, pred);
       const uint32_t mrate = mode_rate(rt, ymode_cost, m, n, DELTA_Y(m));
-      for (int t = 0; t < 5; t++) {
+      for (int t = 0; t < B200_TX_TYPES; t++) {
         const int tt = k_tx_types[t];
         if (!((tx_mask >> t) & 1)) continue;
         if ((pass == 0) != (tt == first_tt)) continue;
@@ -579,7 +595,7 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
         const uint64_t d = trial_plane(e, 0, x, y, n, pred, tt, m, qc, &eobv, recon, &rate);
         if (pass == 0 && eobv) all_first_zero = 0;
         const int64_t J = rd_cost(f, d, rate + mrate);
-        const int c = k * 5 + t;
+        const int c = k * B200_TX_TYPES + t;
         if (J < bestJ || (J == bestJ && c < best_c)) { bestJ = J; best_c = c; best_mode = m; best_tt = tt; eob_y = eobv; }
       }
     }

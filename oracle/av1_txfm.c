@@ -15,7 +15,7 @@
 #include "../cavif_rs_b200/csrc/av1_tables.h"
 #include "txfm1d_gen.h"
 
-enum { DCT_DCT = 0, ADST_DCT = 1, DCT_ADST = 2, ADST_ADST = 3, IDTX = 9 };
+enum { DCT_DCT = 0, ADST_DCT = 1, DCT_ADST = 2, ADST_ADST = 3, IDTX = 9, V_DCT = 10, H_DCT = 11 };
 enum { T_DCT = 0, T_ADST = 1, T_IDT = 2 };
 
 /* vertical (column) kernel, horizontal (row) kernel for a tx_type */
@@ -25,6 +25,8 @@ static void tx_kernels(int tx_type, int *vert, int *horz) {
     case ADST_DCT: *vert = T_ADST; *horz = T_DCT; break;
     case DCT_ADST: *vert = T_DCT; *horz = T_ADST; break;
     case ADST_ADST: *vert = T_ADST; *horz = T_ADST; break;
+    case V_DCT: *vert = T_DCT; *horz = T_IDT; break;      /* DCT down the columns, identity along the rows */
+    case H_DCT: *vert = T_IDT; *horz = T_DCT; break;
     default: *vert = T_IDT; *horz = T_IDT; break;
   }
 }

@@ -27,7 +27,7 @@ class B200Records(ctypes.Structure):
                 ("cdef_idx", ctypes.c_void_p), ("lr", ctypes.c_void_p * 3)]
 
 RATE_TABLES_BYTES = 2 * (20 * 10 + 3 * 2 + 5 * 5 * 13 + 2 * 13 * 14 + 8 * 7 + 8 + 6 * 16 + 2 * 4 * 13 * 16 + 5 * 13 * 2 +
-                         4 * 2 * 12 + 5 * 2 * 9 * 2 + 2 * 3 * 2 + 5 * 2 * 4 * 3 + 5 * 2 * 42 * 4 + 4 * 2 * 21 * 13)
+                         4 * 2 * 2 * 12 + 5 * 2 * 9 * 2 + 2 * 3 * 2 + 5 * 2 * 4 * 3 + 5 * 2 * 42 * 4 + 4 * 2 * 21 * 13)
 
 DEC_DTYPE = np.dtype([("cost", "<i8"), ("y_mode", "u1"), ("tx_type", "u1"), ("uv_mode", "u1"), ("all_zero", "u1"),
                       ("angle_y", "u1"), ("angle_uv", "u1"), ("cfl_js", "u1"), ("cfl_alpha", "u1")])

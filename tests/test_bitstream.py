@@ -50,6 +50,22 @@ def test_each_transform_type_and_size(size, tx):
     roundtrip(96, 64, txmask=1 << tx, pmin=size, pmax=size, rdo_tx=0)
 
 
+@pytest.mark.parametrize("depth", [8, 10])
+@pytest.mark.parametrize("size", [4, 8])
+@pytest.mark.parametrize("tx", [5, 6])
+def test_one_dimensional_dct_types_of_the_7_type_set(size, tx, depth):
+    """V_DCT / H_DCT (intra set of transforms up to 8x8 when reduced_tx_set is off, av1encoder.rs:581): their own scans (mrow /
+    mcol), coefficient contexts of the 1-D transform classes and the 7-symbol tx-type CDF, all decoded by dav1d"""
+    roundtrip(96, 64, depth=depth, txmask=1 << tx, pmin=size, pmax=size, rdo_tx=0, reduced=0)
+
+
+def test_seven_type_search_beats_or_equals_five_types():
+    """full search with the 7-type set on 4x4 / 8x8 transforms: decodes, and the RD search never does worse for having more types"""
+    s7, p7 = roundtrip(200, 136, txmask=0x7f, pmin=4, pmax=8, reduced=0, q=100)
+    s5, p5 = roundtrip(200, 136, txmask=0x1f, pmin=4, pmax=8, reduced=0, q=100)
+    assert s7 <= s5 * 1.01 or p7 >= p5
+
+
 @pytest.mark.parametrize("w,h", [(8, 8), (16, 300), (1000, 24), (129, 101), (128, 85), (72, 40), (200, 136)])
 def test_frame_edges_and_forced_splits(w, h):
     roundtrip(w, h)

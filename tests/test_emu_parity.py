@@ -67,6 +67,8 @@ def compare_analysis(ref, out, f):
     (96, 96, 10, 3, 1, dict(enable_intra_edge_filter=1, partition_max=32, y_mode_mask=0x1fe)),   # directional modes only, up to 32x32
     # coded size 8 mod 16 and wide: the root-region count (129) exceeds n_mi / 16 + 64 (128); every region must be decided
     (2056, 8, 8, 1, 1, dict(partition_min=8, rdo_tx_decision=0)),
+    (136, 88, 8, 3, 1, dict(reduced_tx_set=0)),                    # 7-type transform set on 4x4 / 8x8 (V_DCT, H_DCT: 1-D classes)
+    (96, 72, 10, 3, 2, dict(reduced_tx_set=0, partition_max=32, tx_type_mask=0x61)),   # DCT_DCT + the 1-D DCTs where they exist
       # 4 x 3 superblocks: the reconstruction wavefront waits on its neighbours
 ])
 def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw, rows):

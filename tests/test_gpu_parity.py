@@ -158,6 +158,8 @@ CASES = [
     (200, 136, 8, 3, 121, 2, dict(enable_intra_edge_filter=1)),         # intra edge filter / upsampling
     (256, 192, 10, 3, 100, 1, dict(enable_intra_edge_filter=1, partition_max=32, lr=1)),
     (136, 104, 8, 3, 150, 1, dict(enable_intra_edge_filter=1, y_mode_mask=0x1fe)),       # directional luma modes only
+    (320, 200, 8, 3, 100, 2, dict(reduced_tx_set=0)),                                    # 7-type transform set (V_DCT / H_DCT on 4x4, 8x8)
+    (200, 136, 10, 3, 66, 1, dict(reduced_tx_set=0, partition_max=32, tx_type_mask=0x61)),
 ]
 
 
