@@ -53,7 +53,7 @@ thread_local std::string g_err;
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 #define ARENA_CHECK(c) do { if ((c).dev.overflow || (c).pin.overflow) return fail(B200AVIF_ENCODING_ERROR, "internal error: work arena too small for this batch"); } while (0)
 
-std::atomic<uint64_t> g_launches{0}, g_h2d{0}, g_d2h{0};
+std::atomic<uint64_t> g_launches{0}, g_h2d{0}, g_d2h{0}, g_tma{0};
 std::mutex g_stat_mu;
 double g_ms_rdo = 0, g_ms_total = 0, g_ms_pack = 0;
 
@@ -197,9 +197,11 @@ TmapEncodeFn tmap_encoder() {
   return fn;
 }
 // 2-D map of one sample plane (coded width x height, `stride` samples per row), box = box_w x box_h samples, zero fill
-bool encode_plane_tmap(CUtensorMap *out, void *base, size_t bps, size_t cw, size_t ch, size_t stride, int box_w, int box_h) {
+// pair8: describe an 8-bit plane as 16-bit elements (half the width, half the box): same bytes, x coordinates halve
+bool encode_plane_tmap(CUtensorMap *out, void *base, size_t bps, size_t cw, size_t ch, size_t stride, int box_w, int box_h, bool pair8) {
   TmapEncodeFn fn = tmap_encoder();
   if (!fn || ((uintptr_t)base & 15) || ((stride * bps) & 15)) return false;
+  if (pair8 && bps == 1) { bps = 2; cw /= 2; stride /= 2; box_w /= 2; }
   const cuuint64_t dims[2] = {(cuuint64_t)cw, (cuuint64_t)ch};
   const cuuint64_t strides[1] = {(cuuint64_t)(stride * bps)};
   const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, estr[2] = {1, 1};
@@ -233,6 +235,8 @@ struct FrameJob {
   void *d_dbrows[3] = {nullptr, nullptr, nullptr};   // deblocked rows 54..57 of every superblock row (loop restoration input)
   void *d_deb_full[3] = {nullptr, nullptr, nullptr}; // whole deblocked planes: test seam only
   int8_t *h_cdef = nullptr;
+  unsigned long long *d_lf_sse = nullptr;      // deblocking level search: [3][B200_LF_CANDIDATES] squared errors
+  int32_t *d_lf_out = nullptr, *h_lf_out = nullptr;   // the four chosen levels
   // pinned host
   B200Mi *h_mi = nullptr;
   uint16_t *h_eob[3] = {nullptr, nullptr, nullptr};
@@ -292,6 +296,9 @@ void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
   }
   j.d_cdef = dev.take<int8_t>(j.n_sb());
   j.h_cdef = pin.take<int8_t>(j.n_sb());
+  j.d_lf_sse = dev.take<unsigned long long>(3 * B200_LF_CANDIDATES);
+  j.d_lf_out = dev.take<int32_t>(4);
+  j.h_lf_out = pin.take<int32_t>(4);
   if (j.uses_lr())
     for (int p = 0; p < P; p++) {
       if (!j.d_fin[p]) j.d_fin[p] = dev.take<uint8_t>(j.plane_bytes());
@@ -325,6 +332,8 @@ int configure_frame(B200Frame *f, size_t w, size_t h, int depth, bool mono, int 
   f->split_gate_bits[1] = speed <= 2 ? 0 : 120;
   f->split_gate_bits[2] = speed <= 2 ? 0 : 200;
   if (!tw.cdef) f->enable_cdef = 0;   // ravif: cdef = low_quality && speed <= 9 (av1encoder.rs:590)
+  f->lf_search = tw.fast_deblock ? 0 : 1;       // av1encoder.rs:586: the closed-form level only at the fast presets
+  f->lr_full = tw.sgr_complexity_full ? 1 : 0;  // :573
   f->enable_restoration = tw.lrf ? 1 : 0;     // loop restoration (lrf flag, av1encoder.rs:589): self-guided filter, 64x64 units
   for (int p = 0; p < 3; p++) f->lr_type[p] = (tw.lrf && p < f->planes) ? 1 : 0;
   f->full_range = full_range;
@@ -389,6 +398,7 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     r.mi = j.d_mi;
     for (int lv = 0; lv < B200_LEVELS; lv++) { r.dec[lv] = j.d_dec[lv]; r.satd[lv] = j.d_satd[lv]; }
     r.cdef_idx = j.d_cdef;
+    r.lf_sse = j.d_lf_sse; r.lf_out = j.d_lf_out;
     for (int p = 0; p < 3; p++) { r.fin[p] = j.d_fin[p < j.f.planes ? p : 0]; r.dbrows[p] = p < j.f.planes ? j.d_dbrows[p] : nullptr; r.deb_full[p] = p < j.f.planes ? j.d_deb_full[p] : nullptr; }
     for (int p = 0; p < 3; p++) { r.lr[p] = p < j.f.planes ? j.d_lr[p] : nullptr; r.lr_out[p] = p < j.f.planes ? j.d_lr_out[p] : nullptr; }
     for (int tr = 0; tr < j.f.tile_rows; tr++)
@@ -444,30 +454,35 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
   {
     int max_sb = 0;
     for (FrameJob *jp : jobs) max_sb = std::max(max_sb, (int)jp->n_sb());
-    int with_lr = 0;
-    for (FrameJob *jp : jobs) with_lr |= jp->uses_lr();
+    int with_lr = 0, with_lf = 0;
+    for (FrameJob *jp : jobs) { with_lr |= jp->uses_lr(); with_lf |= jp->f.lf_search != 0; }
+    if (with_lf)
+      for (FrameJob *jp : jobs) CU(cudaMemsetAsync(jp->d_lf_sse, 0, sizeof(unsigned long long) * 3 * B200_LF_CANDIDATES, c.stream_hi));
     // tensor maps of the reconstruction planes for the TMA loads of the fused filter kernel (one per job and plane)
     const void *d_tmaps = nullptr;
+    static const bool tma_pair8 = getenv("B200AVIF_TMA_PAIR8") != nullptr;
     {
       int bw = 0, bh = 0;
       b200_filters_tmap_box(&bw, &bh);
       std::vector<CUtensorMap> maps(jobs.size() * 3);
       bool ok = tmap_encoder() != nullptr;
+      if (jobs[0]->f.bit_depth == 8 && getenv("B200AVIF_TMA_SKIP_U8")) ok = false;
       for (size_t i = 0; ok && i < jobs.size(); i++)
         for (int p = 0; ok && p < 3; p++) {
           FrameJob &j = *jobs[i];
           const int q = p < j.f.planes ? p : 0;
-          ok = encode_plane_tmap(&maps[i * 3 + p], j.d_rec[q], j.bps(), (size_t)j.f.mi_cols * 4, (size_t)j.f.mi_rows * 4, j.stride(), bw, bh);
+          ok = encode_plane_tmap(&maps[i * 3 + p], j.d_rec[q], j.bps(), (size_t)j.f.mi_cols * 4, (size_t)j.f.mi_rows * 4, j.stride(), bw, bh, tma_pair8);
         }
       if (ok) {
         CUtensorMap *d = dev.take<CUtensorMap>(maps.size());
         if (dev.overflow) return fail(B200AVIF_ENCODING_ERROR, "internal error: work arena too small for this batch");
         CU(cudaMemcpyAsync(d, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, c.stream_hi));
         d_tmaps = d;
+        g_tma++;
       }
     }
     b200_mark(nullptr, c.stream_hi);
-    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_sb, with_lr, jobs[0]->f.bit_depth > 8, d_tmaps, c.stream_hi, &n_launched);
+    const int fe = b200_filters_launch(d_jobs, (int)jobs.size(), max_sb, with_lr, with_lf, jobs[0]->f.bit_depth > 8, d_tmaps, tma_pair8 ? 1 : 0, c.stream_hi, &n_launched);
     if (fe != 0) return fail(B200AVIF_ENCODING_ERROR, std::string("filter kernel launch failed: ") + cudaGetErrorString((cudaError_t)fe));
     g_launches += (uint64_t)n_launched;
   }
@@ -476,6 +491,7 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     FrameJob &j = *jp;
     CU(cudaMemcpyAsync(j.h_mi, j.d_mi, j.n_mi() * sizeof(B200Mi), cudaMemcpyDeviceToHost, c.stream_hi));
     CU(cudaMemcpyAsync(j.h_cdef, j.d_cdef, j.n_sb(), cudaMemcpyDeviceToHost, c.stream_hi));
+    if (j.f.lf_search) CU(cudaMemcpyAsync(j.h_lf_out, j.d_lf_out, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream_hi));
     d2h += j.n_mi() * sizeof(B200Mi) + j.n_sb();
     if (j.uses_lr())
       for (int p = 0; p < j.f.planes; p++) {
@@ -578,6 +594,7 @@ void pack_jobs(std::vector<FrameJob *> &jobs) {
   }
   parallel_for(jobs.size(), [&](size_t i) {
     FrameJob &j = *jobs[i];
+    if (j.f.lf_search) for (int k = 0; k < 4; k++) j.f.lf_level[k] = j.h_lf_out[k];      // levels chosen on the device -> frame header
     B200Records rec;
     memset(&rec, 0, sizeof(rec));
     rec.mi = j.h_mi;
@@ -1002,6 +1019,7 @@ void b200avif_get_stats(b200avif_stats *out) {
   std::lock_guard<std::mutex> lk(g_stat_mu);
   out->kernel_launches = g_launches; out->h2d_bytes = g_h2d; out->d2h_bytes = g_d2h;
   out->gpu_ms_rdo = g_ms_rdo; out->gpu_ms_total = g_ms_total; out->host_ms_pack = g_ms_pack;
+  out->tma_launches = g_tma; out->tma_timeouts = b200avif_device_count() > 0 ? b200_filters_tma_timeouts() : 0;
 }
 
 // ---- narrowest seam ------------------------------------------------------------------------------
@@ -1141,7 +1159,8 @@ int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h,
 // ---- test seam: run the device hot path on caller-provided coded planes and frame description -----
 int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi, uint16_t *const eob[3], int16_t *const coef[3],
                     uint16_t *const rec[3], uint16_t *const deblocked[3], uint16_t *const fin[3], int8_t *cdef_idx,
-                    B200BlockDec *const dec[B200_LEVELS], uint32_t *const satd[B200_LEVELS], B200LrUnit *const lr[3], uint16_t *const lr_out[3]) {
+                    B200BlockDec *const dec[B200_LEVELS], uint32_t *const satd[B200_LEVELS], B200LrUnit *const lr[3], uint16_t *const lr_out[3],
+                    int32_t *lf_level_out /* may be NULL: the four deblocking levels the frame ends up with */) {
   if (!f || !src || !mi) return fail(B200AVIF_INVALID_ARGUMENT, "null argument");
   if (b200avif_device_count() <= 0) return fail(B200AVIF_ENCODING_ERROR, "no CUDA device available (this library has no CPU fallback)");
   FrameJob job;
@@ -1174,6 +1193,7 @@ int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi
   std::vector<std::vector<uint8_t>> deb, pre;
   if (int e = run_rdo_and_fetch(c, jobs, c.dev, c.pin, true, &deb, &pre)) return e;
   memcpy(mi, job.h_mi, job.n_mi() * sizeof(B200Mi));
+  if (lf_level_out) for (int k = 0; k < 4; k++) lf_level_out[k] = job.f.lf_search ? job.h_lf_out[k] : job.f.lf_level[k];
   if (cdef_idx) memcpy(cdef_idx, job.h_cdef, job.n_sb());
   for (int lv = 0; lv < B200_LEVELS; lv++) {
     if (dec && dec[lv]) CU(cudaMemcpy(dec[lv], job.d_dec[lv], job.n_blk(lv) * sizeof(B200BlockDec), cudaMemcpyDeviceToHost));

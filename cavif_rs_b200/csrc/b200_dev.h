@@ -27,7 +27,8 @@ int b200av1_convert_run(const uint8_t *pixels, int channels, size_t w, size_t h,
 // open-loop analysis outputs per level (decisions, SATD tables).
 int b200av1_rdo_run(const B200Frame *f, const uint16_t *const src[3], B200Mi *mi, uint16_t *const eob[3],
                     int16_t *const coef[3], uint16_t *const rec[3], uint16_t *const deblocked[3], uint16_t *const fin[3],
-                    int8_t *cdef_idx, B200BlockDec *const dec[B200_LEVELS], uint32_t *const satd[B200_LEVELS], B200LrUnit *const lr[3], uint16_t *const lr_out[3]);
+                    int8_t *cdef_idx, B200BlockDec *const dec[B200_LEVELS], uint32_t *const satd[B200_LEVELS], B200LrUnit *const lr[3], uint16_t *const lr_out[3],
+                    int32_t *lf_level_out);
 #ifdef __cplusplus
 }
 #endif

@@ -177,6 +177,9 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, 
                ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 #endif
+#ifndef B200_EMU
+__device__ unsigned int b200_tma_timeouts;      // TMA tiles that did not land in time (diagnostic; read by b200_filters_tma_timeouts)
+#endif
 constexpr int kTmaBoxW = 80, kTmaBoxH = kFW;   // box of the tensor map: 80 x 78 samples starting at (x0 - 8, y0 - 7)
 __device__ __forceinline__ int cdef_pixel_tile(const uint16_t *T, int lx, int ly, int pri, int sec, int dir, int damping, int cshift) {
   const uint16_t *c = T + (ly + kFH) * kCdefTW + lx + kFH;
@@ -279,7 +282,7 @@ struct LrShared {
   // raw box sums of the band, shared by every candidate set: 3x3 at all A/B rows, 5x5 at the odd rows only
   uint32_t R3a[kLrAH * kLrAW], R5a[((kLrAH + 1) / 2) * kLrAW];
   uint16_t R3b[kLrAH * kLrAW], R5b[((kLrAH + 1) / 2) * kLrAW];
-  unsigned long long acc[B200_LR_CANDIDATES][6];     // H00, H01, H11, C0, C1 (two's complement), S
+  unsigned long long acc[B200_LR_CANDIDATES_FULL][6];     // per candidate set: H00, H01, H11, C0, C1 (two's complement), S
   B200LrUnit best;
 };
 
@@ -352,9 +355,12 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
   const PIX *deb = (const PIX *)job.dbrows[plane], *cdef = (const PIX *)job.fin[plane], *src = (const PIX *)job.src[plane];
   PIX *lr_out = (PIX *)job.lr_out[plane];
   const int tid = threadIdx.x;
-  for (int i = tid; i < B200_LR_CANDIDATES * 6; i += 256) sh.acc[i / 6][i % 6] = 0;
+  for (int i = tid; i < B200_LR_CANDIDATES_FULL * 6; i += 256) sh.acc[i / 6][i % 6] = 0;
   __syncthreads();
   const int8_t cand[B200_LR_CANDIDATES] = {B200_LR_SETS};
+  // sgr_complexity_full (ravif SpeedTweaks, av1encoder.rs:573): every one of the 16 parameter sets, else four
+  const int n_sets = f->lr_full ? B200_LR_CANDIDATES_FULL : B200_LR_CANDIDATES;
+#define LR_SET_OF(ci) (f->lr_full ? (ci) : (int)cand[(ci) & 3])
   // pass over the unit: phase 0 accumulates the normal equations of every candidate set, phase 1 (tests only) applies
   // the winner
   for (int phase = 0; phase < 2; phase++) {
@@ -388,9 +394,9 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
         sh.R5a[ri * kLrAW + aj] = a; sh.R5b[ri * kLrAW + aj] = (uint16_t)b;
       }
       __syncthreads();
-      const int ncand = phase == 0 ? B200_LR_CANDIDATES : 1;
+      const int ncand = phase == 0 ? n_sets : 1;
       for (int ci = 0; ci < ncand; ci++) {
-        const int set = phase == 0 ? cand[ci] : sh.best.set;
+        const int set = phase == 0 ? LR_SET_OF(ci) : sh.best.set;
         if (phase == 1 && !sh.best.use) {       // restoration off in this unit: the CDEF samples pass through
           for (int i = tid; i < bh * w; i += 256) {
             const int py = i / w, px = i % w;
@@ -484,8 +490,8 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
         const long long S = (long long)sh.acc[0][5];
         long long bestJ = ((S >> 8) << 8) + (((long long)f->lambda_q8 * B200_LR_FLAG_COST0) >> 8);
         const long long npx = (long long)w * (y1 - y0);
-        for (int ci = 0; ci < B200_LR_CANDIDATES; ci++) {
-          const int set = cand[ci];
+        for (int ci = 0; ci < n_sets; ci++) {
+          const int set = LR_SET_OF(ci);
           const int r0 = dv_sgr_params[set][0], r1 = dv_sgr_params[set][1];
           const long long H00 = (long long)sh.acc[ci][0], H01 = (long long)sh.acc[ci][1], H11 = (long long)sh.acc[ci][2];
           const long long C0 = (long long)sh.acc[ci][3], C1 = (long long)sh.acc[ci][4];
@@ -536,7 +542,8 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
 // strength index.  Phase 4: apply the winner into job.fin (if present).
 
 template <class PIX>
-__global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs, const unsigned char *tmaps /* CUtensorMap[job][3] of the rec planes, or null */) {
+__global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs, const unsigned char *tmaps /* CUtensorMap[job][3] of the rec planes, or null */,
+                                                          int tma_x_shift /* 1: the maps describe 8-bit planes as 16-bit elements (x coordinate halves) */) {
   const B200RdoJob &job = jobs[blockIdx.y];
   const B200Frame *f = &job.frame;
   const int nsb = f->sb_rows * f->sb_cols;
@@ -573,12 +580,17 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
       for (int p = 0; p < f->planes; p++) {
         const unsigned char *tm = tmaps + ((size_t)blockIdx.y * 3 + p) * 128;
         tmap_acquire(tm);
-        tma_load_2d(dyn_smem + p * kLand, tm, x0 - 8, y0 - kFH, &s_bar);
+        tma_load_2d(dyn_smem + p * kLand, tm, (x0 - 8) >> tma_x_shift, y0 - kFH, &s_bar);
       }
     }
-    // everybody waits for the bytes (bounded: a tile that never lands is a bug, not a hang)
+    // everybody waits for the bytes (bounded: a tile that never lands must not hang the GPU: it is counted in
+    // b200_tma_timeouts and the region is staged with ordinary loads instead)
     unsigned spins = 0;
-    while (!mbar_try_wait(&s_bar, 0)) { if (++spins > (1u << 24)) __trap(); }
+    bool landed = true;
+    while (!mbar_try_wait(&s_bar, 0)) { if (++spins > (1u << 20)) { landed = false; break; } }
+    if (__syncthreads_or(!landed)) {
+      if (tid == 0) atomicAdd(&b200_tma_timeouts, 1u);
+    } else {
     // landing zone (native width, zeros outside the frame) -> working copy (uint16, kCdefNA outside the frame)
     for (int p = 0; p < f->planes; p++) {
       const PIX *Lz = reinterpret_cast<const PIX *>(dyn_smem + p * kLand);
@@ -589,6 +601,7 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
       }
     }
     staged = true;
+    }
   }
 #endif
   if (!staged)
@@ -742,6 +755,106 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
   }
 }
 
+// ---- deblocking level search (frame.lf_search = !fast_deblock, ravif SpeedTweaks av1encoder.rs:586) -----------------
+// One CTA per SAMPLED superblock (even row and column index: a quarter of the frame); grid.y = job.  Per plane the
+// reconstruction of the superblock + halo is staged once, every candidate level (records.h b200_lf_candidate) is applied to a
+// working copy with the same two-pass edge code as the fused kernel, and the squared error against the source over the
+// superblock goes to job.lf_sse[plane][candidate].  b200_lf_pick_kernel then takes the minimum per plane (ties: the earlier
+// candidate) and writes the levels into the job's frame (read by the fused kernel) and into job.lf_out (frame header).
+// Oracle: orc_lf_search (oracle/av1_filters.c).
+template <class PIX>
+__global__ void __launch_bounds__(256) b200_lf_search_kernel(const B200RdoJob *jobs) {
+  const B200RdoJob &job = jobs[blockIdx.y];
+  const B200Frame *f = &job.frame;
+  if (!f->lf_search) return;
+  const int nsb = f->sb_rows * f->sb_cols;
+  if ((int)blockIdx.x >= nsb) return;
+  const int sbr = blockIdx.x / f->sb_cols, sbc = blockIdx.x % f->sb_cols;
+  if (!b200_lf_sampled(sbr, sbc)) return;
+  const int stride = job.stride, W = f->mi_cols * 4, H = f->mi_rows * 4, bd = f->bit_depth;
+  const int tid = threadIdx.x;
+  const int x0 = sbc * 64, y0 = sbr * 64;
+  __shared__ uint16_t s_org[kFW * kCdefTW], s_wrk[kFW * kCdefTW];
+  __shared__ uint8_t s_txs[20 * 20];
+  for (int i = tid; i < 400; i += 256) {
+    const int r = sbr * 16 - 2 + i / 20, c = sbc * 16 - 2 + i % 20;
+    s_txs[i] = (r >= 0 && r < f->mi_rows && c >= 0 && c < f->mi_cols) ? job.mi[r * f->mi_cols + c].tx_size : 0;
+  }
+#define TXS_AT(r, c) s_txs[((r) - (sbr * 16 - 2)) * 20 + ((c) - (sbc * 16 - 2))]
+  for (int plane = 0; plane < f->planes; plane++) {
+    const int base = plane == 0 ? f->lf_level[0] : f->lf_level[plane + 1];
+    if (!base) continue;                   // uniform: nothing to search for this plane
+    __syncthreads();
+    const PIX *R = (const PIX *)job.rec[plane];
+    for (int i = tid; i < kFW * kFW; i += 256) {
+      const int ty = i / kFW, tx = i % kFW;
+      const int yy = y0 - kFH + ty, xx = x0 - kFH + tx;
+      s_org[ty * kCdefTW + tx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (uint16_t)R[(size_t)yy * stride + xx] : kCdefNA;
+    }
+    __syncthreads();
+    const PIX *S = (const PIX *)job.src[plane];
+    for (int k = 0; k < B200_LF_CANDIDATES; k++) {
+      const int lvl = b200_lf_candidate(base, k);
+      for (int i = tid; i < kFW * kCdefTW; i += 256) s_wrk[i] = s_org[i];
+      __syncthreads();
+      if (lvl)
+        for (int pass = 0; pass < 2; pass++) {
+          const int span = pass == 0 ? kFW : 68;
+          for (int i = tid; i < 17 * span; i += 256) {
+            const int kk = i / span, j = i % span;
+            int x, y;
+            if (pass == 0) { x = x0 + 4 * kk; y = y0 - kFH + j; } else { x = x0 - 2 + j; y = y0 + 4 * kk; }
+            if (x < 0 || y < 0 || (x & ~3) >= f->width || (y & ~3) >= f->height) continue;
+            const int r = y >> 2, c = x >> 2;
+            if (pass == 0 ? c == 0 : r == 0) continue;
+            const int tx = 4 << TXS_AT(r, c);
+            if (pass == 0 ? (x & (tx - 1)) : (y & (tx - 1))) continue;
+            const int ptx = 4 << (pass == 0 ? TXS_AT(r, c - 1) : TXS_AT(r - 1, c));
+            const int bs = min(tx, ptx);
+            int flen = plane == 0 ? min(bs, 16) : min(bs, 8);
+            if (plane > 0 && flen == 8) flen = 6;
+            deblock_sample<uint16_t>(&s_wrk[(y - (y0 - kFH)) * kCdefTW + (x - (x0 - kFH))], pass == 0 ? 1 : kCdefTW, flen, lvl, f->lf_sharpness, bd);
+          }
+          __syncthreads();
+        }
+      unsigned long long sse = 0;
+      for (int i = tid; i < 4096; i += 256) {
+        const int ly = i >> 6, lx = i & 63;
+        if (y0 + ly >= H || x0 + lx >= W) continue;
+        const int d = (int)s_wrk[(ly + kFH) * kCdefTW + lx + kFH] - (int)S[(size_t)(y0 + ly) * stride + x0 + lx];
+        sse += (unsigned long long)(d * d);
+      }
+      for (int m = 16; m > 0; m >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, m);
+      if ((tid & 31) == 0 && sse) atomicAdd(&job.lf_sse[plane * B200_LF_CANDIDATES + k], sse);
+      __syncthreads();
+    }
+  }
+#undef TXS_AT
+}
+// one thread per job
+__global__ void b200_lf_pick_kernel(B200RdoJob *jobs, int n_jobs) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_jobs) return;
+  B200RdoJob &job = jobs[j];
+  B200Frame *f = &job.frame;
+  if (f->lf_search) {
+    int out[4] = {f->lf_level[0], f->lf_level[1], f->lf_level[2], f->lf_level[3]};
+    for (int plane = 0; plane < f->planes; plane++) {
+      const int base = plane == 0 ? f->lf_level[0] : f->lf_level[plane + 1];
+      if (!base) continue;
+      int best_lvl = base;
+      unsigned long long best = 0;
+      for (int k = 0; k < B200_LF_CANDIDATES; k++) {
+        const unsigned long long sse = job.lf_sse[plane * B200_LF_CANDIDATES + k];
+        if (k == 0 || sse < best) { best = sse; best_lvl = b200_lf_candidate(base, k); }
+      }
+      if (plane == 0) { out[0] = best_lvl; out[1] = best_lvl; } else out[plane + 1] = best_lvl;
+    }
+    for (int i = 0; i < 4; i++) f->lf_level[i] = out[i];
+  }
+  if (job.lf_out) for (int i = 0; i < 4; i++) job.lf_out[i] = f->lf_level[i];
+}
+
 #ifndef B200_EMU
 namespace {
 template <class PIX> size_t dbcdef_smem_bytes() {
@@ -761,34 +874,52 @@ template <class PIX> void dbcdef_configure() {
 }  // namespace
 // d_tmaps: device array of CUtensorMap[n_jobs][3] describing the rec planes with an 80 x 78 box (b200_filters_tmap_box),
 // or NULL: the fused kernel then stages its region with ordinary loads.
-extern "C" int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_sb, int with_lr, int high_bitdepth, const void *d_tmaps, void *stream,
-                                   int *launched) {
+extern "C" int b200_filters_launch(B200RdoJob *d_jobs, int n_jobs, int max_sb, int with_lr, int with_lf_search, int high_bitdepth, const void *d_tmaps,
+                                   int tma_x_shift, void *stream, int *launched) {
   if (launched) *launched = 0;
   if (n_jobs <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 g2(max_sb, n_jobs), g3(max_sb, n_jobs, 3);       // restoration units <= superblocks
+  if (with_lf_search) {
+    if (high_bitdepth) b200_lf_search_kernel<uint16_t><<<g2, 256, 0, st>>>(d_jobs);
+    else b200_lf_search_kernel<uint8_t><<<g2, 256, 0, st>>>(d_jobs);
+    B200_MARK_F("lf_search", st);
+    b200_lf_pick_kernel<<<(n_jobs + 63) / 64, 64, 0, st>>>(d_jobs, n_jobs);
+    B200_MARK_F("lf_pick", st);
+  }
   if (high_bitdepth) {
     dbcdef_configure<uint16_t>();
-    b200_dbcdef_kernel<uint16_t><<<g2, 256, dbcdef_smem_bytes<uint16_t>(), st>>>(d_jobs, (const unsigned char *)d_tmaps);
+    b200_dbcdef_kernel<uint16_t><<<g2, 256, dbcdef_smem_bytes<uint16_t>(), st>>>(d_jobs, (const unsigned char *)d_tmaps, 0);
     B200_MARK_F("deblock_cdef", st);
     if (with_lr) { b200_lr_kernel<uint16_t><<<g3, 256, 0, st>>>(d_jobs); B200_MARK_F("lr_search", st); }
   } else {
     dbcdef_configure<uint8_t>();
-    b200_dbcdef_kernel<uint8_t><<<g2, 256, dbcdef_smem_bytes<uint8_t>(), st>>>(d_jobs, (const unsigned char *)d_tmaps);
+    b200_dbcdef_kernel<uint8_t><<<g2, 256, dbcdef_smem_bytes<uint8_t>(), st>>>(d_jobs, (const unsigned char *)d_tmaps, tma_x_shift);
     B200_MARK_F("deblock_cdef", st);
     if (with_lr) { b200_lr_kernel<uint8_t><<<g3, 256, 0, st>>>(d_jobs); B200_MARK_F("lr_search", st); }
   }
-  if (launched) *launched = 1 + (with_lr ? 1 : 0);
+  if (launched) *launched = 1 + (with_lr ? 1 : 0) + (with_lf_search ? 2 : 0);
   return (int)cudaGetLastError();
 }
 extern "C" void b200_filters_tmap_box(int *box_w, int *box_h) { *box_w = kTmaBoxW; *box_h = kTmaBoxH; }
+extern "C" unsigned b200_filters_tma_timeouts(void) {
+  unsigned v = 0;
+  if (cudaMemcpyFromSymbol(&v, b200_tma_timeouts, sizeof(v)) != cudaSuccess) cudaGetLastError();
+  return v;
+}
 #else
 static const B200RdoJob *g_f_jobs;
 static bool emu_hbd() { return g_f_jobs[0].frame.bit_depth > 8; }
-static void emu_cdef_entry(void *) { if (emu_hbd()) b200_dbcdef_kernel<uint16_t>(g_f_jobs, nullptr); else b200_dbcdef_kernel<uint8_t>(g_f_jobs, nullptr); }
+static void emu_cdef_entry(void *) { if (emu_hbd()) b200_dbcdef_kernel<uint16_t>(g_f_jobs, nullptr, 0); else b200_dbcdef_kernel<uint8_t>(g_f_jobs, nullptr, 0); }
 static void emu_lr_entry(void *) { if (emu_hbd()) b200_lr_kernel<uint16_t>(g_f_jobs); else b200_lr_kernel<uint8_t>(g_f_jobs); }
+static void emu_lf_entry(void *) { if (emu_hbd()) b200_lf_search_kernel<uint16_t>(g_f_jobs); else b200_lf_search_kernel<uint8_t>(g_f_jobs); }
+static void emu_lf_pick_entry(void *) { b200_lf_pick_kernel(const_cast<B200RdoJob *>(g_f_jobs), 1); }
 extern "C" int b200_filters_launch_emu(const B200RdoJob *jobs, int max_sb) {
   g_f_jobs = jobs;
+  if (jobs[0].frame.lf_search) {
+    emu::launch(emu_lf_entry, nullptr, (unsigned)max_sb, 256);
+    emu::launch(emu_lf_pick_entry, nullptr, 1, 64);
+  }
   emu::launch(emu_cdef_entry, nullptr, (unsigned)max_sb, 256);
   for (g_f_plane = 0; g_f_plane < jobs[0].frame.planes; g_f_plane++)
     if (jobs[0].frame.lr_type[g_f_plane]) emu::launch(emu_lr_entry, nullptr, (unsigned)max_sb, 256);

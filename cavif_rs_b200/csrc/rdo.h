@@ -29,6 +29,10 @@ typedef struct B200RdoJob {
   // strength index (-1: nothing coded in the superblock); fin (optional, may be NULL) receives the CDEF output.
   int8_t *cdef_idx;       // sb_rows*sb_cols
   void *fin[3];
+  // deblocking level search (frame.lf_search): squared error of every (plane, candidate) accumulated by the search kernel,
+  // [3][B200_LF_CANDIDATES], zeroed by the caller; lf_out receives the four chosen levels (the kernel also writes frame.lf_level)
+  unsigned long long *lf_sse;
+  int32_t *lf_out;
   void *dbrows[3];        // deblocked rows 54..57 of every superblock row (4 * sb_rows rows of `stride` samples): loop restoration input
   void *deb_full[3];      // optional (tests): the whole deblocked planes
   // loop restoration (frame.lr_type[p] != 0; needs fin): per-unit decisions, and (optional, tests) the restored planes
@@ -58,8 +62,11 @@ typedef struct B200StreamRegionH { const int16_t *src; const uint32_t *len; } B2
 int b200_stream_gather_launch(const void *d_regions, int n_regions, uint32_t *d_offsets /* n + 1 */, int16_t *out, uint32_t capacity, void *stream);
 // Fused deblocking + CDEF search (1 launch) + loop-restoration search (1 launch when with_lr) for all jobs: grid.y = job.
 // d_tmaps: CUtensorMap[n_jobs][3] of the rec planes (box from b200_filters_tmap_box; coordinates in samples), or NULL
-int b200_filters_launch(const B200RdoJob *d_jobs, int n_jobs, int max_sb, int with_lr, int high_bitdepth, const void *d_tmaps, void *stream, int *launched);
+// with_lf_search: some job has frame.lf_search set (two more launches: level search + pick, in front of the fused kernel)
+int b200_filters_launch(B200RdoJob *d_jobs, int n_jobs, int max_sb, int with_lr, int with_lf_search, int high_bitdepth, const void *d_tmaps,
+                        int tma_x_shift /* 1: 8-bit planes described as 16-bit elements */, void *stream, int *launched);
 void b200_filters_tmap_box(int *box_w, int *box_h);
+unsigned b200_filters_tma_timeouts(void);   // TMA tiles that never landed on the current device (0 in a healthy run)
 
 #ifdef __cplusplus
 }

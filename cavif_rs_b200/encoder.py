@@ -77,7 +77,8 @@ class _Input(ctypes.Structure):
 
 class _Stats(ctypes.Structure):
     _fields_ = [("kernel_launches", ctypes.c_uint64), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
-                ("gpu_ms_rdo", ctypes.c_double), ("gpu_ms_total", ctypes.c_double), ("host_ms_pack", ctypes.c_double)]
+                ("gpu_ms_rdo", ctypes.c_double), ("gpu_ms_total", ctypes.c_double), ("host_ms_pack", ctypes.c_double),
+                ("tma_launches", ctypes.c_uint64), ("tma_timeouts", ctypes.c_uint64)]
 
 
 class _StageTime(ctypes.Structure):

@@ -137,6 +137,8 @@ typedef struct b200avif_stats {
   double gpu_ms_rdo;            /* accumulated CUDA-event time of the RDO kernel */
   double gpu_ms_total;          /* accumulated CUDA-event time of all device work */
   double host_ms_pack;          /* accumulated wall time of symbol packing + muxing */
+  uint64_t tma_launches;        /* fused filter launches whose tiles were staged by TMA (cp.async.bulk.tensor) */
+  uint64_t tma_timeouts;        /* TMA tiles that did not land in time and were re-staged with ordinary loads (0 = healthy) */
 } b200avif_stats;
 void b200avif_get_stats(b200avif_stats *out);
 /* Per-kernel CUDA-event times (accumulated since process start while profiling is on): the time between consecutive

@@ -78,13 +78,12 @@ static void deblock_sample(uint16_t *px, int step, int filter_len, int lvl, int 
   for (int i = -n; i < n; i++) px[i * step] = (uint16_t)o[i + n];
 }
 
-/* Deblock the whole frame in place: per plane, pass 0 (vertical edges) then pass 1 (horizontal edges). */
-void orc_deblock_frame(const B200Frame *f, uint16_t *const planes[3], const B200Mi *mi) {
+/* Deblock one plane in place with the given levels: pass 0 (vertical edges) then pass 1 (horizontal edges). */
+static void deblock_plane(const B200Frame *f, uint16_t *P, const B200Mi *mi, int plane, int lvl_v, int lvl_h) {
   const int stride = f->mi_cols * 4;
-  for (int plane = 0; plane < f->planes; plane++) {
-    uint16_t *P = planes[plane];
+  {
     for (int pass = 0; pass < 2; pass++) {
-      const int lvl = plane == 0 ? f->lf_level[pass] : f->lf_level[plane + 1];
+      const int lvl = pass == 0 ? lvl_v : lvl_h;
       if (!lvl) continue;
       for (int r = 0; r < f->mi_rows; r++)
         for (int c = 0; c < f->mi_cols; c++) {
@@ -105,6 +104,48 @@ void orc_deblock_frame(const B200Frame *f, uint16_t *const planes[3], const B200
         }
     }
   }
+}
+/* Deblock the whole frame in place with the frame's levels. */
+void orc_deblock_frame(const B200Frame *f, uint16_t *const planes[3], const B200Mi *mi) {
+  for (int plane = 0; plane < f->planes; plane++)
+    deblock_plane(f, planes[plane], mi, plane, plane == 0 ? f->lf_level[0] : f->lf_level[plane + 1], plane == 0 ? f->lf_level[1] : f->lf_level[plane + 1]);
+}
+
+/* Deblocking level search (lf_search = !fast_deblock, ravif SpeedTweaks av1encoder.rs:586; rav1e deblock_filter_optimize [EXT]):
+ * per plane, the candidate levels around the closed-form level (records.h b200_lf_candidate) are applied to the
+ * reconstruction and scored by squared error against the source on the sampled superblocks (b200_lf_sampled, coded area);
+ * the lowest error wins, ties keep the earlier candidate.  Luma uses one level for both edge directions.  Updates f->lf_level.
+ * The device kernel b200_lf_search_kernel mirrors this. */
+void orc_lf_search(B200Frame *f, const uint16_t *const rec[3], const uint16_t *const src[3], const B200Mi *mi) {
+  if (!f->lf_search) return;
+  const int stride = f->mi_cols * 4, W = stride, H = f->mi_rows * 4;
+  uint16_t *tmp = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)W * H);
+  int out[4] = {f->lf_level[0], f->lf_level[1], f->lf_level[2], f->lf_level[3]};
+  for (int plane = 0; plane < f->planes; plane++) {
+    const int base = plane == 0 ? f->lf_level[0] : f->lf_level[plane + 1];
+    if (!base) continue;
+    int best_lvl = base;
+    uint64_t best = 0;
+    for (int k = 0; k < B200_LF_CANDIDATES; k++) {
+      const int lvl = b200_lf_candidate(base, k);
+      memcpy(tmp, rec[plane], sizeof(uint16_t) * (size_t)W * H);
+      deblock_plane(f, tmp, mi, plane, lvl, lvl);
+      uint64_t sse = 0;
+      for (int sbr = 0; sbr < f->sb_rows; sbr++)
+        for (int sbc = 0; sbc < f->sb_cols; sbc++) {
+          if (!b200_lf_sampled(sbr, sbc)) continue;
+          for (int y = sbr * 64; y < sbr * 64 + 64 && y < H; y++)
+            for (int x = sbc * 64; x < sbc * 64 + 64 && x < W; x++) {
+              const int d = (int)tmp[y * stride + x] - (int)src[plane][y * stride + x];
+              sse += (uint64_t)(d * d);
+            }
+        }
+      if (k == 0 || sse < best) { best = sse; best_lvl = lvl; }
+    }
+    if (plane == 0) { out[0] = best_lvl; out[1] = best_lvl; } else out[plane + 1] = best_lvl;
+  }
+  free(tmp);
+  for (int i = 0; i < 4; i++) f->lf_level[i] = out[i];
 }
 
 /* ---------------------------------------------------------------------------------------------

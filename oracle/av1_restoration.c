@@ -205,8 +205,10 @@ void orc_lr_search_plane(const B200Frame *f, int plane, const uint16_t *src, con
         n_reg++;
         ys = ye;
       }
-      for (int ci = 0; ci < B200_LR_CANDIDATES; ci++) {
-        const int set = orc_lr_candidate_sets[ci];
+      /* sgr_complexity_full (ravif SpeedTweaks, av1encoder.rs:573): every one of the 16 parameter sets, else four */
+      const int ncand = f->lr_full ? B200_LR_CANDIDATES_FULL : B200_LR_CANDIDATES;
+      for (int ci = 0; ci < ncand; ci++) {
+        const int set = f->lr_full ? ci : orc_lr_candidate_sets[ci];
         const int r0 = av1_sgr_params_tbl[set][0], r1 = av1_sgr_params_tbl[set][1];
         int64_t H00 = 0, H01 = 0, H11 = 0, C0 = 0, C1 = 0, S = 0;
         for (int rg = 0; rg < n_reg; rg++) {

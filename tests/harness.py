@@ -15,7 +15,7 @@ class B200Frame(ctypes.Structure):
         "color_description_present", "color_primaries", "transfer_characteristics", "matrix_coefficients", "full_range",
         "partition_min", "partition_max", "rdo_tx_decision", "fine_directional_intra", "enable_cfl", "enable_intra_edge_filter",
         "lambda_q8", "lambda_satd_q8", "y_mode_mask", "uv_mode_mask", "tx_type_mask")] + [
-        ("split_gate_bits", ctypes.c_int32 * 3),
+        ("split_gate_bits", ctypes.c_int32 * 3), ("lf_search", ctypes.c_int32), ("lr_full", ctypes.c_int32),
         ("lf_level", ctypes.c_int32 * 4), ("lf_sharpness", ctypes.c_int32),
         ("cdef_damping", ctypes.c_int32), ("cdef_bits", ctypes.c_int32),
         ("cdef_y_strength", ctypes.c_int32 * 8), ("cdef_uv_strength", ctypes.c_int32 * 8),
@@ -68,6 +68,7 @@ def oracle():
         # NB: without argtypes ctypes passes Python ints as 32-bit C ints and truncates pointers.
         L.orc_encode_frame.argtypes = [V, V, V, V, V, V, V, V, V]
         L.orc_deblock_frame.argtypes = [V, V, V]
+        L.orc_lf_search.argtypes = [V, V, V, V]
         L.orc_cdef_frame.argtypes = [V, V, V, V, V]
         L.orc_cdef_search_frame.argtypes = [V, V, V, V, V, V]
         L.orc_sgr_region_plane.argtypes = [V, V] + [I] * 11 + [V, V]
@@ -101,7 +102,7 @@ def hostlib():
         _host.b200av1_pack_frame.argtypes = [ctypes.POINTER(B200Frame), ctypes.POINTER(B200Records),
                                              ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
         V, I, Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
-        _host.b200av1_rdo_run.argtypes = [V] * 13
+        _host.b200av1_rdo_run.argtypes = [V] * 14
         _host.b200av1_convert_run.argtypes = [V, I, Z, Z, Z, I, I, V, V]
         _host.b200av1_seq_level_idx.argtypes = [V]
         _host.b200avif_mux.argtypes = [V, V, V]
@@ -111,6 +112,15 @@ def hostlib():
         _host.b200avif_quality_to_quantizer.argtypes = [ctypes.c_float]
         _host.b200avif_last_error_message.restype = ctypes.c_char_p
     return _host
+
+def device_frame(f):
+    """Copy of a frame description as a device run must receive it: closed-form deblocking levels (see oracle_filters)."""
+    fd = type(f).from_buffer_copy(f)
+    if hasattr(f, "_lf_base"):
+        for k in range(4):
+            fd.lf_level[k] = f._lf_base[k]
+    return fd
+
 
 def frame_setup(w, h, depth=8, planes=3, quantizer=121, tiles=1):
     f = B200Frame()
@@ -182,6 +192,14 @@ def oracle_filters(f, rec, src):
     superblock against `src` (fills rec.cdef_idx) and apply it.  Returns (final planes, deblocked planes)."""
     L = oracle()
     deb = [r.copy() for r in rec.rec]
+    src3 = list(src) + [src[0]] * (3 - len(src))
+    # lf_search: the oracle replaces the closed-form levels of f by the searched ones IN PLACE (the packer needs them in the
+    # frame header); the closed-form ones - what a device run of the same frame must start from - are kept in f._lf_base
+    if not hasattr(f, "_lf_base"):
+        f._lf_base = [int(v) for v in f.lf_level]
+    for k in range(4):
+        f.lf_level[k] = f._lf_base[k]
+    L.orc_lf_search(ctypes.byref(f), ptr3(deb), ptr3(src3), rec.mi.ctypes.data)
     L.orc_deblock_frame(ctypes.byref(f), ptr3(deb), rec.mi.ctypes.data)
     out = [np.zeros_like(r) for r in rec.rec]
     src3 = list(src) + [src[0]] * (3 - len(src))

@@ -12,7 +12,7 @@ class RdoJob(ctypes.Structure):
                 ("src", ctypes.c_void_p * 3), ("rec", ctypes.c_void_p * 3),
                 ("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3), ("stream_len", ctypes.c_void_p * 3),
                 ("dec", ctypes.c_void_p * H.LEVELS), ("satd", ctypes.c_void_p * H.LEVELS),
-                ("cdef_idx", ctypes.c_void_p), ("fin", ctypes.c_void_p * 3), ("dbrows", ctypes.c_void_p * 3), ("deb_full", ctypes.c_void_p * 3),
+                ("cdef_idx", ctypes.c_void_p), ("fin", ctypes.c_void_p * 3), ("lf_sse", ctypes.c_void_p), ("lf_out", ctypes.c_void_p), ("dbrows", ctypes.c_void_p * 3), ("deb_full", ctypes.c_void_p * 3),
                 ("lr", ctypes.c_void_p * 3), ("lr_out", ctypes.c_void_p * 3)]
 
 
@@ -67,7 +67,9 @@ def compare_analysis(ref, out, f):
     (96, 96, 10, 3, 1, dict(enable_intra_edge_filter=1, partition_max=32, y_mode_mask=0x1fe)),   # directional modes only, up to 32x32
     # coded size 8 mod 16 and wide: the root-region count (129) exceeds n_mi / 16 + 64 (128); every region must be decided
     (2056, 8, 8, 1, 1, dict(partition_min=8, rdo_tx_decision=0)),
-    (136, 88, 8, 3, 1, dict(reduced_tx_set=0)),                    # 7-type transform set on 4x4 / 8x8 (V_DCT, H_DCT: 1-D classes)
+    (136, 88, 8, 3, 1, dict(reduced_tx_set=0)),
+    (200, 136, 8, 3, 1, dict(lf_search=1, lr=1)),                   # deblocking level search + restoration
+    (136, 104, 10, 1, 1, dict(lf_search=1, lr=1, lr_full=1, partition_min=8)),   # all 16 self-guided sets, monochrome                    # 7-type transform set on 4x4 / 8x8 (V_DCT, H_DCT: 1-D classes)
     (96, 72, 10, 3, 2, dict(reduced_tx_set=0, partition_max=32, tx_type_mask=0x61)),   # DCT_DCT + the 1-D DCTs where they exist
       # 4 x 3 superblocks: the reconstruction wavefront waits on its neighbours
 ])
@@ -88,7 +90,9 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw, rows):
     src = H.pad_planes([img[..., c].astype(np.uint16) * (4 if depth == 10 else 1) for c in range(planes)], f)
     ref = H.oracle_encode(f, rt, src)
     out = H.Records(f)
+    lf_sse = np.zeros(12, np.uint64); lf_out = np.zeros(4, np.int32)
     job = RdoJob(); job.frame = f; job.rate = rt.ctypes.data
+    job.lf_sse = lf_sse.ctypes.data; job.lf_out = lf_out.ctypes.data
     # the kernels work on planes of the native sample width: uint8 for 8-bit video, uint16 for 10-bit
     pix = np.uint8 if depth == 8 else np.uint16
     job.stride = f.mi_cols * 4
@@ -125,12 +129,14 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw, rows):
             assert slen[p][sbr * f.tile_cols + tc] == n, "stream length plane %d region %d,%d" % (p, sbr, tc)
     compare(ref, out, planes)
     # in-loop filter stage: deblock in place, CDEF strength search, CDEF output
-    ref_fin, ref_deb = H.oracle_filters(f, ref, src)
+    ref_fin, ref_deb = H.oracle_filters(f, ref, src)      # lf_search: f.lf_level now holds the searched levels, job.frame the closed-form ones
     deb = [np.zeros_like(r) for r in out.rec]
     dbrows = [np.zeros((f.sb_rows * 4, f.mi_cols * 4), pix) for _ in range(3)]
     for p in range(3):
         job.deb_full[p] = deb[p].ctypes.data; job.dbrows[p] = dbrows[p].ctypes.data
     E.b200_filters_launch_emu(ctypes.byref(job), f.sb_rows * f.sb_cols)
+    if f.lf_search:
+        assert [int(v) for v in lf_out] == [int(v) for v in f.lf_level], "deblocking levels"
     uses_lr = any(f.lr_type[p] for p in range(planes))
     ref_cdef = ref.cdef_out if uses_lr else ref_fin
     for p in range(planes):

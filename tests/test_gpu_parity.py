@@ -24,9 +24,11 @@ def device_rdo(f, src):
     out.final = [np.zeros_like(r) for r in out.rec]
     src3 = list(src) + [src[0]] * (3 - len(src))
     out.lr_out = [np.zeros_like(r) for r in out.rec]
-    rc = L.b200av1_rdo_run(ctypes.byref(f), H.ptr3(src3), out.mi.ctypes.data, H.ptr3(out.eob), H.ptr3(out.coef), H.ptr3(out.rec),
+    out.lf_level = np.zeros(4, np.int32)
+    fd = H.device_frame(f)          # the oracle may already have replaced f's deblocking levels by the searched ones
+    rc = L.b200av1_rdo_run(ctypes.byref(fd), H.ptr3(src3), out.mi.ctypes.data, H.ptr3(out.eob), H.ptr3(out.coef), H.ptr3(out.rec),
                            H.ptr3(out.deblocked), H.ptr3(out.final), out.cdef_idx.ctypes.data, H.ptrn(out.dec), H.ptrn(out.satd),
-                           H.ptr3(out.lr), H.ptr3(out.lr_out))
+                           H.ptr3(out.lr), H.ptr3(out.lr_out), out.lf_level.ctypes.data)
     assert rc == 0, L.b200avif_last_error_message()
     return out
 
@@ -59,6 +61,7 @@ def check_filters(f, ref, ref_fin, ref_deb, out, planes, w, h):
         assert np.array_equal(out.deblocked[p], ref_deb[p]), "deblocked plane %d" % p
         assert np.array_equal(out.final[p], ref_cdef[p]), "CDEF output plane %d" % p
     assert np.array_equal(out.cdef_idx, ref.cdef_idx)
+    assert [int(v) for v in out.lf_level] == [int(v) for v in f.lf_level], "deblocking levels (search)"
     if not uses_lr:
         return out.final
     for p in range(planes):
@@ -158,7 +161,10 @@ CASES = [
     (200, 136, 8, 3, 121, 2, dict(enable_intra_edge_filter=1)),         # intra edge filter / upsampling
     (256, 192, 10, 3, 100, 1, dict(enable_intra_edge_filter=1, partition_max=32, lr=1)),
     (136, 104, 8, 3, 150, 1, dict(enable_intra_edge_filter=1, y_mode_mask=0x1fe)),       # directional luma modes only
-    (320, 200, 8, 3, 100, 2, dict(reduced_tx_set=0)),                                    # 7-type transform set (V_DCT / H_DCT on 4x4, 8x8)
+    (320, 200, 8, 3, 100, 2, dict(reduced_tx_set=0)),
+    (640, 360, 8, 3, 121, 4, dict(lf_search=1, lr=1)),                                   # deblocking level search (4 of 60 superblocks sampled... a quarter)
+    (384, 256, 10, 3, 180, 2, dict(lf_search=1, partition_min=8)),
+    (200, 136, 8, 1, 100, 1, dict(lf_search=1, lr=1, lr_full=1)),                        # all 16 self-guided sets                                    # 7-type transform set (V_DCT / H_DCT on 4x4, 8x8)
     (200, 136, 10, 3, 66, 1, dict(reduced_tx_set=0, partition_max=32, tx_type_mask=0x61)),
 ]
 
