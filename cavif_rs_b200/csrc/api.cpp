@@ -463,7 +463,7 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
     static const bool tma_pair8 = getenv("B200AVIF_TMA_PAIR8") != nullptr;
     {
       int bw = 0, bh = 0;
-      b200_filters_tmap_box(&bw, &bh);
+      b200_filters_tmap_box(jobs[0]->f.bit_depth > 8, &bw, &bh);
       std::vector<CUtensorMap> maps(jobs.size() * 3);
       bool ok = tmap_encoder() != nullptr;
       if (jobs[0]->f.bit_depth == 8 && getenv("B200AVIF_TMA_SKIP_U8")) ok = false;

@@ -180,7 +180,11 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, 
 #ifndef B200_EMU
 __device__ unsigned int b200_tma_timeouts;      // TMA tiles that did not land in time (diagnostic; read by b200_filters_tma_timeouts)
 #endif
-constexpr int kTmaBoxW = 80, kTmaBoxH = kFW;   // box of the tensor map: 80 x 78 samples starting at (x0 - 8, y0 - 7)
+// Box of the tensor map.  The byte offset of the box inside a row must be a multiple of 16 (an 8-byte-aligned start is an
+// illegal instruction at the UTMALDG, found with compute-sanitizer): 16-bit samples start at x0 - 8 (80 wide, 160 bytes),
+// 8-bit samples at x0 - 16 (96 wide); 78 rows from y0 - 7 in both cases.
+constexpr int kTmaBoxH = kFW;
+template <class PIX> struct TmaBox { static constexpr int kOff = sizeof(PIX) == 1 ? 16 : 8, kW = sizeof(PIX) == 1 ? 96 : 80; };
 __device__ __forceinline__ int cdef_pixel_tile(const uint16_t *T, int lx, int ly, int pri, int sec, int dir, int damping, int cshift) {
   const uint16_t *c = T + (ly + kFH) * kCdefTW + lx + kFH;
   const int x = *c;
@@ -560,6 +564,7 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
 #else
   // dynamic shared memory: [3 planes] TMA landing zone (PIX, 80 x 78, 128-byte aligned) | [3 planes] working copy (uint16)
   extern __shared__ __align__(128) unsigned char dyn_smem[];
+  constexpr int kTmaBoxW = TmaBox<PIX>::kW, kTmaOff = TmaBox<PIX>::kOff;
   constexpr int kLand = ((kTmaBoxW * kTmaBoxH * (int)sizeof(PIX) + 127) / 128) * 128;
   uint16_t (*s_px)[kFW * kCdefTW] = reinterpret_cast<uint16_t (*)[kFW * kCdefTW]>(dyn_smem + 3 * kLand);
   __shared__ __align__(8) unsigned long long s_bar;
@@ -580,7 +585,7 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
       for (int p = 0; p < f->planes; p++) {
         const unsigned char *tm = tmaps + ((size_t)blockIdx.y * 3 + p) * 128;
         tmap_acquire(tm);
-        tma_load_2d(dyn_smem + p * kLand, tm, (x0 - 8) >> tma_x_shift, y0 - kFH, &s_bar);
+        tma_load_2d(dyn_smem + p * kLand, tm, (x0 - kTmaOff) >> tma_x_shift, y0 - kFH, &s_bar);
       }
     }
     // everybody waits for the bytes (bounded: a tile that never lands must not hang the GPU: it is counted in
@@ -597,7 +602,7 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
       for (int i = tid; i < kFW * kFW; i += 256) {
         const int ty = i / kFW, tx = i % kFW;
         const int yy = y0 - kFH + ty, xx = x0 - kFH + tx;
-        s_px[p][ty * kCdefTW + tx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (uint16_t)Lz[ty * kTmaBoxW + tx + 1] : kCdefNA;
+        s_px[p][ty * kCdefTW + tx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (uint16_t)Lz[ty * kTmaBoxW + tx + (kTmaOff - kFH)] : kCdefNA;
       }
     }
     staged = true;
@@ -858,7 +863,7 @@ __global__ void b200_lf_pick_kernel(B200RdoJob *jobs, int n_jobs) {
 #ifndef B200_EMU
 namespace {
 template <class PIX> size_t dbcdef_smem_bytes() {
-  return 3 * (size_t)(((kTmaBoxW * kTmaBoxH * (int)sizeof(PIX) + 127) / 128) * 128) + 3 * sizeof(uint16_t) * kFW * kCdefTW;
+  return 3 * (size_t)(((TmaBox<PIX>::kW * kTmaBoxH * (int)sizeof(PIX) + 127) / 128) * 128) + 3 * sizeof(uint16_t) * kFW * kCdefTW;
 }
 template <class PIX> void dbcdef_configure() {
   static std::mutex mu;
@@ -901,7 +906,7 @@ extern "C" int b200_filters_launch(B200RdoJob *d_jobs, int n_jobs, int max_sb, i
   if (launched) *launched = 1 + (with_lr ? 1 : 0) + (with_lf_search ? 2 : 0);
   return (int)cudaGetLastError();
 }
-extern "C" void b200_filters_tmap_box(int *box_w, int *box_h) { *box_w = kTmaBoxW; *box_h = kTmaBoxH; }
+extern "C" void b200_filters_tmap_box(int high_bitdepth, int *box_w, int *box_h) { *box_w = high_bitdepth ? TmaBox<uint16_t>::kW : TmaBox<uint8_t>::kW; *box_h = kTmaBoxH; }
 extern "C" unsigned b200_filters_tma_timeouts(void) {
   unsigned v = 0;
   if (cudaMemcpyFromSymbol(&v, b200_tma_timeouts, sizeof(v)) != cudaSuccess) cudaGetLastError();

@@ -65,7 +65,7 @@ int b200_stream_gather_launch(const void *d_regions, int n_regions, uint32_t *d_
 // with_lf_search: some job has frame.lf_search set (two more launches: level search + pick, in front of the fused kernel)
 int b200_filters_launch(B200RdoJob *d_jobs, int n_jobs, int max_sb, int with_lr, int with_lf_search, int high_bitdepth, const void *d_tmaps,
                         int tma_x_shift /* 1: 8-bit planes described as 16-bit elements */, void *stream, int *launched);
-void b200_filters_tmap_box(int *box_w, int *box_h);
+void b200_filters_tmap_box(int high_bitdepth, int *box_w, int *box_h);
 unsigned b200_filters_tma_timeouts(void);   // TMA tiles that never landed on the current device (0 in a healthy run)
 
 #ifdef __cplusplus
