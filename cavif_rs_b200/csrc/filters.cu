@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
 }
 
 // ---- deblocking level search (frame.lf_search = !fast_deblock, ravif SpeedTweaks av1encoder.rs:586) -----------------
-// One CTA per SAMPLED superblock (even row and column index: a quarter of the frame); grid.y = job.  Per plane the
+// One CTA per SAMPLED superblock (every fourth superblock row and column: 1/16 of the frame); grid.y = job.  Per plane the
 // reconstruction of the superblock + halo is staged once, every candidate level (records.h b200_lf_candidate) is applied to a
 // working copy with the same two-pass edge code as the fused kernel, and the squared error against the source over the
 // superblock goes to job.lf_sse[plane][candidate].  b200_lf_pick_kernel then takes the minimum per plane (ties: the earlier

@@ -383,7 +383,7 @@ __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid
 constexpr int kAnalyzeWarpsTop = 4;      // 16x16 as the top level
 constexpr int kAnalyzeWarpsTop32 = 2;    // 32x32 as the top level (22.9 KB of shared memory per warp)
 template <int LV, bool HBD, int W>
-__global__ void __launch_bounds__(kThreads * W, LV == 3 ? 4 : (LV == 2 ? 16 : 24) / W) b200_analyze_kernel(const B200RdoJob *jobs) {
+__global__ void __launch_bounds__(kThreads * W, W == 6 ? 3 : (LV == 3 ? 4 : (LV == 2 ? 16 : 24) / W)) b200_analyze_kernel(const B200RdoJob *jobs) {
   typedef typename PixOf<HBD>::type PIX;
   typedef SharedT<(LV == 3 ? 32 : 16), PIX> SH;
   __shared__ SH shs[W];
@@ -517,6 +517,7 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
   if (!configured) {
 #define B200_CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
     B200_CARVE((b200_analyze_kernel<2, false, kAnalyzeWarpsTop>)); B200_CARVE((b200_analyze_kernel<2, true, kAnalyzeWarpsTop>));
+    B200_CARVE((b200_analyze_kernel<2, false, 6>));
     B200_CARVE((b200_analyze_kernel<3, false, kAnalyzeWarpsTop32>)); B200_CARVE((b200_analyze_kernel<3, true, kAnalyzeWarpsTop32>));
     B200_CARVE((b200_analyze_kernel<0, false, 1>)); B200_CARVE((b200_analyze_kernel<1, false, 1>)); B200_CARVE((b200_analyze_kernel<2, false, 1>));
     B200_CARVE((b200_analyze_kernel<0, true, 1>)); B200_CARVE((b200_analyze_kernel<1, true, 1>)); B200_CARVE((b200_analyze_kernel<2, true, 1>));
@@ -551,8 +552,14 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
       dim3 gt((per_job + kAnalyzeWarpsTop32 - 1) / kAnalyzeWarpsTop32, n_jobs);
       B200_ANALYZE(3, kAnalyzeWarpsTop32, gt);
     } else if (lv == 2 && top == 2) {      // never pruned: lock-step CTAs
-      dim3 gt((per_job + kAnalyzeWarpsTop - 1) / kAnalyzeWarpsTop, n_jobs);
-      B200_ANALYZE(2, kAnalyzeWarpsTop, gt);
+      static const int top_warps = getenv("B200AVIF_TOP_WARPS") ? atoi(getenv("B200AVIF_TOP_WARPS")) : kAnalyzeWarpsTop;      // experiment knob
+      if (top_warps == 6 && !high_bitdepth) {
+        dim3 gt((per_job + 5) / 6, n_jobs);
+        b200_analyze_kernel<2, false, 6><<<gt, kThreads * 6, 0, st>>>(d_jobs);
+      } else {
+        dim3 gt((per_job + kAnalyzeWarpsTop - 1) / kAnalyzeWarpsTop, n_jobs);
+        B200_ANALYZE(2, kAnalyzeWarpsTop, gt);
+      }
     } else if (lv == 2) B200_ANALYZE(2, 1, ga);
     else if (lv == 1) B200_ANALYZE(1, 1, ga);
     else B200_ANALYZE(0, 1, ga);

@@ -86,8 +86,8 @@ typedef struct B200Frame {
   // most split_gate_bits * lambda ([0]: 8x8 -> 4x4, [1]: 16x16 -> 8x8, [2]: 32x32 -> 16x16; 0 = exhaustive search)
   int32_t split_gate_bits[3];
   // in-loop filter searches (ravif SpeedTweaks): lf_search = !fast_deblock (av1encoder.rs:586): the deblocking level of every
-  // plane is searched on the device (B200_LF_CANDIDATES around the closed-form level, squared error against the source on a
-  // quarter of the superblocks); lr_full = sgr_complexity_full (:573): all 16 self-guided parameter sets instead of 4
+  // plane is searched on the device (B200_LF_CANDIDATES around the closed-form level, squared error against the source on 1/16
+  // of the superblocks); lr_full = sgr_complexity_full (:573): all 16 self-guided parameter sets instead of 4
   int32_t lf_search, lr_full;
   // decisions of the in-loop filter stages
   int32_t lf_level[4];                      // y vertical, y horizontal, u, v
@@ -110,7 +110,7 @@ static inline B200_HD int b200_lr_units(int size) { const int n = (size + 32) >>
 #define B200_LR_SETS 2, 6, 11, 14
 #define B200_LR_CANDIDATES_FULL 16       /* lr_full: every set of av1_sgr_params */
 // deblocking level search: candidate k = clamp((L0 * mult[k] + 2) >> 2, 0, 63), L0 = closed-form level; ties keep the lowest k;
-// evaluated on the superblocks with even row AND even column index (a quarter of the frame)
+// evaluated on every fourth superblock row and column (1/16 of the frame: the level is one number per plane and frame)
 #define B200_LF_CANDIDATES 4
 #define B200_LF_MULTS 4, 2, 6, 0
 static inline B200_HD int b200_lf_candidate(int l0, int k) {
@@ -118,7 +118,7 @@ static inline B200_HD int b200_lf_candidate(int l0, int k) {
   const int v = (l0 * mult[k] + 2) >> 2;
   return v > 63 ? 63 : v;
 }
-static inline B200_HD int b200_lf_sampled(int sbr, int sbc) { return !((sbr | sbc) & 1); }
+static inline B200_HD int b200_lf_sampled(int sbr, int sbc) { return !((sbr | sbc) & 3); }
 #define B200_LR_FLAG_COST0 246
 #define B200_LR_FLAG_COST1 267
 
