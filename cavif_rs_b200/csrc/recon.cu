@@ -113,28 +113,29 @@ __device__ __noinline__ int recon_tx(const B200Frame *f, bool active, const PIX 
   const int bd = f->bit_depth;
   int vert, horz;
   tx_kernels(tx_type, vert, horz);
+  // v[] lives in thread-local memory (it is handed to the out-of-line transforms), so the loops around it stay ROLLED:
+  // a rolled loop sits in the L0 instruction cache, sixteen unrolled copies of it do not.
   int32_t v[N];
   // forward column pass
   if (active) {
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < N; r++) v[r] = ((int)src[r * N + l] - (int)pred[r * N + l]) * 4;
     fwd1d_call<N, HBD>(vert, v, N == 32 ? 12 : 13);
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < N; r++) buf[r * S + l] = rshift_round_t<HBD>(v[r], shift1);
   }
   __syncwarp();
   // forward row pass, quantiser, dequantiser
   int eob = 0;
   if (active) {
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < N; c++) v[c] = buf[l * S + c];
     fwd1d_call<N, HBD>(horz, v, (N == 32 || N == 16) ? 12 : 13);
     const uint32_t dc_q = (uint32_t)f->dc_q, ac_q = (uint32_t)f->ac_q;
     const uint32_t ac_rcp = 0xffffffffu / ac_q, ac_off = (ac_q * 98) >> 8;
-    ScanRow<N> srow;
-    scan_row_load<N>(l, srow);
     const int txc = b200_tx_class(tx_type);      // chroma never uses the 1-D types (tx type derived from the uv mode)
-#pragma unroll
+    const int clamp_b = bd + 8;
+#pragma unroll 1
     for (int c = 0; c < N; c++) {
       uint32_t q = ac_q, rcp = ac_rcp, off = ac_off;
       if (c == 0 && l == 0) { q = dc_q; rcp = 0xffffffffu / dc_q; off = (dc_q * 109) >> 8; }
@@ -146,9 +147,9 @@ __device__ __noinline__ int recon_tx(const B200Frame *f, bool active, const PIX 
       if (rem >= q) lv++;
       if (lv > 32767) lv = 32767;
       const int32_t dqa = (int32_t)((lv * q) & 0xFFFFFF) >> qshift;
-      const int si = txc == 0 ? scan_row_at<N>(srow, c) : (txc == 2 ? l * N + c : c * N + l);
+      const int si = scan_index<N>(txc, l * N + c, l, c);
       qc[si] = (int16_t)(cf < 0 ? -(int)lv : (int)lv);
-      v[c] = clamp_bits(cf < 0 ? -dqa : dqa, bd + 8);
+      v[c] = clamp_bits(cf < 0 ? -dqa : dqa, clamp_b);
       if (lv) eob = max(eob, si + 1);
     }
   }
@@ -156,7 +157,7 @@ __device__ __noinline__ int recon_tx(const B200Frame *f, bool active, const PIX 
   // inverse row pass
   if (active && eob) {
     inv1d_call<N, HBD>(horz, v);
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < N; c++) buf[l * S + c] = rshift_round_t<HBD>(v[c], row_shift);
   }
   __syncwarp();
@@ -164,17 +165,17 @@ __device__ __noinline__ int recon_tx(const B200Frame *f, bool active, const PIX 
     if (eob) {
       const int col_clamp = bd + 6 > 16 ? bd + 6 : 16;
       const int mx = (1 << bd) - 1;
-#pragma unroll
+#pragma unroll 1
       for (int r = 0; r < N; r++) v[r] = clamp_bits(buf[r * S + l], col_clamp);
       inv1d_call<N, HBD>(vert, v);
-#pragma unroll
+#pragma unroll 1
       for (int r = 0; r < N; r++) {
         int y = (int)pred[r * N + l] + rshift_round_t<HBD>(v[r], 4);
         y = y < 0 ? 0 : (y > mx ? mx : y);
         rec[r * kTS + l] = (PIX)y;
       }
     } else {
-#pragma unroll
+#pragma unroll 1
       for (int r = 0; r < N; r++) rec[r * kTS + l] = pred[r * N + l];
     }
   }
