@@ -332,6 +332,7 @@ int configure_frame(B200Frame *f, size_t w, size_t h, int depth, bool mono, int 
   f->split_gate_bits[1] = speed <= 2 ? 0 : 120;
   f->split_gate_bits[2] = speed <= 2 ? 0 : 200;
   if (!tw.cdef) f->enable_cdef = 0;   // ravif: cdef = low_quality && speed <= 9 (av1encoder.rs:590)
+  f->psy = 1;                                    // Tune::Psychovisual, always (av1encoder.rs:694)
   f->lf_search = tw.fast_deblock ? 0 : 1;       // av1encoder.rs:586: the closed-form level only at the fast presets
   f->lr_full = tw.sgr_complexity_full ? 1 : 0;  // :573
   f->enable_restoration = tw.lrf ? 1 : 0;     // loop restoration (lrf flag, av1encoder.rs:589): self-guided filter, 64x64 units

@@ -515,6 +515,30 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
     __syncwarp();
   }
   sse = group_sum<N>(sse);
+  if (N >= 8 && RATE && f->psy) {
+    // Tune::Psychovisual (oracle trial_plane): luma is scored per 8x8 with the variance-aware error of records.h.  Lane l owns
+    // column l of the reconstruction it just wrote; the five sums of an 8x8 are reduced over its 8 lanes.  Every lane takes the
+    // same path (the shuffles are warp wide); groups that code a chroma plane keep their squared error.
+    unsigned long long dist = 0;
+#pragma unroll 1
+    for (int rg = 0; rg < N / 8; rg++) {
+      uint32_t ss = 0, sd = 0, s2 = 0, d2 = 0, sp = 0;
+#pragma unroll 1
+      for (int r = rg * 8; r < rg * 8 + 8; r++) {
+        const uint32_t s = src[r * N + l], d = rec[r * N + l];
+        ss += s; sd += d; s2 += s * s; d2 += d * d; sp += s * d;
+      }
+#pragma unroll
+      for (int m = 4; m > 0; m >>= 1) {
+        ss += __shfl_xor_sync(FULL, ss, m); sd += __shfl_xor_sync(FULL, sd, m); s2 += __shfl_xor_sync(FULL, s2, m);
+        d2 += __shfl_xor_sync(FULL, d2, m); sp += __shfl_xor_sync(FULL, sp, m);
+      }
+      if ((l & 7) == 0) dist += b200_psy_dist8x8(ss, sd, s2, d2, sp, bd);
+    }
+#pragma unroll
+    for (int m = N / 2; m > 0; m >>= 1) dist += __shfl_xor_sync(FULL, dist, m);
+    if (plane == 0) sse = dist > 0xffffffffull ? 0xffffffffu : (uint32_t)dist;
+  }
   __syncwarp();
   TrialOut o;
   o.eob = eob; o.rate = rate; o.sse = sse;

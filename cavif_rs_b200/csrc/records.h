@@ -5,6 +5,7 @@
 #ifndef B200_RECORDS_H_
 #define B200_RECORDS_H_
 #include <stdint.h>
+#include <math.h>
 
 #if defined(__CUDACC__)
 #define B200_HD __host__ __device__
@@ -89,6 +90,9 @@ typedef struct B200Frame {
   // plane is searched on the device (B200_LF_CANDIDATES around the closed-form level, squared error against the source on 1/16
   // of the superblocks); lr_full = sgr_complexity_full (:573): all 16 self-guided parameter sets instead of 4
   int32_t lf_search, lr_full;
+  // Tune::Psychovisual (ravif always selects it, av1encoder.rs:694): luma blocks of 8x8 and larger are scored per 8x8 with the
+  // variance-aware error b200_psy_dist8x8 instead of the plain squared error
+  int32_t psy;
   // decisions of the in-loop filter stages
   int32_t lf_level[4];                      // y vertical, y horizontal, u, v
   int32_t lf_sharpness;
@@ -96,6 +100,27 @@ typedef struct B200Frame {
   int32_t cdef_y_strength[8], cdef_uv_strength[8];   // pri*4 + sec
   int32_t lr_type[3];                       // per plane: 0 RESTORE_NONE, 1 RESTORE_SGRPROJ (64x64 units, lr_unit_shift 0)
 } B200Frame;
+
+// Tune::Psychovisual distortion of one 8x8 luma block from its five sums (source s, reconstruction d over the 64 samples).
+// rav1e's cdef_dist_kernel [EXT: crates.io rav1e 0.8.1, rdo.rs] scales the squared error by an SSIM-like factor
+//   (4033 / 16384) * (svar + dvar + 16384) / sqrt(16265089 + svar * dvar)        (variances at 8-bit scale, x64);
+// this is an integer restatement of that published form (Q12 factor, floor square root, factor capped at 4), not rav1e's code.
+static inline B200_HD uint64_t b200_isqrt64(uint64_t v) {
+  uint64_t r = (uint64_t)sqrt((double)v);
+  while (r * r > v) r--;
+  while ((r + 1) * (r + 1) <= v) r++;
+  return r;
+}
+static inline B200_HD uint32_t b200_psy_dist8x8(uint32_t sum_s, uint32_t sum_d, uint32_t sum_s2, uint32_t sum_d2, uint32_t sum_sd, int bit_depth) {
+  const uint64_t sse = (uint64_t)sum_s2 + sum_d2 - 2 * (uint64_t)sum_sd;
+  const int cs2 = 2 * (bit_depth - 8);
+  const uint64_t svar = ((uint64_t)sum_s2 - (((uint64_t)sum_s * sum_s + 32) >> 6)) >> cs2;
+  const uint64_t dvar = ((uint64_t)sum_d2 - (((uint64_t)sum_d * sum_d + 32) >> 6)) >> cs2;
+  uint64_t boost = (4033ull * (svar + dvar + 16384)) / (4 * b200_isqrt64(16265089ull + svar * dvar));      /* Q12 */
+  if (boost > 4 * 4096) boost = 4 * 4096;
+  const uint64_t d = (sse * boost + 2048) >> 12;
+  return d > 0x3fffffffu ? 0x3fffffffu : (uint32_t)d;
+}
 
 // Loop restoration decision of one 64x64 restoration unit of one plane (self-guided filter, AV1 spec 5.11.58):
 // unit grid = b200_lr_units(height) rows x b200_lr_units(width) columns, row-major.

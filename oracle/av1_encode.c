@@ -428,6 +428,20 @@ static uint64_t trial_plane(const enc_t *e, int plane, int x, int y, int n, cons
   if (eob) orc_inv_txfm2d_add(dq, recon, n, n, tx_type, f->bit_depth);
   *eob_out = (uint16_t)eob;
   *rate = coef_rate(e, plane, n, tx_type, y_mode, qc, eob);
+  if (f->psy && plane == 0 && n >= 8) {      /* Tune::Psychovisual: variance-aware error per 8x8 (records.h b200_psy_dist8x8) */
+    uint64_t total = 0;
+    for (int by = 0; by < n; by += 8)
+      for (int bx = 0; bx < n; bx += 8) {
+        uint32_t ss = 0, sd = 0, s2 = 0, d2 = 0, sp = 0;
+        for (int i = 0; i < 8; i++)
+          for (int j = 0; j < 8; j++) {
+            const uint32_t s = src[(by + i) * e->stride + bx + j], d = recon[(by + i) * n + bx + j];
+            ss += s; sd += d; s2 += s * s; d2 += d * d; sp += s * d;
+          }
+        total += b200_psy_dist8x8(ss, sd, s2, d2, sp, f->bit_depth);
+      }
+    return total > 0xffffffffu ? 0xffffffffu : total;
+  }
   return sse_block(src, e->stride, recon, n);
 }
 

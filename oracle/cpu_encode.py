@@ -56,6 +56,7 @@ def configure(w, h, depth, planes, quantizer, speed, threads=None):
     f.split_gate_bits[0] = 0 if speed <= 2 else 60
     f.split_gate_bits[1] = 0 if speed <= 2 else 120
     f.split_gate_bits[2] = 0 if speed <= 2 else 200
+    f.psy = 1          # Tune::Psychovisual, always (av1encoder.rs:694)
     f.lf_search = 0 if tw.fast_deblock else 1
     f.lr_full = 1 if tw.sgr_complexity_full else 0
     f.enable_cdef = 1 if tw.cdef else 0

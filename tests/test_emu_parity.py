@@ -68,6 +68,8 @@ def compare_analysis(ref, out, f):
     # coded size 8 mod 16 and wide: the root-region count (129) exceeds n_mi / 16 + 64 (128); every region must be decided
     (2056, 8, 8, 1, 1, dict(partition_min=8, rdo_tx_decision=0)),
     (136, 88, 8, 3, 1, dict(reduced_tx_set=0)),
+    (200, 136, 8, 3, 1, dict(psy=1)),                               # Tune::Psychovisual: variance-aware luma error per 8x8
+    (136, 104, 10, 3, 1, dict(psy=1, partition_max=32, reduced_tx_set=0, lr=1)),
     (200, 136, 8, 3, 1, dict(lf_search=1, lr=1)),                   # deblocking level search + restoration
     (136, 104, 10, 1, 1, dict(lf_search=1, lr=1, lr_full=1, partition_min=8)),   # all 16 self-guided sets, monochrome                    # 7-type transform set on 4x4 / 8x8 (V_DCT, H_DCT: 1-D classes)
     (96, 72, 10, 3, 2, dict(reduced_tx_set=0, partition_max=32, tx_type_mask=0x61)),   # DCT_DCT + the 1-D DCTs where they exist

@@ -162,6 +162,8 @@ CASES = [
     (256, 192, 10, 3, 100, 1, dict(enable_intra_edge_filter=1, partition_max=32, lr=1)),
     (136, 104, 8, 3, 150, 1, dict(enable_intra_edge_filter=1, y_mode_mask=0x1fe)),       # directional luma modes only
     (320, 200, 8, 3, 100, 2, dict(reduced_tx_set=0)),
+    (640, 360, 8, 3, 121, 4, dict(psy=1)),                                               # Tune::Psychovisual luma error
+    (320, 256, 10, 3, 66, 2, dict(psy=1, partition_max=32, reduced_tx_set=0, lr=1, lf_search=1)),
     (640, 360, 8, 3, 121, 4, dict(lf_search=1, lr=1)),                                   # deblocking level search (every 4th superblock row and column is sampled)
     (384, 256, 10, 3, 180, 2, dict(lf_search=1, partition_min=8)),
     (200, 136, 8, 1, 100, 1, dict(lf_search=1, lr=1, lr_full=1)),                        # all 16 self-guided sets                                    # 7-type transform set (V_DCT / H_DCT on 4x4, 8x8)
