@@ -228,6 +228,7 @@ struct FrameJob {
   uint32_t *d_stream_len[3] = {nullptr, nullptr, nullptr};   // per (frame superblock row, tile column) region
   B200BlockDec *d_dec[B200_LEVELS] = {};
   uint32_t *d_satd[B200_LEVELS] = {};
+  uint32_t *d_list[B200_LEVELS] = {}, *d_list_n = nullptr;      // survivor lists of the pruned analysis levels
   int8_t *d_cdef = nullptr;
   void *d_fin[3] = {nullptr, nullptr, nullptr};   // CDEF output: input of the loop-restoration search (and the test seam)
   B200LrUnit *d_lr[3] = {nullptr, nullptr, nullptr}, *h_lr[3] = {nullptr, nullptr, nullptr};
@@ -268,7 +269,7 @@ size_t job_dev_bytes(const FrameJob &j, bool own_src) {
   b += P * align256(j.n_coef() * 2);
   b += P * (align256(j.n_regions() * 4) + j.n_regions() * (sizeof(B200StreamRegionH) + 4) + 512);   // stream lengths, gather regions + offsets
   b += align256(j.n_sb());
-  for (int lv = 0; lv < B200_LEVELS; lv++) b += align256(j.n_blk(lv) * sizeof(B200BlockDec)) + align256(j.n_blk(lv) * B200_SATD_WORDS * 4) + 512;
+  for (int lv = 0; lv < B200_LEVELS; lv++) b += align256(j.n_blk(lv) * sizeof(B200BlockDec)) + align256(j.n_blk(lv) * B200_SATD_WORDS * 4) + align256(j.n_blk(lv) * 4) + 768;
   if (j.uses_lr()) b += P * (align256(j.plane_bytes()) + align256(j.dbrows_bytes()) + align256(j.n_lr() * sizeof(B200LrUnit)));
   // the job descriptor and tile list issue_rdo() uploads (one entry per job / tile)
   b += align256(sizeof(B200RdoJob)) + align256((size_t)j.f.tile_rows * j.f.tile_cols * sizeof(B200TileRef)) + 512 + 3 * sizeof(CUtensorMap) + 256;
@@ -293,7 +294,9 @@ void job_take(FrameJob &j, Arena &dev, Arena &pin, bool own_src) {
   for (int lv = 0; lv < B200_LEVELS; lv++) {
     j.d_dec[lv] = dev.take<B200BlockDec>(j.n_blk(lv));
     j.d_satd[lv] = dev.take<uint32_t>(j.n_blk(lv) * B200_SATD_WORDS);
+    j.d_list[lv] = dev.take<uint32_t>(j.n_blk(lv));
   }
+  j.d_list_n = dev.take<uint32_t>(B200_LEVELS);
   j.d_cdef = dev.take<int8_t>(j.n_sb());
   j.h_cdef = pin.take<int8_t>(j.n_sb());
   j.d_lf_sse = dev.take<unsigned long long>(3 * B200_LF_CANDIDATES);
@@ -397,7 +400,8 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
       r.src[p] = j.d_src[q]; r.rec[p] = j.d_rec[q]; r.eob[p] = j.d_eob[q]; r.coef[p] = j.d_coef[q]; r.stream_len[p] = j.d_stream_len[q];
     }
     r.mi = j.d_mi;
-    for (int lv = 0; lv < B200_LEVELS; lv++) { r.dec[lv] = j.d_dec[lv]; r.satd[lv] = j.d_satd[lv]; }
+    for (int lv = 0; lv < B200_LEVELS; lv++) { r.dec[lv] = j.d_dec[lv]; r.satd[lv] = j.d_satd[lv]; r.list[lv] = j.d_list[lv]; }
+    r.list_n = j.d_list_n;
     r.cdef_idx = j.d_cdef;
     r.lf_sse = j.d_lf_sse; r.lf_out = j.d_lf_out;
     for (int p = 0; p < 3; p++) { r.fin[p] = j.d_fin[p < j.f.planes ? p : 0]; r.dbrows[p] = p < j.f.planes ? j.d_dbrows[p] : nullptr; r.deb_full[p] = p < j.f.planes ? j.d_deb_full[p] : nullptr; }

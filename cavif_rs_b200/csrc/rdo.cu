@@ -228,6 +228,12 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
     if (active && lv < B200_LEVELS - 1) {
       const int blk = gid % (cols * rows);
       active = !b200_pruned_by_parent(f, lv, blk % cols, blk / cols, job.dec[lv + 1]);   // top-down pruning
+      if (!active) {                       // never split down to this block
+        B200BlockDec d;
+        d.cost = B200_COST_PRUNED; d.y_mode = 0; d.tx_type = 0; d.uv_mode = 0; d.all_zero = 0; d.angle_y = 0; d.angle_uv = 0;
+        d.cfl_js = 0; d.cfl_alpha = 0;
+        job.dec[lv][blk] = d;
+      }
     }
     const unsigned m = __ballot_sync(FULL, active);
     int off = 0;
@@ -237,6 +243,12 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
   }
   __syncthreads();
   const int cnt = s_n;
+  // the survivors also go to the level's global list (walked by the lock-step analysis kernel)
+  __shared__ unsigned s_goff;
+  if (threadIdx.x == 0 && cnt) s_goff = atomicAdd(&job.list_n[lv], (unsigned)cnt);
+  __syncthreads();
+#pragma unroll 1
+  for (int i = threadIdx.x; i < cnt; i += 128) job.list[lv][s_goff + i] = (uint32_t)(base + s_list[i]);
 #pragma unroll 1
   for (int i = threadIdx.x; i < cnt; i += 128) satd_item<PIX>(job, lv, base + s_list[i], sh_d);
 }
@@ -249,6 +261,7 @@ __global__ void __launch_bounds__(128) b200_satd_direct_kernel(const B200RdoJob 
   const B200Frame *f = &job.frame;
   const int n = 4 << lv;
   if (n < min(f->partition_min, 8) || n > f->partition_max) return;
+  if (blockIdx.x == 0 && threadIdx.x < B200_LEVELS && job.list_n) job.list_n[threadIdx.x] = 0;      // first kernel of the stage: reset the survivor lists
   const int total = b200_level_cols(f, lv) * b200_level_rows(f, lv);
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
@@ -431,6 +444,35 @@ __global__ void __launch_bounds__(kThreads * W, W == 6 ? 3 : (LV == 3 ? 4 : (LV 
   }
 }
 
+// Pruned levels: the W warps of a CTA take W consecutive entries of the level's SURVIVOR LIST (built by the SATD kernel) and
+// analyse them in lock-step, exactly like the top level - no pruned block is ever visited, no warp idles inside a segment, and
+// the warps of a CTA share one instruction stream (free-running warps lose most issue slots to instruction fetch here:
+// stall_no_instruction 6-10 warps per issue, profiles/).  CTAs walk the list grid-stride.
+template <int LV, bool HBD, int W>
+__global__ void __launch_bounds__(kThreads * W, (LV == 2 ? 16 : 24) / W) b200_analyze_listed_kernel(const B200RdoJob *jobs) {
+  typedef typename PixOf<HBD>::type PIX;
+  typedef SharedT<16, PIX> SH;
+  __shared__ SH shs[W];
+  SH &sh = shs[threadIdx.x >> 5];
+  const B200RdoJob &job = jobs[blockIdx.y];
+  const B200Frame *f = &job.frame;
+  constexpr int lv = LV, n = 4 << LV;
+  if (n < min(f->partition_min, 8) || n > f->partition_max) return;
+  TileCtx t;
+  ctx_from_job(job, t);
+  const int cols = b200_level_cols(f, lv);
+  const int total = (int)job.list_n[lv];
+  const int per_iter = gridDim.x * W, iters = (total + per_iter - 1) / per_iter;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    const int want = (it * gridDim.x + blockIdx.x) * W + (threadIdx.x >> 5);
+    const int blk = (int)job.list[lv][want < total ? want : total - 1];        // padding warps repeat the last entry, output discarded
+    const int x = (blk % cols) * n, y = (blk / cols) * n;
+    tile_of_unit(f, y >> 2, x >> 2, t);
+    analyze_block<2 + LV, HBD, true>(t, sh, x, y, job.satd[lv] + (size_t)blk * B200_SATD_WORDS, want < total ? job.dec[lv] + blk : nullptr);
+  }
+}
+
 // ---- stage B: partition decision, one thread per 16x16 region (oracle orc_decide_region)
 namespace {
 __device__ __forceinline__ long long part_cost0(const B200Frame *f, const B200RateTables *rt, int mi_r, int mi_c, int n, int split) {
@@ -518,6 +560,8 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
 #define B200_CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
     B200_CARVE((b200_analyze_kernel<2, false, kAnalyzeWarpsTop>)); B200_CARVE((b200_analyze_kernel<2, true, kAnalyzeWarpsTop>));
     B200_CARVE((b200_analyze_kernel<2, false, 6>));
+    B200_CARVE((b200_analyze_listed_kernel<0, false, 4>)); B200_CARVE((b200_analyze_listed_kernel<1, false, 4>)); B200_CARVE((b200_analyze_listed_kernel<2, false, 4>));
+    B200_CARVE((b200_analyze_listed_kernel<0, true, 4>)); B200_CARVE((b200_analyze_listed_kernel<1, true, 4>)); B200_CARVE((b200_analyze_listed_kernel<2, true, 4>));
     B200_CARVE((b200_analyze_kernel<3, false, kAnalyzeWarpsTop32>)); B200_CARVE((b200_analyze_kernel<3, true, kAnalyzeWarpsTop32>));
     B200_CARVE((b200_analyze_kernel<0, false, 1>)); B200_CARVE((b200_analyze_kernel<1, false, 1>)); B200_CARVE((b200_analyze_kernel<2, false, 1>));
     B200_CARVE((b200_analyze_kernel<0, true, 1>)); B200_CARVE((b200_analyze_kernel<1, true, 1>)); B200_CARVE((b200_analyze_kernel<2, true, 1>));
@@ -560,9 +604,18 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
         dim3 gt((per_job + kAnalyzeWarpsTop - 1) / kAnalyzeWarpsTop, n_jobs);
         B200_ANALYZE(2, kAnalyzeWarpsTop, gt);
       }
-    } else if (lv == 2) B200_ANALYZE(2, 1, ga);
-    else if (lv == 1) B200_ANALYZE(1, 1, ga);
-    else B200_ANALYZE(0, 1, ga);
+    } else {
+      static const bool free_running = getenv("B200AVIF_FREE_RUNNING") != nullptr;      // A/B knob: the single-warp kernels of round 1
+      if (free_running) {
+        if (lv == 2) B200_ANALYZE(2, 1, ga); else if (lv == 1) B200_ANALYZE(1, 1, ga); else B200_ANALYZE(0, 1, ga);
+      } else {
+        dim3 gl(min((nblk + 3) / 4, max(1, (148 * 12) / n_jobs)), n_jobs);
+#define B200_ANALYZE_LISTED(LV) \
+        do { if (high_bitdepth) b200_analyze_listed_kernel<LV, true, 4><<<gl, kThreads * 4, 0, st>>>(d_jobs); \
+             else b200_analyze_listed_kernel<LV, false, 4><<<gl, kThreads * 4, 0, st>>>(d_jobs); } while (0)
+        if (lv == 2) B200_ANALYZE_LISTED(2); else if (lv == 1) B200_ANALYZE_LISTED(1); else B200_ANALYZE_LISTED(0);
+      }
+    }
     B200_MARK(lv == 3 ? "analyze_32x32" : (lv == 2 ? "analyze_16x16" : (lv == 1 ? "analyze_8x8" : "analyze_4x4")), st);
     n_launch++;
   }
@@ -598,11 +651,11 @@ static void emu_satd(void *) {
 static void emu_analyze(void *) {
   const bool hbd = g_emu_jobs[0].frame.bit_depth > 8;
 #define EMU_ANALYZE(LV, W) do { if (hbd) b200_analyze_kernel<LV, true, W>(g_emu_jobs); else b200_analyze_kernel<LV, false, W>(g_emu_jobs); } while (0)
-  if (g_emu_lv == 0) EMU_ANALYZE(0, 1);
-  else if (g_emu_lv == 1) EMU_ANALYZE(1, 1);
-  else if (g_emu_lv == 2 && g_emu_top == 2) EMU_ANALYZE(2, kAnalyzeWarpsTop);
-  else if (g_emu_lv == 2) EMU_ANALYZE(2, 1);
-  else EMU_ANALYZE(3, kAnalyzeWarpsTop32);
+#define EMU_LISTED(LV) do { if (hbd) b200_analyze_listed_kernel<LV, true, 4>(g_emu_jobs); else b200_analyze_listed_kernel<LV, false, 4>(g_emu_jobs); } while (0)
+  if (g_emu_lv == g_emu_top) { if (g_emu_top == 3) EMU_ANALYZE(3, kAnalyzeWarpsTop32); else EMU_ANALYZE(2, kAnalyzeWarpsTop); }
+  else if (g_emu_lv == 2) EMU_LISTED(2);
+  else if (g_emu_lv == 1) EMU_LISTED(1);
+  else EMU_LISTED(0);
 }
 static void emu_decide(void *) { b200_decide_kernel(g_emu_jobs); }
 extern "C" int b200_recon_launch_emu(const B200RdoJob *jobs, const B200TileRef *tiles, int n_tiles, int rows);
@@ -615,7 +668,7 @@ extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *ti
     if (nblk == 0) continue;
     const int items = g_emu_lv == g_emu_top ? 128 : kSatdItems;
     emu::launch(emu_satd, nullptr, (unsigned)((nblk + items - 1) / items), 128);
-    const int w = g_emu_lv == 3 ? kAnalyzeWarpsTop32 : ((g_emu_lv == 2 && g_emu_top == 2) ? kAnalyzeWarpsTop : 1);
+    const int w = g_emu_lv == g_emu_top ? (g_emu_top == 3 ? kAnalyzeWarpsTop32 : kAnalyzeWarpsTop) : 4;
     emu::launch(emu_analyze, nullptr, (unsigned)std::min(nblk, w > 1 ? 3 : 7), kThreads * w);
   }
   const int rn4 = g_emu_top == 3 ? 8 : 4;

@@ -25,6 +25,10 @@ typedef struct B200RdoJob {
   uint32_t *stream_len[3];
   B200BlockDec *dec[B200_LEVELS];   // analysis decisions per level (0: 4x4 .. 3: 32x32), b200_level_rows*cols entries
   uint32_t *satd[B200_LEVELS];      // luma SATD tables per level: [block][14 words]
+  // survivors of the top-down pruning per level: block indices appended by the SATD kernel (any order), count in list_n[lv];
+  // the lock-step analysis of the pruned levels walks these lists
+  uint32_t *list[B200_LEVELS];
+  uint32_t *list_n;                 // [B200_LEVELS], zeroed by the top-level SATD kernel
   // in-loop filter stage (filters.cu): rec is read only (deblocking happens on a staged copy); cdef_idx receives the per-superblock
   // strength index (-1: nothing coded in the superblock); fin (optional, may be NULL) receives the CDEF output.
   int8_t *cdef_idx;       // sb_rows*sb_cols

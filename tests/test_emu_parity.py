@@ -11,7 +11,7 @@ class RdoJob(ctypes.Structure):
     _fields_ = [("frame", H.B200Frame), ("rate", ctypes.c_void_p), ("stride", ctypes.c_int32), ("reserved_", ctypes.c_int32),
                 ("src", ctypes.c_void_p * 3), ("rec", ctypes.c_void_p * 3),
                 ("mi", ctypes.c_void_p), ("eob", ctypes.c_void_p * 3), ("coef", ctypes.c_void_p * 3), ("stream_len", ctypes.c_void_p * 3),
-                ("dec", ctypes.c_void_p * H.LEVELS), ("satd", ctypes.c_void_p * H.LEVELS),
+                ("dec", ctypes.c_void_p * H.LEVELS), ("satd", ctypes.c_void_p * H.LEVELS), ("list", ctypes.c_void_p * H.LEVELS), ("list_n", ctypes.c_void_p),
                 ("cdef_idx", ctypes.c_void_p), ("fin", ctypes.c_void_p * 3), ("lf_sse", ctypes.c_void_p), ("lf_out", ctypes.c_void_p), ("dbrows", ctypes.c_void_p * 3), ("deb_full", ctypes.c_void_p * 3),
                 ("lr", ctypes.c_void_p * 3), ("lr_out", ctypes.c_void_p * 3)]
 
@@ -107,7 +107,11 @@ def test_emulated_kernel_matches_oracle(w, h, depth, planes, tiles, kw, rows):
     for p in range(3):
         job.stream_len[p] = slen[p].ctypes.data
     job.mi = out.mi.ctypes.data
+    lists = [np.zeros(max((f.mi_rows >> lv) * (f.mi_cols >> lv), 1), np.uint32) for lv in range(H.LEVELS)]
+    list_n = np.zeros(H.LEVELS, np.uint32)
+    job.list_n = list_n.ctypes.data
     for lv in range(H.LEVELS):
+        job.list[lv] = lists[lv].ctypes.data
         job.dec[lv] = out.dec[lv].ctypes.data; job.satd[lv] = out.satd[lv].ctypes.data
     nt = f.tile_cols * f.tile_rows
     trs = (TileRef * nt)()
