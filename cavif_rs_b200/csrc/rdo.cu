@@ -253,6 +253,12 @@ __global__ void __launch_bounds__(128) b200_satd_kernel(const B200RdoJob *jobs, 
   for (int i = threadIdx.x; i < cnt; i += 128) satd_item<PIX>(job, lv, base + s_list[i], sh_d);
 }
 
+// first launch of the stage: empty survivor lists for every job of the launch
+__global__ void b200_list_reset_kernel(const B200RdoJob *jobs, int n_jobs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_jobs * B200_LEVELS && jobs[i / B200_LEVELS].list_n) jobs[i / B200_LEVELS].list_n[i % B200_LEVELS] = 0;
+}
+
 // never-pruned top level: one item per thread, no compaction
 template <class PIX>
 __global__ void __launch_bounds__(128) b200_satd_direct_kernel(const B200RdoJob *jobs, int lv) {
@@ -261,7 +267,6 @@ __global__ void __launch_bounds__(128) b200_satd_direct_kernel(const B200RdoJob 
   const B200Frame *f = &job.frame;
   const int n = 4 << lv;
   if (n < min(f->partition_min, 8) || n > f->partition_max) return;
-  if (blockIdx.x == 0 && threadIdx.x < B200_LEVELS && job.list_n) job.list_n[threadIdx.x] = 0;      // first kernel of the stage: reset the survivor lists
   const int total = b200_level_cols(f, lv) * b200_level_rows(f, lv);
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
@@ -568,6 +573,8 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
     configured = true;
   }
   const int top = top_level >= 3 ? 3 : 2;
+  b200_list_reset_kernel<<<(n_jobs * B200_LEVELS + 127) / 128, 128, 0, st>>>(d_jobs, n_jobs);
+  n_launch++;
   B200_MARK(nullptr, st);
   for (int lv = top; lv >= 0; lv--) {   // large to small: every level is pruned by its parent level
     const int nblk = max_blocks4 >> (2 * lv);
@@ -663,6 +670,7 @@ extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *ti
   g_emu_jobs = jobs; g_emu_tiles = tiles;
   const B200Frame *f = &jobs[0].frame;
   g_emu_top = f->partition_max >= 32 ? 3 : 2;
+  if (jobs[0].list_n) for (int k = 0; k < B200_LEVELS; k++) jobs[0].list_n[k] = 0;
   for (g_emu_lv = g_emu_top; g_emu_lv >= 0; g_emu_lv--) {
     const int nblk = (f->mi_rows >> g_emu_lv) * (f->mi_cols >> g_emu_lv);
     if (nblk == 0) continue;

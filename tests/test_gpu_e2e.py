@@ -117,6 +117,19 @@ def test_odd_sizes_match_cpu_pipeline(w, h):
     assert im.size == (w, h)
 
 
+@pytest.mark.parametrize("w,h,speed,quality", [(17, 9, 1, 70.0), (40, 24, 1, 70.0), (200, 136, 2, 70.0), (24, 24, 2, 95.0)])
+def test_mixed_partition_ranges_in_one_launch(w, h, speed, quality):
+    """speed <= 2: the colour frame (quantizer > 121: blocks up to 16x16) and the alpha frame (up to 32x32) of one image go through
+    the same launches with different top levels; frames smaller than a 32x32 block have no block at the top level at all"""
+    import cpu_encode as CE
+    m = C()
+    img = H.synth_image(w, h, w + 3 * h, alpha=True)
+    r = m.Encoder.new().with_quality(quality).with_speed(speed).with_bit_depth(8).encode_rgba(img)
+    ref = CE.encode_rgba(img, quality, speed, 8)
+    col, al = payloads(r.avif_file)
+    assert col == ref["color_obu"] and al == ref["alpha_obu"]
+
+
 def test_premultiplied_mode_matches_cpu_pipeline():
     import cpu_encode as CE
     m = C()
