@@ -67,9 +67,18 @@ double g_ms_rdo = 0, g_ms_total = 0, g_ms_pack = 0;
   } while (0)
 
 // ---- a tiny thread pool for symbol packing -------------------------------------------------------
+// Host threads this process may use for packing: the usable cores (affinity mask bounded by the cgroup quota,
+// RAYON_NUM_THREADS override) divided by the processes that share the node (LOCAL_WORLD_SIZE under torchrun: one process
+// per GPU), B200AVIF_PACK_THREADS overrides.  Eight ranks on one node do not start 8 x all-cores packer threads.
+unsigned packer_threads() {
+  if (const char *ev = getenv("B200AVIF_PACK_THREADS")) { const long v = atol(ev); if (v > 0) return (unsigned)v; }
+  size_t n = b200_host_threads();
+  if (const char *ev = getenv("LOCAL_WORLD_SIZE")) { const long v = atol(ev); if (v > 1) n = (n + (size_t)v - 1) / (size_t)v; }
+  return (unsigned)std::max<size_t>(n, 1);
+}
+
 void parallel_for(size_t n, const std::function<void(size_t)> &fn) {
-  unsigned hw = std::thread::hardware_concurrency();
-  if (hw == 0) hw = 4;
+  const unsigned hw = packer_threads();
   const size_t nt = std::min<size_t>(hw, n);
   if (nt <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
   std::atomic<size_t> next{0};
@@ -593,8 +602,7 @@ int run_rdo_and_fetch(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Are
 void pack_jobs(std::vector<FrameJob *> &jobs) {
   const auto t0 = std::chrono::steady_clock::now();
   {   // few frames (one large image): spread each frame's tiles over the idle host threads
-    unsigned hw = std::thread::hardware_concurrency();
-    if (hw == 0) hw = 4;
+    const unsigned hw = packer_threads();
     b200av1_pack_set_tile_threads(jobs.size() * 2 <= hw ? (int)(hw / std::max<size_t>(jobs.size(), 1)) : 1);
   }
   parallel_for(jobs.size(), [&](size_t i) {

@@ -286,10 +286,18 @@ struct LrShared {
   // raw box sums of the band, shared by every candidate set: 3x3 at all A/B rows, 5x5 at the odd rows only
   uint32_t R3a[kLrAH * kLrAW], R5a[((kLrAH + 1) / 2) * kLrAW];
   uint16_t R3b[kLrAH * kLrAW], R5b[((kLrAH + 1) / 2) * kLrAW];
+  uint16_t xbx[256];      // x_by_xplus1 (spec 7.17.3): indexed by the per-lane variance, so a shared-memory copy (a __constant__ read serialises over distinct addresses)
   unsigned long long acc[B200_LR_CANDIDATES_FULL][6];     // per candidate set: H00, H01, H11, C0, C1 (two's complement), S
   B200LrUnit best;
 };
 
+// floor(i / d) by reciprocal multiplication, magic = ceil(2^20 / d): exact while i < 2^20 / d (here i < 22 * d, d <= 102)
+struct LrDiv { uint32_t d, magic; };
+__device__ __forceinline__ LrDiv lr_div_make(int d) { LrDiv r; r.d = (uint32_t)d; r.magic = ((1u << 20) + (uint32_t)d - 1) / (uint32_t)d; return r; }
+__device__ __forceinline__ void lr_divmod(int i, const LrDiv &dv, int &q, int &r) {
+  q = (int)(((uint32_t)i * dv.magic) >> 20);
+  r = i - q * (int)dv.d;
+}
 __device__ __forceinline__ long long lr_round2(long long v, int n) { return n == 0 ? v : ((v + (1ll << (n - 1))) >> n); }
 
 // box sums of radius r around staged sample (sy, sx)
@@ -303,12 +311,20 @@ __device__ __forceinline__ void lr_box(const uint16_t *S, int sy, int sx, int r,
   *a_out = a; *b_out = b;
 }
 // box sums -> a2 (A entry) and B entry for one parameter set (AV1 spec 7.17.4)
-__device__ __forceinline__ void lr_ab(uint32_t a, uint32_t b, int bd, uint32_t s, uint32_t one_by_n, int n, uint16_t *a_out, int32_t *b_out) {
-  const uint32_t a_s = (uint32_t)lr_round2(a, 2 * (bd - 8)), d = (uint32_t)lr_round2(b, bd - 8);
-  const long long pp = (long long)a_s * n - (long long)d * d;
-  const unsigned long long p = pp < 0 ? 0ull : (unsigned long long)pp;
+// B8 (8-bit samples): no pre-scaling, and a * n, d * d <= 25 * 25 * 255^2 fit 32 bits
+template <bool B8>
+__device__ __forceinline__ void lr_ab(const uint16_t *xbx, uint32_t a, uint32_t b, int bd, uint32_t s, uint32_t one_by_n, int n, uint16_t *a_out, int32_t *b_out) {
+  unsigned long long p;
+  if (B8) {
+    const int32_t pp = (int32_t)(a * (uint32_t)n) - (int32_t)(b * b);
+    p = pp < 0 ? 0u : (uint32_t)pp;
+  } else {
+    const uint32_t a_s = (uint32_t)lr_round2(a, 2 * (bd - 8)), d = (uint32_t)lr_round2(b, bd - 8);
+    const long long pp = (long long)a_s * n - (long long)d * d;
+    p = pp < 0 ? 0ull : (unsigned long long)pp;
+  }
   const unsigned long long z = (p * s + (1u << 19)) >> 20;
-  const uint32_t a2 = dv_x_by_xplus1[z > 255 ? 255 : (int)z];
+  const uint32_t a2 = xbx[z > 255 ? 255 : (int)z];
   *a_out = (uint16_t)a2;
   *b_out = (int32_t)(((256u - a2) * b * one_by_n + (1u << 11)) >> 12);      // (256 - a2) * b * one_by_n < 2^31 for r = 1 and r = 2
 }
@@ -359,7 +375,10 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
   const PIX *deb = (const PIX *)job.dbrows[plane], *cdef = (const PIX *)job.fin[plane], *src = (const PIX *)job.src[plane];
   PIX *lr_out = (PIX *)job.lr_out[plane];
   const int tid = threadIdx.x;
+  // the loops below walk (rows x columns) index spaces of at most 22 x 102 entries: row / column by reciprocal multiplication
+  const LrDiv dv_w = lr_div_make(w), dv_w2 = lr_div_make(w + 2), dv_w6 = lr_div_make(w + 6);
   for (int i = tid; i < B200_LR_CANDIDATES_FULL * 6; i += 256) sh.acc[i / 6][i % 6] = 0;
+  sh.xbx[tid] = dv_x_by_xplus1[tid];
   __syncthreads();
   const int8_t cand[B200_LR_CANDIDATES] = {B200_LR_SETS};
   // sgr_complexity_full (ravif SpeedTweaks, av1encoder.rs:573): every one of the 16 parameter sets, else four
@@ -374,7 +393,8 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
       const int ye = min(min(s_end + 1, y1), ys + kLrBandH), bh = ye - ys;
       // stage the samples (AV1 spec 7.17.6 get_source_sample)
       for (int i = tid; i < (bh + 6) * (w + 6); i += 256) {
-        const int sy = i / (w + 6), sx = i % (w + 6);
+        int sy, sx;
+        lr_divmod(i, dv_w6, sy, sx);
         int y = ys + sy - 3, x = x0 + sx - 3;
         x = min(max(x, 0), W - 1); y = min(max(y, 0), H - 1);
         uint16_t v;
@@ -386,13 +406,15 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
       __syncthreads();
       // raw box sums, once per band
       for (int i = tid; i < (bh + 2) * (w + 2); i += 256) {
-        const int ai = i / (w + 2), aj = i % (w + 2);
+        int ai, aj;
+        lr_divmod(i, dv_w2, ai, aj);
         uint32_t a, b;
         lr_box(sh.S, ai + 2, aj + 2, 1, &a, &b);
         sh.R3a[ai * kLrAW + aj] = a; sh.R3b[ai * kLrAW + aj] = (uint16_t)b;
       }
       for (int i = tid; i < ((bh + 3) / 2) * (w + 2); i += 256) {
-        const int ri = i / (w + 2), aj = i % (w + 2);          // A row index 2 * ri <-> i = -1, 1, 3, ...
+        int ri, aj;                                            // A row index 2 * ri <-> i = -1, 1, 3, ...
+        lr_divmod(i, dv_w2, ri, aj);
         uint32_t a, b;
         lr_box(sh.S, 2 * ri + 2, aj + 2, 2, &a, &b);
         sh.R5a[ri * kLrAW + aj] = a; sh.R5b[ri * kLrAW + aj] = (uint16_t)b;
@@ -403,7 +425,8 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
         const int set = phase == 0 ? LR_SET_OF(ci) : sh.best.set;
         if (phase == 1 && !sh.best.use) {       // restoration off in this unit: the CDEF samples pass through
           for (int i = tid; i < bh * w; i += 256) {
-            const int py = i / w, px = i % w;
+            int py, px;
+            lr_divmod(i, dv_w, py, px);
             lr_out[(ys + py) * stride + x0 + px] = (PIX)sh.S[(py + 3) * kLrSW + px + 3];
           }
           continue;
@@ -419,16 +442,18 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
             // A / B at rows -1..bh (pass 0: odd rows only), columns -1..w
             const int rows = pass == 0 ? (bh + 3) / 2 : bh + 2;
             for (int i = tid; i < rows * (w + 2); i += 256) {
-              const int ri = i / (w + 2), aj = i % (w + 2);
+              int ri, aj;
+              lr_divmod(i, dv_w2, ri, aj);
               const int ai = pass == 0 ? ri * 2 : ri;             // A row index = i + 1, i = -1, 1, 3, ... in the r = 2 pass
               const uint32_t a = pass == 0 ? sh.R5a[ri * kLrAW + aj] : sh.R3a[ri * kLrAW + aj];
               const uint32_t b = pass == 0 ? sh.R5b[ri * kLrAW + aj] : sh.R3b[ri * kLrAW + aj];
-              lr_ab(a, b, bd, s, one_by_n, n, &sh.A[ai * kLrAW + aj], &sh.B[ai * kLrAW + aj]);
+              lr_ab<sizeof(PIX) == 1>(sh.xbx, a, b, bd, s, one_by_n, n, &sh.A[ai * kLrAW + aj], &sh.B[ai * kLrAW + aj]);
             }
           }
           __syncthreads();
           for (int i = tid; i < bh * w; i += 256) {
-            const int py = i / w, px = i % w;
+            int py, px;
+            lr_divmod(i, dv_w, py, px);
             const int u_px = sh.S[(py + 3) * kLrSW + px + 3];
             int32_t fv = 0;
             if (r) {
@@ -461,7 +486,8 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
               const int u = u_px << 4;
               const int sv = ((int)src[(ys + py) * stride + x0 + px] << 4) - u;
               const int av = r0 ? f0 - u : 0, bv = r1 ? f1 - u : 0;
-              h00 += av * av; h01 += av * bv; h11 += bv * bv; c0 += av * sv; c1 += bv * sv; ss += sv * sv;
+              h00 += (long long)av * av; h01 += (long long)av * bv; h11 += (long long)bv * bv;
+              c0 += (long long)av * sv; c1 += (long long)bv * sv; ss += (long long)sv * sv;
             } else {
               const int w0 = sh.best.xqd0, w1 = sh.best.xqd1, w2 = 128 - w0 - w1;
               const long long u = (long long)u_px << 4;
