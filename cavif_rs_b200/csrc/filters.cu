@@ -283,6 +283,7 @@ struct LrShared {
   uint16_t A[kLrAH * kLrAW];
   int32_t B[kLrAH * kLrAW];
   uint16_t F0[kLrBandH * kLrMaxW];
+  uint16_t SRC[kLrBandH * kLrMaxW];     // source samples of the band (read once per band instead of once per candidate set)
   // raw box sums of the band, shared by every candidate set: 3x3 at all A/B rows, 5x5 at the odd rows only
   uint32_t R3a[kLrAH * kLrAW], R5a[((kLrAH + 1) / 2) * kLrAW];
   uint16_t R3b[kLrAH * kLrAW], R5b[((kLrAH + 1) / 2) * kLrAW];
@@ -403,6 +404,12 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
         else v = cdef[y * stride + x];
         sh.S[sy * kLrSW + sx] = v;
       }
+      if (phase == 0)
+        for (int i = tid; i < bh * w; i += 256) {
+          int py, px;
+          lr_divmod(i, dv_w, py, px);
+          sh.SRC[py * kLrMaxW + px] = src[(ys + py) * stride + x0 + px];
+        }
       __syncthreads();
       // raw box sums, once per band
       for (int i = tid; i < (bh + 2) * (w + 2); i += 256) {
@@ -432,9 +439,12 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
           continue;
         }
         const int r0 = dv_sgr_params[set][0], r1 = dv_sgr_params[set][1];
-        long long h00 = 0, h01 = 0, h11 = 0, c0 = 0, c1 = 0, ss = 0;
+        // per-thread partial sums of the band: at most ceil(16 * 95 / 256) = 6 pixels, every product below 2^28 in
+        // magnitude (|f - u|, |src - u| < 2^14 at 10 bits) -> 32-bit accumulators, widened at the warp reduction
+        int32_t h00 = 0, h01 = 0, h11 = 0, c0 = 0, c1 = 0, ss = 0;
         for (int pass = 0; pass < 2; pass++) {
           const int r = pass == 0 ? r0 : r1;
+          if (pass == 0 && !r) continue;        // no first filter in this set: F0 is not read
           if (r) {
             const uint32_t s = (uint32_t)dv_sgr_params[set][2 + pass];
             const int n = (2 * r + 1) * (2 * r + 1);
@@ -480,14 +490,13 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
               }
             }
             if (pass == 0) { sh.F0[py * kLrMaxW + px] = (uint16_t)fv; continue; }
-            const int32_t f0 = sh.F0[py * kLrMaxW + px], f1 = fv;
+            const int32_t f0 = r0 ? sh.F0[py * kLrMaxW + px] : 0, f1 = fv;
             if (phase == 0) {
-              // |av|, |bv|, |sv| < 2^15: the products fit 32 bits, only the sums are 64-bit
               const int u = u_px << 4;
-              const int sv = ((int)src[(ys + py) * stride + x0 + px] << 4) - u;
+              const int sv = ((int)sh.SRC[py * kLrMaxW + px] << 4) - u;
               const int av = r0 ? f0 - u : 0, bv = r1 ? f1 - u : 0;
-              h00 += (long long)av * av; h01 += (long long)av * bv; h11 += (long long)bv * bv;
-              c0 += (long long)av * sv; c1 += (long long)bv * sv; ss += (long long)sv * sv;
+              h00 += av * av; h01 += av * bv; h11 += bv * bv; c0 += av * sv; c1 += bv * sv;
+              if (ci == 0) ss += sv * sv;       // the same for every set: only the first one is used
             } else {
               const int w0 = sh.best.xqd0, w1 = sh.best.xqd1, w2 = 128 - w0 - w1;
               const long long u = (long long)u_px << 4;
@@ -502,11 +511,14 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
           __syncthreads();
         }
         if (phase == 0) {
-          long long v[6] = {h00, h01, h11, c0, c1, ss};
+          const int32_t v[6] = {h00, h01, h11, c0, c1, ss};
 #pragma unroll
           for (int k = 0; k < 6; k++) {
-            for (int m = 16; m > 0; m >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], m);
-            if ((tid & 31) == 0 && v[k]) atomicAdd(&sh.acc[ci][k], (unsigned long long)v[k]);
+            if (k == 5 && ci != 0) continue;
+            // exact 64-bit warp sum from two 32-bit hardware reductions: v = (v >> 16) * 65536 + (v & 0xffff)
+            const int lo = __reduce_add_sync(0xffffffffu, v[k] & 0xffff), hi = __reduce_add_sync(0xffffffffu, v[k] >> 16);
+            const long long tot = (long long)hi * 65536 + lo;
+            if ((tid & 31) == 0 && tot) atomicAdd(&sh.acc[ci][k], (unsigned long long)tot);
           }
         }
       }
@@ -655,7 +667,9 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
   for (int pass = 0; pass < 2; pass++) {
     const int span = pass == 0 ? kFW : 68;
     for (int i = tid; i < f->planes * 17 * span; i += 256) {
-      const int plane = i / (17 * span), k = (i / span) % 17, j = i % span;
+      int plane, k, j;        // constant divisors (multiply-shift) in either pass
+      if (pass == 0) { plane = i / (17 * kFW); k = (i / kFW) % 17; j = i % kFW; }
+      else { plane = i / (17 * 68); k = (i / 68) % 17; j = i % 68; }
       const int lvl = plane == 0 ? f->lf_level[pass] : f->lf_level[plane + 1];
       if (!lvl) continue;
       int x, y;
@@ -832,7 +846,7 @@ __global__ void __launch_bounds__(256) b200_lf_search_kernel(const B200RdoJob *j
         for (int pass = 0; pass < 2; pass++) {
           const int span = pass == 0 ? kFW : 68;
           for (int i = tid; i < 17 * span; i += 256) {
-            const int kk = i / span, j = i % span;
+            const int kk = pass == 0 ? i / kFW : i / 68, j = pass == 0 ? i % kFW : i % 68;
             int x, y;
             if (pass == 0) { x = x0 + 4 * kk; y = y0 - kFH + j; } else { x = x0 - 2 + j; y = y0 + 4 * kk; }
             if (x < 0 || y < 0 || (x & ~3) >= f->width || (y & ~3) >= f->height) continue;

@@ -277,6 +277,86 @@ __global__ void __launch_bounds__(128) b200_satd_direct_kernel(const B200RdoJob 
   satd_item<PIX>(job, lv, gid, sh_d);
 }
 
+// Prediction of the 4x4 sub-block at (sy, sx) of an n x n block, mode m / angle delta, written to out[0..15] (row-major).
+// Same values as pred_px() pixel by pixel; the mode is resolved once per sub-block and every class walks the 16 pixels
+// with its own short loop (pred_px() re-derives the angle, the zone and the table entries for every pixel).
+__device__ __noinline__ void satd_pred4x4(int m, int delta, int n, int sy, int sx, const uint16_t *A, const uint16_t *L, int dc, int *out) {
+  if (m == DC_PRED) {
+#pragma unroll 1
+    for (int k = 0; k < 16; k++) out[k] = dc;
+    return;
+  }
+  if (m == PAETH_PRED) {
+    const int tl = A[-1];
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+      const int l = L[sy + i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int a = A[sx + j], b = a + l - tl;
+        const int pl = abs(b - l), pt = abs(b - a), ptl = abs(b - tl);
+        out[i * 4 + j] = (pl <= pt && pl <= ptl) ? l : (pt <= ptl ? a : tl);
+      }
+    }
+    return;
+  }
+  if (m >= SMOOTH_PRED) {
+    const uint8_t *w = dv_sm_weights + (n == 4 ? 0 : n == 8 ? 4 : n == 16 ? 12 : 28);
+    const int bl = L[n - 1], tr = A[n - 1];
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+      const int wi = w[sy + i], l = L[sy + i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int wj = w[sx + j];
+        const int v = wi * A[sx + j] + (256 - wi) * bl, h = wj * l + (256 - wj) * tr;
+        out[i * 4 + j] = m == SMOOTH_PRED ? (v + h + 256) >> 9 : (m == SMOOTH_V_PRED ? (v + 128) >> 8 : (h + 128) >> 8);
+      }
+    }
+    return;
+  }
+  const int p_angle = dv_mode_to_angle[m] + 3 * delta;
+  if (p_angle == 90 || p_angle == 180) {
+#pragma unroll 1
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) out[i * 4 + j] = p_angle == 90 ? A[sx + j] : L[sy + i];
+    return;
+  }
+  if (p_angle > 90 && p_angle < 180) {
+    const int dx = dv_dr_intra_derivative[180 - p_angle], dy = dv_dr_intra_derivative[p_angle - 90];
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+      const int ii = sy + i, rowx = (ii + 1) * dx;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int jj = sx + j;
+        int idx = (jj << 6) - rowx, base = idx >> 6;
+        const uint16_t *e = A;
+        if (base < -1) { idx = (ii << 6) - (jj + 1) * dy; base = idx >> 6; e = L; }
+        const int shift = (idx >> 1) & 31;
+        out[i * 4 + j] = (e[base] * (32 - shift) + e[base + 1] * shift + 16) >> 5;
+      }
+    }
+    return;
+  }
+  // zone 1 (above row, the walk depends on the pixel row) / zone 3 (left column, it depends on the pixel column)
+  const bool z1 = p_angle < 90;
+  const uint16_t *e = z1 ? A : L;
+  const int d = dv_dr_intra_derivative[z1 ? p_angle : 270 - p_angle], max_base = 2 * n - 1;
+  const int u0 = z1 ? sy : sx, v0 = z1 ? sx : sy;     // u: the coordinate the walk depends on, v: the other one
+#pragma unroll 1
+  for (int a = 0; a < 4; a++) {
+    const int idx = (u0 + a + 1) * d, b0 = (idx >> 6) + v0, shift = (idx >> 1) & 31;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int base = b0 + b;
+      const int v = base < max_base ? (e[base] * (32 - shift) + e[base + 1] * shift + 16) >> 5 : e[max_base];
+      out[z1 ? a * 4 + b : b * 4 + a] = v;
+    }
+  }
+}
+
 template <class PIX>
 __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid, int *sh_d) {
   const B200Frame *f = &job.frame;
@@ -354,8 +434,7 @@ __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid
           if (pass == 0 && !((mask >> c) & 1)) continue;
           const int m = pass ? md : c, delta = pass ? (c < 3 ? c - 3 : c - 2) : 0;
           int tt[16], d[16];
-#pragma unroll 1
-          for (int k = 0; k < 16; k++) sh_d[threadIdx.x * 17 + k] = pred_px(m, delta, n, sy + (k >> 2), sx + (k & 3), A, L, dc);
+          satd_pred4x4(m, delta, n, sy, sx, A, L, dc, sh_d + threadIdx.x * 17);
 #pragma unroll
           for (int k = 0; k < 16; k++) d[k] = s[k] - sh_d[threadIdx.x * 17 + k];
 #pragma unroll
