@@ -344,6 +344,16 @@ __device__ __forceinline__ int32_t clamp_bits(int32_t v, int bits) {
 // Code size matters (the instruction cache is the first bottleneck of this kernel): the function is NOT inlined,
 // each 1-D transform kernel appears once (two-pass loops), and the per-coefficient loops are rolled.
 struct TrialOut { int eob; uint32_t rate, sse; };
+// unroll factors of the per-coefficient quantisation / rate loops (A/B knobs: more ILP against a larger footprint)
+#ifndef B200_UQ
+#define B200_UQ 1
+#endif
+#ifndef B200_UR
+#define B200_UR 1
+#endif
+#define B200_STR2(x) #x
+#define B200_STR(x) B200_STR2(x)
+#define B200_UNROLL(n) _Pragma(B200_STR(unroll n))
 
 // RATE = false (reconstruction stage): the coefficient-rate model is skipped, TrialOut.rate is 0.
 template <int N, bool HBD, class SH, bool RATE = true>
@@ -393,7 +403,7 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
   {
     const uint32_t dc_q = (uint32_t)f->dc_q, ac_q = (uint32_t)f->ac_q;
     const uint32_t dc_rcp = 0xffffffffu / dc_q, ac_rcp = 0xffffffffu / ac_q;
-#pragma unroll 1
+    B200_UNROLL(B200_UQ)
     for (int c = 0; c < N; c++) {
       const int pos = l * N + c;
       const uint32_t q = pos == 0 ? dc_q : ac_q, rcp = pos == 0 ? dc_rcp : ac_rcp;
@@ -437,7 +447,7 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
         rate += 256u * (uint32_t)(nb - 1);
       }
     }
-#pragma unroll 1
+    B200_UNROLL(B200_UR)
     for (int c = 0; c < N; c++) {
       const int pos = l * N + c;
       const int si = scan_index<N>(txc, pos, l, c);

@@ -238,27 +238,29 @@ __device__ __forceinline__ int constrain_adj(int diff, int threshold, int adj) {
   const int v = max(0, min(mag, threshold - (mag >> adj)));
   return diff < 0 ? -v : v;
 }
-// one strength pair on loaded taps.  With only one of the two strengths the result provably stays inside the range of the
-// taps it used (total tap weight 12/16), so the spec's clip to [min, max] is the identity and is skipped.
-__device__ __forceinline__ int cdef_eval(const CdefTaps &t, int pri, int sec, int damping, int cshift) {
-  const int x = t.x;
-  if (!pri && !sec) return x;
-  int sum = 0;
-  if (pri) {
-    const int adj = max(0, damping - floor_log2_d((unsigned)pri));
-    const int w0 = ((pri >> cshift) & 1) ? 3 : 4, w1 = ((pri >> cshift) & 1) ? 3 : 2;
-    sum += w0 * (constrain_adj(t.p[0] - x, pri, adj) + constrain_adj(t.p[1] - x, pri, adj)) +
-           w1 * (constrain_adj(t.p[2] - x, pri, adj) + constrain_adj(t.p[3] - x, pri, adj));
-  }
-  if (sec) {
-    const int adj = max(0, damping - floor_log2_d((unsigned)sec));
-    int s0 = 0, s1 = 0;
+// One strength pair on loaded taps = cdef_finish(cdef_pri_sum + cdef_sec_sum).  With only one of the two strengths the
+// result provably stays inside the range of the taps it used (total tap weight 12/16), so the spec's clip to [min, max] is
+// the identity and is skipped (`both` = false).
+// weighted sum of the primary / secondary taps (pri, sec != 0); the secondary sum depends on the secondary strength only,
+// so candidate pairs that share it (the chroma sets do) share the sum
+__device__ __forceinline__ int cdef_pri_sum(const CdefTaps &t, int pri, int damping, int cshift) {
+  const int x = t.x, adj = max(0, damping - floor_log2_d((unsigned)pri));
+  const int w0 = ((pri >> cshift) & 1) ? 3 : 4, w1 = ((pri >> cshift) & 1) ? 3 : 2;
+  return w0 * (constrain_adj(t.p[0] - x, pri, adj) + constrain_adj(t.p[1] - x, pri, adj)) +
+         w1 * (constrain_adj(t.p[2] - x, pri, adj) + constrain_adj(t.p[3] - x, pri, adj));
+}
+__device__ __forceinline__ int cdef_sec_sum(const CdefTaps &t, int sec, int damping) {
+  const int x = t.x, adj = max(0, damping - floor_log2_d((unsigned)sec));
+  int s0 = 0, s1 = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) { s0 += constrain_adj(t.s[i] - x, sec, adj); s1 += constrain_adj(t.s[4 + i] - x, sec, adj); }
-    sum += 2 * s0 + s1;
-  }
+  for (int i = 0; i < 4; i++) { s0 += constrain_adj(t.s[i] - x, sec, adj); s1 += constrain_adj(t.s[4 + i] - x, sec, adj); }
+  return 2 * s0 + s1;
+}
+// sum: cdef_pri_sum (pri != 0) + cdef_sec_sum (sec != 0)
+__device__ __forceinline__ int cdef_finish(const CdefTaps &t, int sum, bool both) {
+  const int x = t.x;
   int y = x + ((8 + sum - (sum < 0)) >> 4);
-  if (pri && sec) {
+  if (both) {
     int mn = x, mx = x;
 #pragma unroll
     for (int i = 0; i < 4; i++) { mn = min(mn, t.p[i]); mx = max(mx, t.p[i]); }
@@ -759,6 +761,7 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
           vscale = var ? 4 + ((var >> 6) ? min(floor_log2_d((unsigned)(var >> 6)), 12) : 0) : 0;
         }
         const int src = apply ? 0 : (int)S[(size_t)yy * stride + xx];
+        int sec_cached = 0, sec_sum = 0;       // secondary tap sum of the last secondary strength seen (uniform over the CTA)
 #pragma unroll
         for (int k = 0; k < 8; k++) {
           if (k >= nidx || (apply && k != best)) continue;
@@ -772,7 +775,15 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
           else {
             int pri = pri0;
             if (p == 0 && pri) pri = vscale ? (pri * vscale + 8) >> 4 : 0;
-            v = cdef_eval(taps, pri, sec, damping, cshift);
+            if (!pri && !sec) v = taps.x;
+            else {
+              int sum = pri ? cdef_pri_sum(taps, pri, damping, cshift) : 0;
+              if (sec) {
+                if (sec != sec_cached) { sec_sum = cdef_sec_sum(taps, sec, damping); sec_cached = sec; }
+                sum += sec_sum;
+              }
+              v = cdef_finish(taps, sum, pri && sec);
+            }
           }
           if (apply) ((PIX *)job.fin[p])[(size_t)yy * stride + xx] = (PIX)v;
           else { const int d = v - src; sse[k] += (unsigned)(d * d); }

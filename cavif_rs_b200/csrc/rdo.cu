@@ -477,10 +477,13 @@ __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid
 // ---- stage A.2: full trials.  One single-warp CTA loops over blocks of level lv (grid-stride), grid.y = job.
 // W warps per CTA.  W == 1: free-running single-warp CTAs (grid-stride over the blocks).  W > 1 (the never-pruned top
 // level): the W warps of a CTA analyse W different blocks in lock-step (analyze_block<.., SYNC>).
+#ifndef B200_LV2_WARPS
+#define B200_LV2_WARPS 16     // resident warps per SM the 16x16 analysis kernels are compiled for (register budget 65536 / 32 / warps)
+#endif
 constexpr int kAnalyzeWarpsTop = 4;      // 16x16 as the top level
 constexpr int kAnalyzeWarpsTop32 = 2;    // 32x32 as the top level (22.9 KB of shared memory per warp)
 template <int LV, bool HBD, int W>
-__global__ void __launch_bounds__(kThreads * W, W == 6 ? 3 : (LV == 3 ? 4 : (LV == 2 ? 16 : 24) / W)) b200_analyze_kernel(const B200RdoJob *jobs) {
+__global__ void __launch_bounds__(kThreads * W, W == 6 ? 3 : (LV == 3 ? 4 : (LV == 2 ? B200_LV2_WARPS : 24) / W)) b200_analyze_kernel(const B200RdoJob *jobs) {
   typedef typename PixOf<HBD>::type PIX;
   typedef SharedT<(LV == 3 ? 32 : 16), PIX> SH;
   __shared__ SH shs[W];
@@ -533,7 +536,7 @@ __global__ void __launch_bounds__(kThreads * W, W == 6 ? 3 : (LV == 3 ? 4 : (LV 
 // the warps of a CTA share one instruction stream (free-running warps lose most issue slots to instruction fetch here:
 // stall_no_instruction 6-10 warps per issue, profiles/).  CTAs walk the list grid-stride.
 template <int LV, bool HBD, int W>
-__global__ void __launch_bounds__(kThreads * W, (LV == 2 ? 16 : 24) / W) b200_analyze_listed_kernel(const B200RdoJob *jobs) {
+__global__ void __launch_bounds__(kThreads * W, (LV == 2 ? B200_LV2_WARPS : 24) / W) b200_analyze_listed_kernel(const B200RdoJob *jobs) {
   typedef typename PixOf<HBD>::type PIX;
   typedef SharedT<16, PIX> SH;
   __shared__ SH shs[W];
@@ -673,7 +676,7 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
       n_launch++;
     }
     // enough warps to fill the machine several times over, grid-stride inside
-    const int per_job = min(nblk, max(1, (148 * 16 * 4) / n_jobs));
+    const int per_job = min(nblk, max(1, (148 * (lv == 2 ? B200_LV2_WARPS : 16) * 4) / n_jobs));
     dim3 ga(per_job, n_jobs);
 #define B200_ANALYZE(LV, W, GRID) \
     do { if (high_bitdepth) b200_analyze_kernel<LV, true, W><<<GRID, kThreads * W, 0, st>>>(d_jobs); \
