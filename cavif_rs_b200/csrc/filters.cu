@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
 // strength index.  Phase 4: apply the winner into job.fin (if present).
 
 template <class PIX>
-__global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs, const unsigned char *tmaps /* CUtensorMap[job][3] of the rec planes, or null */,
+__global__ void __launch_bounds__(256, 4) b200_dbcdef_kernel(const B200RdoJob *jobs, const unsigned char *tmaps /* CUtensorMap[job][3] of the rec planes, or null */,
                                                           int tma_x_shift /* 1: the maps describe 8-bit planes as 16-bit elements (x coordinate halves) */) {
   const B200RdoJob &job = jobs[blockIdx.y];
   const B200Frame *f = &job.frame;
@@ -599,6 +599,7 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
   __shared__ int s_dir[64], s_var[64], s_skip[64], s_any;
   __shared__ unsigned long long s_sse[8];
   __shared__ int s_best;
+  __shared__ uint32_t s_blk_s[64][2], s_blk_d[64][8][3];     // Psychovisual strength search: per 8x8 luma block sum / sum of squares of the source; per index sum, sum of squares of the output and the cross sum
 #ifdef B200_EMU
   static uint16_t s_px[3][kFW * kCdefTW];         // staged samples: rows y0-7 .. y0+70, columns x0-7 .. x0+70 (kCdefNA outside the frame)
 #else
@@ -614,6 +615,8 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
   if (tid < 16) s_off[tid >> 1][tid & 1] = (int16_t)(dv_cdef_dir[tid >> 1][tid & 1][0] * kCdefTW + dv_cdef_dir[tid >> 1][tid & 1][1]);
   if (tid == 0) s_any = 0;
   if (tid < 8) s_sse[tid] = 0;
+  for (int i = tid; i < 64 * 2; i += 256) (&s_blk_s[0][0])[i] = 0;
+  for (int i = tid; i < 64 * 8 * 3; i += 256) (&s_blk_d[0][0][0])[i] = 0;
   bool staged = false;
 #ifndef B200_EMU
   if (tmaps) {
@@ -743,16 +746,19 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
       const int32_t *strengths = p == 0 ? f->cdef_y_strength : f->cdef_uv_strength;
       const uint16_t *T = s_px[p];
       const PIX *S = (const PIX *)job.src[p];
+      // Tune::Psychovisual: luma is scored per 8x8 block with the variance-aware error of the trials (oracle cdef_sb_sse): the
+      // sums of a block row segment (8 lanes: same block, same row) are reduced with shuffles and added to the block's counters
+      const bool psy = !apply && p == 0 && f->psy;
       for (int i = tid; i < 4096; i += 256) {
         const int ly = i >> 6, lx = i & 63;
         const int yy = y0 + ly, xx = x0 + lx;
-        if (yy >= H || xx >= W) continue;
+        const bool inside = yy < H && xx < W;
         const int b = (ly >> 3) * 8 + (lx >> 3);
         const uint16_t *c = T + (ly + kFH) * kCdefTW + lx + kFH;
-        if (s_skip[b]) {
-          if (apply) ((PIX *)job.fin[p])[(size_t)yy * stride + xx] = (PIX)*c;
-          continue;
-        }
+        const bool act = inside && !s_skip[b];
+        int pv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, psrc = 0;       // psy: filtered value per index and the source sample (0: not counted)
+        if (inside && !act && apply) ((PIX *)job.fin[p])[(size_t)yy * stride + xx] = (PIX)*c;
+        if (act) {
         CdefTaps taps;
         cdef_load_taps(c, &s_off[0][0], s_dir[b], taps);
         int vscale = -1;                            // luma: primary strength scaled by the block variance (spec 7.15.2)
@@ -786,8 +792,37 @@ __global__ void __launch_bounds__(256) b200_dbcdef_kernel(const B200RdoJob *jobs
             }
           }
           if (apply) ((PIX *)job.fin[p])[(size_t)yy * stride + xx] = (PIX)v;
+          else if (psy) pv[k] = v;
           else { const int d = v - src; sse[k] += (unsigned)(d * d); }
         }
+        psrc = src;
+        }
+        if (psy) {        // uniform over the CTA: every lane takes part in the shuffles, inactive lanes add zeros
+          uint32_t a = (uint32_t)psrc, a2 = a * a;
+#pragma unroll
+          for (int m = 1; m < 8; m <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, m); a2 += __shfl_xor_sync(0xffffffffu, a2, m); }
+          if ((lx & 7) == 0 && act) { atomicAdd(&s_blk_s[b][0], a); atomicAdd(&s_blk_s[b][1], a2); }
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            if (k >= nidx) continue;
+            uint32_t d = (uint32_t)pv[k], d2 = d * d, sd = d * (uint32_t)psrc;
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) {
+              d += __shfl_xor_sync(0xffffffffu, d, m); d2 += __shfl_xor_sync(0xffffffffu, d2, m); sd += __shfl_xor_sync(0xffffffffu, sd, m);
+            }
+            if ((lx & 7) == 0 && act) { atomicAdd(&s_blk_d[b][k][0], d); atomicAdd(&s_blk_d[b][k][1], d2); atomicAdd(&s_blk_d[b][k][2], sd); }
+          }
+        }
+      }
+    }
+    if (!apply && f->psy) {
+      // one (block, index) per thread: the block's Psychovisual error from its five sums
+      __syncthreads();
+      for (int i = tid; i < 64 * nidx; i += 256) {
+        const int b = i >> f->cdef_bits, k = i & (nidx - 1);
+        if (s_skip[b]) continue;
+        const unsigned long long dist = b200_psy_dist8x8(s_blk_s[b][0], s_blk_d[b][k][0], s_blk_s[b][1], s_blk_d[b][k][1], s_blk_d[b][k][2], bd);
+        atomicAdd(&s_sse[k], dist);
       }
     }
     if (!apply) {

@@ -478,9 +478,12 @@ __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid
 // W warps per CTA.  W == 1: free-running single-warp CTAs (grid-stride over the blocks).  W > 1 (the never-pruned top
 // level): the W warps of a CTA analyse W different blocks in lock-step (analyze_block<.., SYNC>).
 #ifndef B200_LV2_WARPS
-#define B200_LV2_WARPS 16     // resident warps per SM the 16x16 analysis kernels are compiled for (register budget 65536 / 32 / warps)
+#define B200_LV2_WARPS 20     // resident warps per SM the 16x16 analysis kernels are compiled for (register budget 65536 / 32 / warps)
 #endif
-constexpr int kAnalyzeWarpsTop = 4;      // 16x16 as the top level
+#ifndef B200_TOP_W
+#define B200_TOP_W 5
+#endif
+constexpr int kAnalyzeWarpsTop = B200_TOP_W;      // 16x16 as the top level
 constexpr int kAnalyzeWarpsTop32 = 2;    // 32x32 as the top level (22.9 KB of shared memory per warp)
 template <int LV, bool HBD, int W>
 __global__ void __launch_bounds__(kThreads * W, W == 6 ? 3 : (LV == 3 ? 4 : (LV == 2 ? B200_LV2_WARPS : 24) / W)) b200_analyze_kernel(const B200RdoJob *jobs) {

@@ -269,7 +269,8 @@ void orc_cdef_frame(const B200Frame *f, uint16_t *const in[3], uint16_t *const o
 /* ---------------------------------------------------------------------------------------------
  * CDEF strength search (encoder side, rav1e: rdo_loop_decision [EXT]): for every 64x64 superblock that
  * has at least one non-skip 8x8 block, pick the strength index (0 .. 2^cdef_bits - 1) minimising the
- * squared error of the CDEF output against the source over all planes (ties -> lowest index).
+ * error of the CDEF output against the source over all planes (squared error; luma per 8x8 with the Psychovisual metric when
+ * frame.psy is set) (ties -> lowest index).
  * Writes cdef_idx[] (-1 where the superblock is entirely skipped) and the filtered planes. */
 /* dirvar: optional cache of (direction, variance) per 8x8 block of this superblock (64 entries x 2, dir = -1: not yet
  * computed) - the strength search calls this once per candidate index and the directions do not depend on it */
@@ -303,6 +304,10 @@ static uint64_t cdef_sb_sse(const B200Frame *f, uint16_t *const in[3], uint16_t 
         }
         const uint16_t *I = in[p];
         const int8_t *pt = k_pri_taps[(pri >> cshift) & 1];
+        /* Tune::Psychovisual: the luma error of an 8x8 block is the variance-aware error of the trials (rav1e scores the
+         * luma plane of the loop-filter decisions with cdef_dist_kernel, rdo_loop_plane_error [EXT]); chroma: squared error */
+        const int psy = f->psy && p == 0;
+        uint32_t ps = 0, pd = 0, ps2 = 0, pd2 = 0, psd = 0;
         for (int i = 0; i < 8; i++)
           for (int j = 0; j < 8; j++) {
             const int y0 = r * 4 + i, x0 = c * 4 + j;
@@ -332,10 +337,12 @@ static uint64_t cdef_sb_sse(const B200Frame *f, uint16_t *const in[3], uint16_t 
                 }
               y = clip3(mn, mx, x + ((8 + sum - (sum < 0)) >> 4));
             }
-            const int d = y - (int)src[p][y0 * stride + x0];
-            sse += (uint64_t)(d * d);
+            const int sv = src[p][y0 * stride + x0];
+            if (psy) { ps += (uint32_t)sv; pd += (uint32_t)y; ps2 += (uint32_t)(sv * sv); pd2 += (uint32_t)(y * y); psd += (uint32_t)(sv * y); }
+            else { const int d = y - sv; sse += (uint64_t)(d * d); }
             if (write) out[p][y0 * stride + x0] = (uint16_t)y;
           }
+        if (psy) sse += b200_psy_dist8x8(ps, pd, ps2, pd2, psd, bd);
       }
     }
   return sse;
