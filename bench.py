@@ -444,7 +444,7 @@ def main():
             "config": {"workload": wl["name"], "images_per_gpu": wl["n"], "quality": wl["quality"], "speed": wl["speed"],
                        "depth": wl["depth"], "threads": THREADS, "parallelism": "images sharded one batch per GPU, no data-path collective",
                        "l2": "inputs (%.0f MB/step) larger than L2, no flush needed" % (px_per_step * nch / 1e6),
-                       "tools": "partitions 4..16 (square, top-down early termination), 13 intra modes + angle deltas + CFL, 5 transform types, deblock + CDEF (per-SB strength search) + loop restoration (sgrproj, per-unit search)",
+                       "tools": "what ravif selects for this preset: square partitions (range of the preset, top-down early termination), 13 intra modes + angle deltas + CFL + intra edge filter, transform-type RDO (5-type reduced / 7-type set), Tune::Psychovisual distortion (luma >= 8x8 in the trials and the CDEF search), deblocking level search, CDEF per-SB strength search, loop restoration (sgrproj, 4 or 16 sets, per-unit search)",
                        "avif_bytes_per_step": out_bytes // max(args.steps, 1)},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "Mpixels/s", "h2d_bytes_per_step": d2["h2d_bytes"] // args.steps,
