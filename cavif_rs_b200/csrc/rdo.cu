@@ -684,17 +684,24 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
 #define B200_ANALYZE(LV, W, GRID) \
     do { if (high_bitdepth) b200_analyze_kernel<LV, true, W><<<GRID, kThreads * W, 0, st>>>(d_jobs); \
          else b200_analyze_kernel<LV, false, W><<<GRID, kThreads * W, 0, st>>>(d_jobs); } while (0)
+    // never-pruned top level, lock-step CTAs of W warps that each walk ceil(blocks / (CTAs * W)) blocks: B200_TOP_WAVES waves
+    // of resident CTAs over the launch, so that the last grid-stride iteration is (nearly) full - with many short waves
+    // the partly filled last iteration of every CTA was up to 8 % of the kernel
+#ifndef B200_TOP_WAVES
+#define B200_TOP_WAVES 2
+#endif
+    auto top_grid = [&](int warps_per_cta, int ctas_per_sm) {
+      const int per_job_ctas = std::max(1, (148 * ctas_per_sm * B200_TOP_WAVES) / n_jobs);
+      return dim3((unsigned)std::min(per_job_ctas, (nblk + warps_per_cta - 1) / warps_per_cta), (unsigned)n_jobs);
+    };
     if (lv == 3) {
-      dim3 gt((per_job + kAnalyzeWarpsTop32 - 1) / kAnalyzeWarpsTop32, n_jobs);
-      B200_ANALYZE(3, kAnalyzeWarpsTop32, gt);
-    } else if (lv == 2 && top == 2) {      // never pruned: lock-step CTAs
+      B200_ANALYZE(3, kAnalyzeWarpsTop32, top_grid(kAnalyzeWarpsTop32, 4));
+    } else if (lv == 2 && top == 2) {
       static const int top_warps = getenv("B200AVIF_TOP_WARPS") ? atoi(getenv("B200AVIF_TOP_WARPS")) : kAnalyzeWarpsTop;      // experiment knob
       if (top_warps == 6 && !high_bitdepth) {
-        dim3 gt((per_job + 5) / 6, n_jobs);
-        b200_analyze_kernel<2, false, 6><<<gt, kThreads * 6, 0, st>>>(d_jobs);
+        b200_analyze_kernel<2, false, 6><<<top_grid(6, 3), kThreads * 6, 0, st>>>(d_jobs);
       } else {
-        dim3 gt((per_job + kAnalyzeWarpsTop - 1) / kAnalyzeWarpsTop, n_jobs);
-        B200_ANALYZE(2, kAnalyzeWarpsTop, gt);
+        B200_ANALYZE(2, kAnalyzeWarpsTop, top_grid(kAnalyzeWarpsTop, B200_LV2_WARPS / kAnalyzeWarpsTop));
       }
     } else {
       static const bool free_running = getenv("B200AVIF_FREE_RUNNING") != nullptr;      // A/B knob: the single-warp kernels of round 1
