@@ -122,6 +122,16 @@ template <int N> __device__ __forceinline__ int scan_row_at(const ScanRow<N> &r,
 template <int N> __device__ __forceinline__ int scan_index(int txc, int pos, int l, int c) {
   return txc == 0 ? iscan_at<N>(pos) : (txc == 2 ? pos : c * N + l);
 }
+// scan indices of the FOUR coefficients (row l, columns c .. c + 3; c a multiple of 4) in one load: bytes (N <= 16) or
+// halfwords (N == 32) of the returned pair; scan_quad_at() extracts entry c & 3
+template <int N> __device__ __forceinline__ uint2 scan_quad_load(int l, int c) {
+  if (N == 32) return __ldg(reinterpret_cast<const uint2 *>(dv_iscan32_g + l * 32 + c));
+  return make_uint2(__ldg(reinterpret_cast<const uint32_t *>(dv_iscan_g + scan_base(N) + l * N + c)), 0u);
+}
+template <int N> __device__ __forceinline__ int scan_quad_at(const uint2 &q, int c) {
+  if (N == 32) return (int)((((c & 2) ? q.y : q.x) >> (16 * (c & 1))) & 0xffffu);
+  return (int)((q.x >> (8 * (c & 3))) & 0xffu);
+}
 __device__ __forceinline__ int ilog2_dev(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
 __device__ __noinline__ long long warp_sum_ll(long long v) {
@@ -401,26 +411,43 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
   int eob = 0;
   const int txc = plane == 0 ? b200_tx_class(tx_type) : 0;      // transform class: scan order and coefficient contexts
   {
+    // AC coefficients in the loop (one scan-table load per four of them); the DC coefficient (lane 0 of the group) after it
     const uint32_t dc_q = (uint32_t)f->dc_q, ac_q = (uint32_t)f->ac_q;
-    const uint32_t dc_rcp = 0xffffffffu / dc_q, ac_rcp = 0xffffffffu / ac_q;
+    const uint32_t ac_rcp = 0xffffffffu / ac_q, ac_off = (ac_q * 98) >> 8;
+    uint2 sq = make_uint2(0u, 0u);
     B200_UNROLL(B200_UQ)
     for (int c = 0; c < N; c++) {
       const int pos = l * N + c;
-      const uint32_t q = pos == 0 ? dc_q : ac_q, rcp = pos == 0 ? dc_rcp : ac_rcp;
-      const uint32_t off = pos == 0 ? (q * 109) >> 8 : (q * 98) >> 8;
+      if ((c & 3) == 0 && txc == 0) sq = scan_quad_load<N>(l, c);
+      if (pos == 0) continue;
       const int32_t cf = buf[l * S + c];
-      const uint32_t a = ((uint32_t)(cf < 0 ? -cf : cf) << qshift) + off;
-      uint32_t lv = __umulhi(a, rcp);           // floor(a / q) or one/two less
-      uint32_t rem = a - lv * q;
-      if (rem >= q) { lv++; rem -= q; }
-      if (rem >= q) lv++;
+      const uint32_t a = ((uint32_t)(cf < 0 ? -cf : cf) << qshift) + ac_off;
+      uint32_t lv = __umulhi(a, ac_rcp);        // floor(a / q) or one/two less
+      uint32_t rem = a - lv * ac_q;
+      if (rem >= ac_q) { lv++; rem -= ac_q; }
+      if (rem >= ac_q) lv++;
       if (lv > 32767) lv = 32767;
-      const int32_t dqa = (int32_t)((lv * q) & 0xFFFFFF) >> qshift;
-      const int si = scan_index<N>(txc, pos, l, c);
+      const int32_t dqa = (int32_t)((lv * ac_q) & 0xFFFFFF) >> qshift;
+      const int si = txc == 0 ? scan_quad_at<N>(sq, c) : (txc == 2 ? pos : c * N + l);
       qc[si] = (int16_t)(cf < 0 ? -(int)lv : (int)lv);
       buf[l * S + c] = cf < 0 ? -dqa : dqa;
       lev[l * LS + c] = (uint8_t)(lv > 127 ? 127 : lv);
       if (lv) eob = max(eob, si + 1);
+    }
+    if (l == 0) {       // DC: scan index 0 in every class
+      const uint32_t dc_rcp = 0xffffffffu / dc_q, dc_off = (dc_q * 109) >> 8;
+      const int32_t cf = buf[0];
+      const uint32_t a = ((uint32_t)(cf < 0 ? -cf : cf) << qshift) + dc_off;
+      uint32_t lv = __umulhi(a, dc_rcp);
+      uint32_t rem = a - lv * dc_q;
+      if (rem >= dc_q) { lv++; rem -= dc_q; }
+      if (rem >= dc_q) lv++;
+      if (lv > 32767) lv = 32767;
+      const int32_t dqa = (int32_t)((lv * dc_q) & 0xFFFFFF) >> qshift;
+      qc[0] = (int16_t)(cf < 0 ? -(int)lv : (int)lv);
+      buf[0] = cf < 0 ? -dqa : dqa;
+      lev[0] = (uint8_t)(lv > 127 ? 127 : lv);
+      if (lv) eob = max(eob, 1);
     }
   }
   eob = group_max<N>(eob);
@@ -447,10 +474,12 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
         rate += 256u * (uint32_t)(nb - 1);
       }
     }
+    uint2 sq = make_uint2(0u, 0u);
     B200_UNROLL(B200_UR)
     for (int c = 0; c < N; c++) {
       const int pos = l * N + c;
-      const int si = scan_index<N>(txc, pos, l, c);
+      if ((c & 3) == 0 && txc == 0) sq = scan_quad_load<N>(l, c);
+      const int si = txc == 0 ? scan_quad_at<N>(sq, c) : (txc == 2 ? pos : c * N + l);
       if (si >= eob) continue;
       const int level = abs((int)qc[si]);
       const uint8_t *L = lev + l * LS + c;
@@ -529,7 +558,10 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
     // Tune::Psychovisual (oracle trial_plane): luma is scored per 8x8 with the variance-aware error of records.h.  Lane l owns
     // column l of the reconstruction it just wrote; the five sums of an 8x8 are reduced over its 8 lanes.  Every lane takes the
     // same path (the shuffles are warp wide); groups that code a chroma plane keep their squared error.
+    // Row group rg's five sums end up on every lane of an 8-lane segment; the lane with (l & 7) == rg keeps them, so that
+    // after the loop the N/8 lanes (l & 7) < N/8 of a segment score the N/8 blocks of their column of 8x8 blocks at once.
     unsigned long long dist = 0;
+    uint32_t kss = 0, ksd = 0, ks2 = 0, kd2 = 0, ksp = 0;
 #pragma unroll 1
     for (int rg = 0; rg < N / 8; rg++) {
       uint32_t ss = 0, sd = 0, s2 = 0, d2 = 0, sp = 0;
@@ -543,8 +575,9 @@ __device__ __noinline__ TrialOut trial_batch(const TileCtx &t, SH &sh, int plane
         ss += __shfl_xor_sync(FULL, ss, m); sd += __shfl_xor_sync(FULL, sd, m); s2 += __shfl_xor_sync(FULL, s2, m);
         d2 += __shfl_xor_sync(FULL, d2, m); sp += __shfl_xor_sync(FULL, sp, m);
       }
-      if ((l & 7) == 0) dist += b200_psy_dist8x8(ss, sd, s2, d2, sp, bd);
+      if ((l & 7) == rg) { kss = ss; ksd = sd; ks2 = s2; kd2 = d2; ksp = sp; }
     }
+    if ((l & 7) < N / 8) dist = b200_psy_dist8x8(kss, ksd, ks2, kd2, ksp, bd);
 #pragma unroll
     for (int m = N / 2; m > 0; m >>= 1) dist += __shfl_xor_sync(FULL, dist, m);
     if (plane == 0) sse = dist > 0xffffffffull ? 0xffffffffu : (uint32_t)dist;

@@ -80,18 +80,20 @@ __device__ void deblock_sample(PIX *px, int step, int filter_len, int lvl, int s
   if (filter_len == 16 && flat2) { n = 6; lg = 4; }
   else if (filter_len == 6) { n = 2; lg = 3; }
   else { n = 3; lg = 3; }
-  int s[14], o[12];
+  // Output i (-n <= i < n) = (sum_{j=-n..n} tap_j * s[clip(i + j)] + round) >> lg with taps 1 except 2 at j = 0 (n == 3) or at
+  // |j| < 2 (n == 2, 6); s = the 2n + 2 samples around the edge, indices clipped to [-(n + 1), n] (AV1 spec 7.14.6.3/4).  The
+  // all-ones part is a window sum that slides by one sample per output; the doubled taps never need clipping.
+  int s[14];
   for (int i = 0; i <= n; i++) { s[n - i] = p[i]; s[n + 1 + i] = q[i]; }
+  const int *sc = s + n + 1;          // sc[k], k = -(n + 1) .. n
+  int win = 0;
+  for (int j = -n; j <= n; j++) win += sc[clip3_d(-(n + 1), n, -n + j)];
+  const int rnd = 1 << (lg - 1);
   for (int i = -n; i < n; i++) {
-    int t = 0;
-    for (int j = -n; j <= n; j++) {
-      const int k = clip3_d(-(n + 1), n, i + j);
-      const int tap = (n == 3) ? (j == 0 ? 2 : 1) : (iabs_d(j) < 2 ? 2 : 1);
-      t += tap * s[k + n + 1];
-    }
-    o[i + n] = (t + (1 << (lg - 1))) >> lg;
+    const int t = win + (n == 3 ? sc[i] : sc[i - 1] + sc[i] + sc[i + 1]);
+    px[i * step] = (PIX)((t + rnd) >> lg);
+    win += sc[min(i + 1 + n, n)] - sc[max(i - n, -(n + 1))];
   }
-  for (int i = -n; i < n; i++) px[i * step] = (PIX)o[i + n];
 }
 
 }  // namespace
@@ -291,7 +293,7 @@ struct LrShared {
   uint32_t R3a[kLrAH * kLrAW], R5a[((kLrAH + 1) / 2) * kLrAW];
   uint16_t R3b[kLrAH * kLrAW], R5b[((kLrAH + 1) / 2) * kLrAW];
   uint16_t xbx[256];      // x_by_xplus1 (spec 7.17.3): indexed by the per-lane variance, so a shared-memory copy (a __constant__ read serialises over distinct addresses)
-  unsigned long long acc[B200_LR_CANDIDATES_FULL][6];     // per candidate set: H00, H01, H11, C0, C1 (two's complement), S
+  unsigned long long acc[8][B200_LR_CANDIDATES_FULL][6];  // per warp and candidate set: H00, H01, H11, C0, C1 (two's complement), S - one writer per slot, summed at the end
   B200LrUnit best;
 };
 
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
   const int tid = threadIdx.x;
   // the loops below walk (rows x columns) index spaces of at most 22 x 102 entries: row / column by reciprocal multiplication
   const LrDiv dv_w = lr_div_make(w), dv_w2 = lr_div_make(w + 2), dv_w6 = lr_div_make(w + 6);
-  for (int i = tid; i < B200_LR_CANDIDATES_FULL * 6; i += 256) sh.acc[i / 6][i % 6] = 0;
+  for (int i = tid; i < 8 * B200_LR_CANDIDATES_FULL * 6; i += 256) (&sh.acc[0][0][0])[i] = 0;
   sh.xbx[tid] = dv_x_by_xplus1[tid];
   __syncthreads();
   const int8_t cand[B200_LR_CANDIDATES] = {B200_LR_SETS};
@@ -521,7 +523,7 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
             // exact 64-bit warp sum from two 32-bit hardware reductions: v = (v >> 16) * 65536 + (v & 0xffff)
             const int lo = __reduce_add_sync(0xffffffffu, v[k] & 0xffff), hi = __reduce_add_sync(0xffffffffu, v[k] >> 16);
             const long long tot = (long long)hi * 65536 + lo;
-            if ((tid & 31) == 0 && tot) atomicAdd(&sh.acc[ci][k], (unsigned long long)tot);
+            if ((tid & 31) == 0) sh.acc[tid >> 5][ci][k] += (unsigned long long)tot;
           }
         }
       }
@@ -530,16 +532,22 @@ __global__ void __launch_bounds__(256) b200_lr_kernel(const B200RdoJob *jobs) {
     }
     if (phase == 0) {
       __syncthreads();
+      if (tid < B200_LR_CANDIDATES_FULL * 6) {      // fold the eight per-warp slots into slot 0
+        unsigned long long t = 0;
+        for (int wv = 0; wv < 8; wv++) t += (&sh.acc[wv][0][0])[tid];
+        (&sh.acc[0][0][0])[tid] = t;
+      }
+      __syncthreads();
       if (tid == 0) {
         B200LrUnit best = {0, 0, 0, 0};
-        const long long S = (long long)sh.acc[0][5];
+        const long long S = (long long)sh.acc[0][0][5];
         long long bestJ = ((S >> 8) << 8) + (((long long)f->lambda_q8 * B200_LR_FLAG_COST0) >> 8);
         const long long npx = (long long)w * (y1 - y0);
         for (int ci = 0; ci < n_sets; ci++) {
           const int set = LR_SET_OF(ci);
           const int r0 = dv_sgr_params[set][0], r1 = dv_sgr_params[set][1];
-          const long long H00 = (long long)sh.acc[ci][0], H01 = (long long)sh.acc[ci][1], H11 = (long long)sh.acc[ci][2];
-          const long long C0 = (long long)sh.acc[ci][3], C1 = (long long)sh.acc[ci][4];
+          const long long H00 = (long long)sh.acc[0][ci][0], H01 = (long long)sh.acc[0][ci][1], H11 = (long long)sh.acc[0][ci][2];
+          const long long C0 = (long long)sh.acc[0][ci][3], C1 = (long long)sh.acc[0][ci][4];
           const long long h00 = H00 / npx, h01 = H01 / npx, h11 = H11 / npx, c0 = C0 / npx, c1 = C1 / npx;
           long long xq0 = 0, xq1 = 0;
           if (!r0) { if (h11 <= 0) continue; xq1 = lr_round_div(c1 * 128, h11); }
@@ -618,7 +626,16 @@ __global__ void __launch_bounds__(256, 4) b200_dbcdef_kernel(const B200RdoJob *j
 #endif
   __shared__ uint8_t s_txs[20 * 20];              // tx_size of the 4x4 units (sbr*16 - 2 .. +17) x (sbc*16 - 2 .. +17)
   __shared__ int16_t s_off[8][2];                 // CDEF tap offsets in the staged region per direction
+  __shared__ int16_t s_str[3][8][2];              // per plane and strength index: primary << cshift, secondary (3 -> 4) << cshift
+  __shared__ int8_t s_vs[64];                     // per 8x8 block: luma primary-strength scale 0 | 4 .. 16 from its variance (spec 7.15.2)
   if (tid < 16) s_off[tid >> 1][tid & 1] = (int16_t)(dv_cdef_dir[tid >> 1][tid & 1][0] * kCdefTW + dv_cdef_dir[tid >> 1][tid & 1][1]);
+  if (tid < 24) {
+    const int str = tid < 8 ? f->cdef_y_strength[tid & 7] : f->cdef_uv_strength[tid & 7];
+    int sec = str & 3;
+    if (sec == 3) sec = 4;
+    s_str[tid >> 3][tid & 7][0] = (int16_t)((str >> 2) << cshift);
+    s_str[tid >> 3][tid & 7][1] = (int16_t)(sec << cshift);
+  }
   if (tid == 0) s_any = 0;
   if (tid < 8) s_sse[tid] = 0;
   for (int i = tid; i < 64 * 2; i += 256) (&s_blk_s[0][0])[i] = 0;
@@ -729,7 +746,11 @@ __global__ void __launch_bounds__(256, 4) b200_dbcdef_kernel(const B200RdoJob *j
     if (r < f->mi_rows && c < f->mi_cols) {
       const B200Mi *m = &job.mi[r * f->mi_cols + c];
       skip = (m[0].flags & 1) && (m[1].flags & 1) && (m[f->mi_cols].flags & 1) && (m[f->mi_cols + 1].flags & 1);
-      if (!skip) cdef_direction(&s_px[0][((tid >> 3) * 8 + kFH) * kCdefTW + (tid & 7) * 8 + kFH], kCdefTW, bd, &s_dir[tid], &s_var[tid]);
+      if (!skip) {
+        cdef_direction(&s_px[0][((tid >> 3) * 8 + kFH) * kCdefTW + (tid & 7) * 8 + kFH], kCdefTW, bd, &s_dir[tid], &s_var[tid]);
+        const int var = s_var[tid];
+        s_vs[tid] = (int8_t)(var ? 4 + ((var >> 6) ? min(floor_log2_d((unsigned)(var >> 6)), 12) : 0) : 0);
+      }
     }
     s_skip[tid] = skip;
   }
@@ -758,7 +779,6 @@ __global__ void __launch_bounds__(256, 4) b200_dbcdef_kernel(const B200RdoJob *j
     unsigned int sse[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int p = 0; p < f->planes; p++) {
       const int damping = f->cdef_damping + cshift - (p > 0);
-      const int32_t *strengths = p == 0 ? f->cdef_y_strength : f->cdef_uv_strength;
       const uint16_t *T = s_px[p];
       const PIX *S = (const PIX *)job.src[p];
       // Tune::Psychovisual: luma is scored per 8x8 block with the variance-aware error of the trials (oracle cdef_sb_sse): the
@@ -776,21 +796,13 @@ __global__ void __launch_bounds__(256, 4) b200_dbcdef_kernel(const B200RdoJob *j
         if (act) {
         CdefTaps taps;
         cdef_load_taps(c, &s_off[0][0], s_dir[b], taps);
-        int vscale = -1;                            // luma: primary strength scaled by the block variance (spec 7.15.2)
-        if (p == 0) {
-          const int var = s_var[b];
-          vscale = var ? 4 + ((var >> 6) ? min(floor_log2_d((unsigned)(var >> 6)), 12) : 0) : 0;
-        }
+        const int vscale = p == 0 ? (int)s_vs[b] : -1;      // luma: primary strength scaled by the block variance (spec 7.15.2)
         const int src = apply ? 0 : (int)S[(size_t)yy * stride + xx];
         int sec_cached = 0, sec_sum = 0;       // secondary tap sum of the last secondary strength seen (uniform over the CTA)
 #pragma unroll
         for (int k = 0; k < 8; k++) {
           if (k >= nidx || (apply && k != best)) continue;
-          const int str = strengths[k];
-          const int pri0 = (str >> 2) << cshift;
-          int sec = str & 3;
-          if (sec == 3) sec = 4;
-          sec <<= cshift;
+          const int pri0 = s_str[p][k][0], sec = s_str[p][k][1];
           int v;
           if (pri0 == 0 && sec != 0) v = cdef_pixel_tile(T, lx, ly, 0, sec, 0, damping, cshift);      // direction 0 when the primary strength is zero
           else {

@@ -135,8 +135,10 @@ __device__ __noinline__ int recon_tx(const B200Frame *f, bool active, const PIX 
     const uint32_t ac_rcp = 0xffffffffu / ac_q, ac_off = (ac_q * 98) >> 8;
     const int txc = b200_tx_class(tx_type);      // chroma never uses the 1-D types (tx type derived from the uv mode)
     const int clamp_b = bd + 8;
+    uint2 sq = make_uint2(0u, 0u);       // scan indices of four coefficients per table load
 #pragma unroll 1
     for (int c = 0; c < N; c++) {
+      if ((c & 3) == 0 && txc == 0) sq = scan_quad_load<N>(l, c);
       uint32_t q = ac_q, rcp = ac_rcp, off = ac_off;
       if (c == 0 && l == 0) { q = dc_q; rcp = 0xffffffffu / dc_q; off = (dc_q * 109) >> 8; }
       const int32_t cf = v[c];
@@ -147,7 +149,7 @@ __device__ __noinline__ int recon_tx(const B200Frame *f, bool active, const PIX 
       if (rem >= q) lv++;
       if (lv > 32767) lv = 32767;
       const int32_t dqa = (int32_t)((lv * q) & 0xFFFFFF) >> qshift;
-      const int si = scan_index<N>(txc, l * N + c, l, c);
+      const int si = txc == 0 ? scan_quad_at<N>(sq, c) : (txc == 2 ? l * N + c : c * N + l);
       qc[si] = (int16_t)(cf < 0 ? -(int)lv : (int)lv);
       v[c] = clamp_bits(cf < 0 ? -dqa : dqa, clamp_b);
       if (lv) eob = max(eob, si + 1);

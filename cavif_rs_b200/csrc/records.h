@@ -105,18 +105,37 @@ typedef struct B200Frame {
 // rav1e's cdef_dist_kernel [EXT: crates.io rav1e 0.8.1, rdo.rs] scales the squared error by an SSIM-like factor
 //   (4033 / 16384) * (svar + dvar + 16384) / sqrt(16265089 + svar * dvar)        (variances at 8-bit scale, x64);
 // this is an integer restatement of that published form (Q12 factor, floor square root, factor capped at 4), not rav1e's code.
+// floor(sqrt(v)): a floating-point estimate corrected to the exact integer (single precision on the device: the estimate is
+// within a few units for v < 2^48 and the loops finish the job; the host uses the double-precision root - same result)
 static inline B200_HD uint64_t b200_isqrt64(uint64_t v) {
+#ifdef __CUDA_ARCH__
+  uint64_t r = (uint64_t)__fsqrt_rn((float)v);
+#else
   uint64_t r = (uint64_t)sqrt((double)v);
+#endif
   while (r * r > v) r--;
   while ((r + 1) * (r + 1) <= v) r++;
   return r;
+}
+// floor(num / den) for den != 0, quotients that matter below 2^22 (larger ones only need to stay large: the caller caps them)
+static inline B200_HD uint64_t b200_div_small_quot(uint64_t num, uint64_t den) {
+#ifdef __CUDA_ARCH__
+  const float qf = __fdividef((float)num, (float)den);
+  if (qf > 4.0e6f) return 4000000ull;
+  uint64_t q = (uint64_t)qf;
+  while (q * den > num) q--;
+  while ((q + 1) * den <= num) q++;
+  return q;
+#else
+  return num / den;
+#endif
 }
 static inline B200_HD uint32_t b200_psy_dist8x8(uint32_t sum_s, uint32_t sum_d, uint32_t sum_s2, uint32_t sum_d2, uint32_t sum_sd, int bit_depth) {
   const uint64_t sse = (uint64_t)sum_s2 + sum_d2 - 2 * (uint64_t)sum_sd;
   const int cs2 = 2 * (bit_depth - 8);
   const uint64_t svar = ((uint64_t)sum_s2 - (((uint64_t)sum_s * sum_s + 32) >> 6)) >> cs2;
   const uint64_t dvar = ((uint64_t)sum_d2 - (((uint64_t)sum_d * sum_d + 32) >> 6)) >> cs2;
-  uint64_t boost = (4033ull * (svar + dvar + 16384)) / (4 * b200_isqrt64(16265089ull + svar * dvar));      /* Q12 */
+  uint64_t boost = b200_div_small_quot(4033ull * (svar + dvar + 16384), 4 * b200_isqrt64(16265089ull + svar * dvar));      /* Q12 */
   if (boost > 4 * 4096) boost = 4 * 4096;
   const uint64_t d = (sse * boost + 2048) >> 12;
   return d > 0x3fffffffu ? 0x3fffffffu : (uint32_t)d;
