@@ -452,9 +452,9 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
       const size_t need = b200_recon_smem_bytes(jobs[0]->f.bit_depth > 8, top_level, recon_rows) + 1024;
       const size_t per_sm = need ? (size_t)smem_sm / need : 0;
       if (recon_rows <= max_tile_rows && per_sm * (size_t)sms >= tiles.size()) break;
-      recon_rows >>= 1;
+      recon_rows--;
     }
-    if (const char *ev = getenv("B200AVIF_RECON_ROWS")) { const int v = atoi(ev); if (v == 1 || v == 2 || v == 4) recon_rows = v; }
+    if (const char *ev = getenv("B200AVIF_RECON_ROWS")) { const int v = atoi(ev); if (v >= 1 && v <= 4) recon_rows = v; }
   }
   int n_launched = 0;
   const int le = b200_rdo_launch(d_jobs, (int)jobs.size(), d_tiles, (int)tiles.size(), max_blocks4, max_regions, jobs[0]->f.bit_depth > 8,

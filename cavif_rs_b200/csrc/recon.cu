@@ -475,7 +475,7 @@ struct ReconShared {
 // wave) while leaving room for the throughput kernels of the next chunk on the same SMs: <= 128 registers per thread
 // (16x16 transforms hold 3 x 16 values per lane); the 32x32 instances need the full budget.
 template <bool HBD, int NMAX, int ROWS>
-__global__ void __launch_bounds__(64 * ROWS, NMAX == 32 ? 1 : (ROWS == 1 ? 8 : (ROWS == 2 ? 4 : 2))) b200_recon_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
+__global__ void __launch_bounds__(64 * ROWS, NMAX == 32 ? 1 : (ROWS == 1 ? 8 : (ROWS == 2 ? 4 : 2)))  /* 128 registers per thread */ b200_recon_kernel(const B200RdoJob *jobs, const B200TileRef *tiles) {
   typedef typename PixOf<HBD>::type PIX;
   typedef ReconShared<HBD, NMAX, ROWS> SH;
   B200_RECON_SMEM(SH, sh);
@@ -565,19 +565,19 @@ int recon_launch_t(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int n_t
 }
 }  // namespace
 
-// rows: superblock-row slots per tile (1, 2 or 4: more slots = deeper wavefront, more shared memory per tile)
+// rows: superblock-row slots per tile (1 .. 4: more slots = deeper wavefront, more shared memory per tile)
 extern "C" int b200_recon_launch(const B200RdoJob *d_jobs, const B200TileRef *d_tiles, int n_tiles, int high_bitdepth, int top_level, int rows,
                                  void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (n_tiles <= 0) return 0;
 #define B200_RECON_GO(HBD, NMAX) \
-  (rows >= 4 ? recon_launch_t<HBD, NMAX, 4>(d_jobs, d_tiles, n_tiles, st) : rows >= 2 ? recon_launch_t<HBD, NMAX, 2>(d_jobs, d_tiles, n_tiles, st) \
-                                                                                         : recon_launch_t<HBD, NMAX, 1>(d_jobs, d_tiles, n_tiles, st))
+  (rows >= 4 ? recon_launch_t<HBD, NMAX, 4>(d_jobs, d_tiles, n_tiles, st) : rows == 3 ? recon_launch_t<HBD, NMAX, 3>(d_jobs, d_tiles, n_tiles, st) \
+   : rows == 2 ? recon_launch_t<HBD, NMAX, 2>(d_jobs, d_tiles, n_tiles, st) : recon_launch_t<HBD, NMAX, 1>(d_jobs, d_tiles, n_tiles, st))
   if (top_level >= 3) return high_bitdepth ? B200_RECON_GO(true, 32) : B200_RECON_GO(false, 32);
   return high_bitdepth ? B200_RECON_GO(true, 16) : B200_RECON_GO(false, 16);
 }
 extern "C" size_t b200_recon_smem_bytes(int high_bitdepth, int top_level, int rows) {
-#define B200_RECON_SZ(HBD, NMAX) (rows >= 4 ? sizeof(ReconShared<HBD, NMAX, 4>) : rows >= 2 ? sizeof(ReconShared<HBD, NMAX, 2>) : sizeof(ReconShared<HBD, NMAX, 1>))
+#define B200_RECON_SZ(HBD, NMAX) (rows >= 4 ? sizeof(ReconShared<HBD, NMAX, 4>) : rows == 3 ? sizeof(ReconShared<HBD, NMAX, 3>) : rows == 2 ? sizeof(ReconShared<HBD, NMAX, 2>) : sizeof(ReconShared<HBD, NMAX, 1>))
   if (top_level >= 3) return high_bitdepth ? B200_RECON_SZ(true, 32) : B200_RECON_SZ(false, 32);
   return high_bitdepth ? B200_RECON_SZ(true, 16) : B200_RECON_SZ(false, 16);
 }
@@ -602,6 +602,7 @@ extern "C" int b200_recon_launch_emu(const B200RdoJob *jobs, const B200TileRef *
   g_rc_jobs = jobs; g_rc_tiles = tiles;
   g_rc_top = jobs[0].frame.partition_max >= 32 ? 3 : 2;
   if (rows >= 4) emu::launch(emu_recon_entry<4>, nullptr, (unsigned)n_tiles, 64 * 4);
+  else if (rows == 3) emu::launch(emu_recon_entry<3>, nullptr, (unsigned)n_tiles, 64 * 3);
   else if (rows >= 2) emu::launch(emu_recon_entry<2>, nullptr, (unsigned)n_tiles, 64 * 2);
   else emu::launch(emu_recon_entry<1>, nullptr, (unsigned)n_tiles, 64);
   return 0;

@@ -51,7 +51,7 @@ def compare_analysis(ref, out, f):
             assert np.array_equal(ref.dec[lv][k], out.dec[lv][k]), "decision %s level %d" % (k, lv)
 
 
-@pytest.mark.parametrize("rows", [1, 2, 4])
+@pytest.mark.parametrize("rows", [1, 2, 3, 4])
 @pytest.mark.parametrize("w,h,depth,planes,tiles,kw", [
     (64, 48, 8, 3, 1, {}),
     (40, 72, 10, 1, 2, dict(partition_min=8, rdo_tx_decision=0)),
