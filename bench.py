@@ -495,7 +495,11 @@ def main():
 
 
 # ncu dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of a kernel (profiles/, 16-image chunks of the 1080p workload)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {}
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {
+    # profiles/r02_final_kernel_times_and_dram.txt (read + write per launch)
+    "1080p": {"analyze_16x16": 111.2e6, "recon_chain": 215.3e6, "deblock_cdef": 378.6e6, "lr_search": 205.7e6, "analyze_8x8": 75.9e6,
+              "satd_16x16": 38.9e6, "lf_search": 56.5e6},
+}
 
 if __name__ == "__main__":
     main()
