@@ -467,7 +467,11 @@ int issue_rdo(Context &c, std::vector<FrameJob *> &jobs, Arena &dev, Arena &pin,
       if (recon_rows <= max_tile_rows && per_sm * (size_t)sms >= tiles.size()) break;
       recon_rows--;
     }
-    if (const char *ev = getenv("B200AVIF_RECON_ROWS")) { const int v = atoi(ev); if (v >= 1 && v <= 4) recon_rows = v; }
+    if (const char *ev = getenv("B200AVIF_RECON_ROWS")) {      // A/B and test knob; never more slots than one SM's shared memory holds
+      const int v = atoi(ev);
+      if (v >= 1 && v <= 4) recon_rows = v;
+      while (recon_rows > 1 && b200_recon_smem_bytes(jobs[0]->f.bit_depth > 8, top_level, recon_rows) + 1024 > (size_t)smem_sm) recon_rows--;
+    }
   }
   int n_launched = 0;
   const int le = b200_rdo_launch(d_jobs, (int)jobs.size(), d_tiles, (int)tiles.size(), max_blocks4, max_regions, jobs[0]->f.bit_depth > 8,

@@ -198,6 +198,24 @@ def test_rdo_kernel_matches_oracle_and_dav1d(w, h, depth, planes, q, tiles, kw):
         assert np.array_equal(dec[p], shown[p][:h, :w])
 
 
+@pytest.mark.parametrize("rows", [1, 2, 3, 4])
+@pytest.mark.parametrize("depth,pmax", [(8, 16), (10, 32)])
+def test_reconstruction_chain_row_slots(rows, depth, pmax, monkeypatch):
+    """every wavefront depth of the reconstruction chain (superblock-row slots per tile, normally picked from the shared-memory
+    budget) gives the oracle's records: one tile of six superblock rows, two tile columns"""
+    monkeypatch.setenv("B200AVIF_RECON_ROWS", str(rows))
+    w, h, planes = 200, 328, 3
+    f = H.frame_setup(w, h, depth, planes, 90, 2)
+    f.partition_max = pmax
+    f.partition_min = 4
+    rt = H.rate_tables(f.base_q_idx)
+    img = H.synth_image(w, h, 77 + depth)
+    src = H.pad_planes([img[..., c].astype(np.uint16) * (4 if depth == 10 else 1) for c in range(planes)], f)
+    ref = H.oracle_encode(f, rt, src)
+    out = device_rdo(f, src)
+    check_records(ref, out, planes)
+
+
 @pytest.mark.parametrize("speed,quantizer", [(6, 121), (4, 121), (8, 66)])
 def test_alpha_frame_of_the_fast_presets(speed, quantizer):
     """the monochrome alpha frame exactly as encode_rgba() configures it (real alpha plane: large flat areas, heavy pruning)"""
