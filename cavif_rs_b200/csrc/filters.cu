@@ -320,15 +320,12 @@ __device__ __forceinline__ void lr_box(const uint16_t *S, int sy, int sx, int r,
 // B8 (8-bit samples): no pre-scaling, and a * n, d * d <= 25 * 25 * 255^2 fit 32 bits
 template <bool B8>
 __device__ __forceinline__ void lr_ab(const uint16_t *xbx, uint32_t a, uint32_t b, int bd, uint32_t s, uint32_t one_by_n, int n, uint16_t *a_out, int32_t *b_out) {
-  unsigned long long p;
-  if (B8) {
-    const int32_t pp = (int32_t)(a * (uint32_t)n) - (int32_t)(b * b);
-    p = pp < 0 ? 0u : (uint32_t)pp;
-  } else {
-    const uint32_t a_s = (uint32_t)lr_round2(a, 2 * (bd - 8)), d = (uint32_t)lr_round2(b, bd - 8);
-    const long long pp = (long long)a_s * n - (long long)d * d;
-    p = pp < 0 ? 0ull : (unsigned long long)pp;
-  }
+  // a <= 25 * 1023^2 < 2^25 and b <= 25 * 1023 at 10 bits: the pre-scaled values are in the 8-bit range, so 32 bits hold
+  // a_s * n and d * d for either depth (bit depths above 10 are not produced by ravif)
+  const int sh2 = B8 ? 0 : bd - 8;
+  const uint32_t a_s = B8 ? a : (a + ((1u << (2 * sh2)) >> 1)) >> (2 * sh2), d = B8 ? b : (b + ((1u << sh2) >> 1)) >> sh2;
+  const int32_t pp = (int32_t)(a_s * (uint32_t)n) - (int32_t)(d * d);
+  const unsigned long long p = pp < 0 ? 0u : (uint32_t)pp;
   const unsigned long long z = (p * s + (1u << 19)) >> 20;
   const uint32_t a2 = xbx[z > 255 ? 255 : (int)z];
   *a_out = (uint16_t)a2;
