@@ -366,6 +366,7 @@ int configure_frame(B200Frame *f, size_t w, size_t h, int depth, bool mono, int 
   f->psy = 1;                                    // Tune::Psychovisual, always (av1encoder.rs:694)
   f->lf_search = tw.fast_deblock ? 0 : 1;       // av1encoder.rs:586: the closed-form level only at the fast presets
   f->lr_full = tw.sgr_complexity_full ? 1 : 0;  // :573
+  f->luma_rdo_modes = tw.complex_prediction_modes ? 4 : 2;      // :572, :628
   f->enable_restoration = tw.lrf ? 1 : 0;     // loop restoration (lrf flag, av1encoder.rs:589): self-guided filter, 64x64 units
   for (int p = 0; p < 3; p++) f->lr_type[p] = (tw.lrf && p < f->planes) ? 1 : 0;
   f->full_range = full_range;

@@ -786,17 +786,20 @@ __device__ __noinline__ uint32_t cfl_rate(const B200RateTables *rt, int au, int 
   return r;
 }
 
-// top-2 of 13 mode costs held by lanes 0..12 (kInf when not allowed): lowest cost first, ties -> lowest index
-__device__ __noinline__ void rank_top2(long long c, int &m0, int &m1) {
+// top-4 of 13 mode costs held by lanes 0..12 (kInf when not allowed): lowest cost first, ties -> lowest index; -1 = none
+__device__ __noinline__ void rank_top4(long long c, int &m0, int &m1, int &m2, int &m3) {
   const int lane = lane_id();
-  long long j = lane < 13 ? c : kInf;
-  int i = lane & 15;
-  warp_argmin(j, i);
-  m0 = j == kInf ? -1 : i;
-  long long j2 = (lane < 13 && lane != m0) ? c : kInf;
-  int i2 = lane & 15;
-  warp_argmin(j2, i2);
-  m1 = j2 == kInf ? -1 : i2;
+  unsigned taken = 0;
+  int m[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    long long j = (lane < 13 && !((taken >> lane) & 1)) ? c : kInf;
+    int i = lane & 15;
+    warp_argmin(j, i);
+    m[r] = j == kInf ? -1 : i;
+    if (m[r] >= 0) taken |= 1u << m[r];
+  }
+  m0 = m[0]; m1 = m[1]; m2 = m[2]; m3 = m[3];
 }
 
 __device__ __forceinline__ void tile_of_unit(const B200Frame *f, int mi_r, int mi_c, TileCtx &t) {

@@ -75,6 +75,7 @@ extern "C" int b200av1_frame_setup(B200Frame *f, int width, int height, int bit_
   f->lambda_satd_q8 = (int32_t)isqrt64((uint64_t)f->lambda_q8 << 8);
   f->reduced_tx_set = 1;
   f->partition_min = 4; f->partition_max = 16;
+  f->luma_rdo_modes = 2;
   f->rdo_tx_decision = 1;
   f->fine_directional_intra = 1;
   f->enable_cfl = 1;

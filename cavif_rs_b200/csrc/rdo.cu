@@ -79,20 +79,25 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, SH &sh, int x, i
   long long my_ycost = kInf;
   if (lane < 13 && ((f->y_mode_mask >> lane) & 1))
     my_ycost = (long long)satd[lane] * 64 + (((long long)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, lane, n, DELTA_Y(lane))) >> 8);
-  int m0, m1;
-  rank_top2(my_ycost, m0, m1);
+  int r0, r1, r2, r3;          // ranked modes; full trials on the first frame.luma_rdo_modes (2 or 4) of them, pair by pair
+  rank_top4(my_ycost, r0, r1, r2, r3);
+  const int n_pairs = f->luma_rdo_modes >= 4 ? 2 : 1;
   // ---- luma full trials: candidate c = k * B200_TX_TYPES + ti; lane batches pair the two modes on the same transform type
   const int tx_mask = b200_tx_mask_for(f->tx_type_mask, f->reduced_tx_set, n);      // 32x32: DCT only; 1-D DCTs: 7-type set only
   int first_t = -1;
   for (int k = 0; k < B200_TX_TYPES; k++) if ((tx_mask >> k) & 1) { first_t = k; break; }
   // open loop: the neighbours' modes are not decided yet, the trials assume filter type 0 (oracle)
   const int ief = f->enable_intra_edge_filter ? 0 : -1;
+  long long bestJ = kInf;
+  int bestC = 1 << 20, bestEob = 0;
+#pragma unroll 1
+  for (int pr = 0; pr < n_pairs; pr++) {
+  const int m0 = pr == 0 ? r0 : r2, m1 = pr == 0 ? r1 : r3;
+  __syncwarp();
   predict_any(sh, ief, m0 >= 0 ? m0 : 0, DELTA_Y(m0 >= 0 ? m0 : 0), lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred);
   predict_any(sh, ief, m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0), DELTA_Y(m1 >= 0 ? m1 : (m0 >= 0 ? m0 : 0)), lg, sh.above[0], sh.left[0], ha, hl, bd, sh.pred + PS);
   __syncwarp();
-  long long bestJ = kInf;
-  int bestC = 1 << 20, bestEob = 0;
-  bool skip_rest = false;      // every first-type trial quantised to all-zero: the other transform types are not tried
+  bool skip_rest = false;      // every first-type trial of the pair quantised to all-zero: its other transform types are not tried
 #pragma unroll 1
   for (int b = 0; b * G < 2 * B200_TX_TYPES && (SYNC || !skip_rest); b++) {
     if (SYNC) { __syncthreads(); if (skip_rest) continue; }
@@ -110,15 +115,17 @@ __device__ __forceinline__ void analyze_block(const TileCtx &t, SH &sh, int x, i
     }
     long long wj = kInf;
     int wc = 1 << 20;
-    if (ok) { wj = rd_cost(f, r.sse, r.rate + mode_rate(rt, ymode_cost, m, n, DELTA_Y(m))); wc = k * B200_TX_TYPES + ti; }
+    if (ok) { wj = rd_cost(f, r.sse, r.rate + mode_rate(rt, ymode_cost, m, n, DELTA_Y(m))); wc = (2 * pr + k) * B200_TX_TYPES + ti; }
     warp_argmin(wj, wc);
     if (wj < bestJ || (wj == bestJ && wc < bestC)) {
       bestJ = wj; bestC = wc;
-      const int wg = (wc % B200_TX_TYPES) * 2 + wc / B200_TX_TYPES - b * G;
+      const int wg = (wc % B200_TX_TYPES) * 2 + (wc / B200_TX_TYPES - 2 * pr) - b * G;
       bestEob = __shfl_sync(FULL, r.eob, wg << lg);
     }
   }
-  const int best_mode = bestC / B200_TX_TYPES == 0 ? m0 : m1;
+  }
+  const int best_rank = bestC / B200_TX_TYPES;
+  const int best_mode = best_rank == 0 ? r0 : (best_rank == 1 ? r1 : (best_rank == 2 ? r2 : r3));
   const int best_tt = dv_tx_types[bestC % B200_TX_TYPES];
   long long total = bestJ;
   int uv_best = DC_PRED, eobU = 0, eobV = 0, cfl_js = 0, cfl_idx = 0;

@@ -93,6 +93,9 @@ typedef struct B200Frame {
   // Tune::Psychovisual (ravif always selects it, av1encoder.rs:694): luma blocks of 8x8 and larger are scored per 8x8 with the
   // variance-aware error b200_psy_dist8x8 instead of the plain squared error
   int32_t psy;
+  // luma modes that get full trials, in SATD ranking order: 2, or 4 with ravif's complex_prediction_modes (speed <= 1,
+  // av1encoder.rs:572,628: rav1e's ComplexAll evaluates more intra candidates per block than Simple)
+  int32_t luma_rdo_modes;
   // decisions of the in-loop filter stages
   int32_t lf_level[4];                      // y vertical, y horizontal, u, v
   int32_t lf_sharpness;

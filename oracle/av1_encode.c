@@ -573,15 +573,20 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
    * delta), DC_PRED, and chroma-from-luma - no chroma SATD ranking */
 #define DELTA_UV(m) ((m) == best_mode ? DELTA_Y(m) : 0)
   /* ranking: SATD + mode rate */
-  int64_t bc[2] = {INT64_MAX, INT64_MAX};
-  int bm[2] = {-1, -1};
+  /* the K = frame.luma_rdo_modes (2 or 4) best modes, lowest cost first, ties -> lowest mode index */
+  const int K = f->luma_rdo_modes >= 4 ? 4 : 2;
+  int64_t bc[4] = {INT64_MAX, INT64_MAX, INT64_MAX, INT64_MAX};
+  int bm[4] = {-1, -1, -1, -1};
   for (int m = 0; m < 13; m++) {
     if (!((f->y_mode_mask >> m) & 1)) continue;
     const int64_t c = (int64_t)satd_y[m] * 64 + (((int64_t)f->lambda_satd_q8 * mode_rate(rt, ymode_cost, m, n, DELTA_Y(m))) >> 8);
-    if (c < bc[0]) { bc[1] = bc[0]; bm[1] = bm[0]; bc[0] = c; bm[0] = m; }
-    else if (c < bc[1]) { bc[1] = c; bm[1] = m; }
+    int at = K;
+    while (at > 0 && c < bc[at - 1]) at--;
+    for (int j = K - 1; j > at; j--) { bc[j] = bc[j - 1]; bm[j] = bm[j - 1]; }
+    if (at < K) { bc[at] = c; bm[at] = m; }
   }
-  /* luma trials: top-2 modes x allowed transform types; order (mode rank, type index), strict '<' keeps the earliest */
+  /* luma trials: the ranked modes, pair by pair (ranks 0-1, then 2-3), x allowed transform types; order (mode rank, type
+   * index), strict '<' keeps the earliest */
   /* 32x32: the intra transform set is DCT only (AV1 spec get_tx_set: no tx_type is coded) */
   const int tx_mask = b200_tx_mask_for(f->tx_type_mask, f->reduced_tx_set, n);
   int first_tt = -1;
@@ -593,10 +598,11 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
   /* pass 0: the first allowed transform type on both ranked modes; pass 1: the other types - skipped when every
    * first-type trial quantised to all-zero (nothing left for another transform to gain).  Winner = lowest J,
    * ties -> lowest candidate index c = rank * B200_TX_TYPES + type. */
-  int all_first_zero = 1;
+  for (int pr = 0; pr < K / 2; pr++) {
+  int all_first_zero = 1;       /* per pair of ranked modes */
   for (int pass = 0; pass < 2; pass++) {
     if (pass == 1 && (all_first_zero || !(f->rdo_tx_decision && n <= 16))) break;
-    for (int k = 0; k < 2; k++) {
+    for (int k = 2 * pr; k < 2 * pr + 2; k++) {
       const int m = bm[k];
       if (m < 0) continue;
       orc_predict_intra_ef(m, DELTA_Y(m), n, A[0], L[0], ha, hl, f->bit_depth, ief, pred);
@@ -613,6 +619,7 @@ void orc_analyze_block(enc_t *e, int x, int y, int n, B200BlockDec *out, uint32_
         if (J < bestJ || (J == bestJ && c < best_c)) { bestJ = J; best_c = c; best_mode = m; best_tt = tt; eob_y = eobv; }
       }
     }
+  }
   }
   int64_t total = bestJ;
   int uv_best = DC_PRED, eob_u = 0, eob_v = 0, cfl_js = 0, cfl_idx = 0;

@@ -59,6 +59,7 @@ def configure(w, h, depth, planes, quantizer, speed, threads=None):
     f.psy = 1          # Tune::Psychovisual, always (av1encoder.rs:694)
     f.lf_search = 0 if tw.fast_deblock else 1
     f.lr_full = 1 if tw.sgr_complexity_full else 0
+    f.luma_rdo_modes = 4 if tw.complex_prediction_modes else 2
     f.enable_cdef = 1 if tw.cdef else 0
     f.enable_restoration = 1 if tw.lrf else 0
     for p in range(planes):

@@ -15,7 +15,7 @@ class B200Frame(ctypes.Structure):
         "color_description_present", "color_primaries", "transfer_characteristics", "matrix_coefficients", "full_range",
         "partition_min", "partition_max", "rdo_tx_decision", "fine_directional_intra", "enable_cfl", "enable_intra_edge_filter",
         "lambda_q8", "lambda_satd_q8", "y_mode_mask", "uv_mode_mask", "tx_type_mask")] + [
-        ("split_gate_bits", ctypes.c_int32 * 3), ("lf_search", ctypes.c_int32), ("lr_full", ctypes.c_int32), ("psy", ctypes.c_int32),
+        ("split_gate_bits", ctypes.c_int32 * 3), ("lf_search", ctypes.c_int32), ("lr_full", ctypes.c_int32), ("psy", ctypes.c_int32), ("luma_rdo_modes", ctypes.c_int32),
         ("lf_level", ctypes.c_int32 * 4), ("lf_sharpness", ctypes.c_int32),
         ("cdef_damping", ctypes.c_int32), ("cdef_bits", ctypes.c_int32),
         ("cdef_y_strength", ctypes.c_int32 * 8), ("cdef_uv_strength", ctypes.c_int32 * 8),

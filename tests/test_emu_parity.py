@@ -71,7 +71,9 @@ def compare_analysis(ref, out, f):
     (200, 136, 8, 3, 1, dict(psy=1)),                               # Tune::Psychovisual: variance-aware luma error per 8x8
     (136, 104, 10, 3, 1, dict(psy=1, partition_max=32, reduced_tx_set=0, lr=1)),
     (200, 136, 8, 3, 1, dict(lf_search=1, lr=1)),                   # deblocking level search + restoration
-    (136, 104, 10, 1, 1, dict(lf_search=1, lr=1, lr_full=1, partition_min=8)),   # all 16 self-guided sets, monochrome                    # 7-type transform set on 4x4 / 8x8 (V_DCT, H_DCT: 1-D classes)
+    (136, 104, 10, 1, 1, dict(lf_search=1, lr=1, lr_full=1, partition_min=8)),
+    (136, 104, 8, 3, 1, dict(luma_rdo_modes=4, psy=1, reduced_tx_set=0)),          # four fully evaluated luma modes (complex_prediction_modes)
+    (96, 64, 10, 3, 2, dict(luma_rdo_modes=4, partition_max=32, partition_min=8)),   # all 16 self-guided sets, monochrome                    # 7-type transform set on 4x4 / 8x8 (V_DCT, H_DCT: 1-D classes)
     (96, 72, 10, 3, 2, dict(reduced_tx_set=0, partition_max=32, tx_type_mask=0x61)),   # DCT_DCT + the 1-D DCTs where they exist
       # 4 x 3 superblocks: the reconstruction wavefront waits on its neighbours
 ])

@@ -168,6 +168,8 @@ CASES = [
     (384, 256, 10, 3, 180, 2, dict(lf_search=1, partition_min=8)),
     (200, 136, 8, 1, 100, 1, dict(lf_search=1, lr=1, lr_full=1)),                        # all 16 self-guided sets                                    # 7-type transform set (V_DCT / H_DCT on 4x4, 8x8)
     (200, 136, 10, 3, 66, 1, dict(reduced_tx_set=0, partition_max=32, tx_type_mask=0x61)),
+    (320, 200, 8, 3, 90, 2, dict(luma_rdo_modes=4, psy=1, reduced_tx_set=0)),           # complex_prediction_modes: four fully evaluated luma modes
+    (200, 136, 10, 3, 66, 1, dict(luma_rdo_modes=4, partition_max=32, psy=1, lr=1)),
 ]
 
 
