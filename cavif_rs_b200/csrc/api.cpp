@@ -94,19 +94,6 @@ void parallel_for(size_t n, const std::function<void(size_t)> &fn) {
   for (auto &t : th) t.join();
 }
 
-// pageable caller memory -> pinned staging: one memcpy thread moves ~10 GB/s, a 1080p RGBA frame is 8 MB; pieces of >= 1 MB
-// over up to 8 threads keep the staging copy off the critical path of the upload
-void parallel_memcpy(void *dst, const void *src, size_t bytes) {
-  const size_t piece = 1u << 20;
-  const size_t n = std::min<size_t>(std::min<size_t>(8, packer_threads()), (bytes + piece - 1) / piece);
-  if (n <= 1) { memcpy(dst, src, bytes); return; }
-  const size_t per = ((bytes + n - 1) / n + 63) & ~(size_t)63;
-  parallel_for(n, [&](size_t i) {
-    const size_t a = i * per, b = std::min(bytes, a + per);
-    if (a < b) memcpy((char *)dst + a, (const char *)src + a, b - a);
-  });
-}
-
 // ---- reusable device / pinned-host arenas (one context per concurrent call) ----------------------
 struct Arena {
   char *base = nullptr;
@@ -719,6 +706,29 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
     ch.h_flags = c.pin.take<int>(cnt);
     int *d_flags = c.dev.take<int>(cnt);
     CU(cudaMemsetAsync(d_flags, 0, cnt * sizeof(int), c.stream));
+    // pageable caller memory goes through the pinned arena: every such image of the chunk is staged by ONE parallel copy
+    // (1 MB pieces over up to 16 host threads) before the uploads are issued; page-locked caller memory is copied straight
+    std::vector<uint8_t *> staged(cnt, nullptr);
+    {
+      struct Piece { uint8_t *dst; const uint8_t *src; size_t n; };
+      std::vector<Piece> pieces;
+      for (size_t i = ch.a; i < ch.b; i++) {
+        ImageWork &im = imgs[i];
+        if (im.status || im.raw || im.on_device) continue;
+        const size_t bytes = (im.stride * (im.h - 1) + im.w) * im.channels;
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, im.pixels) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!pinned) cudaGetLastError();
+        if (pinned) continue;
+        uint8_t *stage = c.pin.take<uint8_t>(bytes);
+        ARENA_CHECK(c);
+        staged[i - ch.a] = stage;
+        for (size_t o = 0; o < bytes; o += (1u << 20)) pieces.push_back({stage + o, im.pixels + o, std::min<size_t>(1u << 20, bytes - o)});
+      }
+      const size_t nt = std::min<size_t>(std::min<size_t>(16, packer_threads()), pieces.size());
+      if (nt <= 1) { for (const Piece &pc : pieces) memcpy(pc.dst, pc.src, pc.n); }
+      else parallel_for(nt, [&](size_t t) { for (size_t k = t; k < pieces.size(); k += nt) memcpy(pieces[k].dst, pieces[k].src, pieces[k].n); });
+    }
     for (size_t i = ch.a; i < ch.b; i++) {
       ImageWork &im = imgs[i];
       if (im.status) continue;
@@ -745,18 +755,9 @@ int encode_images(const b200avif_encoder &enc, std::vector<ImageWork> &imgs, b20
       if (im.on_device) d_in = im.pixels;
       else {
         const size_t bytes = (im.stride * (im.h - 1) + im.w) * im.channels;
-        // page-locked caller memory is copied straight to the device; pageable memory goes through the pinned arena
-        cudaPointerAttributes attr;
-        const bool pinned = cudaPointerGetAttributes(&attr, im.pixels) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-        if (!pinned) cudaGetLastError();
-        const uint8_t *from = im.pixels;
-        uint8_t *stage = pinned ? nullptr : c.pin.take<uint8_t>(bytes);
+        const uint8_t *from = staged[i - ch.a] ? staged[i - ch.a] : im.pixels;      // staged above unless page-locked
         uint8_t *d = c.dev.take<uint8_t>(bytes + 16);
         ARENA_CHECK(c);
-        if (!pinned) {
-          parallel_memcpy(stage, im.pixels, bytes);
-          from = stage;
-        }
         CU(cudaMemcpyAsync(d, from, bytes, cudaMemcpyHostToDevice, c.stream));
         h2d += bytes;
         d_in = d;
