@@ -165,6 +165,22 @@ def test_batch_matches_single_and_isolates_errors():
         assert enc.encode_rgba(im).avif_file == b.avif_file
 
 
+def test_very_large_batch_in_one_launch(monkeypatch):
+    """more frame jobs in ONE launch set than the machine has resident CTAs (640 tiny images with alpha = 1280 jobs, one chunk):
+    grids that are sized per job, survivor lists, tile tables and the arenas all scale with the job count"""
+    monkeypatch.setenv("B200AVIF_CHUNKS", "1")
+    m = C()
+    imgs = [H.synth_image(24 + 8 * (i % 3), 16 + 8 * (i % 2), i, alpha=True) for i in range(640)]
+    enc = m.Encoder.new().with_quality(70).with_speed(4)
+    batch = enc.encode_batch(imgs)
+    assert len(batch) == 640
+    monkeypatch.delenv("B200AVIF_CHUNKS")
+    for i in (0, 1, 2, 317, 638, 639):
+        assert enc.encode_rgba(imgs[i]).avif_file == batch[i].avif_file
+        im = Image.open(io.BytesIO(batch[i].avif_file))
+        assert im.size == (imgs[i].shape[1], imgs[i].shape[0]) and im.mode == "RGBA"
+
+
 def test_raw_planes_and_errors():
     m = C()
     w, h = 64, 48
