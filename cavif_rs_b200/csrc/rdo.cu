@@ -487,6 +487,9 @@ __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid
 #ifndef B200_LV2_WARPS
 #define B200_LV2_WARPS 20     // resident warps per SM the 16x16 analysis kernels are compiled for (register budget 65536 / 32 / warps)
 #endif
+#ifndef B200_LV01_WARPS
+#define B200_LV01_WARPS 24    // resident warps per SM of the 8x8 / 4x4 analysis kernels (80 registers)
+#endif
 #ifndef B200_TOP_W
 #define B200_TOP_W 5
 #endif
@@ -546,7 +549,7 @@ __global__ void __launch_bounds__(kThreads * W, W == 6 ? 3 : (LV == 3 ? 4 : (LV 
 // the warps of a CTA share one instruction stream (free-running warps lose most issue slots to instruction fetch here:
 // stall_no_instruction 6-10 warps per issue, profiles/).  CTAs walk the list grid-stride.
 template <int LV, bool HBD, int W>
-__global__ void __launch_bounds__(kThreads * W, (LV == 2 ? B200_LV2_WARPS : 24) / W) b200_analyze_listed_kernel(const B200RdoJob *jobs) {
+__global__ void __launch_bounds__(kThreads * W, (LV == 2 ? B200_LV2_WARPS : B200_LV01_WARPS) / W) b200_analyze_listed_kernel(const B200RdoJob *jobs) {
   typedef typename PixOf<HBD>::type PIX;
   typedef SharedT<16, PIX> SH;
   __shared__ SH shs[W];
@@ -715,7 +718,7 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
       if (free_running) {
         if (lv == 2) B200_ANALYZE(2, 1, ga); else if (lv == 1) B200_ANALYZE(1, 1, ga); else B200_ANALYZE(0, 1, ga);
       } else {
-        dim3 gl(min((nblk + 3) / 4, max(1, (148 * 12) / n_jobs)), n_jobs);
+        dim3 gl(min((nblk + 3) / 4, max(1, (148 * ((lv == 2 ? B200_LV2_WARPS : B200_LV01_WARPS) / 4) * 2) / n_jobs)), n_jobs);      // two waves of resident CTAs
 #define B200_ANALYZE_LISTED(LV) \
         do { if (high_bitdepth) b200_analyze_listed_kernel<LV, true, 4><<<gl, kThreads * 4, 0, st>>>(d_jobs); \
              else b200_analyze_listed_kernel<LV, false, 4><<<gl, kThreads * 4, 0, st>>>(d_jobs); } while (0)
