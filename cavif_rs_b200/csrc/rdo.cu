@@ -5,13 +5,15 @@
 //      the largest level down so that a level can be pruned by its parent (b200_pruned_by_parent, records.h):
 //      luma SATD ranking of the 13 intra modes + angle refinement (b200_satd_direct_kernel for the never-pruned top
 //      level, b200_satd_kernel with per-CTA compaction of the surviving blocks below it: one thread per block), then
-//      full trials of the top-2 luma modes x transform types and of the chroma candidates {luma mode, DC, CFL}
+//      full trials of the top-2 (top-4: frame.luma_rdo_modes) luma modes x transform types and of the chroma candidates
+//      {luma mode, DC, CFL}
 //      (b200_analyze_kernel: one warp per block, lane-batched candidates: lane group g = lane / N owns one candidate,
 //      lane l = lane % N owns column l / row l of its transform; butterflies in registers, transpose through shared
-//      memory, quantiser / rate / dequantiser on the row, SSE by shuffles; the top level runs its warps in lock-step
-//      CTAs for instruction-cache locality).
+//      memory, quantiser / rate / dequantiser on the row, SSE / Psychovisual sums by shuffles; the warps of a CTA run in
+//      lock-step for instruction-cache locality: the top level straight over its blocks, the pruned levels over the
+//      survivor lists the SATD kernel built).
 //   B. PARTITION DECISION (b200_decide_kernel: one thread per root region, NONE vs SPLIT recursively).
-//   C. RECONSTRUCTION (closed loop, b200_recon_kernel: one CTA per TILE, warps on a superblock-row wavefront): the only
+//   C. RECONSTRUCTION (closed loop, recon.cu b200_recon_kernel: one CTA per TILE, warps on a superblock-row wavefront): the only
 //      stage that needs reconstructed neighbours; one trial per decided block and plane, Y/U/V batched over the lane
 //      groups, CFL chroma after its luma.
 //
