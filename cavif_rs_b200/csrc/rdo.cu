@@ -496,6 +496,10 @@ __device__ __forceinline__ void satd_item(const B200RdoJob &job, int lv, int gid
 #define B200_TOP_W 5
 #endif
 constexpr int kAnalyzeWarpsTop = B200_TOP_W;      // 16x16 as the top level
+#ifndef B200_LISTED_W
+#define B200_LISTED_W 4
+#endif
+constexpr int kListedW = B200_LISTED_W;      // warps per lock-step CTA of the pruned levels
 constexpr int kAnalyzeWarpsTop32 = 2;    // 32x32 as the top level (22.9 KB of shared memory per warp)
 template <int LV, bool HBD, int W>
 __global__ void __launch_bounds__(kThreads * W, W == 6 ? 3 : (LV == 3 ? 4 : (LV == 2 ? B200_LV2_WARPS : 24) / W)) b200_analyze_kernel(const B200RdoJob *jobs) {
@@ -662,8 +666,8 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
 #define B200_CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
     B200_CARVE((b200_analyze_kernel<2, false, kAnalyzeWarpsTop>)); B200_CARVE((b200_analyze_kernel<2, true, kAnalyzeWarpsTop>));
     B200_CARVE((b200_analyze_kernel<2, false, 6>));
-    B200_CARVE((b200_analyze_listed_kernel<0, false, 4>)); B200_CARVE((b200_analyze_listed_kernel<1, false, 4>)); B200_CARVE((b200_analyze_listed_kernel<2, false, 4>));
-    B200_CARVE((b200_analyze_listed_kernel<0, true, 4>)); B200_CARVE((b200_analyze_listed_kernel<1, true, 4>)); B200_CARVE((b200_analyze_listed_kernel<2, true, 4>));
+    B200_CARVE((b200_analyze_listed_kernel<0, false, kListedW>)); B200_CARVE((b200_analyze_listed_kernel<1, false, kListedW>)); B200_CARVE((b200_analyze_listed_kernel<2, false, kListedW>));
+    B200_CARVE((b200_analyze_listed_kernel<0, true, kListedW>)); B200_CARVE((b200_analyze_listed_kernel<1, true, kListedW>)); B200_CARVE((b200_analyze_listed_kernel<2, true, kListedW>));
     B200_CARVE((b200_analyze_kernel<3, false, kAnalyzeWarpsTop32>)); B200_CARVE((b200_analyze_kernel<3, true, kAnalyzeWarpsTop32>));
     B200_CARVE((b200_analyze_kernel<0, false, 1>)); B200_CARVE((b200_analyze_kernel<1, false, 1>)); B200_CARVE((b200_analyze_kernel<2, false, 1>));
     B200_CARVE((b200_analyze_kernel<0, true, 1>)); B200_CARVE((b200_analyze_kernel<1, true, 1>)); B200_CARVE((b200_analyze_kernel<2, true, 1>));
@@ -720,10 +724,10 @@ extern "C" int b200_rdo_launch(const B200RdoJob *d_jobs, int n_jobs, const B200T
       if (free_running) {
         if (lv == 2) B200_ANALYZE(2, 1, ga); else if (lv == 1) B200_ANALYZE(1, 1, ga); else B200_ANALYZE(0, 1, ga);
       } else {
-        dim3 gl(min((nblk + 3) / 4, max(1, (148 * ((lv == 2 ? B200_LV2_WARPS : B200_LV01_WARPS) / 4) * 2) / n_jobs)), n_jobs);      // two waves of resident CTAs
+        dim3 gl(min((nblk + kListedW - 1) / kListedW, max(1, (148 * ((lv == 2 ? B200_LV2_WARPS : B200_LV01_WARPS) / kListedW) * 2) / n_jobs)), n_jobs);      // two waves of resident CTAs
 #define B200_ANALYZE_LISTED(LV) \
-        do { if (high_bitdepth) b200_analyze_listed_kernel<LV, true, 4><<<gl, kThreads * 4, 0, st>>>(d_jobs); \
-             else b200_analyze_listed_kernel<LV, false, 4><<<gl, kThreads * 4, 0, st>>>(d_jobs); } while (0)
+        do { if (high_bitdepth) b200_analyze_listed_kernel<LV, true, kListedW><<<gl, kThreads * kListedW, 0, st>>>(d_jobs); \
+             else b200_analyze_listed_kernel<LV, false, kListedW><<<gl, kThreads * kListedW, 0, st>>>(d_jobs); } while (0)
         if (lv == 2) B200_ANALYZE_LISTED(2); else if (lv == 1) B200_ANALYZE_LISTED(1); else B200_ANALYZE_LISTED(0);
       }
     }
@@ -762,7 +766,7 @@ static void emu_satd(void *) {
 static void emu_analyze(void *) {
   const bool hbd = g_emu_jobs[0].frame.bit_depth > 8;
 #define EMU_ANALYZE(LV, W) do { if (hbd) b200_analyze_kernel<LV, true, W>(g_emu_jobs); else b200_analyze_kernel<LV, false, W>(g_emu_jobs); } while (0)
-#define EMU_LISTED(LV) do { if (hbd) b200_analyze_listed_kernel<LV, true, 4>(g_emu_jobs); else b200_analyze_listed_kernel<LV, false, 4>(g_emu_jobs); } while (0)
+#define EMU_LISTED(LV) do { if (hbd) b200_analyze_listed_kernel<LV, true, kListedW>(g_emu_jobs); else b200_analyze_listed_kernel<LV, false, kListedW>(g_emu_jobs); } while (0)
   if (g_emu_lv == g_emu_top) { if (g_emu_top == 3) EMU_ANALYZE(3, kAnalyzeWarpsTop32); else EMU_ANALYZE(2, kAnalyzeWarpsTop); }
   else if (g_emu_lv == 2) EMU_LISTED(2);
   else if (g_emu_lv == 1) EMU_LISTED(1);
@@ -780,7 +784,7 @@ extern "C" int b200_rdo_launch_emu(const B200RdoJob *jobs, const B200TileRef *ti
     if (nblk == 0) continue;
     const int items = g_emu_lv == g_emu_top ? 128 : kSatdItems;
     emu::launch(emu_satd, nullptr, (unsigned)((nblk + items - 1) / items), 128);
-    const int w = g_emu_lv == g_emu_top ? (g_emu_top == 3 ? kAnalyzeWarpsTop32 : kAnalyzeWarpsTop) : 4;
+    const int w = g_emu_lv == g_emu_top ? (g_emu_top == 3 ? kAnalyzeWarpsTop32 : kAnalyzeWarpsTop) : kListedW;
     emu::launch(emu_analyze, nullptr, (unsigned)std::min(nblk, w > 1 ? 3 : 7), kThreads * w);
   }
   const int rn4 = g_emu_top == 3 ? 8 : 4;
