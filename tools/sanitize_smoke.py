@@ -12,6 +12,9 @@ for (w, h, speed, depth, alpha) in ((200, 136, 4, 8, True), (161, 100, 2, 10, Fa
     img = H.synth_image(w, h, w + h, alpha=alpha)
     r = C.Encoder.new().with_quality(70).with_speed(speed).with_bit_depth(depth).encode_rgba(img)
     n += len(r.avif_file)
+# speed 1: four fully evaluated luma modes (complex_prediction_modes), exhaustive partition search
+r = C.Encoder.new().with_quality(60).with_speed(1).encode_rgba(H.synth_image(136, 104, 3, alpha=True))
+n += len(r.avif_file)
 # one tall tile (seven superblock rows): the wavefront of the reconstruction chain at its deepest row-slot count
 r = C.Encoder.new().with_quality(80).with_speed(4).with_num_threads(1).encode_rgba(H.synth_image(128, 420, 9, alpha=False))
 n += len(r.avif_file)
